@@ -1,0 +1,898 @@
+// C ABI implementation: context lifetime, shape-class tables, layout/transfer plumbing, loops 1-4 drivers,
+// accessors and parity taps.  Loop 5 lives in ibm_motion.cu, NCCL in ibm_comm.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "ibm_ctx.h"
+
+using namespace ibm;
+
+static std::string g_createErr;
+
+namespace ibm {
+
+int ctx_fail(ibm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_createErr = msg;
+  return code;
+}
+bool ctx_cuda_ok(ibm_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  if (c) c->err = m; else g_createErr = m;
+  return false;
+}
+
+static cudaEvent_t get_event(ibm_ctx* c) {
+  if (!c->eventPool.empty()) { cudaEvent_t e = c->eventPool.back(); c->eventPool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static void resolve_events(ibm_ctx* c) {
+  if (c->events.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : c->events) {
+    float ms = 0.f;
+    if (p.b && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->accMs[p.cat] += ms;
+    c->eventPool.push_back(p.a);
+    if (p.b) c->eventPool.push_back(p.b);
+  }
+  c->events.clear();
+}
+void ctx_tic(ibm_ctx* c, int cat) {
+  if (c->events.size() >= 2048) resolve_events(c);
+  EventPair p{get_event(c), nullptr, cat};
+  cudaEventRecord(p.a, c->stream);
+  c->events.push_back(p);
+}
+void ctx_toc(ibm_ctx* c) {
+  EventPair& p = c->events.back();
+  p.b = get_event(c);
+  cudaEventRecord(p.b, c->stream);
+}
+
+int ctx_ensure_stage(ibm_ctx* c, size_t doubles) {
+  if (c->stageDoubles >= doubles) return IBM_OK;
+  if (c->dStage) cudaFree(c->dStage);
+  c->dStage = nullptr; c->stageDoubles = 0;
+  IBM_CUDA(c, cudaMalloc(&c->dStage, doubles * sizeof(double)));
+  c->stageDoubles = doubles;
+  return IBM_OK;
+}
+int ctx_ensure_pinned(ibm_ctx* c, size_t doubles) {
+  if (c->hPinnedDoubles >= doubles) return IBM_OK;
+  if (c->hPinned) cudaFreeHost(c->hPinned);
+  c->hPinned = nullptr; c->hPinnedDoubles = 0;
+  IBM_CUDA(c, cudaMallocHost(&c->hPinned, doubles * sizeof(double)));
+  c->hPinnedDoubles = doubles;
+  return IBM_OK;
+}
+
+static int ensure_field(ibm_ctx* c, double** p, int nComp) {
+  if (*p) return IBM_OK;
+  IBM_CUDA(c, cudaMalloc(p, (size_t)nComp * c->L.nCells * sizeof(double)));
+  return IBM_OK;
+}
+
+// ---- shape classes: centeredMesh_ / Sf_ exactly as discretize()/calcSf() evaluate them (host libm) ----
+static void build_class(ShapeClassHost& h, int kind, double d, double a, double b, int nTheta, double delta, double l) {
+  const double Pi = IBM_PI;
+  ShapeClassDev& s = h.dev;
+  s.kind = kind; s.nTheta = nTheta; s.d = d; s.a = a; s.b = b; s.delta = delta; s.l = l;
+  s.nk = (kind == IBM_SPHERE) ? nTheta / 2 : 1;  // sphere.C:66-69 (always), cylinder.C:72, ellipse.C:89
+  s.N = 3 * nTheta * s.nk;
+  const int nk = s.nk;
+  h.centered.assign((size_t)3 * s.N, 0.0);
+  h.Sf.assign((size_t)3 * nTheta * nk, 0.0);
+  h.cosT.resize(nTheta); h.sinT.resize(nTheta); h.sinP.assign(nk, 0.0); h.cosP.assign(nk, 1.0);
+  h.Rtab.assign((size_t)3 * nTheta, 0.0);
+  const double dl[3] = {-1 * delta, 0, delta};
+  const double dTheta = 2.0 * Pi / (nTheta);
+  auto idx = [&](int i, int j, int k) { return i + j * 3 + k * 3 * nTheta; };
+  auto idx2 = [&](int i, int k) { return i + k * nTheta; };
+  for (int j = 0; j < nTheta; ++j) { double th = double(j) * dTheta; h.cosT[j] = std::cos(th); h.sinT[j] = std::sin(th); }
+  if (kind == IBM_SPHERE) {
+    const double R = d / 2.0;
+    const double dPhi = Pi / (nk - 1);
+    for (int k = 0; k < nk; ++k) { double phi = dPhi * double(k); h.sinP[k] = std::sin(phi); h.cosP[k] = std::cos(phi); }
+    for (int i = 0; i < 3; ++i) {
+      double r = R + dl[i];
+      for (int j = 0; j < nTheta; ++j) {
+        h.Rtab[(size_t)i * nTheta + j] = r;
+        double th = double(j) * dTheta;
+        for (int k = 0; k < nk; ++k) {
+          double phi = dPhi * double(k);
+          double* p = &h.centered[(size_t)3 * idx(i, j, k)];
+          p[0] = r * std::cos(th) * std::sin(phi);  // sphere.C:184-190
+          p[1] = r * std::sin(th) * std::sin(phi);
+          p[2] = r * std::cos(phi);
+        }
+      }
+    }
+    const double r = d / 2.0;
+    for (int i = 0; i < nTheta; ++i) {
+      double th = dTheta * double(i);
+      for (int k = 0; k < nk; ++k) {
+        double phi = dPhi * double(k);
+        double f = (r * r) * dTheta;
+        (void)f;
+        double v[3] = {-(std::cos(th) * std::sin(phi)), -(std::sin(th) * std::sin(phi)), -(std::cos(phi))};
+        for (int q = 0; q < 3; ++q) v[q] = v[q] * (r * r) * dTheta;  // -vector(...)*sqr(r)*dTheta  (sphere.C:134-140)
+        double ck;
+        if (k == 0) ck = (std::cos(phi) - std::cos(phi + dPhi / 2.0));
+        else if (k == nk - 1) ck = (std::cos(phi - dPhi / 2.0) - std::cos(phi));
+        else ck = (std::cos(phi - dPhi / 2.0) - std::cos(phi + dPhi / 2.0));
+        for (int q = 0; q < 3; ++q) h.Sf[(size_t)3 * idx2(i, k) + q] = v[q] * ck;
+      }
+    }
+    s.Rbound = d / 2.0;
+    s.V = 1.0 / 6.0 * Pi * (d * d * d);        // sphere.C:262-265
+    s.I = 2.0 / 5.0 * ((d / 2.0) * (d / 2.0));  // sphere.C:64
+    s.A = Pi * ((d / 2.0) * (d / 2.0));        // sphere.C:256-259
+  } else if (kind == IBM_CYLINDER) {
+    const double R = d / 2.0;
+    for (int i = 0; i < 3; ++i) {
+      double r = R + dl[i];
+      for (int j = 0; j < nTheta; ++j) {
+        h.Rtab[(size_t)i * nTheta + j] = r;
+        double th = double(j) * dTheta;
+        double* p = &h.centered[(size_t)3 * idx(i, j, 0)];
+        p[0] = r * std::cos(th); p[1] = r * std::sin(th); p[2] = 0.0;  // cylinder.C:142-148
+      }
+    }
+    const double r = d / 2.0;
+    for (int i = 0; i < nTheta; ++i) {
+      double th = dTheta * double(i);
+      double v[3] = {-std::cos(th), -std::sin(th), -0.0};
+      for (int q = 0; q < 3; ++q) h.Sf[(size_t)3 * idx2(i, 0) + q] = v[q] * r * dTheta * l;  // cylinder.C:116-122
+    }
+    s.Rbound = d / 2.0;
+    s.V = Pi * ((d / 2.0) * (d / 2.0)) * l;  // cylinder.C:215-220
+    s.I = (d / 8.0) * (d / 8.0);             // cylinder.C:71 (as coded)
+    s.A = d * l;                             // cylinder.C:210-213
+  } else {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < nTheta; ++j) {
+        double th = double(j) * dTheta;
+        double ca = std::cos(th) / (a), sb = std::sin(th) / (b);
+        double R = std::sqrt(1.0 / (ca * ca + sb * sb)) + dl[i];  // ellipse.C:135-137
+        h.Rtab[(size_t)i * nTheta + j] = R;
+        double* p = &h.centered[(size_t)3 * idx(i, j, 0)];
+        p[0] = R * std::cos(th); p[1] = R * std::sin(th); p[2] = 0.0;
+      }
+    for (int i = 0; i < nTheta; ++i)
+      for (int q = 0; q < 3; ++q)
+        h.Sf[(size_t)3 * idx2(i, 0) + q] = -h.centered[(size_t)3 * idx(1, i, 0) + q] * dTheta * l;  // ellipse.C:57
+    s.Rbound = std::fmax(a, b);
+    s.V = Pi * a * b * l;     // ellipse.C:234-237
+    s.I = (a * a) + (b * b);  // ellipse.C:88 (as coded)
+    s.A = a * b * Pi;         // ellipse.C:229-232
+  }
+}
+
+static int upload_classes(ibm_ctx* c) {
+  for (auto p : c->classPools) cudaFree(p);
+  c->classPools.clear();
+  std::vector<ShapeClassDev> devs;
+  for (auto& h : c->classes) {
+    size_t n = h.centered.size() + h.Sf.size() + h.cosT.size() + h.sinT.size() + h.sinP.size() + h.cosP.size() + h.Rtab.size();
+    double* pool = nullptr;
+    IBM_CUDA(c, cudaMalloc(&pool, n * sizeof(double)));
+    c->classPools.push_back(pool);
+    std::vector<double> flat;
+    flat.reserve(n);
+    auto put = [&](const std::vector<double>& v, const double*& dst) {
+      dst = pool + flat.size();
+      flat.insert(flat.end(), v.begin(), v.end());
+    };
+    put(h.centered, h.dev.centered); put(h.Sf, h.dev.Sf); put(h.cosT, h.dev.cosT); put(h.sinT, h.dev.sinT);
+    put(h.sinP, h.dev.sinP); put(h.cosP, h.dev.cosP); put(h.Rtab, h.dev.Rtab);
+    IBM_CUDA(c, cudaMemcpy(pool, flat.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    devs.push_back(h.dev);
+  }
+  if (c->dClasses) cudaFree(c->dClasses);
+  c->dClasses = nullptr;
+  if (!devs.empty()) {
+    IBM_CUDA(c, cudaMalloc(&c->dClasses, devs.size() * sizeof(ShapeClassDev)));
+    IBM_CUDA(c, cudaMemcpy(c->dClasses, devs.data(), devs.size() * sizeof(ShapeClassDev), cudaMemcpyHostToDevice));
+  }
+  return IBM_OK;
+}
+
+static int alloc_instances(ibm_ctx* c, InstanceSoA& s, int cap) {
+  auto ai = [&](int** p) -> bool {
+    if (!ctx_cuda_ok(c, cudaMalloc(p, (size_t)cap * sizeof(int)), "cudaMalloc(instances)")) return false;
+    cudaMemset(*p, 0, (size_t)cap * sizeof(int));
+    c->instAllocs.push_back(*p);
+    return true;
+  };
+  auto ad = [&](double** p, int mult = 1) -> bool {
+    if (!ctx_cuda_ok(c, cudaMalloc(p, (size_t)cap * mult * sizeof(double)), "cudaMalloc(instances)")) return false;
+    cudaMemset(*p, 0, (size_t)cap * mult * sizeof(double));
+    c->instAllocs.push_back(*p);
+    return true;
+  };
+  bool ok = ai(&s.index) && ai(&s.copy) && ai(&s.active) && ai(&s.onMesh) && ai(&s.cls) && ai(&s.nShell) && ai(&s.shellOff) &&
+            ai(&s.nPtsOnMesh) && ad(&s.rho) && ad(&s.age) && ad(&s.rot, 9);
+  for (int q = 0; q < 3 && ok; ++q) ok = ad(&s.c[q]) && ad(&s.th[q]) && ad(&s.v[q]) && ad(&s.om[q]) && ad(&s.F[q]) && ad(&s.T[q]);
+  return ok ? IBM_OK : IBM_E_CUDA;
+}
+
+static int clear_live_F(ibm_ctx* c) {
+  if (c->fLive && c->dF) {
+    launch_clear_shell_cells(c->stream, c->dShellCell, c->totalShell, (size_t)c->L.nCells, c->dF);
+    c->nLaunch++;
+  }
+  c->fLive = false;
+  return IBM_OK;
+}
+
+// particleIBM::update() for all instances + deleteInActiveParticles + updateI
+int ctx_update(ibm_ctx* c) {
+  clear_live_F(c);
+  ctx_tic(c, T_UPDATE);
+  launch_k1_count(c->stream, c->L, c->dClasses, c->in, c->nInst);
+  launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
+  launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
+  launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
+  c->nLaunch += 4;
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->nInst > 0 && c->hScal[0] < c->nInst) {  // deleteInActiveParticles (particleCloud.C:940-950)
+    launch_compact_instances(c->stream, c->in, c->in2, c->dKeep, c->dKeepOff, c->nInst);
+    std::swap(c->in, c->in2);
+    c->nInst = c->hScal[0];
+    launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
+    c->nLaunch += 2;
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;
+  if (c->totalShell > c->shellCap) {
+    if (c->dShellCell) cudaFree(c->dShellCell);
+    if (c->dShellJK) cudaFree(c->dShellJK);
+    c->shellCap = c->totalShell + c->totalShell / 4 + 1024;
+    IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
+    IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
+  }
+  launch_k1_fill(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK);
+  int rc = ensure_field(c, &c->dI, 1);
+  if (rc) return rc;
+  IBM_CUDA(c, cudaMemsetAsync(c->dI, 0, (size_t)c->L.nCells * sizeof(double), c->stream));
+  launch_k1_indicator(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dI);
+  c->nLaunch += 3;
+  ctx_toc(c);
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+
+static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, const double* dS, double dt, double* dFext) {
+  const size_t C = (size_t)c->L.nCells;
+  double* F = dFext;
+  if (!F) {
+    int rc = ensure_field(c, &c->dF, 3);
+    if (rc) return rc;
+    F = c->dF;
+    if (!c->fEverZeroed) {
+      IBM_CUDA(c, cudaMemsetAsync(F, 0, 3 * C * sizeof(double), c->stream));
+      c->fEverZeroed = true;
+      c->fLive = false;
+    }
+    clear_live_F(c);
+  } else {
+    IBM_CUDA(c, cudaMemsetAsync(F, 0, 3 * C * sizeof(double), c->stream));
+  }
+  if (c->cfg.coupled) {  // particleCloud.C:1186-1189
+    ctx_tic(c, T_FORCING);
+    if (c->forcingVariant == 0)
+      launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
+    else
+      launch_forcing_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
+    c->nLaunch++;
+    ctx_toc(c);
+    if (!dFext) c->fLive = true;
+    c->nForcingCalls++;
+    c->nUpdates += c->totalShell;
+  }
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+
+static int h2d_field(ibm_ctx* c, const double* hostAoS, int nComp, double* dSoA) {
+  const size_t n = (size_t)nComp * c->L.nCells;
+  int rc = ctx_ensure_stage(c, n);
+  if (rc) return rc;
+  ctx_tic(c, T_H2D);
+  IBM_CUDA(c, cudaMemcpyAsync(c->dStage, hostAoS, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  ctx_toc(c);
+  c->h2dBytes += (long long)(n * sizeof(double));
+  ctx_tic(c, T_LAYOUT);
+  launch_aos_to_soa(c->stream, c->L, c->dStage, nComp, dSoA);
+  c->nLaunch++;
+  ctx_toc(c);
+  return IBM_OK;
+}
+
+static int d2h_field(ibm_ctx* c, const double* dSoA, int nComp, double* hostAoS) {
+  const size_t n = (size_t)nComp * c->L.nCells;
+  int rc = ctx_ensure_stage(c, n);
+  if (rc) return rc;
+  ctx_tic(c, T_LAYOUT);
+  launch_soa_to_aos(c->stream, c->L, dSoA, nComp, c->dStage);
+  c->nLaunch++;
+  ctx_toc(c);
+  ctx_tic(c, T_D2H);
+  IBM_CUDA(c, cudaMemcpyAsync(hostAoS, c->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  ctx_toc(c);
+  c->d2hBytes += (long long)(n * sizeof(double));
+  return IBM_OK;
+}
+
+static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, double* FT_host) {
+  double pRefOverRho = c->cfg.pRef / c->cfg.rhoRef;  // particleCloud.C:1213-1215
+  if (!c->dTcorr) IBM_CUDA(c, cudaMalloc(&c->dTcorr, (size_t)3 * c->cap * sizeof(double)));
+  ctx_tic(c, T_STRESS);
+  if (c->stressVariant == 0)
+    launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+  else
+    launch_stress_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+  c->nLaunch++;
+  ctx_toc(c);
+  IBM_CUDA(c, cudaGetLastError());
+  if (FT_host) {
+    const int n = c->nInst;
+    int rc = ctx_ensure_pinned(c, (size_t)6 * n + 16);
+    if (rc) return rc;
+    ctx_tic(c, T_D2H);
+    for (int q = 0; q < 3; ++q) {
+      IBM_CUDA(c, cudaMemcpyAsync(c->hPinned + (size_t)q * n, c->in.F[q], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaMemcpyAsync(c->hPinned + (size_t)(3 + q) * n, c->in.T[q], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ctx_toc(c);
+    c->d2hBytes += (long long)(6 * n * sizeof(double));
+    IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i)
+      for (int q = 0; q < 6; ++q) FT_host[6 * (size_t)i + q] = c->hPinned[(size_t)q * n + i];
+  }
+  return IBM_OK;
+}
+
+}  // namespace ibm
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int ibm_abi_version(void) { return IBM_ABI_VERSION; }
+
+const char* ibm_last_error(const ibm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, ibm_ctx** out) {
+  if (!mesh || !cfg || !out) return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: null argument");
+  *out = nullptr;
+  if (mesh->nx <= 0 || mesh->ny <= 0 || mesh->nz <= 0) return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: empty lattice");
+  if ((long long)mesh->nx * mesh->ny * mesh->nz > 0x7fffffffLL / 3 * 3 && (long long)mesh->nx * mesh->ny * mesh->nz > 0x7fffffffLL)
+    return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: lattice exceeds 32-bit labels");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return ctx_fail(nullptr, IBM_E_CUDA, "ibm_create: no CUDA device (this path has no CPU fallback)");
+  if (device < 0 || device >= ndev) return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: bad device ordinal");
+  if (!ctx_cuda_ok(nullptr, cudaSetDevice(device), "cudaSetDevice")) return IBM_E_CUDA;
+  ibm_ctx* c = new ibm_ctx;
+  c->device = device;
+  c->cfg = *cfg;
+  if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
+  LatticeDev& L = c->L;
+  L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
+  L.nCells = mesh->nx * mesh->ny * mesh->nz;
+  L.ox = mesh->origin[0]; L.oy = mesh->origin[1]; L.oz = mesh->origin[2];
+  L.dx = mesh->delta[0]; L.dy = mesh->delta[1]; L.dz = mesh->delta[2];
+  L.latToCell = nullptr; L.cellToLat = nullptr;
+  c->zMin = L.oz;
+  c->zMax = L.oz + L.nz * L.dz;
+  // caller cell numbering
+  const size_t n = (size_t)L.nCells;
+  bool haveMap = false;
+  if (mesh->latticeToCell) {
+    c->hLatToCell.assign(mesh->latticeToCell, mesh->latticeToCell + n);
+    haveMap = true;
+  } else if (mesh->nBlocks > 1 || (mesh->nBlocks == 1 && mesh->blocks)) {
+    c->hLatToCell.assign(n, -1);
+    int next = 0;
+    for (int b = 0; b < mesh->nBlocks; ++b) {
+      const int* q = mesh->blocks + 6 * b;
+      for (int K = q[4]; K < q[5]; ++K)
+        for (int J = q[2]; J < q[3]; ++J)
+          for (int I = q[0]; I < q[1]; ++I) {
+            if (I < 0 || I >= L.nx || J < 0 || J >= L.ny || K < 0 || K >= L.nz) { delete c; return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: block outside lattice"); }
+            c->hLatToCell[I + (size_t)L.nx * (J + (size_t)L.ny * K)] = next++;
+          }
+    }
+    if ((size_t)next != n || std::find(c->hLatToCell.begin(), c->hLatToCell.end(), -1) != c->hLatToCell.end()) {
+      delete c;
+      return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: blocks do not tile the lattice");
+    }
+    haveMap = mesh->nBlocks > 1;
+    if (!haveMap) c->hLatToCell.clear();
+  }
+  if (haveMap) {
+    std::vector<int> inv(n, -1);
+    for (size_t l = 0; l < n; ++l) {
+      int id = c->hLatToCell[l];
+      if (id < 0 || (size_t)id >= n || inv[id] != -1) { delete c; return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: latticeToCell is not a permutation"); }
+      inv[id] = (int)l;
+    }
+    if (!ctx_cuda_ok(nullptr, cudaMalloc(&c->dLatToCell, n * sizeof(int)), "cudaMalloc") ||
+        !ctx_cuda_ok(nullptr, cudaMalloc(&c->dCellToLat, n * sizeof(int)), "cudaMalloc")) { delete c; return IBM_E_CUDA; }
+    cudaMemcpy(c->dLatToCell, c->hLatToCell.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->dCellToLat, inv.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+    L.latToCell = c->dLatToCell; L.cellToLat = c->dCellToLat;
+  }
+  // patches (particleCloud.C:1050-1068)
+  bool emptyDir[3] = {false, false, false};
+  for (int p = 0; p < mesh->nPatches; ++p) {
+    const ibm_patch_desc& pd = mesh->patches[p];
+    PatchHost ph;
+    ph.type = pd.type; ph.side = pd.side; ph.neighb = pd.neighbPatch;
+    if (pd.side < 0 || pd.side > 5) { delete c; return ctx_fail(nullptr, IBM_E_ARG, "ibm_create: bad patch side"); }
+    const int axis = pd.side / 2;
+    const bool hi = pd.side & 1;
+    if (pd.type == IBM_EMPTY) emptyDir[axis] = true;
+    if (pd.Cf && pd.Sf && pd.magSf) {
+      ph.Cf.assign(pd.Cf, pd.Cf + 3 * (size_t)pd.nFaces);
+      ph.Sf.assign(pd.Sf, pd.Sf + 3 * (size_t)pd.nFaces);
+      ph.magSf.assign(pd.magSf, pd.magSf + pd.nFaces);
+    } else {
+      // mini-mesh patch faces: transverse lattice order, fastest index first
+      const int nA = (axis == 0) ? L.ny : L.nx, nB = (axis == 2) ? L.ny : L.nz;
+      const double d3[3] = {L.dx, L.dy, L.dz}, o3[3] = {L.ox, L.oy, L.oz};
+      const int n3[3] = {L.nx, L.ny, L.nz};
+      for (int b = 0; b < nB; ++b)
+        for (int a = 0; a < nA; ++a) {
+          int ijk[3];
+          if (axis == 0) { ijk[0] = hi ? L.nx - 1 : 0; ijk[1] = a; ijk[2] = b; }
+          else if (axis == 1) { ijk[0] = a; ijk[1] = hi ? L.ny - 1 : 0; ijk[2] = b; }
+          else { ijk[0] = a; ijk[1] = b; ijk[2] = hi ? L.nz - 1 : 0; }
+          double cf[3], sf[3] = {0, 0, 0};
+          for (int q = 0; q < 3; ++q) cf[q] = o3[q] + (ijk[q] + 0.5) * d3[q];
+          cf[axis] = hi ? o3[axis] + n3[axis] * d3[axis] : o3[axis];
+          double area = (axis == 0) ? d3[1] * d3[2] : (axis == 1 ? d3[0] * d3[2] : d3[0] * d3[1]);
+          sf[axis] = (hi ? 1.0 : -1.0) * area;
+          for (int q = 0; q < 3; ++q) { ph.Cf.push_back(cf[q]); ph.Sf.push_back(sf[q]); }
+          ph.magSf.push_back(std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]));
+        }
+    }
+    if (ph.nFaces() > 0) {
+      size_t nf = (size_t)ph.nFaces();
+      if (!ctx_cuda_ok(nullptr, cudaMalloc(&ph.dCf, 3 * nf * sizeof(double)), "cudaMalloc") ||
+          !ctx_cuda_ok(nullptr, cudaMalloc(&ph.dSf, 3 * nf * sizeof(double)), "cudaMalloc") ||
+          !ctx_cuda_ok(nullptr, cudaMalloc(&ph.dMagSf, nf * sizeof(double)), "cudaMalloc")) { delete c; return IBM_E_CUDA; }
+      cudaMemcpy(ph.dCf, ph.Cf.data(), 3 * nf * sizeof(double), cudaMemcpyHostToDevice);
+      cudaMemcpy(ph.dSf, ph.Sf.data(), 3 * nf * sizeof(double), cudaMemcpyHostToDevice);
+      cudaMemcpy(ph.dMagSf, ph.magSf.data(), nf * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if ((pd.type == IBM_CYCLIC || pd.type == IBM_PROCESSOR) && ph.nFaces() != 0) c->cyclics.push_back(p);
+    else if (pd.type == IBM_WALL) c->walls.push_back(p);
+    c->patches.push_back(std::move(ph));
+  }
+  c->nGeometricD = 3 - (int)emptyDir[0] - (int)emptyDir[1] - (int)emptyDir[2];
+  if (!ctx_cuda_ok(nullptr, cudaMalloc(&c->dScal, 64 * sizeof(int)), "cudaMalloc") ||
+      !ctx_cuda_ok(nullptr, cudaMallocHost(&c->hScal, 64 * sizeof(int)), "cudaMallocHost")) { delete c; return IBM_E_CUDA; }
+  cudaMemset(c->dScal, 0, 64 * sizeof(int));
+  *out = c;
+  return IBM_OK;
+}
+
+int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
+  if (!c || n < 0 || (n > 0 && !init)) return ctx_fail(c, IBM_E_ARG, "ibm_set_particles: bad arguments");
+  cudaSetDevice(c->device);
+  if (c->cap != 0) return ctx_fail(c, IBM_E_STATE, "ibm_set_particles: particles already set");
+  c->nParticles = n;
+  c->orig.assign(init, init + n);
+  c->origCls.assign(n, -1);
+  c->maxCopies.assign(n, -1);
+  const double l = std::fabs(c->zMax - c->zMin);  // cylinder.C:73, ellipse.C:90
+  for (int i = 0; i < n; ++i) {
+    const ibm_particle_init& p = init[i];
+    // sphere.C:79-84, cylinder.C:64-70, ellipse.C:80-86: FatalError in the reference
+    if (p.kind == IBM_SPHERE && c->nGeometricD != 3) return ctx_fail(c, IBM_E_ARG, "Sphere particle shape only valid for 3D meshes");
+    if ((p.kind == IBM_CYLINDER || p.kind == IBM_ELLIPSE) && c->nGeometricD != 2)
+      return ctx_fail(c, IBM_E_ARG, "cylinder/ellipse particle shape with 1 point in axis only valid for 2D meshes");
+    if (p.kind < 0 || p.kind > 2) return ctx_fail(c, IBM_E_ARG, "Unknown particleShape type");  // particleShapeNew.C:44-49
+    if (p.nTheta < 2 || (p.kind == IBM_SPHERE && p.nTheta < 4) || p.nTheta > 65535) return ctx_fail(c, IBM_E_ARG, "nTheta out of range");
+    int found = -1;
+    for (size_t k = 0; k < c->classes.size(); ++k) {
+      const ShapeClassDev& s = c->classes[k].dev;
+      if (s.kind == p.kind && s.nTheta == p.nTheta && s.delta == p.delta &&
+          ((p.kind == IBM_ELLIPSE) ? (s.a == p.a && s.b == p.b) : (s.d == p.d))) { found = (int)k; break; }
+    }
+    if (found < 0) {
+      c->classes.emplace_back();
+      build_class(c->classes.back(), p.kind, p.d, p.a, p.b, p.nTheta, p.delta, l);
+      found = (int)c->classes.size() - 1;
+    }
+    c->origCls[i] = found;
+  }
+  int rc = upload_classes(c);
+  if (rc) return rc;
+  c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;
+  if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
+  if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
+  IBM_CUDA(c, cudaMalloc(&c->dKeep, (size_t)c->cap * sizeof(int)));
+  IBM_CUDA(c, cudaMalloc(&c->dKeepOff, (size_t)c->cap * sizeof(int)));
+  // upload originals: particleIBM(mesh, dict, index)  particleIBM.C:269-315
+  std::vector<int> iv(n);
+  std::vector<double> dv(n);
+  auto upI = [&](int* dst, auto f) { for (int i = 0; i < n; ++i) iv[i] = f(i); cudaMemcpy(dst, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice); };
+  auto upD = [&](double* dst, auto f) { for (int i = 0; i < n; ++i) dv[i] = f(i); cudaMemcpy(dst, dv.data(), n * sizeof(double), cudaMemcpyHostToDevice); };
+  if (n > 0) {
+    upI(c->in.index, [&](int i) { return i; });
+    upI(c->in.copy, [&](int) { return 0; });
+    upI(c->in.active, [&](int) { return 1; });
+    upI(c->in.onMesh, [&](int) { return IBM_ON_MESH; });
+    upI(c->in.cls, [&](int i) { return c->origCls[i]; });
+    for (int q = 0; q < 3; ++q) {
+      upD(c->in.c[q], [&](int i) { return init[i].position[q]; });
+      upD(c->in.th[q], [&](int i) { return init[i].theta[q]; });
+      upD(c->in.v[q], [&](int i) { return init[i].v[q]; });
+      upD(c->in.om[q], [&](int i) { return init[i].omega[q]; });
+    }
+    upD(c->in.rho, [&](int i) { return init[i].rho; });
+  }
+  c->nInst = n;
+  rc = ctx_update(c);
+  if (rc) return rc;
+  // maxCopies_[index] = 0 for every surviving particle (particleCloud.C:1127-1131)
+  if (c->nInst > 0) {
+    std::vector<int> idx(c->nInst);
+    cudaMemcpy(idx.data(), c->in.index, c->nInst * sizeof(int), cudaMemcpyDeviceToHost);
+    for (int i : idx) c->maxCopies[i] = 0;
+  }
+  return IBM_OK;
+}
+
+int ibm_destroy(ibm_ctx* c) {
+  if (!c) return IBM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  motion_destroy(c);
+  comm_destroy(c);
+  for (auto& p : c->events) { cudaEventDestroy(p.a); if (p.b) cudaEventDestroy(p.b); }
+  for (auto e : c->eventPool) cudaEventDestroy(e);
+  for (auto p : c->instAllocs) cudaFree(p);
+  for (auto p : c->classPools) cudaFree(p);
+  for (auto& ph : c->patches) { cudaFree(ph.dCf); cudaFree(ph.dSf); cudaFree(ph.dMagSf); }
+  void* frees[] = {c->dLatToCell, c->dCellToLat, c->dClasses, c->dShellCell, c->dShellJK, c->dScal, c->dKeep, c->dKeepOff,
+                   c->dU, c->dUold, c->dS, c->dF, c->dP, c->dTau, c->dI, c->dStage, c->dTcorr};
+  for (void* p : frees) if (p) cudaFree(p);
+  if (c->hScal) cudaFreeHost(c->hScal);
+  if (c->hPinned) cudaFreeHost(c->hPinned);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return IBM_OK;
+}
+
+int ibm_update(ibm_ctx* c) {
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  return ctx_update(c);
+}
+
+int ibm_forcing(ibm_ctx* c, const double* U, const double* Uold, const double* S, double dt, double* F) {
+  if (!c || !U || !Uold || !S || !F) return ctx_fail(c, IBM_E_ARG, "ibm_forcing: null argument");
+  cudaSetDevice(c->device);
+  const size_t C = (size_t)c->L.nCells;
+  if (!c->cfg.coupled) {  // particleCloud.C:1186-1189: a zero field
+    std::memset(F, 0, 3 * C * sizeof(double));
+    return IBM_OK;
+  }
+  int rc;
+  if ((rc = ensure_field(c, &c->dU, 3)) || (rc = ensure_field(c, &c->dUold, 3)) || (rc = ensure_field(c, &c->dS, 3))) return rc;
+  if ((rc = h2d_field(c, U, 3, c->dU)) || (rc = h2d_field(c, Uold, 3, c->dUold)) || (rc = h2d_field(c, S, 3, c->dS))) return rc;
+  if ((rc = forcing_on_device(c, c->dU, c->dUold, c->dS, dt, nullptr))) return rc;
+  if ((rc = d2h_field(c, c->dF, 3, F))) return rc;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return IBM_OK;
+}
+
+int ibm_forcing_device(ibm_ctx* c, const double* dU, const double* dUold, const double* dS, double dt, double* dF) {
+  if (!c || !dU || !dUold || !dS) return ctx_fail(c, IBM_E_ARG, "ibm_forcing_device: null argument");
+  cudaSetDevice(c->device);
+  return forcing_on_device(c, dU, dUold, dS, dt, dF);
+}
+
+int ibm_integrate_stress(ibm_ctx* c, const double* p, const double* tau6, double* FT) {
+  if (!c || !p || !tau6) return ctx_fail(c, IBM_E_ARG, "ibm_integrate_stress: null argument");
+  cudaSetDevice(c->device);
+  int rc;
+  if ((rc = ensure_field(c, &c->dP, 1)) || (rc = ensure_field(c, &c->dTau, 6))) return rc;
+  if ((rc = h2d_field(c, p, 1, c->dP)) || (rc = h2d_field(c, tau6, 6, c->dTau))) return rc;
+  if ((rc = stress_on_device(c, c->dP, c->dTau, FT))) return rc;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return IBM_OK;
+}
+
+int ibm_integrate_stress_device(ibm_ctx* c, const double* dP, const double* dTau6, double* FT_host) {
+  if (!c || !dP || !dTau6) return ctx_fail(c, IBM_E_ARG, "ibm_integrate_stress_device: null argument");
+  cudaSetDevice(c->device);
+  return stress_on_device(c, dP, dTau6, FT_host);
+}
+
+int ibm_combine_forces(ibm_ctx* c) {
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  return combine_forces(c);
+}
+
+int ibm_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  return motion_advance(c, dt, stats);
+}
+
+int ibm_substep(ibm_ctx* c, double localDt) {
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  return motion_substep(c, localDt);
+}
+
+int ibm_solve(ibm_ctx* c, const double* p, const double* tau6, double dt, ibm_solve_stats* stats) {
+  int rc = ibm_integrate_stress(c, p, tau6, nullptr);
+  if (rc) return rc;
+  if ((rc = combine_forces(c))) return rc;
+  return motion_advance(c, dt, stats);
+}
+
+int ibm_solve_device(ibm_ctx* c, const double* dP, const double* dTau6, double dt, ibm_solve_stats* stats) {
+  int rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr);
+  if (rc) return rc;
+  if ((rc = combine_forces(c))) return rc;
+  return motion_advance(c, dt, stats);
+}
+
+int ibm_n_instances(ibm_ctx* c, int* n) {
+  if (!c || !n) return IBM_E_ARG;
+  *n = c->nInst;
+  return IBM_OK;
+}
+
+int ibm_get_particles(ibm_ctx* c, ibm_particle_state* out) {
+  if (!c || (!out && c->nInst > 0)) return ctx_fail(c, IBM_E_ARG, "ibm_get_particles: null argument");
+  cudaSetDevice(c->device);
+  const int n = c->nInst;
+  if (n == 0) return IBM_OK;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<int> iv(n);
+  std::vector<double> dv(n);
+  auto dnI = [&](const int* src, auto f) { cudaMemcpy(iv.data(), src, n * sizeof(int), cudaMemcpyDeviceToHost); for (int i = 0; i < n; ++i) f(i, iv[i]); };
+  auto dnD = [&](const double* src, auto f) { cudaMemcpy(dv.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost); for (int i = 0; i < n; ++i) f(i, dv[i]); };
+  dnI(c->in.index, [&](int i, int v) { out[i].index = v; });
+  dnI(c->in.copy, [&](int i, int v) { out[i].copy = v; });
+  dnI(c->in.active, [&](int i, int v) { out[i].active = v; });
+  dnI(c->in.onMesh, [&](int i, int v) { out[i].onMesh = v; });
+  dnI(c->in.nShell, [&](int i, int v) { out[i].nShell = v; });
+  dnI(c->in.cls, [&](int i, int v) { out[i].N = c->classes[v].dev.N; });
+  for (int q = 0; q < 3; ++q) {
+    dnD(c->in.c[q], [&](int i, double v) { out[i].center[q] = v; });
+    dnD(c->in.th[q], [&](int i, double v) { out[i].theta[q] = v; });
+    dnD(c->in.v[q], [&](int i, double v) { out[i].v[q] = v; });
+    dnD(c->in.om[q], [&](int i, double v) { out[i].omega[q] = v; });
+    dnD(c->in.F[q], [&](int i, double v) { out[i].F[q] = v; });
+    dnD(c->in.T[q], [&](int i, double v) { out[i].T[q] = v; });
+  }
+  dnD(c->in.rho, [&](int i, double v) { out[i].rho = v; });
+  dnD(c->in.age, [&](int i, double v) { out[i].age = v; });
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+
+int ibm_set_force_torque(ibm_ctx* c, const double* FT) {
+  if (!c || !FT) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  const int n = c->nInst;
+  std::vector<double> dv(n);
+  for (int q = 0; q < 6; ++q) {
+    for (int i = 0; i < n; ++i) dv[i] = FT[6 * (size_t)i + q];
+    IBM_CUDA(c, cudaMemcpy(q < 3 ? c->in.F[q] : c->in.T[q - 3], dv.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return IBM_OK;
+}
+
+int ibm_cd(ibm_ctx* c, double* out) {
+  if (!c || !out) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  const int n = c->nInst;
+  if (n == 0) return IBM_OK;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<double> F(3 * (size_t)n);
+  std::vector<int> cls(n);
+  for (int q = 0; q < 3; ++q) IBM_CUDA(c, cudaMemcpy(F.data() + (size_t)q * n, c->in.F[q], n * sizeof(double), cudaMemcpyDeviceToHost));
+  IBM_CUDA(c, cudaMemcpy(cls.data(), c->in.cls, n * sizeof(int), cudaMemcpyDeviceToHost));
+  // particleIBM::Cd  particleIBM.C:583-600 (O(nInstances) scalar post-processing of the device result)
+  const double* U = c->cfg.UInf;
+  double magU = std::sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
+  double nU[3] = {U[0] / magU, U[1] / magU, U[2] / magU};
+  double magSqrU = U[0] * U[0] + U[1] * U[1] + U[2] * U[2];
+  for (int i = 0; i < n; ++i) {
+    double dotF = nU[0] * F[i] + nU[1] * F[(size_t)n + i] + nU[2] * F[2 * (size_t)n + i];
+    out[i] = dotF * 2.0 / (c->cfg.rhoRef * magSqrU * c->classes[cls[i]].dev.A);
+  }
+  return IBM_OK;
+}
+
+int ibm_max_co_num(ibm_ctx* c, double* out) {
+  if (!c || !out) return IBM_E_ARG;
+  *out = 0.0;  // particleCloud.C:1145-1156: the expression result is discarded, maxCo stays 0 (App. B #9)
+  return IBM_OK;
+}
+
+int ibm_particle_mass(ibm_ctx* c, int inst, double* mass, double* inertia) {
+  if (!c || inst < 0 || inst >= c->nInst) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  int cls;
+  double rho;
+  IBM_CUDA(c, cudaMemcpy(&cls, c->in.cls + inst, sizeof(int), cudaMemcpyDeviceToHost));
+  IBM_CUDA(c, cudaMemcpy(&rho, c->in.rho + inst, sizeof(double), cudaMemcpyDeviceToHost));
+  if (mass) *mass = c->classes[cls].dev.V * rho;
+  if (inertia) *inertia = c->classes[cls].dev.I;
+  return IBM_OK;
+}
+
+int ibm_substep_schedule(double dt, double* dts, int maxN) {
+  // literal loop of particleCloud.C:1247-1275 (App. B #22)
+  int n = 0;
+  double localDt = dt / 100.0, localTime = localDt;
+  while (localTime < dt) {
+    if (dts && n < maxN) dts[n] = localDt;
+    ++n;
+    if (localTime + localDt > dt) localDt = dt - localTime;
+    else localTime += localDt;
+  }
+  return n;
+}
+
+// ---- parity taps --------------------------------------------------------------------------------
+int ibm_get_shell(ibm_ctx* c, int inst, int* cells, int* jk, int* Is, int* Os, double* w, double* W) {
+  if (!c || inst < 0 || inst >= c->nInst) return ctx_fail(c, IBM_E_ARG, "ibm_get_shell: bad instance");
+  cudaSetDevice(c->device);
+  int n = 0;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  IBM_CUDA(c, cudaMemcpy(&n, c->in.nShell + inst, sizeof(int), cudaMemcpyDeviceToHost));
+  if (n == 0) return IBM_OK;
+  int *dI = nullptr;
+  double* dD = nullptr;
+  IBM_CUDA(c, cudaMalloc(&dI, (size_t)n * 15 * sizeof(int)));
+  IBM_CUDA(c, cudaMalloc(&dD, (size_t)n * 9 * sizeof(double)));
+  launch_tap_shell(c->stream, c->L, c->dClasses, c->in, inst, c->dShellCell, c->dShellJK, dI, dI + n, dI + 3 * (size_t)n, dI + 11 * (size_t)n, dD, dD + 8 * (size_t)n);
+  std::vector<int> hI((size_t)n * 15);
+  std::vector<double> hD((size_t)n * 9);
+  cudaMemcpyAsync(hI.data(), dI, hI.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(hD.data(), dD, hD.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dI); cudaFree(dD);
+  IBM_CUDA(c, e);
+  // the reference lists shell cells in ascending cell id (its scan order, sphere.C:208)
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hI[a] < hI[b]; });
+  for (int o = 0; o < n; ++o) {
+    int s = order[o];
+    if (cells) cells[o] = hI[s];
+    if (jk) { jk[2 * o] = hI[n + 2 * (size_t)s]; jk[2 * o + 1] = hI[n + 2 * (size_t)s + 1]; }
+    for (int q = 0; q < 8; ++q) {
+      if (Is) Is[8 * (size_t)o + q] = hI[3 * (size_t)n + 8 * (size_t)s + q];
+      if (w) w[8 * (size_t)o + q] = hD[8 * (size_t)s + q];
+    }
+    for (int q = 0; q < 4; ++q) if (Os) Os[4 * (size_t)o + q] = hI[11 * (size_t)n + 4 * (size_t)s + q];
+    if (W) W[o] = hD[8 * (size_t)n + s];
+  }
+  return IBM_OK;
+}
+
+int ibm_get_points(ibm_ctx* c, int inst, double* pts, int* cell, int* nFaces, int* otherCell, double* w, double* W) {
+  if (!c || inst < 0 || inst >= c->nInst) return ctx_fail(c, IBM_E_ARG, "ibm_get_points: bad instance");
+  cudaSetDevice(c->device);
+  int cls = 0;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  IBM_CUDA(c, cudaMemcpy(&cls, c->in.cls + inst, sizeof(int), cudaMemcpyDeviceToHost));
+  const size_t N = (size_t)c->classes[cls].dev.N;
+  int* dI = nullptr;
+  double* dD = nullptr;
+  IBM_CUDA(c, cudaMalloc(&dI, N * 8 * sizeof(int)));
+  IBM_CUDA(c, cudaMalloc(&dD, N * 10 * sizeof(double)));
+  launch_tap_points(c->stream, c->L, c->dClasses, c->in, inst, dD, dI, dI + N, dI + 2 * N, dD + 3 * N, dD + 9 * N);
+  std::vector<int> hI(N * 8);
+  std::vector<double> hD(N * 10);
+  cudaMemcpyAsync(hI.data(), dI, hI.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(hD.data(), dD, hD.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dI); cudaFree(dD);
+  IBM_CUDA(c, e);
+  if (pts) std::memcpy(pts, hD.data(), 3 * N * sizeof(double));
+  if (cell) std::memcpy(cell, hI.data(), N * sizeof(int));
+  if (nFaces) std::memcpy(nFaces, hI.data() + N, N * sizeof(int));
+  if (otherCell) std::memcpy(otherCell, hI.data() + 2 * N, 6 * N * sizeof(int));
+  if (w) std::memcpy(w, hD.data() + 3 * N, 6 * N * sizeof(double));
+  if (W) std::memcpy(W, hD.data() + 9 * N, N * sizeof(double));
+  return IBM_OK;
+}
+
+int ibm_get_sf(ibm_ctx* c, int inst, double* Sf) {
+  if (!c || !Sf || inst < 0 || inst >= c->nInst) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  int cls = 0;
+  IBM_CUDA(c, cudaMemcpy(&cls, c->in.cls + inst, sizeof(int), cudaMemcpyDeviceToHost));
+  const ShapeClassHost& h = c->classes[cls];
+  IBM_CUDA(c, cudaMemcpy(Sf, h.dev.Sf, h.Sf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  return IBM_OK;
+}
+
+int ibm_get_indicator(ibm_ctx* c, double* I) {
+  if (!c || !I) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  if (!c->dI) return ctx_fail(c, IBM_E_STATE, "ibm_get_indicator: no particles set");
+  int rc = d2h_field(c, c->dI, 1, I);
+  if (rc) return rc;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return IBM_OK;
+}
+
+// ---- device-resident helpers ---------------------------------------------------------------------
+int ibm_device_field_bytes(ibm_ctx* c, int nComp, size_t* bytes) {
+  if (!c || !bytes || nComp <= 0) return IBM_E_ARG;
+  *bytes = (size_t)nComp * c->L.nCells * sizeof(double);
+  return IBM_OK;
+}
+int ibm_upload_field(ibm_ctx* c, const double* hostAoS, int nComp, double* dSoA) {
+  if (!c || !hostAoS || !dSoA) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  return h2d_field(c, hostAoS, nComp, dSoA);
+}
+int ibm_download_field(ibm_ctx* c, const double* dSoA, int nComp, double* hostAoS) {
+  if (!c || !hostAoS) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  const double* src = dSoA ? dSoA : c->dF;  // NULL = the persistent forcing field
+  if (!src) return ctx_fail(c, IBM_E_STATE, "ibm_download_field: no forcing field yet");
+  int rc = d2h_field(c, src, nComp, hostAoS);
+  if (rc) return rc;
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return IBM_OK;
+}
+int ibm_sync(ibm_ctx* c) {
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return IBM_OK;
+}
+int ibm_set_kernel_variant(ibm_ctx* c, int fv, int sv) {
+  if (!c) return IBM_E_ARG;
+  c->forcingVariant = fv;
+  c->stressVariant = sv;
+  return IBM_OK;
+}
+
+int ibm_timings(ibm_ctx* c, ibm_timing* out) {
+  if (!c || !out) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  resolve_events(c);
+  out->update_ms = c->accMs[T_UPDATE]; out->forcing_ms = c->accMs[T_FORCING]; out->stress_ms = c->accMs[T_STRESS];
+  out->advance_ms = c->accMs[T_ADVANCE]; out->h2d_ms = c->accMs[T_H2D]; out->d2h_ms = c->accMs[T_D2H];
+  out->layout_ms = c->accMs[T_LAYOUT];
+  out->h2d_bytes = c->h2dBytes; out->d2h_bytes = c->d2hBytes; out->n_kernel_launches = c->nLaunch;
+  out->n_forcing_calls = c->nForcingCalls; out->n_updates = c->nUpdates;
+  return IBM_OK;
+}
+int ibm_timings_reset(ibm_ctx* c) {
+  if (!c) return IBM_E_ARG;
+  resolve_events(c);
+  for (double& x : c->accMs) x = 0;
+  c->h2dBytes = c->d2hBytes = c->nLaunch = c->nForcingCalls = c->nUpdates = 0;
+  return IBM_OK;
+}
+
+}  // extern "C"

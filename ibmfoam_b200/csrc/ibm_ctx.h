@@ -1,0 +1,110 @@
+// Host-side context of one particleCloud bound to one CUDA device + stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ibmfoam_b200.h"
+#include "ibm_kernels.h"
+
+namespace ibm {
+
+struct PatchHost {
+  int type = 0, side = 0, neighb = -1;
+  std::vector<double> Cf, Sf, magSf;
+  double *dCf = nullptr, *dSf = nullptr, *dMagSf = nullptr;
+  int nFaces() const { return (int)magSf.size(); }
+};
+
+struct ShapeClassHost {
+  ShapeClassDev dev{};  // device pointers filled after upload
+  std::vector<double> centered, Sf, cosT, sinT, sinP, cosP, Rtab;
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int cat;
+};
+
+enum TimeCat { T_UPDATE = 0, T_FORCING, T_STRESS, T_ADVANCE, T_H2D, T_D2H, T_LAYOUT, T_NCAT };
+
+}  // namespace ibm
+
+struct ibm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  ibm_cloud_cfg cfg{};
+  ibm::LatticeDev L{};
+  int* dLatToCell = nullptr;
+  int* dCellToLat = nullptr;
+  std::vector<int> hLatToCell;
+  std::vector<ibm::PatchHost> patches;
+  std::vector<int> walls, cyclics;  // patch ids (particleCloud.C:1050-1068)
+  int nGeometricD = 3;
+  double zMin = 0, zMax = 0;  // min/max(mesh.points()).z  (cylinder.C:73)
+
+  std::vector<ibm::ShapeClassHost> classes;
+  ibm::ShapeClassDev* dClasses = nullptr;
+  std::vector<double*> classPools;
+
+  int cap = 0, nInst = 0, nParticles = 0;
+  ibm::InstanceSoA in{};
+  ibm::InstanceSoA in2{};  // compaction / append scratch
+  std::vector<void*> instAllocs;
+  std::vector<ibm_particle_init> orig;  // origParticles_ (particleCloud.C:1082-1092)
+  std::vector<int> origCls;
+  std::vector<int> maxCopies;
+
+  int* dShellCell = nullptr;
+  int* dShellJK = nullptr;
+  int shellCap = 0, totalShell = 0;
+  int* dScal = nullptr;   // small device scalars (totals, counters)
+  int* hScal = nullptr;   // pinned mirror
+  int* dKeep = nullptr;   // keep flags / prefix
+  int* dKeepOff = nullptr;
+
+  double *dU = nullptr, *dUold = nullptr, *dS = nullptr, *dF = nullptr, *dP = nullptr, *dTau = nullptr, *dI = nullptr;
+  double* dStage = nullptr;
+  size_t stageDoubles = 0;
+  double* dTcorr = nullptr;
+  bool fLive = false;       // dF holds a previous forcing result on the current shell cells
+  bool fEverZeroed = false;
+  double* hPinned = nullptr;  // small pinned scratch for results
+  size_t hPinnedDoubles = 0;
+
+  int forcingVariant = 1, stressVariant = 1;
+
+  // motion (loop 5) scratch lives in ibm_motion.cu
+  void* motion = nullptr;
+  // comm
+  void* comm = nullptr;
+
+  std::vector<ibm::EventPair> events;
+  std::vector<cudaEvent_t> eventPool;
+  double accMs[ibm::T_NCAT] = {0, 0, 0, 0, 0, 0, 0};
+  long long h2dBytes = 0, d2hBytes = 0, nLaunch = 0, nForcingCalls = 0, nUpdates = 0;
+};
+
+namespace ibm {
+int ctx_fail(ibm_ctx* c, int code, const std::string& msg);
+bool ctx_cuda_ok(ibm_ctx* c, cudaError_t e, const char* what);
+void ctx_tic(ibm_ctx* c, int cat);
+void ctx_toc(ibm_ctx* c);
+int ctx_ensure_stage(ibm_ctx* c, size_t doubles);
+int ctx_ensure_pinned(ibm_ctx* c, size_t doubles);
+int ctx_update(ibm_ctx* c);
+// ibm_motion.cu
+int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats);
+int motion_substep(ibm_ctx* c, double localDt);
+void motion_destroy(ibm_ctx* c);
+int combine_forces(ibm_ctx* c);
+// ibm_comm.cu
+void comm_destroy(ibm_ctx* c);
+}  // namespace ibm
+
+#define IBM_CUDA(c, call)                                            \
+  do {                                                               \
+    if (!ibm::ctx_cuda_ok((c), (call), #call)) return IBM_E_CUDA;    \
+  } while (0)

@@ -1,0 +1,39 @@
+// Kernel launchers shared between translation units (reference-order TU, tuned TU, motion TU, C ABI).
+#pragma once
+#include "ibm_device.cuh"
+
+namespace ibm {
+
+// ---- ibm_kernels_ref.cu (compiled with -fmad=false) ----
+void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
+void launch_k1_fill(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                    int* shellCell, int* shellJK);
+void launch_k1_indicator(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                         double* Ifield);
+void launch_tap_shell(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int inst,
+                      const int* shellCell, const int* shellJK, int* cells, int* jk, int* Is, int* Os, double* w, double* W);
+void launch_tap_points(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int inst,
+                       double* pts, int* cell, int* nFaces, int* otherCell, double* w, double* W);
+void launch_forcing_ref(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                        const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
+                        double dT, double* F);
+void launch_stress_ref(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
+// ---- ibm_kernels_fast.cu ----
+void launch_forcing_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                         const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S, double dT,
+                         double* F);
+void launch_stress_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                        const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
+// ---- ibm_kernels_util.cu ----
+void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep);
+void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,
+                              int nInst);
+void launch_exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total);
+void launch_aos_to_soa(cudaStream_t st, const LatticeDev& L, const double* aos, int nComp, double* soa);
+void launch_soa_to_aos(cudaStream_t st, const LatticeDev& L, const double* soa, int nComp, double* aos);
+void launch_clear_shell_cells(cudaStream_t st, const int* shellCell, int total, size_t C, double* F);
+
+}  // namespace ibm

@@ -1,0 +1,107 @@
+// Plumbing kernels: exclusive scan of the per-instance shell counts, and the layout kernels that turn
+// OpenFOAM's caller-ordered array-of-structures fields (vector = 3 doubles, symmTensor = 6) into the
+// lattice-ordered structure-of-arrays planes the hot kernels read (and back for F).
+#include "ibm_kernels.h"
+
+namespace ibm {
+
+// single-block exclusive scan (n <= a few 1e5 instances; runs once per update)
+__global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total) {
+  __shared__ int warpSum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSum[warp] = x;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int q = 0; q < nw; ++q) { if (q < warp) wbase += warpSum[q]; tot += warpSum[q]; }
+    int c = carry;
+    if (i < n) out[i] = c + wbase + x - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_aos_to_soa(LatticeDev L, const double* __restrict__ aos, int nComp, double* __restrict__ soa) {
+  const size_t C = (size_t)L.nCells;
+  for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < C; l += (size_t)gridDim.x * blockDim.x) {
+    size_t c = L.latToCell ? (size_t)L.latToCell[l] : l;
+    for (int q = 0; q < nComp; ++q) soa[(size_t)q * C + l] = aos[c * nComp + q];
+  }
+}
+
+__global__ void k_soa_to_aos(LatticeDev L, const double* __restrict__ soa, int nComp, double* __restrict__ aos) {
+  const size_t C = (size_t)L.nCells;
+  for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < C; l += (size_t)gridDim.x * blockDim.x) {
+    size_t c = L.latToCell ? (size_t)L.latToCell[l] : l;
+    for (int q = 0; q < nComp; ++q) aos[c * nComp + q] = soa[(size_t)q * C + l];
+  }
+}
+
+// re-zero only the cells a previous forcing call touched (the persistent F stays zero elsewhere)
+__global__ void k_clear_shell_cells(const int* __restrict__ shellCell, int total, size_t C, double* __restrict__ F) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lat = shellCell[i];
+    F[lat] = 0.0; F[C + lat] = 0.0; F[2 * C + lat] = 0.0;
+  }
+}
+
+// deleteInActiveParticles (particleCloud.C:940-950): keep = onMesh != OFF_MESH, order preserved
+__global__ void k_keep_flags(InstanceSoA in, int n, int* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = in.onMesh[i] != 0;
+}
+
+__global__ void k_compact_instances(InstanceSoA s, InstanceSoA d, const int* __restrict__ keep, const int* __restrict__ keepOff, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  int j = keepOff[i];
+  d.index[j] = s.index[i]; d.copy[j] = s.copy[i]; d.active[j] = s.active[i]; d.onMesh[j] = s.onMesh[i]; d.cls[j] = s.cls[i];
+  d.nShell[j] = s.nShell[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i];
+  d.rho[j] = s.rho[i]; d.age[j] = s.age[i];
+  for (int q = 0; q < 3; ++q) {
+    d.c[q][j] = s.c[q][i]; d.th[q][j] = s.th[q][i]; d.v[q][j] = s.v[q][i]; d.om[q][j] = s.om[q][i];
+    d.F[q][j] = s.F[q][i]; d.T[q][j] = s.T[q][i];
+  }
+  for (int q = 0; q < 9; ++q) d.rot[9 * (size_t)j + q] = s.rot[9 * (size_t)i + q];
+}
+
+void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep) {
+  if (nInst > 0) k_keep_flags<<<(nInst + 255) / 256, 256, 0, st>>>(in, nInst, keep);
+}
+void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,
+                              int nInst) {
+  if (nInst > 0) k_compact_instances<<<(nInst + 255) / 256, 256, 0, st>>>(src, dst, keep, keepOff, nInst);
+}
+
+void launch_exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total) {
+  k_exclusive_scan<<<1, 1024, 0, st>>>(in, out, n, total);
+}
+static int grid_for(size_t n, int block, int maxBlocks = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g > (size_t)maxBlocks) g = maxBlocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+void launch_aos_to_soa(cudaStream_t st, const LatticeDev& L, const double* aos, int nComp, double* soa) {
+  k_aos_to_soa<<<grid_for(L.nCells, 256), 256, 0, st>>>(L, aos, nComp, soa);
+}
+void launch_soa_to_aos(cudaStream_t st, const LatticeDev& L, const double* soa, int nComp, double* aos) {
+  k_soa_to_aos<<<grid_for(L.nCells, 256), 256, 0, st>>>(L, soa, nComp, aos);
+}
+void launch_clear_shell_cells(cudaStream_t st, const int* shellCell, int total, size_t C, double* F) {
+  if (total > 0) k_clear_shell_cells<<<grid_for(total, 256), 256, 0, st>>>(shellCell, total, C, F);
+}
+
+}  // namespace ibm

@@ -1,0 +1,198 @@
+/* ibmfoam_b200 — C ABI of the B200-native immersed-boundary hot path.
+ *
+ * This is the drop-in boundary for IBMFoam's per-step IB loops.  The reference has no C plugin
+ * interface: its boundary is the C++ class API of libIBMparticleCloud / libparticleIBM
+ * (src/particleCloud/particleCloud.H:267-358, src/particles/particles/particleIBM/particleIBM.H:194-391),
+ * called by pimpleIBMFoam at three sites (createFields.H:60, UEqn.H:20-26, pimpleIBMFoam.C:62,87).
+ * Every entry point below cites the reference member it replaces; shim/particleCloud.{H,C} shows
+ * the OpenFOAM-side binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns 0 on success or a
+ *     negative IBM_E_* code; ibm_last_error(ctx) gives the message (the reference aborts through
+ *     FatalErrorInFunction; the shim turns a non-zero status into exactly that).
+ *   - one ibm_ctx per particleCloud, bound to one CUDA device and one stream; not re-entrant.
+ *   - all arithmetic is fp64 (OpenFOAM scalar), labels are 32-bit.
+ *   - "host" entry points take caller-ordered AoS arrays exactly as OpenFOAM stores them
+ *     (vector = 3 doubles, symmTensor = xx xy xz yy yz zz) and include the pinned H2D/D2H copies;
+ *     "_device" entry points take device pointers to structure-of-arrays fields in LATTICE order
+ *     ([component][k][j][i], i fastest) and never touch the host.
+ *   - there is no CPU fallback: without a CUDA device ibm_create fails with IBM_E_CUDA.
+ */
+#ifndef IBMFOAM_B200_H
+#define IBMFOAM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBM_ABI_VERSION 1
+
+enum { IBM_OK = 0, IBM_E_ARG = -1, IBM_E_CUDA = -2, IBM_E_STATE = -3, IBM_E_UNSUPPORTED = -4, IBM_E_COMM = -5,
+       IBM_E_CAPACITY = -6 };
+
+enum { IBM_SPHERE = 0, IBM_CYLINDER = 1, IBM_ELLIPSE = 2 };            /* particleShape run-time table: particleShapeNew.C:27-82 */
+enum { IBM_PATCH = 0, IBM_WALL = 1, IBM_CYCLIC = 2, IBM_EMPTY = 3, IBM_PROCESSOR = 4 }; /* particleCloud.C:1050-1068 */
+enum { IBM_OFF_MESH = 0, IBM_PARTIAL = 1, IBM_ON_MESH = 2 };           /* particleShape.H:62-67 */
+enum { IBM_XMIN = 0, IBM_XMAX = 1, IBM_YMIN = 2, IBM_YMAX = 3, IBM_ZMIN = 4, IBM_ZMAX = 5 };
+
+typedef struct ibm_ctx ibm_ctx;
+
+/* One boundary patch (fvPatch).  Cf/Sf/magSf are mesh.Cf()/Sf()/magSf().boundaryField()[patchi]
+ * (particleIBM.C:466-470, 504-508) in patch face order; NULL = generate them for a lattice side in
+ * the mini-mesh order (transverse index, fastest first). */
+typedef struct {
+  int type;        /* IBM_PATCH .. IBM_PROCESSOR */
+  int side;        /* IBM_XMIN .. IBM_ZMAX: lattice side the patch lies on */
+  int neighbPatch; /* cyclicPolyPatch::neighbPatchID(), else -1 */
+  int nFaces;      /* ignored when Cf == NULL */
+  const double* Cf;    /* [nFaces][3] */
+  const double* Sf;    /* [nFaces][3] */
+  const double* magSf; /* [nFaces]    */
+} ibm_patch_desc;
+
+/* The fvMesh as the path sees it: a uniform hex lattice (blockMesh with simpleGrading 1) whose cells
+ * the caller numbers block by block.  Geometry the reference reads from polyMesh (cellCentres,
+ * faceCentres, cells(), findCell — particleShape.C:39-66, sphere.C:208-216) is evaluated from the
+ * lattice on the device and never stored. */
+typedef struct {
+  int nx, ny, nz;
+  double origin[3];
+  double delta[3];
+  int nBlocks;            /* 0 = one block */
+  const int* blocks;      /* [nBlocks][6] = i0,i1,j0,j1,k0,k1 (half-open), blockMesh order */
+  const int* latticeToCell; /* optional explicit caller cell id per lattice cell (overrides blocks) */
+  int nPatches;
+  const ibm_patch_desc* patches;
+} ibm_mesh_desc;
+
+/* constant/IBMProperties top level + g (particleCloud.C:989-1005, 1034-1036; createFields.H:1) */
+typedef struct {
+  int moving, rotating, coupled;
+  double e;
+  double UInf[3];
+  double rhoRef, pRef;
+  double g[3];
+  int cyclicWithoutWalls; /* 0 = as coded (no periodic copies unless a wall patch exists) */
+  int maxInstances;       /* capacity for particle instances (originals + periodic / processor copies); 0 = 2n+64 */
+} ibm_cloud_cfg;
+
+/* constant/IBMProperties particle.<i> (particleIBM.C:269-297, particleShape.C:241-245, sphere.C:62, ellipse.C:77-78) */
+typedef struct {
+  int kind;
+  double position[3];
+  double d, a, b;
+  int nTheta, nk;
+  double delta;
+  double theta[3], v[3], omega[3];
+  double rho;
+} ibm_particle_init;
+
+/* particleIBM accessors (particleIBMI.H:25-213) for one instance, in cloud iteration order */
+typedef struct {
+  int index, copy, active, onMesh;
+  double center[3], theta[3], v[3], omega[3];
+  double rho, age;
+  double F[3], T[3];
+  int nShell, N;
+} ibm_particle_state;
+
+/* end-of-solve log block (particleCloud.C:1288-1323) */
+typedef struct {
+  int nSubSteps, nInstances;
+  double avgV[3], avgOmega[3], avgP[3];
+  double totK;
+} ibm_solve_stats;
+
+/* accumulated since ibm_timings_reset: kernel time and transfer time are reported SEPARATELY */
+typedef struct {
+  double update_ms, forcing_ms, stress_ms, advance_ms; /* kernels, CUDA events on the ctx stream */
+  double h2d_ms, d2h_ms, layout_ms;                    /* pinned copies; AoS<->SoA + cell-order kernels */
+  long long h2d_bytes, d2h_bytes;
+  long long n_kernel_launches;
+  long long n_forcing_calls, n_updates;                /* cell-particle updates (SURVEY §8d unit) */
+} ibm_timing;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* particleCloud::particleCloud(mesh, dict, g)  particleCloud.C:974-1134 (mesh + top-level dict part) */
+int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, ibm_ctx** out);
+/* ... the per-particle part of the constructor: particleIBM(mesh, dict, index) for every entry,
+ * deleteInActiveParticles, setCollisions, updateI  (particleCloud.C:1070-1133) */
+int ibm_set_particles(ibm_ctx* ctx, int n, const ibm_particle_init* init);
+int ibm_destroy(ibm_ctx* ctx);
+const char* ibm_last_error(const ibm_ctx* ctx); /* ctx may be NULL: error of the last failed ibm_create */
+int ibm_abi_version(void);
+
+/* ---- loop 1: marking ----------------------------------------------------------------------------- */
+/* particleIBM::update() for every instance + deleteInActiveParticles + updateI
+ * (particleIBM.C:602-620; {sphere,cylinder,ellipse}::updateCellLists; particleShape::setNeighbours/setWeights;
+ *  particleCloud.C:940-969) */
+int ibm_update(ibm_ctx* ctx);
+
+/* ---- loops 2+3: direct forcing ------------------------------------------------------------------- */
+/* tmp<volVectorField> particleCloud::forcing(const volVectorField& S)   particleCloud.C:1158-1208
+ * U, Uold are the "U" and U.oldTime() internal fields the reference looks up itself (:1193-1194);
+ * dt = mesh.time().deltaT() (particleIBM.C:223).  F receives the full field (zero outside shells). */
+int ibm_forcing(ibm_ctx* ctx, const double* U, const double* Uold, const double* S, double dt, double* F);
+int ibm_forcing_device(ibm_ctx* ctx, const double* dU, const double* dUold, const double* dS, double dt, double* dF);
+
+/* ---- loop 4: surface-stress integral ------------------------------------------------------------- */
+/* particleCloud::integrateSurfaceStresses()  particleCloud.C:1210-1229 — p is the "p" field, devRhoReff the
+ * cell field of particleCloud::devRhoReff() (:41-101, stays OpenFOAM's).  FT (optional) gets [nInstances][6]. */
+int ibm_integrate_stress(ibm_ctx* ctx, const double* p, const double* devRhoReff6, double* FT);
+int ibm_integrate_stress_device(ibm_ctx* ctx, const double* dP, const double* dTau6, double* FT_host);
+/* particleCloud::combineForces()  particleCloud.C:171-313 (all-reduce of the partials when ibm_comm_init was called) */
+int ibm_combine_forces(ibm_ctx* ctx);
+
+/* ---- loop 5: collisions, walls, periodic copies, integration -------------------------------------- */
+/* the sub-step loop + update part of particleCloud::solve()  particleCloud.C:1247-1324 */
+int ibm_advance(ibm_ctx* ctx, double dt, ibm_solve_stats* stats);
+/* void particleCloud::solve()  particleCloud.C:1242-1324  = integrate_stress + combine_forces + advance */
+int ibm_solve(ibm_ctx* ctx, const double* p, const double* devRhoReff6, double dt, ibm_solve_stats* stats);
+int ibm_solve_device(ibm_ctx* ctx, const double* dP, const double* dTau6, double dt, ibm_solve_stats* stats);
+/* one literal pass of the sub-step body (computeCollisions, computeWallHits, computeCyclicHits,
+ * particleIBM::solve, setPositions: particleCloud.C:1253-1265) — known-answer tests */
+int ibm_substep(ibm_ctx* ctx, double localDt);
+
+/* ---- accessors ----------------------------------------------------------------------------------- */
+int ibm_n_instances(ibm_ctx* ctx, int* n);                    /* Cloud<particleIBM>::size(), particleCloud.H:282-285 */
+int ibm_get_particles(ibm_ctx* ctx, ibm_particle_state* out); /* [nInstances] */
+int ibm_set_force_torque(ibm_ctx* ctx, const double* FT);     /* particleIBM::F()/T() non-const refs, particleIBMI.H:136-149 */
+int ibm_cd(ibm_ctx* ctx, double* out);                        /* particleCloud::Cd, particleCloud.C:1231-1240 */
+int ibm_max_co_num(ibm_ctx* ctx, double* out);                /* particleCloud::maxCoNum — always 0, particleCloud.C:1145-1156 */
+int ibm_particle_mass(ibm_ctx* ctx, int inst, double* mass, double* inertia); /* particleIBMI.H:96-99, particleShapeI.H */
+int ibm_substep_schedule(double dt, double* dts, int maxN);   /* literal loop of particleCloud.C:1247-1275; returns count */
+
+/* ---- parity taps (membership is part of the contract: bit-exact) --------------------------------- */
+/* shellCells_, neighbourPoints_ (j,k), Is_, Os_, wFromLocal_, WFromLocal_ of one instance, shell cells in
+ * ascending caller cell id (particleShape.H:131-158).  Any pointer may be NULL. */
+int ibm_get_shell(ibm_ctx* ctx, int inst, int* cells, int* jk, int* Is, int* Os, double* w, double* W);
+/* mesh_[N], findCell(mesh_[n]), number of internal faces, neighbour cell across each face (cells() order),
+ * wToLocal_, WToLocal_ (particleShape.C:42-91).  Any pointer may be NULL. */
+int ibm_get_points(ibm_ctx* ctx, int inst, double* pts, int* cell, int* nFaces, int* otherCell, double* w, double* W);
+int ibm_get_sf(ibm_ctx* ctx, int inst, double* Sf);           /* Sf_ [nTheta*nk][3] */
+int ibm_get_indicator(ibm_ctx* ctx, double* I);               /* I.ibm, caller cell order (particleCloud.C:952-969) */
+
+/* ---- device-resident helpers (bench / multi-GPU harness) ----------------------------------------- */
+int ibm_device_field_bytes(ibm_ctx* ctx, int nComponents, size_t* bytes);
+/* caller AoS (host) -> lattice SoA (device) and back, using the ctx stream and pinned staging */
+int ibm_upload_field(ibm_ctx* ctx, const double* hostAoS, int nComponents, double* dSoA);
+int ibm_download_field(ibm_ctx* ctx, const double* dSoA, int nComponents, double* hostAoS);
+int ibm_sync(ibm_ctx* ctx);
+int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant); /* 0 = reference-order kernels, 1 = tuned */
+
+/* ---- timing -------------------------------------------------------------------------------------- */
+int ibm_timings(ibm_ctx* ctx, ibm_timing* out);
+int ibm_timings_reset(ibm_ctx* ctx);
+
+/* ---- multi-GPU (slab decomposition; replaces the Pstream::combineReduce call sites) --- */
+int ibm_comm_unique_id_bytes(void);
+int ibm_comm_get_unique_id(void* idBytes);
+int ibm_comm_init(ibm_ctx* ctx, const void* idBytes, int rank, int nRanks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBMFOAM_B200_H */

@@ -1,0 +1,41 @@
+"""Shared helpers for the parity tests (oracle = checker, CUDA library = thing under test)."""
+import numpy as np
+
+from ibmfoam_b200 import cases
+
+
+def caller_fields(case, **kw):
+    """Synthetic frozen fields in CALLER cell order (AoS), like OpenFOAM internal fields."""
+    f = cases.synthetic_fields(case.mesh, **kw)
+    l2c = case.mesh.lattice_to_cell()
+    out = {}
+    for k, v in f.items():
+        o = np.empty_like(v)
+        o[l2c] = v
+        out[k] = o
+    return out
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  (field-norm relative error)."""
+    a, b = np.asarray(a), np.asarray(b)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / den) if den > 0 else float(np.max(np.abs(a - b)))
+
+
+def small_assembly(n=32, n_particles=12, seed=7, moving=False, d=8.0):
+    return cases.assembly(n=n, n_particles=n_particles, seed=seed, moving=moving, d=d)
+
+
+def ellipse_case():
+    """2-D lattice with two rotated ellipses (no reference validation case uses them; shape code only)."""
+    nx = ny = 96
+    mesh = cases.MeshSpec(nx, ny, 1, origin=(-0.3, -0.3, -0.01), delta=(0.6 / nx, 0.6 / ny, 0.02),
+                          patches=[(cases.XMIN, cases.WALL, -1), (cases.XMAX, cases.WALL, -1), (cases.YMIN, cases.CYCLIC, 3),
+                                   (cases.YMAX, cases.CYCLIC, 2), (cases.ZMIN, cases.EMPTY, -1), (cases.ZMAX, cases.EMPTY, -1)])
+    cloud = cases.CloudSpec(moving=True, rotating=True, coupled=True, e=1.0, UInf=(0.3, 0, 0))
+    parts = cases.ParticleTable.uniform(2, cases.ELLIPSE, [[-0.0713, 0.0131, 0.0], [0.0917, -0.0277, 0.0]], a=0.06, b=0.035,
+                                        nTheta=120, nk=1, delta=0.0125, rho=1200,
+                                        theta=[[0, 0, 0.37], [0, 0, 2.05]], v=[[0.1, 0.02, 0], [-0.1, 0.01, 0]],
+                                        omega=[[0, 0, 0.5], [0, 0, -0.8]])
+    return cases.Case("ellipse2", mesh, cloud, parts, dt=1e-3)
