@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the immersed-boundary hot path (BASELINE.json metric: IB cell-particle updates/s).
+
+A "step" is one fluid time step of the IB path over the synthetic scale-up workload (512^3 periodic box,
+10^5 moving spheres d = 8 cells): particleCloud::forcing (nOuter = 1) + particleCloud::solve (surface-stress
+integral, force combination, the literal sub-step loop, re-marking).  One cell-particle update = one
+(shell cell, particle instance) pair receiving its forcing contribution.
+
+  value     device-resident: SoA fields already in HBM, kernels only
+  e2e       through the host C-ABI calls with pinned host AoS fields, H2D/D2H inside the timed region
+  roofline  forcing kernel: algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, rank 0, N = 1 only
+
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "ib_cell_particle_updates_per_s"
+UNIT = "updates/s"
+
+WORKLOADS = {
+    # name: (box n, moving)
+    "big512": (512, True),
+    "big256": (256, True),
+    "asm128": (128, False),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def make_case(workload):
+    from ibmfoam_b200 import cases
+    n, moving = WORKLOADS[workload]
+    return cases.assembly(n=n, phi=0.2, moving=moving,
+                          n_particles=100000 if n == 512 else None, cyclic_without_walls=True)
+
+
+def device_fields(mesh, device):
+    """Taylor-Green-type synthetic fields, generated on the device in lattice SoA order ([comp][k][j][i])."""
+    import torch
+    nx, ny, nz = mesh.nx, mesh.ny, mesh.nz
+    dt64 = torch.float64
+    x = ((torch.arange(nx, device=device, dtype=dt64) + 0.5) * mesh.delta[0]) * (2 * math.pi / (nx * mesh.delta[0]))
+    y = ((torch.arange(ny, device=device, dtype=dt64) + 0.5) * mesh.delta[1]) * (2 * math.pi / (ny * mesh.delta[1]))
+    z = ((torch.arange(nz, device=device, dtype=dt64) + 0.5) * mesh.delta[2]) * (2 * math.pi / (nz * mesh.delta[2]))
+    X, Y, Z = x[None, None, :], y[None, :, None], z[:, None, None]
+    U0, nu = 1.0, 0.01
+    kx = 2 * math.pi / (nx * mesh.delta[0])
+
+    def vel(ph):
+        out = torch.empty((3, nz, ny, nx), device=device, dtype=dt64)
+        out[0] = U0 * torch.sin(X + ph) * torch.cos(Y) * torch.cos(Z)
+        out[1] = -U0 * torch.cos(X + ph) * torch.sin(Y) * torch.cos(Z)
+        out[2] = 0.0
+        return out
+
+    U, Uold = vel(0.0), vel(0.01)
+    S = torch.empty((3, nz, ny, nx), device=device, dtype=dt64)
+    S[0] = 0.25 * U0 * U0 * kx * torch.sin(2 * X) * torch.cos(Z) ** 2 + 0 * Y
+    S[1] = 0.25 * U0 * U0 * kx * torch.sin(2 * Y) * torch.cos(Z) ** 2 + 0 * X
+    S[2] = -(U0 * U0 / 8.0) * kx * (torch.cos(2 * X) + torch.cos(2 * Y)) * torch.sin(2 * Z)
+    P = (U0 * U0 / 16.0) * (torch.cos(2 * X) + torch.cos(2 * Y)) * (torch.cos(2 * Z) + 2.0)
+    P = P.contiguous()
+    Tau = torch.empty((6, nz, ny, nx), device=device, dtype=dt64)
+    Tau[0] = -2 * nu * U0 * kx * torch.cos(X) * torch.cos(Y) * torch.cos(Z)
+    Tau[1] = 0.0 * (X + Y + Z)
+    Tau[2] = nu * U0 * kx * torch.sin(X) * torch.cos(Y) * torch.sin(Z)
+    Tau[3] = 2 * nu * U0 * kx * torch.cos(X) * torch.cos(Y) * torch.cos(Z)
+    Tau[4] = -nu * U0 * kx * torch.cos(X) * torch.sin(Y) * torch.sin(Z)
+    Tau[5] = 0.0 * (X + Y + Z)
+    return U, Uold, S, P, Tau
+
+
+def algorithmic_bytes_forcing(case, total_shell, n_inst):
+    """72*n_touch + 72*n_s per particle per call; n_touch from the closed form for spheres on a
+    uniform grid, n_touch = 4/3 pi ((R+delta+1)^3 - (R-delta-1)^3) in cell units; n_s measured."""
+    d = float(case.particles.d[0]) / case.mesh.delta[0]
+    dl = float(case.particles.delta[0]) / case.mesh.delta[0]
+    R = d / 2
+    n_touch = 4.0 / 3.0 * math.pi * ((R + dl + 1) ** 3 - max(R - dl - 1, 0) ** 3)
+    return 72.0 * n_touch * n_inst + 72.0 * total_shell, n_touch
+
+
+def run_step_device(cloud, ptrs, dt, have_motion):
+    U, Uold, S, P, Tau = ptrs
+    cloud.forcing_device(U, Uold, S, dt)
+    if have_motion:
+        cloud.solve_device(P, Tau, dt)
+    else:
+        cloud.integrate_stress_device(P, Tau)
+        cloud.update()
+
+
+def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345):
+    """The CPU oracle (port of the reference's algorithm, 1 thread like one MPI rank of the reference) on a
+    bounded sample of the same workload: an n^3 box at the same solid fraction and particle shape."""
+    from ibmfoam_b200 import cases
+    from oracle.pyoracle import OracleCloud
+    import ibm_testutil as util
+    case = cases.assembly(n=n, moving=False, seed=seed)
+    f = util.caller_fields(case)
+    oc = OracleCloud(case)
+    t0 = time.perf_counter()
+    steps, updates = 0, 0
+    while True:
+        _, nu = oc.forcing(f["U"], f["Uold"], f["S"], case.dt)
+        oc.integrate_stress(f["p"], f["tau"])
+        oc.update()
+        steps += 1
+        updates += nu
+        if time.perf_counter() - t0 > seconds_budget or steps >= 8:
+            break
+    el = time.perf_counter() - t0
+    return updates / el, steps, el, case.particles.n
+
+
+def _ref_worker(args):
+    seed, budget, n = args
+    return cpu_baseline_sample(budget, n, seed)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the reference itself needs OpenFOAM and
+    cannot be built here), one process per host core like the reference's one-MPI-rank-per-subdomain model."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n = 128
+    budget = 12.0
+    vals, per_step = [], []
+    t_all = time.perf_counter()
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            t_all = time.perf_counter()
+        with mp.Pool(cores) as pool:
+            res = pool.map(_ref_worker, [(1000 + 17 * it + r, budget if it >= args.warmup else 1.0, n) for r in range(cores)])
+        if it >= args.warmup:
+            vals.append(sum(r[0] for r in res))
+            per_step.append(max(r[2] / r[1] for r in res))
+        if time.perf_counter() - t_all > 150:
+            break
+    v = float(np.mean(vals))
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "note": "reference algorithm on host cores (oracle port)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} independent {n}^3 sub-boxes (1565 spheres d=8 each, same solid fraction as the workload), "
+                                       "forcing + stress integral + re-marking per step, fast (ijk) search"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="big512")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from ibmfoam_b200.cloud import ParticleCloud
+    from ibmfoam_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the immersed-boundary path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    case = make_case(args.workload)
+    mesh = case.mesh
+    t0 = time.time()
+    cloud = ParticleCloud(case, device=local_rank)
+    cloud.set_kernel_variant(args.variant, args.variant)
+    setup_s = time.time() - t0
+    have_motion = True
+    try:
+        cloud.combineForces()
+    except capi.IbmError:
+        have_motion = False
+    U, Uold, S, P, Tau = device_fields(mesh, dev)
+    torch.cuda.synchronize()
+    ptrs = (U.data_ptr(), Uold.data_ptr(), S.data_ptr(), P.data_ptr(), Tau.data_ptr())
+    dt = case.dt
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        cloud.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        run_step_device(cloud, ptrs, dt, have_motion)
+    barrier()
+    cloud.timings(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        run_step_device(cloud, ptrs, dt, have_motion)
+    cloud.sync()
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop()
+    tm = cloud.timings()
+    # device time of the step = sum of the library's CUDA-event intervals on its own stream (torch events only see
+    # torch's stream); the wall clock around the synchronised region bounds it from above.
+    dev_ms = tm["update_ms"] + tm["forcing_ms"] + tm["stress_ms"] + tm["advance_ms"]
+    step_ms = max(wall_ms, dev_ms) / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    updates_per_step = tm["n_updates"] / max(1, tm["n_forcing_calls"])
+    value = updates_per_step / (step_ms * 1e-3)
+
+    n_inst = cloud.nParticles()
+    peaks, peak_kind = measured_peaks()
+    alg_bytes, n_touch = algorithmic_bytes_forcing(case, updates_per_step, n_inst)
+    forcing_ms = tm["forcing_ms"] / max(1, tm["n_forcing_calls"])
+    achieved = alg_bytes / (forcing_ms * 1e-3) / 1e9 if forcing_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "k_forcing", "peak_kind": f"of {peak_kind}",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": forcing_ms, "n_touch_closed_form": n_touch,
+                "forcing_updates_per_s": updates_per_step / (forcing_ms * 1e-3) if forcing_ms > 0 else None}
+    breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}
+
+    # ---- e2e: host C-ABI calls, pinned AoS buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e and rank == 0 and world == 1:
+        C = mesh.n_cells
+        pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        hU, hUold, hS, hF, hP, hTau = pin(C, 3), pin(C, 3), pin(C, 3), pin(C, 3), pin(C), pin(C, 6)
+        hU.copy_(U.reshape(3, C).t()); hUold.copy_(Uold.reshape(3, C).t()); hS.copy_(S.reshape(3, C).t())
+        hP.copy_(P.reshape(C)); hTau.copy_(Tau.reshape(6, C).t())
+        L = capi.load()
+        import ctypes as Ct
+        vp = lambda t: Ct.c_void_p(t.data_ptr())
+
+        def e2e_step():
+            capi.check(L.ibm_forcing(cloud.handle, vp(hU), vp(hUold), vp(hS), dt, vp(hF)), cloud.handle)
+            if have_motion:
+                st = capi.SolveStats()
+                capi.check(L.ibm_solve(cloud.handle, vp(hP), vp(hTau), dt, Ct.byref(st)), cloud.handle)
+            else:
+                capi.check(L.ibm_integrate_stress(cloud.handle, vp(hP), vp(hTau), None), cloud.handle)
+                cloud.update()
+
+        e2e_step()
+        cloud.timings(reset=True)
+        cloud.sync()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        cloud.sync()
+        e2e_ms = (time.perf_counter() - t1) * 1e3 / args.e2e_steps
+        tm2 = cloud.timings()
+        upd2 = tm2["n_updates"] / max(1, tm2["n_forcing_calls"])
+        e2e = {"value": upd2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": tm2["h2d_bytes"] // args.e2e_steps,
+               "d2h_bytes_per_step": tm2["d2h_bytes"] // args.e2e_steps, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "h2d_ms_per_step": tm2["h2d_ms"] / args.e2e_steps, "d2h_ms_per_step": tm2["d2h_ms"] / args.e2e_steps,
+               "layout_ms_per_step": tm2["layout_ms"] / args.e2e_steps}
+
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        v, steps, el, npart = cpu_baseline_sample()
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"128^3 sub-box, {npart} spheres d=8 (same solid fraction/shape as the workload), {steps} steps of "
+                         f"forcing + stress integral + re-marking in {el:.1f} s, fast (ijk) search, 1 thread"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "cells": mesh.n_cells, "particles": case.particles.n, "instances": n_inst,
+                           "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)" if have_motion else "n/a",
+                           "step": "forcing + solve(stress, combine, sub-steps, re-marking)" if have_motion else "forcing + stress + re-marking (loop 5 not built)",
+                           "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["n_kernel_launches"], "clocks": clocks,
+                "breakdown_ms_per_step": breakdown, "wall_ms_per_step": wall_ms / args.steps}
+        print(json.dumps(line))
+    cloud.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

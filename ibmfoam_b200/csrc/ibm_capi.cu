@@ -245,6 +245,7 @@ int ctx_update(ibm_ctx* c) {
     launch_compact_instances(c->stream, c->in, c->in2, c->dKeep, c->dKeepOff, c->nInst);
     std::swap(c->in, c->in2);
     c->nInst = c->hScal[0];
+    motion_invalidate_groups(c);
     launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
     c->nLaunch += 2;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));

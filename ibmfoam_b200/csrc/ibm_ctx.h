@@ -99,6 +99,7 @@ int ctx_update(ibm_ctx* c);
 int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats);
 int motion_substep(ibm_ctx* c, double localDt);
 void motion_destroy(ibm_ctx* c);
+void motion_invalidate_groups(ibm_ctx* c);
 int combine_forces(ibm_ctx* c);
 // ibm_comm.cu
 void comm_destroy(ibm_ctx* c);

@@ -1,8 +1,882 @@
-// Loop 5 — collisions, wall hits, periodic copies, sub-stepped integration (placeholder until K5 lands).
+// Loop 5 — collisions, wall hits, periodic copies, sub-stepped integration, force combination.
+// (translation unit compiled with -fmad=false: every operation below is a plain IEEE +,-,*,/,sqrt in the
+//  reference's evaluation order, so sphere / cylinder trajectories are bit-identical to an x86-64 build.)
+//
+//   particleCloud::computeCollisions  particleCloud.C:482-581   -> k5_sort_keys + radix sort + k5_contacts + k5_merge
+//   particleIBM::collision            particleIBM.C:41-205      -> pair_collision()
+//   particleCloud::computeWallHits    particleCloud.C:584-656   -> k5_walls (+ k5_merge)
+//   particleCloud::computeCyclicHits  particleCloud.C:659-937   -> k5_cyclic_detect + scan + k5_append
+//   particleIBM::solve                particleIBM.C:393-450     -> k5_solve
+//   particleCloud::setPositions       particleCloud.C:316-444   -> k5_set_positions
+//   particleCloud::combineForces      particleCloud.C:171-313   -> k_combine_forces
+//   particleCloud::solve (loop+log)   particleCloud.C:1247-1324 -> motion_advance
+//
+// The reference keeps dense nParticles x nParticles force tables and visits all ordered pairs; here a uniform
+// cell list (bin edge >= largest diameter, realised as a sorted key array + binary search) yields the same
+// contact set, stored sparsely per instance and summed in partner-index order (the reference's sum() order).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+
 #include "ibm_ctx.h"
+
 namespace ibm {
-int motion_advance(ibm_ctx* c, double, ibm_solve_stats*) { return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_advance: not built yet"); }
-int motion_substep(ibm_ctx* c, double) { return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_substep: not built yet"); }
-void motion_destroy(ibm_ctx*) {}
-int combine_forces(ibm_ctx* c) { return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_combine_forces: not built yet"); }
+
+#define CONTACT_CAP 24
+
+struct PatchDev {
+  int type, side, neighb, nFaces;
+  const double *Cf, *Sf, *magSf;
+  int latticeOrdered;  // faces in transverse lattice order (fastest index first): candidate faces by index box
+  int nA, nB;          // transverse extents
+};
+
+struct MotionDev {
+  int cap, nParticles, nWalls, nCyc;
+  int* nInst;  // device-side instance count (appends happen on the device)
+  // cell list
+  double bx0, by0, bz0, binEdge;
+  int nbx, nby, nbz;
+  unsigned* keys; unsigned* keysSorted; int* vals; int* valsSorted;
+  // sparse contact tables (sorted by partner index)
+  int* cCnt; int* cIdx; double* cF; double* cT;
+  int* cCnt2; int* cIdx2; double* cF2; double* cT2;
+  int* overflow;
+  // wall tables [cap][nWalls][3]
+  double* Fw; double* Tw; double* Fw2; double* Tw2;
+  // same-index groups in cloud order
+  int* idxHead; int* idxTail; int* instNext;
+  // originals (origParticles_) and copy counters
+  const int* origCls; const double* origRho; int* maxCopies;
+  // cyclic hits
+  int* hitFlag; int* hitOff; int* hitFace; double* hitCenter; int* hitTotal;
+  const PatchDev* patches; const int* wallPatch; const int* cycPatch;
+  double gx, gy, gz, e;
+  int moving, rotating;
+};
+
+struct Motion {
+  MotionDev d{};
+  std::vector<void*> allocs;
+  void* cubTemp = nullptr;
+  size_t cubTempBytes = 0;
+  PatchDev* dPatches = nullptr;
+  bool groupsValid = false;
+  int* dIdxKeys = nullptr; int* dIdxKeys2 = nullptr;
+  double* dStats = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers in the reference's evaluation order
+// ------------------------------------------------------------------------------------------------
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ D3 operator/(D3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ double dot3(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 cross3(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double magSqr3(D3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ double mag3(D3 a) { return sqrt(magSqr3(a)); }
+__device__ __forceinline__ D3 ld3(double* const* p, int i) { return {p[0][i], p[1][i], p[2][i]}; }
+__device__ __forceinline__ void st3(double* const* p, int i, D3 v) { p[0][i] = v.x; p[1][i] = v.y; p[2][i] = v.z; }
+__device__ __forceinline__ D3 rotv(const double* R, D3 v) {
+  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
+}
+__device__ __forceinline__ D3 classD(const ShapeClassDev& s) { return s.kind == 2 ? D3{s.a, s.b, s.l} : D3{s.d, s.d, s.d}; }
+__device__ __forceinline__ double cmptMax3(D3 a) { return fmax(a.x, fmax(a.y, a.z)); }
+
+__device__ __forceinline__ double shape_r_at(const ShapeClassDev& sc, D3 c, double thz, D3 pt) {
+  if (sc.kind != 2) return sc.d / 2.0;
+  D3 diff = pt - c;
+  double th = atan2(diff.y, diff.x) - thz;
+  double ca = cos(th) / sc.a, sb = sin(th) / sc.b;
+  return sqrt(1.0 / (ca * ca + sb * sb));
+}
+
+// particleShape::setRotationMatrix (particleShape.C:186-223) — used for freshly appended copies
+__device__ void rot_from_theta(double tx, double ty, double tz, double* R) {
+  R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+  auto mul = [&](const double* B) {
+    double A[9];
+    for (int q = 0; q < 9; ++q) A[q] = R[q];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) R[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+  };
+  if (fabs(tx) > IBM_SMALL) { double c = cos(tx), s = sin(tx); double B[9] = {1.0, 0.0, 0.0, 0.0, c, -s, 0.0, s, c}; mul(B); }
+  if (fabs(ty) > IBM_SMALL) { double c = cos(ty), s = sin(ty); double B[9] = {c, 0.0, s, 0.0, 1.0, 0.0, -s, 0.0, c}; mul(B); }
+  if (fabs(tz) > IBM_SMALL) { double c = cos(tz), s = sin(tz); double B[9] = {c, -s, 0.0, s, c, 0.0, 0.0, 0.0, 1.0}; mul(B); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// particleIBM::collision(p1, p2, collisionPt)   particleIBM.C:41-205
+// ------------------------------------------------------------------------------------------------
+struct PView {
+  D3 c; D3 D; double thz; const double* R; const ShapeClassDev* sc;
+};
+
+__device__ bool pair_collision(const PView& p1, const PView& p2, D3& collisionPt) {
+  const double pi = IBM_PI;
+  D3 center1 = p1.c, center2 = p2.c;
+  D3 diff = center2 - center1;
+  D3 d1 = p1.D, d2 = p2.D;
+  if (mag3(diff) > 0.5 * (cmptMax3(d1) + cmptMax3(d2))) return false;
+  if ((d1.x + d1.y + d1.z) / 3.0 == cmptMax3(d1) && (d2.x + d2.y + d2.z) / 3.0 == cmptMax3(d2))  // App. B #21
+    return 0.5 * (cmptMax3(d1) + cmptMax3(d2)) > mag3(diff);
+  D3 pt1 = center1, pt2 = center2;
+  const double* R1 = p1.R;
+  const double* R2 = p2.R;
+  double gamma1 = atan2(diff.y, diff.x) - p1.thz;
+  double gamma2 = atan2(diff.y, diff.x) - p2.thz;
+  if (center2.x < center1.x) gamma2 -= pi; else gamma1 -= pi;
+  double r1 = shape_r_at(*p1.sc, p1.c, p1.thz, pt2), r2 = shape_r_at(*p2.sc, p2.c, p2.thz, pt1);
+  double x1 = r1 * cos(gamma1), x2 = r2 * cos(gamma2);
+  const bool flip = tan(p1.thz) * tan(p2.thz) < 0;
+  if (flip) { x1 *= -1.0; x2 *= -1.0; }
+  bool converged = false, hit = false;
+  int itt = 0;
+  while (!converged) {
+    itt++;
+    pt1 = rotv(R1, D3{x1, 0, 0}) + center1;
+    pt2 = rotv(R2, D3{x2, 0, 0}) + center2;
+    D3 oldDiff = diff;
+    diff = pt2 - pt1;
+    double alpha1 = atan2(diff.y, diff.x) - p1.thz;
+    double alpha2 = atan2(diff.y, diff.x) - p2.thz;
+    if (center2.x < center1.x) alpha2 -= pi; else alpha1 -= pi;
+    D3 rp1 = pt1, rp1Local = rp1;
+    {
+      double m = tan(alpha1), I = -m * x1;
+      double a = m * m + (d1.y / d1.x) * (d1.y / d1.x), b = 2.0 * m * I, c = I * I - d1.y * d1.y;
+      double posRoot = (-b + sqrt(b * b - 4.0 * a * c)) / (2.0 * a);
+      double negRoot = (-b - sqrt(b * b - 4.0 * a * c)) / (2.0 * a);
+      D3 rpPos = rotv(R1, D3{posRoot, I + posRoot * m, 0}) + center1;
+      D3 rpNeg = rotv(R1, D3{negRoot, I + negRoot * m, 0}) + center1;
+      if (mag3(rpPos - center2) < mag3(rpNeg - center2)) { rp1 = rpPos; rp1Local = D3{posRoot, I + posRoot * m, 0}; }
+      else { rp1 = rpNeg; rp1Local = D3{negRoot, I + negRoot * m, 0}; }
+      gamma1 = atan2(rp1Local.y, rp1Local.x);
+    }
+    D3 rp2 = pt2, rp2Local = rp2;
+    {
+      double m = tan(alpha2), I = -m * x2;
+      double a = m * m + (d2.y / d2.x) * (d2.y / d2.x), b = 2.0 * m * I, c = I * I - d2.y * d2.y;
+      double posRoot = (-b + sqrt(b * b - 4.0 * a * c)) / (2.0 * a);
+      double negRoot = (-b - sqrt(b * b - 4.0 * a * c)) / (2.0 * a);
+      D3 rpPos = rotv(R2, D3{posRoot, I + posRoot * m, 0}) + center2;
+      D3 rpNeg = rotv(R2, D3{negRoot, I + negRoot * m, 0}) + center2;
+      if (mag3(rpPos - center1) < mag3(rpNeg - center1)) { rp2 = rpPos; rp2Local = D3{posRoot, I + posRoot * m, 0}; }
+      else { rp2 = rpNeg; rp2Local = D3{negRoot, I + negRoot * m, 0}; }
+      gamma2 = atan2(rp2Local.y, rp2Local.x);
+    }
+    r1 = mag3(rp1Local);
+    r2 = mag3(rp2Local);
+    x1 = r1 * cos(gamma1);
+    x2 = r2 * cos(gamma2);
+    if (flip) { x1 *= -1.0; x2 *= -1.0; }
+    if (dot3(diff, rp2 - rp1) < 0) {
+      converged = true;
+      hit = true;
+      collisionPt = 0.5 * (rp1 + rp2);
+    }
+    if (mag3(oldDiff) < mag3(diff) || itt > 10) converged = true;
+  }
+  return hit;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell list: key per instance, sorted by a stable radix sort (ties keep cloud order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bin_of(const MotionDev& m, D3 c, int& bx, int& by, int& bz) {
+  bx = min(max((int)floor((c.x - m.bx0) / m.binEdge), 0), m.nbx - 1);
+  by = min(max((int)floor((c.y - m.by0) / m.binEdge), 0), m.nby - 1);
+  bz = min(max((int)floor((c.z - m.bz0) / m.binEdge), 0), m.nbz - 1);
+}
+
+__global__ void k5_sort_keys(MotionDev m, InstanceSoA in) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.cap) return;
+  unsigned key = 0xffffffffu;
+  if (i < *m.nInst) {
+    int bx, by, bz;
+    bin_of(m, ld3(in.c, i), bx, by, bz);
+    key = (unsigned)(bx + m.nbx * (by + m.nby * bz));
+  }
+  m.keys[i] = key;
+  m.vals[i] = i;
+}
+
+__device__ __forceinline__ int lower_bound_u(const unsigned* a, int n, unsigned key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// particleCloud::computeCollisions, pair part (particleCloud.C:484-523).  Thread i builds its own sparse row
+// collisionForces_[.] by evaluating every pair it takes part in exactly as the reference would (as p1 when its
+// index is the larger one, as p2 otherwise).  Duplicate partner indices (periodic copies): the last write in
+// the reference's loop order wins == the partner with the largest cloud position.
+__global__ void k5_contacts(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = *m.nInst;
+  if (i >= n) return;
+  int cnt = 0;
+  int eIdx[CONTACT_CAP], ePos[CONTACT_CAP];
+  D3 eF[CONTACT_CAP], eT[CONTACT_CAP];
+  if (in.onMesh[i] != 0) {
+    const ShapeClassDev* sci = classes + in.cls[i];
+    PView me{ld3(in.c, i), classD(*sci), in.th[2][i], in.rot + 9 * (size_t)i, sci};
+    const D3 vi = ld3(in.v, i);
+    const double mi = sci->V * in.rho[i];
+    const int idxI = in.index[i];
+    int bx, by, bz;
+    bin_of(m, me.c, bx, by, bz);
+    for (int dz = -1; dz <= 1; ++dz) {
+      int z = bz + dz;
+      if (z < 0 || z >= m.nbz) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        int y = by + dy;
+        if (y < 0 || y >= m.nby) continue;
+        int x0 = max(bx - 1, 0), x1 = min(bx + 1, m.nbx - 1);
+        unsigned k0 = (unsigned)(x0 + m.nbx * (y + m.nby * z)), k1 = (unsigned)(x1 + m.nbx * (y + m.nby * z));
+        int s = lower_bound_u(m.keysSorted, n, k0), e = lower_bound_u(m.keysSorted, n, k1 + 1u);
+        for (int q = s; q < e; ++q) {
+          int j = m.valsSorted[q];
+          if (j == i) continue;
+          const int idxJ = in.index[j];
+          if (idxJ == idxI || in.onMesh[j] == 0) continue;
+          const ShapeClassDev* scj = classes + in.cls[j];
+          PView other{ld3(in.c, j), classD(*scj), in.th[2][j], in.rot + 9 * (size_t)j, scj};
+          const D3 vj = ld3(in.v, j);
+          const double mj = scj->V * in.rho[j];
+          const bool iAmP1 = idxI > idxJ;
+          const PView& p1 = iAmP1 ? me : other;
+          const PView& p2 = iAmP1 ? other : me;
+          D3 x12 = p1.c - p2.c;
+          D3 v12 = iAmP1 ? (vi - vj) : (vj - vi);
+          D3 hitPt{0, 0, 0};
+          if (!pair_collision(p1, p2, hitPt)) continue;
+          if (!(dot3(x12, v12) < 0)) continue;
+          double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
+          double M = mass1 * mass2 / (mass1 + mass2);
+          double x12Dotv12 = dot3(x12, v12);
+          double x12Sqr = magSqr3(x12);
+          D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
+          D3 myF = iAmP1 ? -F : F;
+          D3 myT = iAmP1 ? cross3(-F, hitPt) : cross3(F, hitPt);
+          int slot = -1;
+          for (int t = 0; t < cnt; ++t) if (eIdx[t] == idxJ) slot = t;
+          if (slot < 0) {
+            if (cnt >= CONTACT_CAP) { atomicExch(m.overflow, 1); continue; }
+            slot = cnt++;
+            eIdx[slot] = idxJ; ePos[slot] = -1;
+          }
+          if (j > ePos[slot]) { ePos[slot] = j; eF[slot] = myF; eT[slot] = myT; }
+        }
+      }
+    }
+  }
+  // sort by partner index (sum(collisionForces_) runs over the table in index order, particleIBM.C:408-411)
+  for (int a = 1; a < cnt; ++a) {
+    int ki = eIdx[a]; D3 f = eF[a], t = eT[a];
+    int b = a - 1;
+    while (b >= 0 && eIdx[b] > ki) { eIdx[b + 1] = eIdx[b]; eF[b + 1] = eF[b]; eT[b + 1] = eT[b]; --b; }
+    eIdx[b + 1] = ki; eF[b + 1] = f; eT[b + 1] = t;
+  }
+  m.cCnt[i] = cnt;
+  for (int a = 0; a < cnt; ++a) {
+    size_t o = (size_t)i * CONTACT_CAP + a;
+    m.cIdx[o] = eIdx[a];
+    m.cF[3 * o] = eF[a].x; m.cF[3 * o + 1] = eF[a].y; m.cF[3 * o + 2] = eF[a].z;
+    m.cT[3 * o] = eT[a].x; m.cT[3 * o + 1] = eT[a].y; m.cT[3 * o + 2] = eT[a].z;
+  }
+}
+
+// particleIBM::wallHit for every wall slot (particleIBM.C:453-488, particleCloud.C:591-597)
+__device__ __forceinline__ void face_range(const MotionDev& m, const LatticeDev& L, const PatchDev& p, D3 c, double r, int& a0, int& a1,
+                                           int& b0, int& b1) {
+  a0 = 0; a1 = p.nA - 1; b0 = 0; b1 = p.nB - 1;
+  if (!p.latticeOrdered) { a0 = 0; a1 = p.nFaces - 1; b0 = b1 = 0; return; }
+  const int axis = p.side / 2;
+  const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz}, c3[3] = {c.x, c.y, c.z};
+  const int ta = (axis == 0) ? 1 : 0, tb = (axis == 2) ? 1 : 2;
+  a0 = max(0, (int)floor((c3[ta] - r - o3[ta]) / d3[ta]) - 1); a1 = min(p.nA - 1, (int)floor((c3[ta] + r - o3[ta]) / d3[ta]) + 1);
+  b0 = max(0, (int)floor((c3[tb] - r - o3[tb]) / d3[tb]) - 1); b1 = min(p.nB - 1, (int)floor((c3[tb] + r - o3[tb]) / d3[tb]) + 1);
+}
+
+__global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *m.nInst) return;
+  if (in.onMesh[i] == 0) return;
+  const ShapeClassDev* sc = classes + in.cls[i];
+  const D3 c = ld3(in.c, i), v = ld3(in.v, i), om = ld3(in.om, i);
+  const double thz = in.th[2][i];
+  const double mass = sc->V * in.rho[i];
+  for (int w = 0; w < m.nWalls; ++w) {
+    const PatchDev& p = m.patches[m.wallPatch[w]];
+    int a0, a1, b0, b1;
+    face_range(m, L, p, c, sc->Rbound, a0, a1, b0, b1);
+    bool done = false;
+    for (int b = b0; b <= b1 && !done; ++b)
+      for (int a = a0; a <= a1 && !done; ++a) {
+        int facei = p.latticeOrdered ? a + p.nA * b : a;
+        D3 fc{p.Cf[3 * facei], p.Cf[3 * facei + 1], p.Cf[3 * facei + 2]};
+        D3 sf{p.Sf[3 * facei], p.Sf[3 * facei + 1], p.Sf[3 * facei + 2]};
+        D3 norm = sf / p.magSf[facei];
+        D3 rv = cross3(-(fc - c), om) + v;  // v(faceCentre)
+        D3 R = c - fc;
+        if (mag3(R) <= shape_r_at(*sc, c, thz, fc) && dot3(rv, norm) > 0) {
+          D3 vNorm = norm * dot3(norm, rv);
+          D3 rHat = R / mag3(R);
+          D3 F = -2.0 * mass * vNorm / dt;
+          D3 Fw = dot3(F, rHat) * rHat;
+          D3 Tw = cross3(F - Fw, R);
+          size_t o = 3 * ((size_t)i * m.nWalls + w);
+          m.Fw[o] = Fw.x; m.Fw[o + 1] = Fw.y; m.Fw[o + 2] = Fw.z;
+          m.Tw[o] = Tw.x; m.Tw[o + 1] = Tw.y; m.Tw[o + 2] = Tw.z;
+          done = true;  // only one hit per patch
+        }
+      }
+  }
+}
+
+// Copies of one index share the larger-magnitude entry (particleCloud.C:525-554, 599-620).  The reference's
+// in-place pair sweep leaves every member of a same-index group with the entry of largest magnitude, ties going
+// to the member latest in cloud order; evaluated here per instance from the pre-merge tables (double buffered).
+__global__ void k5_merge(MotionDev m, InstanceSoA in) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *m.nInst) return;
+  const int idx = in.index[i];
+  const int head = m.idxHead[idx];
+  int cnt = 0;
+  int eIdx[CONTACT_CAP];
+  D3 eF[CONTACT_CAP], eT[CONTACT_CAP];
+  double eMag[CONTACT_CAP];
+  for (int mem = head; mem >= 0; mem = m.instNext[mem]) {
+    int c = m.cCnt[mem];
+    for (int a = 0; a < c; ++a) {
+      size_t o = (size_t)mem * CONTACT_CAP + a;
+      int k = m.cIdx[o];
+      D3 f{m.cF[3 * o], m.cF[3 * o + 1], m.cF[3 * o + 2]};
+      double mg = mag3(f);
+      int slot = -1;
+      for (int t = 0; t < cnt; ++t) if (eIdx[t] == k) slot = t;
+      if (slot < 0) {
+        if (cnt >= CONTACT_CAP) { atomicExch(m.overflow, 1); continue; }
+        slot = cnt++;
+        eIdx[slot] = k; eMag[slot] = -1.0;
+      }
+      if (mg >= eMag[slot]) {  // members are visited in cloud order: ">=" lets the later member win ties
+        eMag[slot] = mg; eF[slot] = f;
+        eT[slot] = D3{m.cT[3 * o], m.cT[3 * o + 1], m.cT[3 * o + 2]};
+      }
+    }
+  }
+  for (int a = 1; a < cnt; ++a) {
+    int ki = eIdx[a]; D3 f = eF[a], t = eT[a];
+    int b = a - 1;
+    while (b >= 0 && eIdx[b] > ki) { eIdx[b + 1] = eIdx[b]; eF[b + 1] = eF[b]; eT[b + 1] = eT[b]; --b; }
+    eIdx[b + 1] = ki; eF[b + 1] = f; eT[b + 1] = t;
+  }
+  m.cCnt2[i] = cnt;
+  for (int a = 0; a < cnt; ++a) {
+    size_t o = (size_t)i * CONTACT_CAP + a;
+    m.cIdx2[o] = eIdx[a];
+    m.cF2[3 * o] = eF[a].x; m.cF2[3 * o + 1] = eF[a].y; m.cF2[3 * o + 2] = eF[a].z;
+    m.cT2[3 * o] = eT[a].x; m.cT2[3 * o + 1] = eT[a].y; m.cT2[3 * o + 2] = eT[a].z;
+  }
+  for (int w = 0; w < m.nWalls; ++w) {
+    double best = -1.0;
+    D3 bf{0, 0, 0}, bt{0, 0, 0};
+    for (int mem = head; mem >= 0; mem = m.instNext[mem]) {
+      size_t o = 3 * ((size_t)mem * m.nWalls + w);
+      D3 f{m.Fw[o], m.Fw[o + 1], m.Fw[o + 2]};
+      double mg = mag3(f);
+      if (mg >= best) { best = mg; bf = f; bt = D3{m.Tw[o], m.Tw[o + 1], m.Tw[o + 2]}; }
+    }
+    size_t o = 3 * ((size_t)i * m.nWalls + w);
+    m.Fw2[o] = bf.x; m.Fw2[o + 1] = bf.y; m.Fw2[o + 2] = bf.z;
+    m.Tw2[o] = bt.x; m.Tw2[o + 1] = bt.y; m.Tw2[o + 2] = bt.z;
+  }
+}
+
+// particleIBM::patchHit + found() for every (cyclic patch, instance)   particleIBM.C:490-517, particleCloud.C:447-479, 685-730
+__global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int slot = blockIdx.y;
+  const int n = *m.nInst;
+  if (i >= m.cap) return;
+  size_t h = (size_t)slot * m.cap + i;
+  m.hitFlag[h] = 0;
+  if (i >= n || in.onMesh[i] == 0) return;
+  const PatchDev& p = m.patches[m.cycPatch[slot]];
+  if (p.type != IBM_CYCLIC) return;  // processor patches are handled by the slab exchange, not here
+  const ShapeClassDev* sc = classes + in.cls[i];
+  const D3 c = ld3(in.c, i), v = ld3(in.v, i);
+  const double thz = in.th[2][i];
+  int a0, a1, b0, b1;
+  face_range(m, L, p, c, sc->Rbound, a0, a1, b0, b1);
+  for (int b = b0; b <= b1; ++b)
+    for (int a = a0; a <= a1; ++a) {
+      int facei = p.latticeOrdered ? a + p.nA * b : a;
+      D3 fc{p.Cf[3 * facei], p.Cf[3 * facei + 1], p.Cf[3 * facei + 2]};
+      D3 sf{p.Sf[3 * facei], p.Sf[3 * facei + 1], p.Sf[3 * facei + 2]};
+      D3 norm = sf / p.magSf[facei];
+      D3 R = c - fc;
+      if (mag3(R) <= shape_r_at(*sc, c, thz, fc) && dot3(v, norm) > 0) {
+        const PatchDev& q = m.patches[p.neighb];
+        D3 nc = R + D3{q.Cf[3 * facei], q.Cf[3 * facei + 1], q.Cf[3 * facei + 2]};
+        bool f = false;
+        for (int mem = m.idxHead[in.index[i]]; mem >= 0; mem = m.instNext[mem])
+          if (mag3(nc - ld3(in.c, mem)) < 1e-4) f = true;  // App. B #15
+        if (!f) {
+          m.hitFlag[h] = 1;
+          m.hitFace[h] = facei;
+          m.hitCenter[3 * h] = nc.x; m.hitCenter[3 * h + 1] = nc.y; m.hitCenter[3 * h + 2] = nc.z;
+        }
+        return;
+      }
+    }
+}
+
+// append the new periodic copies in the reference's order (patch-major, cloud order within a patch):
+// particleIBM copy constructor (particleIBM.C:318-350) from origParticles_[index]   particleCloud.C:815-832
+__global__ void k5_append(MotionDev m, InstanceSoA in) {
+  const int total = *m.hitTotal;
+  if (total == 0) return;
+  const int n0 = *m.nInst;
+  const int nSlots = m.nCyc * m.cap;
+  const int room = m.cap - n0;
+  if (total > room) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(m.overflow, 2); return; }
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nSlots; h += gridDim.x * blockDim.x) {
+    if (!m.hitFlag[h]) continue;
+    int src = h % m.cap;
+    int dst = n0 + m.hitOff[h];
+    int idx = in.index[src];
+    in.index[dst] = idx;
+    in.copy[dst] = -1;  // assigned sequentially below
+    in.active[dst] = 0;
+    in.onMesh[dst] = IBM_PARTIAL;
+    in.cls[dst] = m.origCls[idx];
+    for (int q = 0; q < 3; ++q) {
+      in.c[q][dst] = m.hitCenter[3 * (size_t)h + q];
+      in.th[q][dst] = in.th[q][src];
+      in.v[q][dst] = in.v[q][src];
+      in.om[q][dst] = in.om[q][src];
+      in.F[q][dst] = 0.0;  // integratedForce_ of origParticles_[index] (never updated after construction)
+      in.T[q][dst] = 0.0;
+    }
+    in.rho[dst] = m.origRho[idx];
+    in.age[dst] = in.age[src];
+    in.nShell[dst] = 0; in.shellOff[dst] = 0; in.nPtsOnMesh[dst] = 0;
+    rot_from_theta(in.th[0][src], in.th[1][src], in.th[2][src], in.rot + 9 * (size_t)dst);
+    m.cCnt[dst] = 0;
+    m.cCnt2[dst] = 0;
+    for (int w = 0; w < m.nWalls; ++w)
+      for (int q = 0; q < 3; ++q) {
+        size_t o = 3 * ((size_t)dst * m.nWalls + w) + q;
+        m.Fw[o] = 0.0; m.Tw[o] = 0.0; m.Fw2[o] = 0.0; m.Tw2[o] = 0.0;
+      }
+  }
+}
+
+__global__ void k5_append_total(MotionDev m) {
+  const int last = m.nCyc * m.cap - 1;
+  *m.hitTotal = m.hitOff[last] + m.hitFlag[last];
+}
+
+// sequential part of the append: copy ids (maxCopies_[index]+1, ++) and the same-index lists, in append order
+__global__ void k5_append_link(MotionDev m, InstanceSoA in) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int total = *m.hitTotal;
+  if (total == 0 || total > m.cap - *m.nInst) return;
+  const int n0 = *m.nInst;
+  for (int t = 0; t < total; ++t) {
+    int dst = n0 + t;
+    int idx = in.index[dst];
+    in.copy[dst] = m.maxCopies[idx] + 1;
+    m.maxCopies[idx] += 1;
+    m.instNext[dst] = -1;
+    int tail = m.idxTail[idx];
+    if (tail >= 0) m.instNext[tail] = dst; else m.idxHead[idx] = dst;
+    m.idxTail[idx] = dst;
+  }
+  *m.nInst = n0 + total;
+}
+
+// particleIBM::solve(dt, g, moving, rotation)   particleIBM.C:393-450
+__global__ void k5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt,
+                         const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA, int* cCntB) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *m.nInst) return;
+  if (in.onMesh[i] == 0) return;
+  const ShapeClassDev* sc = classes + in.cls[i];
+  const double mass = sc->V * in.rho[i];
+  const int cnt = cCnt[i];
+  if (m.moving) {
+    D3 sFc{0, 0, 0}, sFw{0, 0, 0};
+    for (int a = 0; a < cnt; ++a) { size_t o = 3 * ((size_t)i * CONTACT_CAP + a); sFc = sFc + D3{cF[o], cF[o + 1], cF[o + 2]}; }
+    for (int w = 0; w < m.nWalls; ++w) { size_t o = 3 * ((size_t)i * m.nWalls + w); sFw = sFw + D3{Fw[o], Fw[o + 1], Fw[o + 2]}; }
+    D3 F = ld3(in.F, i) + sFc + sFw;
+    D3 v = ld3(in.v, i);
+    v = v + dt * (F / mass + D3{m.gx, m.gy, m.gz});
+    st3(in.v, i, v);
+    D3 dx = dt * v;
+    D3 c = ld3(in.c, i) + dx;
+    st3(in.c, i, c);
+    int I, J, K;
+    in.active[i] = find_cell(L, c.x, c.y, c.z, I, J, K) >= 0;  // particleIBM.C:417-424
+  }
+  if (m.rotating) {
+    D3 sTc{0, 0, 0}, sTw{0, 0, 0};
+    for (int a = 0; a < cnt; ++a) { size_t o = 3 * ((size_t)i * CONTACT_CAP + a); sTc = sTc + D3{cT[o], cT[o + 1], cT[o + 2]}; }
+    for (int w = 0; w < m.nWalls; ++w) { size_t o = 3 * ((size_t)i * m.nWalls + w); sTw = sTw + D3{Tw[o], Tw[o + 1], Tw[o + 2]}; }
+    D3 T = ld3(in.T, i) + sTc + sTw;
+    D3 om = ld3(in.om, i);
+    om = om + dt * T / (mass * sc->I);
+    st3(in.om, i, om);
+    D3 th = ld3(in.th, i) + om * dt;
+    if (th.z < 0) th.z += IBM_TWOPI;
+    if (th.z >= IBM_TWOPI) th.z -= IBM_TWOPI;
+    st3(in.th, i, th);
+  }
+  // collisionForces_ = Zero; ... (particleIBM.C:446-449)
+  cCntA[i] = 0;
+  cCntB[i] = 0;
+  for (int w = 0; w < m.nWalls; ++w)
+    for (int q = 0; q < 3; ++q) {
+      size_t o = 3 * ((size_t)i * m.nWalls + w) + q;
+      m.Fw[o] = 0.0; m.Tw[o] = 0.0; m.Fw2[o] = 0.0; m.Tw2[o] = 0.0;
+    }
+}
+
+// particleCloud::setPositions, serial branch (particleCloud.C:411-443): processed in cloud order, every inactive
+// instance pushes its theta/v/omega to the other copies of its index.
+__global__ void k5_set_positions(MotionDev m, InstanceSoA in) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m.nParticles) return;
+  int head = m.idxHead[idx];
+  if (head < 0 || m.instNext[head] < 0) return;  // single instance: nothing to copy
+  for (int p = head; p >= 0; p = m.instNext[p]) {
+    if (in.active[p]) continue;
+    D3 th = ld3(in.th, p), v = ld3(in.v, p), om = ld3(in.om, p);
+    int cp = in.copy[p];
+    for (int p2 = head; p2 >= 0; p2 = m.instNext[p2])
+      if (in.copy[p2] != cp) { st3(in.th, p2, th); st3(in.v, p2, v); st3(in.om, p2, om); }
+  }
+}
+
+// particleCloud::combineForces, serial branch (particleCloud.C:268-312)
+__global__ void k_combine_forces(MotionDev m, InstanceSoA in) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m.nParticles) return;
+  int head = m.idxHead[idx];
+  if (head < 0) return;
+  D3 totF{0, 0, 0}, totT{0, 0, 0};
+  for (int p = head; p >= 0; p = m.instNext[p]) { totF = totF + ld3(in.F, p); totT = totT + ld3(in.T, p); }
+  for (int p = head; p >= 0; p = m.instNext[p]) { st3(in.F, p, totF); st3(in.T, p, totT); }
+}
+
+// same-index lists from a stable sort of (index, position)
+__global__ void k_group_keys(InstanceSoA in, int n, int cap, int* keys, int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  keys[i] = i < n ? in.index[i] : 0x7fffffff;
+  vals[i] = i;
+}
+__global__ void k_group_link(const int* __restrict__ keys, const int* __restrict__ vals, int n, MotionDev m) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int k = keys[q], pos = vals[q];
+  bool first = (q == 0) || keys[q - 1] != k;
+  bool last = (q == n - 1) || keys[q + 1] != k;
+  if (first) m.idxHead[k] = pos;
+  if (last) m.idxTail[k] = pos;
+  m.instNext[pos] = last ? -1 : vals[q + 1];
+}
+
+// end-of-solve log block (particleCloud.C:1296-1308): fixed-shape tree => deterministic
+__global__ void k_stats(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int n, double* out) {
+  __shared__ double red[32][10];
+  double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double act = in.active[i] ? 1.0 : 0.0;
+    D3 v = ld3(in.v, i), om = ld3(in.om, i);
+    double mass = classes[in.cls[i]].V * in.rho[i];
+    acc[0] += om.x * act; acc[1] += om.y * act; acc[2] += om.z * act;
+    acc[3] += v.x * act; acc[4] += v.y * act; acc[5] += v.z * act;
+    acc[6] += v.x * mass * act; acc[7] += v.y * mass * act; acc[8] += v.z * mass * act;
+    acc[9] += 0.5 * mass * dot3(v, v) * act;
+  }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < 10; ++q) {
+    double v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double v = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static bool dalloc(ibm_ctx* c, Motion* M, T** p, size_t n) {
+  if (!ctx_cuda_ok(c, cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(T)), "cudaMalloc(motion)")) return false;
+  cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+  M->allocs.push_back(*p);
+  return true;
+}
+
+static int motion_init(ibm_ctx* c) {
+  if (c->motion) return IBM_OK;
+  if (c->cap == 0) return ctx_fail(c, IBM_E_STATE, "loop 5: particles not set");
+  Motion* M = new Motion;
+  c->motion = M;
+  MotionDev& d = M->d;
+  d.cap = c->cap; d.nParticles = c->nParticles;
+  d.nWalls = (int)c->walls.size(); d.nCyc = (int)c->cyclics.size();
+  d.gx = c->cfg.g[0]; d.gy = c->cfg.g[1]; d.gz = c->cfg.g[2]; d.e = c->cfg.e;
+  d.moving = c->cfg.moving; d.rotating = c->cfg.rotating;
+  // cell list geometry: bin edge = largest cmptMax(D) over the shape classes
+  double dmax = 0;
+  for (auto& h : c->classes) dmax = std::max(dmax, h.dev.kind == 2 ? std::max(h.dev.a, std::max(h.dev.b, h.dev.l)) : h.dev.d);
+  if (!(dmax > 0)) dmax = 1.0;
+  const LatticeDev& L = c->L;
+  d.binEdge = dmax;
+  d.bx0 = L.ox - dmax; d.by0 = L.oy - dmax; d.bz0 = L.oz - dmax;
+  auto nb = [&](double len) { return std::max(1, (int)std::ceil((len + 2 * dmax) / dmax)); };
+  d.nbx = nb(L.nx * L.dx); d.nby = nb(L.ny * L.dy); d.nbz = c->nGeometricD == 2 ? 1 : nb(L.nz * L.dz);
+  if (c->nGeometricD == 2) d.bz0 = L.oz - 1e300;
+  while ((double)d.nbx * d.nby * d.nbz > 4.0e9) { d.binEdge *= 2; d.nbx = (d.nbx + 1) / 2; d.nby = (d.nby + 1) / 2; d.nbz = (d.nbz + 1) / 2; }
+  const size_t cap = (size_t)c->cap;
+  bool ok = dalloc(c, M, &d.nInst, 1) && dalloc(c, M, &d.keys, cap) && dalloc(c, M, &d.keysSorted, cap) && dalloc(c, M, &d.vals, cap) &&
+            dalloc(c, M, &d.valsSorted, cap) && dalloc(c, M, &d.cCnt, cap) && dalloc(c, M, &d.cIdx, cap * CONTACT_CAP) &&
+            dalloc(c, M, &d.cF, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cT, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cCnt2, cap) &&
+            dalloc(c, M, &d.cIdx2, cap * CONTACT_CAP) && dalloc(c, M, &d.cF2, 3 * cap * CONTACT_CAP) &&
+            dalloc(c, M, &d.cT2, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.overflow, 1) && dalloc(c, M, &d.Fw, 3 * cap * std::max(1, d.nWalls)) &&
+            dalloc(c, M, &d.Tw, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.Fw2, 3 * cap * std::max(1, d.nWalls)) &&
+            dalloc(c, M, &d.Tw2, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.idxHead, (size_t)std::max(1, c->nParticles)) &&
+            dalloc(c, M, &d.idxTail, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.instNext, cap) &&
+            dalloc(c, M, &d.maxCopies, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.hitFlag, cap * std::max(1, d.nCyc)) &&
+            dalloc(c, M, &d.hitOff, cap * std::max(1, d.nCyc)) && dalloc(c, M, &d.hitFace, cap * std::max(1, d.nCyc)) &&
+            dalloc(c, M, &d.hitCenter, 3 * cap * std::max(1, d.nCyc)) && dalloc(c, M, &d.hitTotal, 1) &&
+            dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16);
+  if (!ok) return IBM_E_CUDA;
+  // originals
+  int* oc = nullptr; double* orho = nullptr; int* wp = nullptr; int* cp = nullptr;
+  ok = dalloc(c, M, &oc, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &orho, (size_t)std::max(1, c->nParticles)) &&
+       dalloc(c, M, &wp, (size_t)std::max(1, d.nWalls)) && dalloc(c, M, &cp, (size_t)std::max(1, d.nCyc));
+  if (!ok) return IBM_E_CUDA;
+  std::vector<double> rho(c->nParticles);
+  for (int i = 0; i < c->nParticles; ++i) rho[i] = c->orig[i].rho;
+  if (c->nParticles) {
+    cudaMemcpy(oc, c->origCls.data(), c->nParticles * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(orho, rho.data(), c->nParticles * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(d.maxCopies, c->maxCopies.data(), c->nParticles * sizeof(int), cudaMemcpyHostToDevice);
+  }
+  if (d.nWalls) cudaMemcpy(wp, c->walls.data(), d.nWalls * sizeof(int), cudaMemcpyHostToDevice);
+  if (d.nCyc) cudaMemcpy(cp, c->cyclics.data(), d.nCyc * sizeof(int), cudaMemcpyHostToDevice);
+  d.origCls = oc; d.origRho = orho; d.wallPatch = wp; d.cycPatch = cp;
+  // patches
+  std::vector<PatchDev> pd;
+  for (auto& ph : c->patches) {
+    PatchDev q{};
+    q.type = ph.type; q.side = ph.side; q.neighb = ph.neighb; q.nFaces = ph.nFaces();
+    q.Cf = ph.dCf; q.Sf = ph.dSf; q.magSf = ph.dMagSf;
+    const int axis = ph.side / 2;
+    q.nA = (axis == 0) ? L.ny : L.nx;
+    q.nB = (axis == 2) ? L.ny : L.nz;
+    // lattice-ordered iff the face centres match the mini-mesh order (then candidate faces come from an index box)
+    q.latticeOrdered = 0;
+    if (q.nFaces == q.nA * q.nB) {
+      const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz};
+      const int ta = (axis == 0) ? 1 : 0, tb = (axis == 2) ? 1 : 2;
+      bool match = true;
+      for (int b = 0; b < q.nB && match; ++b)
+        for (int a = 0; a < q.nA && match; ++a) {
+          const double* f = &ph.Cf[3 * ((size_t)a + (size_t)q.nA * b)];
+          double ea = o3[ta] + (a + 0.5) * d3[ta], eb = o3[tb] + (b + 0.5) * d3[tb];
+          if (std::fabs(f[ta] - ea) > 1e-9 * d3[ta] || std::fabs(f[tb] - eb) > 1e-9 * d3[tb]) match = false;
+        }
+      q.latticeOrdered = match ? 1 : 0;
+    }
+    pd.push_back(q);
+  }
+  if (!pd.empty()) {
+    if (!dalloc(c, M, &M->dPatches, pd.size())) return IBM_E_CUDA;
+    cudaMemcpy(M->dPatches, pd.data(), pd.size() * sizeof(PatchDev), cudaMemcpyHostToDevice);
+  }
+  d.patches = M->dPatches;
+  // cub temp storage
+  size_t b1 = 0, b2 = 0, b3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, d.keys, d.keysSorted, d.vals, d.valsSorted, c->cap);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, M->dIdxKeys, M->dIdxKeys2, d.vals, d.valsSorted, c->cap);
+  cub::DeviceScan::ExclusiveSum(nullptr, b3, d.hitFlag, d.hitOff, (int)(cap * std::max(1, d.nCyc)));
+  M->cubTempBytes = std::max(b1, std::max(b2, b3)) + 256;
+  if (!ctx_cuda_ok(c, cudaMalloc(&M->cubTemp, M->cubTempBytes), "cudaMalloc(cub)")) return IBM_E_CUDA;
+  return IBM_OK;
+}
+
+static int blocks_for(int n, int b = 128) { return std::max(1, (n + b - 1) / b); }
+
+// (re)build the same-index lists after the instance array changed on the host side (set_particles, compaction)
+static int rebuild_groups(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  IBM_CUDA(c, cudaMemsetAsync(d.idxHead, 0xff, (size_t)std::max(1, c->nParticles) * sizeof(int), st));
+  IBM_CUDA(c, cudaMemsetAsync(d.idxTail, 0xff, (size_t)std::max(1, c->nParticles) * sizeof(int), st));
+  k_set_int<<<1, 1, 0, st>>>(d.nInst, c->nInst);
+  if (c->nInst > 0) {
+    k_group_keys<<<blocks_for(c->cap), 128, 0, st>>>(c->in, c->nInst, c->cap, M->dIdxKeys, d.vals);
+    size_t tb = M->cubTempBytes;
+    cub::DeviceRadixSort::SortPairs(M->cubTemp, tb, M->dIdxKeys, M->dIdxKeys2, d.vals, d.valsSorted, c->cap, 0, 32, st);
+    k_group_link<<<blocks_for(c->nInst), 128, 0, st>>>(M->dIdxKeys2, d.valsSorted, c->nInst, d);
+    c->nLaunch += 4;
+  }
+  M->groupsValid = true;
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+
+static int ensure_motion(ibm_ctx* c) {
+  int rc = motion_init(c);
+  if (rc) return rc;
+  Motion* M = (Motion*)c->motion;
+  if (!M->groupsValid) return rebuild_groups(c);
+  return IBM_OK;
+}
+
+void motion_invalidate_groups(ibm_ctx* c) {
+  if (c->motion) ((Motion*)c->motion)->groupsValid = false;
+}
+
+int combine_forces(ibm_ctx* c) {
+  int rc = ensure_motion(c);
+  if (rc) return rc;
+  Motion* M = (Motion*)c->motion;
+  if (c->nParticles > 0) {
+    k_combine_forces<<<blocks_for(c->nParticles), 128, 0, c->stream>>>(M->d, c->in);
+    c->nLaunch++;
+  }
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+
+static int substep_launch(ibm_ctx* c, double localDt) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  const int cap = c->cap;
+  const bool copiesPossible = d.nCyc > 0;
+  const int* cCnt = d.cCnt; const int* cIdx = d.cIdx; const double* cF = d.cF; const double* cT = d.cT;
+  double* Fw = d.Fw; double* Tw = d.Tw;
+  if (c->cfg.moving) {
+    // computeCollisions
+    k5_sort_keys<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
+    size_t tb = M->cubTempBytes;
+    cub::DeviceRadixSort::SortPairs(M->cubTemp, tb, d.keys, d.keysSorted, d.vals, d.valsSorted, cap, 0, 32, st);
+    k5_contacts<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
+    c->nLaunch += 3;
+    // computeWallHits
+    if (d.nWalls > 0) { k5_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->L, c->in, c->dClasses, localDt); c->nLaunch++; }
+    if (copiesPossible) {
+      k5_merge<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in);
+      c->nLaunch++;
+      cCnt = d.cCnt2; cIdx = d.cIdx2; cF = d.cF2; cT = d.cT2; Fw = d.Fw2; Tw = d.Tw2;
+      // computeCyclicHits (App. B #10: as coded it returns when the mesh has no wall patch)
+      if (d.nWalls > 0 || c->cfg.cyclicWithoutWalls) {
+        dim3 g(blocks_for(cap), d.nCyc);
+        k5_cyclic_detect<<<g, 128, 0, st>>>(d, c->L, c->in, c->dClasses);
+        size_t tb2 = M->cubTempBytes;
+        cub::DeviceScan::ExclusiveSum(M->cubTemp, tb2, d.hitFlag, d.hitOff, cap * d.nCyc, st);
+        // total = last offset + last flag
+        k5_append_total<<<1, 1, 0, st>>>(d);
+        k5_append<<<blocks_for(cap * d.nCyc, 256), 256, 0, st>>>(d, c->in);
+        k5_append_link<<<1, 32, 0, st>>>(d, c->in);
+        c->nLaunch += 5;
+      }
+    }
+  }
+  k5_solve<<<blocks_for(cap), 128, 0, st>>>(d, c->L, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
+  c->nLaunch++;
+  if (copiesPossible && c->nParticles > 0) { k5_set_positions<<<blocks_for(c->nParticles), 128, 0, st>>>(d, c->in); c->nLaunch++; }
+  return IBM_OK;
+}
+
+static int finish_substeps(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  // instance count and overflow flags back to the host
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 8, M->d.nInst, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 9, M->d.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  IBM_CUDA(c, cudaGetLastError());
+  if (c->hScal[9] == 1) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: more than CONTACT_CAP simultaneous contacts on one particle");
+  if (c->hScal[9] == 2) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: instance capacity exhausted (raise ibm_cloud_cfg.maxInstances)");
+  c->nInst = c->hScal[8];
+  return IBM_OK;
+}
+
+int motion_substep(ibm_ctx* c, double localDt) {
+  int rc = ensure_motion(c);
+  if (rc) return rc;
+  ctx_tic(c, T_ADVANCE);
+  substep_launch(c, localDt);
+  ctx_toc(c);
+  return finish_substeps(c);
+}
+
+int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
+  int rc = ensure_motion(c);
+  if (rc) return rc;
+  Motion* M = (Motion*)c->motion;
+  ctx_tic(c, T_ADVANCE);
+  // literal loop of particleCloud.C:1247-1275 (App. B #22)
+  int nSub = 0;
+  double localDt = dt / 100.0, localTime = localDt;
+  while (localTime < dt) {
+    substep_launch(c, localDt);
+    ++nSub;
+    if (localTime + localDt > dt) localDt = dt - localTime;
+    else localTime += localDt;
+  }
+  ctx_toc(c);
+  if ((rc = finish_substeps(c))) return rc;
+  // update() for every instance, deleteInActiveParticles, (indicator), then the log block
+  if ((rc = ctx_update(c))) return rc;  // invalidates the same-index lists when instances were deleted
+  if ((rc = ensure_motion(c))) return rc;
+  if (stats) {
+    k_stats<<<1, 1024, 0, c->stream>>>(M->d, c->in, c->dClasses, c->nInst, M->dStats);
+    c->nLaunch++;
+    double h[10];
+    IBM_CUDA(c, cudaMemcpyAsync(h, M->dStats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double np = c->nParticles > 0 ? (double)c->nParticles : 1.0;
+    stats->nSubSteps = nSub;
+    stats->nInstances = c->nInst;
+    for (int q = 0; q < 3; ++q) { stats->avgOmega[q] = h[q] / np; stats->avgV[q] = h[3 + q] / np; stats->avgP[q] = h[6 + q] / np; }
+    stats->totK = h[9];
+  }
+  return IBM_OK;
+}
+
+void motion_destroy(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  if (!M) return;
+  for (void* p : M->allocs) cudaFree(p);
+  if (M->cubTemp) cudaFree(M->cubTemp);
+  delete M;
+  c->motion = nullptr;
+}
+
 }  // namespace ibm

@@ -1,0 +1,120 @@
+"""Loop 5 parity (GPU): collisions, wall hits, periodic copies, sub-stepped integration, force combination.
+
+Spheres and cylinders use only IEEE +,-,*,/,sqrt on this path, so with identical hydrodynamic F/T handed to both
+sides the trajectories must be BIT-IDENTICAL to the oracle over N fluid steps (N x ~100 sub-steps).  Ellipses go
+through atan2/tan/cos (device libm vs glibc): tolerance 1e-9 relative over the horizon (stated tolerance)."""
+import numpy as np
+import pytest
+
+from ibmfoam_b200 import cases
+from ibmfoam_b200.cloud import ParticleCloud
+from oracle.pyoracle import OracleCloud
+import ibm_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+KEYS_I = ("index", "copy", "active", "onMesh", "nShell")
+KEYS_D = ("center", "theta", "v", "omega", "F", "T")
+
+
+def _compare(oc, gc, exact=True, tol=1e-9):
+    so, sg = oc.state_arrays(), gc.state_arrays()
+    assert gc.nParticles() == oc.n_instances
+    for k in KEYS_I:
+        assert np.array_equal(so[k], sg[k]), k
+    for k in KEYS_D:
+        if exact:
+            assert np.array_equal(so[k], sg[k]), (k, np.max(np.abs(so[k] - sg[k])))
+        else:
+            scale = max(np.max(np.abs(so[k])), 1e-300)
+            assert np.max(np.abs(so[k] - sg[k])) / scale < tol, k
+
+
+def _run(case, n_steps, exact=True, seed=0, ft_scale=1e-6):
+    oc, gc = OracleCloud(case), ParticleCloud(case)
+    rng = np.random.default_rng(seed)
+    stats = None
+    for _ in range(n_steps):
+        FT = rng.normal(0, ft_scale, (oc.n_instances, 6))
+        if case.mesh.nz == 1:
+            FT[:, 2] = 0
+            FT[:, 3:5] = 0
+        oc.set_force_torque(FT); gc.set_force_torque(FT)
+        oc.combine_forces(); gc.combineForces()
+        so = oc.advance(case.dt)
+        st = gc.advance(case.dt)
+        assert st.nSubSteps == int(so[0]) and st.nInstances == int(so[1])
+        _compare(oc, gc, exact)
+        stats = (so, st)
+    so, st = stats
+    ref = np.concatenate([so[2:5], so[5:8], so[8:11], [so[11]]])
+    got = np.concatenate([list(st.avgV), list(st.avgOmega), list(st.avgP), [st.totK]])
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-300)
+    return oc, gc
+
+
+def test_two_spheres_head_on_closed_form():
+    """e = 1, equal spheres exchange their normal velocities in one sub-step; momentum conserved."""
+    case = cases.two_spheres(n=40, e=1.0, speed=1.0, gap=0.02)
+    gc = ParticleCloud(case)
+    m, _ = gc.mass_inertia(0)
+    v0 = gc.state_arrays()["v"].copy()
+    local_dt = 0.02
+    for _ in range(3):
+        gc.substep(local_dt)
+    v1 = gc.state_arrays()["v"]
+    assert np.allclose(v1[0], v0[1], rtol=1e-14, atol=1e-15) and np.allclose(v1[1], v0[0], rtol=1e-14, atol=1e-15)
+    assert np.allclose(m * v1.sum(axis=0), m * v0.sum(axis=0), atol=1e-13)
+    gc.close()
+
+
+@pytest.mark.parametrize("e", [1.0, 0.8])
+def test_two_spheres_vs_oracle(e):
+    _run(cases.two_spheres(n=40, e=e, speed=0.7, gap=0.3), n_steps=3, exact=True, ft_scale=1e-3)
+
+
+def test_colliding_cylinders_walls_cyclic_copies():
+    """validation/collidingParticles verbatim (45 cylinders, x walls, y cyclic, g): walls, periodic copies,
+    copy merge and setPositions are all exercised; bit-identical over 4 fluid steps (404 sub-steps)."""
+    case = cases.colliding_particles()
+    rng = np.random.default_rng(2)
+    case.particles.v[:, :2] = rng.normal(0, 0.8, (45, 2))
+    case.particles.omega[:, 2] = rng.normal(0, 30.0, 45)
+    case.dt = 2.5e-4
+    oc, gc = _run(case, n_steps=4, exact=True, ft_scale=1e-7)
+    assert oc.n_instances > 45, "test should create periodic copies"
+
+
+def test_assembly_periodic_copies_and_deletion():
+    case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    case.particles.v *= 25.0
+    case.dt = 0.5
+    oc, gc = _run(case, n_steps=4, exact=True, ft_scale=1e-3)
+    assert oc.n_instances != 60
+
+
+def test_as_coded_no_copies_without_walls():
+    """App. B #10 as coded: computeCyclicHits returns when the mesh has no wall patch."""
+    case = cases.assembly(n=48, n_particles=40, seed=4, moving=True, cyclic_without_walls=False)
+    case.particles.v *= 25.0
+    oc, gc = _run(case, n_steps=2, exact=True)
+    assert np.all(gc.state_arrays()["copy"] == 0)
+
+
+def test_ellipses_tolerance():
+    case = util.ellipse_case()
+    case.particles.v[:] = [[0.6, 0.1, 0], [-0.6, 0.1, 0]]
+    _run(case, n_steps=3, exact=False)
+
+
+def test_combine_forces_sums_copies():
+    case = cases.colliding_particles(n_particles=6)
+    case.particles.position[0] = [0.0, 0.0193, 0.0]
+    case.particles.v[0] = [0.0, 2.0, 0.0]
+    oc, gc = OracleCloud(case), ParticleCloud(case)
+    oc.advance(1e-4); gc.advance(1e-4)
+    assert gc.nParticles() == oc.n_instances and gc.nParticles() > 6
+    FT = np.arange(6 * gc.nParticles(), dtype=float).reshape(-1, 6)
+    oc.set_force_torque(FT); gc.set_force_torque(FT)
+    oc.combine_forces(); gc.combineForces()
+    _compare(oc, gc, exact=True)
