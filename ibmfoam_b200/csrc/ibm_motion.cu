@@ -2,7 +2,7 @@
 // (translation unit compiled with -fmad=false: every operation below is a plain IEEE +,-,*,/,sqrt in the
 //  reference's evaluation order, so sphere / cylinder trajectories are bit-identical to an x86-64 build.)
 //
-//   particleCloud::computeCollisions  particleCloud.C:482-581   -> k5_sort_keys + radix sort + k5_contacts + k5_merge
+//   particleCloud::computeCollisions  particleCloud.C:482-581   -> k5_bin + k5_contacts + k5_merge
 //   particleIBM::collision            particleIBM.C:41-205      -> pair_collision()
 //   particleCloud::computeWallHits    particleCloud.C:584-656   -> k5_walls (+ k5_merge)
 //   particleCloud::computeCyclicHits  particleCloud.C:659-937   -> k5_cyclic_detect + scan + k5_append
@@ -12,7 +12,7 @@
 //   particleCloud::solve (loop+log)   particleCloud.C:1247-1324 -> motion_advance
 //
 // The reference keeps dense nParticles x nParticles force tables and visits all ordered pairs; here a uniform
-// cell list (bin edge >= largest diameter, realised as a sorted key array + binary search) yields the same
+// cell list (bin edge >= largest diameter, fixed-capacity bins refilled every sub-step) yields the same
 // contact set, stored sparsely per instance and summed in partner-index order (the reference's sum() order).
 #include <cub/cub.cuh>
 
@@ -30,6 +30,7 @@ struct PatchDev {
   const double *Cf, *Sf, *magSf;
   int latticeOrdered;  // faces in transverse lattice order (fastest index first): candidate faces by index box
   int nA, nB;          // transverse extents
+  double lo[3], hi[3]; // bounding box of the face centres (cheap rejection: |centre - Cf| >= distance to the box)
 };
 
 struct MotionDev {
@@ -38,7 +39,8 @@ struct MotionDev {
   // cell list
   double bx0, by0, bz0, binEdge;
   int nbx, nby, nbz;
-  unsigned* keys; unsigned* keysSorted; int* vals; int* valsSorted;
+  int binCap; int* binCnt; int* binItems;   // fixed-capacity cell list, rebuilt every sub-step
+  unsigned* keys; unsigned* keysSorted; int* vals; int* valsSorted;  // scratch for the same-index list build
   // sparse contact tables (sorted by partner index)
   int* cCnt; int* cIdx; double* cF; double* cT;
   int* cCnt2; int* cIdx2; double* cF2; double* cT2;
@@ -50,7 +52,8 @@ struct MotionDev {
   // originals (origParticles_) and copy counters
   const int* origCls; const double* origRho; int* maxCopies;
   // cyclic hits
-  int* hitFlag; int* hitOff; int* hitFace; double* hitCenter; int* hitTotal;
+  int* candCount; int* candKey; int candCap;      // (patch, instance) pairs within reach of a cyclic patch
+  int* hitCount; int* hitKey; double* hitCenter;  // compact list of new periodic copies (key = patchSlot*cap + instance)
   const PatchDev* patches; const int* wallPatch; const int* cycPatch;
   double gx, gy, gz, e;
   int moving, rotating;
@@ -195,23 +198,15 @@ __device__ __forceinline__ void bin_of(const MotionDev& m, D3 c, int& bx, int& b
   bz = min(max((int)floor((c.z - m.bz0) / m.binEdge), 0), m.nbz - 1);
 }
 
-__global__ void k5_sort_keys(MotionDev m, InstanceSoA in) {
+__global__ void k5_bin(MotionDev m, InstanceSoA in) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m.cap) return;
-  unsigned key = 0xffffffffu;
-  if (i < *m.nInst) {
-    int bx, by, bz;
-    bin_of(m, ld3(in.c, i), bx, by, bz);
-    key = (unsigned)(bx + m.nbx * (by + m.nby * bz));
-  }
-  m.keys[i] = key;
-  m.vals[i] = i;
-}
-
-__device__ __forceinline__ int lower_bound_u(const unsigned* a, int n, unsigned key) {
-  int lo = 0, hi = n;
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
-  return lo;
+  if (i >= *m.nInst || in.onMesh[i] == 0) return;
+  int bx, by, bz;
+  bin_of(m, ld3(in.c, i), bx, by, bz);
+  int b = bx + m.nbx * (by + m.nby * bz);
+  int slot = atomicAdd(&m.binCnt[b], 1);
+  if (slot < m.binCap) m.binItems[(size_t)b * m.binCap + slot] = i;
+  else atomicExch(m.overflow, 3);
 }
 
 // particleCloud::computeCollisions, pair part (particleCloud.C:484-523).  Thread i builds its own sparse row
@@ -220,8 +215,7 @@ __device__ __forceinline__ int lower_bound_u(const unsigned* a, int n, unsigned 
 // the reference's loop order wins == the partner with the largest cloud position.
 __global__ void k5_contacts(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = *m.nInst;
-  if (i >= n) return;
+  if (i >= *m.nInst) return;
   int cnt = 0;
   int eIdx[CONTACT_CAP], ePos[CONTACT_CAP];
   D3 eF[CONTACT_CAP], eT[CONTACT_CAP];
@@ -239,12 +233,18 @@ __global__ void k5_contacts(MotionDev m, InstanceSoA in, const ShapeClassDev* __
       for (int dy = -1; dy <= 1; ++dy) {
         int y = by + dy;
         if (y < 0 || y >= m.nby) continue;
-        int x0 = max(bx - 1, 0), x1 = min(bx + 1, m.nbx - 1);
-        unsigned k0 = (unsigned)(x0 + m.nbx * (y + m.nby * z)), k1 = (unsigned)(x1 + m.nbx * (y + m.nby * z));
-        int s = lower_bound_u(m.keysSorted, n, k0), e = lower_bound_u(m.keysSorted, n, k1 + 1u);
-        for (int q = s; q < e; ++q) {
-          int j = m.valsSorted[q];
+        for (int x = max(bx - 1, 0); x <= min(bx + 1, m.nbx - 1); ++x) {
+        const int bin = x + m.nbx * (y + m.nby * z);
+        const int nb = min(m.binCnt[bin], m.binCap);
+        for (int q = 0; q < nb; ++q) {
+          int j = m.binItems[(size_t)bin * m.binCap + q];
           if (j == i) continue;
+          {
+            // cheap rejection on the centres alone: the reference's early-out (particleIBM.C:56-59) fails for every
+            // pair farther apart than the largest diameter (== bin edge), evaluated with a safety factor
+            double ddx = in.c[0][j] - me.c.x, ddy = in.c[1][j] - me.c.y, ddz = in.c[2][j] - me.c.z;
+            if (ddx * ddx + ddy * ddy + ddz * ddz > m.binEdge * m.binEdge * (1.0 + 1e-9)) continue;
+          }
           const int idxJ = in.index[j];
           if (idxJ == idxI || in.onMesh[j] == 0) continue;
           const ShapeClassDev* scj = classes + in.cls[j];
@@ -274,6 +274,7 @@ __global__ void k5_contacts(MotionDev m, InstanceSoA in, const ShapeClassDev* __
             eIdx[slot] = idxJ; ePos[slot] = -1;
           }
           if (j > ePos[slot]) { ePos[slot] = j; eF[slot] = myF; eT[slot] = myT; }
+        }
         }
       }
     }
@@ -306,6 +307,12 @@ __device__ __forceinline__ void face_range(const MotionDev& m, const LatticeDev&
   b0 = max(0, (int)floor((c3[tb] - r - o3[tb]) / d3[tb]) - 1); b1 = min(p.nB - 1, (int)floor((c3[tb] + r - o3[tb]) / d3[tb]) + 1);
 }
 
+__device__ __forceinline__ bool patch_in_reach(const PatchDev& p, D3 c, double r) {
+  double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
+         dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
+  return dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300;
+}
+
 __global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *m.nInst) return;
@@ -316,6 +323,7 @@ __global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeC
   const double mass = sc->V * in.rho[i];
   for (int w = 0; w < m.nWalls; ++w) {
     const PatchDev& p = m.patches[m.wallPatch[w]];
+    if (!patch_in_reach(p, c, sc->Rbound)) continue;
     int a0, a1, b0, b1;
     face_range(m, L, p, c, sc->Rbound, a0, a1, b0, b1);
     bool done = false;
@@ -323,10 +331,11 @@ __global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeC
       for (int a = a0; a <= a1 && !done; ++a) {
         int facei = p.latticeOrdered ? a + p.nA * b : a;
         D3 fc{p.Cf[3 * facei], p.Cf[3 * facei + 1], p.Cf[3 * facei + 2]};
+        D3 R = c - fc;
+        if (magSqr3(R) > sc->Rbound * sc->Rbound * (1.0 + 1e-9)) continue;  // cannot pass mag(R) <= r(faceCentre)
         D3 sf{p.Sf[3 * facei], p.Sf[3 * facei + 1], p.Sf[3 * facei + 2]};
         D3 norm = sf / p.magSf[facei];
         D3 rv = cross3(-(fc - c), om) + v;  // v(faceCentre)
-        D3 R = c - fc;
         if (mag3(R) <= shape_r_at(*sc, c, thz, fc) && dot3(rv, norm) > 0) {
           D3 vNorm = norm * dot3(norm, rv);
           D3 rHat = R / mag3(R);
@@ -350,6 +359,7 @@ __global__ void k5_merge(MotionDev m, InstanceSoA in) {
   if (i >= *m.nInst) return;
   const int idx = in.index[i];
   const int head = m.idxHead[idx];
+  if (head < 0 || m.instNext[head] < 0) return;  // single instance of this index: k5_solve reads the raw tables
   int cnt = 0;
   int eIdx[CONTACT_CAP];
   D3 eF[CONTACT_CAP], eT[CONTACT_CAP];
@@ -403,57 +413,90 @@ __global__ void k5_merge(MotionDev m, InstanceSoA in) {
 }
 
 // particleIBM::patchHit + found() for every (cyclic patch, instance)   particleIBM.C:490-517, particleCloud.C:447-479, 685-730
-__global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+// stage 1: (patch, instance) pairs whose centre is within reach of the patch
+__global__ void k5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int slot = blockIdx.y;
-  const int n = *m.nInst;
-  if (i >= m.cap) return;
-  size_t h = (size_t)slot * m.cap + i;
-  m.hitFlag[h] = 0;
-  if (i >= n || in.onMesh[i] == 0) return;
-  const PatchDev& p = m.patches[m.cycPatch[slot]];
-  if (p.type != IBM_CYCLIC) return;  // processor patches are handled by the slab exchange, not here
-  const ShapeClassDev* sc = classes + in.cls[i];
-  const D3 c = ld3(in.c, i), v = ld3(in.v, i);
-  const double thz = in.th[2][i];
-  int a0, a1, b0, b1;
-  face_range(m, L, p, c, sc->Rbound, a0, a1, b0, b1);
-  for (int b = b0; b <= b1; ++b)
-    for (int a = a0; a <= a1; ++a) {
+  if (i >= *m.nInst || in.onMesh[i] == 0) return;
+  const D3 c = ld3(in.c, i);
+  const double r = classes[in.cls[i]].Rbound;
+  for (int slot = 0; slot < m.nCyc; ++slot) {
+    const PatchDev& p = m.patches[m.cycPatch[slot]];
+    if (p.type != IBM_CYCLIC) continue;  // processor patches are handled by the slab exchange, not here
+    if (!patch_in_reach(p, c, r)) continue;
+    int h = atomicAdd(m.candCount, 1);
+    if (h < m.candCap) m.candKey[h] = slot * m.cap + i;
+    else atomicExch(m.overflow, 4);
+  }
+}
+
+// stage 2: one warp per candidate; lanes scan the candidate faces in patch order, the first qualifying face
+// (lowest position in that order) is the reference's patchHit() result.
+__global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  const int lane = threadIdx.x & 31;
+  const int nCand = min(*m.candCount, m.candCap);
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nCand; w += (gridDim.x * blockDim.x) >> 5) {
+    const int key = m.candKey[w];
+    const int slot = key / m.cap, i = key % m.cap;
+    const PatchDev& p = m.patches[m.cycPatch[slot]];
+    const ShapeClassDev* sc = classes + in.cls[i];
+    const D3 c = ld3(in.c, i), v = ld3(in.v, i);
+    const double thz = in.th[2][i];
+    int a0, a1, b0, b1;
+    face_range(m, L, p, c, sc->Rbound, a0, a1, b0, b1);
+    const int na = a1 - a0 + 1, nf = na * (b1 - b0 + 1);
+    int firstPos = 0x7fffffff;
+    for (int base = 0; base < nf && firstPos == 0x7fffffff; base += 32) {
+      int pos = base + lane;
+      bool ok = false;
+      if (pos < nf) {
+        int a = a0 + pos % na, b = b0 + pos / na;
+        int facei = p.latticeOrdered ? a + p.nA * b : a;
+        D3 fc{p.Cf[3 * facei], p.Cf[3 * facei + 1], p.Cf[3 * facei + 2]};
+        D3 R = c - fc;
+        if (magSqr3(R) <= sc->Rbound * sc->Rbound * (1.0 + 1e-9)) {
+          D3 sf{p.Sf[3 * facei], p.Sf[3 * facei + 1], p.Sf[3 * facei + 2]};
+          D3 norm = sf / p.magSf[facei];
+          ok = mag3(R) <= shape_r_at(*sc, c, thz, fc) && dot3(v, norm) > 0;
+        }
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (bal) firstPos = base + __ffs(bal) - 1;
+    }
+    if (firstPos != 0x7fffffff && lane == 0) {
+      int a = a0 + firstPos % na, b = b0 + firstPos / na;
       int facei = p.latticeOrdered ? a + p.nA * b : a;
       D3 fc{p.Cf[3 * facei], p.Cf[3 * facei + 1], p.Cf[3 * facei + 2]};
-      D3 sf{p.Sf[3 * facei], p.Sf[3 * facei + 1], p.Sf[3 * facei + 2]};
-      D3 norm = sf / p.magSf[facei];
       D3 R = c - fc;
-      if (mag3(R) <= shape_r_at(*sc, c, thz, fc) && dot3(v, norm) > 0) {
-        const PatchDev& q = m.patches[p.neighb];
-        D3 nc = R + D3{q.Cf[3 * facei], q.Cf[3 * facei + 1], q.Cf[3 * facei + 2]};
-        bool f = false;
-        for (int mem = m.idxHead[in.index[i]]; mem >= 0; mem = m.instNext[mem])
-          if (mag3(nc - ld3(in.c, mem)) < 1e-4) f = true;  // App. B #15
-        if (!f) {
-          m.hitFlag[h] = 1;
-          m.hitFace[h] = facei;
-          m.hitCenter[3 * h] = nc.x; m.hitCenter[3 * h + 1] = nc.y; m.hitCenter[3 * h + 2] = nc.z;
+      const PatchDev& q = m.patches[p.neighb];
+      D3 nc = R + D3{q.Cf[3 * facei], q.Cf[3 * facei + 1], q.Cf[3 * facei + 2]};
+      bool f = false;
+      for (int mem = m.idxHead[in.index[i]]; mem >= 0; mem = m.instNext[mem])
+        if (mag3(nc - ld3(in.c, mem)) < 1e-4) f = true;  // App. B #15
+      if (!f) {
+        int h = atomicAdd(m.hitCount, 1);
+        if (h < m.cap) {
+          m.hitKey[h] = key;
+          m.hitCenter[3 * (size_t)h] = nc.x; m.hitCenter[3 * (size_t)h + 1] = nc.y; m.hitCenter[3 * (size_t)h + 2] = nc.z;
         }
-        return;
       }
     }
+  }
 }
 
 // append the new periodic copies in the reference's order (patch-major, cloud order within a patch):
-// particleIBM copy constructor (particleIBM.C:318-350) from origParticles_[index]   particleCloud.C:815-832
+// particleIBM copy constructor (particleIBM.C:318-350) from origParticles_[index]   particleCloud.C:815-832.
+// The hit list is unordered (atomics); each hit finds its rank by counting smaller keys.
 __global__ void k5_append(MotionDev m, InstanceSoA in) {
-  const int total = *m.hitTotal;
+  const int total = *m.hitCount;
   if (total == 0) return;
   const int n0 = *m.nInst;
-  const int nSlots = m.nCyc * m.cap;
-  const int room = m.cap - n0;
-  if (total > room) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(m.overflow, 2); return; }
-  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nSlots; h += gridDim.x * blockDim.x) {
-    if (!m.hitFlag[h]) continue;
-    int src = h % m.cap;
-    int dst = n0 + m.hitOff[h];
+  if (total > m.cap - n0) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(m.overflow, 2); return; }
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < total; h += gridDim.x * blockDim.x) {
+    const int key = m.hitKey[h];
+    int rank = 0;
+    for (int q = 0; q < total; ++q) rank += m.hitKey[q] < key;
+    int src = key % m.cap;
+    int dst = n0 + rank;
     int idx = in.index[src];
     in.index[dst] = idx;
     in.copy[dst] = -1;  // assigned sequentially below
@@ -482,16 +525,14 @@ __global__ void k5_append(MotionDev m, InstanceSoA in) {
   }
 }
 
-__global__ void k5_append_total(MotionDev m) {
-  const int last = m.nCyc * m.cap - 1;
-  *m.hitTotal = m.hitOff[last] + m.hitFlag[last];
-}
-
 // sequential part of the append: copy ids (maxCopies_[index]+1, ++) and the same-index lists, in append order
 __global__ void k5_append_link(MotionDev m, InstanceSoA in) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int total = *m.hitTotal;
-  if (total == 0 || total > m.cap - *m.nInst) return;
+  *m.candCount = 0;
+  const int total = *m.hitCount;
+  if (total == 0) return;
+  *m.hitCount = 0;
+  if (total > m.cap - *m.nInst) return;
   const int n0 = *m.nInst;
   for (int t = 0; t < total; ++t) {
     int dst = n0 + t;
@@ -514,6 +555,12 @@ __global__ void k5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeC
   if (in.onMesh[i] == 0) return;
   const ShapeClassDev* sc = classes + in.cls[i];
   const double mass = sc->V * in.rho[i];
+  {
+    // instances whose index has copies read the merged tables (k5_merge), all others the raw ones
+    const int head = m.idxHead[in.index[i]];
+    const bool multi = head >= 0 && m.instNext[head] >= 0;
+    if (!multi) { cCnt = m.cCnt; cF = m.cF; cT = m.cT; Fw = m.Fw; Tw = m.Tw; }
+  }
   const int cnt = cCnt[i];
   if (m.moving) {
     D3 sFc{0, 0, 0}, sFw{0, 0, 0};
@@ -658,7 +705,16 @@ static int motion_init(ibm_ctx* c) {
   d.nbx = nb(L.nx * L.dx); d.nby = nb(L.ny * L.dy); d.nbz = c->nGeometricD == 2 ? 1 : nb(L.nz * L.dz);
   if (c->nGeometricD == 2) d.bz0 = L.oz - 1e300;
   while ((double)d.nbx * d.nby * d.nbz > 4.0e9) { d.binEdge *= 2; d.nbx = (d.nbx + 1) / 2; d.nby = (d.nby + 1) / 2; d.nbz = (d.nbz + 1) / 2; }
+  {
+    // capacity per bin: bodies of the smallest class that fit (with slack for overlap) in a bin of the largest
+    double dmin = dmax;
+    for (auto& h : c->classes) dmin = std::min(dmin, h.dev.kind == 2 ? std::min(h.dev.a, h.dev.b) : h.dev.d);
+    double ratio = d.binEdge / std::max(dmin, 1e-300);
+    double est = (c->nGeometricD == 2 ? 4.0 * ratio * ratio : 8.0 * ratio * ratio * ratio) + 4.0;
+    d.binCap = (int)std::min(64.0, std::max(12.0, std::ceil(est)));
+  }
   const size_t cap = (size_t)c->cap;
+  d.candCap = (int)(3 * cap);
   bool ok = dalloc(c, M, &d.nInst, 1) && dalloc(c, M, &d.keys, cap) && dalloc(c, M, &d.keysSorted, cap) && dalloc(c, M, &d.vals, cap) &&
             dalloc(c, M, &d.valsSorted, cap) && dalloc(c, M, &d.cCnt, cap) && dalloc(c, M, &d.cIdx, cap * CONTACT_CAP) &&
             dalloc(c, M, &d.cF, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cT, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cCnt2, cap) &&
@@ -667,9 +723,10 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.Tw, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.Fw2, 3 * cap * std::max(1, d.nWalls)) &&
             dalloc(c, M, &d.Tw2, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.idxHead, (size_t)std::max(1, c->nParticles)) &&
             dalloc(c, M, &d.idxTail, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.instNext, cap) &&
-            dalloc(c, M, &d.maxCopies, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.hitFlag, cap * std::max(1, d.nCyc)) &&
-            dalloc(c, M, &d.hitOff, cap * std::max(1, d.nCyc)) && dalloc(c, M, &d.hitFace, cap * std::max(1, d.nCyc)) &&
-            dalloc(c, M, &d.hitCenter, 3 * cap * std::max(1, d.nCyc)) && dalloc(c, M, &d.hitTotal, 1) &&
+            dalloc(c, M, &d.maxCopies, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.hitCount, 1) && dalloc(c, M, &d.candCount, 1) &&
+            dalloc(c, M, &d.candKey, 3 * cap) &&
+            dalloc(c, M, &d.hitKey, cap) && dalloc(c, M, &d.hitCenter, 3 * cap) &&
+            dalloc(c, M, &d.binCnt, (size_t)d.nbx * d.nby * d.nbz) && dalloc(c, M, &d.binItems, (size_t)d.nbx * d.nby * d.nbz * d.binCap) &&
             dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16);
   if (!ok) return IBM_E_CUDA;
   // originals
@@ -697,6 +754,9 @@ static int motion_init(ibm_ctx* c) {
     q.nA = (axis == 0) ? L.ny : L.nx;
     q.nB = (axis == 2) ? L.ny : L.nz;
     // lattice-ordered iff the face centres match the mini-mesh order (then candidate faces come from an index box)
+    for (int a = 0; a < 3; ++a) { q.lo[a] = 1e300; q.hi[a] = -1e300; }
+    for (int f = 0; f < q.nFaces; ++f)
+      for (int a = 0; a < 3; ++a) { q.lo[a] = std::min(q.lo[a], ph.Cf[3 * (size_t)f + a]); q.hi[a] = std::max(q.hi[a], ph.Cf[3 * (size_t)f + a]); }
     q.latticeOrdered = 0;
     if (q.nFaces == q.nA * q.nB) {
       const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz};
@@ -718,11 +778,9 @@ static int motion_init(ibm_ctx* c) {
   }
   d.patches = M->dPatches;
   // cub temp storage
-  size_t b1 = 0, b2 = 0, b3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b1, d.keys, d.keysSorted, d.vals, d.valsSorted, c->cap);
+  size_t b2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b2, M->dIdxKeys, M->dIdxKeys2, d.vals, d.valsSorted, c->cap);
-  cub::DeviceScan::ExclusiveSum(nullptr, b3, d.hitFlag, d.hitOff, (int)(cap * std::max(1, d.nCyc)));
-  M->cubTempBytes = std::max(b1, std::max(b2, b3)) + 256;
+  M->cubTempBytes = b2 + 256;
   if (!ctx_cuda_ok(c, cudaMalloc(&M->cubTemp, M->cubTempBytes), "cudaMalloc(cub)")) return IBM_E_CUDA;
   return IBM_OK;
 }
@@ -783,9 +841,8 @@ static int substep_launch(ibm_ctx* c, double localDt) {
   double* Fw = d.Fw; double* Tw = d.Tw;
   if (c->cfg.moving) {
     // computeCollisions
-    k5_sort_keys<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
-    size_t tb = M->cubTempBytes;
-    cub::DeviceRadixSort::SortPairs(M->cubTemp, tb, d.keys, d.keysSorted, d.vals, d.valsSorted, cap, 0, 32, st);
+    cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
+    k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
     k5_contacts<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
     c->nLaunch += 3;
     // computeWallHits
@@ -796,15 +853,11 @@ static int substep_launch(ibm_ctx* c, double localDt) {
       cCnt = d.cCnt2; cIdx = d.cIdx2; cF = d.cF2; cT = d.cT2; Fw = d.Fw2; Tw = d.Tw2;
       // computeCyclicHits (App. B #10: as coded it returns when the mesh has no wall patch)
       if (d.nWalls > 0 || c->cfg.cyclicWithoutWalls) {
-        dim3 g(blocks_for(cap), d.nCyc);
-        k5_cyclic_detect<<<g, 128, 0, st>>>(d, c->L, c->in, c->dClasses);
-        size_t tb2 = M->cubTempBytes;
-        cub::DeviceScan::ExclusiveSum(M->cubTemp, tb2, d.hitFlag, d.hitOff, cap * d.nCyc, st);
-        // total = last offset + last flag
-        k5_append_total<<<1, 1, 0, st>>>(d);
-        k5_append<<<blocks_for(cap * d.nCyc, 256), 256, 0, st>>>(d, c->in);
+        k5_cyclic_candidates<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+        k5_cyclic_detect<<<148, 256, 0, st>>>(d, c->L, c->in, c->dClasses);
+        k5_append<<<64, 128, 0, st>>>(d, c->in);
         k5_append_link<<<1, 32, 0, st>>>(d, c->in);
-        c->nLaunch += 5;
+        c->nLaunch += 4;
       }
     }
   }
@@ -822,6 +875,8 @@ static int finish_substeps(ibm_ctx* c) {
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   IBM_CUDA(c, cudaGetLastError());
   if (c->hScal[9] == 1) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: more than CONTACT_CAP simultaneous contacts on one particle");
+  if (c->hScal[9] == 4) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: periodic-patch candidate list overflow");
+  if (c->hScal[9] == 3) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: cell-list bin capacity exceeded (strongly polydisperse or overlapping bodies)");
   if (c->hScal[9] == 2) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: instance capacity exhausted (raise ibm_cloud_cfg.maxInstances)");
   c->nInst = c->hScal[8];
   return IBM_OK;
