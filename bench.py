@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--variant", type=int, default=-1, help="-1 = library defaults")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -249,7 +249,8 @@ def main():
     mesh = case.mesh
     t0 = time.time()
     cloud = ParticleCloud(case, device=local_rank)
-    cloud.set_kernel_variant(args.variant, args.variant)
+    if args.variant >= 0:
+        cloud.set_kernel_variant(args.variant, args.variant)
     setup_s = time.time() - t0
     have_motion = True
     try:

@@ -18,6 +18,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 UNITS = [
     ("ibm_kernels_ref.cu", ["-fmad=false"]),
     ("ibm_kernels_fast.cu", []),
+    ("ibm_kernels_v2.cu", []),
+    ("ibm_kernels_v3.cu", []),
     ("ibm_kernels_util.cu", []),
     ("ibm_motion.cu", ["-fmad=false"]),
     ("ibm_comm.cu", []),

@@ -238,8 +238,9 @@ int ctx_update(ibm_ctx* c) {
   launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
   launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
   launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
-  c->nLaunch += 4;
-  IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2);
+  c->nLaunch += 9;
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->nInst > 0 && c->hScal[0] < c->nInst) {  // deleteInActiveParticles (particleCloud.C:940-950)
     launch_compact_instances(c->stream, c->in, c->in2, c->dKeep, c->dKeepOff, c->nInst);
@@ -247,11 +248,13 @@ int ctx_update(ibm_ctx* c) {
     c->nInst = c->hScal[0];
     motion_invalidate_groups(c);
     launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
-    c->nLaunch += 2;
-    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2);
+    c->nLaunch += 7;
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;
+  c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
   if (c->totalShell > c->shellCap) {
     if (c->dShellCell) cudaFree(c->dShellCell);
     if (c->dShellJK) cudaFree(c->dShellJK);
@@ -290,6 +293,12 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     ctx_tic(c, T_FORCING);
     if (c->forcingVariant == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
+    else if (c->forcingVariant == 3)
+      launch_forcing_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
+                        dS, dt, F);
+    else if (c->forcingVariant == 2)
+      launch_forcing_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
+                        dS, dt, F);
     else
       launch_forcing_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
     c->nLaunch++;
@@ -338,6 +347,10 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   ctx_tic(c, T_STRESS);
   if (c->stressVariant == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+  else if (c->stressVariant == 3)
+    launch_stress_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+  else if (c->stressVariant == 2)
+    launch_stress_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   else
     launch_stress_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   c->nLaunch++;
@@ -524,6 +537,7 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;
   if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
   if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
+  if (schedule_alloc(c->sched, c->cap)) return ctx_fail(c, IBM_E_CUDA, "schedule_alloc failed");
   IBM_CUDA(c, cudaMalloc(&c->dKeep, (size_t)c->cap * sizeof(int)));
   IBM_CUDA(c, cudaMalloc(&c->dKeepOff, (size_t)c->cap * sizeof(int)));
   // upload originals: particleIBM(mesh, dict, index)  particleIBM.C:269-315
@@ -563,6 +577,7 @@ int ibm_destroy(ibm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   motion_destroy(c);
   comm_destroy(c);
+  schedule_free(c->sched);
   for (auto& p : c->events) { cudaEventDestroy(p.a); if (p.b) cudaEventDestroy(p.b); }
   for (auto e : c->eventPool) cudaEventDestroy(e);
   for (auto p : c->instAllocs) cudaFree(p);

@@ -74,7 +74,9 @@ struct ibm_ctx {
   double* hPinned = nullptr;  // small pinned scratch for results
   size_t hPinnedDoubles = 0;
 
-  int forcingVariant = 1, stressVariant = 1;
+  int forcingVariant = 2, stressVariant = 3;  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging
+  ibm::Schedule sched;
+  int totalChunks = 0;
 
   // motion (loop 5) scratch lives in ibm_motion.cu
   void* motion = nullptr;

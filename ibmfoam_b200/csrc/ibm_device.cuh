@@ -87,6 +87,25 @@ __device__ __forceinline__ int find_cell(const LatticeDev& L, double x, double y
   return lat_index(L, I, J, K);
 }
 
+// Same result as find_cell without the three fp64 divisions on the common path: floor(q*inv) equals
+// floor(fl(q/d)) unless q/d lies within a few ulp of an integer; those cases fall back to the exact division.
+__device__ __forceinline__ bool floor_div_exact(double q, double d, double inv, int n, int& I) {
+  double t = q * inv;
+  double f = floor(t);
+  double fr = t - f;
+  if (fr < 1e-9 || fr > 1.0 - 1e-9) f = floor(xdiv(q, d));
+  if (!(f >= 0.0 && f < (double)n)) return false;
+  I = (int)f;
+  return true;
+}
+__device__ __forceinline__ int find_cell_fast(const LatticeDev& L, double idx, double idy, double idz, double x, double y, double z,
+                                              int& I, int& J, int& K) {
+  if (!floor_div_exact(xsub(x, L.ox), L.dx, idx, L.nx, I)) return -1;
+  if (!floor_div_exact(xsub(y, L.oy), L.dy, idy, L.ny, J)) return -1;
+  if (!floor_div_exact(xsub(z, L.oz), L.dz, idz, L.nz, K)) return -1;
+  return lat_index(L, I, J, K);
+}
+
 // mesh_[n] = rotate(centeredMesh_[n]) + center   (particleShape.C:291-302; ellipse.C:61-64)
 __device__ __forceinline__ V3 shape_point(const ShapeClassDev& sc, const double* rot, double cx, double cy, double cz, int n) {
   double px = sc.centered[3 * n], py = sc.centered[3 * n + 1], pz = sc.centered[3 * n + 2];

@@ -27,6 +27,31 @@ void launch_forcing_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassD
 void launch_stress_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                         const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
 
+// ---- schedule (ibm_kernels_util.cu): Morton-sorted instance order + table of <=FORCING_CHUNK-cell work items ----
+#define FORCING_CHUNK 128
+struct Schedule {
+  unsigned* keys = nullptr; unsigned* keysSorted = nullptr;
+  int* iota = nullptr; int* order = nullptr;      // order[pos] = instance scheduled at position pos
+  int* chunkCnt = nullptr; int* chunkOff = nullptr;  // per sorted position; chunkOff has n+1 entries
+  void* temp = nullptr; size_t tempBytes = 0;
+  int cap = 0;
+};
+int schedule_alloc(Schedule& s, int cap);
+void schedule_free(Schedule& s);
+// builds order[] and chunkOff[]; writes the total number of work items to *dTotalChunks
+void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks);
+void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
+                       const double* Uold, const double* S, double dT, double* F);
+void launch_stress_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
+void launch_forcing_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
+                       const double* Uold, const double* S, double dT, double* F);
+void launch_stress_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
 // ---- ibm_kernels_util.cu ----
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep);
 void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,

@@ -1,6 +1,8 @@
 // Plumbing kernels: exclusive scan of the per-instance shell counts, and the layout kernels that turn
 // OpenFOAM's caller-ordered array-of-structures fields (vector = 3 doubles, symmTensor = 6) into the
 // lattice-ordered structure-of-arrays planes the hot kernels read (and back for F).
+#include <cub/cub.cuh>
+
 #include "ibm_kernels.h"
 
 namespace ibm {
@@ -75,6 +77,70 @@ __global__ void k_compact_instances(InstanceSoA s, InstanceSoA d, const int* __r
     d.F[q][j] = s.F[q][i]; d.T[q][j] = s.T[q][i];
   }
   for (int q = 0; q < 9; ++q) d.rot[9 * (size_t)j + q] = s.rot[9 * (size_t)i + q];
+}
+
+// ---- schedule -----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void k_morton_keys(LatticeDev L, InstanceSoA in, int n, int cap, unsigned* keys, int* iota) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  iota[i] = i;
+  if (i >= n) { keys[i] = 0xffffffffu; return; }
+  int I = min(max((int)floor((in.c[0][i] - L.ox) / L.dx), 0), L.nx - 1);
+  int J = min(max((int)floor((in.c[1][i] - L.oy) / L.dy), 0), L.ny - 1);
+  int K = min(max((int)floor((in.c[2][i] - L.oz) / L.dz), 0), L.nz - 1);
+  // 4-cell granularity keeps 10 bits per axis up to 4096 cells
+  int sh = 0;
+  while (((max(L.nx, max(L.ny, L.nz)) - 1) >> sh) > 1023) ++sh;
+  keys[i] = spread10((unsigned)(I >> sh)) | (spread10((unsigned)(J >> sh)) << 1) | (spread10((unsigned)(K >> sh)) << 2);
+}
+__global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, int n, int* cnt) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos > n) return;
+  int c = 0;
+  if (pos < n) {
+    int i = order[pos];
+    if (in.onMesh[i] != 0) c = (in.nShell[i] + FORCING_CHUNK - 1) / FORCING_CHUNK;
+  }
+  cnt[pos] = c;  // entry n is a zero sentinel so that the exclusive scan yields n+1 offsets
+}
+__global__ void k_last_offset(const int* off, int n, int* out) { *out = off[n]; }
+
+int schedule_alloc(Schedule& s, int cap) {
+  s.cap = cap;
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, s.keys, s.keysSorted, s.iota, s.order, cap);
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, s.chunkCnt, s.chunkOff, cap + 1);
+  s.tempBytes = (b1 > b2 ? b1 : b2) + 256;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  A((void**)&s.keys, cap * sizeof(unsigned)); A((void**)&s.keysSorted, cap * sizeof(unsigned));
+  A((void**)&s.iota, cap * sizeof(int)); A((void**)&s.order, cap * sizeof(int));
+  A((void**)&s.chunkCnt, (cap + 1) * sizeof(int)); A((void**)&s.chunkOff, (cap + 1) * sizeof(int));
+  A(&s.temp, s.tempBytes);
+  return e == cudaSuccess ? 0 : -1;
+}
+void schedule_free(Schedule& s) {
+  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp};
+  for (void* p : ps) if (p) cudaFree(p);
+  s = Schedule{};
+}
+void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks) {
+  const int cap = s.cap;
+  k_morton_keys<<<(cap + 255) / 256, 256, 0, st>>>(L, in, nInst, cap, s.keys, s.iota);
+  size_t tb = s.tempBytes;
+  cub::DeviceRadixSort::SortPairs(s.temp, tb, s.keys, s.keysSorted, s.iota, s.order, cap, 0, 32, st);
+  k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt);
+  tb = s.tempBytes;
+  cub::DeviceScan::ExclusiveSum(s.temp, tb, s.chunkCnt, s.chunkOff, nInst + 1, st);
+  k_last_offset<<<1, 1, 0, st>>>(s.chunkOff, nInst, dTotalChunks);
 }
 
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep) {
