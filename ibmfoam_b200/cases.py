@@ -29,6 +29,21 @@ class MeshSpec:
     delta: tuple
     blocks: list = field(default_factory=list)   # [(i0,i1,j0,j1,k0,k1)] in blockMesh order; [] = one block
     patches: list = field(default_factory=list)  # [(side, type, neighbour patch id or -1)]
+    kz0: int = 0                                 # slab of a decomposed mesh: global z-plane of local plane 0
+
+    def slab(self, k0: int, k1: int) -> "MeshSpec":
+        """The processor mesh holding z-planes [k0,k1): same geometry (global plane index), z-sides that are interior
+        cuts become processor patches (their faces are boundary faces, skipped by the gather like the reference's)."""
+        assert not self.blocks, "slab decomposition needs a single-block lattice"
+        pats = []
+        for (side, typ, nb) in self.patches:
+            if side == ZMIN and k0 > 0:
+                pats.append((side, PROCESSOR, -1))
+            elif side == ZMAX and k1 < self.nz:
+                pats.append((side, PROCESSOR, -1))
+            else:
+                pats.append((side, typ, nb))
+        return MeshSpec(self.nx, self.ny, k1 - k0, self.origin, self.delta, [], pats, kz0=self.kz0 + k0)
 
     @property
     def n_cells(self) -> int:
@@ -38,7 +53,7 @@ class MeshSpec:
         """Centres in lattice order (x fastest), same expression as the mini-mesh definition."""
         x = self.origin[0] + (np.arange(self.nx) + 0.5) * self.delta[0]
         y = self.origin[1] + (np.arange(self.ny) + 0.5) * self.delta[1]
-        z = self.origin[2] + (np.arange(self.nz) + 0.5) * self.delta[2]
+        z = self.origin[2] + (np.arange(self.nz) + self.kz0 + 0.5) * self.delta[2]
         Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
         return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
 

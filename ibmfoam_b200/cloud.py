@@ -25,7 +25,10 @@ def _c(a, dt=np.float64):
 
 
 class ParticleCloud:
-    def __init__(self, case=None, *, mesh=None, cloud=None, particles=None, device=0, max_instances=0):
+    def __init__(self, case=None, *, mesh=None, cloud=None, particles=None, device=0, max_instances=0,
+                 slab=None, local_group=None, nccl_id=None, rank=0, n_ranks=1):
+        """slab=(k0,k1): this rank's z-planes of the (whole) mesh; local_group / nccl_id select the transport of the
+        F/T and status all-reduces (multi-GPU: slab-decomposed fields, replicated particle state)."""
         L = capi.load()
         if case is not None:
             mesh, cloud, particles = case.mesh, case.cloud, case.particles
@@ -59,6 +62,15 @@ class ParticleCloud:
         self._h = h
         self._L = L
         self.n_cells = mesh.n_cells
+        self.slab = slab
+        if slab is not None:
+            check(L.ibm_set_slab(h, int(slab[0]), int(slab[1])), h)
+            self.n_cells = mesh.nx * mesh.ny * (int(slab[1]) - int(slab[0]))
+        if local_group is not None:
+            check(L.ibm_comm_init_local(h, local_group, int(rank)), h)
+        elif nccl_id is not None:
+            buf = C.create_string_buffer(bytes(nccl_id), L.ibm_comm_unique_id_bytes())
+            check(L.ibm_comm_init(h, buf, int(rank), int(n_ranks)), h)
         n = particles.n
         inits = (capi.ParticleInit * max(1, n))()
         for i in range(n):
@@ -228,6 +240,38 @@ class ParticleCloud:
             out = np.empty((self.n_cells, n_comp) if n_comp > 1 else (self.n_cells,))
         check(self._L.ibm_download_field(self._h, C.c_void_p(d_soa) if d_soa else None, int(n_comp), _ptr(out)), self._h)
         return out
+
+
+def nccl_unique_id() -> bytes:
+    L = capi.load()
+    buf = C.create_string_buffer(L.ibm_comm_unique_id_bytes())
+    check(L.ibm_comm_get_unique_id(buf))
+    return buf.raw
+
+
+class LocalGroup:
+    """In-process transport for tests: ranks are host threads sharing one device."""
+
+    def __init__(self, n):
+        self.n = n
+        self.handle = C.c_void_p()
+        check(capi.load().ibm_comm_local_group_create(int(n), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            capi.load().ibm_comm_local_group_destroy(self.handle)
+            self.handle = None
+
+
+def slab_ranges(nz, n_ranks):
+    """Contiguous z-plane ranges, as even as possible (first ranks take the remainder)."""
+    base, rem = divmod(nz, n_ranks)
+    out, k = [], 0
+    for r in range(n_ranks):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
 
 
 def substep_schedule(dt, max_n=256):

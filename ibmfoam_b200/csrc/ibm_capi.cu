@@ -216,7 +216,7 @@ static int alloc_instances(ibm_ctx* c, InstanceSoA& s, int cap) {
     return true;
   };
   bool ok = ai(&s.index) && ai(&s.copy) && ai(&s.active) && ai(&s.onMesh) && ai(&s.cls) && ai(&s.nShell) && ai(&s.shellOff) &&
-            ai(&s.nPtsOnMesh) && ad(&s.rho) && ad(&s.age) && ad(&s.rot, 9);
+            ai(&s.nPtsOnMesh) && ai(&s.onLocal) && ad(&s.rho) && ad(&s.age) && ad(&s.rot, 9);
   for (int q = 0; q < 3 && ok; ++q) ok = ad(&s.c[q]) && ad(&s.th[q]) && ad(&s.v[q]) && ad(&s.om[q]) && ad(&s.F[q]) && ad(&s.T[q]);
   return ok ? IBM_OK : IBM_E_CUDA;
 }
@@ -235,6 +235,12 @@ int ctx_update(ibm_ctx* c) {
   clear_live_F(c);
   ctx_tic(c, T_UPDATE);
   launch_k1_count(c->stream, c->L, c->dClasses, c->in, c->nInst);
+  if (comm_ranks(c) > 1 && c->nInst > 0) {
+    // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs
+    int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst, 1);
+    if (rcc) return rcc;
+  }
+  launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
   launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
   launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
   launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
@@ -407,6 +413,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   L.ox = mesh->origin[0]; L.oy = mesh->origin[1]; L.oz = mesh->origin[2];
   L.dx = mesh->delta[0]; L.dy = mesh->delta[1]; L.dz = mesh->delta[2];
   L.latToCell = nullptr; L.cellToLat = nullptr;
+  L.kz0 = 0;
   c->zMin = L.oz;
   c->zMax = L.oz + L.nz * L.dz;
   // caller cell numbering
@@ -495,6 +502,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
     c->patches.push_back(std::move(ph));
   }
   c->nGeometricD = 3 - (int)emptyDir[0] - (int)emptyDir[1] - (int)emptyDir[2];
+  c->Lg = c->L;
   if (!ctx_cuda_ok(nullptr, cudaMalloc(&c->dScal, 64 * sizeof(int)), "cudaMalloc") ||
       !ctx_cuda_ok(nullptr, cudaMallocHost(&c->hScal, 64 * sizeof(int)), "cudaMallocHost")) { delete c; return IBM_E_CUDA; }
   cudaMemset(c->dScal, 0, 64 * sizeof(int));
@@ -590,6 +598,18 @@ int ibm_destroy(ibm_ctx* c) {
   if (c->hPinned) cudaFreeHost(c->hPinned);
   cudaStreamDestroy(c->stream);
   delete c;
+  return IBM_OK;
+}
+
+int ibm_set_slab(ibm_ctx* c, int k0, int k1) {
+  if (!c) return IBM_E_ARG;
+  if (c->cap != 0) return ctx_fail(c, IBM_E_STATE, "ibm_set_slab: call before ibm_set_particles");
+  if (c->Lg.latToCell) return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_set_slab: slab decomposition needs a single-block lattice");
+  if (k0 < 0 || k1 > c->Lg.nz || k0 >= k1) return ctx_fail(c, IBM_E_ARG, "ibm_set_slab: bad plane range");
+  c->L = c->Lg;
+  c->L.kz0 = k0;
+  c->L.nz = k1 - k0;
+  c->L.nCells = c->L.nx * c->L.ny * c->L.nz;
   return IBM_OK;
 }
 

@@ -36,7 +36,8 @@ struct ibm_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   ibm_cloud_cfg cfg{};
-  ibm::LatticeDev L{};
+  ibm::LatticeDev L{};   // lattice loops 1-4 run on: the whole mesh, or this rank's z-slab
+  ibm::LatticeDev Lg{};  // the whole mesh (loop 5, patches, global location status)
   int* dLatToCell = nullptr;
   int* dCellToLat = nullptr;
   std::vector<int> hLatToCell;
@@ -105,6 +106,9 @@ void motion_invalidate_groups(ibm_ctx* c);
 int combine_forces(ibm_ctx* c);
 // ibm_comm.cu
 void comm_destroy(ibm_ctx* c);
+int comm_allreduce_sum(ibm_ctx* c, void* buf, size_t count, int isInt);
+int comm_ranks(ibm_ctx* c);
+int comm_rank(ibm_ctx* c);
 }  // namespace ibm
 
 #define IBM_CUDA(c, call)                                            \

@@ -28,6 +28,9 @@ struct LatticeDev {
   double dx, dy, dz;
   const int* latToCell;  // nullptr = identity
   const int* cellToLat;  // nullptr = identity
+  int kz0;               // slab decomposition: global z-plane of local plane 0 (nz is the LOCAL plane count);
+                         // geometry is always evaluated with the global plane index K + kz0, exactly as a
+                         // decomposed OpenFOAM mesh keeps the global cell centres
 };
 
 struct ShapeClassDev {
@@ -52,6 +55,7 @@ struct InstanceSoA {
   double* rot;        // [cap][9] rotationMatrix_
   int* nShell; int* shellOff;
   int* nPtsOnMesh;
+  int* onLocal;       // rank-local location status (== onMesh on one GPU): which instances loops 1-4 skip on this slab
 };
 
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
@@ -81,7 +85,7 @@ __device__ __forceinline__ double fc(double o, int I, double d) { return xadd(o,
 __device__ __forceinline__ int find_cell(const LatticeDev& L, double x, double y, double z, int& I, int& J, int& K) {
   double tx = floor(xdiv(xsub(x, L.ox), L.dx));
   double ty = floor(xdiv(xsub(y, L.oy), L.dy));
-  double tz = floor(xdiv(xsub(z, L.oz), L.dz));
+  double tz = floor(xdiv(xsub(z, L.oz), L.dz)) - (double)L.kz0;
   if (!(tx >= 0.0 && tx < (double)L.nx && ty >= 0.0 && ty < (double)L.ny && tz >= 0.0 && tz < (double)L.nz)) return -1;
   I = (int)tx; J = (int)ty; K = (int)tz;
   return lat_index(L, I, J, K);
@@ -89,11 +93,12 @@ __device__ __forceinline__ int find_cell(const LatticeDev& L, double x, double y
 
 // Same result as find_cell without the three fp64 divisions on the common path: floor(q*inv) equals
 // floor(fl(q/d)) unless q/d lies within a few ulp of an integer; those cases fall back to the exact division.
-__device__ __forceinline__ bool floor_div_exact(double q, double d, double inv, int n, int& I) {
+__device__ __forceinline__ bool floor_div_exact(double q, double d, double inv, int n, int& I, int off = 0) {
   double t = q * inv;
   double f = floor(t);
   double fr = t - f;
   if (fr < 1e-9 || fr > 1.0 - 1e-9) f = floor(xdiv(q, d));
+  f -= (double)off;
   if (!(f >= 0.0 && f < (double)n)) return false;
   I = (int)f;
   return true;
@@ -102,7 +107,7 @@ __device__ __forceinline__ int find_cell_fast(const LatticeDev& L, double idx, d
                                               int& I, int& J, int& K) {
   if (!floor_div_exact(xsub(x, L.ox), L.dx, idx, L.nx, I)) return -1;
   if (!floor_div_exact(xsub(y, L.oy), L.dy, idy, L.ny, J)) return -1;
-  if (!floor_div_exact(xsub(z, L.oz), L.dz, idz, L.nz, K)) return -1;
+  if (!floor_div_exact(xsub(z, L.oz), L.dz, idz, L.nz, K, L.kz0)) return -1;
   return lat_index(L, I, J, K);
 }
 
@@ -167,13 +172,13 @@ __device__ __forceinline__ int cell_faces(const LatticeDev& L, int I, int J, int
 
 // face centre of cell (I,J,K) in direction d
 __device__ __forceinline__ V3 face_centre(const LatticeDev& L, int I, int J, int K, int d) {
-  V3 f{cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K, L.dz)};
+  V3 f{cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz)};
   if (d == 0) f.x = fc(L.ox, I + 1, L.dx);
   if (d == 1) f.x = fc(L.ox, I, L.dx);
   if (d == 2) f.y = fc(L.oy, J + 1, L.dy);
   if (d == 3) f.y = fc(L.oy, J, L.dy);
-  if (d == 4) f.z = fc(L.oz, K + 1, L.dz);
-  if (d == 5) f.z = fc(L.oz, K, L.dz);
+  if (d == 4) f.z = fc(L.oz, K + L.kz0 + 1, L.dz);
+  if (d == 5) f.z = fc(L.oz, K + L.kz0, L.dz);
   return f;
 }
 

@@ -23,7 +23,7 @@ __device__ __forceinline__ void make_stencil7(const LatticeDev& L, const V3& p, 
   int I, J, K;
   s.self = find_cell(L, p.x, p.y, p.z, I, J, K);
   if (s.self < 0) return;
-  const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + 0.5) * L.dz;
+  const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
   const double ex = Cx - p.x, ey = Cy - p.y, ez = Cz - p.z;  // cell centre - point
   const double hx = 0.5 * L.dx, hy = 0.5 * L.dy, hz = 0.5 * L.dz;
   const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128) k_forcing_v1(LatticeDev L, const ShapeCla
                                                     const double* __restrict__ S, double dT, double* __restrict__ F) {
   const int b = blockIdx.x;
   if (b >= nInst) return;
-  if (in.onMesh[b] == 0) return;
+  if (in.onLocal[b] == 0) return;
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double* rot = in.rot + 9 * (size_t)b;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) k_forcing_v1(LatticeDev L, const ShapeCla
       const int pk = shellJK[off + c];
       const int j = pk & 0xffff, k = pk >> 16;
       const int I = lat % L.nx, J = (lat / L.nx) % L.ny, K = lat / (L.nx * L.ny);
-      const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + 0.5) * L.dz;
+      const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
       // corner q of the bin (particleShape.C:150-180)
       int pI, pS, pO;
       if (sc.nk != 1 && k == sc.nk - 1) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_stress_v1(LatticeDev L, const ShapeClas
   const double* rot = in.rot + 9 * (size_t)b;
   const size_t C = (size_t)L.nCells;
   const int nS = sc.nTheta * sc.nk;
-  const bool on = in.onMesh[b] != 0;
+  const bool on = in.onLocal[b] != 0;
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int s = threadIdx.x; s < nS; s += blockDim.x) {
     const int i = s / sc.nk, k = s % sc.nk;

@@ -79,7 +79,7 @@ __device__ __forceinline__ Box bounding_box(const LatticeDev& L, double cx, doub
   Box b;
   b.i0 = max(0, (int)floor((cx - R - L.ox) / L.dx) - 1); b.i1 = min(L.nx - 1, (int)floor((cx + R - L.ox) / L.dx) + 1);
   b.j0 = max(0, (int)floor((cy - R - L.oy) / L.dy) - 1); b.j1 = min(L.ny - 1, (int)floor((cy + R - L.oy) / L.dy) + 1);
-  b.k0 = max(0, (int)floor((cz - R - L.oz) / L.dz) - 1); b.k1 = min(L.nz - 1, (int)floor((cz + R - L.oz) / L.dz) + 1);
+  b.k0 = max(0, (int)floor((cz - R - L.oz) / L.dz) - 1 - L.kz0); b.k1 = min(L.nz - 1, (int)floor((cz + R - L.oz) / L.dz) + 1 - L.kz0);
   return b;
 }
 
@@ -124,7 +124,7 @@ __global__ void k1_count(LatticeDev L, const ShapeClassDev* __restrict__ classes
   for (int t = threadIdx.x; t < nb; t += blockDim.x) {
     int I = bx.i0 + t % bi, J = bx.j0 + (t / bi) % bj, K = bx.k0 + t / (bi * bj);
     int j, k;
-    if (mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K, L.dz), j, k)) ++cnt;
+    if (mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k)) ++cnt;
   }
   int nShell = block_sum(cnt, sm);
   int on = 0;
@@ -138,11 +138,21 @@ __global__ void k1_count(LatticeDev L, const ShapeClassDev* __restrict__ classes
     int I, J, K;
     int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
     in.nShell[b] = nShell;
-    in.nPtsOnMesh[b] = nOn;
-    // particleShape.C:97-108
-    in.onMesh[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
-    in.active[b] = cOn;  // particleIBM.C:607-614
+    in.nPtsOnMesh[b] = nOn;  // local count; summed over the slabs before k1_status on several GPUs
+    in.onLocal[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
   }
+}
+
+// particleShape.C:97-108 and particleIBM.C:607-614 on the WHOLE mesh: nPtsOnMesh holds the point count over all
+// slabs, Lg is the global lattice.  On one GPU this reproduces the local status exactly.
+__global__ void k1_status(LatticeDev Lg, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nInst) return;
+  int I, J, K;
+  int cOn = find_cell(Lg, in.c[0][b], in.c[1][b], in.c[2][b], I, J, K) >= 0;
+  int nOn = in.nPtsOnMesh[b];
+  in.onMesh[b] = (nOn == 0 && !cOn) ? 0 : (nOn == classes[in.cls[b]].N ? 2 : 1);
+  in.active[b] = cOn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -169,7 +179,7 @@ __global__ void k1_fill(LatticeDev L, const ShapeClassDev* __restrict__ classes,
     bool hit = false;
     if (t < nb) {
       int I = bx.i0 + t % bi, J = bx.j0 + (t / bi) % bj, K = bx.k0 + t / (bi * bj);
-      hit = mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K, L.dz), j, k);
+      hit = mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k);
       lat = lat_index(L, I, J, K);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -201,7 +211,7 @@ __global__ void k1_indicator(LatticeDev L, const ShapeClassDev* __restrict__ cla
   int nb = (bi > 0 && bj > 0 && bk > 0) ? bi * bj * bk : 0;
   for (int t = threadIdx.x; t < nb; t += blockDim.x) {
     int I = bx.i0 + t % bi, J = bx.j0 + (t / bi) % bj, K = bx.k0 + t / (bi * bj);
-    double Cx = cc(L.ox, I, L.dx), Cy = cc(L.oy, J, L.dy), Cz = cc(L.oz, K, L.dz);
+    double Cx = cc(L.ox, I, L.dx), Cy = cc(L.oy, J, L.dy), Cz = cc(L.oz, K + L.kz0, L.dz);
     double r = shape_r(sc, cx, cy, thz, Cx, Cy);
     if (r > xmag(xsub(cx, Cx), xsub(cy, Cy), xsub(cz, Cz))) Ifield[lat_index(L, I, J, K)] = 1.0;
   }
@@ -298,7 +308,7 @@ __global__ void k_tap_shell(LatticeDev L, const ShapeClassDev* __restrict__ clas
     int Is[8], Os[4];
     neighbour_ids(sc, j, k, Is, Os);
     double w[8], W;
-    scatter_weights(sc, rot, cx, cy, cz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K, L.dz), Is, w, W);
+    scatter_weights(sc, rot, cx, cy, cz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), Is, w, W);
     cells[c] = caller_id(L, lat);
     jk[2 * c] = j; jk[2 * c + 1] = k;
     for (int q = 0; q < 8; ++q) { IsOut[8 * c + q] = Is[q]; wOut[8 * c + q] = w[q]; }
@@ -345,7 +355,7 @@ __global__ void k_forcing_ref(LatticeDev L, const ShapeClassDev* __restrict__ cl
                               double dT, double* __restrict__ F) {
   const int b = blockIdx.x;
   if (b >= nInst) return;
-  if (in.onMesh[b] == 0) return;  // particleIBM.C:218-221
+  if (in.onLocal[b] == 0) return;  // particleIBM.C:218-221 (rank-local status, like a decomposed run)
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double* rot = in.rot + 9 * (size_t)b;
@@ -359,7 +369,7 @@ __global__ void k_forcing_ref(LatticeDev L, const ShapeClassDev* __restrict__ cl
     int Is[8], Os[4];
     neighbour_ids(sc, j, k, Is, Os);
     double w[8], W;
-    scatter_weights(sc, rot, cx, cy, cz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K, L.dz), Is, w, W);
+    scatter_weights(sc, rot, cx, cy, cz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), Is, w, W);
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     for (int q = 0; q < 4; ++q) {
       V3 pO = shape_point(sc, rot, cx, cy, cz, Os[q]);
@@ -416,7 +426,7 @@ __global__ void k_stress_ref(LatticeDev L, const ShapeClassDev* __restrict__ cla
   const size_t C = (size_t)L.nCells;
   const int nS = sc.nTheta * sc.nk;
   double Fx = 0, Fy = 0, Fz = 0, Tx = 0, Ty = 0, Tz = 0, Ux = 0, Uy = 0, Uz = 0;
-  const bool on = in.onMesh[b] != 0;
+  const bool on = in.onLocal[b] != 0;
   for (int s0 = 0; s0 < nS; s0 += STRESS_CHUNK) {
     int s = s0 + threadIdx.x;
     if (threadIdx.x < STRESS_CHUNK && s < nS) {
@@ -491,6 +501,9 @@ __global__ void k_stress_ref(LatticeDev L, const ShapeClassDev* __restrict__ cla
 // ------------------------------------------------------------------------------------------------
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
   if (nInst > 0) k1_count<<<nInst, 128, 0, st>>>(L, classes, in, nInst);
+}
+void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
+  if (nInst > 0) k1_status<<<(nInst + 127) / 128, 128, 0, st>>>(Lg, classes, in, nInst);
 }
 void launch_k1_fill(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                     int* shellCell, int* shellJK) {

@@ -70,7 +70,7 @@ __global__ void k_compact_instances(InstanceSoA s, InstanceSoA d, const int* __r
   if (i >= n || !keep[i]) return;
   int j = keepOff[i];
   d.index[j] = s.index[i]; d.copy[j] = s.copy[i]; d.active[j] = s.active[i]; d.onMesh[j] = s.onMesh[i]; d.cls[j] = s.cls[i];
-  d.nShell[j] = s.nShell[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i];
+  d.nShell[j] = s.nShell[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i]; d.onLocal[j] = s.onLocal[i];
   d.rho[j] = s.rho[i]; d.age[j] = s.age[i];
   for (int q = 0; q < 3; ++q) {
     d.c[q][j] = s.c[q][i]; d.th[q][j] = s.th[q][i]; d.v[q][j] = s.v[q][i]; d.om[q][j] = s.om[q][i];
@@ -95,7 +95,7 @@ __global__ void k_morton_keys(LatticeDev L, InstanceSoA in, int n, int cap, unsi
   if (i >= n) { keys[i] = 0xffffffffu; return; }
   int I = min(max((int)floor((in.c[0][i] - L.ox) / L.dx), 0), L.nx - 1);
   int J = min(max((int)floor((in.c[1][i] - L.oy) / L.dy), 0), L.ny - 1);
-  int K = min(max((int)floor((in.c[2][i] - L.oz) / L.dz), 0), L.nz - 1);
+  int K = min(max((int)floor((in.c[2][i] - L.oz) / L.dz) - L.kz0, 0), L.nz - 1);
   // 4-cell granularity keeps 10 bits per axis up to 4096 cells
   int sh = 0;
   while (((max(L.nx, max(L.ny, L.nz)) - 1) >> sh) > 1023) ++sh;
@@ -107,7 +107,7 @@ __global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, in
   int c = 0;
   if (pos < n) {
     int i = order[pos];
-    if (in.onMesh[i] != 0) c = (in.nShell[i] + FORCING_CHUNK - 1) / FORCING_CHUNK;
+    if (in.onLocal[i] != 0) c = (in.nShell[i] + FORCING_CHUNK - 1) / FORCING_CHUNK;
   }
   cnt[pos] = c;  // entry n is a zero sentinel so that the exclusive scan yields n+1 offsets
 }

@@ -30,7 +30,7 @@ __device__ __forceinline__ void make_stencil7(const LatticeDev& L, double idx, d
   int I, J, K;
   s.self = find_cell_fast(L, idx, idy, idz, p.x, p.y, p.z, I, J, K);
   if (s.self < 0) return;
-  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + 0.5) * L.dz) - p.z;
+  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + L.kz0 + 0.5) * L.dz) - p.z;
   const double hx = 0.5 * L.dx, hy = 0.5 * L.dy, hz = 0.5 * L.dz;
   const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
   double d2[6];
@@ -198,7 +198,7 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   // ---- C: one thread per shell cell ----
   if (live) {
     const int I = myLat % L.nx, J = (myLat / L.nx) % L.ny, K = myLat / (L.nx * L.ny);
-    const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + 0.5) * L.dz;
+    const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0, W = 0.0;
     double wI[4], wS[4];
     int slot[4];
@@ -255,7 +255,7 @@ k_stress_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   const double* rot = in.rot + 9 * (size_t)b;
   const size_t C = (size_t)L.nCells;
   const int nS = sc.nTheta * sc.nk;
-  const bool on = in.onMesh[b] != 0;
+  const bool on = in.onLocal[b] != 0;
   const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int s = threadIdx.x; s < nS; s += blockDim.x) {

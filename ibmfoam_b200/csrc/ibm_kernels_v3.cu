@@ -46,7 +46,7 @@ __device__ __forceinline__ void make_st7(const LatticeDev& L, double idx, double
   int lat = find_cell_fast(L, idx, idy, idz, p.x, p.y, p.z, I, J, K);
   s.self = lat;
   if (lat < 0) return;
-  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + 0.5) * L.dz) - p.z;
+  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + L.kz0 + 0.5) * L.dz) - p.z;
   const double hx = 0.5 * L.dx, hy = 0.5 * L.dy, hz = 0.5 * L.dz;
   const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
   double d2[6];
@@ -304,7 +304,7 @@ k_forcing_v3(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     int slot[2] = {0, 0};
     if (live) {
       const int I = myLat % L.nx, J = (myLat / L.nx) % L.ny, K = myLat / (L.nx * L.ny);
-      const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + 0.5) * L.dz;
+      const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int key = myKeys[q];
@@ -373,7 +373,7 @@ k_stress_v3(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   const double* rot = in.rot + 9 * (size_t)b;
   const size_t C = (size_t)L.nCells;
   const int nS = sc.nTheta * sc.nk;
-  const bool on = in.onMesh[b] != 0;
+  const bool on = in.onLocal[b] != 0;
   const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
   if (threadIdx.x == 0) { sb[0] = sb[1] = sb[2] = 0x7fffffff; sb[3] = sb[4] = sb[5] = -1; }
   __syncthreads();

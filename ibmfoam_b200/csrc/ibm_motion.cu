@@ -698,7 +698,7 @@ static int motion_init(ibm_ctx* c) {
   double dmax = 0;
   for (auto& h : c->classes) dmax = std::max(dmax, h.dev.kind == 2 ? std::max(h.dev.a, std::max(h.dev.b, h.dev.l)) : h.dev.d);
   if (!(dmax > 0)) dmax = 1.0;
-  const LatticeDev& L = c->L;
+  const LatticeDev& L = c->Lg;
   d.binEdge = dmax;
   d.bx0 = L.ox - dmax; d.by0 = L.oy - dmax; d.bz0 = L.oz - dmax;
   auto nb = [&](double len) { return std::max(1, (int)std::ceil((len + 2 * dmax) / dmax)); };
@@ -823,6 +823,14 @@ int combine_forces(ibm_ctx* c) {
   int rc = ensure_motion(c);
   if (rc) return rc;
   Motion* M = (Motion*)c->motion;
+  if (comm_ranks(c) > 1 && c->nInst > 0) {
+    // cross-rank part of combineForces (particleCloud.C:236-237): every rank holds every instance, so the partials
+    // of one instance over the slabs are summed element-wise
+    for (int q = 0; q < 3; ++q) {
+      if ((rc = comm_allreduce_sum(c, c->in.F[q], (size_t)c->nInst, 0))) return rc;
+      if ((rc = comm_allreduce_sum(c, c->in.T[q], (size_t)c->nInst, 0))) return rc;
+    }
+  }
   if (c->nParticles > 0) {
     k_combine_forces<<<blocks_for(c->nParticles), 128, 0, c->stream>>>(M->d, c->in);
     c->nLaunch++;
@@ -846,7 +854,7 @@ static int substep_launch(ibm_ctx* c, double localDt) {
     k5_contacts<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
     c->nLaunch += 3;
     // computeWallHits
-    if (d.nWalls > 0) { k5_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->L, c->in, c->dClasses, localDt); c->nLaunch++; }
+    if (d.nWalls > 0) { k5_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt); c->nLaunch++; }
     if (copiesPossible) {
       k5_merge<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in);
       c->nLaunch++;
@@ -854,14 +862,14 @@ static int substep_launch(ibm_ctx* c, double localDt) {
       // computeCyclicHits (App. B #10: as coded it returns when the mesh has no wall patch)
       if (d.nWalls > 0 || c->cfg.cyclicWithoutWalls) {
         k5_cyclic_candidates<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
-        k5_cyclic_detect<<<148, 256, 0, st>>>(d, c->L, c->in, c->dClasses);
+        k5_cyclic_detect<<<148, 256, 0, st>>>(d, c->Lg, c->in, c->dClasses);
         k5_append<<<64, 128, 0, st>>>(d, c->in);
         k5_append_link<<<1, 32, 0, st>>>(d, c->in);
         c->nLaunch += 4;
       }
     }
   }
-  k5_solve<<<blocks_for(cap), 128, 0, st>>>(d, c->L, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
+  k5_solve<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
   c->nLaunch++;
   if (copiesPossible && c->nParticles > 0) { k5_set_positions<<<blocks_for(c->nParticles), 128, 0, st>>>(d, c->in); c->nLaunch++; }
   return IBM_OK;

@@ -187,10 +187,19 @@ int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant);
 int ibm_timings(ibm_ctx* ctx, ibm_timing* out);
 int ibm_timings_reset(ibm_ctx* ctx);
 
-/* ---- multi-GPU (slab decomposition; replaces the Pstream::combineReduce call sites) --- */
+/* ---- multi-GPU: slab-decomposed fields, replicated particle state (replaces the Pstream::combineReduce call
+ * sites of particleCloud.C:201-264 and the decomposePar sub-meshes).  Order of calls on every
+ * rank: ibm_create(WHOLE mesh) -> ibm_set_slab -> ibm_comm_init -> ibm_set_particles(ALL particles).
+ * Cell fields handed to ibm_forcing / ibm_integrate_stress are then the rank's own z-planes [k0,k1). --- */
+int ibm_set_slab(ibm_ctx* ctx, int k0, int k1);
 int ibm_comm_unique_id_bytes(void);
-int ibm_comm_get_unique_id(void* idBytes);
-int ibm_comm_init(ibm_ctx* ctx, const void* idBytes, int rank, int nRanks);
+int ibm_comm_get_unique_id(void* idBytes);               /* rank 0; broadcast the bytes with the launcher's own transport */
+int ibm_comm_init(ibm_ctx* ctx, const void* idBytes, int rank, int nRanks);   /* NCCL, one process per GPU */
+int ibm_comm_info(ibm_ctx* ctx, int* rank, int* nRanks);
+/* in-process transport for tests: ranks are host threads, all contexts on one device */
+int ibm_comm_local_group_create(int nRanks, void** group);
+int ibm_comm_local_group_destroy(void* group);
+int ibm_comm_init_local(ibm_ctx* ctx, void* group, int rank);
 
 #ifdef __cplusplus
 }

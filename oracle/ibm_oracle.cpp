@@ -39,13 +39,13 @@ struct orc_instance_state {
 
 void* orc_mesh_create(int nx, int ny, int nz, const double* origin, const double* delta, int nBlocks,
                       const int* blocks, int nPatches, const int* patchSide, const int* patchType,
-                      const int* patchNeighb) {
+                      const int* patchNeighb, int kz0) {
   std::vector<BlockDesc> bl;
   for (int b = 0; b < nBlocks; ++b)
     bl.push_back({blocks[6 * b], blocks[6 * b + 1], blocks[6 * b + 2], blocks[6 * b + 3], blocks[6 * b + 4], blocks[6 * b + 5]});
   std::vector<int> ps(patchSide, patchSide + nPatches), pt(patchType, patchType + nPatches),
       pn(patchNeighb, patchNeighb + nPatches);
-  return buildMesh(nx, ny, nz, {origin[0], origin[1], origin[2]}, {delta[0], delta[1], delta[2]}, bl, ps, pt, pn);
+  return buildMesh(nx, ny, nz, {origin[0], origin[1], origin[2]}, {delta[0], delta[1], delta[2]}, bl, ps, pt, pn, kz0);
 }
 void orc_mesh_destroy(void* h) { delete (Mesh*)h; }
 int orc_mesh_ncells(void* h) { return ((Mesh*)h)->nCells; }

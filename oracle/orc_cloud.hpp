@@ -281,7 +281,7 @@ struct Shape {
     auto hi = [&](double c, double o, double dlt) { return (int)std::floor((c + R - o) / dlt) + 1; };
     int i0 = std::max(0, lo(center.x, m.origin.x, m.delta.x)), i1 = std::min(m.nx - 1, hi(center.x, m.origin.x, m.delta.x));
     int j0 = std::max(0, lo(center.y, m.origin.y, m.delta.y)), j1 = std::min(m.ny - 1, hi(center.y, m.origin.y, m.delta.y));
-    int k0 = std::max(0, lo(center.z, m.origin.z, m.delta.z)), k1 = std::min(m.nz - 1, hi(center.z, m.origin.z, m.delta.z));
+    int k0 = std::max(0, lo(center.z, m.origin.z, m.delta.z) - m.kz0), k1 = std::min(m.nz - 1, hi(center.z, m.origin.z, m.delta.z) - m.kz0);
     for (int K = k0; K <= k1; ++K)
       for (int J = j0; J <= j1; ++J)
         for (int I = i0; I <= i1; ++I) out.push_back(m.latticeToCell[m.lat(I, J, K)]);

@@ -44,6 +44,8 @@ struct Patch {
 
 struct Mesh {
   int nx = 0, ny = 0, nz = 0;
+  int kz0 = 0;  // slab of a decomposed mesh: global z-plane of local plane 0; geometry uses the global index
+                // (decomposePar keeps the global points, so processor-mesh cell centres equal the undecomposed ones)
   vec3 origin{0, 0, 0}, delta{1, 1, 1};
   int nCells = 0, nInternalFaces = 0;
   std::vector<vec3> C;        // cellCentres()
@@ -63,7 +65,7 @@ struct Mesh {
   int findCell(const vec3& p) const {
     double tx = std::floor((p.x - origin.x) / delta.x);
     double ty = std::floor((p.y - origin.y) / delta.y);
-    double tz = std::floor((p.z - origin.z) / delta.z);
+    double tz = std::floor((p.z - origin.z) / delta.z) - kz0;
     if (!(tx >= 0 && tx < nx && ty >= 0 && ty < ny && tz >= 0 && tz < nz)) return -1;
     return latticeToCell[lat((int)tx, (int)ty, (int)tz)];
   }
@@ -76,7 +78,7 @@ struct Mesh {
     int l = cellToLattice[celli];
     int I = l % nx, J = (l / nx) % ny, K = l / (nx * ny);
     return std::floor((p.x - origin.x) / delta.x) == I && std::floor((p.y - origin.y) / delta.y) == J &&
-           std::floor((p.z - origin.z) / delta.z) == K;
+           std::floor((p.z - origin.z) / delta.z) - kz0 == K;
   }
 
   // polyMesh::findCell as the reference calls it: nearest cell centre by linear scan (first
@@ -100,9 +102,9 @@ struct BlockDesc { int i0, i1, j0, j1, k0, k1; };
 
 inline Mesh* buildMesh(int nx, int ny, int nz, vec3 origin, vec3 delta, const std::vector<BlockDesc>& blocksIn,
                        const std::vector<int>& patchSide, const std::vector<int>& patchType,
-                       const std::vector<int>& patchNeighb) {
+                       const std::vector<int>& patchNeighb, int kz0 = 0) {
   Mesh* m = new Mesh;
-  m->nx = nx; m->ny = ny; m->nz = nz; m->origin = origin; m->delta = delta;
+  m->nx = nx; m->ny = ny; m->nz = nz; m->origin = origin; m->delta = delta; m->kz0 = kz0;
   std::vector<BlockDesc> blocks = blocksIn;
   if (blocks.empty()) blocks.push_back({0, nx, 0, ny, 0, nz});
   const int64_t n = (int64_t)nx * ny * nz;
@@ -124,10 +126,10 @@ inline Mesh* buildMesh(int nx, int ny, int nz, vec3 origin, vec3 delta, const st
   for (int c = 0; c < (int)n; ++c) {
     int l = m->cellToLattice[c];
     int I = l % nx, J = (l / nx) % ny, K = l / (nx * ny);
-    m->C[c] = {origin.x + (I + 0.5) * delta.x, origin.y + (J + 0.5) * delta.y, origin.z + (K + 0.5) * delta.z};
+    m->C[c] = {origin.x + (I + 0.5) * delta.x, origin.y + (J + 0.5) * delta.y, origin.z + (K + kz0 + 0.5) * delta.z};
   }
-  m->bbMin = origin;
-  m->bbMax = {origin.x + nx * delta.x, origin.y + ny * delta.y, origin.z + nz * delta.z};
+  m->bbMin = {origin.x, origin.y, origin.z + kz0 * delta.z};
+  m->bbMax = {origin.x + nx * delta.x, origin.y + ny * delta.y, origin.z + (kz0 + nz) * delta.z};
 
   // internal faces, upper-triangular order
   std::vector<std::vector<int>> nbrFaces(n);  // faces for which the cell is the neighbour
@@ -158,8 +160,8 @@ inline Mesh* buildMesh(int nx, int ny, int nz, vec3 origin, vec3 delta, const st
       if (d == 1) { cf.x = origin.x + I * delta.x;       sf.x = -(delta.y * delta.z); }
       if (d == 2) { cf.y = origin.y + (J + 1) * delta.y; sf.y = delta.x * delta.z; }
       if (d == 3) { cf.y = origin.y + J * delta.y;       sf.y = -(delta.x * delta.z); }
-      if (d == 4) { cf.z = origin.z + (K + 1) * delta.z; sf.z = delta.x * delta.y; }
-      if (d == 5) { cf.z = origin.z + K * delta.z;       sf.z = -(delta.x * delta.y); }
+      if (d == 4) { cf.z = origin.z + (K + kz0 + 1) * delta.z; sf.z = delta.x * delta.y; }
+      if (d == 5) { cf.z = origin.z + (K + kz0) * delta.z;     sf.z = -(delta.x * delta.y); }
       m->Cf.push_back(cf);
       m->Sf.push_back(sf);
       ownFaces[c].push_back(f);
@@ -206,7 +208,7 @@ inline Mesh* buildMesh(int nx, int ny, int nz, vec3 origin, vec3 delta, const st
         double sgn = hiSide ? 1.0 : -1.0;
         if (axis == 0) { cf.x = hiSide ? origin.x + nx * delta.x : origin.x; sf.x = sgn * (delta.y * delta.z); }
         if (axis == 1) { cf.y = hiSide ? origin.y + ny * delta.y : origin.y; sf.y = sgn * (delta.x * delta.z); }
-        if (axis == 2) { cf.z = hiSide ? origin.z + nz * delta.z : origin.z; sf.z = sgn * (delta.x * delta.y); }
+        if (axis == 2) { cf.z = hiSide ? origin.z + (kz0 + nz) * delta.z : origin.z + kz0 * delta.z; sf.z = sgn * (delta.x * delta.y); }
         pt.Cf.push_back(cf);
         pt.Sf.push_back(sf);
         pt.magSf.push_back(mag(sf));

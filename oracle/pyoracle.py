@@ -80,7 +80,7 @@ class OracleMesh:
         origin, delta = _c(spec.origin), _c(spec.delta)
         blocks = _c(blocks, np.int32)
         self.h = C.c_void_p(L.orc_mesh_create(spec.nx, spec.ny, spec.nz, _dp(origin), _dp(delta), blocks.shape[0],
-                                              _ip(blocks), pat.shape[0], _ip(side), _ip(typ), _ip(nb)))
+                                              _ip(blocks), pat.shape[0], _ip(side), _ip(typ), _ip(nb), int(getattr(spec, "kz0", 0))))
         self.n_cells = L.orc_mesh_ncells(self.h)
         self.n_internal_faces = L.orc_mesh_ninternal_faces(self.h)
 

@@ -1,0 +1,139 @@
+"""Multi-rank path (slab-decomposed fields, replicated particle state) on ONE GPU: ranks are host threads joined by
+the in-process transport; the checker is one oracle per slab (the decomposed reference semantics: shape points
+outside the local mesh contribute nothing, particleShape.C:45-47) plus the serial oracle for loop 5."""
+import threading
+
+import numpy as np
+import pytest
+
+from ibmfoam_b200 import cases
+from ibmfoam_b200.cloud import LocalGroup, ParticleCloud, slab_ranges
+from oracle.pyoracle import OracleCloud, OracleMesh
+import ibm_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_ranks(n_ranks, fn):
+    out, err = [None] * n_ranks, [None] * n_ranks
+
+    def work(r):
+        try:
+            out[r] = fn(r)
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n_ranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def _slab_case(case, k0, k1):
+    import copy
+    c = copy.copy(case)
+    c.mesh = case.mesh.slab(k0, k1)
+    return c
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_loops_1_to_4_match_decomposed_oracle(n_ranks):
+    case = cases.assembly(n=48, n_particles=70, seed=11, moving=True, cyclic_without_walls=True)
+    ranges = slab_ranges(case.mesh.nz, n_ranks)
+    f_lat = cases.synthetic_fields(case.mesh)
+    nxy = case.mesh.nx * case.mesh.ny
+    group = LocalGroup(n_ranks)
+    oracles = [OracleCloud(_slab_case(case, *ranges[r])) for r in range(n_ranks)]
+    FTo = []
+    for r, oc in enumerate(oracles):
+        k0, k1 = ranges[r]
+        sl = slice(k0 * nxy, k1 * nxy)
+        FTo.append(oc.integrate_stress(f_lat["p"][sl], f_lat["tau"][sl]))
+
+    def rank(r):
+        k0, k1 = ranges[r]
+        sl = slice(k0 * nxy, k1 * nxy)
+        gc = ParticleCloud(case, slab=(k0, k1), local_group=group.handle, rank=r)
+        oc = oracles[r]
+        sg, so = gc.state_arrays(), oc.state_arrays()
+        assert gc.nParticles() == case.particles.n  # replicated: every rank holds every instance
+        pos = {int(i): n for n, i in enumerate(sg["index"])}
+        # marking: every instance the decomposed reference keeps on this rank has the same shell here
+        for n_o, idx in enumerate(so["index"]):
+            g = pos[int(idx)]
+            a, b = oc.shell(n_o), gc.shell(g)
+            assert np.array_equal(a["cells"], b["cells"]) and np.array_equal(a["jk"], b["jk"])
+        absent = set(pos) - set(int(i) for i in so["index"])
+        assert all(sg["nShell"][pos[i]] == 0 for i in absent)
+        # forcing on the local planes
+        Fo, _ = oc.forcing(f_lat["U"][sl], f_lat["Uold"][sl], f_lat["S"][sl], case.dt)
+        Fg = gc.forcing(f_lat["S"][sl], f_lat["U"][sl], f_lat["Uold"][sl], case.dt)
+        assert util.rel_err(Fg, Fo) < 1e-12
+        # stress partials, then the cross-rank sum
+        FTg = gc.integrateSurfaceStresses(f_lat["p"][sl], f_lat["tau"][sl])
+        scale = max(np.max(np.abs(x)) for x in FTo)
+        for n_o, idx in enumerate(so["index"]):
+            assert np.max(np.abs(FTg[pos[int(idx)]] - FTo[r][n_o])) < 1e-10 * scale
+        for i in absent:
+            assert not np.any(FTg[pos[i]])
+        gc.combineForces()
+        tot = np.zeros((case.particles.n, 6))
+        for rr, o2 in enumerate(oracles):
+            for n_o, idx in enumerate(o2.state_arrays()["index"]):
+                tot[pos[int(idx)]] += FTo[rr][n_o]
+        st = gc.state_arrays()
+        got = np.concatenate([st["F"], st["T"]], axis=1)
+        assert np.max(np.abs(got - tot)) < 1e-10 * scale
+        res = (st["F"].copy(), st["T"].copy())
+        gc.close()
+        return res
+
+    res = _run_ranks(n_ranks, rank)
+    for r in range(1, n_ranks):  # identical bits on every rank (rank-ordered sum)
+        assert np.array_equal(res[0][0], res[r][0]) and np.array_equal(res[0][1], res[r][1])
+    group.close()
+
+
+def test_loop5_replicated_equals_serial_oracle():
+    """Loop 5 runs redundantly on every rank from identical state: trajectories, periodic copies and deletions are
+    those of the SERIAL reference (decomposition-independent), bit for bit, on every rank."""
+    n_ranks = 2
+    case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    case.particles.v *= 25.0
+    case.dt = 0.5
+    ranges = slab_ranges(case.mesh.nz, n_ranks)
+    group = LocalGroup(n_ranks)
+    oc = OracleCloud(case)
+    rng = np.random.default_rng(0)
+    FTs = [rng.normal(0, 1e-3, (400, 6)) for _ in range(3)]
+    ref = []
+    for s in range(3):
+        oc.set_force_torque(FTs[s][:oc.n_instances])
+        oc.combine_forces()
+        oc.advance(case.dt)
+        ref.append(oc.state_arrays())
+
+    def rank(r):
+        gc = ParticleCloud(case, slab=ranges[r], local_group=group.handle, rank=r)
+        for s in range(3):
+            # hand each rank 1/n of the total so that the all-reduce restores the serial value exactly (powers of two)
+            gc.set_force_torque(FTs[s][:gc.nParticles()] / n_ranks)
+            gc.combineForces()
+            gc.advance(case.dt)
+            sg = gc.state_arrays()
+            for k in ("index", "copy", "active", "onMesh"):
+                assert np.array_equal(sg[k], ref[s][k]), k
+            for k in ("center", "theta", "v", "omega"):
+                assert np.array_equal(sg[k], ref[s][k]), k
+        n = gc.nParticles()
+        gc.close()
+        return n
+
+    ns = _run_ranks(n_ranks, rank)
+    assert ns[0] == ns[1] == oc.n_instances and ns[0] != 60
+    group.close()
