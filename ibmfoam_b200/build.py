@@ -60,6 +60,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    # host-side C++ mirror of the reference class API: compile its driver against the C ABI (runs on the GPU box)
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(LIBDIR, "test_host_mirror")
+    srcs = [os.path.join(host, "test_host_mirror.cpp"), os.path.join(host, "particleCloud.H")]
+    if force or _stale(exe, srcs + [LIB]):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, srcs[0], "-L" + LIBDIR, "-libmfoam_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("host mirror driver failed to build")
     return LIB
 
 

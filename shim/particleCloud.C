@@ -1,0 +1,278 @@
+/*---------------------------------------------------------------------------*\
+  OpenFOAM-side binding of libibmfoam_b200 — see particleCloud.H.  Every member forwards to one C-ABI call
+  (include/ibmfoam_b200.h); OpenFOAM keeps the mesh, the fields, the PIMPLE loop and the linear solvers.
+\*---------------------------------------------------------------------------*/
+#include "particleCloud.H"
+
+namespace Foam
+{
+    defineTypeNameAndDebug(particleCloud, 0);
+}
+
+void Foam::particleCloud::check(const int rc, const char* where) const
+{
+    if (rc != IBM_OK)
+    {
+        FatalErrorInFunction
+            << where << ": " << ibm_last_error(ctx_) << exit(FatalError);
+    }
+}
+
+void Foam::particleCloud::describeMesh(ibm_mesh_desc& md, List<ibm_patch_desc>& pats, labelList& blocks) const
+{
+    // IBMProperties { lattice { n (nx ny nz); origin (x y z); delta (dx dy dz); blocks ((i0 i1 j0 j1 k0 k1) ...); } }
+    const dictionary& lat = dict_.subDict("lattice");
+    const labelVector n(lat.lookup("n"));
+    const vector origin(lat.lookup("origin")), delta(lat.lookup("delta"));
+    md.nx = n.x(); md.ny = n.y(); md.nz = n.z();
+    forAll(origin, d) { md.origin[d] = origin[d]; md.delta[d] = delta[d]; }
+    if (lat.found("blocks"))
+    {
+        List<labelList> b(lat.lookup("blocks"));
+        blocks.setSize(6*b.size());
+        forAll(b, i) forAll(b[i], j) blocks[6*i + j] = b[i][j];
+    }
+    md.nBlocks = blocks.size()/6;
+    md.blocks = blocks.size() ? blocks.begin() : nullptr;
+    md.latticeToCell = nullptr;
+
+    // boundary patches with their OpenFOAM face arrays (particleIBM.C:466-470, 504-508)
+    const fvBoundaryMesh& bm = mesh_.boundary();
+    pats.setSize(bm.size());
+    const wordList sides(lat.lookup("patchSides"));   // one of xMin xMax yMin yMax zMin zMax per patch
+    forAll(bm, patchi)
+    {
+        ibm_patch_desc& p = pats[patchi];
+        p.type =
+            isA<wallFvPatch>(bm[patchi]) ? IBM_WALL
+          : isA<cyclicFvPatch>(bm[patchi]) ? IBM_CYCLIC
+          : isA<processorFvPatch>(bm[patchi]) ? IBM_PROCESSOR
+          : isA<emptyFvPatch>(bm[patchi]) ? IBM_EMPTY : IBM_PATCH;
+        const word& s = sides[patchi];
+        p.side = s == "xMin" ? IBM_XMIN : s == "xMax" ? IBM_XMAX : s == "yMin" ? IBM_YMIN
+               : s == "yMax" ? IBM_YMAX : s == "zMin" ? IBM_ZMIN : IBM_ZMAX;
+        p.neighbPatch =
+            isA<cyclicFvPatch>(bm[patchi])
+          ? refCast<const cyclicPolyPatch>(mesh_.boundaryMesh()[patchi]).neighbPatchID() : -1;
+        p.nFaces = bm[patchi].size();
+        // Foam::vector is three contiguous doubles: the boundary fields can be passed as they are
+        p.Cf = reinterpret_cast<const double*>(mesh_.Cf().boundaryField()[patchi].begin());
+        p.Sf = reinterpret_cast<const double*>(mesh_.Sf().boundaryField()[patchi].begin());
+        p.magSf = mesh_.magSf().boundaryField()[patchi].begin();
+    }
+    md.nPatches = pats.size();
+    md.patches = pats.begin();
+}
+
+Foam::particleCloud::particleCloud
+(
+    const fvMesh& mesh,
+    const dictionary& dict,
+    const dimensionedVector& g
+)
+:
+    regIOobject(IOobject("IBMparticles", mesh.time().timeName(), "lagrangian", mesh, IOobject::NO_READ, IOobject::AUTO_WRITE)),
+    mesh_(mesh),
+    dict_(dict),
+    nParticles_(readLabel(dict_.lookup("nParticles"))),
+    UInf_(dict_.subDict("flow").lookupOrDefault<vector>("UInf", Zero)),
+    rhoRef_(dict_.subDict("flow").lookupOrDefault<scalar>("rhoInf", 1.0)),
+    pRef_(dict_.subDict("flow").lookupOrDefault<scalar>("pInf", 0.0)),
+    g_(g.value()),
+    e_(readScalar(dict_.lookup("e"))),
+    coupled_(dict_.lookup("coupled")),
+    moving_(dict_.lookup("moving")),
+    rotating_(dict_.lookup("rotating")),
+    I_(IOobject(IOobject::groupName("I", "ibm"), mesh.time().timeName(), mesh), mesh, dimensionedScalar("0", dimless, 0.0)),
+    ctx_(nullptr)
+{
+    ibm_mesh_desc md;
+    List<ibm_patch_desc> pats;
+    labelList blocks;
+    describeMesh(md, pats, blocks);
+
+    ibm_cloud_cfg cfg;
+    cfg.moving = moving_; cfg.rotating = rotating_; cfg.coupled = coupled_; cfg.e = e_;
+    forAll(UInf_, d) { cfg.UInf[d] = UInf_[d]; cfg.g[d] = g_[d]; }
+    cfg.rhoRef = rhoRef_; cfg.pRef = pRef_;
+    cfg.cyclicWithoutWalls = dict_.lookupOrDefault<Switch>("cyclicWithoutWalls", false);
+    cfg.maxInstances = dict_.lookupOrDefault<label>("maxInstances", 0);
+
+    const label device = dict_.lookupOrDefault<label>("device", Pstream::parRun() ? Pstream::myProcNo() % 8 : 0);
+    if (ibm_create(&md, &cfg, device, &ctx_) != IBM_OK)
+    {
+        FatalErrorInFunction << ibm_last_error(nullptr) << exit(FatalError);
+    }
+
+    // particle.<i> sub-dictionaries (reference particleCloud.C:1070-1117, particleIBM.C:269-297)
+    List<ibm_particle_init> init(nParticles_);
+    forAll(init, i)
+    {
+        const dictionary& pDict = dict_.subDict(IOobject::groupName("particle", Foam::name(i)));
+        ibm_particle_init& p = init[i];
+        const word shape(pDict.lookup("particleShape"));
+        p.kind = shape == "sphere" ? IBM_SPHERE : shape == "cylinder" ? IBM_CYLINDER : shape == "ellipse" ? IBM_ELLIPSE : -1;
+        const vector pos(pDict.lookup("position"));
+        const vector theta(pDict.lookupOrDefault<vector>("theta", Zero));
+        const vector v(pDict.lookupOrDefault<vector>("v", Zero));
+        const vector omega(pDict.lookupOrDefault<vector>("omega", Zero));
+        forAll(pos, d) { p.position[d] = pos[d]; p.theta[d] = theta[d]; p.v[d] = v[d]; p.omega[d] = omega[d]; }
+        p.d = pDict.lookupOrDefault<scalar>("d", 0.0);
+        p.a = pDict.lookupOrDefault<scalar>("a", 0.0);
+        p.b = pDict.lookupOrDefault<scalar>("b", 0.0);
+        p.nTheta = readLabel(pDict.lookup("nTheta"));
+        p.nk = pDict.lookupOrDefault<label>("nk", 1);
+        p.delta = readScalar(pDict.lookup("delta"));
+        p.rho = readScalar(pDict.lookup("rho"));
+    }
+    check(ibm_set_particles(ctx_, init.size(), init.begin()), "particleCloud");
+    check(ibm_get_indicator(ctx_, I_.primitiveFieldRef().begin()), "updateI");
+}
+
+Foam::particleCloud::~particleCloud()
+{
+    ibm_destroy(ctx_);
+}
+
+Foam::label Foam::particleCloud::nParticles() const
+{
+    int n = 0;
+    ibm_n_instances(ctx_, &n);
+    return n;
+}
+
+Foam::scalar Foam::particleCloud::maxCoNum() const
+{
+    double v = 0;
+    ibm_max_co_num(ctx_, &v);
+    return v;
+}
+
+Foam::tmp<Foam::volVectorField> Foam::particleCloud::forcing(const volVectorField& S)
+{
+    tmp<volVectorField> tmpF
+    (
+        new volVectorField
+        (
+            IOobject("F", mesh_.time().timeName(), mesh_, IOobject::NO_READ, IOobject::NO_WRITE, false),
+            mesh_,
+            dimensionedVector("F", dimForce/dimVolume/dimDensity, Zero)
+        )
+    );
+    if (!coupled_) return tmpF;
+
+    const volVectorField& U = mesh_.lookupObject<volVectorField>("U");
+    // Foam::vector is three contiguous doubles: internal fields are handed over without a copy
+    check
+    (
+        ibm_forcing
+        (
+            ctx_,
+            reinterpret_cast<const double*>(U.primitiveField().begin()),
+            reinterpret_cast<const double*>(U.oldTime().primitiveField().begin()),
+            reinterpret_cast<const double*>(S.primitiveField().begin()),
+            mesh_.time().deltaT().value(),
+            reinterpret_cast<double*>(tmpF.ref().primitiveFieldRef().begin())
+        ),
+        "forcing"
+    );
+    return tmpF;
+}
+
+void Foam::particleCloud::integrateSurfaceStresses()
+{
+    const volScalarField& p = mesh_.lookupObject<volScalarField>("p");
+    tmp<volSymmTensorField> tau(devRhoReff());
+    check
+    (
+        ibm_integrate_stress
+        (
+            ctx_,
+            p.primitiveField().begin(),
+            reinterpret_cast<const double*>(tau().primitiveField().begin()),
+            nullptr
+        ),
+        "integrateSurfaceStresses"
+    );
+}
+
+void Foam::particleCloud::Cd(IOField<scalar>& Cds) const
+{
+    Cds.setSize(nParticles());
+    ibm_cd(ctx_, Cds.begin());
+}
+
+void Foam::particleCloud::solve()
+{
+    const volScalarField& p = mesh_.lookupObject<volScalarField>("p");
+    tmp<volSymmTensorField> tau(devRhoReff());
+    ibm_solve_stats st;
+    check
+    (
+        ibm_solve
+        (
+            ctx_,
+            p.primitiveField().begin(),
+            reinterpret_cast<const double*>(tau().primitiveField().begin()),
+            mesh_.time().deltaT().value(),
+            &st
+        ),
+        "solve"
+    );
+    check(ibm_get_indicator(ctx_, I_.primitiveFieldRef().begin()), "updateI");
+    // the Info<< block of the reference (particleCloud.C:1317-1322)
+    Info<< "    Actual number of active particles: " << nParticles_ << nl
+        << "    Total number of solved particles: " << st.nInstances << nl
+        << "    Average velocity: " << vector(st.avgV[0], st.avgV[1], st.avgV[2]) << nl
+        << "    Average omega: " << vector(st.avgOmega[0], st.avgOmega[1], st.avgOmega[2]) << nl
+        << "    Average momentum: " << vector(st.avgP[0], st.avgP[1], st.avgP[2]) << nl
+        << "    total K: " << st.totK << endl;
+}
+
+void Foam::particleCloud::writeFields() const
+{
+    // lagrangian/IBMparticles/{index,copy,active,center,theta,v,omega,rho,age}  (reference particleIBMIO.C:58-108)
+    const label n = nParticles();
+    List<ibm_particle_state> st(n);
+    if (n) ibm_get_particles(ctx_, st.begin());
+    IOField<label> index(IOobject("index", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<label> copy(IOobject("copy", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<label> active(IOobject("active", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<vector> center(IOobject("center", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<vector> theta(IOobject("theta", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<vector> v(IOobject("v", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<vector> omega(IOobject("omega", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<scalar> rho(IOobject("rho", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    IOField<scalar> age(IOobject("age", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
+    forAll(st, i)
+    {
+        index[i] = st[i].index; copy[i] = st[i].copy; active[i] = st[i].active;
+        center[i] = vector(st[i].center[0], st[i].center[1], st[i].center[2]);
+        theta[i] = vector(st[i].theta[0], st[i].theta[1], st[i].theta[2]);
+        v[i] = vector(st[i].v[0], st[i].v[1], st[i].v[2]);
+        omega[i] = vector(st[i].omega[0], st[i].omega[1], st[i].omega[2]);
+        rho[i] = st[i].rho; age[i] = st[i].age;
+    }
+    index.write(); copy.write(); active.write(); center.write(); theta.write(); v.write(); omega.write();
+    rho.write(); age.write();
+}
+
+bool Foam::particleCloud::writeObject
+(
+    IOstream::streamFormat,
+    IOstream::versionNumber,
+    IOstream::compressionType,
+    const bool
+) const
+{
+    writeFields();
+    return true;
+}
+
+void Foam::particleCloud::readParticles()
+{
+    NotImplemented;  // restart from lagrangian/IBMparticles: SURVEY §8(f) row 1
+}
+
+// devRhoReff()/rho(): verbatim logic of the reference's private members (particleCloud.C:41-169) belongs here;
+// it only calls OpenFOAM (turbulence model / transport properties / fvc::grad) and is not part of the GPU path.
