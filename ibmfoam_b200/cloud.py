@@ -207,6 +207,9 @@ class ParticleCloud:
     def set_kernel_variant(self, forcing=1, stress=1):
         check(self._L.ibm_set_kernel_variant(self._h, int(forcing), int(stress)), self._h)
 
+    def set_option(self, name, value):
+        check(self._L.ibm_set_option(self._h, name.encode(), int(value)), self._h)
+
     def sync(self):
         check(self._L.ibm_sync(self._h), self._h)
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -406,6 +407,8 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   ibm_ctx* c = new ibm_ctx;
   c->device = device;
   c->cfg = *cfg;
+  if (const char* e = getenv("IBM_FUSED_LOOP5")) c->fusedLoop5 = std::atoi(e) != 0;  // developer switches (profiling)
+  if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
   if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
   LatticeDev& L = c->L;
   L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
@@ -910,6 +913,13 @@ int ibm_set_kernel_variant(ibm_ctx* c, int fv, int sv) {
   c->forcingVariant = fv;
   c->stressVariant = sv;
   return IBM_OK;
+}
+
+int ibm_set_option(ibm_ctx* c, const char* name, int value) {
+  if (!c || !name) return IBM_E_ARG;
+  if (std::strcmp(name, "fused_loop5") == 0) { c->fusedLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "graph_loop5") == 0) { c->graphLoop5 = value != 0; return IBM_OK; }
+  return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_option: unknown option ") + name);
 }
 
 int ibm_timings(ibm_ctx* c, ibm_timing* out) {

@@ -79,6 +79,8 @@ struct ibm_ctx {
   ibm::Schedule sched;
   int totalChunks = 0;
 
+  bool fusedLoop5 = false;  // one persistent cooperative kernel for the sub-step loop
+  bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph
   // motion (loop 5) scratch lives in ibm_motion.cu
   void* motion = nullptr;
   // comm

@@ -14,12 +14,15 @@
 // The reference keeps dense nParticles x nParticles force tables and visits all ordered pairs; here a uniform
 // cell list (bin edge >= largest diameter, fixed-capacity bins refilled every sub-step) yields the same
 // contact set, stored sparsely per instance and summed in partner-index order (the reference's sum() order).
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cmath>
 
 #include "ibm_ctx.h"
+
+namespace cg = cooperative_groups;
 
 namespace ibm {
 
@@ -31,6 +34,8 @@ struct PatchDev {
   int latticeOrdered;  // faces in transverse lattice order (fastest index first): candidate faces by index box
   int nA, nB;          // transverse extents
   double lo[3], hi[3]; // bounding box of the face centres (cheap rejection: |centre - Cf| >= distance to the box)
+  int planar;          // every face has bit-identical Sf and magSf: Sf/magSf is one vector for the whole patch
+  double nrm[3];       // that vector
 };
 
 struct MotionDev {
@@ -39,7 +44,9 @@ struct MotionDev {
   // cell list
   double bx0, by0, bz0, binEdge;
   int nbx, nby, nbz;
-  int binCap; int* binCnt; int* binItems;   // fixed-capacity cell list, rebuilt every sub-step
+  int binCap; int* binCnt; int* binItems; double* binPos;   // fixed-capacity cell list (entry = instance + its centre)
+  int* pairCount; int* pairI; int* pairJ; int pairCap;       // near-contact candidate pairs of the current sub-step
+  int* cPos;                                                 // cloud position of the partner behind each row entry
   unsigned* keys; unsigned* keysSorted; int* vals; int* valsSorted;  // scratch for the same-index list build
   // sparse contact tables (sorted by partner index)
   int* cCnt; int* cIdx; double* cF; double* cT;
@@ -53,7 +60,7 @@ struct MotionDev {
   const int* origCls; const double* origRho; int* maxCopies;
   // cyclic hits
   int* candCount; int* candKey; int candCap;      // (patch, instance) pairs within reach of a cyclic patch
-  int* hitCount; int* hitKey; double* hitCenter;  // compact list of new periodic copies (key = patchSlot*cap + instance)
+  int* hitCount; int* hitKey; double* hitCenter; int* blocksDone;  // compact list of new periodic copies (key = patchSlot*cap + instance)
   const PatchDev* patches; const int* wallPatch; const int* cycPatch;
   double gx, gy, gz, e;
   int moving, rotating;
@@ -66,6 +73,12 @@ struct Motion {
   size_t cubTempBytes = 0;
   PatchDev* dPatches = nullptr;
   bool groupsValid = false;
+  double* dDts = nullptr;
+  int fusedBlocks = 0;
+  // CUDA graph of the unfused sub-step sequence, cached for one schedule of local time steps
+  cudaGraphExec_t graphExec = nullptr;
+  std::vector<double> graphDts;
+  long long graphLaunches = 0;
   int* dIdxKeys = nullptr; int* dIdxKeys2 = nullptr;
   double* dStats = nullptr;
 };
@@ -198,101 +211,130 @@ __device__ __forceinline__ void bin_of(const MotionDev& m, D3 c, int& bx, int& b
   bz = min(max((int)floor((c.z - m.bz0) / m.binEdge), 0), m.nbz - 1);
 }
 
-__global__ void k5_bin(MotionDev m, InstanceSoA in) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_bin(MotionDev m, InstanceSoA in, int i) {
   if (i >= *m.nInst || in.onMesh[i] == 0) return;
   int bx, by, bz;
-  bin_of(m, ld3(in.c, i), bx, by, bz);
+  const D3 c = ld3(in.c, i);
+  bin_of(m, c, bx, by, bz);
   int b = bx + m.nbx * (by + m.nby * bz);
   int slot = atomicAdd(&m.binCnt[b], 1);
-  if (slot < m.binCap) m.binItems[(size_t)b * m.binCap + slot] = i;
-  else atomicExch(m.overflow, 3);
+  if (slot < m.binCap) {
+    const size_t o = (size_t)b * m.binCap + slot;
+    m.binItems[o] = i;
+    m.binPos[3 * o] = c.x; m.binPos[3 * o + 1] = c.y; m.binPos[3 * o + 2] = c.z;  // centre travels with the bin entry
+  } else atomicExch(m.overflow, 3);
 }
 
-// particleCloud::computeCollisions, pair part (particleCloud.C:484-523).  Thread i builds its own sparse row
-// collisionForces_[.] by evaluating every pair it takes part in exactly as the reference would (as p1 when its
-// index is the larger one, as p2 otherwise).  Duplicate partner indices (periodic copies): the last write in
-// the reference's loop order wins == the partner with the largest cloud position.
-__global__ void k5_contacts(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *m.nInst) return;
-  int cnt = 0;
-  int eIdx[CONTACT_CAP], ePos[CONTACT_CAP];
-  D3 eF[CONTACT_CAP], eT[CONTACT_CAP];
-  if (in.onMesh[i] != 0) {
-    const ShapeClassDev* sci = classes + in.cls[i];
-    PView me{ld3(in.c, i), classD(*sci), in.th[2][i], in.rot + 9 * (size_t)i, sci};
-    const D3 vi = ld3(in.v, i);
-    const double mi = sci->V * in.rho[i];
-    const int idxI = in.index[i];
-    int bx, by, bz;
-    bin_of(m, me.c, bx, by, bz);
-    for (int dz = -1; dz <= 1; ++dz) {
-      int z = bz + dz;
-      if (z < 0 || z >= m.nbz) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
-        int y = by + dy;
-        if (y < 0 || y >= m.nby) continue;
-        for (int x = max(bx - 1, 0); x <= min(bx + 1, m.nbx - 1); ++x) {
+// particleCloud::computeCollisions, pair part (particleCloud.C:484-523), in three light phases:
+//   d5_find_pairs   thread per instance: 27-bin neighbourhood, centre-distance rejection -> (i, j) candidate list
+//                   (the reference's early-out, particleIBM.C:56-59, fails for every pair farther apart than the
+//                   largest diameter == bin edge, so the list holds little more than the actual contacts);
+//   d5_pair_force   thread per candidate: the pair exactly as the reference evaluates it (instance i builds ITS
+//                   row: as p1 when its index is the larger one, as p2 otherwise) -> appended to row i;
+//   d5_rows_finish  thread per instance with more than one entry: duplicate partner indices (periodic copies) keep
+//                   the entry written last in the reference's loop order (largest cloud position of the partner),
+//                   then sort by partner index (sum(collisionForces_) order, particleIBM.C:408-411).
+__device__ __forceinline__ void d5_find_pairs(MotionDev m, InstanceSoA in, int t) {
+  // three threads per instance: one per z-layer of the 27-bin neighbourhood
+  const int i = t / 3, dz0 = t % 3 - 1;
+  if (i >= *m.nInst || in.onMesh[i] == 0) return;
+  const D3 c = ld3(in.c, i);
+  int bx, by, bz;
+  bin_of(m, c, bx, by, bz);
+  const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
+  for (int dz = dz0; dz <= dz0; ++dz) {
+    const int z = bz + dz;
+    if (z < 0 || z >= m.nbz) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = by + dy;
+      if (y < 0 || y >= m.nby) continue;
+      for (int x = max(bx - 1, 0); x <= min(bx + 1, m.nbx - 1); ++x) {
         const int bin = x + m.nbx * (y + m.nby * z);
         const int nb = min(m.binCnt[bin], m.binCap);
         for (int q = 0; q < nb; ++q) {
-          int j = m.binItems[(size_t)bin * m.binCap + q];
+          const size_t o = (size_t)bin * m.binCap + q;
+          const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+          if (ddx * ddx + ddy * ddy + ddz * ddz > cut) continue;
+          const int j = m.binItems[o];
           if (j == i) continue;
-          {
-            // cheap rejection on the centres alone: the reference's early-out (particleIBM.C:56-59) fails for every
-            // pair farther apart than the largest diameter (== bin edge), evaluated with a safety factor
-            double ddx = in.c[0][j] - me.c.x, ddy = in.c[1][j] - me.c.y, ddz = in.c[2][j] - me.c.z;
-            if (ddx * ddx + ddy * ddy + ddz * ddz > m.binEdge * m.binEdge * (1.0 + 1e-9)) continue;
-          }
-          const int idxJ = in.index[j];
-          if (idxJ == idxI || in.onMesh[j] == 0) continue;
-          const ShapeClassDev* scj = classes + in.cls[j];
-          PView other{ld3(in.c, j), classD(*scj), in.th[2][j], in.rot + 9 * (size_t)j, scj};
-          const D3 vj = ld3(in.v, j);
-          const double mj = scj->V * in.rho[j];
-          const bool iAmP1 = idxI > idxJ;
-          const PView& p1 = iAmP1 ? me : other;
-          const PView& p2 = iAmP1 ? other : me;
-          D3 x12 = p1.c - p2.c;
-          D3 v12 = iAmP1 ? (vi - vj) : (vj - vi);
-          D3 hitPt{0, 0, 0};
-          if (!pair_collision(p1, p2, hitPt)) continue;
-          if (!(dot3(x12, v12) < 0)) continue;
-          double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
-          double M = mass1 * mass2 / (mass1 + mass2);
-          double x12Dotv12 = dot3(x12, v12);
-          double x12Sqr = magSqr3(x12);
-          D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
-          D3 myF = iAmP1 ? -F : F;
-          D3 myT = iAmP1 ? cross3(-F, hitPt) : cross3(F, hitPt);
-          int slot = -1;
-          for (int t = 0; t < cnt; ++t) if (eIdx[t] == idxJ) slot = t;
-          if (slot < 0) {
-            if (cnt >= CONTACT_CAP) { atomicExch(m.overflow, 1); continue; }
-            slot = cnt++;
-            eIdx[slot] = idxJ; ePos[slot] = -1;
-          }
-          if (j > ePos[slot]) { ePos[slot] = j; eF[slot] = myF; eT[slot] = myT; }
-        }
+          const int h = atomicAdd(m.pairCount, 1);
+          if (h < m.pairCap) { m.pairI[h] = i; m.pairJ[h] = j; }
+          else atomicExch(m.overflow, 5);
         }
       }
     }
   }
-  // sort by partner index (sum(collisionForces_) runs over the table in index order, particleIBM.C:408-411)
+}
+
+__device__ __forceinline__ void d5_pair_force(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT, int h) {
+  if (h >= min(*m.pairCount, m.pairCap)) return;
+  const int i = m.pairI[h], j = m.pairJ[h];
+  const int idxI = in.index[i], idxJ = in.index[j];
+  if (idxJ == idxI || in.onMesh[j] == 0) return;  // particleCloud.C:502
+  const ShapeClassDev* sci = classes + in.cls[i];
+  const ShapeClassDev* scj = classes + in.cls[j];
+  PView me{ld3(in.c, i), classD(*sci), in.th[2][i], in.rot + 9 * (size_t)i, sci};
+  PView other{ld3(in.c, j), classD(*scj), in.th[2][j], in.rot + 9 * (size_t)j, scj};
+  const D3 vi = ld3(in.v, i), vj = ld3(in.v, j);
+  const double mi = sci->V * in.rho[i], mj = scj->V * in.rho[j];
+  const bool iAmP1 = idxI > idxJ;
+  const PView& p1 = iAmP1 ? me : other;
+  const PView& p2 = iAmP1 ? other : me;
+  D3 x12 = p1.c - p2.c;
+  D3 v12 = iAmP1 ? (vi - vj) : (vj - vi);
+  D3 hitPt{0, 0, 0};
+  if (!pair_collision(p1, p2, hitPt)) return;
+  if (!(dot3(x12, v12) < 0)) return;
+  double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
+  double M = mass1 * mass2 / (mass1 + mass2);
+  double x12Dotv12 = dot3(x12, v12);
+  double x12Sqr = magSqr3(x12);
+  D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
+  D3 myF = iAmP1 ? -F : F;
+  D3 myT = iAmP1 ? cross3(-F, hitPt) : cross3(F, hitPt);
+  const int slot = atomicAdd(&m.cCnt[i], 1);
+  if (slot >= CONTACT_CAP) { atomicExch(m.overflow, 1); return; }
+  const size_t o = (size_t)i * CONTACT_CAP + slot;
+  m.cIdx[o] = idxJ;
+  m.cPos[o] = j;
+  m.cF[3 * o] = myF.x; m.cF[3 * o + 1] = myF.y; m.cF[3 * o + 2] = myF.z;
+  m.cT[3 * o] = myT.x; m.cT[3 * o + 1] = myT.y; m.cT[3 * o + 2] = myT.z;
+}
+
+__device__ __forceinline__ void d5_rows_finish(MotionDev m, InstanceSoA in, int i) {
+  if (i >= *m.nInst) return;
+  int cnt = min(m.cCnt[i], CONTACT_CAP);
+  if (cnt < 2) { if (m.cCnt[i] > CONTACT_CAP) m.cCnt[i] = CONTACT_CAP; return; }
+  const size_t r0 = (size_t)i * CONTACT_CAP;
+  // duplicates of one partner index: keep the entry of the partner latest in cloud order
+  for (int a = 0; a < cnt; ++a)
+    for (int b2 = a + 1; b2 < cnt;) {
+      if (m.cIdx[r0 + b2] == m.cIdx[r0 + a]) {
+        const int keep = m.cPos[r0 + b2] > m.cPos[r0 + a] ? b2 : a;
+        if (keep == b2) {
+          m.cPos[r0 + a] = m.cPos[r0 + b2];
+          for (int q = 0; q < 3; ++q) { m.cF[3 * (r0 + a) + q] = m.cF[3 * (r0 + b2) + q]; m.cT[3 * (r0 + a) + q] = m.cT[3 * (r0 + b2) + q]; }
+        }
+        --cnt;  // move the last entry into b2
+        m.cIdx[r0 + b2] = m.cIdx[r0 + cnt]; m.cPos[r0 + b2] = m.cPos[r0 + cnt];
+        for (int q = 0; q < 3; ++q) { m.cF[3 * (r0 + b2) + q] = m.cF[3 * (r0 + cnt) + q]; m.cT[3 * (r0 + b2) + q] = m.cT[3 * (r0 + cnt) + q]; }
+      } else ++b2;
+    }
+  // insertion sort by partner index
   for (int a = 1; a < cnt; ++a) {
-    int ki = eIdx[a]; D3 f = eF[a], t = eT[a];
-    int b = a - 1;
-    while (b >= 0 && eIdx[b] > ki) { eIdx[b + 1] = eIdx[b]; eF[b + 1] = eF[b]; eT[b + 1] = eT[b]; --b; }
-    eIdx[b + 1] = ki; eF[b + 1] = f; eT[b + 1] = t;
+    const int ki = m.cIdx[r0 + a], kp = m.cPos[r0 + a];
+    double f[3], t[3];
+    for (int q = 0; q < 3; ++q) { f[q] = m.cF[3 * (r0 + a) + q]; t[q] = m.cT[3 * (r0 + a) + q]; }
+    int b2 = a - 1;
+    while (b2 >= 0 && m.cIdx[r0 + b2] > ki) {
+      m.cIdx[r0 + b2 + 1] = m.cIdx[r0 + b2]; m.cPos[r0 + b2 + 1] = m.cPos[r0 + b2];
+      for (int q = 0; q < 3; ++q) { m.cF[3 * (r0 + b2 + 1) + q] = m.cF[3 * (r0 + b2) + q]; m.cT[3 * (r0 + b2 + 1) + q] = m.cT[3 * (r0 + b2) + q]; }
+      --b2;
+    }
+    m.cIdx[r0 + b2 + 1] = ki; m.cPos[r0 + b2 + 1] = kp;
+    for (int q = 0; q < 3; ++q) { m.cF[3 * (r0 + b2 + 1) + q] = f[q]; m.cT[3 * (r0 + b2 + 1) + q] = t[q]; }
   }
   m.cCnt[i] = cnt;
-  for (int a = 0; a < cnt; ++a) {
-    size_t o = (size_t)i * CONTACT_CAP + a;
-    m.cIdx[o] = eIdx[a];
-    m.cF[3 * o] = eF[a].x; m.cF[3 * o + 1] = eF[a].y; m.cF[3 * o + 2] = eF[a].z;
-    m.cT[3 * o] = eT[a].x; m.cT[3 * o + 1] = eT[a].y; m.cT[3 * o + 2] = eT[a].z;
-  }
 }
 
 // particleIBM::wallHit for every wall slot (particleIBM.C:453-488, particleCloud.C:591-597)
@@ -313,8 +355,7 @@ __device__ __forceinline__ bool patch_in_reach(const PatchDev& p, D3 c, double r
   return dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300;
 }
 
-__global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt, int i) {
   if (i >= *m.nInst) return;
   if (in.onMesh[i] == 0) return;
   const ShapeClassDev* sc = classes + in.cls[i];
@@ -354,8 +395,7 @@ __global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeC
 // Copies of one index share the larger-magnitude entry (particleCloud.C:525-554, 599-620).  The reference's
 // in-place pair sweep leaves every member of a same-index group with the entry of largest magnitude, ties going
 // to the member latest in cloud order; evaluated here per instance from the pre-merge tables (double buffered).
-__global__ void k5_merge(MotionDev m, InstanceSoA in) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_merge(MotionDev m, InstanceSoA in, int i) {
   if (i >= *m.nInst) return;
   const int idx = in.index[i];
   const int head = m.idxHead[idx];
@@ -414,8 +454,7 @@ __global__ void k5_merge(MotionDev m, InstanceSoA in) {
 
 // particleIBM::patchHit + found() for every (cyclic patch, instance)   particleIBM.C:490-517, particleCloud.C:447-479, 685-730
 // stage 1: (patch, instance) pairs whose centre is within reach of the patch
-__global__ void k5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int i) {
   if (i >= *m.nInst || in.onMesh[i] == 0) return;
   const D3 c = ld3(in.c, i);
   const double r = classes[in.cls[i]].Rbound;
@@ -423,6 +462,10 @@ __global__ void k5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeCla
     const PatchDev& p = m.patches[m.cycPatch[slot]];
     if (p.type != IBM_CYCLIC) continue;  // processor patches are handled by the slab exchange, not here
     if (!patch_in_reach(p, c, r)) continue;
+    if (p.planar) {  // patchHit needs (v & norm) > 0 for the hit face (particleIBM.C:511): same test, once per patch
+      const D3 v = ld3(in.v, i);
+      if (!(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
+    }
     int h = atomicAdd(m.candCount, 1);
     if (h < m.candCap) m.candKey[h] = slot * m.cap + i;
     else atomicExch(m.overflow, 4);
@@ -431,10 +474,11 @@ __global__ void k5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeCla
 
 // stage 2: one warp per candidate; lanes scan the candidate faces in patch order, the first qualifying face
 // (lowest position in that order) is the reference's patchHit() result.
-__global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+__device__ __forceinline__ void d5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes,
+                                                 int tid, int nth) {
   const int lane = threadIdx.x & 31;
   const int nCand = min(*m.candCount, m.candCap);
-  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nCand; w += (gridDim.x * blockDim.x) >> 5) {
+  for (int w = tid >> 5; w < nCand; w += nth >> 5) {
     const int key = m.candKey[w];
     const int slot = key / m.cap, i = key % m.cap;
     const PatchDev& p = m.patches[m.cycPatch[slot]];
@@ -486,12 +530,12 @@ __global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, cons
 // append the new periodic copies in the reference's order (patch-major, cloud order within a patch):
 // particleIBM copy constructor (particleIBM.C:318-350) from origParticles_[index]   particleCloud.C:815-832.
 // The hit list is unordered (atomics); each hit finds its rank by counting smaller keys.
-__global__ void k5_append(MotionDev m, InstanceSoA in) {
+__device__ __forceinline__ void d5_append(MotionDev m, InstanceSoA in, int tid, int nth) {
   const int total = *m.hitCount;
   if (total == 0) return;
   const int n0 = *m.nInst;
-  if (total > m.cap - n0) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(m.overflow, 2); return; }
-  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < total; h += gridDim.x * blockDim.x) {
+  if (total > m.cap - n0) { if (tid == 0) atomicExch(m.overflow, 2); return; }
+  for (int h = tid; h < total; h += nth) {
     const int key = m.hitKey[h];
     int rank = 0;
     for (int q = 0; q < total; ++q) rank += m.hitKey[q] < key;
@@ -526,8 +570,7 @@ __global__ void k5_append(MotionDev m, InstanceSoA in) {
 }
 
 // sequential part of the append: copy ids (maxCopies_[index]+1, ++) and the same-index lists, in append order
-__global__ void k5_append_link(MotionDev m, InstanceSoA in) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void d5_append_link(MotionDev m, InstanceSoA in) {
   *m.candCount = 0;
   const int total = *m.hitCount;
   if (total == 0) return;
@@ -548,9 +591,8 @@ __global__ void k5_append_link(MotionDev m, InstanceSoA in) {
 }
 
 // particleIBM::solve(dt, g, moving, rotation)   particleIBM.C:393-450
-__global__ void k5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt,
-                         const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA, int* cCntB) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt,
+                         const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA, int* cCntB, int i) {
   if (i >= *m.nInst) return;
   if (in.onMesh[i] == 0) return;
   const ShapeClassDev* sc = classes + in.cls[i];
@@ -601,8 +643,7 @@ __global__ void k5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeC
 
 // particleCloud::setPositions, serial branch (particleCloud.C:411-443): processed in cloud order, every inactive
 // instance pushes its theta/v/omega to the other copies of its index.
-__global__ void k5_set_positions(MotionDev m, InstanceSoA in) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d5_set_positions(MotionDev m, InstanceSoA in, int idx) {
   if (idx >= m.nParticles) return;
   int head = m.idxHead[idx];
   if (head < 0 || m.instNext[head] < 0) return;  // single instance: nothing to copy
@@ -612,6 +653,139 @@ __global__ void k5_set_positions(MotionDev m, InstanceSoA in) {
     int cp = in.copy[p];
     for (int p2 = head; p2 >= 0; p2 = m.instNext[p2])
       if (in.copy[p2] != cp) { st3(in.th, p2, th); st3(in.v, p2, v); st3(in.om, p2, om); }
+  }
+}
+
+__global__ void k5_bin(MotionDev m, InstanceSoA in) {
+  d5_bin(m, in, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_bin_cand(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int doCyclic) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  d5_bin(m, in, i);
+  if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
+}
+__global__ void k5_find_pairs(MotionDev m, InstanceSoA in) { d5_find_pairs(m, in, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void k5_pair_force(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT) {
+  d5_pair_force(m, in, classes, deltaT, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void k5_rows_finish(MotionDev m, InstanceSoA in) {
+  d5_rows_finish(m, in, blockIdx.x * blockDim.x + threadIdx.x);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *m.pairCount = 0;  // pair_force is done: ready for the next sub-step
+}
+__global__ void k5_solve_clear(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt,
+                               const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA,
+                               int* cCntB) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  d5_solve(m, L, in, classes, dt, cCnt, cIdx, cF, cT, Fw, Tw, cCntA, cCntB, i);
+  const int nBins = m.nbx * m.nby * m.nbz;
+  for (int b = i; b < nBins; b += gridDim.x * blockDim.x) m.binCnt[b] = 0;  // contacts are done: bins ready for the next sub-step
+}
+// append + its sequential tail in one launch: the block that finishes last links the new instances
+__global__ void k5_append_all(MotionDev m, InstanceSoA in) {
+  __shared__ int last;
+  d5_append(m, in, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(m.blocksDone, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *m.blocksDone = 0;
+    __threadfence();
+    d5_append_link(m, in);
+  }
+}
+
+__global__ void k5_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
+  d5_walls(m, L, in, classes, dt, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_merge(MotionDev m, InstanceSoA in) {
+  d5_merge(m, in, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_cyclic_candidates(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  d5_cyclic_candidates(m, in, classes, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_solve(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt, const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA, int* cCntB) {
+  d5_solve(m, L, in, classes, dt, cCnt, cIdx, cF, cT, Fw, Tw, cCntA, cCntB, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_set_positions(MotionDev m, InstanceSoA in) {
+  d5_set_positions(m, in, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  d5_cyclic_detect(m, L, in, classes, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void k5_append(MotionDev m, InstanceSoA in) { d5_append(m, in, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void k5_append_link(MotionDev m, InstanceSoA in) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) d5_append_link(m, in);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole sub-step loop of particleCloud::solve (particleCloud.C:1251-1275) as ONE persistent cooperative
+// kernel: phases are separated by grid-wide barriers instead of kernel launches (the unfused sequence above
+// costs ~8 launches x 100 sub-steps per fluid step and was launch-bound).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k5_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
+         int doCyclic) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nBins = m.nbx * m.nby * m.nbz;
+  const bool copies = m.nCyc > 0;
+  for (int s = 0; s < nSub; ++s) {
+    const double dt = dts[s];
+    if (m.moving) {
+      int n = *m.nInst;  // only the link phase changes it, and a grid barrier follows
+      for (int i = tid; i < n; i += nth) d5_bin(m, in, i);
+      grid.sync();
+      for (int t = tid; t < 3 * n; t += nth) d5_find_pairs(m, in, t);
+      for (int i = tid; i < n; i += nth) {
+        if (m.nWalls > 0) d5_walls(m, L, in, classes, dt, i);
+        if (copies && doCyclic) d5_cyclic_candidates(m, in, classes, i);
+      }
+      grid.sync();
+      {
+        const int np = min(*m.pairCount, m.pairCap);
+        for (int h = tid; h < np; h += nth) d5_pair_force(m, in, classes, dt, h);
+      }
+      grid.sync();
+      for (int i = tid; i < n; i += nth) d5_rows_finish(m, in, i);
+      if (tid == 0) *m.pairCount = 0;
+      grid.sync();
+      if (copies) {
+        for (int i = tid; i < n; i += nth) d5_merge(m, in, i);
+        if (doCyclic) d5_cyclic_detect(m, L, in, classes, tid, nth);
+        grid.sync();
+        if (doCyclic) {
+          const int total = *m.hitCount;  // complete after the barrier, identical for every thread
+          if (total > 0) {
+            d5_append(m, in, tid, nth);
+            grid.sync();
+            if (tid == 0) d5_append_link(m, in);
+            grid.sync();
+          } else if (tid == 0) {
+            *m.candCount = 0;
+          }
+        }
+      }
+    }
+    {
+      const int n = *m.nInst;
+      const int* cCnt = copies ? m.cCnt2 : m.cCnt;
+      for (int i = tid; i < n; i += nth)
+        d5_solve(m, L, in, classes, dt, cCnt, copies ? m.cIdx2 : m.cIdx, copies ? m.cF2 : m.cF, copies ? m.cT2 : m.cT,
+                 copies ? m.Fw2 : m.Fw, copies ? m.Tw2 : m.Tw, m.cCnt, m.cCnt2, i);
+      for (int b = tid; b < nBins; b += nth) m.binCnt[b] = 0;  // contacts are done: ready for the next sub-step
+    }
+    grid.sync();
+    if (copies) {
+      for (int idx = tid; idx < m.nParticles; idx += nth) d5_set_positions(m, in, idx);
+      grid.sync();
+    }
   }
 }
 
@@ -715,6 +889,7 @@ static int motion_init(ibm_ctx* c) {
   }
   const size_t cap = (size_t)c->cap;
   d.candCap = (int)(3 * cap);
+  d.pairCap = (int)(16 * cap);
   bool ok = dalloc(c, M, &d.nInst, 1) && dalloc(c, M, &d.keys, cap) && dalloc(c, M, &d.keysSorted, cap) && dalloc(c, M, &d.vals, cap) &&
             dalloc(c, M, &d.valsSorted, cap) && dalloc(c, M, &d.cCnt, cap) && dalloc(c, M, &d.cIdx, cap * CONTACT_CAP) &&
             dalloc(c, M, &d.cF, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cT, 3 * cap * CONTACT_CAP) && dalloc(c, M, &d.cCnt2, cap) &&
@@ -723,10 +898,12 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.Tw, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.Fw2, 3 * cap * std::max(1, d.nWalls)) &&
             dalloc(c, M, &d.Tw2, 3 * cap * std::max(1, d.nWalls)) && dalloc(c, M, &d.idxHead, (size_t)std::max(1, c->nParticles)) &&
             dalloc(c, M, &d.idxTail, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.instNext, cap) &&
-            dalloc(c, M, &d.maxCopies, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.hitCount, 1) && dalloc(c, M, &d.candCount, 1) &&
+            dalloc(c, M, &d.maxCopies, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &d.hitCount, 1) && dalloc(c, M, &d.blocksDone, 1) && dalloc(c, M, &d.candCount, 1) &&
             dalloc(c, M, &d.candKey, 3 * cap) &&
             dalloc(c, M, &d.hitKey, cap) && dalloc(c, M, &d.hitCenter, 3 * cap) &&
             dalloc(c, M, &d.binCnt, (size_t)d.nbx * d.nby * d.nbz) && dalloc(c, M, &d.binItems, (size_t)d.nbx * d.nby * d.nbz * d.binCap) &&
+            dalloc(c, M, &d.binPos, (size_t)3 * d.nbx * d.nby * d.nbz * d.binCap) && dalloc(c, M, &d.pairCount, 1) &&
+            dalloc(c, M, &d.pairI, (size_t)d.pairCap) && dalloc(c, M, &d.pairJ, (size_t)d.pairCap) && dalloc(c, M, &d.cPos, cap * CONTACT_CAP) &&
             dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16);
   if (!ok) return IBM_E_CUDA;
   // originals
@@ -757,6 +934,11 @@ static int motion_init(ibm_ctx* c) {
     for (int a = 0; a < 3; ++a) { q.lo[a] = 1e300; q.hi[a] = -1e300; }
     for (int f = 0; f < q.nFaces; ++f)
       for (int a = 0; a < 3; ++a) { q.lo[a] = std::min(q.lo[a], ph.Cf[3 * (size_t)f + a]); q.hi[a] = std::max(q.hi[a], ph.Cf[3 * (size_t)f + a]); }
+    q.planar = q.nFaces > 0 ? 1 : 0;
+    for (int f = 1; f < q.nFaces && q.planar; ++f)
+      if (ph.Sf[3 * (size_t)f] != ph.Sf[0] || ph.Sf[3 * (size_t)f + 1] != ph.Sf[1] || ph.Sf[3 * (size_t)f + 2] != ph.Sf[2] ||
+          ph.magSf[f] != ph.magSf[0]) q.planar = 0;
+    for (int a = 0; a < 3; ++a) q.nrm[a] = q.nFaces > 0 ? ph.Sf[a] / ph.magSf[0] : 0.0;
     q.latticeOrdered = 0;
     if (q.nFaces == q.nA * q.nB) {
       const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz};
@@ -781,6 +963,14 @@ static int motion_init(ibm_ctx* c) {
   size_t b2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b2, M->dIdxKeys, M->dIdxKeys2, d.vals, d.valsSorted, c->cap);
   M->cubTempBytes = b2 + 256;
+  if (!dalloc(c, M, &M->dDts, 256)) return IBM_E_CUDA;
+  {
+    int perSm = 0, sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_fused, 256, 0) == cudaSuccess && perSm > 0)
+      M->fusedBlocks = sms * std::min(perSm, 4);
+  }
   if (!ctx_cuda_ok(c, cudaMalloc(&M->cubTemp, M->cubTempBytes), "cudaMalloc(cub)")) return IBM_E_CUDA;
   return IBM_OK;
 }
@@ -845,31 +1035,30 @@ static int substep_launch(ibm_ctx* c, double localDt) {
   cudaStream_t st = c->stream;
   const int cap = c->cap;
   const bool copiesPossible = d.nCyc > 0;
+  const bool doCyclic = copiesPossible && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls);  // App. B #10
   const int* cCnt = d.cCnt; const int* cIdx = d.cIdx; const double* cF = d.cF; const double* cT = d.cT;
   double* Fw = d.Fw; double* Tw = d.Tw;
   if (c->cfg.moving) {
-    // computeCollisions
-    cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
-    k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
-    k5_contacts<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
-    c->nLaunch += 3;
+    // computeCollisions (bins are cleared by the previous k5_solve_clear / by ensure_bins_clear)
+    k5_bin_cand<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, doCyclic ? 1 : 0);
+    k5_find_pairs<<<blocks_for(3 * cap), 128, 0, st>>>(d, c->in);
+    k5_pair_force<<<blocks_for(std::min(d.pairCap, 4 * c->nInst + 1024), 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
+    k5_rows_finish<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
+    c->nLaunch += 4;
     // computeWallHits
     if (d.nWalls > 0) { k5_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt); c->nLaunch++; }
     if (copiesPossible) {
       k5_merge<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in);
       c->nLaunch++;
       cCnt = d.cCnt2; cIdx = d.cIdx2; cF = d.cF2; cT = d.cT2; Fw = d.Fw2; Tw = d.Tw2;
-      // computeCyclicHits (App. B #10: as coded it returns when the mesh has no wall patch)
-      if (d.nWalls > 0 || c->cfg.cyclicWithoutWalls) {
-        k5_cyclic_candidates<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+      if (doCyclic) {  // computeCyclicHits
         k5_cyclic_detect<<<148, 256, 0, st>>>(d, c->Lg, c->in, c->dClasses);
-        k5_append<<<64, 128, 0, st>>>(d, c->in);
-        k5_append_link<<<1, 32, 0, st>>>(d, c->in);
-        c->nLaunch += 4;
+        k5_append_all<<<32, 128, 0, st>>>(d, c->in);
+        c->nLaunch += 2;
       }
     }
   }
-  k5_solve<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
+  k5_solve_clear<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
   c->nLaunch++;
   if (copiesPossible && c->nParticles > 0) { k5_set_positions<<<blocks_for(c->nParticles), 128, 0, st>>>(d, c->in); c->nLaunch++; }
   return IBM_OK;
@@ -883,6 +1072,7 @@ static int finish_substeps(ibm_ctx* c) {
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   IBM_CUDA(c, cudaGetLastError());
   if (c->hScal[9] == 1) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: more than CONTACT_CAP simultaneous contacts on one particle");
+  if (c->hScal[9] == 5) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: candidate pair list overflow");
   if (c->hScal[9] == 4) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: periodic-patch candidate list overflow");
   if (c->hScal[9] == 3) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: cell-list bin capacity exceeded (strongly polydisperse or overlapping bodies)");
   if (c->hScal[9] == 2) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: instance capacity exhausted (raise ibm_cloud_cfg.maxInstances)");
@@ -890,9 +1080,18 @@ static int finish_substeps(ibm_ctx* c) {
   return IBM_OK;
 }
 
+static void ensure_bins_clear(ibm_ctx* c) {
+  MotionDev& d = ((Motion*)c->motion)->d;
+  cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), c->stream);
+  cudaMemsetAsync(d.pairCount, 0, sizeof(int), c->stream);
+  cudaMemsetAsync(d.candCount, 0, sizeof(int), c->stream);
+  cudaMemsetAsync(d.hitCount, 0, sizeof(int), c->stream);
+}
+
 int motion_substep(ibm_ctx* c, double localDt) {
   int rc = ensure_motion(c);
   if (rc) return rc;
+  ensure_bins_clear(c);
   ctx_tic(c, T_ADVANCE);
   substep_launch(c, localDt);
   ctx_toc(c);
@@ -904,14 +1103,51 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
   if (rc) return rc;
   Motion* M = (Motion*)c->motion;
   ctx_tic(c, T_ADVANCE);
-  // literal loop of particleCloud.C:1247-1275 (App. B #22)
+  // literal loop of particleCloud.C:1247-1275 (App. B #22): the schedule of local time steps is plain fp64
+  // scalar arithmetic, evaluated here and handed to the persistent kernel
   int nSub = 0;
+  double dts[256];
   double localDt = dt / 100.0, localTime = localDt;
   while (localTime < dt) {
-    substep_launch(c, localDt);
+    if (nSub < 256) dts[nSub] = localDt;
     ++nSub;
     if (localTime + localDt > dt) localDt = dt - localTime;
     else localTime += localDt;
+  }
+  ensure_bins_clear(c);
+  if (c->fusedLoop5 && nSub <= 256 && M->fusedBlocks > 0) {
+    MotionDev& d = M->d;
+    IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IBM_CUDA(c, cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), c->stream));
+    int doCyclic = (d.nWalls > 0 || c->cfg.cyclicWithoutWalls) ? 1 : 0;
+    const ShapeClassDev* cls = c->dClasses;
+    const double* dd = M->dDts;
+    void* args[] = {&d, &c->Lg, &c->in, &cls, &dd, &nSub, &doCyclic};
+    IBM_CUDA(c, cudaLaunchCooperativeKernel((void*)k5_fused, dim3(M->fusedBlocks), dim3(256), args, 0, c->stream));
+    c->nLaunch++;
+  } else if (c->graphLoop5 && nSub <= 256) {
+    // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
+    // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
+    bool same = M->graphExec && (int)M->graphDts.size() == nSub;
+    for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
+    if (!same) {
+      if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
+      cudaGraph_t g = nullptr;
+      IBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const long long before = c->nLaunch;
+      for (int s = 0; s < nSub; ++s) substep_launch(c, dts[s]);
+      M->graphLaunches = c->nLaunch - before;
+      c->nLaunch = before;
+      IBM_CUDA(c, cudaStreamEndCapture(c->stream, &g));
+      cudaError_t e = cudaGraphInstantiate(&M->graphExec, g, 0);
+      cudaGraphDestroy(g);
+      IBM_CUDA(c, e);
+      M->graphDts.assign(dts, dts + nSub);
+    }
+    IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));
+    c->nLaunch += M->graphLaunches;
+  } else {
+    for (int s = 0; s < nSub; ++s) substep_launch(c, s < 256 ? dts[s] : dts[255]);
   }
   ctx_toc(c);
   if ((rc = finish_substeps(c))) return rc;
@@ -936,6 +1172,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
 void motion_destroy(ibm_ctx* c) {
   Motion* M = (Motion*)c->motion;
   if (!M) return;
+  if (M->graphExec) cudaGraphExecDestroy(M->graphExec);
   for (void* p : M->allocs) cudaFree(p);
   if (M->cubTemp) cudaFree(M->cubTemp);
   delete M;

@@ -181,7 +181,8 @@ int ibm_device_field_bytes(ibm_ctx* ctx, int nComponents, size_t* bytes);
 int ibm_upload_field(ibm_ctx* ctx, const double* hostAoS, int nComponents, double* dSoA);
 int ibm_download_field(ibm_ctx* ctx, const double* dSoA, int nComponents, double* hostAoS);
 int ibm_sync(ibm_ctx* ctx);
-int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant); /* 0 = reference-order kernels, 1 = tuned */
+int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant); /* 0 = reference-order kernels, 1.. = tuned generations */
+int ibm_set_option(ibm_ctx* ctx, const char* name, int value); /* "graph_loop5" (default 1): sub-step launch sequence replayed as a CUDA graph; "fused_loop5" (default 0): one persistent cooperative kernel */
 
 /* ---- timing -------------------------------------------------------------------------------------- */
 int ibm_timings(ibm_ctx* ctx, ibm_timing* out);

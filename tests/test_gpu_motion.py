@@ -30,8 +30,24 @@ def _compare(oc, gc, exact=True, tol=1e-9):
             assert np.max(np.abs(so[k] - sg[k])) / scale < tol, k
 
 
+FUSED = [1]
+
+
+@pytest.fixture(autouse=True, params=["graph", "fused", "plain"])
+def _loop5_mode(request):
+    FUSED[0] = request.param
+    yield
+
+
+def _gpu_cloud(case):
+    gc = ParticleCloud(case)
+    gc.set_option("fused_loop5", int(FUSED[0] == "fused"))
+    gc.set_option("graph_loop5", int(FUSED[0] == "graph"))
+    return gc
+
+
 def _run(case, n_steps, exact=True, seed=0, ft_scale=1e-6):
-    oc, gc = OracleCloud(case), ParticleCloud(case)
+    oc, gc = OracleCloud(case), _gpu_cloud(case)
     rng = np.random.default_rng(seed)
     stats = None
     for _ in range(n_steps):
@@ -111,7 +127,7 @@ def test_combine_forces_sums_copies():
     case = cases.colliding_particles(n_particles=6)
     case.particles.position[0] = [0.0, 0.0193, 0.0]
     case.particles.v[0] = [0.0, 2.0, 0.0]
-    oc, gc = OracleCloud(case), ParticleCloud(case)
+    oc, gc = OracleCloud(case), _gpu_cloud(case)
     oc.advance(1e-4); gc.advance(1e-4)
     assert gc.nParticles() == oc.n_instances and gc.nParticles() > 6
     FT = np.arange(6 * gc.nParticles(), dtype=float).reshape(-1, 6)
