@@ -235,46 +235,63 @@ static int clear_live_F(ibm_ctx* c) {
 int ctx_update(ibm_ctx* c) {
   clear_live_F(c);
   ctx_tic(c, T_UPDATE);
-  launch_k1_count(c->stream, c->L, c->dClasses, c->in, c->nInst);
-  if (comm_ranks(c) > 1 && c->nInst > 0) {
-    // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs
-    int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst, 1);
-    if (rcc) return rcc;
+  if (c->shellCap == 0) {
+    // first guess: volume of the shell / cell volume per instance, with slack; grown on overflow
+    size_t guess = 1024;
+    const double cellV = c->L.dx * c->L.dy * (c->nGeometricD == 2 ? 1.0 : c->L.dz);
+    for (int i = 0; i < c->nParticles; ++i) {
+      const ShapeClassDev& s = c->classes[c->origCls[i]].dev;
+      const double R = s.Rbound, r = std::max(0.0, R - s.delta);
+      const double vol = c->nGeometricD == 2 ? IBM_PI * (R * R - r * r) : 4.0 / 3.0 * IBM_PI * (R * R * R - r * r * r);
+      guess += (size_t)(1.3 * vol / cellV) + 16;
+    }
+    c->shellCap = (int)std::min<size_t>(guess * 3 / 2, 0x7fffffff);
+    IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
+    IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
   }
-  launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
-  launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
-  launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
-  launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
-  launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2);
-  c->nLaunch += 9;
-  IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    IBM_CUDA(c, cudaMemsetAsync(c->dScal, 0, 8 * sizeof(int), c->stream));
+    // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
+    launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4);
+    if (comm_ranks(c) > 1 && c->nInst > 0) {
+      // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs
+      int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst, 1);
+      if (rcc) return rcc;
+    }
+    launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
+    launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
+    launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
+    launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    c->nLaunch += 9;
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->hScal[4]) break;
+    // shell buffer too small (every rank takes the same path only if it overflows itself: the collective above is
+    // re-entered by all ranks or none, because the rerun repeats it) -> grow and redo
+    cudaFree(c->dShellCell); cudaFree(c->dShellJK);
+    c->shellCap = (int)std::min<long long>((long long)c->hScal[1] * 5 / 4 + 4096, 0x7fffffff);
+    IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
+    IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
+    if (comm_ranks(c) > 1) return ctx_fail(c, IBM_E_CAPACITY, "shell buffer overflow on a multi-rank run (unexpected: sized from the whole cloud)");
+  }
   if (c->nInst > 0 && c->hScal[0] < c->nInst) {  // deleteInActiveParticles (particleCloud.C:940-950)
     launch_compact_instances(c->stream, c->in, c->in2, c->dKeep, c->dKeepOff, c->nInst);
     std::swap(c->in, c->in2);
     c->nInst = c->hScal[0];
     motion_invalidate_groups(c);
-    launch_exclusive_scan(c->stream, c->in.nShell, c->in.shellOff, c->nInst, c->dScal + 1);
-    launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2);
-    c->nLaunch += 7;
-    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    c->nLaunch += 6;
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;
+  c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;   // extent of the shell buffer in use
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
-  if (c->totalShell > c->shellCap) {
-    if (c->dShellCell) cudaFree(c->dShellCell);
-    if (c->dShellJK) cudaFree(c->dShellJK);
-    c->shellCap = c->totalShell + c->totalShell / 4 + 1024;
-    IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
-    IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
-  }
-  launch_k1_fill(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK);
+  c->updatesPerCall = c->nInst > 0 ? c->hScal[3] : 0;
   int rc = ensure_field(c, &c->dI, 1);
   if (rc) return rc;
   IBM_CUDA(c, cudaMemsetAsync(c->dI, 0, (size_t)c->L.nCells * sizeof(double), c->stream));
   launch_k1_indicator(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dI);
-  c->nLaunch += 3;
+  c->nLaunch += 2;
   ctx_toc(c);
   IBM_CUDA(c, cudaGetLastError());
   return IBM_OK;
@@ -312,7 +329,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     ctx_toc(c);
     if (!dFext) c->fLive = true;
     c->nForcingCalls++;
-    c->nUpdates += c->totalShell;
+    c->nUpdates += c->updatesPerCall;
   }
   IBM_CUDA(c, cudaGetLastError());
   return IBM_OK;

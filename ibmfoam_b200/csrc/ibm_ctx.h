@@ -78,6 +78,7 @@ struct ibm_ctx {
   int forcingVariant = 2, stressVariant = 3;  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging
   ibm::Schedule sched;
   int totalChunks = 0;
+  int updatesPerCall = 0;
 
   bool fusedLoop5 = false;  // one persistent cooperative kernel for the sub-step loop
   bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph

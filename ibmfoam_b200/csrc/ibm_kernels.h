@@ -6,6 +6,8 @@ namespace ibm {
 
 // ---- ibm_kernels_ref.cu (compiled with -fmad=false) ----
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
+void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow);
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_fill(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                     int* shellCell, int* shellJK);
@@ -40,7 +42,8 @@ struct Schedule {
 int schedule_alloc(Schedule& s, int cap);
 void schedule_free(Schedule& s);
 // builds order[] and chunkOff[]; writes the total number of work items to *dTotalChunks
-void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks);
+void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks,
+                           int* dTotalUpdates);
 void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
                        const double* Uold, const double* S, double dT, double* F);

@@ -143,6 +143,103 @@ __global__ void k1_count(LatticeDev L, const ShapeClassDev* __restrict__ classes
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 single pass: rotation matrix, status counts and the shell list in ONE kernel.  Shell cells found in the
+// bounding box go to a shared-memory list; one atomicAdd on a global cursor reserves the instance's segment of the
+// shell buffer (segments are contiguous per instance; their order in the buffer is irrelevant).  Shells larger
+// than the shared list are re-evaluated and written directly.  The on-mesh point count is skipped for instances
+// whose outermost point layer lies strictly inside the lattice (then all N points are on the mesh).
+// ------------------------------------------------------------------------------------------------
+#define K1_LIST 1024
+__global__ void k1_mark(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst,
+                        int* __restrict__ shellCell, int* __restrict__ shellJK, int shellCap, int* __restrict__ cursor,
+                        int* __restrict__ overflow) {
+  __shared__ int sm[32];
+  __shared__ double srot[9];
+  __shared__ int listCell[K1_LIST], listJK[K1_LIST];
+  __shared__ int nList, segOff, nDirect;
+  const int b = blockIdx.x;
+  if (b >= nInst) return;
+  const ShapeClassDev sc = classes[in.cls[b]];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  if (threadIdx.x == 0) {
+    set_rotation_matrix(in.th[0][b], in.th[1][b], in.th[2][b], srot);  // particleShape::moveMesh (particleShape.C:291-295)
+    for (int q = 0; q < 9; ++q) in.rot[9 * (size_t)b + q] = srot[q];
+    if (sc.kind == 2) {  // ellipse::updateCellLists wraps theta.z first (ellipse.C:155-157)
+      double tz = in.th[2][b];
+      if (tz < 0) tz = xadd(tz, IBM_TWOPI);
+      if (tz > IBM_TWOPI) tz = xsub(tz, IBM_TWOPI);
+      in.th[2][b] = tz;
+    }
+    nList = 0; nDirect = 0;
+  }
+  __syncthreads();
+  const double thz = in.th[2][b];
+  Box bx = bounding_box(L, cx, cy, cz, sc.Rbound);
+  const int bi = bx.i1 - bx.i0 + 1, bj = bx.j1 - bx.j0 + 1, bk = bx.k1 - bx.k0 + 1;
+  const int nb = (bi > 0 && bj > 0 && bk > 0) ? bi * bj * bk : 0;
+  int cnt = 0;
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+    const int I = bx.i0 + t % bi, J = bx.j0 + (t / bi) % bj, K = bx.k0 + t / (bi * bj);
+    int j, k;
+    if (mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k)) {
+      ++cnt;
+      const int s = atomicAdd(&nList, 1);
+      if (s < K1_LIST) { listCell[s] = lat_index(L, I, J, K); listJK[s] = j | (k << 16); }
+    }
+  }
+  const int nShell = block_sum(cnt, sm);
+  if (threadIdx.x == 0) {
+    const int o = atomicAdd(cursor, nShell);
+    segOff = o;
+    if (o + nShell > shellCap) { atomicExch(overflow, 1); segOff = -1; }
+  }
+  __syncthreads();
+  const int off = segOff;
+  if (off >= 0) {
+    if (nShell <= K1_LIST) {
+      for (int s = threadIdx.x; s < nShell; s += blockDim.x) { shellCell[off + s] = listCell[s]; shellJK[off + s] = listJK[s]; }
+    } else {
+      for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+        const int I = bx.i0 + t % bi, J = bx.j0 + (t / bi) % bj, K = bx.k0 + t / (bi * bj);
+        int j, k;
+        if (mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k)) {
+          const int s = atomicAdd(&nDirect, 1);
+          shellCell[off + s] = lat_index(L, I, J, K);
+          shellJK[off + s] = j | (k << 16);
+        }
+      }
+    }
+  }
+  // on-mesh point count (particleShape.C:41-91): all N when the outer layer is strictly inside the lattice
+  double rOut = sc.Rbound + sc.delta;
+  const double mx = 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
+  rOut += mx;
+  const bool inside = cx - rOut > L.ox && cx + rOut < L.ox + L.nx * L.dx && cy - rOut > L.oy && cy + rOut < L.oy + L.ny * L.dy &&
+                      (L.nz == 1 && sc.kind != 0 ? (cz > L.oz + L.kz0 * L.dz && cz < L.oz + (L.kz0 + L.nz) * L.dz)
+                                                 : (cz - rOut > L.oz + L.kz0 * L.dz && cz + rOut < L.oz + (L.kz0 + L.nz) * L.dz));
+  int nOn;
+  if (inside) {
+    nOn = sc.N;
+  } else {
+    int on = 0;
+    for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {
+      V3 p = shape_point(sc, srot, cx, cy, cz, n);
+      int I, J, K;
+      if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0) ++on;
+    }
+    nOn = block_sum(on, sm);
+  }
+  if (threadIdx.x == 0) {
+    int I, J, K;
+    const int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
+    in.nShell[b] = off >= 0 ? nShell : 0;
+    in.shellOff[b] = off >= 0 ? off : 0;
+    in.nPtsOnMesh[b] = nOn;
+    in.onLocal[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
+  }
+}
+
 // particleShape.C:97-108 and particleIBM.C:607-614 on the WHOLE mesh: nPtsOnMesh holds the point count over all
 // slabs, Lg is the global lattice.  On one GPU this reproduces the local status exactly.
 __global__ void k1_status(LatticeDev Lg, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst) {
@@ -501,6 +598,10 @@ __global__ void k_stress_ref(LatticeDev L, const ShapeClassDev* __restrict__ cla
 // ------------------------------------------------------------------------------------------------
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
   if (nInst > 0) k1_count<<<nInst, 128, 0, st>>>(L, classes, in, nInst);
+}
+void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow) {
+  if (nInst > 0) k1_mark<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
 }
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
   if (nInst > 0) k1_status<<<(nInst + 127) / 128, 128, 0, st>>>(Lg, classes, in, nInst);

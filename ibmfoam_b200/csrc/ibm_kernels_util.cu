@@ -101,15 +101,17 @@ __global__ void k_morton_keys(LatticeDev L, InstanceSoA in, int n, int cap, unsi
   while (((max(L.nx, max(L.ny, L.nz)) - 1) >> sh) > 1023) ++sh;
   keys[i] = spread10((unsigned)(I >> sh)) | (spread10((unsigned)(J >> sh)) << 1) | (spread10((unsigned)(K >> sh)) << 2);
 }
-__global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, int n, int* cnt) {
+__global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, int n, int* cnt, int* totalUpdates) {
   int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos > n) return;
-  int c = 0;
+  int c = 0, ns = 0;
   if (pos < n) {
     int i = order[pos];
-    if (in.onLocal[i] != 0) c = (in.nShell[i] + FORCING_CHUNK - 1) / FORCING_CHUNK;
+    if (in.onLocal[i] != 0) { ns = in.nShell[i]; c = (ns + FORCING_CHUNK - 1) / FORCING_CHUNK; }
   }
-  cnt[pos] = c;  // entry n is a zero sentinel so that the exclusive scan yields n+1 offsets
+  if (pos <= n) cnt[pos] = c;  // entry n is a zero sentinel so that the exclusive scan yields n+1 offsets
+  // cell-particle updates of one forcing call = shell cells of the instances the forcing kernels process
+  for (int o = 16; o > 0; o >>= 1) ns += __shfl_down_sync(0xffffffffu, ns, o);
+  if ((threadIdx.x & 31) == 0 && ns) atomicAdd(totalUpdates, ns);
 }
 __global__ void k_last_offset(const int* off, int n, int* out) { *out = off[n]; }
 
@@ -132,12 +134,14 @@ void schedule_free(Schedule& s) {
   for (void* p : ps) if (p) cudaFree(p);
   s = Schedule{};
 }
-void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks) {
+void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks,
+                           int* dTotalUpdates) {
   const int cap = s.cap;
   k_morton_keys<<<(cap + 255) / 256, 256, 0, st>>>(L, in, nInst, cap, s.keys, s.iota);
   size_t tb = s.tempBytes;
   cub::DeviceRadixSort::SortPairs(s.temp, tb, s.keys, s.keysSorted, s.iota, s.order, cap, 0, 32, st);
-  k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt);
+  cudaMemsetAsync(dTotalUpdates, 0, sizeof(int), st);
+  k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt, dTotalUpdates);
   tb = s.tempBytes;
   cub::DeviceScan::ExclusiveSum(s.temp, tb, s.chunkCnt, s.chunkOff, nInst + 1, st);
   k_last_offset<<<1, 1, 0, st>>>(s.chunkOff, nInst, dTotalChunks);
