@@ -90,6 +90,8 @@ static void build_class(ShapeClassHost& h, int kind, double d, double a, double 
   h.Sf.assign((size_t)3 * nTheta * nk, 0.0);
   h.cosT.resize(nTheta); h.sinT.resize(nTheta); h.sinP.assign(nk, 0.0); h.cosP.assign(nk, 1.0);
   h.Rtab.assign((size_t)3 * nTheta, 0.0);
+  h.ck.assign(nk, 1.0);
+  s.dTheta = 2.0 * Pi / (nTheta);
   const double dl[3] = {-1 * delta, 0, delta};
   const double dTheta = 2.0 * Pi / (nTheta);
   auto idx = [&](int i, int j, int k) { return i + j * 3 + k * 3 * nTheta; };
@@ -127,6 +129,7 @@ static void build_class(ShapeClassHost& h, int kind, double d, double a, double 
         else if (k == nk - 1) ck = (std::cos(phi - dPhi / 2.0) - std::cos(phi));
         else ck = (std::cos(phi - dPhi / 2.0) - std::cos(phi + dPhi / 2.0));
         for (int q = 0; q < 3; ++q) h.Sf[(size_t)3 * idx2(i, k) + q] = v[q] * ck;
+        h.ck[k] = ck;
       }
     }
     s.Rbound = d / 2.0;
@@ -179,7 +182,7 @@ static int upload_classes(ibm_ctx* c) {
   c->classPools.clear();
   std::vector<ShapeClassDev> devs;
   for (auto& h : c->classes) {
-    size_t n = h.centered.size() + h.Sf.size() + h.cosT.size() + h.sinT.size() + h.sinP.size() + h.cosP.size() + h.Rtab.size();
+    size_t n = h.centered.size() + h.Sf.size() + h.cosT.size() + h.sinT.size() + h.sinP.size() + h.cosP.size() + h.Rtab.size() + h.ck.size();
     double* pool = nullptr;
     IBM_CUDA(c, cudaMalloc(&pool, n * sizeof(double)));
     c->classPools.push_back(pool);
@@ -190,7 +193,7 @@ static int upload_classes(ibm_ctx* c) {
       flat.insert(flat.end(), v.begin(), v.end());
     };
     put(h.centered, h.dev.centered); put(h.Sf, h.dev.Sf); put(h.cosT, h.dev.cosT); put(h.sinT, h.dev.sinT);
-    put(h.sinP, h.dev.sinP); put(h.cosP, h.dev.cosP); put(h.Rtab, h.dev.Rtab);
+    put(h.sinP, h.dev.sinP); put(h.cosP, h.dev.cosP); put(h.Rtab, h.dev.Rtab); put(h.ck, h.dev.ck);
     IBM_CUDA(c, cudaMemcpy(pool, flat.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     devs.push_back(h.dev);
   }
@@ -249,6 +252,7 @@ int ctx_update(ibm_ctx* c) {
     IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
     IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
   }
+  c->sched.chunk = (c->forcingVariant == 2 && c->chunk256) ? 256 : FORCING_CHUNK;
   for (int attempt = 0; attempt < 8; ++attempt) {
     IBM_CUDA(c, cudaMemsetAsync(c->dScal, 0, 8 * sizeof(int), c->stream));
     // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
@@ -287,6 +291,7 @@ int ctx_update(ibm_ctx* c) {
   c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;   // extent of the shell buffer in use
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
   c->updatesPerCall = c->nInst > 0 ? c->hScal[3] : 0;
+  if (schedule_fill_items(c->stream, c->sched, c->nInst, c->totalChunks)) return ctx_fail(c, IBM_E_CUDA, "schedule_fill_items failed");
   int rc = ensure_field(c, &c->dI, 1);
   if (rc) return rc;
   IBM_CUDA(c, cudaMemsetAsync(c->dI, 0, (size_t)c->L.nCells * sizeof(double), c->stream));
@@ -317,7 +322,10 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     ctx_tic(c, T_FORCING);
     if (c->forcingVariant == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
-    else if (c->forcingVariant == 3)
+    else if (c->forcingVariant >= 4 && c->v4Forcing)
+      launch_forcing_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
+                        dS, dt, F);
+    else if (c->forcingVariant >= 3)
       launch_forcing_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
     else if (c->forcingVariant == 2)
@@ -371,7 +379,9 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   ctx_tic(c, T_STRESS);
   if (c->stressVariant == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
-  else if (c->stressVariant == 3)
+  else if (c->stressVariant >= 4 && c->v4Stress)
+    launch_stress_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
+  else if (c->stressVariant >= 3)
     launch_stress_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   else if (c->stressVariant == 2)
     launch_stress_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
@@ -426,6 +436,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   c->cfg = *cfg;
   if (const char* e = getenv("IBM_FUSED_LOOP5")) c->fusedLoop5 = std::atoi(e) != 0;  // developer switches (profiling)
   if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
   LatticeDev& L = c->L;
   L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
@@ -562,6 +573,27 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   }
   int rc = upload_classes(c);
   if (rc) return rc;
+  {
+    // fourth-generation kernels need the class tables and the staged box to fit their shared-memory budget
+    c->v4Stress = c->v4Forcing = !c->classes.empty();
+    const double d3[3] = {c->L.dx, c->L.dy, c->L.dz};
+    for (auto& h : c->classes) {
+      const ShapeClassDev& s = h.dev;
+      bool tab = s.kind != IBM_ELLIPSE && s.nTheta <= V4_MAX_NTHETA && s.nk <= V4_MAX_NK;
+      auto cells = [&](double reach) {
+        long long n = 1;
+        for (int q = 0; q < 3; ++q) {
+          long long e = (long long)std::ceil(2.0 * reach / d3[q]) + 3;  // floor(x+y)-floor(x) <= ceil(y), +1 inclusive, +2 margins
+          const int nq = q == 0 ? c->L.nx : (q == 1 ? c->L.ny : c->L.nz);
+          e = std::min<long long>(e, nq);
+          n *= (q == 0) ? (e | 1) : e;
+        }
+        return n;
+      };
+      if (!tab || cells(s.Rbound) > V4_STRESS_BOX) c->v4Stress = false;
+      if (!tab || cells(s.Rbound + s.delta) > V4_FORCING_BOX) c->v4Forcing = false;
+    }
+  }
   c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;
   if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
   if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
@@ -929,6 +961,7 @@ int ibm_set_kernel_variant(ibm_ctx* c, int fv, int sv) {
   if (!c) return IBM_E_ARG;
   c->forcingVariant = fv;
   c->stressVariant = sv;
+  if (c->cap != 0) return ctx_update(c);  // the work-item table depends on the forcing kernel generation
   return IBM_OK;
 }
 
@@ -936,6 +969,7 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (!c || !name) return IBM_E_ARG;
   if (std::strcmp(name, "fused_loop5") == 0) { c->fusedLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "graph_loop5") == 0) { c->graphLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
   return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_option: unknown option ") + name);
 }
 

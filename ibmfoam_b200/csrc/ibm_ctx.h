@@ -19,7 +19,7 @@ struct PatchHost {
 
 struct ShapeClassHost {
   ShapeClassDev dev{};  // device pointers filled after upload
-  std::vector<double> centered, Sf, cosT, sinT, sinP, cosP, Rtab;
+  std::vector<double> centered, Sf, cosT, sinT, sinP, cosP, Rtab, ck;
 };
 
 struct EventPair {
@@ -75,11 +75,13 @@ struct ibm_ctx {
   double* hPinned = nullptr;  // small pinned scratch for results
   size_t hPinnedDoubles = 0;
 
-  int forcingVariant = 2, stressVariant = 3;  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging
+  bool v4Stress = false, v4Forcing = false;  // every shape class fits the fourth-generation kernels (tables + staged box)
+  int forcingVariant = 2, stressVariant = 4;  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging
   ibm::Schedule sched;
   int totalChunks = 0;
   int updatesPerCall = 0;
 
+  bool chunk256 = false;    // direct-gather forcing kernel: 256 shell cells per work item (one item per d=8 sphere)
   bool fusedLoop5 = false;  // one persistent cooperative kernel for the sub-step loop
   bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph
   // motion (loop 5) scratch lives in ibm_motion.cu

@@ -45,6 +45,8 @@ struct ShapeClassDev {
   const double* sinP;      // [nk]      sin(k*dPhi)   (sphere)
   const double* cosP;      // [nk]
   const double* Rtab;      // [3][nTheta] layer radii (ellipse: rho(theta_j)+delta_i; else R+delta_i)
+  const double* ck;        // [nk]      polar band factor of Sf_ (sphere.C:142-157); 1 for 2-D shapes
+  double dTheta;           // 2*pi/nTheta
 };
 
 struct InstanceSoA {

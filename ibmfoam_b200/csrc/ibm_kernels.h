@@ -36,6 +36,8 @@ struct Schedule {
   unsigned* keys = nullptr; unsigned* keysSorted = nullptr;
   int* iota = nullptr; int* order = nullptr;      // order[pos] = instance scheduled at position pos
   int* chunkCnt = nullptr; int* chunkOff = nullptr;  // per sorted position; chunkOff has n+1 entries
+  int* itemPos = nullptr; int itemCap = 0;           // sorted position of every work item (filled on demand)
+  int chunk = FORCING_CHUNK;                         // shell cells per work item (128: staged kernels, 256: direct-gather v2)
   void* temp = nullptr; size_t tempBytes = 0;
   int cap = 0;
 };
@@ -55,6 +57,18 @@ void launch_forcing_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
                        const double* Uold, const double* S, double dT, double* F);
 void launch_stress_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
+// ---- ibm_kernels_v4.cu ----
+#define V4_MAX_NTHETA 256
+#define V4_MAX_NK 128
+#define V4_STRESS_BOX 1792
+#define V4_FORCING_BOX 2560
+void launch_forcing_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
+                       const double* Uold, const double* S, double dT, double* F);
+int schedule_fill_items(cudaStream_t st, Schedule& s, int nInst, int totalChunks);
+void launch_stress_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 
 // ---- ibm_kernels_util.cu ----
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep);

@@ -218,9 +218,14 @@ __global__ void k1_mark(LatticeDev L, const ShapeClassDev* __restrict__ classes,
   const bool inside = cx - rOut > L.ox && cx + rOut < L.ox + L.nx * L.dx && cy - rOut > L.oy && cy + rOut < L.oy + L.ny * L.dy &&
                       (L.nz == 1 && sc.kind != 0 ? (cz > L.oz + L.kz0 * L.dz && cz < L.oz + (L.kz0 + L.nz) * L.dz)
                                                  : (cz - rOut > L.oz + L.kz0 * L.dz && cz + rOut < L.oz + (L.kz0 + L.nz) * L.dz));
+  // ... and none when the outer layer cannot reach the local lattice at all (other slabs' instances on a multi-GPU run)
+  const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
+                       cz + rOut < L.oz + L.kz0 * L.dz || cz - rOut > L.oz + (L.kz0 + L.nz) * L.dz;
   int nOn;
   if (inside) {
     nOn = sc.N;
+  } else if (outside) {
+    nOn = 0;
   } else {
     int on = 0;
     for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {

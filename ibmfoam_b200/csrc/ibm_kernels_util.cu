@@ -101,12 +101,12 @@ __global__ void k_morton_keys(LatticeDev L, InstanceSoA in, int n, int cap, unsi
   while (((max(L.nx, max(L.ny, L.nz)) - 1) >> sh) > 1023) ++sh;
   keys[i] = spread10((unsigned)(I >> sh)) | (spread10((unsigned)(J >> sh)) << 1) | (spread10((unsigned)(K >> sh)) << 2);
 }
-__global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, int n, int* cnt, int* totalUpdates) {
+__global__ void k_chunk_counts(InstanceSoA in, const int* __restrict__ order, int n, int* cnt, int* totalUpdates, int chunk) {
   int pos = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0, ns = 0;
   if (pos < n) {
     int i = order[pos];
-    if (in.onLocal[i] != 0) { ns = in.nShell[i]; c = (ns + FORCING_CHUNK - 1) / FORCING_CHUNK; }
+    if (in.onLocal[i] != 0) { ns = in.nShell[i]; c = (ns + chunk - 1) / chunk; }
   }
   if (pos <= n) cnt[pos] = c;  // entry n is a zero sentinel so that the exclusive scan yields n+1 offsets
   // cell-particle updates of one forcing call = shell cells of the instances the forcing kernels process
@@ -129,8 +129,22 @@ int schedule_alloc(Schedule& s, int cap) {
   A(&s.temp, s.tempBytes);
   return e == cudaSuccess ? 0 : -1;
 }
+__global__ void k_item_pos(const int* __restrict__ chunkOff, int n, int* __restrict__ itemPos) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  for (int it = chunkOff[pos]; it < chunkOff[pos + 1]; ++it) itemPos[it] = pos;
+}
+int schedule_fill_items(cudaStream_t st, Schedule& s, int nInst, int totalChunks) {
+  if (totalChunks > s.itemCap) {
+    if (s.itemPos) cudaFree(s.itemPos);
+    s.itemCap = totalChunks + totalChunks / 4 + 1024;
+    if (cudaMalloc((void**)&s.itemPos, (size_t)s.itemCap * sizeof(int)) != cudaSuccess) { s.itemPos = nullptr; s.itemCap = 0; return -1; }
+  }
+  if (nInst > 0 && totalChunks > 0) k_item_pos<<<(nInst + 255) / 256, 256, 0, st>>>(s.chunkOff, nInst, s.itemPos);
+  return 0;
+}
 void schedule_free(Schedule& s) {
-  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp};
+  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp, s.itemPos};
   for (void* p : ps) if (p) cudaFree(p);
   s = Schedule{};
 }
@@ -141,7 +155,7 @@ void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceS
   size_t tb = s.tempBytes;
   cub::DeviceRadixSort::SortPairs(s.temp, tb, s.keys, s.keysSorted, s.iota, s.order, cap, 0, 32, st);
   cudaMemsetAsync(dTotalUpdates, 0, sizeof(int), st);
-  k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt, dTotalUpdates);
+  k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt, dTotalUpdates, s.chunk);
   tb = s.tempBytes;
   cub::DeviceScan::ExclusiveSum(s.temp, tb, s.chunkCnt, s.chunkOff, nInst + 1, st);
   k_last_offset<<<1, 1, 0, st>>>(s.chunkOff, nInst, dTotalChunks);

@@ -12,12 +12,13 @@
 //   C  one thread per shell cell forms F_i = sum_q (wI_q tO_q + wS_q tS_q)/W from shared memory and adds it
 //      to the forcing field.
 // Arithmetic differs from the reference-order kernel only by re-association (<= 1e-12 relative, tested).
+#include <cstdlib>
+
 #include "ibm_kernels.h"
+#include "ibm_tables.cuh"
 
 namespace ibm {
 
-#define FHASH 1024
-#define FMAXCOL (4 * FORCING_CHUNK + 1)
 
 struct Stencil7 {
   int self;
@@ -76,7 +77,8 @@ __device__ __forceinline__ V3 rigid_v(const V3& pt, double cx, double cy, double
   return V3{v.x + (om.y * rz - om.z * ry), v.y + (om.z * rx - om.x * rz), v.z + (om.x * ry - om.y * rx)};
 }
 
-__device__ __forceinline__ unsigned hash_col(int key) { return ((unsigned)key * 2654435761u) >> 22; }  // 10 bits
+template <int HBITS>
+__device__ __forceinline__ unsigned hash_col(int key) { return ((unsigned)key * 2654435761u) >> (32 - HBITS); }
 
 // schedule lookup: position with chunkOff[pos] <= item < chunkOff[pos+1]
 __device__ __forceinline__ int find_pos(const int* __restrict__ off, int n, int item) {
@@ -88,31 +90,38 @@ __device__ __forceinline__ int find_pos(const int* __restrict__ off, int n, int 
   return lo;
 }
 
-__global__ void __launch_bounds__(128, 5)
+template <int CH, int HBITS, int MINB>
+__global__ void __launch_bounds__(CH, MINB)
 k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
              const int* __restrict__ chunkOff, const int* __restrict__ shellCell, const int* __restrict__ shellJK,
              const double* __restrict__ U, const double* __restrict__ Uold, const double* __restrict__ S, double dT,
              double* __restrict__ F) {
-  __shared__ int hKey[FHASH];
-  __shared__ unsigned short hSlot[FHASH];
-  __shared__ int colKey[FMAXCOL];
-  __shared__ double colVal[FMAXCOL][6];
+  constexpr int FHASH = 1 << HBITS, FMAXCOL = 4 * CH + 1;
+  extern __shared__ double smem2[];
+  double (*colVal)[6] = (double (*)[6])smem2;             // [FMAXCOL][6]
+  int* hKey = (int*)(smem2 + 6 * FMAXCOL);                // [FHASH]
+  int* colKey = hKey + FHASH;                             // [FMAXCOL]
+  unsigned short* hSlot = (unsigned short*)(colKey + FMAXCOL + 1);  // [FHASH]
   __shared__ int nCol;
+  Tab4& tab = *(Tab4*)nullptr;  // unused (see useTab)
   const int item = blockIdx.x;
   const int pos = find_pos(chunkOff, nInst, item);
   const int b = order[pos];
-  const int c0 = (item - chunkOff[pos]) * FORCING_CHUNK;
+  const int c0 = (item - chunkOff[pos]) * CH;
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double* rot = in.rot + 9 * (size_t)b;
   const int off = in.shellOff[b] + c0;
-  const int n = min(FORCING_CHUNK, in.nShell[b] - c0);
+  const int n = min(CH, in.nShell[b] - c0);
   const size_t C = (size_t)L.nCells;
   const int nT = sc.nTheta;
   const int degenerateKey = nT * sc.nk;  // App. B #3: bins with k == nk-1 reference point 0 twelve times
 
   for (int t = threadIdx.x; t < FHASH; t += blockDim.x) hKey[t] = -1;
   if (threadIdx.x == 0) nCol = 0;
+  // shared-memory trig tables cost more than they save here: every KB of shared memory is a KB less L1 for the gathers
+  const bool useTab = false;
+  const double Rsh = sc.d / 2.0;
   __syncthreads();
 
   // ---- A: register columns ----
@@ -132,7 +141,7 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int key = myKeys[q];
-      unsigned h = hash_col(key);
+      unsigned h = hash_col<HBITS>(key);
       while (true) {
         int old = atomicCAS(&hKey[h], -1, key);
         if (old == -1) {
@@ -156,18 +165,20 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   for (int s = threadIdx.x; s < ncol; s += blockDim.x) {
     const int key = colKey[s];
     int pI, pS, pO;
-    if (key == degenerateKey) { pI = pS = pO = 0; }
-    else { pI = pt_index(nT, 0, key % nT, key / nT); pS = pI + 1; pO = pI + 2; }
+    const bool deg = key == degenerateKey;
+    const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
+    if (deg) { pI = pS = pO = 0; }
+    else { pI = pt_index(nT, 0, jq, kq); pS = pI + 1; pO = pI + 2; }
     double tO[3], tS[3];
     Stencil7 st;
     {  // inner point: Uold only
-      const V3 x = shape_point(sc, rot, cx, cy, cz, pI);
+      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, 0, jq, kq) : shape_point(sc, rot, cx, cy, cz, pI);
       make_stencil7(L, idx, idy, idz, x, st);
 #pragma unroll
       for (int q = 0; q < 3; ++q) tO[q] = st.self >= 0 ? -gather7(st, Uold + q * C) : 0.0;
     }
     {  // outer point: U and S, rigid-body velocity
-      const V3 x = shape_point(sc, rot, cx, cy, cz, pO);
+      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 2, jq, kq) : shape_point(sc, rot, cx, cy, cz, pO);
       make_stencil7(L, idx, idy, idz, x, st);
       const V3 vv = rigid_v(x, cx, cy, cz, om, vp);
       const double v3[3] = {vv.x, vv.y, vv.z};
@@ -179,7 +190,7 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       }
     }
     {  // surface point: Uold and S
-      const V3 x = shape_point(sc, rot, cx, cy, cz, pS);
+      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 1, jq, kq) : shape_point(sc, rot, cx, cy, cz, pS);
       make_stencil7(L, idx, idy, idz, x, st);
       const V3 vv = rigid_v(x, cx, cy, cz, om, vp);
       const double v3[3] = {vv.x, vv.y, vv.z};
@@ -207,13 +218,15 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int key = myKeys[q];
-      unsigned h = hash_col(key);
+      unsigned h = hash_col<HBITS>(key);
       while (hKey[h] != key) h = (h + 1) & (FHASH - 1);
       slot[q] = hSlot[h];
-      const int pI = (key == degenerateKey) ? 0 : pt_index(nT, 0, key % nT, key / nT);
-      const int pS = (key == degenerateKey) ? 0 : pI + 1;
-      const V3 xI = shape_point(sc, rot, cx, cy, cz, pI);
-      const V3 xS = shape_point(sc, rot, cx, cy, cz, pS);
+      const bool deg = key == degenerateKey;
+      const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
+      const int pI = deg ? 0 : pt_index(nT, 0, jq, kq);
+      const int pS = deg ? 0 : pI + 1;
+      const V3 xI = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, 0, jq, kq) : shape_point(sc, rot, cx, cy, cz, pI);
+      const V3 xS = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 1, jq, kq) : shape_point(sc, rot, cx, cy, cz, pS);
       const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
       const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
       wI[q] = rsqrt(dI2);
@@ -310,8 +323,25 @@ k_stress_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
 void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
                        const double* Uold, const double* S, double dT, double* F) {
-  if (nInst > 0 && totalChunks > 0)
-    k_forcing_v2<<<totalChunks, 128, 0, st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S, dT, F);
+  if (nInst <= 0 || totalChunks <= 0) return;
+  if (s.chunk == 256) {
+    constexpr int CH = 256, HB = 11;
+    const size_t sm = (size_t)(4 * CH + 1) * 6 * sizeof(double) + (size_t)((1 << HB) + 4 * CH + 2) * sizeof(int) + (1 << HB) * sizeof(unsigned short);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_forcing_v2<CH, HB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr = true; }
+    k_forcing_v2<CH, HB, 2><<<totalChunks, CH, sm, st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S, dT, F);
+  } else {
+    constexpr int CH = 128, HB = 10;
+    const size_t sm = (size_t)(4 * CH + 1) * 6 * sizeof(double) + (size_t)((1 << HB) + 4 * CH + 2) * sizeof(int) + (1 << HB) * sizeof(unsigned short);
+    static bool attr2 = false;
+    if (!attr2) {
+      // the gathers are served by L1: leave it as much of the unified 228 KB as the resident CTAs allow
+      int pct = getenv("IBM_V2_CARVEOUT") ? atoi(getenv("IBM_V2_CARVEOUT")) : -1;
+      if (pct >= 0) cudaFuncSetAttribute(k_forcing_v2<CH, HB, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      attr2 = true;
+    }
+    k_forcing_v2<CH, HB, 5><<<totalChunks, CH, sm, st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S, dT, F);
+  }
 }
 void launch_stress_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr) {
