@@ -235,6 +235,11 @@ def main():
     from ibmfoam_b200.cloud import ParticleCloud
     from ibmfoam_b200 import capi
 
+    # a diverged or dead-locked multi-rank run must not sit on the GPUs until an external limit kills it
+    watchdog = threading.Timer(float(os.environ.get("IBM_BENCH_WATCHDOG_S", "900")), lambda: (sys.stderr.write("bench.py watchdog: run exceeded its time limit\n"), os._exit(17)))
+    watchdog.daemon = True
+    watchdog.start()
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -277,11 +282,14 @@ def main():
     dt = case.dt
 
     def barrier():
+        # drain the library's own stream (and its NCCL all-reduces) BEFORE touching torch's communicator: collectives
+        # of two communicators are never in flight at the same time
+        cloud.sync()
+        torch.cuda.synchronize()
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
-        cloud.sync()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
         run_step_device(cloud, ptrs, dt, have_motion)
@@ -392,10 +400,12 @@ def main():
                 "parallelism": None if world == 1 else f"z-slabs x{world}: fields decomposed, particle state replicated, NCCL all-reduce of F/T partials and on-mesh counts",
                 "breakdown_ms_per_step": breakdown, "wall_ms_per_step": wall_ms / args.steps}
         print(json.dumps(line))
+    barrier()
     cloud.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    watchdog.cancel()
 
 
 if __name__ == "__main__":

@@ -121,12 +121,14 @@ k_stress_v4(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   const double R = sc.d / 2.0;
   const Box4 B = box4_around(L, cx, cy, cz, sc.Rbound);
   const bool fits = tab4_ok(sc) && B.bx > 0 && B.by > 0 && B.bz > 0 && B.px * B.by * B.bz <= SBOX4;
-  if (!fits) {  // handled by the v3 kernel in a second launch
+  // Instances without local points (other slabs' instances on a multi-GPU run) do no work but MUST still write
+  // zero partials below: their F/T slots hold last step's combined totals, and the cross-rank sum adds whatever is
+  // in them.  `fits` is guaranteed by the host for every instance that is on the local mesh (ibm_set_particles).
+  if (on && !fits) {
     if (threadIdx.x == 0) atomicExch(fallback, 1);
-    return;
   }
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (on) {
+  if (on && fits) {
     tab4_load(sc, tab);
     stage4(L, B, P, C, 1, box, SBOX4);
     stage4(L, B, Tau, C, 6, box + SBOX4, SBOX4);

@@ -534,7 +534,8 @@ __device__ __forceinline__ void d5_append(MotionDev m, InstanceSoA in, int tid, 
   const int total = *m.hitCount;
   if (total == 0) return;
   const int n0 = *m.nInst;
-  if (total > m.cap - n0) { if (tid == 0) atomicExch(m.overflow, 2); return; }
+  // the rank of a hit is found by counting smaller keys (O(total^2)): bounded so that a diverged run fails fast
+  if (total > m.cap - n0 || total > 131072) { if (tid == 0) atomicExch(m.overflow, 2); return; }
   for (int h = tid; h < total; h += nth) {
     const int key = m.hitKey[h];
     int rank = 0;
@@ -575,7 +576,7 @@ __device__ __forceinline__ void d5_append_link(MotionDev m, InstanceSoA in) {
   const int total = *m.hitCount;
   if (total == 0) return;
   *m.hitCount = 0;
-  if (total > m.cap - *m.nInst) return;
+  if (total > m.cap - *m.nInst || total > 131072) return;
   const int n0 = *m.nInst;
   for (int t = 0; t < total; ++t) {
     int dst = n0 + t;

@@ -89,6 +89,13 @@ def test_loops_1_to_4_match_decomposed_oracle(n_ranks):
         st = gc.state_arrays()
         got = np.concatenate([st["F"], st["T"]], axis=1)
         assert np.max(np.abs(got - tot)) < 1e-10 * scale
+        # a second stress call (after the combined totals were written back): instances without local points must
+        # contribute ZERO partials again, not last step's totals (they would be multiplied by the rank count)
+        FTg2 = gc.integrateSurfaceStresses(f_lat["p"][sl], f_lat["tau"][sl])
+        assert np.array_equal(FTg2, FTg)
+        gc.combineForces()
+        st2 = gc.state_arrays()
+        assert np.array_equal(st2["F"], st["F"]) and np.array_equal(st2["T"], st["T"])
         res = (st["F"].copy(), st["T"].copy())
         gc.close()
         return res
