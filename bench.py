@@ -332,8 +332,16 @@ def main():
     alg_bytes, n_touch = algorithmic_bytes_forcing(case, local_updates, n_inst * (local_updates / max(updates_per_step, 1.0)))
     forcing_ms = tm["forcing_ms"] / max(1, tm["n_forcing_calls"])
     achieved = alg_bytes / (forcing_ms * 1e-3) / 1e9 if forcing_ms > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload and world == 1:
+            traffic = next(v["dram_bytes"] for k, v in tj["kernels"].items() if "k_forcing" in k)
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "k_forcing", "peak_kind": f"of {peak_kind}",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_forcing", "peak_kind": f"of {peak_kind}",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": forcing_ms, "n_touch_closed_form": n_touch,
                 "forcing_updates_per_s": updates_per_step / (forcing_ms * 1e-3) if forcing_ms > 0 else None}
     breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}

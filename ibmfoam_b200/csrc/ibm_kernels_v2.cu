@@ -15,7 +15,6 @@
 #include <cstdlib>
 
 #include "ibm_kernels.h"
-#include "ibm_tables.cuh"
 
 namespace ibm {
 
@@ -103,7 +102,6 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   int* colKey = hKey + FHASH;                             // [FMAXCOL]
   unsigned short* hSlot = (unsigned short*)(colKey + FMAXCOL + 1);  // [FHASH]
   __shared__ int nCol;
-  Tab4& tab = *(Tab4*)nullptr;  // unused (see useTab)
   const int item = blockIdx.x;
   const int pos = find_pos(chunkOff, nInst, item);
   const int b = order[pos];
@@ -119,9 +117,8 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
 
   for (int t = threadIdx.x; t < FHASH; t += blockDim.x) hKey[t] = -1;
   if (threadIdx.x == 0) nCol = 0;
-  // shared-memory trig tables cost more than they save here: every KB of shared memory is a KB less L1 for the gathers
-  const bool useTab = false;
-  const double Rsh = sc.d / 2.0;
+  // (shape points come from the class template in global memory: shared-memory trig tables were measured to cost
+  //  more than they save here — every KB of shared memory is a KB less L1 for the gathers)
   __syncthreads();
 
   // ---- A: register columns ----
@@ -172,13 +169,13 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     double tO[3], tS[3];
     Stencil7 st;
     {  // inner point: Uold only
-      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, 0, jq, kq) : shape_point(sc, rot, cx, cy, cz, pI);
+      const V3 x = shape_point(sc, rot, cx, cy, cz, pI);
       make_stencil7(L, idx, idy, idz, x, st);
 #pragma unroll
       for (int q = 0; q < 3; ++q) tO[q] = st.self >= 0 ? -gather7(st, Uold + q * C) : 0.0;
     }
     {  // outer point: U and S, rigid-body velocity
-      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 2, jq, kq) : shape_point(sc, rot, cx, cy, cz, pO);
+      const V3 x = shape_point(sc, rot, cx, cy, cz, pO);
       make_stencil7(L, idx, idy, idz, x, st);
       const V3 vv = rigid_v(x, cx, cy, cz, om, vp);
       const double v3[3] = {vv.x, vv.y, vv.z};
@@ -190,7 +187,7 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       }
     }
     {  // surface point: Uold and S
-      const V3 x = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 1, jq, kq) : shape_point(sc, rot, cx, cy, cz, pS);
+      const V3 x = shape_point(sc, rot, cx, cy, cz, pS);
       make_stencil7(L, idx, idy, idz, x, st);
       const V3 vv = rigid_v(x, cx, cy, cz, om, vp);
       const double v3[3] = {vv.x, vv.y, vv.z};
@@ -225,8 +222,8 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
       const int pI = deg ? 0 : pt_index(nT, 0, jq, kq);
       const int pS = deg ? 0 : pI + 1;
-      const V3 xI = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, 0, jq, kq) : shape_point(sc, rot, cx, cy, cz, pI);
-      const V3 xS = useTab ? tab4_point(sc, tab, Rsh, cx, cy, cz, deg ? 0 : 1, jq, kq) : shape_point(sc, rot, cx, cy, cz, pS);
+      const V3 xI = shape_point(sc, rot, cx, cy, cz, pI);
+      const V3 xS = shape_point(sc, rot, cx, cy, cz, pS);
       const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
       const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
       wI[q] = rsqrt(dI2);
