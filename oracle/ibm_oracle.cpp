@@ -268,6 +268,29 @@ double orc_cloud_max_co_num(void* /*h*/) { return 0.0; }  // [B#9] particleCloud
 double orc_particle_mass(void* h, int inst) { return nth((Cloud*)h, inst).mass(); }
 double orc_particle_inertia(void* h, int inst) { return nth((Cloud*)h, inst).shape.momentOfInertia; }
 
+const char* orc_impl() { return "port"; }
+
+// collision tables of one instance after computeCollisions/computeWallHits, expanded to the reference's dense layout
+// (Fc/Tc [nParticles][3] pre-zeroed by the caller, Fw/Tw [nWalls][3])
+void orc_particle_collision_tables(void* h, int inst, double* Fc, double* Tc, double* Fw, double* Tw) {
+  const Particle& p = nth((Cloud*)h, inst);
+  for (const auto& kv : p.Fc)
+    for (int a = 0; a < 3; ++a) Fc[3 * kv.first + a] = kv.second[a];
+  for (const auto& kv : p.Tc)
+    for (int a = 0; a < 3; ++a) Tc[3 * kv.first + a] = kv.second[a];
+  for (size_t i = 0; i < p.Fw.size(); ++i)
+    for (int a = 0; a < 3; ++a) { Fw[3 * i + a] = p.Fw[i][a]; Tw[3 * i + a] = p.Tw[i][a]; }
+}
+
+// particleIBM::collision (static, particleIBM.C:41-205) on two instances
+int orc_pair_collision(void* h, int inst1, int inst2, double* hitPt) {
+  Cloud* c = (Cloud*)h;
+  vec3 pt = Zero3;
+  bool hit = Particle::collision(nth(c, inst1), nth(c, inst2), pt);
+  for (int a = 0; a < 3; ++a) hitPt[a] = pt[a];
+  return hit ? 1 : 0;
+}
+
 // sub-step schedule of particleCloud.C:1247-1275 for a given dt: writes up to maxN local dts, returns count
 int orc_substep_schedule(double dt, double* dts, int maxN) {
   int n = 0;

@@ -33,6 +33,8 @@ struct ParticleDict {
 
 struct SearchMode {
   bool faithful = false;  // true: linear scans exactly like the reference; false: ijk + bounding box
+  bool staleTables = false;  // true: quirk B#8 AS CODED (gather tables of points that left the mesh keep their old
+                             // entries) - only used to compare against the compiled reference (oracle/_ref)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -378,9 +380,11 @@ struct Shape {
     int nPtsOnMesh = 0;
     for (int pti = 0; pti < N; ++pti) {
       // [B#8] DEFINED: tables cleared on every update (the reference keeps stale entries)
-      wToLocal[pti].clear();
-      facesToLocal[pti].clear();
-      WToLocal[pti] = 0.0;
+      if (!mode.staleTables) {
+        wToLocal[pti].clear();
+        facesToLocal[pti].clear();
+        WToLocal[pti] = 0.0;
+      }
       vec3 pt = mesh[pti];
       int celli = findCell(pt);
       pointCell[pti] = celli;
@@ -742,7 +746,8 @@ struct Cloud {
   std::vector<int> patches, walls, maxCopies;
   std::vector<double> I;  // indicator field I.ibm
 
-  SearchMode sm() const { return SearchMode{cfg.faithfulSearch != 0}; }
+  // cfg.faithfulSearch: bit 0 = linear-scan searches, bit 1 = quirk B#8 as coded
+  SearchMode sm() const { return SearchMode{(cfg.faithfulSearch & 1) != 0, (cfg.faithfulSearch & 2) != 0}; }
 
   // particleCloud.C:974-1134 (time == 0 branch)
   Cloud(const Mesh* m, const CloudCfg& c, const std::vector<ParticleDict>& dicts) : mesh(m), cfg(c) {
@@ -779,7 +784,7 @@ struct Cloud {
   // particleCloud.C:952-969
   void updateI() {
     std::fill(I.begin(), I.end(), 0.0);
-    if (cfg.faithfulSearch) {
+    if (cfg.faithfulSearch & 1) {
       for (int celli = 0; celli < mesh->nCells; ++celli) {
         const vec3& pt = mesh->C[celli];
         for (auto& p : particles)
@@ -899,7 +904,7 @@ struct Cloud {
         }
       }
     };
-    if (cfg.faithfulSearch || particles.size() < 64) {
+    if ((cfg.faithfulSearch & 1) || particles.size() < 64) {
       for (auto& p1 : particles)
         for (auto& p2 : particles) pairStep(p1, p2);
     } else {
