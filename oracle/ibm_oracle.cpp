@@ -1,4 +1,8 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
+// PARITY PINNED against the reference's own code: oracle/_ref (the reference's sources compiled against
+// oracle/mockfoam) agrees with this restatement bit for bit (tests/test_oracle_vs_reference.py), and the vectors that
+// build produced are committed (tests/golden/, tests/test_golden_oracle.py).  OpenFOAM's own arithmetic (mesh geometry,
+// findCell, linear face interpolation) is restated, not pinned: see oracle/README.md.
 // extern "C" surface of the CPU restatement, loaded with ctypes by tests/ and bench.py.
 #include <chrono>
 #include <cstring>

@@ -1,7 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-// legs may load anything under oracle/.  PARITY UNPINNED: the reference ships no golden
-// vectors and cannot be built here (needs OpenFOAM); see oracle/README.md.
+// legs may load anything under oracle/.
+// PARITY PINNED against the reference's own code: oracle/_ref (the reference's sources compiled against
+// oracle/mockfoam) agrees with this restatement bit for bit (tests/test_oracle_vs_reference.py), and the vectors that
+// build produced are committed (tests/golden/, tests/test_golden_oracle.py).  OpenFOAM's own arithmetic (mesh geometry,
+// findCell, linear face interpolation) is restated, not pinned: see oracle/README.md.
 //
 // Minimal restatement of the OpenFOAM primitive arithmetic the reference's hot path uses
 // (Vector / Tensor / SymmTensor operators).  Evaluation order follows OpenFOAM's

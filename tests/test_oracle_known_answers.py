@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/ — test infrastructure) with analytic known answers derived from the reference's
-own formulas.  The reference ships no golden vectors and cannot be built here, so the
-oracle is PARITY UNPINNED by the reference itself; these checks are what stands in.  CPU only."""
+own formulas.  The reference ships no vectors of its own; the restatement is pinned bit
+for bit against the reference's compiled code (test_oracle_vs_reference.py, test_golden_oracle.py) and these analytic
+checks stand beside that.  CPU only."""
 import math
 
 import numpy as np
