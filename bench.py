@@ -9,7 +9,10 @@ integral, force combination, the literal sub-step loop, re-marking).  One cell-p
   value     device-resident: SoA fields already in HBM, kernels only
   e2e       through the host C-ABI calls with pinned host AoS fields, H2D/D2H inside the timed region
   roofline  forcing kernel: algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, rank 0, N = 1 only
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, rank 0, N = 1 only;
+                next to it the reference's OWN code (oracle/_ref, compiled from /root/reference against oracle/mockfoam)
+                on a smaller sample it can finish (it allocates a labelList(nFaces) per shape point per update)
+  --impl reference   the reference arm: oracle/_ref when that library exists, else the port; all host cores
 
 python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128]
 """
@@ -153,15 +156,20 @@ def run_step_device(cloud, ptrs, dt, have_motion):
         cloud.update()
 
 
-def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345):
-    """The CPU oracle (port of the reference's algorithm, 1 thread like one MPI rank of the reference) on a
-    bounded sample of the same workload: an n^3 box at the same solid fraction and particle shape."""
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libibm_ref.so")
+REF_SAMPLE_N = 32   # the as-coded reference costs O(nFaces) per shape point per update: 0.8 s per step at 32^3, 10 s at 48^3
+
+
+def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345, impl="port", max_steps=8):
+    """A CPU implementation of the path (1 thread, like one MPI rank of the reference) on a bounded sample of the same
+    workload: an n^3 periodic box at the same solid fraction and particle shape.  impl="port": the oracle restatement
+    (fast ijk search); impl="reference": the reference's own code as coded (oracle/_ref)."""
     from ibmfoam_b200 import cases
     from oracle.pyoracle import OracleCloud
     import ibm_testutil as util
     case = cases.assembly(n=n, moving=False, seed=seed)
     f = util.caller_fields(case)
-    oc = OracleCloud(case)
+    oc = OracleCloud(case, impl=impl)
     t0 = time.perf_counter()
     steps, updates = 0, 0
     while True:
@@ -170,26 +178,30 @@ def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345):
         oc.update()
         steps += 1
         updates += nu
-        if time.perf_counter() - t0 > seconds_budget or steps >= 8:
+        if time.perf_counter() - t0 > seconds_budget or steps >= max_steps:
             break
     el = time.perf_counter() - t0
     return updates / el, steps, el, case.particles.n
 
 
 def _ref_worker(args):
-    seed, budget, n = args
-    return cpu_baseline_sample(budget, n, seed)
+    seed, budget, n, impl = args
+    return cpu_baseline_sample(budget, n, seed, impl)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference itself needs OpenFOAM and
-    cannot be built here), one process per host core like the reference's one-MPI-rank-per-subdomain model."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, one process per core
+    like the reference's one-MPI-rank-per-subdomain model.  oracle/_ref (the reference's sources compiled against
+    oracle/mockfoam) when that library exists, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    from oracle import pyoracle
     cores = os.cpu_count() or 1
-    n = 128
+    impl = "reference" if (os.path.exists(REF_LIB) or os.path.isdir(pyoracle.REFERENCE_SRC)) else "port"
+    pyoracle.lib(impl)  # build / load once in the parent; the forked workers inherit it
+    n = REF_SAMPLE_N if impl == "reference" else 128
     budget = 12.0
     vals, per_step = [], []
     t_all = time.perf_counter()
@@ -197,20 +209,27 @@ def run_reference(args):
         if it == args.warmup:
             t_all = time.perf_counter()
         with mp.Pool(cores) as pool:
-            res = pool.map(_ref_worker, [(1000 + 17 * it + r, budget if it >= args.warmup else 1.0, n) for r in range(cores)])
+            res = pool.map(_ref_worker, [(1000 + 17 * it + r, budget if it >= args.warmup else 1.0, n, impl) for r in range(cores)])
         if it >= args.warmup:
             vals.append(sum(r[0] for r in res))
             per_step.append(max(r[2] / r[1] for r in res))
         if time.perf_counter() - t_all > 150:
             break
     v = float(np.mean(vals))
+    npart = res[0][3]
+    if impl == "reference":
+        note = ("the reference's own sources (particleShape/sphere/particleIBM/particleCloud .C) compiled against oracle/mockfoam, "
+                "as coded: O(nCells) marking scan per particle and a labelList(nFaces) per shape point per update")
+        how = "as coded"
+    else:
+        note, how = "reference algorithm on host cores (oracle port; oracle/_ref not present)", "fast (ijk) search"
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "note": "reference algorithm on host cores (oracle port)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cores} independent {n}^3 sub-boxes (1565 spheres d=8 each, same solid fraction as the workload), "
-                                       "forcing + stress integral + re-marking per step, fast (ijk) search"},
+            "config": {"workload": args.workload, "note": note},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": impl,
+                             "sample": f"{cores} independent {n}^3 periodic sub-boxes ({npart} spheres d=8 each, same solid fraction and "
+                                       f"shape as the workload), forcing + stress integral + re-marking per step, {how}"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -395,6 +414,10 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"128^3 sub-box, {npart} spheres d=8 (same solid fraction/shape as the workload), {steps} steps of "
                          f"forcing + stress integral + re-marking in {el:.1f} s, fast (ijk) search, 1 thread"}
+        if os.path.exists(REF_LIB):  # the reference's own code, as coded, on the sample it can finish
+            v2, steps2, el2, npart2 = cpu_baseline_sample(6.0, REF_SAMPLE_N, 12345, "reference", 6)
+            cpu["reference_as_coded"] = {"value": v2, "unit": UNIT, "cores": 1, "kind": "reference",
+                                         "sample": f"{REF_SAMPLE_N}^3 sub-box, {npart2} spheres, {steps2} steps in {el2:.1f} s (oracle/_ref)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
