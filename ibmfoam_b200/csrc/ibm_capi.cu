@@ -322,6 +322,9 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     ctx_tic(c, T_FORCING);
     if (c->forcingVariant == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
+    else if (c->forcingVariant >= 5 && c->v5Forcing)
+      launch_forcing_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
+                        c->dScal + 7);
     else if (c->forcingVariant >= 4 && c->v4Forcing)
       launch_forcing_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
@@ -379,6 +382,8 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   ctx_tic(c, T_STRESS);
   if (c->stressVariant == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+  else if (c->stressVariant >= 5 && c->v4Stress)  // same tables and box as the fourth generation
+    launch_stress_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
   else if (c->stressVariant >= 4 && c->v4Stress)
     launch_stress_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
   else if (c->stressVariant >= 3)
@@ -575,7 +580,7 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   if (rc) return rc;
   {
     // fourth-generation kernels need the class tables and the staged box to fit their shared-memory budget
-    c->v4Stress = c->v4Forcing = !c->classes.empty();
+    c->v4Stress = c->v4Forcing = c->v5Forcing = !c->classes.empty();
     const double d3[3] = {c->L.dx, c->L.dy, c->L.dz};
     for (auto& h : c->classes) {
       const ShapeClassDev& s = h.dev;
@@ -592,6 +597,7 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
       };
       if (!tab || cells(s.Rbound) > V4_STRESS_BOX) c->v4Stress = false;
       if (!tab || cells(s.Rbound + s.delta) > V4_FORCING_BOX) c->v4Forcing = false;
+      if (!tab || cells(s.Rbound + s.delta) > V5_FORCING_BOX) c->v5Forcing = false;
     }
   }
   c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;

@@ -76,7 +76,10 @@ struct ibm_ctx {
   size_t hPinnedDoubles = 0;
 
   bool v4Stress = false, v4Forcing = false;  // every shape class fits the fourth-generation kernels (tables + staged box)
-  int forcingVariant = 2, stressVariant = 4;  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging
+  bool v5Forcing = false;                    // ... and the fifth-generation forcing kernel (its box is a little smaller)
+  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging, 4 lean staging,
+  // 5 one CTA per instance + cp.async staging (not yet measured on hardware: selected explicitly only)
+  int forcingVariant = 2, stressVariant = 4;
   ibm::Schedule sched;
   int totalChunks = 0;
   int updatesPerCall = 0;

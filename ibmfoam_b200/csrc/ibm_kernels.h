@@ -70,6 +70,14 @@ int schedule_fill_items(cudaStream_t st, Schedule& s, int nInst, int totalChunks
 void launch_stress_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 
+// ---- ibm_kernels_v5.cu (kernels in ibm_kernels_v5.cuh): one CTA per instance, cp.async box staging, forcing split by field ----
+#define V5_FORCING_BOX 2208
+void launch_forcing_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                       const double* S, double dT, double* F, int* dFallback);
+void launch_stress_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
+
 // ---- ibm_kernels_util.cu ----
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep);
 void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,
