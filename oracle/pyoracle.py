@@ -293,6 +293,18 @@ class OracleCloud:
         self.L.orc_particle_collision_tables(self.h, inst, _dp(Fc), _dp(Tc), _dp(Fw), _dp(Tw))
         return Fc, Tc, Fw[:n_walls], Tw[:n_walls]
 
+    def written_fields(self):
+        """lagrangian/IBMparticles/* as the reference's own writeFields() writes them (reference build only)."""
+        self._chk(self.L.orc_cloud_write_fields(self.h))
+        out = {}
+        for name, width in (("positions", 3), ("index", 1), ("copy", 1), ("active", 1), ("center", 3), ("theta", 3), ("d", 1),
+                            ("D", 3), ("v", 3), ("omega", 3), ("rho", 1), ("age", 1)):
+            buf = np.zeros(3 * max(1, self.n_instances))
+            n = self.L.orc_written_field(self.h, name.encode(), _dp(buf), buf.size)
+            if n >= 0:
+                out[name] = buf[:n].reshape(-1, width) if width > 1 else buf[:n].copy()
+        return out
+
     def pair_collision(self, i1, i2):
         pt = np.zeros(3)
         hit = self.L.orc_pair_collision(self.h, int(i1), int(i2), _dp(pt))

@@ -21,17 +21,6 @@ namespace Foam
 {
 defineTypeNameAndDebug(particle, 0);
 
-// IO members of the reference classes live in particleCloudIO.C / particleIBMIO.C, which are not compiled (restart IO
-// is outside the path).  The vtable needs the virtuals.
-void particleCloud::writeFields() const {}
-bool particleCloud::writeObject(IOstream::streamFormat, IOstream::versionNumber, IOstream::compressionType, const bool) const
-{
-    return true;
-}
-void particleCloud::readParticles()
-{
-    FatalErrorInFunction << "restart is not modelled: start the mock Time at 0" << exit(FatalError);
-}
 }
 
 namespace
@@ -448,6 +437,27 @@ void orc_cloud_cd(void* h, double* out)
 double orc_cloud_max_co_num(void* h) { return ((RefCloud*)h)->cloud->maxCoNum(); }
 double orc_particle_mass(void* h, int inst) { return nth((RefCloud*)h, inst).mass(); }
 double orc_particle_inertia(void* h, int inst) { return nth((RefCloud*)h, inst).shape_->I(); }
+
+// the reference's own restart writer (particleCloudIO.C:30-45 -> particleIBMIO.C:58-108): the mock keeps what the IOFields
+// write in memory.  orc_written_field copies the field lagrangian/IBMparticles/<name> (flattened) and returns its length.
+int orc_cloud_write_fields(void* h)
+{
+    RefCloud* c = (RefCloud*)h;
+    return guarded([&]() {
+        mockWrittenFields().clear();
+        c->cloud->writeObject(IOstream::ASCII, IOstream::versionNumber(), IOstream::UNCOMPRESSED, true);
+    });
+}
+int orc_written_field(void* h, const char* name, double* out, int maxN)
+{
+    RefCloud* c = (RefCloud*)h;
+    const std::string path = std::string(c->time.timeName()) + "/lagrangian/IBMparticles/" + name;
+    auto it = mockWrittenFields().find(path);
+    if (it == mockWrittenFields().end()) return -1;
+    const int n = (int)it->second.size();
+    for (int i = 0; i < n && i < maxN; ++i) out[i] = it->second[size_t(i)];
+    return n;
+}
 
 // collision tables of one instance after computeCollisions/computeWallHits (dense, as the reference stores them)
 void orc_particle_collision_tables(void* h, int inst, double* Fc, double* Tc, double* Fw, double* Tw)

@@ -1,5 +1,5 @@
 /*---------------------------------------------------------------------------*\
-  OpenFOAM-side binding of libibmfoam_b200 — see particleCloud.H.  Every member forwards to one C-ABI call
+  OpenFOAM-side binding of libibmfoam_b200 - see particleCloud.H.  Every member forwards to one C-ABI call
   (include/ibmfoam_b200.h); OpenFOAM keeps the mesh, the fields, the PIMPLE loop and the linear solvers.
 \*---------------------------------------------------------------------------*/
 #include "particleCloud.H"
@@ -274,5 +274,53 @@ void Foam::particleCloud::readParticles()
     NotImplemented;  // restart from lagrangian/IBMparticles: SURVEY §8(f) row 1
 }
 
-// devRhoReff()/rho(): verbatim logic of the reference's private members (particleCloud.C:41-169) belongs here;
-// it only calls OpenFOAM (turbulence model / transport properties / fvc::grad) and is not part of the GPU path.
+// ---- the viscous stress stays OpenFOAM's (it is not part of the GPU path).  Same sources, in the same order of
+//      preference, as the reference's private members (particleCloud.C:41-169), which follow OpenFOAM's `forces`
+//      function object: a compressible turbulence model's devRhoReff, an incompressible one's rho*devReff, a fluidThermo
+//      mu, a transportModel nu, or the `nu` entry of a transportProperties dictionary. ----
+Foam::tmp<Foam::volScalarField> Foam::particleCloud::rho() const
+{
+    if (mesh_.foundObject<volScalarField>("thermo:rho"))
+    {
+        return mesh_.lookupObject<volScalarField>("thermo:rho");
+    }
+    return tmp<volScalarField>
+    (
+        new volScalarField
+        (
+            IOobject("rho", mesh_.time().timeName(), mesh_),
+            mesh_,
+            dimensionedScalar("rho", dimDensity, rhoRef_)
+        )
+    );
+}
+
+Foam::tmp<Foam::volSymmTensorField> Foam::particleCloud::devRhoReff() const
+{
+    typedef compressible::turbulenceModel cmpModel;
+    typedef incompressible::turbulenceModel icoModel;
+    if (mesh_.foundObject<cmpModel>(cmpModel::propertiesName))
+    {
+        return mesh_.lookupObject<cmpModel>(cmpModel::propertiesName).devRhoReff();
+    }
+    if (mesh_.foundObject<icoModel>(icoModel::propertiesName))
+    {
+        return rho()*mesh_.lookupObject<icoModel>(icoModel::propertiesName).devReff();
+    }
+    const volVectorField& U = mesh_.lookupObject<volVectorField>("U");
+    if (mesh_.foundObject<fluidThermo>(fluidThermo::dictName))
+    {
+        return -mesh_.lookupObject<fluidThermo>(fluidThermo::dictName).mu()*dev(twoSymm(fvc::grad(U)));
+    }
+    if (mesh_.foundObject<transportModel>("transportProperties"))
+    {
+        return -rho()*mesh_.lookupObject<transportModel>("transportProperties").nu()*dev(twoSymm(fvc::grad(U)));
+    }
+    if (mesh_.foundObject<dictionary>("transportProperties"))
+    {
+        const dimensionedScalar nu(mesh_.lookupObject<dictionary>("transportProperties").lookup("nu"));
+        return -rho()*nu*dev(twoSymm(fvc::grad(U)));
+    }
+    FatalErrorInFunction << "No valid model for viscous stress calculation" << exit(FatalError);
+    return volSymmTensorField::null();
+}

@@ -1,0 +1,41 @@
+"""Drop-in demonstration on the GPU: ONE solver-side driver (shim/dropin/dropin_driver.cpp, the calls pimpleIBMFoam makes,
+in its order) compiled twice - against the reference's own particleCloud (CPU) and against shim/particleCloud.{H,C} +
+libibmfoam_b200.so (B200) - both on the OpenFOAM look-alike of oracle/mockfoam.  What comes back across the class
+interface must agree: forcing fields 1e-12 relative, drag coefficients / particle state 1e-9 relative (force/torque are
+1e-10 relative and feed the motion), instance lists and flags exactly, lagrangian/IBMparticles/* restart fields included.
+
+Written without access to a GPU (the round's GPU budget was spent); sorts last for that reason."""
+import os
+
+import numpy as np
+import pytest
+
+import dropin_util as du
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not (os.path.exists(du.REFERENCE_BIN) and os.path.exists(du.SHIM_BIN)), reason="drop-in binaries not built")
+@pytest.mark.parametrize("name", sorted(du.CASES))
+def test_shim_is_a_drop_in_for_the_reference_class(tmp_path, name):
+    case, n_steps, n_outer = du.CASES[name]()
+    cp = str(tmp_path / "case.txt")
+    du.write_case(cp, case, n_steps, n_outer)
+    outs = {}
+    for side, binary in (("reference", du.REFERENCE_BIN), ("shim", du.SHIM_BIN)):
+        op = str(tmp_path / f"{side}.bin")
+        r = du.run(binary, cp, op)
+        assert r.returncode == 0, (side, r.stderr)
+        outs[side] = du.parse(op)
+    (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]
+    assert h_ref == h_shim
+    assert [t for t, _ in rec_ref] == [t for t, _ in rec_shim]
+    for (tag, a), (_, b) in zip(rec_ref, rec_shim):
+        assert a.shape == b.shape, tag
+        if tag in ("index", "copy", "active", "CoNum"):
+            assert np.array_equal(a, b), tag
+        elif tag == "F":
+            assert np.max(np.abs(a - b)) < 1e-12 * np.max(np.abs(a)), tag          # tolerance: 1e-12 relative
+        else:
+            scale = max(np.max(np.abs(a)), 1e-300)
+            assert np.max(np.abs(a - b)) < 1e-9 * scale, (tag, np.max(np.abs(a - b)) / scale)
