@@ -39,3 +39,33 @@ def ellipse_case():
                                         theta=[[0, 0, 0.37], [0, 0, 2.05]], v=[[0.1, 0.02, 0], [-0.1, 0.01, 0]],
                                         omega=[[0, 0, 0.5], [0, 0, -0.8]])
     return cases.Case("ellipse2", mesh, cloud, parts, dt=1e-3)
+
+
+class OracleAsCloud:
+    """The CPU checker behind the particleCloud call interface the mini flow solver drives (tests only)."""
+
+    def __init__(self, case, impl="port", **kw):
+        from oracle.pyoracle import OracleCloud
+        self.oc = OracleCloud(case, impl=impl, **kw)
+
+    def forcing(self, S, U, Uold, dt):
+        return self.oc.forcing(U, Uold, S, dt)[0]
+
+    def solve(self, p, devRhoReff, dt):
+        return self.oc.solve(p, devRhoReff, dt)
+
+    def Cd(self):
+        return self.oc.cd()
+
+
+def cylinder_re30_setup(dt=1e-3):
+    """validation/cylinderRe30 for the mini flow solver: the case, the flow object and the lattice <-> caller cell maps"""
+    import numpy as np
+    from ibmfoam_b200.validation import mini_flow
+    case = cases.cylinder_re30()
+    case.dt = dt
+    m = case.mesh
+    flow = mini_flow.Channel2D(m.nx, m.ny, m.delta[0], 0.3, 1e-3, dt)   # U_inf = 0.3, nu = 1e-3: Re = U d / nu = 30
+    l2c = m.lattice_to_cell()
+    c2l = np.argsort(l2c)
+    return case, flow, (lambda a: a[c2l]), (lambda a: a[l2c])

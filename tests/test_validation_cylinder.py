@@ -1,0 +1,46 @@
+"""validation/cylinderRe30 end to end on the CPU: the mini flow solver (ibmfoam_b200/validation/mini_flow.py, the caller
+either side of the IB path) coupled to the CPU restatement must reproduce, bit for bit, the drag history it produces
+when coupled to the REFERENCE'S OWN particleCloud - live (oracle/_ref) and from the committed golden history."""
+import os
+
+import numpy as np
+import pytest
+
+from ibmfoam_b200.validation import mini_flow
+from oracle import pyoracle
+import golden_util as gu
+import ibm_testutil as util
+
+GOLD = os.path.join(gu.GOLDEN, "cylinder_re30_cd_history.npz")
+
+
+def _run(impl, n_steps):
+    case, flow, to_caller, from_caller = util.cylinder_re30_setup()
+    cloud = util.OracleAsCloud(case, impl=impl)
+    cds = mini_flow.run_cylinder(cloud, flow, n_steps, to_caller, from_caller, every=1)
+    return np.array([c for _, c in cds]), flow
+
+
+def test_restatement_reproduces_reference_drag_history():
+    g = np.load(GOLD)
+    n = 60
+    cd, flow = _run("port", n)
+    assert np.array_equal(cd, g["cd"][:n])
+    assert 2.0 < cd[-1] < 5.0 and cd[0] > 10 * cd[-1], "impulsive start: a large added-mass spike that relaxes within tens of steps"
+
+
+@pytest.mark.skipif(not pyoracle.have_reference(), reason="no oracle/_ref/libibm_ref.so and no /root/reference")
+def test_compiled_reference_matches_its_golden_history():
+    g = np.load(GOLD)
+    n = 25
+    cd, _ = _run("reference", n)
+    assert np.array_equal(cd, g["cd"][:n])
+
+
+def test_uniform_flow_without_a_body_stays_uniform():
+    """the flow solver alone: no forcing, uniform inflow -> nothing happens (guards the Poisson / ghost-cell plumbing)"""
+    flow = mini_flow.Channel2D(40, 20, 0.05, 0.3, 1e-3, 1e-3)
+    for _ in range(5):
+        Sx, Sy = flow.explicit_terms()
+        flow.project(flow.u - flow.dt * Sx, flow.v - flow.dt * Sy)
+    assert np.allclose(flow.u, 0.3, atol=1e-13) and np.allclose(flow.v, 0.0, atol=1e-13) and np.allclose(flow.p, 0.0, atol=1e-10)

@@ -1,0 +1,31 @@
+"""validation/cylinderRe30 end to end on the GPU: mini flow solver + the CUDA path through the host C ABI, against the
+drag history the same solver produces with the REFERENCE'S OWN particleCloud (tests/golden/cylinder_re30_cd_history.npz).
+Tolerance: 1e-8 relative on Cd over 150 coupled steps (force/torque are 1e-10 relative per call and the forcing field
+1e-12; the flow feeds them back).  Written without access to a GPU; sorts last for that reason."""
+import os
+
+import numpy as np
+import pytest
+
+from ibmfoam_b200.cloud import ParticleCloud
+from ibmfoam_b200.validation import mini_flow
+import golden_util as gu
+import ibm_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cylinder_re30_drag_history_matches_reference():
+    g = np.load(os.path.join(gu.GOLDEN, "cylinder_re30_cd_history.npz"))
+    case, flow, to_caller, from_caller = util.cylinder_re30_setup()
+    cloud = ParticleCloud(case)
+    n = len(g["cd"])
+    cds = mini_flow.run_cylinder(cloud, flow, n, to_caller, from_caller, every=1)
+    cd = np.array([c for _, c in cds])
+    rel = np.abs(cd - g["cd"]) / np.abs(g["cd"])
+    assert np.max(rel) < 1e-8, float(np.max(rel))
+    pr = g["probes"]
+    for name, a in (("u", flow.u), ("v", flow.v), ("p", flow.p)):
+        ref = g[name + "_probe"]
+        assert np.max(np.abs(a.ravel()[pr] - ref)) < 1e-8 * max(np.max(np.abs(ref)), 1e-3), name
+    cloud.close()
