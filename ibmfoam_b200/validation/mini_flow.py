@@ -123,6 +123,94 @@ class Channel2D:
         return np.stack([ax.ravel(), ay.ravel(), np.zeros(ax.size)], axis=1)
 
 
+class PeriodicBox3D:
+    """n^3 uniform cells, periodic in all directions (validation/sphere's blockMeshDict: every patch cyclic), with the mean
+    velocity held at U_inf by a uniform body force.  In steady state that force balances the drag of the body:
+    F_drag = rho * f_body * V_box - an independent check of the surface-stress integral."""
+
+    def __init__(self, n, h, U_inf, nu, dt):
+        self.n, self.h, self.nu, self.dt = n, float(h), float(nu), float(dt)
+        self.Uinf = np.asarray(U_inf, dtype=np.float64)
+        self.U = [np.full((n, n, n), float(self.Uinf[c])) for c in range(3)]   # index [k][j][i]
+        self.p = np.zeros((n, n, n))
+        self.Uf = [np.full((n, n, n), float(self.Uinf[c])) for c in range(3)]  # face-normal velocity at +1/2 in direction c
+        k = 2.0 * np.pi * np.fft.fftfreq(n)
+        ev = (2.0 * np.cos(k) - 2.0) / (h * h)
+        self._eig = ev[:, None, None] + ev[None, :, None] + ev[None, None, :]
+        self._eig[0, 0, 0] = 1.0
+        self.body_force = np.zeros(3)
+
+    @staticmethod
+    def _ax(c):           # array axis of direction c (x = last axis)
+        return 2 - c
+
+    def explicit_terms(self):
+        h, nu = self.h, self.nu
+        S = []
+        for c in range(3):
+            a = self.U[c]
+            conv = np.zeros_like(a)
+            lap = -6.0 * a
+            for d in range(3):
+                ax = self._ax(d)
+                face = 0.5 * (a + np.roll(a, -1, axis=ax)) * self.Uf[d]
+                conv += (face - np.roll(face, 1, axis=ax)) / h
+                lap += np.roll(a, 1, axis=ax) + np.roll(a, -1, axis=ax)
+            axc = self._ax(c)
+            dp = (np.roll(self.p, -1, axis=axc) - np.roll(self.p, 1, axis=axc)) / (2 * h)
+            S.append(conv + dp - nu * lap / (h * h))
+        return S
+
+    def project(self, Us):
+        h, dt = self.h, self.dt
+        Uf = [0.5 * (Us[d] + np.roll(Us[d], -1, axis=self._ax(d))) for d in range(3)]
+        div = sum((Uf[d] - np.roll(Uf[d], 1, axis=self._ax(d))) / h for d in range(3))
+        ph = np.fft.fftn(div / dt) / self._eig
+        ph[0, 0, 0] = 0.0
+        phi = np.real(np.fft.ifftn(ph))
+        for d in range(3):
+            ax = self._ax(d)
+            self.Uf[d] = Uf[d] - dt * (np.roll(phi, -1, axis=ax) - phi) / h
+            self.U[d] = Us[d] - dt * (np.roll(phi, -1, axis=ax) - np.roll(phi, 1, axis=ax)) / (2 * h)
+        self.p = self.p + phi
+        # hold the mean velocity: a uniform body force f = (U_inf - <U>)/dt   (applied to centres and faces alike)
+        for d in range(3):
+            corr = self.Uinf[d] - self.U[d].mean()
+            self.body_force[d] = corr / dt
+            self.U[d] += corr
+            self.Uf[d] += corr
+
+    def dev_rho_reff(self, rho=1.0):
+        h = self.h
+        g = [[(np.roll(self.U[c], -1, axis=self._ax(d)) - np.roll(self.U[c], 1, axis=self._ax(d))) / (2 * h) for d in range(3)] for c in range(3)]
+        tr3 = 2.0 * (g[0][0] + g[1][1] + g[2][2]) / 3.0
+        k = -rho * self.nu
+        comps = [k * (2 * g[0][0] - tr3), k * (g[0][1] + g[1][0]), k * (g[0][2] + g[2][0]), k * (2 * g[1][1] - tr3), k * (g[1][2] + g[2][1]),
+                 k * (2 * g[2][2] - tr3)]
+        return np.stack([c.ravel() for c in comps], axis=1)
+
+    def vec(self, comps):
+        return np.stack([c.ravel() for c in comps], axis=1)
+
+
+def run_sphere(cloud, flow: PeriodicBox3D, n_steps, every=1, log=None):
+    """Same call sites as run_cylinder for a body in the periodic box.  Returns [(step, Cd from the cloud, body force)]."""
+    out = []
+    dt = flow.dt
+    shape = flow.p.shape
+    for step in range(1, n_steps + 1):
+        S = flow.explicit_terms()
+        Us = [flow.U[c] - dt * S[c] for c in range(3)]
+        F = cloud.forcing(flow.vec(S), flow.vec(Us), flow.vec(flow.U), dt)
+        flow.project([flow.U[c] + dt * (F[:, c].reshape(shape) - S[c]) for c in range(3)])
+        if step % every == 0 or step == n_steps:
+            cloud.solve(flow.p.ravel(), flow.dev_rho_reff(), dt)
+            out.append((step, float(np.asarray(cloud.Cd())[0]), flow.body_force.copy()))
+            if log:
+                log(*out[-1])
+    return out
+
+
 def run_cylinder(cloud, flow: Channel2D, n_steps, to_caller=None, from_caller=None, every=1, log=None):
     """Time loop with the reference's call sites.  `cloud` has forcing(S, U, Uold, dt) -> F [C,3], solve(p, tau6, dt),
     Cd() -> per-instance drag coefficients.  Cell fields cross the interface in the CALLER's cell order."""
