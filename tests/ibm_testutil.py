@@ -69,3 +69,20 @@ def cylinder_re30_setup(dt=1e-3):
     l2c = m.lattice_to_cell()
     c2l = np.argsort(l2c)
     return case, flow, (lambda a: a[c2l]), (lambda a: a[l2c])
+
+
+def sphere_box_setup(n=32, Re=20.0, nTheta=60):
+    """validation/sphere on a coarse periodic box for the mini flow solver: d = 0.004 in a 0.02 box, U_inf = 0.1 along y
+    (system/initializeIBMDict), delta = one cell, viscosity from the requested Reynolds number."""
+    from ibmfoam_b200.validation import mini_flow
+    L, d, Uinf = 0.02, 0.004, 0.1
+    h = L / n
+    nu = Uinf * d / Re
+    case = cases.sphere_case(n=n)
+    case.particles.delta[:] = h
+    case.particles.nTheta[:] = nTheta
+    case.cloud.UInf = (0.0, Uinf, 0.0)
+    case.cloud.rhoRef = 1.0
+    case.dt = min(0.2 * h / Uinf, 0.1 * h * h / nu)
+    flow = mini_flow.PeriodicBox3D(n, h, (0.0, Uinf, 0.0), nu, case.dt)
+    return case, flow

@@ -44,3 +44,14 @@ def test_uniform_flow_without_a_body_stays_uniform():
         Sx, Sy = flow.explicit_terms()
         flow.project(flow.u - flow.dt * Sx, flow.v - flow.dt * Sy)
     assert np.allclose(flow.u, 0.3, atol=1e-13) and np.allclose(flow.v, 0.0, atol=1e-13) and np.allclose(flow.p, 0.0, atol=1e-10)
+
+
+def test_sphere_in_periodic_box_restatement_reproduces_reference_history():
+    """3-D: coarse validation/sphere (periodic box, mean flow held by a body force), 40 coupled steps"""
+    g = np.load(os.path.join(gu.GOLDEN, "sphere_box_cd_history.npz"))
+    case, flow = util.sphere_box_setup(n=int(g["n"]))
+    cloud = util.OracleAsCloud(case)
+    hist = mini_flow.run_sphere(cloud, flow, len(g["cd"]), every=1)
+    assert np.array_equal([c for _, c, _ in hist], g["cd"])
+    assert np.array_equal([f for _, _, f in hist], g["body_force"])
+    assert hist[-1][2][1] > 0, "a positive body force along the mean flow balances the drag"

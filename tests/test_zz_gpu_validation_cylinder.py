@@ -29,3 +29,15 @@ def test_cylinder_re30_drag_history_matches_reference():
         ref = g[name + "_probe"]
         assert np.max(np.abs(a.ravel()[pr] - ref)) < 1e-8 * max(np.max(np.abs(ref)), 1e-3), name
     cloud.close()
+
+
+def test_sphere_box_drag_history_matches_reference():
+    g = np.load(os.path.join(gu.GOLDEN, "sphere_box_cd_history.npz"))
+    case, flow = util.sphere_box_setup(n=int(g["n"]))
+    cloud = ParticleCloud(case)
+    hist = mini_flow.run_sphere(cloud, flow, len(g["cd"]), every=1)
+    cd = np.array([c for _, c, _ in hist])
+    bf = np.array([f for _, _, f in hist])
+    assert np.max(np.abs(cd - g["cd"]) / np.abs(g["cd"])) < 1e-8
+    assert np.max(np.abs(bf - g["body_force"])) < 1e-8 * np.max(np.abs(g["body_force"]))
+    cloud.close()
