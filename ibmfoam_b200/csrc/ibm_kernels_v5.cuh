@@ -183,6 +183,10 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
 #pragma unroll 1
   for (int c0 = 0; c0 < nS; c0 += F5_CELLS) {
     const int n = min(F5_CELLS, nS - c0);
+    // the first field of the chunk starts loading now: the box is free (every gather of the previous chunk finished
+    // before its last barrier) and the copies fly while the column hash and the scatter weights are built
+    stage5_async(L, Bs, Uold, C, 3, box, F5_BOX);
+    __pipeline_commit();
     for (int t = threadIdx.x; t < F5_HASH; t += blockDim.x) hKey[t] = -1;
     if (threadIdx.x == 0) nCol = 0;
     __syncthreads();  // hash cleared, tables loaded; the previous chunk has finished with colVal
@@ -261,8 +265,10 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       const double* fld = (phase == 0) ? Uold : (phase == 1 ? S : U);
       const Box5& B = (phase == 0) ? Bs : Bo;
       const int pxy = B.px * B.by;
-      stage5_async(L, B, fld, C, 3, box, F5_BOX);
-      __pipeline_commit();
+      if (phase > 0) {  // (phase 0 was issued at the top of the chunk)
+        stage5_async(L, B, fld, C, 3, box, F5_BOX);
+        __pipeline_commit();
+      }
       __pipeline_wait_prior(0);
       __syncthreads();  // the three planes of this field are in shared memory
 
