@@ -89,6 +89,7 @@ SYMBOLS = {
     "ibm_get_points": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ibm_get_sf": (C.c_int, [_VP, C.c_int, _VP]),
     "ibm_get_indicator": (C.c_int, [_VP, _VP]),
+    "ibm_get_solid_fraction": (C.c_int, [_VP, C.c_int, _VP]),
     "ibm_device_field_bytes": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
     "ibm_upload_field": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "ibm_download_field": (C.c_int, [_VP, _VP, C.c_int, _VP]),

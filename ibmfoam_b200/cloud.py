@@ -204,6 +204,12 @@ class ParticleCloud:
         check(self._L.ibm_get_indicator(self._h, _ptr(out)), self._h)
         return out
 
+    def solid_fraction(self, n_sub=8):
+        """EXTENSION (no reference counterpart): fractional solid volume fraction per cell, caller cell order."""
+        out = np.empty(self.mesh_spec.n_cells)
+        check(self._L.ibm_get_solid_fraction(self._h, int(n_sub), _ptr(out)), self._h)
+        return out
+
     def set_kernel_variant(self, forcing=1, stress=1):
         check(self._L.ibm_set_kernel_variant(self._h, int(forcing), int(stress)), self._h)
 

@@ -936,6 +936,24 @@ int ibm_get_indicator(ibm_ctx* c, double* I) {
   return IBM_OK;
 }
 
+// EXTENSION (no reference counterpart): fractional solid volume fraction, nSub^D sample points per cell
+int ibm_get_solid_fraction(ibm_ctx* c, int nSub, double* alpha) {
+  if (!c || !alpha) return IBM_E_ARG;
+  if (nSub < 1 || nSub > 32) return ctx_fail(c, IBM_E_ARG, "ibm_get_solid_fraction: nSub must be 1..32");
+  cudaSetDevice(c->device);
+  if (c->cap == 0) return ctx_fail(c, IBM_E_STATE, "ibm_get_solid_fraction: no particles set");
+  double* dA = nullptr;
+  IBM_CUDA(c, cudaMalloc(&dA, (size_t)c->L.nCells * sizeof(double)));
+  launch_solid_fraction(c->stream, c->L, c->dClasses, c->in, c->nInst, nSub, dA);
+  c->nLaunch += 2;
+  int rc = d2h_field(c, dA, 1, alpha);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dA);
+  if (rc) return rc;
+  IBM_CUDA(c, e);
+  return IBM_OK;
+}
+
 // ---- device-resident helpers ---------------------------------------------------------------------
 int ibm_device_field_bytes(ibm_ctx* c, int nComp, size_t* bytes) {
   if (!c || !bytes || nComp <= 0) return IBM_E_ARG;

@@ -78,6 +78,10 @@ void launch_forcing_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
 void launch_stress_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 
+// ---- ibm_kernels_alpha.cu: fractional solid volume fraction (extension) ----
+void launch_solid_fraction(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, int nSub,
+                           double* alpha);
+
 // ---- ibm_kernels_util.cu ----
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep);
 void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,

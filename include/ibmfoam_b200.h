@@ -174,6 +174,10 @@ int ibm_get_shell(ibm_ctx* ctx, int inst, int* cells, int* jk, int* Is, int* Os,
 int ibm_get_points(ibm_ctx* ctx, int inst, double* pts, int* cell, int* nFaces, int* otherCell, double* w, double* W);
 int ibm_get_sf(ibm_ctx* ctx, int inst, double* Sf);           /* Sf_ [nTheta*nk][3] */
 int ibm_get_indicator(ibm_ctx* ctx, double* I);               /* I.ibm, caller cell order (particleCloud.C:952-969) */
+/* EXTENSION, no reference counterpart (the reference only has the binary I.ibm): fractional solid volume fraction
+ * alpha_s[cell] = min(1, sum over instances of the share of nSub^D regularly spaced sample points of the cell that lie
+ * inside the body), caller cell order.  BASELINE.json north star, loop (1); SURVEY.md §8f row 4. */
+int ibm_get_solid_fraction(ibm_ctx* ctx, int nSub, double* alpha);
 
 /* ---- device-resident helpers (bench / multi-GPU harness) ----------------------------------------- */
 int ibm_device_field_bytes(ibm_ctx* ctx, int nComponents, size_t* bytes);

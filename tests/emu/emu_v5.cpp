@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ibm_kernels_v5.cuh"
+#include "ibm_kernels_alpha.cuh"
 
 using namespace ibm;
 
@@ -96,6 +97,23 @@ int emu_stress_v5(const int* n, const double* origin, const double* delta, int k
     k_stress_v5(L, classes, in, nInst, order, P, Tau, pRefOverRho, rhoRef, Tcorr, &fallback);
   });
   return fallback;
+}
+
+// solid volume fraction (extension): kind 0/1 via d, kind 2 via a, b and the per-instance rotation matrices
+void emu_solid_fraction(const int* n, const double* origin, const double* delta, int kz0, int kind, double d, double a, double b,
+                        int nInst, double* centre, double* rot, int nSub, double* alpha) {
+  LatticeDev L = lattice(n, origin, delta, kz0);
+  ShapeClassDev sc{};
+  sc.kind = kind; sc.d = d; sc.a = a; sc.b = b; sc.Rbound = (kind == 2) ? std::fmax(a, b) : d / 2.0;
+  std::vector<int> cls(nInst, 0);
+  InstanceSoA in{};
+  in.cls = cls.data();
+  for (int q = 0; q < 3; ++q) in.c[q] = centre + (size_t)q * nInst;
+  in.rot = rot;
+  const ShapeClassDev* classes = &sc;
+  emu::launch((unsigned)nInst, ALPHA_THREADS, 0, [&]() { k_solid_fraction(L, classes, in, nInst, nSub, alpha); });
+  const size_t C = (size_t)L.nCells;
+  emu::launch(4, 64, 0, [&]() { k_clamp_unit(alpha, C); });
 }
 
 }  // extern "C"

@@ -220,3 +220,55 @@ def test_stress_v5_writes_zero_partials_for_instances_without_local_points(emu):
                       C.c_double(1.0), _dp(Fout), _dp(Tout), None)
     assert not Fout[:, ::2].any() and not Tout[:, ::2].any()
     assert Fout[:, 1::2].any()
+
+
+# ---- solid volume fraction (extension; ibm_kernels_alpha.cuh) ----
+def _alpha(emu, case, n_sub=8, rot=None):
+    from oracle import alpha_oracle
+    p = case.particles
+    n, origin, delta = _lattice_args(case.mesh)
+    centres = np.ascontiguousarray(p.position.T, dtype=np.float64)
+    rot = np.ascontiguousarray(rot if rot is not None else np.tile(np.eye(3).reshape(1, 9), (p.n, 1)))
+    out = np.zeros(case.mesh.n_cells)
+    emu.emu_solid_fraction(_ip(n), _dp(origin), _dp(delta), int(case.mesh.kz0), int(p.kind[0]), C.c_double(p.d[0]), C.c_double(p.a[0]),
+                           C.c_double(p.b[0]), p.n, _dp(centres), _dp(rot), int(n_sub), _dp(out))
+    ref = alpha_oracle.solid_fraction(case.mesh, int(p.kind[0]), p.position, d=float(p.d[0]), a=float(p.a[0]), b=float(p.b[0]),
+                                      rot=rot.reshape(-1, 3, 3), n_sub=n_sub)
+    return out, ref
+
+
+@pytest.mark.parametrize("name", ["asm32", "wallbox", "aligned", "cyl8", "ellipse"])
+def test_solid_fraction_emulated_is_exact_and_integrates_to_the_body_volume(emu, name):
+    rot = None
+    if name == "ellipse":
+        case = util.ellipse_case()
+        rot = np.stack([_rotation(t) for t in case.particles.theta]).reshape(-1, 9)
+    else:
+        case = FORCING_CASES[name]()
+    a, ref = _alpha(emu, case, rot=rot)
+    assert np.array_equal(a, ref)                       # integer sample counts: exact
+    assert a.min() >= 0.0 and a.max() == 1.0
+    p, m = case.particles, case.mesh
+    cell_v = m.delta[0] * m.delta[1] * m.delta[2]
+    if name in ("asm32", "cyl8", "ellipse"):            # bodies entirely inside the lattice, not overlapping
+        L = m.nz * m.delta[2]
+        vol = {0: np.pi * p.d[0] ** 3 / 6.0, 1: np.pi * (p.d[0] / 2) ** 2 * L, 2: np.pi * p.a[0] * p.b[0] * L}[int(p.kind[0])] * p.n
+        if name == "asm32":                             # periodic box: spheres cut by the sides lose the part outside
+            inside = np.all((p.position - p.d[0] / 2 >= 0) & (p.position + p.d[0] / 2 <= m.nx), axis=1)
+            a2, _ = _alpha(emu, type(case)(case.name, m, case.cloud, _subset(p, inside), case.dt))
+            vol, a = np.pi * p.d[0] ** 3 / 6.0 * inside.sum(), a2
+        assert abs(a.sum() * cell_v - vol) < 2e-3 * vol
+
+
+def _subset(p, mask):
+    return cases.ParticleTable(**{k: getattr(p, k)[mask] for k in ("kind", "position", "d", "a", "b", "nTheta", "nk", "delta", "theta", "v",
+                                                                    "omega", "rho")})
+
+
+def test_solid_fraction_is_consistent_with_the_reference_indicator(emu):
+    """I.ibm (cell centre inside) is 1 exactly where more than ~half of the cell is solid, for convex bodies; alpha = 1 deep
+    inside and 0 far outside"""
+    case = FORCING_CASES["asm32"]()
+    a, _ = _alpha(emu, case)
+    I = OracleCloud(case).indicator()[np.argsort(case.mesh.lattice_to_cell())]  # -> lattice order (single block: identity)
+    assert np.all(a[I == 1] > 0.35) and np.all(a[I == 0] < 0.65)

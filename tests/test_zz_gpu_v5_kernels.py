@@ -111,3 +111,27 @@ def test_v5_full_step_matches_default_kernels():
         assert np.array_equal(s0[k], s5[k]), k
     for k in ("center", "v", "omega"):
         assert np.allclose(s0[k], s5[k], rtol=1e-9, atol=1e-12), k
+
+
+@pytest.mark.parametrize("name", ["asm48", "wc3d", "cyl8", "ellipse2"])
+def test_solid_fraction_extension_matches_its_definition(name):
+    """EXTENSION without a reference counterpart: alpha_s against the numpy restatement of its
+    definition - exact for spheres / cylinders (integer sample counts); ellipses within a few samples (device sin/cos in
+    the rotation matrix)."""
+    from oracle import alpha_oracle
+    case = CASES[name]()
+    gc = ParticleCloud(case)
+    a = gc.solid_fraction(8)
+    p = case.particles
+    rot = None
+    if p.kind[0] == cases.ELLIPSE:
+        th = p.theta[:, 2]
+        rot = np.stack([np.array([[np.cos(t), -np.sin(t), 0], [np.sin(t), np.cos(t), 0], [0, 0, 1]]) for t in th])
+    ref_lat = alpha_oracle.solid_fraction(case.mesh, int(p.kind[0]), p.position, d=float(p.d[0]), a=float(p.a[0]), b=float(p.b[0]), rot=rot)
+    ref_caller = np.empty_like(ref_lat)
+    ref_caller[case.mesh.lattice_to_cell()] = ref_lat          # lattice order -> the caller's cell order
+    if p.kind[0] == cases.ELLIPSE:
+        assert np.max(np.abs(a - ref_caller)) <= 3.0 / 64.0
+    else:
+        assert np.array_equal(a, ref_caller)
+    gc.close()
