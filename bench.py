@@ -465,6 +465,24 @@ def main():
     for _ in range(max(3, args.warmup)):
         run_step_device(cloud, ptrs, dt, have_motion)
     barrier()
+    if world > 1:
+        # replicated particle state: after the warm-up steps every rank must hold the same instance list and finite
+        # kinematics; a diverged run is reported at once instead of being timed (or left to the watchdog)
+        import torch.distributed as dist
+        st = cloud.state_arrays()
+        finite = bool(np.isfinite(st["center"]).all() and np.isfinite(st["v"]).all() and np.isfinite(st["F"]).all())
+        chk = torch.tensor([cloud.nParticles(), -cloud.nParticles(), 1 if finite else 0, float(np.abs(st["v"]).max()) if finite else 0.0],
+                           device=dev, dtype=torch.float64)
+        dist.all_reduce(chk[:3], op=dist.ReduceOp.MIN)
+        vmax = chk[3:].clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        same_n = chk[0].item() == -chk[1].item()
+        if not (same_n and chk[2].item() == 1 and abs(vmax.item() - chk[3].item()) <= 1e-9 * max(vmax.item(), 1e-300)):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "impl": "b200",
+                                  "error": f"ranks diverged during warm-up: instances min/max {int(chk[0].item())}/{int(-chk[1].item())}, "
+                                           f"finite {bool(chk[2].item())}, max|v| {chk[3].item()} vs {vmax.item()}"}))
+            os._exit(3)
     cloud.timings(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
