@@ -471,17 +471,15 @@ def main():
         import torch.distributed as dist
         st = cloud.state_arrays()
         finite = bool(np.isfinite(st["center"]).all() and np.isfinite(st["v"]).all() and np.isfinite(st["F"]).all())
-        chk = torch.tensor([cloud.nParticles(), -cloud.nParticles(), 1 if finite else 0, float(np.abs(st["v"]).max()) if finite else 0.0],
-                           device=dev, dtype=torch.float64)
-        dist.all_reduce(chk[:3], op=dist.ReduceOp.MIN)
-        vmax = chk[3:].clone()
-        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
-        same_n = chk[0].item() == -chk[1].item()
-        if not (same_n and chk[2].item() == 1 and abs(vmax.item() - chk[3].item()) <= 1e-9 * max(vmax.item(), 1e-300)):
+        vloc = float(np.abs(st["v"]).max()) if finite else 0.0
+        chk = torch.tensor([cloud.nParticles(), -cloud.nParticles(), 1 if finite else 0, vloc, -vloc], device=dev, dtype=torch.float64)
+        dist.all_reduce(chk, op=dist.ReduceOp.MIN)   # every rank sees the same five numbers and takes the same decision
+        n_min, n_max, all_finite, v_min, v_max = int(chk[0].item()), int(-chk[1].item()), chk[2].item() == 1, chk[3].item(), -chk[4].item()
+        if not (n_min == n_max and all_finite and (v_max - v_min) <= 1e-9 * max(v_max, 1e-300)):
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "impl": "b200",
-                                  "error": f"ranks diverged during warm-up: instances min/max {int(chk[0].item())}/{int(-chk[1].item())}, "
-                                           f"finite {bool(chk[2].item())}, max|v| {chk[3].item()} vs {vmax.item()}"}))
+                                  "error": f"ranks diverged during warm-up: instances min/max {n_min}/{n_max}, finite {all_finite}, "
+                                           f"max|v| min/max {v_min}/{v_max}"}))
             os._exit(3)
     cloud.timings(reset=True)
     sampler = ClockSampler(local_rank)
