@@ -211,6 +211,24 @@ def run_sphere(cloud, flow: PeriodicBox3D, n_steps, every=1, log=None):
     return out
 
 
+def run_moving_bodies(cloud, flow: PeriodicBox3D, n_steps, state=None):
+    """validation/collidingParticles-type loop: freely moving bodies in the periodic box - forcing(S) with the rigid-body
+    target velocity, then solve() = stress integral, force combination, sub-stepped collisions / integration, re-marking.
+    `state(cloud)` (optional) is called after every step and its results are collected."""
+    out = []
+    dt = flow.dt
+    shape = flow.p.shape
+    for _ in range(n_steps):
+        S = flow.explicit_terms()
+        Us = [flow.U[c] - dt * S[c] for c in range(3)]
+        F = cloud.forcing(flow.vec(S), flow.vec(Us), flow.vec(flow.U), dt)
+        flow.project([flow.U[c] + dt * (F[:, c].reshape(shape) - S[c]) for c in range(3)])
+        cloud.solve(flow.p.ravel(), flow.dev_rho_reff(), dt)
+        if state is not None:
+            out.append(state(cloud))
+    return out
+
+
 def run_cylinder(cloud, flow: Channel2D, n_steps, to_caller=None, from_caller=None, every=1, log=None):
     """Time loop with the reference's call sites.  `cloud` has forcing(S, U, Uold, dt) -> F [C,3], solve(p, tau6, dt),
     Cd() -> per-instance drag coefficients.  Cell fields cross the interface in the CALLER's cell order."""

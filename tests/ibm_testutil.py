@@ -86,3 +86,26 @@ def sphere_box_setup(n=32, Re=20.0, nTheta=60):
     case.dt = min(0.2 * h / Uinf, 0.1 * h * h / nu)
     flow = mini_flow.PeriodicBox3D(n, h, (0.0, Uinf, 0.0), nu, case.dt)
     return case, flow
+
+
+def colliding_spheres_setup(n=32, nu=0.05, dt=0.05):
+    """two spheres d = 8 cells approaching head-on in a periodic box of fluid at rest (the 3-D counterpart of
+    validation/collidingParticles that BASELINE.json's config list describes): forcing + collision + integration loop"""
+    from ibmfoam_b200.validation import mini_flow
+    case = cases.assembly(n=n, n_particles=2, seed=1, moving=True)
+    c = n / 2 + 0.123
+    sep = 8.5
+    case.particles.position[:] = [[c - sep / 2, c + 0.211, c - 0.317], [c + sep / 2, c + 0.211, c - 0.317]]
+    case.particles.v[:] = [[1.0, 0.05, 0.0], [-1.0, 0.0, 0.03]]
+    case.particles.omega[:] = [[0.0, 0.1, 0.2], [0.1, 0.0, -0.2]]
+    case.cloud.rhoRef = 1.0
+    case.dt = dt
+    flow = mini_flow.PeriodicBox3D(n, 1.0, (0.0, 0.0, 0.0), nu, dt)
+    return case, flow
+
+
+def kinematics(cloud_like):
+    """centre, v, omega of every instance (works for the CUDA cloud and for OracleAsCloud)"""
+    import numpy as np
+    st = cloud_like.oc.state_arrays() if hasattr(cloud_like, "oc") else cloud_like.state_arrays()
+    return np.concatenate([st["center"], st["v"], st["omega"], st["F"], st["T"]], axis=1)

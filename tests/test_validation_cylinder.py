@@ -55,3 +55,15 @@ def test_sphere_in_periodic_box_restatement_reproduces_reference_history():
     assert np.array_equal([c for _, c, _ in hist], g["cd"])
     assert np.array_equal([f for _, _, f in hist], g["body_force"])
     assert hist[-1][2][1] > 0, "a positive body force along the mean flow balances the drag"
+
+
+def test_colliding_spheres_coupled_loop_reproduces_reference_trajectory():
+    """forcing (moving target velocity) + stress integral + collision + sub-stepped integration + re-marking, coupled to
+    the flow: 16 fluid steps (1600 sub-steps), the pair collides on the way"""
+    g = np.load(os.path.join(gu.GOLDEN, "colliding_spheres_coupled.npz"))["history"]
+    case, flow = util.colliding_spheres_setup()
+    cloud = util.OracleAsCloud(case, stale_tables=True)
+    hist = np.array(mini_flow.run_moving_bodies(cloud, flow, len(g), state=util.kinematics))
+    assert np.array_equal(hist, g)
+    vx = hist[:, 0, 3]
+    assert vx[0] > 0.5 and vx[-1] < -0.1, "the pair must have collided and separated"

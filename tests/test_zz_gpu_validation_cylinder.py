@@ -41,3 +41,17 @@ def test_sphere_box_drag_history_matches_reference():
     assert np.max(np.abs(cd - g["cd"]) / np.abs(g["cd"])) < 1e-8
     assert np.max(np.abs(bf - g["body_force"])) < 1e-8 * np.max(np.abs(g["body_force"]))
     cloud.close()
+
+
+def test_colliding_spheres_coupled_trajectory_matches_reference():
+    """validation/collidingParticles-type loop on the GPU.  Stated tolerance over the 16 fluid steps (1600 sub-steps):
+    1e-8 relative on centres / velocities / angular velocities, 1e-7 on force / torque (relative to the largest entry)."""
+    g = np.load(os.path.join(gu.GOLDEN, "colliding_spheres_coupled.npz"))["history"]
+    case, flow = util.colliding_spheres_setup()
+    cloud = ParticleCloud(case)
+    hist = np.array(mini_flow.run_moving_bodies(cloud, flow, len(g), state=util.kinematics))
+    assert hist.shape == g.shape
+    for sl, tol in ((slice(0, 3), 1e-8), (slice(3, 6), 1e-8), (slice(6, 9), 1e-8), (slice(9, 15), 1e-7)):
+        ref = g[:, :, sl]
+        assert np.max(np.abs(hist[:, :, sl] - ref)) < tol * np.max(np.abs(ref)), sl
+    cloud.close()
