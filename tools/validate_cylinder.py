@@ -4,7 +4,7 @@
     python tools/validate_cylinder.py [--steps 8000] [--checker port|reference]
 
 Default: the CUDA path (needs a B200).  --checker runs the CPU checker instead (test infrastructure; the restatement is
-bit-identical to the reference's own code on this case, tests/test_validation_cylinder.py) - that is how the number in
+bit-identical to the reference's own code on this case, tests/test_validation_cases.py) - that is how the number in
 DESIGN.md §8 was produced while no GPU was available.  Literature anchor: Cd ~ 1.74 for an unbounded cylinder at Re = 30;
 the case is a transversally periodic row with 10 % blockage and only 5 d of upstream length, which raises it to ~2.1."""
 import argparse
