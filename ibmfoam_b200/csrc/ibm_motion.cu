@@ -78,6 +78,11 @@ struct Motion {
   // CUDA graph of the unfused sub-step sequence, cached for one schedule of local time steps
   cudaGraphExec_t graphExec = nullptr;
   std::vector<double> graphDts;
+  // A captured graph freezes its kernel arguments (the InstanceSoA pointers, which ctx_update swaps with the second set
+  // when it compacts the instance list) and its grid sizes (k5_pair_force is sized from the instance count): it is only
+  // replayed while both still hold.
+  bool graphValid = false;
+  int graphNInst = 0;
   long long graphLaunches = 0;
   int* dIdxKeys = nullptr; int* dIdxKeys2 = nullptr;
   double* dStats = nullptr;
@@ -1007,7 +1012,10 @@ static int ensure_motion(ibm_ctx* c) {
 }
 
 void motion_invalidate_groups(ibm_ctx* c) {
-  if (c->motion) ((Motion*)c->motion)->groupsValid = false;
+  if (c->motion) {
+    ((Motion*)c->motion)->groupsValid = false;
+    ((Motion*)c->motion)->graphValid = false;  // the instance arrays were exchanged / rewritten on the host side
+  }
 }
 
 int combine_forces(ibm_ctx* c) {
@@ -1129,7 +1137,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
   } else if (c->graphLoop5 && nSub <= 256) {
     // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
     // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
-    bool same = M->graphExec && (int)M->graphDts.size() == nSub;
+    bool same = M->graphExec && M->graphValid && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
     for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
     if (!same) {
       if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
@@ -1144,6 +1152,8 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       cudaGraphDestroy(g);
       IBM_CUDA(c, e);
       M->graphDts.assign(dts, dts + nSub);
+      M->graphValid = true;
+      M->graphNInst = c->nInst;
     }
     IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));
     c->nLaunch += M->graphLaunches;

@@ -17,3 +17,13 @@ def oracle_lib():
     from oracle import pyoracle
     pyoracle.build()
     return pyoracle
+
+
+# TEST INFRASTRUCTURE ONLY: `IBM_TEST_EMU_LIB=tools/cuda_emu/_build/libibmfoam_b200_emu.so pytest -m gpu ...` points the
+# ctypes loader at the CPU emulation build of the library (tools/cuda_emu/build_emu.py) so that the GPU parity tests can
+# be exercised on a machine without a GPU.  The product package has no such switch: ibmfoam_b200.capi always loads
+# ibmfoam_b200/lib/libibmfoam_b200.so, and that library refuses to run without a CUDA device.
+_EMU = os.environ.get("IBM_TEST_EMU_LIB")
+if _EMU:
+    from ibmfoam_b200 import capi as _capi
+    _capi.LIB_PATH = os.path.abspath(_EMU)

@@ -25,7 +25,7 @@ typedef void* cudaStream_t;
 #define gridDim (::emu::blk()->gridDim)
 
 inline void __syncthreads() { ::emu::syncthreads(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { ::emu::warp_barrier(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { ::emu::group_barrier(mask); }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __dmul_rn(double a, double b) { return a * b; }
@@ -48,7 +48,148 @@ inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 
-inline double __shfl_down_sync(unsigned, double v, int d) { return ::emu::shfl(v, ::emu::lane_id() + d); }
-inline double __shfl_xor_sync(unsigned, double v, int m) { return ::emu::shfl(v, ::emu::lane_id() ^ m); }
-inline int __shfl_down_sync(unsigned, int v, int d) { return (int)::emu::shfl((double)v, ::emu::lane_id() + d); }
-inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)::emu::shfl((double)v, ::emu::lane_id() ^ m); }
+inline double __shfl_down_sync(unsigned k, double v, int d) { return ::emu::shfl(k, v, ::emu::lane_id() + d); }
+inline double __shfl_xor_sync(unsigned k, double v, int m) { return ::emu::shfl(k, v, ::emu::lane_id() ^ m); }
+inline int __shfl_down_sync(unsigned k, int v, int d) { return (int)::emu::shfl(k, (double)v, ::emu::lane_id() + d); }
+inline int __shfl_xor_sync(unsigned k, int v, int m) { return (int)::emu::shfl(k, (double)v, ::emu::lane_id() ^ m); }
+inline double __shfl_sync(unsigned k, double v, int src) { return ::emu::shfl(k, v, src); }
+inline int __shfl_sync(unsigned k, int v, int src) { return (int)::emu::shfl(k, (double)v, src); }
+
+// ================================================================================================
+// Runtime API stand-in (whole-library emulation, tools/cuda_emu/build_emu.py): device memory is host memory, streams
+// are synchronous, events read the host clock, a captured graph is the list of recorded launches.
+// ================================================================================================
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned X = 1, unsigned Y = 1, unsigned Z = 1) : x(X), y(Y), z(Z) {}
+};
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorNotSupported = 801, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaStreamNonBlocking = 1 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrCooperativeLaunch = 95 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+
+namespace emu {
+struct Event { std::chrono::steady_clock::time_point t; };
+typedef std::vector<std::function<void()>> Graph;
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+inline Graph*& capturing() { static thread_local Graph* g = nullptr; return g; }
+inline void submit(std::function<void()> fn) {
+  if (capturing()) { capturing()->push_back(std::move(fn)); return; }
+  fn();
+}
+template <class K, class... A>
+inline void rt_launch(dim3 grid, dim3 block, size_t smem, K kern, A... args) {
+  auto tup = std::make_tuple(args...);  // arguments are evaluated NOW, like a real launch (also under graph capture)
+  submit([=]() {
+    std::lock_guard<std::mutex> lk(launch_mutex());  // one emulated kernel at a time (static __shared__ storage)
+    ::emu::launch(grid.x * grid.y * grid.z, block.x * block.y * block.z, smem, [&]() { std::apply(kern, tup); });
+  });
+}
+}  // namespace emu
+#define EMU_LAUNCH(kern, grid, block, smem, stream, ...) ::emu::rt_launch(dim3(grid), dim3(block), (size_t)(smem), kern, ##__VA_ARGS__)
+
+typedef emu::Event* cudaEvent_t;
+typedef emu::Graph* cudaGraph_t;
+typedef emu::Graph* cudaGraphExec_t;
+
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = std::malloc(n ? n : 1);
+  if (!*p) return 2;
+  std::memset(*p, 0xA5, n);  // device memory is not zeroed: make reads of uninitialised memory visible
+  return cudaSuccess;
+}
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
+  emu::submit([=]() { std::memmove(d, s, n); });
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) {
+  emu::submit([=]() { std::memset(d, v, n); });
+  return cudaSuccess;
+}
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)1; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu::Event; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaLaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+  if (emu::capturing()) return cudaErrorInvalidValue;
+  emu::capturing() = new emu::Graph;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = emu::capturing(); emu::capturing() = nullptr; return *g ? cudaSuccess : cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long = 0) { *e = new emu::Graph(*g); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) {
+  for (auto& fn : *g) fn();
+  return cudaSuccess;
+}
+
+// ---- more device intrinsics (whole-library emulation) ----
+inline unsigned __ballot_sync(unsigned mask, int pred) { return ::emu::ballot(mask, pred != 0); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline void __threadfence() {}
+inline int __shfl_up_sync(unsigned k, int v, int d) { const int l = ::emu::lane_id(); return (int)::emu::shfl(k, (double)v, l - d >= 0 ? l - d : l); }
+inline double __shfl_up_sync(unsigned k, double v, int d) { const int l = ::emu::lane_id(); return ::emu::shfl(k, v, l - d >= 0 ? l - d : l); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
+inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { unsigned o = *p; if (o == c) *p = v; return o; }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
+inline long long __double_as_longlong(double d) { long long l; std::memcpy(&l, &d, 8); return l; }
+inline double __longlong_as_double(long long l) { double d; std::memcpy(&d, &l, 8); return d; }
+using std::fabs;
+using std::sqrt;
+using std::sin;
+using std::cos;
+using std::atan2;
+using std::acos;
+using std::tan;
+using std::fmax;
+using std::fmin;
+inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
+inline size_t max(size_t a, size_t b) { return a > b ? a : b; }

@@ -10,10 +10,12 @@
 #pragma once
 #include <ucontext.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <vector>
 
 namespace emu {
@@ -22,11 +24,14 @@ struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 
 struct PendingCopy { void* dst; const void* src; size_t n; };
 
+struct GroupBarrier { unsigned arrived = 0; long gen = 0; };  // rendez-vous of the lanes named by one mask
+
 struct Fiber {
   std::vector<PendingCopy> pending;  // cp.async copies issued and not yet waited for (performed at the wait)
   ucontext_t ctx;
   char* stack = nullptr;
-  int state = 0;  // 0 runnable, 1 at block barrier, 2 at warp barrier, 3 done
+  int state = 0;  // 0 runnable, 1 at block barrier, 2 at warp-level rendez-vous, 3 done
+  const GroupBarrier* waitObj = nullptr;
   long warpGen = 0;
   Dim3 tid;
 };
@@ -37,8 +42,7 @@ struct Block {
   int cur = -1;
   Dim3 blockIdx, blockDim, gridDim;
   std::vector<unsigned char> dynSmem;
-  std::vector<long> warpGen;       // generation counter per warp
-  std::vector<int> warpArrived;
+  std::vector<std::map<unsigned, GroupBarrier>> groups;  // per warp: one rendez-vous object per participation mask
   std::vector<double> shflBuf;     // [warp][32] exchange slots (doubles hold ints exactly)
   const std::function<void()>* body = nullptr;
 };
@@ -57,31 +61,55 @@ inline void syncthreads() {
 inline int lane_id() { const Fiber& f = cur(); return (int)(f.tid.x % 32); }
 inline int warp_id() { const Fiber& f = cur(); return (int)(f.tid.x / 32); }
 
-// all 32 lanes of the warp (or all lanes that exist, for a partial last warp) rendez-vous
-inline void warp_barrier() {
+inline unsigned existing_lanes() {
+  Block* b = blk();
+  const int lanes = std::min<int>(32, (int)b->blockDim.x - 32 * warp_id());
+  return lanes >= 32 ? 0xffffffffu : ((1u << lanes) - 1u);
+}
+inline int warp_lanes() { return __builtin_popcount(existing_lanes()); }
+
+// the lanes named in `mask` rendez-vous (sub-warp groups with disjoint masks proceed independently, as on the hardware;
+// a lane that is named but has exited, or never arrives, is reported as a deadlock by the scheduler)
+inline void group_barrier(unsigned mask) {
   Block* b = blk();
   Fiber& f = cur();
-  const int w = warp_id();
-  const int lanes = std::min<int>(32, (int)b->blockDim.x - 32 * w);
-  const long g = b->warpGen[w];
-  if (++b->warpArrived[w] == lanes) {
-    b->warpArrived[w] = 0;
-    ++b->warpGen[w];
+  mask &= existing_lanes();
+  GroupBarrier& g = b->groups[warp_id()][mask];
+  g.arrived |= 1u << lane_id();
+  if ((g.arrived & mask) == mask) {
+    g.arrived = 0;
+    ++g.gen;
     return;
   }
   f.state = 2;
-  f.warpGen = g;
+  f.waitObj = &g;
+  f.warpGen = g.gen;
   yield();
 }
+inline void warp_barrier() { group_barrier(0xffffffffu); }
 
-inline double shfl(double v, int srcLane) {
+// every named lane deposits a predicate, all read the word (ballot)
+inline unsigned ballot(unsigned mask, bool pred) {
   Block* b = blk();
   const int w = warp_id(), l = lane_id();
+  mask &= existing_lanes();
+  b->shflBuf[32 * w + l] = pred ? 1.0 : 0.0;
+  group_barrier(mask);
+  unsigned word = 0;
+  for (int s = 0; s < 32; ++s)
+    if (((mask >> s) & 1u) && b->shflBuf[32 * w + s] != 0.0) word |= (1u << s);
+  group_barrier(mask);
+  return word;
+}
+
+inline double shfl(unsigned mask, double v, int srcLane) {
+  Block* b = blk();
+  const int w = warp_id(), l = lane_id();
+  mask &= existing_lanes();
   b->shflBuf[32 * w + l] = v;
-  warp_barrier();
-  const int lanes = std::min<int>(32, (int)b->blockDim.x - 32 * w);
-  const double r = (srcLane >= 0 && srcLane < lanes) ? b->shflBuf[32 * w + srcLane] : v;
-  warp_barrier();
+  group_barrier(mask);
+  const double r = (srcLane >= 0 && srcLane < 32 && ((mask >> srcLane) & 1u)) ? b->shflBuf[32 * w + srcLane] : v;
+  group_barrier(mask);
   return r;
 }
 
@@ -110,8 +138,7 @@ inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std:
   b.body = &body;
   for (unsigned bx = 0; bx < gridX; ++bx) {
     b.blockIdx.x = bx;
-    b.warpGen.assign(nWarps, 0);
-    b.warpArrived.assign(nWarps, 0);
+    b.groups.assign((size_t)nWarps, {});
     b.shflBuf.assign(32 * (size_t)nWarps, 0.0);
     // shared memory is NOT cleared between blocks: like the hardware, a kernel must not rely on its initial content
     for (unsigned t = 0; t < blockX; ++t) {
@@ -132,7 +159,7 @@ inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std:
       for (unsigned t = 0; t < blockX; ++t) {
         Fiber& f = b.fibers[t];
         if (f.state == 3) continue;
-        if (f.state == 2 && b.warpGen[t / 32] != f.warpGen) f.state = 0;
+        if (f.state == 2 && f.waitObj->gen != f.warpGen) f.state = 0;
         if (f.state == 0) {
           b.cur = (int)t;
           swapcontext(&b.sched, &f.ctx);
