@@ -1,0 +1,79 @@
+"""The product's CUDA sources under the CPU emulation (tools/cuda_emu): `build_emu.py` compiles ibmfoam_b200/csrc/*.cu
+unchanged (only `<<<...>>>` and `extern __shared__` are rewritten syntactically) against stand-in CUDA headers, and the GPU
+parity tests are then run against that library in a child pytest.  This is how kernel and host logic is checked where no
+GPU exists - it found the stale-graph bug of loop 5 - and it is test infrastructure only: the product never
+loads the emulated library, `-m gpu` on a B200 remains the parity gate, and nothing here says anything about performance.
+
+Default: a subset that runs in about a minute after a ~1.5 min build.  IBM_RUN_EMULATED_FULL=1 runs every GPU test file
+(several minutes: loop 5 executes ~10 kernels x 100 sub-steps per fluid step, one fiber per CUDA thread)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    import build_emu
+    return build_emu.build()
+
+
+def _child(emu_lib, args, timeout):
+    env = dict(os.environ, IBM_TEST_EMU_LIB=emu_lib)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", *args], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=timeout)
+    tail = (r.stdout + r.stderr)[-2500:]
+    assert r.returncode == 0, tail
+    return tail
+
+
+SUBSET = [
+    "tests/test_gpu_marking.py::test_marking_bit_exact",
+    "tests/test_gpu_zz_reference_vectors.py::test_marking_forcing_stress_against_reference_vectors",
+    "tests/test_gpu_zz_reference_vectors.py::test_trajectories_against_reference_vectors[col8-graph]",
+    "tests/test_zz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned]",
+    "tests/test_zz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
+    "tests/test_zz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
+]
+
+
+def test_gpu_parity_subset_under_emulation(emu_lib):
+    out = _child(emu_lib, SUBSET, timeout=1500)
+    assert " passed" in out and "failed" not in out
+
+
+def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
+    """shim/particleCloud.C + the emulated library against the reference's own class through the same solver-side driver"""
+    import numpy as np
+    import dropin_util as du
+    if not os.path.exists(du.REFERENCE_BIN):
+        pytest.skip("dropin_reference not built (needs /root/reference)")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "shim", "dropin"), "-s", "shim_emu"])
+    case, n_steps, n_outer = du.CASES["cyl2d_fixed"]()
+    cp = str(tmp_path / "case.txt")
+    du.write_case(cp, case, n_steps, n_outer)
+    outs = {}
+    for side, binary in (("reference", du.REFERENCE_BIN), ("shim", os.path.join(du.BUILD, "dropin_shim_emu"))):
+        op = str(tmp_path / f"{side}.bin")
+        r = du.run(binary, cp, op)
+        assert r.returncode == 0, (side, r.stderr)
+        outs[side] = du.parse(op)
+    (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]
+    assert h_ref == h_shim and [t for t, _ in rec_ref] == [t for t, _ in rec_shim]
+    for (tag, a), (_, b) in zip(rec_ref, rec_shim):
+        if tag in ("index", "copy", "active", "CoNum"):
+            assert np.array_equal(a, b), tag
+        else:
+            assert np.max(np.abs(a - b)) <= (1e-12 if tag == "F" else 1e-9) * max(np.max(np.abs(a)), 1e-300), tag
+
+
+@pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (several minutes)")
+@pytest.mark.parametrize("path", ["tests/test_gpu_forcing.py", "tests/test_gpu_marking.py", "tests/test_gpu_stress.py", "tests/test_gpu_motion.py",
+                                  "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_zz_gpu_v5_kernels.py",
+                                  "tests/test_zz_gpu_validation_cases.py"])
+def test_gpu_parity_file_under_emulation(emu_lib, path):
+    _child(emu_lib, [path], timeout=6000)
