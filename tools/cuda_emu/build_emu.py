@@ -97,11 +97,20 @@ def transform(text):
     return text
 
 
-def build(verbose=False):
+def build(verbose=False, asan=False):
+    """asan=True: a second library (…_asan.so) instrumented with AddressSanitizer - device memory is host memory here, so
+    an out-of-bounds global or static-shared access of a kernel is reported like compute-sanitizer's memcheck would
+    (run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)."""
+    global SRC_OUT, LIB
+    if asan:
+        SRC_OUT = os.path.join(OUT, "src_asan")
+        LIB = os.path.join(OUT, "libibmfoam_b200_emu_asan.so")
     os.makedirs(SRC_OUT, exist_ok=True)
     objs = []
     units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     flags = ["-x", "c++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-w", "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("emu.hpp", "cuda_runtime.h", "cuda_pipeline.h",
                                                                                                  "cooperative_groups.h", "build_emu.py")]
     deps.append(os.path.join(HERE, "cub", "cub.cuh"))
@@ -123,7 +132,8 @@ def build(verbose=False):
             raise RuntimeError(f"emulation build failed on {u}")
         if verbose:
             print("compiled", u)
-    r = subprocess.run(["g++", "-shared", "-o", LIB, *objs, "-ldl", "-lpthread"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", LIB, *objs, "-ldl", "-lpthread"] + (["-fsanitize=address"] if asan else []),
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stderr[-6000:])
         raise RuntimeError("emulation link failed")
@@ -131,4 +141,4 @@ def build(verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose=True))
+    print(build(verbose=True, asan="--asan" in sys.argv))
