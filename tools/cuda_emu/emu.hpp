@@ -136,7 +136,23 @@ inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std:
   b.dynSmem.assign(smemBytes + 128, 0);
   const int nWarps = (int)(blockX + 31) / 32;
   b.body = &body;
-  for (unsigned bx = 0; bx < gridX; ++bx) {
+  // EMU_ORDER=reverse | shuffle:<seed> perturbs the order in which blocks run and in which the fibers of a block are
+  // resumed: a kernel whose result depends on it (beyond the rounding of floating-point atomics) has a race
+  static const char* orderEnv = std::getenv("EMU_ORDER");
+  const bool reverse = orderEnv && std::strcmp(orderEnv, "reverse") == 0;
+  const bool shuffle = orderEnv && std::strncmp(orderEnv, "shuffle", 7) == 0;
+  static unsigned long long rng = (shuffle && std::strlen(orderEnv) > 8) ? std::strtoull(orderEnv + 8, nullptr, 10) * 2654435761ull + 1 : 88172645463325252ull;
+  auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  std::vector<unsigned> blockOrder(gridX), threadOrder(blockX);
+  for (unsigned i = 0; i < gridX; ++i) blockOrder[i] = reverse ? gridX - 1 - i : i;
+  for (unsigned i = 0; i < blockX; ++i) threadOrder[i] = reverse ? blockX - 1 - i : i;
+  if (shuffle) {
+    for (unsigned i = gridX; i > 1; --i) std::swap(blockOrder[i - 1], blockOrder[next() % i]);
+  }
+  for (unsigned bo = 0; bo < gridX; ++bo) {
+    const unsigned bx = blockOrder[bo];
+    if (shuffle)
+      for (unsigned i = blockX; i > 1; --i) std::swap(threadOrder[i - 1], threadOrder[next() % i]);
     b.blockIdx.x = bx;
     b.groups.assign((size_t)nWarps, {});
     b.shflBuf.assign(32 * (size_t)nWarps, 0.0);
@@ -156,7 +172,8 @@ inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std:
     while (done < blockX) {
       bool progressed = false;
       unsigned atBarrier = 0, live = 0;
-      for (unsigned t = 0; t < blockX; ++t) {
+      for (unsigned to = 0; to < blockX; ++to) {
+        const unsigned t = threadOrder[to];
         Fiber& f = b.fibers[t];
         if (f.state == 3) continue;
         if (f.state == 2 && f.waitObj->gen != f.warpGen) f.state = 0;
