@@ -36,6 +36,8 @@ struct PatchDev {
   double lo[3], hi[3]; // bounding box of the face centres (cheap rejection: |centre - Cf| >= distance to the box)
   int planar;          // every face has bit-identical Sf and magSf: Sf/magSf is one vector for the whole patch
   double nrm[3];       // that vector
+  int uniformShift;    // cyclic pair that is a pure translation: Cf_neighbour[f] - Cf[f] is one vector for every face
+  double shift[3];     // that vector (the image of a centre c is c + shift up to rounding, whichever face is hit)
 };
 
 struct MotionDev {
@@ -470,6 +472,18 @@ __device__ __forceinline__ void d5_cyclic_candidates(MotionDev m, InstanceSoA in
     if (p.planar) {  // patchHit needs (v & norm) > 0 for the hit face (particleIBM.C:511): same test, once per patch
       const D3 v = ld3(in.v, i);
       if (!(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
+    }
+    if (p.uniformShift) {
+      // found() (particleCloud.C:447-479, App. B #15) rejects the new copy when an instance of the same index lies
+      // within 1e-4 of the image centre R + Cf_neighbour[face].  For a pure translation that centre is c + shift up to
+      // ~1e-12 whichever face is hit, so an instance within HALF that distance settles it here, without the face scan
+      // (in steady state nearly every candidate already has its copy); anything closer to the threshold goes on to the
+      // exact test of stage 2.
+      const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
+      bool have = false;
+      for (int mem = m.idxHead[in.index[i]]; mem >= 0 && !have; mem = m.instNext[mem])
+        have = magSqr3(nc - ld3(in.c, mem)) < 0.25e-8;
+      if (have) continue;
     }
     int h = atomicAdd(m.candCount, 1);
     if (h < m.candCap) m.candKey[h] = slot * m.cap + i;
@@ -957,6 +971,18 @@ static int motion_init(ibm_ctx* c) {
           if (std::fabs(f[ta] - ea) > 1e-9 * d3[ta] || std::fabs(f[tb] - eb) > 1e-9 * d3[tb]) match = false;
         }
       q.latticeOrdered = match ? 1 : 0;
+    }
+    q.uniformShift = 0;
+    if (ph.type == IBM_CYCLIC && ph.neighb >= 0 && ph.neighb < (int)c->patches.size() && q.nFaces > 0 &&
+        c->patches[ph.neighb].nFaces() == q.nFaces) {
+      const auto& nb = c->patches[ph.neighb];
+      double scale = 0.0;
+      for (int a = 0; a < 3; ++a) { q.shift[a] = nb.Cf[a] - ph.Cf[a]; scale = std::max(scale, std::fabs(q.shift[a])); }
+      bool uniform = true;
+      for (int f = 1; f < q.nFaces && uniform; ++f)
+        for (int a = 0; a < 3; ++a)
+          if (std::fabs((nb.Cf[3 * (size_t)f + a] - ph.Cf[3 * (size_t)f + a]) - q.shift[a]) > 1e-9 * scale) uniform = false;
+      q.uniformShift = uniform ? 1 : 0;
     }
     pd.push_back(q);
   }
