@@ -98,10 +98,31 @@ class ClockSampler:
 
 
 def make_case(workload):
+    """the synthetic assembly of the workload; the (deterministic, seeded) sphere placement is a pure-Python loop of ~25 s
+    for 10^5 spheres, so its result is kept in /tmp for the other processes of the run (probe child, ranks, reference arm)"""
     from ibmfoam_b200 import cases
     n, moving = WORKLOADS[workload]
-    return cases.assembly(n=n, phi=0.2, moving=moving,
-                          n_particles=100000 if n == 512 else None, cyclic_without_walls=True)
+    P = 100000 if n == 512 else None
+    cache = os.path.join("/tmp", f"ibmfoam_b200_positions_{workload}_seed12345.npy")
+    pos = None
+    try:
+        if os.path.exists(cache):
+            pos = np.load(cache)
+    except Exception:
+        pos = None
+    try:
+        case = cases.assembly(n=n, phi=0.2, moving=moving, n_particles=P, cyclic_without_walls=True, positions=pos)
+    except AssertionError:  # a stale cache of another size
+        case = cases.assembly(n=n, phi=0.2, moving=moving, n_particles=P, cyclic_without_walls=True)
+        pos = None
+    if pos is None and int(os.environ.get("RANK", "0")) == 0:
+        try:
+            tmp = cache + f".{os.getpid()}.tmp.npy"
+            np.save(tmp, case.particles.position)
+            os.replace(tmp, cache)
+        except Exception:
+            pass
+    return case
 
 
 def device_fields(mesh, device):
@@ -221,16 +242,50 @@ def run_probe(args):
     eF = float(np.max(np.abs(res[5][0] - res[None][0])) / np.max(np.abs(res[None][0])))
     eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
     out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
-    if not (eF < 1e-11 and eT < 1e-9):
+    out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
+    # the quiet/active split of loop 5 must give the very same trajectory as the unsplit path (bit for bit)
+    fast = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    fast.particles.v *= 25.0
+    fast.dt = 0.5
+    traj = {}
+    for split in (0, 1):
+        gc = ParticleCloud(fast)
+        gc.set_option("active_loop5", split)
+        rng = np.random.default_rng(0)
+        for _ in range(4):
+            gc.set_force_torque(rng.normal(0, 1e-3, (gc.nParticles(), 6)))
+            gc.combineForces()
+            gc.advance(fast.dt)
+        traj[split] = gc.state_arrays()
+        gc.close()
+    out["loop5_split_ok"] = bool(all(np.array_equal(traj[0][k], traj[1][k]) for k in traj[0]))
+    if not (out["kernels_ok"] or out["loop5_split_ok"]):
         print(json.dumps(out))
         return
-    # (b) timing on a 256^3 / 12.5k-sphere workload, device-resident fields
+    t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}}
+    # (b) loop 5 at the run's own instance count (it needs the particles, not the fields): without / with the split
+    if out["loop5_split_ok"]:
+        big = make_case(args.workload)
+        if big.cloud.moving:
+            for split in (0, 1):
+                gc = ParticleCloud(big, device=0)
+                gc.set_option("active_loop5", split)
+                for _ in range(2):
+                    gc.advance(big.dt)
+                gc.sync()
+                gc.timings(reset=True)
+                for _ in range(4):
+                    gc.advance(big.dt)
+                gc.sync()
+                t["advance_ms"][str(split)] = gc.timings()["advance_ms"] / 4
+                gc.close()
+        del big
+    # (c) forcing / stress kernels on a 256^3 / 12.5k-sphere workload, device-resident fields
     case = make_case("big256")
     dev = torch.device("cuda", 0)
     U, Uold, S, P, Tau = device_fields(case.mesh, dev)
     torch.cuda.synchronize()
     cloud = ParticleCloud(case, device=0)
-    t = {"forcing_ms": {}, "stress_ms": {}}
     for gen_f, gen_s in ((DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]), (5, 5)):
         cloud.set_kernel_variant(gen_f, gen_s)
         for _ in range(2):
@@ -251,7 +306,7 @@ def run_probe(args):
     print(json.dumps(out))
 
 
-def choose_variants(local_rank, timeout_s=240):
+def choose_variants(local_rank, timeout_s=360):
     """parent: run the probe in a child process on this rank's GPU (or reuse the result an earlier run on this box left in
     /tmp) and pick, per kernel, the faster verified generation.  Returns (forcing, stress, info)."""
     info = None
@@ -279,14 +334,17 @@ def choose_variants(local_rank, timeout_s=240):
                 json.dump(info, fh)
         except Exception:
             pass
-    fv, sv = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]
+    fv, sv, split = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0
     if info.get("ok"):
-        fm, sm = info["forcing_ms"], info["stress_ms"]
-        if fm.get("5", 1e30) < fm.get(str(fv), 0.0):
-            fv = 5
-        if sm.get("5", 1e30) < sm.get(str(sv), 0.0):
-            sv = 5
-    return fv, sv, info
+        fm, sm, am = info["forcing_ms"], info["stress_ms"], info.get("advance_ms", {})
+        if info.get("kernels_ok"):
+            if fm.get("5", 1e30) < fm.get(str(fv), 0.0):
+                fv = 5
+            if sm.get("5", 1e30) < sm.get(str(sv), 0.0):
+                sv = 5
+        if info.get("loop5_split_ok") and am.get("1", 1e30) < am.get("0", 0.0):
+            split = 1
+    return fv, sv, split, info
 
 
 def _ref_worker(args):
@@ -378,12 +436,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     # which kernel generation: local rank 0 asks a child process BEFORE joining the process group (the others wait in the
     # rendezvous), then everyone gets its answer
-    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]]
+    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0]   # forcing generation, stress generation, loop-5 split
     probe_info = None
     if args.variant >= 0:
-        variants = [args.variant, args.variant]
+        variants = [args.variant, args.variant, 0]
     elif not args.no_probe and rank == 0:
-        variants[0], variants[1], probe_info = choose_variants(local_rank)
+        variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -409,6 +467,7 @@ def main():
     t0 = time.time()
     cloud = ParticleCloud(case, device=local_rank, slab=slab, nccl_id=nccl_id, rank=rank, n_ranks=world)
     cloud.set_kernel_variant(variants[0], variants[1])
+    cloud.set_option("active_loop5", variants[2])
     setup_s = time.time() - t0
     have_motion = True
     try:
@@ -433,7 +492,7 @@ def main():
     # A generation chosen by the probe is verified once more at the FULL size, on the device, against the default
     # generation (forcing field 1e-11, force/torque 1e-9 relative); any disagreement reverts to the defaults.
     verify = None
-    if args.variant < 0 and variants != [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]]:
+    if args.variant < 0 and variants[:2] != [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]]:
         Fa = torch.empty_like(U)
         Fb = torch.empty_like(U)
 
@@ -458,7 +517,7 @@ def main():
             ok = bool(flag.item())
         verify = {"forcing_rel_diff": eF, "force_torque_rel_diff": eT, "ok": ok}
         if not ok:
-            variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]]
+            variants[0], variants[1] = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]
         cloud.set_kernel_variant(variants[0], variants[1])
         del Fa, Fb
 
@@ -595,7 +654,9 @@ def main():
                            "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)" if have_motion else "n/a",
                            "step": "forcing + solve(stress, combine, sub-steps, re-marking)" if have_motion else "forcing + stress + re-marking (loop 5 not built)",
                            "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s,
-                           "kernel_generations": {"forcing": variants[0], "stress": variants[1],
+                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "loop5_quiet_active_split": bool(variants[2]),
+                                                  "loop5_active_instances": cloud.counter("loop5_active_instances") if variants[2] else None,
+                                                  "loop5_fallbacks": cloud.counter("loop5_fallbacks") if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else
                                                                   "library defaults" if args.no_probe else
                                                                   "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),

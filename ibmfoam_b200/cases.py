@@ -260,7 +260,7 @@ def two_spheres(n=64, e=1.0, speed=1.0, gap=0.5) -> Case:
     return Case("two_spheres", mesh, cloud, parts, dt=0.25)
 
 
-def assembly(n=128, phi=0.2, seed=12345, moving=False, d=8.0, n_particles=None, cyclic_without_walls=False) -> Case:
+def assembly(n=128, phi=0.2, seed=12345, moving=False, d=8.0, n_particles=None, cyclic_without_walls=False, positions=None) -> Case:
     """Synthetic assembly (asm / big): n^3 periodic unit-spacing box of monodisperse spheres d = 8, delta = 1,
     nTheta = 50 (nk = 25).  asm: n=128, fixed, P=1565.  big: n=512, P=100000, moving+rotating."""
     mesh = MeshSpec(n, n, n, origin=(0.0, 0.0, 0.0), delta=(1.0, 1.0, 1.0),
@@ -268,7 +268,9 @@ def assembly(n=128, phi=0.2, seed=12345, moving=False, d=8.0, n_particles=None, 
                              (ZMIN, CYCLIC, 5), (ZMAX, CYCLIC, 4)])
     vp = math.pi * d ** 3 / 6.0
     P = n_particles if n_particles is not None else int(round(phi * n ** 3 / vp))
-    pos = place_spheres(P, (0, 0, 0), (n, n, n), d / 2.0, seed=seed, periodic=True)
+    # positions: the result of an earlier place_spheres call with the same arguments (the placement is a pure-Python loop)
+    pos = place_spheres(P, (0, 0, 0), (n, n, n), d / 2.0, seed=seed, periodic=True) if positions is None else np.asarray(positions, dtype=np.float64)
+    assert pos.shape == (P, 3)
     rng = np.random.default_rng(seed + 1)
     U0 = 1.0
     if moving:

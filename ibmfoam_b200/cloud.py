@@ -216,6 +216,11 @@ class ParticleCloud:
     def set_option(self, name, value):
         check(self._L.ibm_set_option(self._h, name.encode(), int(value)), self._h)
 
+    def counter(self, name):
+        v = C.c_longlong()
+        check(self._L.ibm_get_counter(self._h, name.encode(), C.byref(v)), self._h)
+        return v.value
+
     def sync(self):
         check(self._L.ibm_sync(self._h), self._h)
 

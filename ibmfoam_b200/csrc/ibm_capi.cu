@@ -442,6 +442,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_FUSED_LOOP5")) c->fusedLoop5 = std::atoi(e) != 0;  // developer switches (profiling)
   if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
   if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
   LatticeDev& L = c->L;
   L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
@@ -989,11 +990,18 @@ int ibm_set_kernel_variant(ibm_ctx* c, int fv, int sv) {
   return IBM_OK;
 }
 
+int ibm_get_counter(ibm_ctx* c, const char* name, long long* value) {
+  if (!c || !name || !value) return IBM_E_ARG;
+  return motion_counter(c, name, value) ? IBM_OK : ctx_fail(c, IBM_E_ARG, std::string("ibm_get_counter: unknown counter ") + name);
+}
+
 int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (!c || !name) return IBM_E_ARG;
   if (std::strcmp(name, "fused_loop5") == 0) { c->fusedLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "graph_loop5") == 0) { c->graphLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
+  if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_option: unknown option ") + name);
 }
 

@@ -87,6 +87,9 @@ struct ibm_ctx {
   bool chunk256 = false;    // direct-gather forcing kernel: 256 shell cells per work item (one item per d=8 sphere)
   bool fusedLoop5 = false;  // one persistent cooperative kernel for the sub-step loop
   bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph
+  bool activeLoop5 = false; // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
+                            // sub-step; written after round 1's GPU budget was spent, verified under emulation only
+  int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (tests shrink it to force the fallback)
   // motion (loop 5) scratch lives in ibm_motion.cu
   void* motion = nullptr;
   // comm
@@ -111,6 +114,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats);
 int motion_substep(ibm_ctx* c, double localDt);
 void motion_destroy(ibm_ctx* c);
 void motion_invalidate_groups(ibm_ctx* c);
+bool motion_counter(ibm_ctx* c, const char* name, long long* value);
 int combine_forces(ibm_ctx* c);
 // ibm_comm.cu
 void comm_destroy(ibm_ctx* c);

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "ibm_ctx.h"
 
@@ -66,6 +67,15 @@ struct MotionDev {
   const PatchDev* patches; const int* wallPatch; const int* cycPatch;
   double gx, gy, gz, e;
   int moving, rotating;
+  // quiet / active split of a fluid step (option active_loop5): see the block comment above k5q_bounds
+  int activeMode;                  // 1 while the split is in force (append_link then keeps the active list up to date)
+  int* act; int* nAct;             // instances that can take part in a contact, a wall / patch hit or a copy group this step
+  int* quiet;                      // 1 = integrates alone, all sub-steps in one kernel
+  double* c0;                      // [3][cap] centre at the start of the step (at creation for copies appended later)
+  unsigned long long* vaBits;      // bit patterns of max |v| and max |F/m + g| over the instances at the start of the step
+  double* budget;                  // S: displacement an instance is assumed not to exceed during the step
+  int* violated;                   // an active instance moved farther than S: the step is redone without the split
+  double safety;
 };
 
 struct Motion {
@@ -88,6 +98,13 @@ struct Motion {
   long long graphLaunches = 0;
   int* dIdxKeys = nullptr; int* dIdxKeys2 = nullptr;
   double* dStats = nullptr;
+  // quiet / active split: what is needed to redo a step whose displacement budget was exceeded
+  double* snap = nullptr;       // [12][cap] c, theta, v, omega at the start of the step
+  int* snapActive = nullptr;    // [cap]
+  int* snapMaxCopies = nullptr; // [nParticles]
+  bool graphActive = false;     // the captured graph is of the split sequence
+  double graphSafety = 0.0;     // ... with this safety factor (MotionDev is captured by value)
+  long long nFallbacks = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -606,6 +623,12 @@ __device__ __forceinline__ void d5_append_link(MotionDev m, InstanceSoA in) {
     int tail = m.idxTail[idx];
     if (tail >= 0) m.instNext[tail] = dst; else m.idxHead[idx] = dst;
     m.idxTail[idx] = dst;
+    if (m.activeMode) {  // a copy belongs to a group of more than one instance: active from its creation on
+      m.act[*m.nAct] = dst;
+      *m.nAct += 1;
+      m.quiet[dst] = 0;
+      for (int q = 0; q < 3; ++q) m.c0[(size_t)q * m.cap + dst] = in.c[q][dst];
+    }
   }
   *m.nInst = n0 + total;
 }
@@ -742,6 +765,170 @@ __global__ void k5_cyclic_detect(MotionDev m, LatticeDev L, InstanceSoA in, cons
 __global__ void k5_append(MotionDev m, InstanceSoA in) { d5_append(m, in, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void k5_append_link(MotionDev m, InstanceSoA in) {
   if (threadIdx.x == 0 && blockIdx.x == 0) d5_append_link(m, in);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quiet / active split of a fluid step (option active_loop5; same results, less work per sub-step).
+//
+// The hydrodynamic force and torque are frozen over the ~100 sub-steps of particleCloud::solve (particleCloud.C:1247-1275),
+// so an instance that cannot touch anything during the step - no other body, no wall, no periodic patch - and that is the
+// only instance of its index just integrates  v += dt (F/m + g); x += dt v; ...  (particleIBM.C:393-450) on its own: all
+// its sub-steps are done by ONE thread in ONE kernel (k5q_quiet), with the very arithmetic of the per-sub-step path.  Only
+// the remaining ACTIVE instances (a few per cent of a dilute-to-moderate suspension) go through the per-sub-step chain of
+// bins, pair search, wall / patch tests, copy handling and merging, on a compact list.
+//
+// "Cannot touch anything" is decided at the start of the step from a displacement budget
+//     S = safety * (max|v| dt + max|F/m + g| dt^2 / 2)          (maxima over all instances, dt = the fluid step)
+// an instance is ACTIVE when its index has several instances, when another body's centre is within
+// (Dmax_i + Dmax_j)/2 + 2 S  (particleIBM.C:56-59 is the reference's own early-out at (Dmax_i + Dmax_j)/2), or when a
+// wall or periodic patch is within its reach + S.  A quiet instance moves at most S/safety by construction (it feels no
+// impulse); an active one is CHECKED: if it ever gets farther than S from where it started (impulses can speed it up),
+// `violated` is raised and the host redoes the whole step from a snapshot without the split.  Under that check two bodies
+// that are not both active can never come within contact distance, so the split changes nothing but the work done.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmax_of(const ShapeClassDev& s) { return s.kind == 2 ? fmax(s.a, fmax(s.b, s.l)) : s.d; }
+
+__global__ void k5q_bounds(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double sp = 0.0, ac = 0.0;
+  if (i < *m.nInst && in.onMesh[i] != 0) {
+    const ShapeClassDev* sc = classes + in.cls[i];
+    const double mass = sc->V * in.rho[i];
+    sp = mag3(ld3(in.v, i));
+    ac = mag3(ld3(in.F, i) / mass + D3{m.gx, m.gy, m.gz});
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sp = fmax(sp, __shfl_xor_sync(0xffffffffu, sp, o));
+    ac = fmax(ac, __shfl_xor_sync(0xffffffffu, ac, o));
+  }
+  if ((threadIdx.x & 31) == 0) {  // non-negative doubles order like their bit patterns
+    atomicMax(m.vaBits, (unsigned long long)__double_as_longlong(sp));
+    atomicMax(m.vaBits + 1, (unsigned long long)__double_as_longlong(ac));
+  }
+}
+
+__global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dtStep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double vmax = __longlong_as_double((long long)m.vaBits[0]), amax = __longlong_as_double((long long)m.vaBits[1]);
+  const double S = m.safety * (vmax * dtStep + 0.5 * amax * dtStep * dtStep) + 1e-12 * m.binEdge;
+  if (i == 0) *m.budget = S;
+  if (i >= *m.nInst) return;
+  const D3 c = ld3(in.c, i);
+  for (int q = 0; q < 3; ++q) m.c0[(size_t)q * m.cap + i] = in.c[q][i];
+  int quiet = 1;
+  if (in.onMesh[i] != 0) {  // (an instance that is off the mesh does not move at all: particleIBM.C:400-403)
+    const ShapeClassDev* sc = classes + in.cls[i];
+    const int head = m.idxHead[in.index[i]];
+    if (head >= 0 && m.instNext[head] >= 0) quiet = 0;
+    if (quiet && m.moving) {
+      const double reach = sc->Rbound + S;
+      for (int w = 0; w < m.nWalls && quiet; ++w)
+        if (patch_in_reach(m.patches[m.wallPatch[w]], c, reach)) quiet = 0;
+      for (int s = 0; s < m.nCyc && quiet; ++s)
+        if (patch_in_reach(m.patches[m.cycPatch[s]], c, reach)) quiet = 0;
+    }
+    if (quiet && m.moving) {
+      if (2.0 * S > m.binEdge) quiet = 0;  // the +-2-bin search below no longer covers the cut-off: no split this step
+      else {
+        int bx, by, bz;
+        bin_of(m, c, bx, by, bz);
+        const double di = dmax_of(*sc);
+        for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1) && quiet; ++z)
+          for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1) && quiet; ++y)
+            for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1) && quiet; ++x) {
+              const int bin = x + m.nbx * (y + m.nby * z);
+              const int nb = m.binCnt[bin];
+              if (nb > m.binCap) { quiet = 0; break; }  // overflowing bin: entries are missing, decide nothing from it
+              for (int q = 0; q < nb; ++q) {
+                const size_t o = (size_t)bin * m.binCap + q;
+                const int j = m.binItems[o];
+                if (j == i) continue;
+                const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + 2.0 * S;
+                const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+                if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) { quiet = 0; break; }
+              }
+            }
+      }
+    }
+  }
+  m.quiet[i] = quiet;
+  if (!quiet) m.act[atomicAdd(m.nAct, 1)] = i;
+}
+
+// every sub-step of a quiet instance, in order, by one thread
+__global__ void k5q_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts,
+                          int nSub) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (runs before the first sub-step: *m.nInst is the count at the start of the step)
+  if (i >= *m.nInst || !m.quiet[i] || in.onMesh[i] == 0) return;
+  for (int s = 0; s < nSub; ++s) d5_solve(m, L, in, classes, dts[s], m.cCnt, m.cIdx, m.cF, m.cT, m.Fw, m.Tw, m.cCnt, m.cCnt2, i);
+}
+
+// the per-sub-step chain on the compact list of active instances
+#define IBM_ACT_I                                                  \
+  const int t_ = blockIdx.x * blockDim.x + threadIdx.x;            \
+  if (t_ >= *m.nAct) return;                                       \
+  const int i = m.act[t_]
+__global__ void k5a_bin_cand(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int doCyclic) {
+  IBM_ACT_I;
+  d5_bin(m, in, i);
+  if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
+}
+__global__ void k5a_find_pairs(MotionDev m, InstanceSoA in) {
+  const int t3 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t3 / 3 >= *m.nAct) return;
+  d5_find_pairs(m, in, 3 * m.act[t3 / 3] + t3 % 3);
+}
+__global__ void k5a_rows_finish(MotionDev m, InstanceSoA in) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *m.pairCount = 0;  // pair_force is done: ready for the next sub-step
+  IBM_ACT_I;
+  d5_rows_finish(m, in, i);
+}
+__global__ void k5a_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
+  IBM_ACT_I;
+  d5_walls(m, L, in, classes, dt, i);
+}
+__global__ void k5a_merge(MotionDev m, InstanceSoA in) {
+  IBM_ACT_I;
+  d5_merge(m, in, i);
+}
+__global__ void k5a_solve_clear(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt,
+                                const int* cCnt, const int* cIdx, const double* cF, const double* cT, double* Fw, double* Tw, int* cCntA,
+                                int* cCntB) {
+  IBM_ACT_I;
+  if (i < *m.nInst && in.onMesh[i] != 0) {  // the bin this instance was put in (its centre has not changed since): ready for the next sub-step
+    int bx, by, bz;
+    bin_of(m, ld3(in.c, i), bx, by, bz);
+    m.binCnt[bx + m.nbx * (by + m.nby * bz)] = 0;
+  }
+  d5_solve(m, L, in, classes, dt, cCnt, cIdx, cF, cT, Fw, Tw, cCntA, cCntB, i);
+  if (i < *m.nInst) {
+    const double S = *m.budget;
+    const D3 d0 = ld3(in.c, i) - D3{m.c0[i], m.c0[(size_t)m.cap + i], m.c0[2 * (size_t)m.cap + i]};
+    if (magSqr3(d0) > S * S) atomicExch(m.violated, 1);
+  }
+}
+__global__ void k5a_set_positions(MotionDev m, InstanceSoA in) {
+  IBM_ACT_I;
+  if (i >= *m.nInst) return;
+  const int idx = in.index[i];
+  if (m.idxHead[idx] != i) return;  // the first instance of a group does the group
+  d5_set_positions(m, in, idx);
+}
+
+__global__ void k5q_snapshot(MotionDev m, InstanceSoA in, double* __restrict__ snap, int* __restrict__ snapActive, int* __restrict__ snapMaxCopies,
+                             int restore) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t cap = (size_t)m.cap;
+  if (i < m.cap) {
+    for (int q = 0; q < 3; ++q) {
+      if (restore) { in.c[q][i] = snap[q * cap + i]; in.th[q][i] = snap[(3 + q) * cap + i]; in.v[q][i] = snap[(6 + q) * cap + i]; in.om[q][i] = snap[(9 + q) * cap + i]; }
+      else { snap[q * cap + i] = in.c[q][i]; snap[(3 + q) * cap + i] = in.th[q][i]; snap[(6 + q) * cap + i] = in.v[q][i]; snap[(9 + q) * cap + i] = in.om[q][i]; }
+    }
+    if (restore) in.active[i] = snapActive[i]; else snapActive[i] = in.active[i];
+  }
+  if (i < m.nParticles) {
+    if (restore) m.maxCopies[i] = snapMaxCopies[i]; else snapMaxCopies[i] = m.maxCopies[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -924,8 +1111,13 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.binCnt, (size_t)d.nbx * d.nby * d.nbz) && dalloc(c, M, &d.binItems, (size_t)d.nbx * d.nby * d.nbz * d.binCap) &&
             dalloc(c, M, &d.binPos, (size_t)3 * d.nbx * d.nby * d.nbz * d.binCap) && dalloc(c, M, &d.pairCount, 1) &&
             dalloc(c, M, &d.pairI, (size_t)d.pairCap) && dalloc(c, M, &d.pairJ, (size_t)d.pairCap) && dalloc(c, M, &d.cPos, cap * CONTACT_CAP) &&
-            dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16);
+            dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16) &&
+            dalloc(c, M, &d.act, cap) && dalloc(c, M, &d.nAct, 1) && dalloc(c, M, &d.quiet, cap) && dalloc(c, M, &d.c0, 3 * cap) &&
+            dalloc(c, M, &d.vaBits, 2) && dalloc(c, M, &d.budget, 1) && dalloc(c, M, &d.violated, 1) && dalloc(c, M, &M->snap, 12 * cap) &&
+            dalloc(c, M, &M->snapActive, cap) && dalloc(c, M, &M->snapMaxCopies, (size_t)std::max(1, c->nParticles));
   if (!ok) return IBM_E_CUDA;
+  d.activeMode = 0;
+  d.safety = 2.0;
   // originals
   int* oc = nullptr; double* orho = nullptr; int* wp = nullptr; int* cp = nullptr;
   ok = dalloc(c, M, &oc, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &orho, (size_t)std::max(1, c->nParticles)) &&
@@ -1044,6 +1236,13 @@ void motion_invalidate_groups(ibm_ctx* c) {
   }
 }
 
+bool motion_counter(ibm_ctx* c, const char* name, long long* value) {
+  Motion* M = (Motion*)c->motion;
+  if (std::strcmp(name, "loop5_fallbacks") == 0) { *value = M ? M->nFallbacks : 0; return true; }
+  if (std::strcmp(name, "loop5_active_instances") == 0) { *value = (M && M->d.activeMode) ? c->hScal[11] : -1; return true; }  // of the last advance
+  return false;
+}
+
 int combine_forces(ibm_ctx* c) {
   int rc = ensure_motion(c);
   if (rc) return rc;
@@ -1099,11 +1298,64 @@ static int substep_launch(ibm_ctx* c, double localDt) {
   return IBM_OK;
 }
 
+// the same chain over the compact list of active instances (quiet / active split)
+static int substep_launch_active(ibm_ctx* c, double localDt) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  const int cap = c->cap;
+  const bool copiesPossible = d.nCyc > 0;
+  const bool doCyclic = copiesPossible && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls);  // App. B #10
+  const int* cCnt = d.cCnt; const int* cIdx = d.cIdx; const double* cF = d.cF; const double* cT = d.cT;
+  double* Fw = d.Fw; double* Tw = d.Tw;
+  if (c->cfg.moving) {
+    k5a_bin_cand<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, doCyclic ? 1 : 0);
+    k5a_find_pairs<<<blocks_for(3 * cap), 128, 0, st>>>(d, c->in);
+    k5_pair_force<<<blocks_for(std::min(d.pairCap, 4 * c->nInst + 1024), 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
+    k5a_rows_finish<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
+    c->nLaunch += 4;
+    if (d.nWalls > 0) { k5a_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt); c->nLaunch++; }
+    if (copiesPossible) {
+      k5a_merge<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in);
+      c->nLaunch++;
+      cCnt = d.cCnt2; cIdx = d.cIdx2; cF = d.cF2; cT = d.cT2; Fw = d.Fw2; Tw = d.Tw2;
+      if (doCyclic) {
+        k5_cyclic_detect<<<148, 256, 0, st>>>(d, c->Lg, c->in, c->dClasses);
+        k5_append_all<<<32, 128, 0, st>>>(d, c->in);
+        c->nLaunch += 2;
+      }
+    }
+  }
+  k5a_solve_clear<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt, cCnt, cIdx, cF, cT, Fw, Tw, d.cCnt, d.cCnt2);
+  c->nLaunch++;
+  if (copiesPossible && c->nParticles > 0) { k5a_set_positions<<<blocks_for(cap), 128, 0, st>>>(d, c->in); c->nLaunch++; }
+  return IBM_OK;
+}
+
+// start of a split step: bounds, bins at the start positions, classification, then every sub-step of the quiet instances
+static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  const int cap = c->cap;
+  cudaMemsetAsync(d.vaBits, 0, 2 * sizeof(unsigned long long), st);
+  cudaMemsetAsync(d.nAct, 0, sizeof(int), st);
+  cudaMemsetAsync(d.violated, 0, sizeof(int), st);
+  k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
+  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
+  cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
+  k5q_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
+  c->nLaunch += 4;
+}
+
 static int finish_substeps(ibm_ctx* c) {
   Motion* M = (Motion*)c->motion;
   // instance count and overflow flags back to the host
   IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 8, M->d.nInst, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 9, M->d.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 10, M->d.violated, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 11, M->d.nAct, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   IBM_CUDA(c, cudaGetLastError());
   if (c->hScal[9] == 1) return ctx_fail(c, IBM_E_CAPACITY, "loop 5: more than CONTACT_CAP simultaneous contacts on one particle");
@@ -1160,31 +1412,68 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     void* args[] = {&d, &c->Lg, &c->in, &cls, &dd, &nSub, &doCyclic};
     IBM_CUDA(c, cudaLaunchCooperativeKernel((void*)k5_fused, dim3(M->fusedBlocks), dim3(256), args, 0, c->stream));
     c->nLaunch++;
-  } else if (c->graphLoop5 && nSub <= 256) {
-    // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
-    // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
-    bool same = M->graphExec && M->graphValid && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
-    for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
-    if (!same) {
-      if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
-      cudaGraph_t g = nullptr;
-      IBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      const long long before = c->nLaunch;
-      for (int s = 0; s < nSub; ++s) substep_launch(c, dts[s]);
-      M->graphLaunches = c->nLaunch - before;
-      c->nLaunch = before;
-      IBM_CUDA(c, cudaStreamEndCapture(c->stream, &g));
-      cudaError_t e = cudaGraphInstantiate(&M->graphExec, g, 0);
-      cudaGraphDestroy(g);
-      IBM_CUDA(c, e);
-      M->graphDts.assign(dts, dts + nSub);
-      M->graphValid = true;
-      M->graphNInst = c->nInst;
-    }
-    IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));
-    c->nLaunch += M->graphLaunches;
   } else {
-    for (int s = 0; s < nSub; ++s) substep_launch(c, s < 256 ? dts[s] : dts[255]);
+    // quiet / active split (see k5q_bounds): same results, the per-sub-step chain only over the instances that can interact
+    const bool split = c->activeLoop5 && nSub <= 256 && c->nInst > 0;
+    const int nInst0 = c->nInst;
+    M->d.activeMode = split ? 1 : 0;
+    M->d.safety = 1e-6 * c->activeSafetyPpm;
+    if (split) {
+      IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 0);
+      c->nLaunch++;
+    }
+    auto sequence = [&]() {
+      if (split) active_prologue(c, dt, nSub);
+      for (int s = 0; s < nSub; ++s) {
+        const double ls = s < 256 ? dts[s] : dts[255];
+        if (split) substep_launch_active(c, ls); else substep_launch(c, ls);
+      }
+    };
+    if (c->graphLoop5 && nSub <= 256) {
+      // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
+      // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
+      bool same = M->graphExec && M->graphValid && M->graphActive == split && M->graphSafety == M->d.safety && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
+      for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
+      if (!same) {
+        if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
+        cudaGraph_t g = nullptr;
+        IBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = c->nLaunch;
+        sequence();
+        M->graphLaunches = c->nLaunch - before;
+        c->nLaunch = before;
+        IBM_CUDA(c, cudaStreamEndCapture(c->stream, &g));
+        cudaError_t e = cudaGraphInstantiate(&M->graphExec, g, 0);
+        cudaGraphDestroy(g);
+        IBM_CUDA(c, e);
+        M->graphDts.assign(dts, dts + nSub);
+        M->graphValid = true;
+        M->graphActive = split;
+        M->graphSafety = M->d.safety;
+        M->graphNInst = c->nInst;
+      }
+      IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));
+      c->nLaunch += M->graphLaunches;
+    } else {
+      sequence();
+    }
+    if (split) {
+      if ((rc = finish_substeps(c))) { ctx_toc(c); return rc; }
+      if (c->hScal[10]) {
+        // an active instance outran the displacement budget: put the start of the step back and redo it without the split
+        M->nFallbacks++;
+        k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 1);
+        k_set_int<<<1, 1, 0, c->stream>>>(M->d.nInst, nInst0);
+        c->nLaunch += 2;
+        c->nInst = nInst0;
+        M->d.activeMode = 0;
+        M->groupsValid = false;  // copies appended by the abandoned attempt are gone: relink the same-index lists
+        if ((rc = ensure_motion(c))) { ctx_toc(c); return rc; }
+        ensure_bins_clear(c);
+        for (int s = 0; s < nSub; ++s) substep_launch(c, s < 256 ? dts[s] : dts[255]);
+      }
+    }
   }
   ctx_toc(c);
   if ((rc = finish_substeps(c))) return rc;

@@ -1,0 +1,109 @@
+"""Quiet / active split of loop 5 (option active_loop5, ibm_motion.cu: k5q_*): instances that cannot interact during a
+fluid step integrate all their sub-steps in one kernel, only the others go through the per-sub-step chain.  The results
+must be the ones of the unsplit path - bit-identical trajectories against the oracle and against the reference vectors -
+also when the displacement budget is exceeded and the step is redone from the snapshot.
+
+Written after the round's GPU budget was spent; verified under the CPU emulation (tools/cuda_emu).  Not a default."""
+import numpy as np
+import pytest
+
+from ibmfoam_b200 import cases
+from ibmfoam_b200.cloud import ParticleCloud
+from oracle.pyoracle import OracleCloud
+import golden_util as gu
+import ibm_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+KEYS_I = ("index", "copy", "active", "onMesh", "nShell")
+KEYS_D = ("center", "theta", "v", "omega", "F", "T")
+
+
+def _cloud(case, graph, safety_ppm=None):
+    gc = ParticleCloud(case)
+    gc.set_option("fused_loop5", 0)
+    gc.set_option("graph_loop5", int(graph))
+    gc.set_option("active_loop5", 1)
+    if safety_ppm is not None:
+        gc.set_option("active_loop5_safety_ppm", int(safety_ppm))
+    return gc
+
+
+def _run_vs_oracle(case, n_steps, graph, safety_ppm=None, ft_scale=1e-3, seed=0):
+    oc, gc = OracleCloud(case), _cloud(case, graph, safety_ppm)
+    rng = np.random.default_rng(seed)
+    actives = []
+    for _ in range(n_steps):
+        FT = rng.normal(0, ft_scale, (oc.n_instances, 6))
+        if case.mesh.nz == 1:
+            FT[:, 2] = 0
+            FT[:, 3:5] = 0
+        oc.set_force_torque(FT); gc.set_force_torque(FT)
+        oc.combine_forces(); gc.combineForces()
+        so = oc.advance(case.dt)
+        st = gc.advance(case.dt)
+        assert st.nSubSteps == int(so[0]) and st.nInstances == int(so[1])
+        a, b = oc.state_arrays(), gc.state_arrays()
+        for k in KEYS_I + KEYS_D:
+            assert np.array_equal(a[k], b[k]), (k, len(actives))
+        actives.append(gc.counter("loop5_active_instances"))
+    return oc, gc, actives
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_dilute_assembly_most_instances_are_quiet(graph):
+    case = cases.assembly(n=64, n_particles=120, seed=9, moving=True, cyclic_without_walls=True)
+    oc, gc, actives = _run_vs_oracle(case, 3, graph)
+    assert 0 <= max(actives) < gc.nParticles(), actives     # the split did something
+    assert gc.counter("loop5_fallbacks") == 0
+    gc.close()
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_fast_assembly_with_periodic_copies_and_deletion(graph):
+    case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    case.particles.v *= 25.0
+    case.dt = 0.5
+    oc, gc, actives = _run_vs_oracle(case, 4, graph)
+    assert oc.n_instances != 60
+    gc.close()
+
+
+def test_two_spheres_head_on():
+    _, gc, _ = _run_vs_oracle(cases.two_spheres(n=40, e=0.8, speed=0.7, gap=0.3), 3, True)
+    gc.close()
+
+
+def test_colliding_cylinders_walls_and_copies():
+    case = cases.colliding_particles()
+    rng = np.random.default_rng(2)
+    case.particles.v[:, :2] = rng.normal(0, 0.8, (45, 2))
+    case.particles.omega[:, 2] = rng.normal(0, 30.0, 45)
+    case.dt = 2.5e-4
+    oc, gc, _ = _run_vs_oracle(case, 3, True, ft_scale=1e-7)
+    assert oc.n_instances > 45
+    gc.close()
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_exceeded_budget_redoes_the_step_without_the_split(graph):
+    """a vanishing safety factor: active instances outrun the budget at once -> snapshot restored, unsplit path, same result"""
+    case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    case.particles.v *= 25.0
+    case.dt = 0.5
+    oc, gc, _ = _run_vs_oracle(case, 3, graph, safety_ppm=1)
+    assert gc.counter("loop5_fallbacks") > 0
+    gc.close()
+
+
+@pytest.mark.parametrize("name", ["col8", "wc2d_cyl", "wc3d_sph"])
+def test_trajectories_against_reference_vectors_with_the_split(name):
+    case, g, n_steps = gu.load_dynamic(name)
+    gc = _cloud(case, graph=True)
+    for s in range(1, n_steps + 1):
+        gc.set_force_torque(g[f"s{s}_FT_used"])
+        gc.advance(case.dt)
+        st = gc.state_arrays()
+        for k in ("index", "copy", "active", "onMesh", "nShell", "center", "theta", "v", "omega"):
+            assert np.array_equal(st[k], g[f"s{s}_{k}"]), (s, k)
+    gc.close()
