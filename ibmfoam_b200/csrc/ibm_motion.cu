@@ -1379,6 +1379,7 @@ int motion_substep(ibm_ctx* c, double localDt) {
   int rc = ensure_motion(c);
   if (rc) return rc;
   ensure_bins_clear(c);
+  ((Motion*)c->motion)->d.activeMode = 0;  // a single literal sub-step is always the unsplit chain
   ctx_tic(c, T_ADVANCE);
   substep_launch(c, localDt);
   ctx_toc(c);

@@ -35,9 +35,9 @@ SUBSET = [
     "tests/test_gpu_marking.py::test_marking_bit_exact",
     "tests/test_gpu_zz_reference_vectors.py::test_marking_forcing_stress_against_reference_vectors",
     "tests/test_gpu_zz_reference_vectors.py::test_trajectories_against_reference_vectors[col8-graph]",
-    "tests/test_zz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned]",
-    "tests/test_zz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
-    "tests/test_zz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
+    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned]",
+    "tests/test_zzz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
+    "tests/test_zzz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
 ]
 
 
@@ -73,7 +73,7 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
 
 @pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (several minutes)")
 @pytest.mark.parametrize("path", ["tests/test_gpu_forcing.py", "tests/test_gpu_marking.py", "tests/test_gpu_stress.py", "tests/test_gpu_motion.py",
-                                  "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_zz_gpu_v5_kernels.py",
+                                  "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_zzz_gpu_v5_kernels.py", "tests/test_zzz_gpu_active_loop5.py",
                                   "tests/test_zz_gpu_validation_cases.py"])
 def test_gpu_parity_file_under_emulation(emu_lib, path):
     _child(emu_lib, [path], timeout=6000)
