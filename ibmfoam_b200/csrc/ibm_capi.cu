@@ -292,11 +292,10 @@ int ctx_update(ibm_ctx* c) {
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
   c->updatesPerCall = c->nInst > 0 ? c->hScal[3] : 0;
   if (schedule_fill_items(c->stream, c->sched, c->nInst, c->totalChunks)) return ctx_fail(c, IBM_E_CUDA, "schedule_fill_items failed");
-  int rc = ensure_field(c, &c->dI, 1);
-  if (rc) return rc;
-  IBM_CUDA(c, cudaMemsetAsync(c->dI, 0, (size_t)c->L.nCells * sizeof(double), c->stream));
-  launch_k1_indicator(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dI);
-  c->nLaunch += 2;
+  // I.ibm (particleCloud::updateI, particleCloud.C:952-969) is not an input of loops 2-5: it is refreshed with the cell
+  // lists by definition (App. B #13) but only MATERIALISED when somebody asks for it (ibm_get_indicator) - an 8-byte
+  // write per mesh cell and a kernel per update otherwise spent on a field nobody reads
+  c->indicatorStale = true;
   ctx_toc(c);
   IBM_CUDA(c, cudaGetLastError());
   return IBM_OK;
@@ -930,8 +929,18 @@ int ibm_get_sf(ibm_ctx* c, int inst, double* Sf) {
 int ibm_get_indicator(ibm_ctx* c, double* I) {
   if (!c || !I) return IBM_E_ARG;
   cudaSetDevice(c->device);
-  if (!c->dI) return ctx_fail(c, IBM_E_STATE, "ibm_get_indicator: no particles set");
-  int rc = d2h_field(c, c->dI, 1, I);
+  if (c->cap == 0) return ctx_fail(c, IBM_E_STATE, "ibm_get_indicator: no particles set");
+  int rc = ensure_field(c, &c->dI, 1);
+  if (rc) return rc;
+  if (c->indicatorStale) {
+    ctx_tic(c, T_UPDATE);
+    IBM_CUDA(c, cudaMemsetAsync(c->dI, 0, (size_t)c->L.nCells * sizeof(double), c->stream));
+    launch_k1_indicator(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dI);
+    c->nLaunch += 2;
+    ctx_toc(c);
+    c->indicatorStale = false;
+  }
+  rc = d2h_field(c, c->dI, 1, I);
   if (rc) return rc;
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   return IBM_OK;

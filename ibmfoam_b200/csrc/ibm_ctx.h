@@ -70,6 +70,7 @@ struct ibm_ctx {
   double* dStage = nullptr;
   size_t stageDoubles = 0;
   double* dTcorr = nullptr;
+  bool indicatorStale = true;  // I.ibm is computed on demand (ibm_get_indicator), not on every update
   bool fLive = false;       // dF holds a previous forcing result on the current shell cells
   bool fEverZeroed = false;
   double* hPinned = nullptr;  // small pinned scratch for results
