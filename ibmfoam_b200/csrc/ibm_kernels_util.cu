@@ -7,32 +7,28 @@
 
 namespace ibm {
 
-// single-block exclusive scan (n <= a few 1e5 instances; runs once per update)
+// single-block exclusive scan (n <= a few 1e5 instances; runs once per update): every thread owns one contiguous
+// segment - serial sum, one block-wide scan of the 1024 segment totals, serial write - i.e. three passes and two
+// barriers whatever n is (the tile-by-tile version it replaces took 3 barriers per 1024 elements: 168 us at n = 1e5)
 __global__ void k_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total) {
   __shared__ int warpSum[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int base = 0; base < n; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int v = i < n ? in[i] : 0;
-    int x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warpSum[warp] = x;
-    __syncthreads();
-    int wbase = 0, tot = 0;
-    for (int q = 0; q < nw; ++q) { if (q < warp) wbase += warpSum[q]; tot += warpSum[q]; }
-    int c = carry;
-    if (i < n) out[i] = c + wbase + x - v;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + tot;
-    __syncthreads();
+  const int seg = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int i0 = min((int)threadIdx.x * seg, n), i1 = min(i0 + seg, n);
+  int mine = 0;
+  for (int i = i0; i < i1; ++i) mine += in[i];
+  int x = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (lane == 31) warpSum[warp] = x;
+  __syncthreads();
+  int wbase = 0, tot = 0;
+  for (int q = 0; q < nw; ++q) { if (q < warp) wbase += warpSum[q]; tot += warpSum[q]; }
+  int run = wbase + x - mine;  // sum of everything before this thread's segment
+  for (int i = i0; i < i1; ++i) { const int v = in[i]; out[i] = run; run += v; }
+  if (threadIdx.x == 0) *total = tot;
 }
 
 __global__ void k_aos_to_soa(LatticeDev L, const double* __restrict__ aos, int nComp, double* __restrict__ soa) {
