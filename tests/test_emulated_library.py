@@ -77,3 +77,22 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
                                   "tests/test_zz_gpu_validation_cases.py"])
 def test_gpu_parity_file_under_emulation(emu_lib, path):
     _child(emu_lib, [path], timeout=6000)
+
+
+@pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (about two minutes)")
+def test_bench_control_flow_dry_run(emu_lib):
+    """bench.py's logic (probe, selection, full-size re-verification, timing, end-to-end leg, JSON assembly) on a 32^3
+    stand-in workload against the emulated library; the numbers mean nothing, the keys and the flow are what is checked"""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cuda_emu", "bench_dryrun.py"), "--steps", "2", "--warmup", "1",
+                        "--e2e-steps", "1"], cwd=ROOT, capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0
+    kg = line["config"]["kernel_generations"]
+    assert kg["probe"]["ok"] and kg["probe"]["kernels_ok"] and kg["probe"]["loop5_split_ok"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
