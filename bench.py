@@ -19,7 +19,7 @@ integral, force combination, the literal sub-step loop, re-marking).  One cell-p
                 a child process on this very box shows parity with the defaults AND a lower time, and a second check at
                 the full size agrees; config.kernel_generations records what ran and why (--no-probe: defaults only).
 
-python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe]
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1]
 """
 from __future__ import annotations
 
@@ -409,6 +409,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="-1 = probe (verified + faster generation per kernel), >= 0 = force that generation")
     ap.add_argument("--no-probe", action="store_true", help="library defaults without the child-process probe")
+    ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 / 1 = forced")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -442,6 +443,8 @@ def main():
         variants = [args.variant, args.variant, 0]
     elif not args.no_probe and rank == 0:
         variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank)
+    if args.split >= 0:
+        variants[2] = 1 if args.split else 0
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
