@@ -6,7 +6,7 @@ the CPU emulation of tools/cuda_emu, so that the GPU parity tests can be run on 
     IBM_TEST_EMU_LIB=tools/cuda_emu/_build/libibmfoam_b200_emu.so python -m pytest tests -m gpu -k "not fused" ...
 
 The only source transformation is syntactic: `kernel<<<grid, block, smem, stream>>>(args)` becomes a call of the
-emulator's launch function and `extern __shared__ T name[]` a pointer to the emulated dynamic shared memory; everything
+emulator's launch function, `cudaLaunchCooperativeKernel((void*)kernel, ...)` one that still knows the kernel's type, and `extern __shared__ T name[]` a pointer to the emulated dynamic shared memory; everything
 else is handled by the stand-in headers (cuda_runtime.h, cub/cub.cuh, cooperative_groups.h, cuda_pipeline.h).
 It checks LOGIC.  It is slow (every CUDA thread is a fiber), says nothing about performance or about the hardware memory
 model, and is never loaded by the product: only tests/conftest.py knows IBM_TEST_EMU_LIB (it re-points the ctypes loader
@@ -93,6 +93,7 @@ def transform(text):
         out.append(f"EMU_LAUNCH(({kern}), {cfg[0]}, {cfg[1]}, {cfg[2]}, {cfg[3]}" + (f", {args}" if args else "") + ")")
         pos = a1
     text = "".join(out)
+    text = re.sub(r"cudaLaunchCooperativeKernel\(\s*\(void\s*\*\)\s*(\w+)\s*,", r"::emu::coop_launch_erased(\1,", text)
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)::emu::dyn_smem();", text)
     return text
 

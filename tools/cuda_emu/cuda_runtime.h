@@ -66,6 +66,8 @@ inline int __shfl_sync(unsigned k, int v, int src) { return (int)::emu::shfl(k, 
 #include <functional>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 struct dim3 {
@@ -97,6 +99,26 @@ inline void rt_launch(dim3 grid, dim3 block, size_t smem, K kern, A... args) {
     ::emu::launch(grid.x * grid.y * grid.z, block.x * block.y * block.z, smem, [&]() { std::apply(kern, tup); });
   });
 }
+// cooperative launch: every block resident, grid.sync() available (reached through ibm::launch_cooperative)
+template <class K, class... A>
+inline cudaError_t coop_launch(dim3 grid, dim3 block, size_t smem, K kern, A... args) {
+  auto tup = std::make_tuple(args...);
+  submit([=]() {
+    std::lock_guard<std::mutex> lk(launch_mutex());
+    ::emu::launch(grid.x * grid.y * grid.z, block.x * block.y * block.z, smem, [&]() { std::apply(kern, tup); }, true);
+  });
+  return cudaSuccess;
+}
+// cudaLaunchCooperativeKernel((void*)kernel, ...) is rewritten by build_emu.py to this: the kernel keeps its type, so the
+// void** argument block can be unpacked (and copied NOW, like a real launch)
+template <class... P, size_t... I>
+inline cudaError_t coop_unpack(void (*kern)(P...), dim3 grid, dim3 block, void** args, size_t smem, std::index_sequence<I...>) {
+  return coop_launch(grid, block, smem, kern, *(typename std::remove_reference<P>::type*)args[I]...);
+}
+template <class... P>
+inline cudaError_t coop_launch_erased(void (*kern)(P...), dim3 grid, dim3 block, void** args, size_t smem, void* /*stream*/) {
+  return coop_unpack(kern, grid, block, args, smem, std::index_sequence_for<P...>{});
+}
 }  // namespace emu
 #define EMU_LAUNCH(kern, grid, block, smem, stream, ...) ::emu::rt_launch(dim3(grid), dim3(block), (size_t)(smem), kern, ##__VA_ARGS__)
 
@@ -126,7 +148,7 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : (a == cudaDevAttrCooperativeLaunch) ? 1 : 0; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)1; return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -3,7 +3,7 @@
 // hashing, barrier placement, reductions) against the oracle.  It says nothing about performance and nothing about
 // hardware memory-model effects; the GPU parity tests remain the gate.
 //
-// Model: blocks run one after another; the threads of a block are fibers (ucontext) scheduled round-robin by one OS
+// Model: blocks run one after another (all at once for a cooperative launch); the threads of a block are fibers (ucontext) scheduled round-robin by one OS
 // thread.  __syncthreads() parks a fiber until every live fiber of the block has arrived; warp shuffles park a fiber
 // until all 32 lanes of its warp have deposited their value.  A fiber runs undisturbed between two such points, so a
 // missing barrier shows up as a deterministic wrong answer (thread 0 runs far ahead of thread 255).
@@ -30,7 +30,7 @@ struct Fiber {
   std::vector<PendingCopy> pending;  // cp.async copies issued and not yet waited for (performed at the wait)
   ucontext_t ctx;
   char* stack = nullptr;
-  int state = 0;  // 0 runnable, 1 at block barrier, 2 at warp-level rendez-vous, 3 done
+  int state = 0;  // 0 runnable, 1 at block barrier, 2 at warp-level rendez-vous, 3 done, 4 at the grid barrier
   const GroupBarrier* waitObj = nullptr;
   long warpGen = 0;
   Dim3 tid;
@@ -124,18 +124,67 @@ inline void fiber_entry() {
   swapcontext(&b->fibers[b->cur].ctx, &b->sched);
 }
 
-// run `body` as a kernel: grid.x blocks of block.x threads (1-D is all the kernels here use)
-inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std::function<void()>& body) {
+// one scheduling round over the fibers of block b (blk() must point at it): returns whether anything moved
+inline bool block_round(Block& b, const std::vector<unsigned>& threadOrder, unsigned& done) {
+  const unsigned blockX = b.blockDim.x;
+  bool progressed = false;
+  unsigned atBarrier = 0, live = 0;
+  for (unsigned to = 0; to < blockX; ++to) {
+    const unsigned t = threadOrder[to];
+    Fiber& f = b.fibers[t];
+    if (f.state == 3) continue;
+    if (f.state == 2 && f.waitObj->gen != f.warpGen) f.state = 0;
+    if (f.state == 0) {
+      b.cur = (int)t;
+      swapcontext(&b.sched, &f.ctx);
+      progressed = true;
+      if (f.state == 3) ++done;
+    }
+  }
+  for (unsigned t = 0; t < blockX; ++t) {
+    const Fiber& f = b.fibers[t];
+    if (f.state != 3) ++live;
+    if (f.state == 1) ++atBarrier;
+  }
+  if (live > 0 && atBarrier == live) {  // every live thread is at the barrier: release
+    for (auto& f : b.fibers)
+      if (f.state == 1) f.state = 0;
+    progressed = true;
+  }
+  return progressed;
+}
+
+inline void block_arm(Block& b, unsigned bx, size_t stack) {
+  const int nWarps = (int)(b.blockDim.x + 31) / 32;
+  b.blockIdx.x = bx;
+  b.groups.assign((size_t)nWarps, {});
+  b.shflBuf.assign(32 * (size_t)nWarps, 0.0);
+  for (unsigned t = 0; t < b.blockDim.x; ++t) {
+    Fiber& f = b.fibers[t];
+    f.state = 0;
+    f.tid.x = t;
+    f.pending.clear();
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = stack;
+    f.ctx.uc_link = &b.sched;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+  }
+}
+
+// grid-wide barrier of a cooperative launch (state 4): released by launch(..., cooperative) once every live thread of
+// every block has arrived
+inline void gridsync() {
+  cur().state = 4;
+  yield();
+}
+
+// run `body` as a kernel: grid.x blocks of block.x threads (1-D is all the kernels here use).  cooperative = all blocks
+// are resident at once (their fibers are scheduled block after block, round after round) so that grid.sync() works;
+// static __shared__ storage is one object for the whole process here, so a cooperative kernel may only use dynamic
+// shared memory.
+inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std::function<void()>& body, bool cooperative = false) {
   static const size_t STACK = 192 * 1024;
-  Block b;
-  blk() = &b;
-  b.gridDim.x = gridX;
-  b.blockDim.x = blockX;
-  b.fibers.resize(blockX);
-  for (auto& f : b.fibers) f.stack = (char*)std::malloc(STACK);
-  b.dynSmem.assign(smemBytes + 128, 0);
-  const int nWarps = (int)(blockX + 31) / 32;
-  b.body = &body;
   // EMU_ORDER=reverse | shuffle:<seed> perturbs the order in which blocks run and in which the fibers of a block are
   // resumed: a kernel whose result depends on it (beyond the rounding of floating-point atomics) has a race
   static const char* orderEnv = std::getenv("EMU_ORDER");
@@ -149,59 +198,71 @@ inline void launch(unsigned gridX, unsigned blockX, size_t smemBytes, const std:
   if (shuffle) {
     for (unsigned i = gridX; i > 1; --i) std::swap(blockOrder[i - 1], blockOrder[next() % i]);
   }
-  for (unsigned bo = 0; bo < gridX; ++bo) {
-    const unsigned bx = blockOrder[bo];
-    if (shuffle)
-      for (unsigned i = blockX; i > 1; --i) std::swap(threadOrder[i - 1], threadOrder[next() % i]);
-    b.blockIdx.x = bx;
-    b.groups.assign((size_t)nWarps, {});
-    b.shflBuf.assign(32 * (size_t)nWarps, 0.0);
-    // shared memory is NOT cleared between blocks: like the hardware, a kernel must not rely on its initial content
-    for (unsigned t = 0; t < blockX; ++t) {
-      Fiber& f = b.fibers[t];
-      f.state = 0;
-      f.tid.x = t;
-      f.pending.clear();
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack;
-      f.ctx.uc_stack.ss_size = STACK;
-      f.ctx.uc_link = &b.sched;
-      makecontext(&f.ctx, (void (*)())fiber_entry, 0);
-    }
-    unsigned done = 0;
-    while (done < blockX) {
+  const unsigned resident = cooperative ? gridX : 1;
+  std::vector<Block> blocks(resident);
+  for (auto& b : blocks) {
+    b.gridDim.x = gridX;
+    b.blockDim.x = blockX;
+    b.fibers.resize(blockX);
+    for (auto& f : b.fibers) f.stack = (char*)std::malloc(STACK);
+    b.dynSmem.assign(smemBytes + 128, 0);
+    b.body = &body;
+  }
+  if (cooperative) {
+    std::vector<unsigned> done(gridX, 0);
+    for (unsigned bo = 0; bo < gridX; ++bo) { blk() = &blocks[bo]; block_arm(blocks[bo], blockOrder[bo], STACK); }
+    unsigned finished = 0;
+    while (finished < gridX) {
       bool progressed = false;
-      unsigned atBarrier = 0, live = 0;
-      for (unsigned to = 0; to < blockX; ++to) {
-        const unsigned t = threadOrder[to];
-        Fiber& f = b.fibers[t];
-        if (f.state == 3) continue;
-        if (f.state == 2 && f.waitObj->gen != f.warpGen) f.state = 0;
-        if (f.state == 0) {
-          b.cur = (int)t;
-          swapcontext(&b.sched, &f.ctx);
-          progressed = true;
-          if (f.state == 3) ++done;
+      for (unsigned bo = 0; bo < gridX; ++bo) {
+        Block& b = blocks[bo];
+        if (done[bo] >= blockX) continue;
+        if (shuffle)
+          for (unsigned i = blockX; i > 1; --i) std::swap(threadOrder[i - 1], threadOrder[next() % i]);
+        blk() = &b;
+        if (block_round(b, threadOrder, done[bo])) progressed = true;
+        if (done[bo] >= blockX) ++finished;
+      }
+      size_t live = 0, atGrid = 0;
+      for (auto& b : blocks)
+        for (auto& f : b.fibers) {
+          if (f.state != 3) ++live;
+          if (f.state == 4) ++atGrid;
         }
-      }
-      for (unsigned t = 0; t < blockX; ++t) {
-        const Fiber& f = b.fibers[t];
-        if (f.state != 3) ++live;
-        if (f.state == 1) ++atBarrier;
-      }
-      if (live > 0 && atBarrier == live) {  // every live thread is at the barrier: release
-        for (auto& f : b.fibers)
-          if (f.state == 1) f.state = 0;
+      if (live > 0 && atGrid == live) {
+        for (auto& b : blocks)
+          for (auto& f : b.fibers)
+            if (f.state == 4) f.state = 0;
         progressed = true;
       }
       if (!progressed) {
-        std::fprintf(stderr, "cuda_emu: deadlock in block %u (%u live, %u at __syncthreads, the rest at a warp barrier)\n", bx, live,
-                     atBarrier);
+        std::fprintf(stderr, "cuda_emu: deadlock in a cooperative launch (%zu live threads, %zu at grid.sync)\n", live, atGrid);
         std::abort();
       }
     }
+  } else {
+    Block& b = blocks[0];
+    blk() = &b;
+    for (unsigned bo = 0; bo < gridX; ++bo) {
+      const unsigned bx = blockOrder[bo];
+      if (shuffle)
+        for (unsigned i = blockX; i > 1; --i) std::swap(threadOrder[i - 1], threadOrder[next() % i]);
+      // shared memory is NOT cleared between blocks: like the hardware, a kernel must not rely on its initial content
+      block_arm(b, bx, STACK);
+      unsigned done = 0;
+      while (done < blockX) {
+        if (!block_round(b, threadOrder, done)) {
+          unsigned live = 0, atBarrier = 0;
+          for (auto& f : b.fibers) { if (f.state != 3) ++live; if (f.state == 1) ++atBarrier; }
+          std::fprintf(stderr, "cuda_emu: deadlock in block %u (%u live, %u at __syncthreads, the rest at a warp barrier%s)\n", bx, live,
+                       atBarrier, "");
+          std::abort();
+        }
+      }
+    }
   }
-  for (auto& f : b.fibers) std::free(f.stack);
+  for (auto& b : blocks)
+    for (auto& f : b.fibers) std::free(f.stack);
   blk() = nullptr;
 }
 
