@@ -90,7 +90,8 @@ struct ibm_ctx {
   bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph
   bool activeLoop5 = false; // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
                             // sub-step; written after round 1's GPU budget was spent, verified under emulation only
-  int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (tests shrink it to force the fallback)
+  int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (>= 1: a quiet instance needs B_i >= s_i)
+  int activeCheckPpm = 1000000;   // fraction of B_i the per-sub-step check allows (tests shrink it to force the fallback)
   // motion (loop 5) scratch lives in ibm_motion.cu
   void* motion = nullptr;
   // comm

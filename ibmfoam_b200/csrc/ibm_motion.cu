@@ -72,10 +72,13 @@ struct MotionDev {
   int* act; int* nAct;             // instances that can take part in a contact, a wall / patch hit or a copy group this step
   int* quiet;                      // 1 = integrates alone, all sub-steps in one kernel
   double* c0;                      // [3][cap] centre at the start of the step (at creation for copies appended later)
-  unsigned long long* vaBits;      // bit patterns of max |v| and max |F/m + g| over the instances at the start of the step
-  double* budget;                  // S: displacement an instance is assumed not to exceed during the step
-  int* violated;                   // an active instance moved farther than S: the step is redone without the split
-  double safety;
+  unsigned long long* vaBits;      // bit pattern of the largest own displacement bound s_i over the instances
+  double* budget;                  // S = safety * max s_i: no instance is assumed to move farther than this during the step
+  double* sOwn; double* uMax;      // [cap] own ballistic bound s_i; its maximum over the instance and its possible partners
+  double* bud;                     // [cap] B_i: displacement budget of instance i (two-hop maximum of s, times safety)
+  int* violated;                   // an active instance moved farther than its B_i: the step is redone without the split
+  int* noSplit;                    // the start configuration defeats the classification (see k5q_ghosts): everything is active
+  double safety, check;            // budget factor; fraction of B_i the check allows (1 except in tests of the fallback)
 };
 
 struct Motion {
@@ -104,6 +107,8 @@ struct Motion {
   int* snapMaxCopies = nullptr; // [nParticles]
   bool graphActive = false;     // the captured graph is of the split sequence
   double graphSafety = 0.0;     // ... with this safety factor (MotionDev is captured by value)
+  double graphDt = 0.0;         // ... and this fluid step (an argument of k5q_bounds)
+  bool splitAllowed = true;     // every cyclic patch is a pure translation (k5q_ghosts needs the image of a centre)
   long long nFallbacks = 0;
 };
 
@@ -596,6 +601,7 @@ __device__ __forceinline__ void d5_append(MotionDev m, InstanceSoA in, int tid, 
     in.age[dst] = in.age[src];
     in.nShell[dst] = 0; in.shellOff[dst] = 0; in.nPtsOnMesh[dst] = 0;
     rot_from_theta(in.th[0][src], in.th[1][src], in.th[2][src], in.rot + 9 * (size_t)dst);
+    if (m.activeMode) m.bud[dst] = m.bud[src];  // quiet / active split: the copy inherits its source's displacement budget
     m.cCnt[dst] = 0;
     m.cCnt2[dst] = 0;
     for (int w = 0; w < m.nWalls; ++w)
@@ -777,51 +783,133 @@ __global__ void k5_append_link(MotionDev m, InstanceSoA in) {
 // the remaining ACTIVE instances (a few per cent of a dilute-to-moderate suspension) go through the per-sub-step chain of
 // bins, pair search, wall / patch tests, copy handling and merging, on a compact list.
 //
-// "Cannot touch anything" is decided at the start of the step from a displacement budget
-//     S = safety * (max|v| dt + max|F/m + g| dt^2 / 2)          (maxima over all instances, dt = the fluid step)
-// an instance is ACTIVE when its index has several instances, when another body's centre is within
-// (Dmax_i + Dmax_j)/2 + 2 S  (particleIBM.C:56-59 is the reference's own early-out at (Dmax_i + Dmax_j)/2), or when a
-// wall or periodic patch is within its reach + S.  A quiet instance moves at most S/safety by construction (it feels no
-// impulse); an active one is CHECKED: if it ever gets farther than S from where it started (impulses can speed it up),
-// `violated` is raised and the host redoes the whole step from a snapshot without the split.  Under that check two bodies
-// that are not both active can never come within contact distance, so the split changes nothing but the work done.
+// "Cannot touch anything" is decided at the start of the step from displacement budgets.  With dt the fluid step,
+//     s_i = 1.02 (|v_i| dt + |F_i/m_i + g| dt^2 / 2)       what instance i covers if it feels no impulse (the 2 % pays for the
+//                                                         symplectic-Euler sum  sum_k dt_k |v_0 + a t_{k+1}|  of ~100 sub-steps)
+//     S   = safety * max_i s_i
+//     B_i = safety * max{ s_j : j within two hops of i in the graph of pairs closer than (Dmax_i + Dmax_j)/2 + 2 S }
+// (an elastic impulse hands a body at most its partners' momentum, so the neighbourhood maximum is what an instance can
+// plausibly reach; `safety` > sqrt(2) covers one exchange among equal bodies outright).  Instance i is ACTIVE when
+//   * its index has several instances (periodic copies share and exchange state, particleCloud.C:316-444, 525-554),
+//   * a wall or periodic patch is within its reach + B_i,
+//   * another body j is within (Dmax_i + Dmax_j)/2 + B_i + B_j (particleIBM.C:56-59 is the reference's own early-out at
+//     (Dmax_i + Dmax_j)/2), or
+//   * the IMAGE of a body g that may spawn a periodic copy this step (g within its reach + S of a cyclic patch, whichever
+//     way it moves now: a contact can turn it round) is within (Dmax_i + Dmax_g)/2 + B_i + (1 + n) B_g, n = number of
+//     translations composed in the image (a copy is created within B_g of the image of g's start and then has B_g of its own).
+// A quiet instance covers at most s_i <= B_i by construction; an active one is CHECKED after every sub-step: farther than
+// B_i from where it started (or was created) raises `violated` and the host redoes the whole step from a snapshot without
+// the split.  Under that check a quiet instance can never come within contact distance of anything, so the split changes
+// nothing but the work done.  Cyclic patches that are not pure translations switch the split off (host side).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dmax_of(const ShapeClassDev& s) { return s.kind == 2 ? fmax(s.a, fmax(s.b, s.l)) : s.d; }
 
-__global__ void k5q_bounds(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+__global__ void k5q_bounds(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dtStep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double sp = 0.0, ac = 0.0;
-  if (i < *m.nInst && in.onMesh[i] != 0) {
-    const ShapeClassDev* sc = classes + in.cls[i];
-    const double mass = sc->V * in.rho[i];
-    sp = mag3(ld3(in.v, i));
-    ac = mag3(ld3(in.F, i) / mass + D3{m.gx, m.gy, m.gz});
+  double sb = 0.0;
+  if (i < *m.nInst) {
+    if (in.onMesh[i] != 0) {
+      const ShapeClassDev* sc = classes + in.cls[i];
+      const double mass = sc->V * in.rho[i];
+      sb = 1.02 * (mag3(ld3(in.v, i)) * dtStep + 0.5 * mag3(ld3(in.F, i) / mass + D3{m.gx, m.gy, m.gz}) * dtStep * dtStep);
+    }
+    m.sOwn[i] = sb;
+    for (int q = 0; q < 3; ++q) m.c0[(size_t)q * m.cap + i] = in.c[q][i];
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    sp = fmax(sp, __shfl_xor_sync(0xffffffffu, sp, o));
-    ac = fmax(ac, __shfl_xor_sync(0xffffffffu, ac, o));
+  for (int o = 16; o > 0; o >>= 1) sb = fmax(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(m.vaBits, (unsigned long long)__double_as_longlong(sb));  // non-negative doubles order like their bit patterns
+}
+
+__device__ __forceinline__ double split_S(const MotionDev& m) {
+  return m.safety * __longlong_as_double((long long)m.vaBits[0]) + 1e-12 * m.binEdge;
+}
+
+// bin entries < 0 are images: -(1 + 4 g + (n - 1)) = the image of instance g under n composed translations
+__device__ __forceinline__ bool bin_entry(int item, int& inst, int& mult) {
+  if (item >= 0) { inst = item; mult = 1; return false; }
+  const int e = -item - 1;
+  inst = e >> 2;
+  mult = (e & 3) + 2;
+  return true;
+}
+
+// images of the instances that may spawn a periodic copy this step, entered into the bins next to the real centres
+__global__ void k5q_ghosts(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *m.nInst || in.onMesh[i] == 0) return;
+  const D3 c = ld3(in.c, i);
+  const double reach = classes[in.cls[i]].Rbound + split_S(m);
+  D3 sh[3];
+  int n = 0;
+  for (int s = 0; s < m.nCyc; ++s) {
+    const PatchDev& p = m.patches[m.cycPatch[s]];
+    if (!patch_in_reach(p, c, reach)) continue;
+    if (n == 3) { atomicExch(m.noSplit, 1); return; }  // both sides of one direction in reach: a domain a few bodies wide
+    sh[n++] = D3{p.shift[0], p.shift[1], p.shift[2]};
   }
-  if ((threadIdx.x & 31) == 0) {  // non-negative doubles order like their bit patterns
-    atomicMax(m.vaBits, (unsigned long long)__double_as_longlong(sp));
-    atomicMax(m.vaBits + 1, (unsigned long long)__double_as_longlong(ac));
+  for (int sub = 1; sub < (1 << n); ++sub) {
+    D3 g = c;
+    int cnt = 0;
+    for (int q = 0; q < n; ++q)
+      if (sub & (1 << q)) { g = g + sh[q]; ++cnt; }
+    int bx, by, bz;
+    bin_of(m, g, bx, by, bz);
+    const int b = bx + m.nbx * (by + m.nby * bz);
+    const int slot = atomicAdd(&m.binCnt[b], 1);
+    if (slot < m.binCap) {  // (a full bin keeps its count above the capacity: the classification then decides nothing from it)
+      const size_t o = (size_t)b * m.binCap + slot;
+      m.binItems[o] = -(1 + 4 * i + (cnt - 1));
+      m.binPos[3 * o] = g.x; m.binPos[3 * o + 1] = g.y; m.binPos[3 * o + 2] = g.z;
+    }
   }
 }
 
-__global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dtStep) {
+// one hop of the neighbourhood maximum: dst_i = scale * max(src_i, src_j over the bodies and images within Rij + 2 S) (+ floor)
+__global__ void k5q_nbrmax(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ src,
+                           double* __restrict__ dst, double scale, double floorB) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double vmax = __longlong_as_double((long long)m.vaBits[0]), amax = __longlong_as_double((long long)m.vaBits[1]);
-  const double S = m.safety * (vmax * dtStep + 0.5 * amax * dtStep * dtStep) + 1e-12 * m.binEdge;
+  if (i >= *m.nInst) return;
+  double u = src[i];
+  const double S = split_S(m);
+  if (in.onMesh[i] != 0 && m.moving && 2.0 * S <= m.binEdge) {
+    const D3 c = ld3(in.c, i);
+    const double di = dmax_of(classes[in.cls[i]]);
+    int bx, by, bz;
+    bin_of(m, c, bx, by, bz);
+    for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
+      for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
+        for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
+          const int bin = x + m.nbx * (y + m.nby * z);
+          const int nb = min(m.binCnt[bin], m.binCap);
+          for (int q = 0; q < nb; ++q) {
+            const size_t o = (size_t)bin * m.binCap + q;
+            int j, mult;
+            bin_entry(m.binItems[o], j, mult);
+            if (j == i) continue;
+            const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + 2.0 * S;
+            const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+            if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) u = fmax(u, src[j]);
+          }
+        }
+  }
+  dst[i] = scale * u + floorB;
+}
+
+__global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double S = split_S(m);
   if (i == 0) *m.budget = S;
   if (i >= *m.nInst) return;
   const D3 c = ld3(in.c, i);
-  for (int q = 0; q < 3; ++q) m.c0[(size_t)q * m.cap + i] = in.c[q][i];
   int quiet = 1;
   if (in.onMesh[i] != 0) {  // (an instance that is off the mesh does not move at all: particleIBM.C:400-403)
     const ShapeClassDev* sc = classes + in.cls[i];
+    const double Bi = m.bud[i];
     const int head = m.idxHead[in.index[i]];
     if (head >= 0 && m.instNext[head] >= 0) quiet = 0;
+    if (*m.noSplit) quiet = 0;
     if (quiet && m.moving) {
-      const double reach = sc->Rbound + S;
+      const double reach = sc->Rbound + Bi;
       for (int w = 0; w < m.nWalls && quiet; ++w)
         if (patch_in_reach(m.patches[m.wallPatch[w]], c, reach)) quiet = 0;
       for (int s = 0; s < m.nCyc && quiet; ++s)
@@ -841,9 +929,10 @@ __global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* _
               if (nb > m.binCap) { quiet = 0; break; }  // overflowing bin: entries are missing, decide nothing from it
               for (int q = 0; q < nb; ++q) {
                 const size_t o = (size_t)bin * m.binCap + q;
-                const int j = m.binItems[o];
+                int j, mult;
+                bin_entry(m.binItems[o], j, mult);
                 if (j == i) continue;
-                const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + 2.0 * S;
+                const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + Bi + mult * m.bud[j];
                 const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
                 if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) { quiet = 0; break; }
               }
@@ -902,9 +991,9 @@ __global__ void k5a_solve_clear(MotionDev m, LatticeDev L, InstanceSoA in, const
   }
   d5_solve(m, L, in, classes, dt, cCnt, cIdx, cF, cT, Fw, Tw, cCntA, cCntB, i);
   if (i < *m.nInst) {
-    const double S = *m.budget;
+    const double B = m.check * m.bud[i];
     const D3 d0 = ld3(in.c, i) - D3{m.c0[i], m.c0[(size_t)m.cap + i], m.c0[2 * (size_t)m.cap + i]};
-    if (magSqr3(d0) > S * S) atomicExch(m.violated, 1);
+    if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
   }
 }
 __global__ void k5a_set_positions(MotionDev m, InstanceSoA in) {
@@ -1113,11 +1202,13 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.pairI, (size_t)d.pairCap) && dalloc(c, M, &d.pairJ, (size_t)d.pairCap) && dalloc(c, M, &d.cPos, cap * CONTACT_CAP) &&
             dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16) &&
             dalloc(c, M, &d.act, cap) && dalloc(c, M, &d.nAct, 1) && dalloc(c, M, &d.quiet, cap) && dalloc(c, M, &d.c0, 3 * cap) &&
-            dalloc(c, M, &d.vaBits, 2) && dalloc(c, M, &d.budget, 1) && dalloc(c, M, &d.violated, 1) && dalloc(c, M, &M->snap, 12 * cap) &&
+            dalloc(c, M, &d.vaBits, 2) && dalloc(c, M, &d.budget, 1) && dalloc(c, M, &d.violated, 1) &&
+            dalloc(c, M, &d.sOwn, cap) && dalloc(c, M, &d.uMax, cap) && dalloc(c, M, &d.bud, cap) && dalloc(c, M, &d.noSplit, 1) && dalloc(c, M, &M->snap, 12 * cap) &&
             dalloc(c, M, &M->snapActive, cap) && dalloc(c, M, &M->snapMaxCopies, (size_t)std::max(1, c->nParticles));
   if (!ok) return IBM_E_CUDA;
   d.activeMode = 0;
   d.safety = 2.0;
+  d.check = 1.0;
   // originals
   int* oc = nullptr; double* orho = nullptr; int* wp = nullptr; int* cp = nullptr;
   ok = dalloc(c, M, &oc, (size_t)std::max(1, c->nParticles)) && dalloc(c, M, &orho, (size_t)std::max(1, c->nParticles)) &&
@@ -1176,6 +1267,7 @@ static int motion_init(ibm_ctx* c) {
           if (std::fabs((nb.Cf[3 * (size_t)f + a] - ph.Cf[3 * (size_t)f + a]) - q.shift[a]) > 1e-9 * scale) uniform = false;
       q.uniformShift = uniform ? 1 : 0;
     }
+    if (ph.type == IBM_CYCLIC && !q.uniformShift) M->splitAllowed = false;  // images are not translations: no quiet / active split
     pd.push_back(q);
   }
   if (!pd.empty()) {
@@ -1338,15 +1430,20 @@ static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
   MotionDev& d = M->d;
   cudaStream_t st = c->stream;
   const int cap = c->cap;
+  const bool doCyclic = d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls);  // App. B #10: copies are created at all
   cudaMemsetAsync(d.vaBits, 0, 2 * sizeof(unsigned long long), st);
   cudaMemsetAsync(d.nAct, 0, sizeof(int), st);
   cudaMemsetAsync(d.violated, 0, sizeof(int), st);
-  k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  cudaMemsetAsync(d.noSplit, 0, sizeof(int), st);
+  k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
   k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
-  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
+  if (doCyclic) { k5q_ghosts<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses); c->nLaunch++; }
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0);
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge);
+  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
   cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
   k5q_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
-  c->nLaunch += 4;
+  c->nLaunch += 6;
 }
 
 static int finish_substeps(ibm_ctx* c) {
@@ -1415,10 +1512,11 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     c->nLaunch++;
   } else {
     // quiet / active split (see k5q_bounds): same results, the per-sub-step chain only over the instances that can interact
-    const bool split = c->activeLoop5 && nSub <= 256 && c->nInst > 0;
+    const bool split = c->activeLoop5 && M->splitAllowed && nSub <= 256 && c->nInst > 0;
     const int nInst0 = c->nInst;
     M->d.activeMode = split ? 1 : 0;
-    M->d.safety = 1e-6 * c->activeSafetyPpm;
+    M->d.safety = std::max(1.0, 1e-6 * c->activeSafetyPpm);  // (a quiet instance needs B_i >= s_i)
+    M->d.check = std::min(1.0, 1e-6 * c->activeCheckPpm);
     if (split) {
       IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 0);
@@ -1434,7 +1532,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     if (c->graphLoop5 && nSub <= 256) {
       // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
       // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
-      bool same = M->graphExec && M->graphValid && M->graphActive == split && M->graphSafety == M->d.safety && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
+      bool same = M->graphExec && M->graphValid && M->graphActive == split && M->graphSafety == M->d.safety * M->d.check && M->graphDt == dt && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
       for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
       if (!same) {
         if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
@@ -1451,7 +1549,8 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
         M->graphDts.assign(dts, dts + nSub);
         M->graphValid = true;
         M->graphActive = split;
-        M->graphSafety = M->d.safety;
+        M->graphSafety = M->d.safety * M->d.check;
+        M->graphDt = dt;
         M->graphNInst = c->nInst;
       }
       IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));

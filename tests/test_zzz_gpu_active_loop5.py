@@ -19,18 +19,20 @@ KEYS_I = ("index", "copy", "active", "onMesh", "nShell")
 KEYS_D = ("center", "theta", "v", "omega", "F", "T")
 
 
-def _cloud(case, graph, safety_ppm=None):
+def _cloud(case, graph, safety_ppm=None, check_ppm=None):
     gc = ParticleCloud(case)
     gc.set_option("fused_loop5", 0)
     gc.set_option("graph_loop5", int(graph))
     gc.set_option("active_loop5", 1)
     if safety_ppm is not None:
         gc.set_option("active_loop5_safety_ppm", int(safety_ppm))
+    if check_ppm is not None:
+        gc.set_option("active_loop5_check_ppm", int(check_ppm))
     return gc
 
 
-def _run_vs_oracle(case, n_steps, graph, safety_ppm=None, ft_scale=1e-3, seed=0):
-    oc, gc = OracleCloud(case), _cloud(case, graph, safety_ppm)
+def _run_vs_oracle(case, n_steps, graph, safety_ppm=None, ft_scale=1e-3, seed=0, check_ppm=None):
+    oc, gc = OracleCloud(case), _cloud(case, graph, safety_ppm, check_ppm)
     rng = np.random.default_rng(seed)
     actives = []
     for _ in range(n_steps):
@@ -87,11 +89,12 @@ def test_colliding_cylinders_walls_and_copies():
 
 @pytest.mark.parametrize("graph", [True, False])
 def test_exceeded_budget_redoes_the_step_without_the_split(graph):
-    """a vanishing safety factor: active instances outrun the budget at once -> snapshot restored, unsplit path, same result"""
+    """the check allows a vanishing fraction of the budget: active instances outrun it at once -> snapshot restored, unsplit
+    path, same result"""
     case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     case.particles.v *= 25.0
     case.dt = 0.5
-    oc, gc, _ = _run_vs_oracle(case, 3, graph, safety_ppm=1)
+    oc, gc, _ = _run_vs_oracle(case, 3, graph, check_ppm=1)
     assert gc.counter("loop5_fallbacks") > 0
     gc.close()
 
@@ -106,4 +109,26 @@ def test_trajectories_against_reference_vectors_with_the_split(name):
         st = gc.state_arrays()
         for k in ("index", "copy", "active", "onMesh", "nShell", "center", "theta", "v", "omega"):
             assert np.array_equal(st[k], g[f"s{s}_{k}"]), (s, k)
+    gc.close()
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_copy_created_after_a_rebound_next_to_a_resting_body(graph):
+    """A body inside the reach of a periodic patch but moving AWAY from it has no copy; a contact turns it round in mid-step,
+    the copy appears on the far side and at once overlaps a body that rests there with nothing near it at the start of the
+    step: that body must not have been classified quiet (the images entered by k5q_ghosts see to it)."""
+    n = 48
+    pos = np.array([[2.0, 24.3, 24.1],                # g: 2 cells from the x-min face (r = 4), moving away from it
+                    [2.0 + 8.05, 24.3, 24.1],         # h: hits g and hands it its velocity towards the face
+                    [n - 5.7, 24.3, 24.1],            # q: 5.7 cells from the x-max face, 7.7 from where g's copy will appear
+                    [24.0, 10.0, 37.0]])              # a bystander
+    case = cases.assembly(n=n, n_particles=4, seed=3, moving=True, cyclic_without_walls=True, positions=pos)
+    case.particles.v[:] = [[0.5, 0, 0], [-1.0, 0, 0], [0, 0, 0], [0.01, 0.02, 0.0]]
+    case.particles.omega[:] = 0.0
+    oc, gc, actives = _run_vs_oracle(case, 2, graph, ft_scale=1e-9)
+    st = gc.state_arrays()
+    q = int(np.where((st["index"] == 2) & (st["copy"] == 0))[0][0])
+    assert st["v"][q, 0] < -0.5                   # q was struck by the copy
+    assert oc.n_instances > 4
+    assert gc.counter("loop5_fallbacks") == 0
     gc.close()
