@@ -19,7 +19,7 @@ integral, force combination, the literal sub-step loop, re-marking).  One cell-p
                 a child process on this very box shows parity with the defaults AND a lower time, and a second check at
                 the full size agrees; config.kernel_generations records what ran and why (--no-probe: defaults only).
 
-python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1]
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1|2]
 """
 from __future__ import annotations
 
@@ -248,9 +248,10 @@ def run_probe(args):
     fast.particles.v *= 25.0
     fast.dt = 0.5
     traj = {}
-    for split in (0, 1):
+    for split in (0, 1, 2):   # 0 = unsplit chain, 1 = quiet/active split, 2 = split with the active list in one cooperative kernel
         gc = ParticleCloud(fast)
-        gc.set_option("active_loop5", split)
+        gc.set_option("active_loop5", int(split > 0))
+        gc.set_option("fused_active_loop5", int(split == 2))
         rng = np.random.default_rng(0)
         for _ in range(4):
             gc.set_force_torque(rng.normal(0, 1e-3, (gc.nParticles(), 6)))
@@ -259,17 +260,21 @@ def run_probe(args):
         traj[split] = gc.state_arrays()
         gc.close()
     out["loop5_split_ok"] = bool(all(np.array_equal(traj[0][k], traj[1][k]) for k in traj[0]))
+    out["loop5_fused_active_ok"] = bool(all(np.array_equal(traj[0][k], traj[2][k]) for k in traj[0]))
     if not (out["kernels_ok"] or out["loop5_split_ok"]):
         print(json.dumps(out))
         return
     t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}}
     # (b) loop 5 at the run's own instance count (it needs the particles, not the fields): without / with the split
-    if out["loop5_split_ok"]:
+    if out["loop5_split_ok"] or out["loop5_fused_active_ok"]:
         big = make_case(args.workload)
         if big.cloud.moving:
-            for split in (0, 1):
+            for split in (0, 1, 2):
+                if (split == 1 and not out["loop5_split_ok"]) or (split == 2 and not out["loop5_fused_active_ok"]):
+                    continue
                 gc = ParticleCloud(big, device=0)
-                gc.set_option("active_loop5", split)
+                gc.set_option("active_loop5", int(split > 0))
+                gc.set_option("fused_active_loop5", int(split == 2))
                 for _ in range(2):
                     gc.advance(big.dt)
                 gc.sync()
@@ -342,8 +347,10 @@ def choose_variants(local_rank, timeout_s=360):
                 fv = 5
             if sm.get("5", 1e30) < sm.get(str(sv), 0.0):
                 sv = 5
-        if info.get("loop5_split_ok") and am.get("1", 1e30) < am.get("0", 0.0):
-            split = 1
+        best = am.get("0", 0.0)
+        for mode, key in ((1, "loop5_split_ok"), (2, "loop5_fused_active_ok")):
+            if info.get(key) and am.get(str(mode), 1e30) < best:
+                split, best = mode, am[str(mode)]
     return fv, sv, split, info
 
 
@@ -409,7 +416,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="-1 = probe (verified + faster generation per kernel), >= 0 = force that generation")
     ap.add_argument("--no-probe", action="store_true", help="library defaults without the child-process probe")
-    ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 / 1 = forced")
+    ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 = off, 1 = on, 2 = on with the active list in one cooperative kernel")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -444,7 +451,7 @@ def main():
     elif not args.no_probe and rank == 0:
         variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank)
     if args.split >= 0:
-        variants[2] = 1 if args.split else 0
+        variants[2] = min(max(args.split, 0), 2)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -470,7 +477,8 @@ def main():
     t0 = time.time()
     cloud = ParticleCloud(case, device=local_rank, slab=slab, nccl_id=nccl_id, rank=rank, n_ranks=world)
     cloud.set_kernel_variant(variants[0], variants[1])
-    cloud.set_option("active_loop5", variants[2])
+    cloud.set_option("active_loop5", int(variants[2] > 0))
+    cloud.set_option("fused_active_loop5", int(variants[2] == 2))
     setup_s = time.time() - t0
     have_motion = True
     try:
@@ -657,7 +665,7 @@ def main():
                            "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)" if have_motion else "n/a",
                            "step": "forcing + solve(stress, combine, sub-steps, re-marking)" if have_motion else "forcing + stress + re-marking (loop 5 not built)",
                            "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s,
-                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "loop5_quiet_active_split": bool(variants[2]),
+                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "loop5_quiet_active_split": bool(variants[2]), "loop5_active_list_fused": variants[2] == 2,
                                                   "loop5_active_instances": cloud.counter("loop5_active_instances") if variants[2] else None,
                                                   "loop5_fallbacks": cloud.counter("loop5_fallbacks") if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else

@@ -439,6 +439,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   c->device = device;
   c->cfg = *cfg;
   if (const char* e = getenv("IBM_FUSED_LOOP5")) c->fusedLoop5 = std::atoi(e) != 0;  // developer switches (profiling)
+  if (const char* e = getenv("IBM_FUSED_ACTIVE_LOOP5")) c->fusedActive = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
@@ -1011,6 +1012,7 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
   if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
+  if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_check_ppm") == 0) { c->activeCheckPpm = value; return IBM_OK; }
   return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_option: unknown option ") + name);
 }

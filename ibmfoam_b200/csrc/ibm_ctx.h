@@ -91,6 +91,7 @@ struct ibm_ctx {
   bool activeLoop5 = false; // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
                             // sub-step; written after round 1's GPU budget was spent, verified under emulation only
   int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (>= 1: a quiet instance needs B_i >= s_i)
+  bool fusedActive = false;       // split steps: the active list's sub-steps in one persistent cooperative kernel (k5a_fused)
   int activeCheckPpm = 1000000;   // fraction of B_i the per-sub-step check allows (tests shrink it to force the fallback)
   // motion (loop 5) scratch lives in ibm_motion.cu
   void* motion = nullptr;

@@ -90,6 +90,7 @@ struct Motion {
   bool groupsValid = false;
   double* dDts = nullptr;
   int fusedBlocks = 0;
+  int fusedActBlocks = 0;       // upper bound of the grid of k5a_fused (co-residency)
   // CUDA graph of the unfused sub-step sequence, cached for one schedule of local time steps
   cudaGraphExec_t graphExec = nullptr;
   std::vector<double> graphDts;
@@ -110,6 +111,7 @@ struct Motion {
   double graphDt = 0.0;         // ... and this fluid step (an argument of k5q_bounds)
   bool splitAllowed = true;     // every cyclic patch is a pure translation (k5q_ghosts needs the image of a centre)
   long long nFallbacks = 0;
+  int lastActive = 0;           // active instances of the previous split step (sizes the grid of k5a_fused)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1085,6 +1087,83 @@ k5_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restr
   }
 }
 
+// The sub-step loop of the ACTIVE instances of a split step (k5q_* above) as one persistent cooperative kernel: the active
+// list is a fraction of the cloud, so a small grid holds it and its grid-wide barriers are cheap next to the ~9 launches
+// per sub-step of the unfused chain.  Phases and their order are those of substep_launch_active.
+__global__ void __launch_bounds__(256)
+k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
+          int doCyclic) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const bool copies = m.nCyc > 0;
+  for (int s = 0; s < nSub; ++s) {
+    const double dt = dts[s];
+    if (m.moving) {
+      const int na = *m.nAct;  // only the link phase changes it, and a grid barrier follows
+      for (int t = tid; t < na; t += nth) {
+        const int i = m.act[t];
+        d5_bin(m, in, i);
+        if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
+      }
+      grid.sync();
+      for (int t = tid; t < 3 * na; t += nth) d5_find_pairs(m, in, 3 * m.act[t / 3] + t % 3);
+      if (m.nWalls > 0)
+        for (int t = tid; t < na; t += nth) d5_walls(m, L, in, classes, dt, m.act[t]);
+      grid.sync();
+      {
+        const int np = min(*m.pairCount, m.pairCap);
+        for (int h = tid; h < np; h += nth) d5_pair_force(m, in, classes, dt, h);
+      }
+      grid.sync();
+      for (int t = tid; t < na; t += nth) d5_rows_finish(m, in, m.act[t]);
+      if (tid == 0) *m.pairCount = 0;
+      if (copies) {
+        grid.sync();
+        for (int t = tid; t < na; t += nth) d5_merge(m, in, m.act[t]);
+        if (doCyclic) {
+          d5_cyclic_detect(m, L, in, classes, tid, nth);
+          grid.sync();
+          const int total = *m.hitCount;  // complete after the barrier, identical for every thread
+          if (total > 0) {
+            d5_append(m, in, tid, nth);
+            grid.sync();
+            if (tid == 0) d5_append_link(m, in);
+          } else if (tid == 0) {
+            *m.candCount = 0;
+          }
+        }
+      }
+      grid.sync();
+    }
+    {
+      const int na = *m.nAct;
+      for (int t = tid; t < na; t += nth) {
+        const int i = m.act[t];
+        if (i >= *m.nInst) continue;
+        if (in.onMesh[i] != 0) {  // the bin this instance was put in (its centre has not changed since): ready for the next sub-step
+          int bx, by, bz;
+          bin_of(m, ld3(in.c, i), bx, by, bz);
+          m.binCnt[bx + m.nbx * (by + m.nby * bz)] = 0;
+        }
+        d5_solve(m, L, in, classes, dt, copies ? m.cCnt2 : m.cCnt, copies ? m.cIdx2 : m.cIdx, copies ? m.cF2 : m.cF, copies ? m.cT2 : m.cT,
+                 copies ? m.Fw2 : m.Fw, copies ? m.Tw2 : m.Tw, m.cCnt, m.cCnt2, i);
+        const double B = m.check * m.bud[i];
+        const D3 d0 = ld3(in.c, i) - D3{m.c0[i], m.c0[(size_t)m.cap + i], m.c0[2 * (size_t)m.cap + i]};
+        if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
+      }
+    }
+    grid.sync();
+    if (copies) {
+      const int na = *m.nAct;
+      for (int t = tid; t < na; t += nth) {
+        const int i = m.act[t];
+        if (i < *m.nInst && m.idxHead[in.index[i]] == i) d5_set_positions(m, in, in.index[i]);  // the first instance of a group does the group
+      }
+      grid.sync();
+    }
+  }
+}
+
 // particleCloud::combineForces, serial branch (particleCloud.C:268-312)
 __global__ void k_combine_forces(MotionDev m, InstanceSoA in) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1286,6 +1365,9 @@ static int motion_init(ibm_ctx* c) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_fused, 256, 0) == cudaSuccess && perSm > 0)
       M->fusedBlocks = sms * std::min(perSm, 4);
+    perSm = 0;
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5a_fused, 256, 0) == cudaSuccess && perSm > 0)
+      M->fusedActBlocks = sms * std::min(perSm, 2);
   }
   if (!ctx_cuda_ok(c, cudaMalloc(&M->cubTemp, M->cubTempBytes), "cudaMalloc(cub)")) return IBM_E_CUDA;
   return IBM_OK;
@@ -1529,7 +1611,20 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
         if (split) substep_launch_active(c, ls); else substep_launch(c, ls);
       }
     };
-    if (c->graphLoop5 && nSub <= 256) {
+    if (split && c->fusedActive && M->fusedActBlocks > 0) {
+      // prologue as plain launches, then ONE cooperative kernel for every sub-step of the active list.  Its grid is sized
+      // from the active count of the previous step (the kernel strides, so any size is correct) and bounded by co-residency.
+      active_prologue(c, dt, nSub);
+      const int guess = M->lastActive > 0 ? M->lastActive : std::max(1, c->nInst / 3);
+      const int blocks = std::max(std::min(M->fusedActBlocks, 4), std::min(M->fusedActBlocks, (int)((guess + guess / 4 + 255) / 256)));
+      MotionDev& d = M->d;
+      int doCyclic = (d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls)) ? 1 : 0;
+      const ShapeClassDev* cls = c->dClasses;
+      const double* dd = M->dDts;
+      void* args[] = {&d, &c->Lg, &c->in, &cls, &dd, &nSub, &doCyclic};
+      IBM_CUDA(c, cudaLaunchCooperativeKernel((void*)k5a_fused, dim3(blocks), dim3(256), args, 0, c->stream));
+      c->nLaunch++;
+    } else if (c->graphLoop5 && nSub <= 256) {
       // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
       // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
       bool same = M->graphExec && M->graphValid && M->graphActive == split && M->graphSafety == M->d.safety * M->d.check && M->graphDt == dt && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
@@ -1560,6 +1655,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     }
     if (split) {
       if ((rc = finish_substeps(c))) { ctx_toc(c); return rc; }
+      M->lastActive = c->hScal[11];
       if (c->hScal[10]) {
         // an active instance outran the displacement budget: put the start of the step back and redo it without the split
         M->nFallbacks++;

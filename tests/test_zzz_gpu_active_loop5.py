@@ -22,8 +22,9 @@ KEYS_D = ("center", "theta", "v", "omega", "F", "T")
 def _cloud(case, graph, safety_ppm=None, check_ppm=None):
     gc = ParticleCloud(case)
     gc.set_option("fused_loop5", 0)
-    gc.set_option("graph_loop5", int(graph))
+    gc.set_option("graph_loop5", int(graph is True))
     gc.set_option("active_loop5", 1)
+    gc.set_option("fused_active_loop5", int(graph == "fused"))   # the active list's sub-steps in one cooperative kernel
     if safety_ppm is not None:
         gc.set_option("active_loop5_safety_ppm", int(safety_ppm))
     if check_ppm is not None:
@@ -52,7 +53,7 @@ def _run_vs_oracle(case, n_steps, graph, safety_ppm=None, ft_scale=1e-3, seed=0,
     return oc, gc, actives
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "fused"])
 def test_dilute_assembly_most_instances_are_quiet(graph):
     case = cases.assembly(n=64, n_particles=120, seed=9, moving=True, cyclic_without_walls=True)
     oc, gc, actives = _run_vs_oracle(case, 3, graph)
@@ -61,7 +62,7 @@ def test_dilute_assembly_most_instances_are_quiet(graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "fused"])
 def test_fast_assembly_with_periodic_copies_and_deletion(graph):
     case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     case.particles.v *= 25.0
@@ -71,23 +72,25 @@ def test_fast_assembly_with_periodic_copies_and_deletion(graph):
     gc.close()
 
 
-def test_two_spheres_head_on():
-    _, gc, _ = _run_vs_oracle(cases.two_spheres(n=40, e=0.8, speed=0.7, gap=0.3), 3, True)
+@pytest.mark.parametrize("graph", [True, "fused"])
+def test_two_spheres_head_on(graph):
+    _, gc, _ = _run_vs_oracle(cases.two_spheres(n=40, e=0.8, speed=0.7, gap=0.3), 3, graph)
     gc.close()
 
 
-def test_colliding_cylinders_walls_and_copies():
+@pytest.mark.parametrize("graph", [True, "fused"])
+def test_colliding_cylinders_walls_and_copies(graph):
     case = cases.colliding_particles()
     rng = np.random.default_rng(2)
     case.particles.v[:, :2] = rng.normal(0, 0.8, (45, 2))
     case.particles.omega[:, 2] = rng.normal(0, 30.0, 45)
     case.dt = 2.5e-4
-    oc, gc, _ = _run_vs_oracle(case, 3, True, ft_scale=1e-7)
+    oc, gc, _ = _run_vs_oracle(case, 3, graph, ft_scale=1e-7)
     assert oc.n_instances > 45
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "fused"])
 def test_exceeded_budget_redoes_the_step_without_the_split(graph):
     """the check allows a vanishing fraction of the budget: active instances outrun it at once -> snapshot restored, unsplit
     path, same result"""
@@ -99,10 +102,11 @@ def test_exceeded_budget_redoes_the_step_without_the_split(graph):
     gc.close()
 
 
+@pytest.mark.parametrize("graph", [True, "fused"])
 @pytest.mark.parametrize("name", ["col8", "wc2d_cyl", "wc3d_sph"])
-def test_trajectories_against_reference_vectors_with_the_split(name):
+def test_trajectories_against_reference_vectors_with_the_split(name, graph):
     case, g, n_steps = gu.load_dynamic(name)
-    gc = _cloud(case, graph=True)
+    gc = _cloud(case, graph=graph)
     for s in range(1, n_steps + 1):
         gc.set_force_torque(g[f"s{s}_FT_used"])
         gc.advance(case.dt)
@@ -112,7 +116,7 @@ def test_trajectories_against_reference_vectors_with_the_split(name):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "fused"])
 def test_copy_created_after_a_rebound_next_to_a_resting_body(graph):
     """A body inside the reach of a periodic patch but moving AWAY from it has no copy; a contact turns it round in mid-step,
     the copy appears on the far side and at once overlaps a body that rests there with nothing near it at the start of the

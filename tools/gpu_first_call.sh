@@ -34,6 +34,8 @@ leg bench_defaults 600 $PY bench.py --steps 5 --warmup 3 --no-probe --no-cpu-bas
 leg bench_v5 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --no-cpu-baseline --no-e2e
 leg bench_v5_split 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --split 1 --no-cpu-baseline --no-e2e
 leg bench_v2_split 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 1 --no-cpu-baseline --no-e2e
+leg bench_v2_split_fused 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 2 --no-cpu-baseline --no-e2e
+leg bench_v5_split_fused 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --split 2 --no-cpu-baseline --no-e2e
 leg bench_reference 600 $PY bench.py --impl reference --steps 2 --warmup 1
 
 # 3. launch list of a step (v5 + split) and one full capture of each fifth-generation kernel (one GPU, after the runs above exited)
