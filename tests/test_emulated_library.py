@@ -38,6 +38,9 @@ SUBSET = [
     "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned]",
     "tests/test_zzz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
     "tests/test_zzz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
+    "tests/test_zzz_gpu_active_loop5.py::test_copy_created_after_a_rebound_next_to_a_resting_body[fused]",
+    "tests/test_zzz_gpu_active_loop5.py::test_two_spheres_head_on[fused]",
+    "tests/test_gpu_motion.py::test_two_spheres_head_on_closed_form[fused]",
 ]
 
 
