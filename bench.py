@@ -220,6 +220,24 @@ DEFAULT_VARIANTS = {"forcing": 2, "stress": 4}
 PROBE_CACHE = os.path.join("/tmp", "ibmfoam_b200_probe.json")
 
 
+def _time_loop5(big, mode):
+    """ms per fluid step of loop 5 (+ re-marking) at the workload's own instance count; mode as in run_probe"""
+    from ibmfoam_b200.cloud import ParticleCloud
+    gc = ParticleCloud(big, device=0)
+    gc.set_option("active_loop5", int(mode > 0))
+    gc.set_option("fused_active_loop5", int(mode == 2))
+    for _ in range(2):
+        gc.advance(big.dt)
+    gc.sync()
+    gc.timings(reset=True)
+    for _ in range(4):
+        gc.advance(big.dt)
+    gc.sync()
+    ms = gc.timings()["advance_ms"] / 4
+    gc.close()
+    return ms
+
+
 def run_probe(args):
     """child: python bench.py --probe  ->  one JSON line {"ok", "forcing_ms": {gen: ms}, "stress_ms": {gen: ms}, ...}"""
     import torch
@@ -231,7 +249,7 @@ def run_probe(args):
     case = cases.assembly(n=64, n_particles=150, seed=3, moving=True, cyclic_without_walls=True)
     f = util.caller_fields(case)
     res = {}
-    for gen in (None, 5):
+    for gen in (() if args.probe_fused else (None, 5)):
         gc = ParticleCloud(case)
         if gen is not None:
             gc.set_kernel_variant(gen, gen)
@@ -239,16 +257,18 @@ def run_probe(args):
         FT = gc.integrateSurfaceStresses(f["p"], f["tau"])
         res[gen] = (F, FT)
         gc.close()
-    eF = float(np.max(np.abs(res[5][0] - res[None][0])) / np.max(np.abs(res[None][0])))
-    eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
-    out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
-    out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
+    if not args.probe_fused:
+        eF = float(np.max(np.abs(res[5][0] - res[None][0])) / np.max(np.abs(res[None][0])))
+        eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
+        out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
+        out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
     # the quiet/active split of loop 5 must give the very same trajectory as the unsplit path (bit for bit)
     fast = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     fast.particles.v *= 25.0
     fast.dt = 0.5
     traj = {}
-    for split in (0, 1, 2):   # 0 = unsplit chain, 1 = quiet/active split, 2 = split with the active list in one cooperative kernel
+    modes = (0, 2) if args.probe_fused else (0, 1)   # 0 = unsplit chain, 1 = quiet/active split, 2 = split with the active
+    for split in modes:                               # list in one cooperative kernel (probed by a child of its own)
         gc = ParticleCloud(fast)
         gc.set_option("active_loop5", int(split > 0))
         gc.set_option("fused_active_loop5", int(split == 2))
@@ -259,31 +279,27 @@ def run_probe(args):
             gc.advance(fast.dt)
         traj[split] = gc.state_arrays()
         gc.close()
-    out["loop5_split_ok"] = bool(all(np.array_equal(traj[0][k], traj[1][k]) for k in traj[0]))
-    out["loop5_fused_active_ok"] = bool(all(np.array_equal(traj[0][k], traj[2][k]) for k in traj[0]))
+    key = "loop5_fused_active_ok" if args.probe_fused else "loop5_split_ok"
+    out[key] = bool(all(np.array_equal(traj[0][k], traj[modes[1]][k]) for k in traj[0]))
+    if args.probe_fused:
+        out["advance_ms"] = {}
+        if out[key]:
+            big = make_case(args.workload)
+            if big.cloud.moving:
+                out["advance_ms"]["2"] = _time_loop5(big, 2)
+        out["ok"] = True
+        print(json.dumps(out))
+        return
     if not (out["kernels_ok"] or out["loop5_split_ok"]):
         print(json.dumps(out))
         return
     t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}}
     # (b) loop 5 at the run's own instance count (it needs the particles, not the fields): without / with the split
-    if out["loop5_split_ok"] or out["loop5_fused_active_ok"]:
+    if out["loop5_split_ok"]:
         big = make_case(args.workload)
         if big.cloud.moving:
-            for split in (0, 1, 2):
-                if (split == 1 and not out["loop5_split_ok"]) or (split == 2 and not out["loop5_fused_active_ok"]):
-                    continue
-                gc = ParticleCloud(big, device=0)
-                gc.set_option("active_loop5", int(split > 0))
-                gc.set_option("fused_active_loop5", int(split == 2))
-                for _ in range(2):
-                    gc.advance(big.dt)
-                gc.sync()
-                gc.timings(reset=True)
-                for _ in range(4):
-                    gc.advance(big.dt)
-                gc.sync()
-                t["advance_ms"][str(split)] = gc.timings()["advance_ms"] / 4
-                gc.close()
+            for split in (0, 1):
+                t["advance_ms"][str(split)] = _time_loop5(big, split)
         del big
     # (c) forcing / stress kernels on a 256^3 / 12.5k-sphere workload, device-resident fields
     case = make_case("big256")
@@ -311,7 +327,7 @@ def run_probe(args):
     print(json.dumps(out))
 
 
-def choose_variants(local_rank, timeout_s=360):
+def choose_variants(local_rank, timeout_s=360, workload="big512"):
     """parent: run the probe in a child process on this rank's GPU (or reuse the result an earlier run on this box left in
     /tmp) and pick, per kernel, the faster verified generation.  Returns (forcing, stress, info)."""
     info = None
@@ -328,12 +344,25 @@ def choose_variants(local_rank, timeout_s=360):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         ids = vis.split(",") if vis else None
         env["CUDA_VISIBLE_DEVICES"] = ids[local_rank] if ids and local_rank < len(ids) else str(local_rank)
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe"], capture_output=True, text=True, timeout=timeout_s, env=env)
-            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            info = json.loads(line[-1]) if (r.returncode == 0 and line) else {"ok": False, "error": (r.stderr or "no output")[-300:]}
-        except Exception as ex:  # timeout, crash, malformed output: keep the defaults
-            info = {"ok": False, "error": repr(ex)[:300]}
+        def child(flag, limit):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, "--workload", workload], capture_output=True, text=True,
+                                   timeout=limit, env=env)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                return json.loads(line[-1]) if (r.returncode == 0 and line) else {"ok": False, "error": (r.stderr or "no output")[-300:]}
+            except Exception as ex:  # timeout, crash, malformed output: keep the defaults
+                return {"ok": False, "error": repr(ex)[:300]}
+
+        info = child("--probe", timeout_s)
+        if info.get("ok") and info.get("loop5_split_ok"):
+            # the persistent cooperative kernel of the active list gets a child (and a shorter leash) of its own: a
+            # grid-wide barrier that never completes on this box must not cost the other results
+            fused = child("--probe-fused", 150)
+            info["loop5_fused_active_ok"] = bool(fused.get("ok") and fused.get("loop5_fused_active_ok"))
+            if info["loop5_fused_active_ok"]:
+                info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
+            elif not fused.get("ok"):
+                info["loop5_fused_active_error"] = fused.get("error", "")[:200]
         try:
             with open(PROBE_CACHE, "w") as fh:
                 json.dump(info, fh)
@@ -418,11 +447,12 @@ def main():
     ap.add_argument("--no-probe", action="store_true", help="library defaults without the child-process probe")
     ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 = off, 1 = on, 2 = on with the active list in one cooperative kernel")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--probe-fused", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.probe:
+    if args.probe or args.probe_fused:
         run_probe(args)
         return
 
@@ -449,7 +479,7 @@ def main():
     if args.variant >= 0:
         variants = [args.variant, args.variant, 0]
     elif not args.no_probe and rank == 0:
-        variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank)
+        variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank, workload=args.workload)
     if args.split >= 0:
         variants[2] = min(max(args.split, 0), 2)
     if world > 1:

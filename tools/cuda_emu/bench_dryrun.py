@@ -64,16 +64,25 @@ def main(argv):
     bench.make_case = make_case
     bench.PROBE_CACHE = os.path.join("/tmp", f"ibmfoam_b200_probe_dryrun_{os.getpid()}.json")
 
-    def choose_variants(local_rank, timeout_s=0):
-        """the probe in-process (the real one runs it in a child on the GPU), then bench.py's own selection logic"""
-        buf = io.StringIO()
-        args = type("A", (), {"workload": "big512"})()
-        with contextlib.redirect_stdout(buf):
-            bench.run_probe(args)
-        info = json.loads([ln for ln in buf.getvalue().splitlines() if ln.startswith("{")][-1])
+    def choose_variants(local_rank, timeout_s=0, workload="big512"):
+        """both probes in-process (the real ones run in children on the GPU), merged as bench.choose_variants merges them,
+        then bench.py's own selection logic on the result"""
+        def part(fused):
+            buf = io.StringIO()
+            args = type("A", (), {"workload": workload, "probe_fused": fused})()
+            with contextlib.redirect_stdout(buf):
+                bench.run_probe(args)
+            return json.loads([ln for ln in buf.getvalue().splitlines() if ln.startswith("{")][-1])
+
+        info = part(False)
+        if info.get("ok") and info.get("loop5_split_ok"):
+            fused = part(True)
+            info["loop5_fused_active_ok"] = bool(fused.get("ok") and fused.get("loop5_fused_active_ok"))
+            if info["loop5_fused_active_ok"]:
+                info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
         with open(bench.PROBE_CACHE, "w") as fh:
             json.dump(info, fh)
-        return real_choose(local_rank)
+        return real_choose(local_rank, workload=workload)
 
     real_choose = bench.choose_variants
     bench.choose_variants = choose_variants
