@@ -327,7 +327,7 @@ def run_probe(args):
     print(json.dumps(out))
 
 
-def choose_variants(local_rank, timeout_s=360, workload="big512"):
+def choose_variants(local_rank, timeout_s=300, workload="big512"):
     """parent: run the probe in a child process on this rank's GPU (or reuse the result an earlier run on this box left in
     /tmp) and pick, per kernel, the faster verified generation.  Returns (forcing, stress, info)."""
     info = None
@@ -357,7 +357,7 @@ def choose_variants(local_rank, timeout_s=360, workload="big512"):
         if info.get("ok") and info.get("loop5_split_ok"):
             # the persistent cooperative kernel of the active list gets a child (and a shorter leash) of its own: a
             # grid-wide barrier that never completes on this box must not cost the other results
-            fused = child("--probe-fused", 150)
+            fused = child("--probe-fused", 100)
             info["loop5_fused_active_ok"] = bool(fused.get("ok") and fused.get("loop5_fused_active_ok"))
             if info["loop5_fused_active_ok"]:
                 info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
@@ -461,7 +461,7 @@ def main():
     from ibmfoam_b200 import capi
 
     # a diverged or dead-locked multi-rank run must not sit on the GPUs until an external limit kills it
-    watchdog = threading.Timer(float(os.environ.get("IBM_BENCH_WATCHDOG_S", "900")), lambda: (sys.stderr.write("bench.py watchdog: run exceeded its time limit\n"), os._exit(17)))
+    watchdog = threading.Timer(float(os.environ.get("IBM_BENCH_WATCHDOG_S", "1200")), lambda: (sys.stderr.write("bench.py watchdog: run exceeded its time limit\n"), os._exit(17)))
     watchdog.daemon = True
     watchdog.start()
 
@@ -484,7 +484,9 @@ def main():
         variants[2] = min(max(args.split, 0), 2)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # (the other ranks wait here while rank 0 runs the probe children: up to ~7 minutes if both hang)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=30))
         vt = torch.tensor(variants, device=dev, dtype=torch.int32)
         dist.broadcast(vt, 0)
         variants = [int(x) for x in vt.tolist()]
