@@ -96,6 +96,7 @@ SYMBOLS = {
     "ibm_sync": (C.c_int, [_VP]),
     "ibm_set_kernel_variant": (C.c_int, [_VP, C.c_int, C.c_int]),
     "ibm_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int]),
+    "ibm_set_real_option": (C.c_int, [_VP, C.c_char_p, C.c_double]),
     "ibm_get_counter": (C.c_int, [_VP, C.c_char_p, C.POINTER(C.c_longlong)]),
     "ibm_timings": (C.c_int, [_VP, C.POINTER(Timing)]),
     "ibm_timings_reset": (C.c_int, [_VP]),

@@ -216,6 +216,16 @@ class ParticleCloud:
     def set_option(self, name, value):
         check(self._L.ibm_set_option(self._h, name.encode(), int(value)), self._h)
 
+    def set_real_option(self, name, value):
+        check(self._L.ibm_set_real_option(self._h, name.encode(), float(value)), self._h)
+
+    def soft_sphere(self, kn, gamma_n=0.0, gamma_t=0.0, mu=0.0):
+        """EXTENSION (no counterpart in the reference): spring - dashpot - slider contact law for sphere / cylinder pairs
+        instead of the hard-sphere impulse; see include/ibmfoam_b200.h at ibm_set_real_option."""
+        for k, v in (("soft_sphere_kn", kn), ("soft_sphere_gamma_n", gamma_n), ("soft_sphere_gamma_t", gamma_t), ("soft_sphere_mu", mu)):
+            self.set_real_option(k, v)
+        self.set_option("collision_model", 1)
+
     def counter(self, name):
         v = C.c_longlong()
         check(self._L.ibm_get_counter(self._h, name.encode(), C.byref(v)), self._h)

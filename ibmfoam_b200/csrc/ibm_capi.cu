@@ -1014,7 +1014,27 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_check_ppm") == 0) { c->activeCheckPpm = value; return IBM_OK; }
+  if (std::strcmp(name, "collision_model") == 0) {
+    if (value != 0 && value != 1) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: collision_model is 0 (reference impulse) or 1 (soft sphere)");
+    c->collisionModel = value;
+    motion_invalidate_graph(c);
+    return IBM_OK;
+  }
   return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_option: unknown option ") + name);
+}
+
+int ibm_set_real_option(ibm_ctx* c, const char* name, double value) {
+  if (!c || !name) return IBM_E_ARG;
+  double* slot = nullptr;
+  if (std::strcmp(name, "soft_sphere_kn") == 0) slot = &c->softKn;
+  else if (std::strcmp(name, "soft_sphere_gamma_n") == 0) slot = &c->softGammaN;
+  else if (std::strcmp(name, "soft_sphere_gamma_t") == 0) slot = &c->softGammaT;
+  else if (std::strcmp(name, "soft_sphere_mu") == 0) slot = &c->softMu;
+  if (!slot) return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_real_option: unknown option ") + name);
+  if (!(value >= 0.0)) return ctx_fail(c, IBM_E_ARG, std::string("ibm_set_real_option: ") + name + " must be >= 0");
+  *slot = value;
+  motion_invalidate_graph(c);
+  return IBM_OK;
 }
 
 int ibm_timings(ibm_ctx* c, ibm_timing* out) {

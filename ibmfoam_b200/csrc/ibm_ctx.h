@@ -91,6 +91,8 @@ struct ibm_ctx {
   bool activeLoop5 = false; // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
                             // sub-step; written after round 1's GPU budget was spent, verified under emulation only
   int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (>= 1: a quiet instance needs B_i >= s_i)
+  int collisionModel = 0;         // EXTENSION: 1 = soft-sphere contact law (ibm_motion.cu d5_pair_force); 0 = the reference's impulse
+  double softKn = 0.0, softGammaN = 0.0, softGammaT = 0.0, softMu = 0.0;
   bool fusedActive = false;       // split steps: the active list's sub-steps in one persistent cooperative kernel (k5a_fused)
   int activeCheckPpm = 1000000;   // fraction of B_i the per-sub-step check allows (tests shrink it to force the fallback)
   // motion (loop 5) scratch lives in ibm_motion.cu
@@ -117,6 +119,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats);
 int motion_substep(ibm_ctx* c, double localDt);
 void motion_destroy(ibm_ctx* c);
 void motion_invalidate_groups(ibm_ctx* c);
+void motion_invalidate_graph(ibm_ctx* c);
 bool motion_counter(ibm_ctx* c, const char* name, long long* value);
 int combine_forces(ibm_ctx* c);
 // ibm_comm.cu

@@ -67,6 +67,9 @@ struct MotionDev {
   const PatchDev* patches; const int* wallPatch; const int* cycPatch;
   double gx, gy, gz, e;
   int moving, rotating;
+  // EXTENSION (no counterpart in the reference): soft-sphere contact law instead of the hard-sphere impulse
+  int model;                       // 0 = particleCloud.C:505-521 as coded, 1 = linear spring - dashpot - Coulomb slider
+  double kn, gn, gt, mu;           // normal stiffness, normal / tangential damping, friction coefficient
   // quiet / active split of a fluid step (option active_loop5): see the block comment above k5q_bounds
   int activeMode;                  // 1 while the split is in force (append_link then keeps the active list up to date)
   int* act; int* nAct;             // instances that can take part in a contact, a wall / patch hit or a copy group this step
@@ -315,14 +318,42 @@ __device__ __forceinline__ void d5_pair_force(MotionDev m, InstanceSoA in, const
   D3 v12 = iAmP1 ? (vi - vj) : (vj - vi);
   D3 hitPt{0, 0, 0};
   if (!pair_collision(p1, p2, hitPt)) return;
-  if (!(dot3(x12, v12) < 0)) return;
-  double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
-  double M = mass1 * mass2 / (mass1 + mass2);
-  double x12Dotv12 = dot3(x12, v12);
-  double x12Sqr = magSqr3(x12);
-  D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
-  D3 myF = iAmP1 ? -F : F;
-  D3 myT = iAmP1 ? cross3(-F, hitPt) : cross3(F, hitPt);
+  D3 myF, myT;
+  if (m.model == 1 && sci->kind != 2 && scj->kind != 2) {
+    // EXTENSION: linear spring - dashpot in the normal direction, viscous tangential force capped by Coulomb friction
+    // (no tangential spring, hence no contact history), acting for as long as the bodies overlap.  Evaluated once in
+    // the canonical order (p1 = larger index) so that the two rows of a pair hold exactly opposite forces.
+    const D3 w1 = iAmP1 ? ld3(in.om, i) : ld3(in.om, j), w2 = iAmP1 ? ld3(in.om, j) : ld3(in.om, i);
+    const double r1 = 0.5 * cmptMax3(p1.D), r2 = 0.5 * cmptMax3(p2.D);
+    const double dist = mag3(x12);
+    if (!(dist > 0.0)) return;
+    const D3 n = x12 / dist;                       // from p2 to p1
+    const double overlap = (r1 + r2) - dist;       // > 0 (pair_collision)
+    const D3 a1 = -(r1 - 0.5 * overlap) * n;       // contact point relative to the centre of p1
+    const D3 a2 = (r2 - 0.5 * overlap) * n;        // ... of p2
+    const D3 vrel = (v12 + cross3(w1, a1)) - cross3(w2, a2);
+    const double vn = dot3(vrel, n);
+    double Fn = m.kn * overlap - m.gn * vn;
+    if (Fn < 0.0) Fn = 0.0;                        // no attraction while the bodies separate
+    const D3 vt = vrel - vn * n;
+    const double vtMag = mag3(vt);
+    D3 F1 = Fn * n;
+    if (vtMag > 0.0) {
+      const double Ft = fmin(m.gt * vtMag, m.mu * Fn);
+      F1 = F1 - (Ft / vtMag) * vt;
+    }
+    myF = iAmP1 ? F1 : -F1;
+    myT = iAmP1 ? cross3(a1, F1) : cross3(a2, -F1);
+  } else {
+    if (!(dot3(x12, v12) < 0)) return;
+    double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
+    double M = mass1 * mass2 / (mass1 + mass2);
+    double x12Dotv12 = dot3(x12, v12);
+    double x12Sqr = magSqr3(x12);
+    D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
+    myF = iAmP1 ? -F : F;
+    myT = iAmP1 ? cross3(-F, hitPt) : cross3(F, hitPt);
+  }
   const int slot = atomicAdd(&m.cCnt[i], 1);
   if (slot >= CONTACT_CAP) { atomicExch(m.overflow, 1); return; }
   const size_t o = (size_t)i * CONTACT_CAP + slot;
@@ -1554,9 +1585,19 @@ static void ensure_bins_clear(ibm_ctx* c) {
   cudaMemsetAsync(d.hitCount, 0, sizeof(int), c->stream);
 }
 
+static void refresh_contact_model(ibm_ctx* c) {
+  MotionDev& d = ((Motion*)c->motion)->d;
+  d.model = c->collisionModel; d.kn = c->softKn; d.gn = c->softGammaN; d.gt = c->softGammaT; d.mu = c->softMu;
+}
+
+void motion_invalidate_graph(ibm_ctx* c) {
+  if (c->motion) ((Motion*)c->motion)->graphValid = false;  // MotionDev is captured by value
+}
+
 int motion_substep(ibm_ctx* c, double localDt) {
   int rc = ensure_motion(c);
   if (rc) return rc;
+  refresh_contact_model(c);
   ensure_bins_clear(c);
   ((Motion*)c->motion)->d.activeMode = 0;  // a single literal sub-step is always the unsplit chain
   ctx_tic(c, T_ADVANCE);
@@ -1569,6 +1610,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
   int rc = ensure_motion(c);
   if (rc) return rc;
   Motion* M = (Motion*)c->motion;
+  refresh_contact_model(c);
   ctx_tic(c, T_ADVANCE);
   // literal loop of particleCloud.C:1247-1275 (App. B #22): the schedule of local time steps is plain fp64
   // scalar arithmetic, evaluated here and handed to the persistent kernel

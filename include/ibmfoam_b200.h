@@ -190,6 +190,16 @@ int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant);
 int ibm_get_counter(ibm_ctx* ctx, const char* name, long long* value);
 int ibm_set_option(ibm_ctx* ctx, const char* name, int value); /* "graph_loop5" (default 1): sub-step launch sequence replayed as a CUDA graph; "fused_loop5" (default 0): one persistent cooperative kernel; "active_loop5" (default 0): quiet / active split of a fluid step (same results; instances that cannot interact integrate all sub-steps in one kernel), "fused_active_loop5" (default 0): with the split, the active list's sub-steps in one persistent cooperative kernel, "active_loop5_safety_ppm" (default 2000000): displacement-budget factor */
 
+/* EXTENSION without a counterpart in the reference (the reference names a soft-sphere model in
+ * src/particleCloud/Make/files but ships none): ibm_set_option(ctx, "collision_model", 1) replaces the hard-sphere impulse of
+ * particleCloud::computeCollisions (particleCloud.C:505-521) for sphere / cylinder pairs by a linear spring - dashpot -
+ * Coulomb-slider contact law evaluated every sub-step while the bodies overlap:
+ *   F_n = max(0, kn * overlap - gamma_n * (v_rel . n)),   F_t = -min(gamma_t |v_t|, mu F_n) v_t / |v_t|
+ * with v_rel the relative velocity of the two surfaces at the contact point (rotation included).  Walls and periodic
+ * copies keep the reference's treatment.  Parameters (all >= 0): "soft_sphere_kn", "soft_sphere_gamma_n",
+ * "soft_sphere_gamma_t", "soft_sphere_mu".  Default collision_model = 0 = the reference, bit for bit. */
+int ibm_set_real_option(ibm_ctx* ctx, const char* name, double value);
+
 /* ---- timing -------------------------------------------------------------------------------------- */
 int ibm_timings(ibm_ctx* ctx, ibm_timing* out);
 int ibm_timings_reset(ibm_ctx* ctx);

@@ -104,6 +104,19 @@ Foam::particleCloud::particleCloud
         FatalErrorInFunction << ibm_last_error(nullptr) << exit(FatalError);
     }
 
+    // EXTENSION (absent from the reference, which only names a soft-sphere model in src/particleCloud/Make/files):
+    //     collisionModel softSphere;  softSphereCoeffs { kn ...; gamman ...; gammat ...; mu ...; }
+    // in IBMProperties selects the spring - dashpot - slider contact law; without the keyword the reference's impulse is used
+    if (dict_.lookupOrDefault<word>("collisionModel", "hardSphere") == "softSphere")
+    {
+        const dictionary& sDict = dict_.subDict("softSphereCoeffs");
+        check(ibm_set_real_option(ctx_, "soft_sphere_kn", readScalar(sDict.lookup("kn"))), "softSphereCoeffs");
+        check(ibm_set_real_option(ctx_, "soft_sphere_gamma_n", sDict.lookupOrDefault<scalar>("gamman", 0.0)), "softSphereCoeffs");
+        check(ibm_set_real_option(ctx_, "soft_sphere_gamma_t", sDict.lookupOrDefault<scalar>("gammat", 0.0)), "softSphereCoeffs");
+        check(ibm_set_real_option(ctx_, "soft_sphere_mu", sDict.lookupOrDefault<scalar>("mu", 0.0)), "softSphereCoeffs");
+        check(ibm_set_option(ctx_, "collision_model", 1), "collisionModel");
+    }
+
     // particle.<i> sub-dictionaries (reference particleCloud.C:1070-1117, particleIBM.C:269-297)
     List<ibm_particle_init> init(nParticles_);
     forAll(init, i)

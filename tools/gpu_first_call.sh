@@ -23,7 +23,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 for f in tests/test_gpu_forcing.py tests/test_gpu_marking.py tests/test_gpu_stress.py tests/test_gpu_motion.py \
          tests/test_gpu_multirank.py tests/test_gpu_zz_device_api.py tests/test_gpu_zz_reference_vectors.py tests/test_host_mirror.py \
          tests/test_zz_gpu_shim_dropin.py tests/test_zz_gpu_validation_cases.py tests/test_zzz_gpu_active_loop5.py \
-         tests/test_zzz_gpu_v5_kernels.py; do
+         tests/test_zzz_gpu_soft_sphere.py tests/test_zzz_gpu_v5_kernels.py; do
   [ -f "$f" ] && leg "pytest_$(basename "$f" .py)" 900 $PY -m pytest "$f" -m gpu -q -p no:cacheprovider
 done
 leg smoke 300 $PY -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
