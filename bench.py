@@ -19,7 +19,7 @@ integral, force combination, the literal sub-step loop, re-marking).  One cell-p
                 a child process on this very box shows parity with the defaults AND a lower time, and a second check at
                 the full size agrees; config.kernel_generations records what ran and why (--no-probe: defaults only).
 
-python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1|2]
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1|2] [--mark 0|1]
 """
 from __future__ import annotations
 
@@ -262,6 +262,20 @@ def run_probe(args):
         eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
         out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
         out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
+    if not args.probe_fused:
+        # the second marking kernel must produce the very same shell lists and statuses
+        ga, gb = ParticleCloud(case), ParticleCloud(case)
+        gb.set_option("mark_variant", 1)
+        gb.update()
+        sa, sb = ga.state_arrays(), gb.state_arrays()
+        same = all(np.array_equal(sa[k], sb[k]) for k in ("nShell", "onMesh", "active", "N"))
+        for inst in range(ga.nParticles()):
+            if not same:
+                break
+            x, y = ga.shell(inst), gb.shell(inst)
+            same = np.array_equal(x["cells"], y["cells"]) and np.array_equal(x["jk"], y["jk"])
+        out["mark2_ok"] = bool(same)
+        ga.close(); gb.close()
     # the quiet/active split of loop 5 must give the very same trajectory as the unsplit path (bit for bit)
     fast = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     fast.particles.v *= 25.0
@@ -290,16 +304,29 @@ def run_probe(args):
         out["ok"] = True
         print(json.dumps(out))
         return
-    if not (out["kernels_ok"] or out["loop5_split_ok"]):
+    if not (out["kernels_ok"] or out["loop5_split_ok"] or out["mark2_ok"]):
         print(json.dumps(out))
         return
-    t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}}
+    t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}, "update_ms": {}}
     # (b) loop 5 at the run's own instance count (it needs the particles, not the fields): without / with the split
-    if out["loop5_split_ok"]:
+    if out["loop5_split_ok"] or out["mark2_ok"]:
         big = make_case(args.workload)
-        if big.cloud.moving:
+        if big.cloud.moving and out["loop5_split_ok"]:
             for split in (0, 1):
                 t["advance_ms"][str(split)] = _time_loop5(big, split)
+        if out["mark2_ok"]:
+            gc = ParticleCloud(big, device=0)
+            for mv in (0, 1):
+                gc.set_option("mark_variant", mv)
+                for _ in range(2):
+                    gc.update()
+                gc.sync()
+                gc.timings(reset=True)
+                for _ in range(4):
+                    gc.update()
+                gc.sync()
+                t["update_ms"][str(mv)] = gc.timings()["update_ms"] / 4
+            gc.close()
         del big
     # (c) forcing / stress kernels on a 256^3 / 12.5k-sphere workload, device-resident fields
     case = make_case("big256")
@@ -368,8 +395,11 @@ def choose_variants(local_rank, timeout_s=300, workload="big512"):
                 json.dump(info, fh)
         except Exception:
             pass
-    fv, sv, split = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0
+    fv, sv, split, mark = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0, 0
     if info.get("ok"):
+        um = info.get("update_ms", {})
+        if info.get("mark2_ok") and um.get("1", 1e30) < um.get("0", 0.0):
+            mark = 1
         fm, sm, am = info["forcing_ms"], info["stress_ms"], info.get("advance_ms", {})
         if info.get("kernels_ok"):
             if fm.get("5", 1e30) < fm.get(str(fv), 0.0):
@@ -380,7 +410,7 @@ def choose_variants(local_rank, timeout_s=300, workload="big512"):
         for mode, key in ((1, "loop5_split_ok"), (2, "loop5_fused_active_ok")):
             if info.get(key) and am.get(str(mode), 1e30) < best:
                 split, best = mode, am[str(mode)]
-    return fv, sv, split, info
+    return fv, sv, split, mark, info
 
 
 def _ref_worker(args):
@@ -444,6 +474,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="-1 = probe (verified + faster generation per kernel), >= 0 = force that generation")
+    ap.add_argument("--mark", type=int, default=-1, help="marking kernel: -1 = as probed (first version without a probe), 0 / 1 = forced")
     ap.add_argument("--no-probe", action="store_true", help="library defaults without the child-process probe")
     ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 = off, 1 = on, 2 = on with the active list in one cooperative kernel")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
@@ -474,14 +505,16 @@ def main():
     dev = torch.device("cuda", local_rank)
     # which kernel generation: local rank 0 asks a child process BEFORE joining the process group (the others wait in the
     # rendezvous), then everyone gets its answer
-    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0]   # forcing generation, stress generation, loop-5 split
+    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0, 0]   # forcing generation, stress generation, loop-5 mode, marking kernel
     probe_info = None
     if args.variant >= 0:
-        variants = [args.variant, args.variant, 0]
+        variants = [args.variant, args.variant, 0, 0]
     elif not args.no_probe and rank == 0:
-        variants[0], variants[1], variants[2], probe_info = choose_variants(local_rank, workload=args.workload)
+        variants[0], variants[1], variants[2], variants[3], probe_info = choose_variants(local_rank, workload=args.workload)
     if args.split >= 0:
         variants[2] = min(max(args.split, 0), 2)
+    if args.mark >= 0:
+        variants[3] = 1 if args.mark else 0
     if world > 1:
         import torch.distributed as dist
         import datetime
@@ -511,6 +544,18 @@ def main():
     cloud.set_kernel_variant(variants[0], variants[1])
     cloud.set_option("active_loop5", int(variants[2] > 0))
     cloud.set_option("fused_active_loop5", int(variants[2] == 2))
+    mark_check = None
+    if variants[3]:
+        # full-size check of the second marking kernel: same shell count and on-mesh status for every instance
+        st0 = cloud.state_arrays()
+        cloud.set_option("mark_variant", 1)
+        cloud.update()
+        st1 = cloud.state_arrays()
+        mark_check = bool(np.array_equal(st0["nShell"], st1["nShell"]) and np.array_equal(st0["onMesh"], st1["onMesh"]))
+        if not mark_check:
+            variants[3] = 0
+            cloud.set_option("mark_variant", 0)
+            cloud.update()
     setup_s = time.time() - t0
     have_motion = True
     try:
@@ -697,7 +742,7 @@ def main():
                            "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)" if have_motion else "n/a",
                            "step": "forcing + solve(stress, combine, sub-steps, re-marking)" if have_motion else "forcing + stress + re-marking (loop 5 not built)",
                            "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s,
-                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "loop5_quiet_active_split": bool(variants[2]), "loop5_active_list_fused": variants[2] == 2,
+                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "marking": 1 + variants[3], "marking_full_size_check": mark_check, "loop5_quiet_active_split": bool(variants[2]), "loop5_active_list_fused": variants[2] == 2,
                                                   "loop5_active_instances": cloud.counter("loop5_active_instances") if variants[2] else None,
                                                   "loop5_fallbacks": cloud.counter("loop5_fallbacks") if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else

@@ -256,7 +256,7 @@ int ctx_update(ibm_ctx* c) {
   for (int attempt = 0; attempt < 8; ++attempt) {
     IBM_CUDA(c, cudaMemsetAsync(c->dScal, 0, 8 * sizeof(int), c->stream));
     // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
-    launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4);
+    launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant);
     if (comm_ranks(c) > 1 && c->nInst > 0) {
       // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs
       int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst, 1);
@@ -443,6 +443,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_MARK_VARIANT")) c->markVariant = std::atoi(e) == 1 ? 1 : 0;
   if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
   LatticeDev& L = c->L;
   L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
@@ -1014,6 +1015,11 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_check_ppm") == 0) { c->activeCheckPpm = value; return IBM_OK; }
+  if (std::strcmp(name, "mark_variant") == 0) {
+    if (value != 0 && value != 1) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: mark_variant is 0 or 1");
+    c->markVariant = value;
+    return IBM_OK;
+  }
   if (std::strcmp(name, "collision_model") == 0) {
     if (value != 0 && value != 1) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: collision_model is 0 (reference impulse) or 1 (soft sphere)");
     c->collisionModel = value;

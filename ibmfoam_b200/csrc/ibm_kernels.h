@@ -7,7 +7,7 @@ namespace ibm {
 // ---- ibm_kernels_ref.cu (compiled with -fmad=false) ----
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow);
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant = 0);
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_fill(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                     int* shellCell, int* shellJK);

@@ -143,6 +143,44 @@ __global__ void k1_count(LatticeDev L, const ShapeClassDev* __restrict__ classes
   }
 }
 
+// second half of the marking kernels: on-mesh point count, status, per-instance outputs (block-wide; `off` < 0 = shell
+// buffer overflow)
+__device__ __forceinline__ void mark_finish(const LatticeDev& L, const ShapeClassDev& sc, InstanceSoA& in, int b, double cx, double cy,
+                                            double cz, const double* srot, int* sm, int off, int nShell) {
+  // on-mesh point count (particleShape.C:41-91): all N when the outer layer is strictly inside the lattice
+  double rOut = sc.Rbound + sc.delta;
+  const double mx = 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
+  rOut += mx;
+  const bool inside = cx - rOut > L.ox && cx + rOut < L.ox + L.nx * L.dx && cy - rOut > L.oy && cy + rOut < L.oy + L.ny * L.dy &&
+                      (L.nz == 1 && sc.kind != 0 ? (cz > L.oz + L.kz0 * L.dz && cz < L.oz + (L.kz0 + L.nz) * L.dz)
+                                                 : (cz - rOut > L.oz + L.kz0 * L.dz && cz + rOut < L.oz + (L.kz0 + L.nz) * L.dz));
+  // ... and none when the outer layer cannot reach the local lattice at all (other slabs' instances on a multi-GPU run)
+  const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
+                       cz + rOut < L.oz + L.kz0 * L.dz || cz - rOut > L.oz + (L.kz0 + L.nz) * L.dz;
+  int nOn;
+  if (inside) {
+    nOn = sc.N;
+  } else if (outside) {
+    nOn = 0;
+  } else {
+    int on = 0;
+    for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {
+      V3 p = shape_point(sc, srot, cx, cy, cz, n);
+      int I, J, K;
+      if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0) ++on;
+    }
+    nOn = block_sum(on, sm);
+  }
+  if (threadIdx.x == 0) {
+    int I, J, K;
+    const int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
+    in.nShell[b] = off >= 0 ? nShell : 0;
+    in.shellOff[b] = off >= 0 ? off : 0;
+    in.nPtsOnMesh[b] = nOn;
+    in.onLocal[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 single pass: rotation matrix, status counts and the shell list in ONE kernel.  Shell cells found in the
 // bounding box go to a shared-memory list; one atomicAdd on a global cursor reserves the instance's segment of the
@@ -211,38 +249,123 @@ __global__ void k1_mark(LatticeDev L, const ShapeClassDev* __restrict__ classes,
       }
     }
   }
-  // on-mesh point count (particleShape.C:41-91): all N when the outer layer is strictly inside the lattice
-  double rOut = sc.Rbound + sc.delta;
-  const double mx = 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
-  rOut += mx;
-  const bool inside = cx - rOut > L.ox && cx + rOut < L.ox + L.nx * L.dx && cy - rOut > L.oy && cy + rOut < L.oy + L.ny * L.dy &&
-                      (L.nz == 1 && sc.kind != 0 ? (cz > L.oz + L.kz0 * L.dz && cz < L.oz + (L.kz0 + L.nz) * L.dz)
-                                                 : (cz - rOut > L.oz + L.kz0 * L.dz && cz + rOut < L.oz + (L.kz0 + L.nz) * L.dz));
-  // ... and none when the outer layer cannot reach the local lattice at all (other slabs' instances on a multi-GPU run)
-  const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
-                       cz + rOut < L.oz + L.kz0 * L.dz || cz - rOut > L.oz + (L.kz0 + L.nz) * L.dz;
-  int nOn;
-  if (inside) {
-    nOn = sc.N;
-  } else if (outside) {
-    nOn = 0;
-  } else {
-    int on = 0;
-    for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {
-      V3 p = shape_point(sc, srot, cx, cy, cz, n);
-      int I, J, K;
-      if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0) ++on;
+  mark_finish(L, sc, in, b, cx, cy, cz, srot, sm, off, nShell);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 single pass, second version (option mark_variant = 1; same outputs).  What the line-level profile of k1_mark said
+// (profiles/r1_lines_k1_mark_big512_final.txt): the kernel is instruction-bound, and the instructions are the atan2 /
+// acos of the polar bin executed by warps in which ~1 lane in 5 holds a shell cell (the shell is 21 % of its bounding
+// box), plus the runtime integer divisions that turn the box index into (I, J, K) and a block-wide reduction.  Here
+//   phase A  every thread runs only the radial test over its box cells and appends the box index of each shell cell to
+//            the shared list (spheres / cylinders; an ellipse's radius needs the angle, so it takes mark_cell at once),
+//   phase B  the threads walk the COMPACT list and compute the polar bin with all lanes busy,
+// the box index is split with a float reciprocal and one correction step, and the shell count is the list counter.
+// The per-cell arithmetic is mark_cell's, unchanged, so the lists are the same sets of (cell, j, k).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_box_index(int t, int bi, int bij, float rbi, float rbij, int& i, int& j, int& k) {
+  k = (int)((float)t * rbij);
+  int rem = t - k * bij;
+  if (rem < 0) { --k; rem += bij; } else if (rem >= bij) { ++k; rem -= bij; }
+  j = (int)((float)rem * rbi);
+  i = rem - j * bi;
+  if (i < 0) { --j; i += bi; } else if (i >= bi) { ++j; i -= bi; }
+}
+
+__global__ void k1_mark2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst,
+                         int* __restrict__ shellCell, int* __restrict__ shellJK, int shellCap, int* __restrict__ cursor,
+                         int* __restrict__ overflow) {
+  __shared__ int sm[32];
+  __shared__ double srot[9];
+  __shared__ int listCell[K1_LIST], listJK[K1_LIST];
+  __shared__ int nList, segOff, nDirect;
+  const int b = blockIdx.x;
+  if (b >= nInst) return;
+  const ShapeClassDev sc = classes[in.cls[b]];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  if (threadIdx.x == 0) {
+    set_rotation_matrix(in.th[0][b], in.th[1][b], in.th[2][b], srot);  // particleShape::moveMesh (particleShape.C:291-295)
+    for (int q = 0; q < 9; ++q) in.rot[9 * (size_t)b + q] = srot[q];
+    if (sc.kind == 2) {  // ellipse::updateCellLists wraps theta.z first (ellipse.C:155-157)
+      double tz = in.th[2][b];
+      if (tz < 0) tz = xadd(tz, IBM_TWOPI);
+      if (tz > IBM_TWOPI) tz = xsub(tz, IBM_TWOPI);
+      in.th[2][b] = tz;
     }
-    nOn = block_sum(on, sm);
+    nList = 0; nDirect = 0;
+  }
+  __syncthreads();
+  const double thz = in.th[2][b];
+  Box bx = bounding_box(L, cx, cy, cz, sc.Rbound);
+  const int bi = bx.i1 - bx.i0 + 1, bj = bx.j1 - bx.j0 + 1, bk = bx.k1 - bx.k0 + 1;
+  const int nb = (bi > 0 && bj > 0 && bk > 0) ? bi * bj * bk : 0;
+  const int bij = bi * bj;
+  const bool fastSplit = nb < (1 << 20);  // float quotients are within one of the truth well beyond this
+  const float rbi = 1.0f / (float)max(bi, 1), rbij = 1.0f / (float)max(bij, 1);
+  const bool radial = sc.kind != 2;
+  const double Rr = sc.d / 2.0, innerR = xsub(Rr, sc.delta);
+#define cell_of(t, I, J, K)                                                \
+  do {                                                                     \
+    int i_, j_, k_;                                                        \
+    if (fastSplit) split_box_index((t), bi, bij, rbi, rbij, i_, j_, k_);   \
+    else { i_ = (t) % bi; j_ = ((t) / bi) % bj; k_ = (t) / bij; }          \
+    I = bx.i0 + i_; J = bx.j0 + j_; K = bx.k0 + k_;                        \
+  } while (0)
+  // phase A
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+    int I, J, K;
+    cell_of(t, I, J, K);
+    const double Cx = cc(L.ox, I, L.dx), Cy = cc(L.oy, J, L.dy), Cz = cc(L.oz, K + L.kz0, L.dz);
+    if (radial) {
+      const double r = xmag(xsub(Cx, cx), xsub(Cy, cy), xsub(Cz, cz));  // the test of mark_cell, sphere.C:212-216, cylinder.C:169-173
+      if (r >= innerR && r <= Rr) {
+        const int s = atomicAdd(&nList, 1);
+        if (s < K1_LIST) listCell[s] = t;
+      }
+    } else {
+      int j, k;
+      if (mark_cell(sc, cx, cy, cz, thz, Cx, Cy, Cz, j, k)) {
+        const int s = atomicAdd(&nList, 1);
+        if (s < K1_LIST) { listCell[s] = lat_index(L, I, J, K); listJK[s] = j | (k << 16); }
+      }
+    }
+  }
+  __syncthreads();
+  const int nShell = nList;
+  // phase B: polar bins of the compact list
+  if (radial && nShell <= K1_LIST) {
+    for (int s = threadIdx.x; s < nShell; s += blockDim.x) {
+      int I, J, K, j = 0, k = 0;
+      cell_of(listCell[s], I, J, K);
+      mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k);
+      listCell[s] = lat_index(L, I, J, K);
+      listJK[s] = j | (k << 16);
+    }
   }
   if (threadIdx.x == 0) {
-    int I, J, K;
-    const int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
-    in.nShell[b] = off >= 0 ? nShell : 0;
-    in.shellOff[b] = off >= 0 ? off : 0;
-    in.nPtsOnMesh[b] = nOn;
-    in.onLocal[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
+    const int o = atomicAdd(cursor, nShell);
+    segOff = o;
+    if (o + nShell > shellCap) { atomicExch(overflow, 1); segOff = -1; }
   }
+  __syncthreads();
+  const int off = segOff;
+  if (off >= 0) {
+    if (nShell <= K1_LIST) {
+      for (int s = threadIdx.x; s < nShell; s += blockDim.x) { shellCell[off + s] = listCell[s]; shellJK[off + s] = listJK[s]; }
+    } else {
+      for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+        int I, J, K, j, k;
+        cell_of(t, I, J, K);
+        if (mark_cell(sc, cx, cy, cz, thz, cc(L.ox, I, L.dx), cc(L.oy, J, L.dy), cc(L.oz, K + L.kz0, L.dz), j, k)) {
+          const int s = atomicAdd(&nDirect, 1);
+          shellCell[off + s] = lat_index(L, I, J, K);
+          shellJK[off + s] = j | (k << 16);
+        }
+      }
+    }
+  }
+  mark_finish(L, sc, in, b, cx, cy, cz, srot, sm, off, nShell);
+#undef cell_of
 }
 
 // particleShape.C:97-108 and particleIBM.C:607-614 on the WHOLE mesh: nPtsOnMesh holds the point count over all
@@ -605,8 +728,10 @@ void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* 
   if (nInst > 0) k1_count<<<nInst, 128, 0, st>>>(L, classes, in, nInst);
 }
 void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow) {
-  if (nInst > 0) k1_mark<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant) {
+  if (nInst <= 0) return;
+  if (variant == 1) k1_mark2<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
+  else k1_mark<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
 }
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
   if (nInst > 0) k1_status<<<(nInst + 127) / 128, 128, 0, st>>>(Lg, classes, in, nInst);

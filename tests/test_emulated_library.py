@@ -42,6 +42,7 @@ SUBSET = [
     "tests/test_zzz_gpu_active_loop5.py::test_two_spheres_head_on[fused]",
     "tests/test_gpu_motion.py::test_two_spheres_head_on_closed_form[fused]",
     "tests/test_zzz_gpu_soft_sphere.py",
+    "tests/test_zzz_gpu_mark_variant.py",
 ]
 
 
@@ -78,7 +79,7 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
 @pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (several minutes)")
 @pytest.mark.parametrize("path", ["tests/test_gpu_forcing.py", "tests/test_gpu_marking.py", "tests/test_gpu_stress.py", "tests/test_gpu_motion.py",
                                   "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_zzz_gpu_v5_kernels.py", "tests/test_zzz_gpu_active_loop5.py",
-                                  "tests/test_zz_gpu_validation_cases.py", "tests/test_zzz_gpu_soft_sphere.py"])
+                                  "tests/test_zz_gpu_validation_cases.py", "tests/test_zzz_gpu_soft_sphere.py", "tests/test_zzz_gpu_mark_variant.py"])
 def test_gpu_parity_file_under_emulation(emu_lib, path):
     _child(emu_lib, [path], timeout=6000)
 

@@ -82,7 +82,7 @@ def main(argv):
                 info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
         with open(bench.PROBE_CACHE, "w") as fh:
             json.dump(info, fh)
-        return real_choose(local_rank, workload=workload)
+        return real_choose(local_rank, workload=workload)   # (forcing, stress, loop-5 mode, marking kernel, info)
 
     real_choose = bench.choose_variants
     bench.choose_variants = choose_variants

@@ -23,7 +23,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 for f in tests/test_gpu_forcing.py tests/test_gpu_marking.py tests/test_gpu_stress.py tests/test_gpu_motion.py \
          tests/test_gpu_multirank.py tests/test_gpu_zz_device_api.py tests/test_gpu_zz_reference_vectors.py tests/test_host_mirror.py \
          tests/test_zz_gpu_shim_dropin.py tests/test_zz_gpu_validation_cases.py tests/test_zzz_gpu_active_loop5.py \
-         tests/test_zzz_gpu_soft_sphere.py tests/test_zzz_gpu_v5_kernels.py; do
+         tests/test_zzz_gpu_mark_variant.py tests/test_zzz_gpu_soft_sphere.py tests/test_zzz_gpu_v5_kernels.py; do
   [ -f "$f" ] && leg "pytest_$(basename "$f" .py)" 900 $PY -m pytest "$f" -m gpu -q -p no:cacheprovider
 done
 leg smoke 300 $PY -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
@@ -36,6 +36,7 @@ leg bench_v5_split 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --split 1 -
 leg bench_v2_split 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 1 --no-cpu-baseline --no-e2e
 leg bench_v2_split_fused 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 2 --no-cpu-baseline --no-e2e
 leg bench_v5_split_fused 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --split 2 --no-cpu-baseline --no-e2e
+leg bench_v2_mark2 600 $PY bench.py --steps 5 --warmup 3 --no-probe --mark 1 --no-cpu-baseline --no-e2e
 leg bench_reference 600 $PY bench.py --impl reference --steps 2 --warmup 1
 
 # 3. launch list of a step (v5 + split) and one full capture of each fifth-generation kernel (one GPU, after the runs above exited)
