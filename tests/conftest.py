@@ -27,3 +27,18 @@ _EMU = os.environ.get("IBM_TEST_EMU_LIB")
 if _EMU:
     from ibmfoam_b200 import capi as _capi
     _capi.LIB_PATH = os.path.abspath(_EMU)
+
+
+def pytest_collection_modifyitems(config, items):
+    """On hardware no GPU test may hang the run: a kernel that never returns (a grid-wide barrier that cannot complete, say)
+    is turned into a failure of that test after 10 minutes - `thread` method, because a Python-level signal cannot interrupt
+    a blocked CUDA call.  Not under the emulation, where a test is legitimately slow (every CUDA thread is a fiber)."""
+    if _EMU:
+        return
+    try:
+        import pytest_timeout  # noqa: F401
+    except Exception:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(600, method="thread"))
