@@ -300,9 +300,15 @@ __device__ __forceinline__ void d5_find_pairs(MotionDev m, InstanceSoA in, int t
   }
 }
 
+__device__ __forceinline__ void d5_pair_eval(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT, int i, int j);
+
 __device__ __forceinline__ void d5_pair_force(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT, int h) {
   if (h >= min(*m.pairCount, m.pairCap)) return;
-  const int i = m.pairI[h], j = m.pairJ[h];
+  d5_pair_eval(m, in, classes, deltaT, m.pairI[h], m.pairJ[h]);
+}
+
+// the pair (i, j) as the reference evaluates it, appended to the contact row of instance i
+__device__ __forceinline__ void d5_pair_eval(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT, int i, int j) {
   const int idxI = in.index[i], idxJ = in.index[j];
   if (idxJ == idxI || in.onMesh[j] == 0) return;  // particleCloud.C:502
   const ShapeClassDev* sci = classes + in.cls[i];
@@ -397,6 +403,31 @@ __device__ __forceinline__ void d5_rows_finish(MotionDev m, InstanceSoA in, int 
     for (int q = 0; q < 3; ++q) { m.cF[3 * (r0 + b2 + 1) + q] = f[q]; m.cT[3 * (r0 + b2 + 1) + q] = t[q]; }
   }
   m.cCnt[i] = cnt;
+}
+
+// find_pairs + pair_force + rows_finish of ONE instance by one thread (used where the instances are few and a phase
+// boundary is a grid-wide barrier, k5a_fused): same candidates (27 bins, centre distance <= bin edge), same pair
+// evaluation, same finished row - the order in which entries are appended differs, the finished row does not depend on it.
+__device__ __forceinline__ void d5_row_direct(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT, int i) {
+  if (i >= *m.nInst || in.onMesh[i] == 0) return;
+  const D3 c = ld3(in.c, i);
+  int bx, by, bz;
+  bin_of(m, c, bx, by, bz);
+  const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
+  for (int z = max(bz - 1, 0); z <= min(bz + 1, m.nbz - 1); ++z)
+    for (int y = max(by - 1, 0); y <= min(by + 1, m.nby - 1); ++y)
+      for (int x = max(bx - 1, 0); x <= min(bx + 1, m.nbx - 1); ++x) {
+        const int bin = x + m.nbx * (y + m.nby * z);
+        const int nb = min(m.binCnt[bin], m.binCap);
+        for (int q = 0; q < nb; ++q) {
+          const size_t o = (size_t)bin * m.binCap + q;
+          const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+          if (ddx * ddx + ddy * ddy + ddz * ddz > cut) continue;
+          const int j = m.binItems[o];
+          if (j != i) d5_pair_eval(m, in, classes, deltaT, i, j);
+        }
+      }
+  d5_rows_finish(m, in, i);
 }
 
 // particleIBM::wallHit for every wall slot (particleIBM.C:453-488, particleCloud.C:591-597)
@@ -1120,7 +1151,8 @@ k5_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restr
 
 // The sub-step loop of the ACTIVE instances of a split step (k5q_* above) as one persistent cooperative kernel: the active
 // list is a fraction of the cloud, so a small grid holds it and its grid-wide barriers are cheap next to the ~9 launches
-// per sub-step of the unfused chain.  Phases and their order are those of substep_launch_active.
+// per sub-step of the unfused chain.  Phases are those of substep_launch_active, except that every instance builds its own
+// contact row in one go (d5_row_direct) instead of the pair list + pair kernel + row finalisation: 5-6 barriers per sub-step.
 __global__ void __launch_bounds__(256)
 k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
           int doCyclic) {
@@ -1137,17 +1169,11 @@ k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __rest
         if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
       }
       grid.sync();
-      for (int t = tid; t < 3 * na; t += nth) d5_find_pairs(m, in, 3 * m.act[t / 3] + t % 3);
-      if (m.nWalls > 0)
-        for (int t = tid; t < na; t += nth) d5_walls(m, L, in, classes, dt, m.act[t]);
-      grid.sync();
-      {
-        const int np = min(*m.pairCount, m.pairCap);
-        for (int h = tid; h < np; h += nth) d5_pair_force(m, in, classes, dt, h);
+      for (int t = tid; t < na; t += nth) {  // every instance builds and finishes its own contact row (no pair list, no atomics)
+        const int i = m.act[t];
+        d5_row_direct(m, in, classes, dt, i);
+        if (m.nWalls > 0) d5_walls(m, L, in, classes, dt, i);
       }
-      grid.sync();
-      for (int t = tid; t < na; t += nth) d5_rows_finish(m, in, m.act[t]);
-      if (tid == 0) *m.pairCount = 0;
       if (copies) {
         grid.sync();
         for (int t = tid; t < na; t += nth) d5_merge(m, in, m.act[t]);
