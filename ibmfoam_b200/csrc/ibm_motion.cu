@@ -897,6 +897,18 @@ __device__ __forceinline__ bool bin_entry(int item, int& inst, int& mult) {
   return true;
 }
 
+// translations of the cyclic patches within `reach` of c (at most three: a corner); false = both sides of a direction
+__device__ __forceinline__ bool image_shifts(const MotionDev& m, D3 c, double reach, D3* sh, int& n) {
+  n = 0;
+  for (int s = 0; s < m.nCyc; ++s) {
+    const PatchDev& p = m.patches[m.cycPatch[s]];
+    if (!patch_in_reach(p, c, reach)) continue;
+    if (n == 3) return false;
+    sh[n++] = D3{p.shift[0], p.shift[1], p.shift[2]};
+  }
+  return true;
+}
+
 // images of the instances that may spawn a periodic copy this step, entered into the bins next to the real centres
 __global__ void k5q_ghosts(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -904,13 +916,8 @@ __global__ void k5q_ghosts(MotionDev m, InstanceSoA in, const ShapeClassDev* __r
   const D3 c = ld3(in.c, i);
   const double reach = classes[in.cls[i]].Rbound + split_S(m);
   D3 sh[3];
-  int n = 0;
-  for (int s = 0; s < m.nCyc; ++s) {
-    const PatchDev& p = m.patches[m.cycPatch[s]];
-    if (!patch_in_reach(p, c, reach)) continue;
-    if (n == 3) { atomicExch(m.noSplit, 1); return; }  // both sides of one direction in reach: a domain a few bodies wide
-    sh[n++] = D3{p.shift[0], p.shift[1], p.shift[2]};
-  }
+  int n;
+  if (!image_shifts(m, c, reach, sh, n)) { atomicExch(m.noSplit, 1); return; }  // both sides of one direction in reach: a domain a few bodies wide
   for (int sub = 1; sub < (1 << n); ++sub) {
     D3 g = c;
     int cnt = 0;
@@ -928,35 +935,66 @@ __global__ void k5q_ghosts(MotionDev m, InstanceSoA in, const ShapeClassDev* __r
   }
 }
 
-// one hop of the neighbourhood maximum: dst_i = scale * max(src_i, src_j over the bodies and images within Rij + 2 S) (+ floor)
+// maximum of src over the bodies and images within Rij + 2 S of position c (instance i itself and its own images excluded)
+__device__ __forceinline__ double nbr_scan_max(const MotionDev& m, const InstanceSoA& in, const ShapeClassDev* __restrict__ classes,
+                                               const double* __restrict__ src, D3 c, double di, int i, double S, double u) {
+  int bx, by, bz;
+  bin_of(m, c, bx, by, bz);
+  for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
+    for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
+      for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
+        const int bin = x + m.nbx * (y + m.nby * z);
+        const int nb = min(m.binCnt[bin], m.binCap);
+        for (int q = 0; q < nb; ++q) {
+          const size_t o = (size_t)bin * m.binCap + q;
+          int j, mult;
+          bin_entry(m.binItems[o], j, mult);
+          if (j == i) continue;
+          const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + 2.0 * S;
+          const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+          if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) u = fmax(u, src[j]);
+        }
+      }
+  return u;
+}
+
+// one hop of the neighbourhood maximum: dst_i = scale * max(src_i, src_j over the bodies and images near instance i AND near
+// the places where a copy of i may appear this step) + floor
 __global__ void k5q_nbrmax(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ src,
-                           double* __restrict__ dst, double scale, double floorB) {
+                           double* __restrict__ dst, double scale, double floorB, int doCyclic) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *m.nInst) return;
   double u = src[i];
   const double S = split_S(m);
   if (in.onMesh[i] != 0 && m.moving && 2.0 * S <= m.binEdge) {
     const D3 c = ld3(in.c, i);
-    const double di = dmax_of(classes[in.cls[i]]);
-    int bx, by, bz;
-    bin_of(m, c, bx, by, bz);
-    for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
-      for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
-        for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
-          const int bin = x + m.nbx * (y + m.nby * z);
-          const int nb = min(m.binCnt[bin], m.binCap);
-          for (int q = 0; q < nb; ++q) {
-            const size_t o = (size_t)bin * m.binCap + q;
-            int j, mult;
-            bin_entry(m.binItems[o], j, mult);
-            if (j == i) continue;
-            const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + 2.0 * S;
-            const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
-            if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) u = fmax(u, src[j]);
-          }
+    const ShapeClassDev* sc = classes + in.cls[i];
+    const double di = dmax_of(*sc);
+    u = nbr_scan_max(m, in, classes, src, c, di, i, S, u);
+    if (doCyclic) {
+      D3 sh[3];
+      int n;
+      if (image_shifts(m, c, sc->Rbound + S, sh, n))
+        for (int sub = 1; sub < (1 << n); ++sub) {
+          D3 g = c;
+          for (int q = 0; q < n; ++q)
+            if (sub & (1 << q)) g = g + sh[q];
+          u = nbr_scan_max(m, in, classes, src, g, di, i, S, u);
         }
+    }
   }
   dst[i] = scale * u + floorB;
+}
+
+// the instances of one index are one body (they exchange state every sub-step): they share the largest budget of the group
+__global__ void k5q_group_budget(MotionDev m) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m.nParticles) return;
+  const int head = m.idxHead[idx];
+  if (head < 0 || m.instNext[head] < 0) return;
+  double b = 0.0;
+  for (int p = head; p >= 0; p = m.instNext[p]) b = fmax(b, m.bud[p]);
+  for (int p = head; p >= 0; p = m.instNext[p]) m.bud[p] = b;
 }
 
 __global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
@@ -1577,8 +1615,9 @@ static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
   k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
   k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
   if (doCyclic) { k5q_ghosts<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses); c->nLaunch++; }
-  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0);
-  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge);
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0, doCyclic ? 1 : 0);
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge, doCyclic ? 1 : 0);
+  if (c->nParticles > 0) { k5q_group_budget<<<blocks_for(c->nParticles), 128, 0, st>>>(d); c->nLaunch++; }
   k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
   cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
   k5q_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
