@@ -853,7 +853,8 @@ __global__ void k5_append_link(MotionDev m, InstanceSoA in) {
 //     S   = safety * max_i s_i
 //     B_i = safety * max{ s_j : j within two hops of i in the graph of pairs closer than (Dmax_i + Dmax_j)/2 + 2 S }
 // (an elastic impulse hands a body at most its partners' momentum, so the neighbourhood maximum is what an instance can
-// plausibly reach; `safety` > sqrt(2) covers one exchange among equal bodies outright).  Instance i is ACTIVE when
+// plausibly reach; `safety` > sqrt(2) covers one exchange among equal bodies outright; the neighbourhood of i includes the
+// places where a copy of i may appear, and the instances of one index share the largest B of their group).  Instance i is ACTIVE when
 //   * its index has several instances (periodic copies share and exchange state, particleCloud.C:316-444, 525-554),
 //   * a wall or periodic patch is within its reach + B_i,
 //   * another body j is within (Dmax_i + Dmax_j)/2 + B_i + B_j (particleIBM.C:56-59 is the reference's own early-out at
