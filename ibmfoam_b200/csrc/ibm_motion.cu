@@ -1730,8 +1730,14 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       const ShapeClassDev* cls = c->dClasses;
       const double* dd = M->dDts;
       void* args[] = {&d, &c->Lg, &c->in, &cls, &dd, &nSub, &doCyclic};
-      IBM_CUDA(c, cudaLaunchCooperativeKernel((void*)k5a_fused, dim3(blocks), dim3(256), args, 0, c->stream));
-      c->nLaunch++;
+      if (cudaLaunchCooperativeKernel((void*)k5a_fused, dim3(blocks), dim3(256), args, 0, c->stream) == cudaSuccess) {
+        c->nLaunch++;
+      } else {
+        // refused on this device / in this context (co-residency cannot be guaranteed): the unfused chain, now and from here on
+        cudaGetLastError();
+        M->fusedActBlocks = 0;
+        for (int s = 0; s < nSub; ++s) substep_launch_active(c, s < 256 ? dts[s] : dts[255]);
+      }
     } else if (c->graphLoop5 && nSub <= 256) {
       // the launch sequence of one fluid step is fixed (same kernels, same grids, same pointers): capture it once
       // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each

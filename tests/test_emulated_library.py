@@ -22,8 +22,8 @@ def emu_lib():
     return build_emu.build()
 
 
-def _child(emu_lib, args, timeout):
-    env = dict(os.environ, IBM_TEST_EMU_LIB=emu_lib)
+def _child(emu_lib, args, timeout, **extra_env):
+    env = dict(os.environ, IBM_TEST_EMU_LIB=emu_lib, **extra_env)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", *args], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=timeout)
     tail = (r.stdout + r.stderr)[-2500:]
@@ -48,6 +48,14 @@ SUBSET = [
 
 def test_gpu_parity_subset_under_emulation(emu_lib):
     out = _child(emu_lib, SUBSET, timeout=1500)
+    assert " passed" in out and "failed" not in out
+
+
+def test_refused_cooperative_launch_falls_back_to_the_unfused_chain(emu_lib):
+    """fused_active_loop5 on a device / context that refuses cooperative launches: same results through the unfused chain"""
+    out = _child(emu_lib, ["tests/test_zzz_gpu_active_loop5.py::test_two_spheres_head_on[fused]",
+                           "tests/test_zzz_gpu_active_loop5.py::test_copy_created_after_a_rebound_next_to_a_resting_body[fused]"],
+                 timeout=1500, EMU_REFUSE_COOP="1")
     assert " passed" in out and "failed" not in out
 
 

@@ -117,6 +117,7 @@ inline cudaError_t coop_unpack(void (*kern)(P...), dim3 grid, dim3 block, void**
 }
 template <class... P>
 inline cudaError_t coop_launch_erased(void (*kern)(P...), dim3 grid, dim3 block, void** args, size_t smem, void* /*stream*/) {
+  if (std::getenv("EMU_REFUSE_COOP")) return cudaErrorNotSupported;  // tests of the product's handling of a refused launch
   return coop_unpack(kern, grid, block, args, smem, std::index_sequence_for<P...>{});
 }
 }  // namespace emu
