@@ -1065,19 +1065,10 @@ __global__ void k5a_bin_cand(MotionDev m, InstanceSoA in, const ShapeClassDev* _
   d5_bin(m, in, i);
   if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
 }
-__global__ void k5a_find_pairs(MotionDev m, InstanceSoA in) {
-  const int t3 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t3 / 3 >= *m.nAct) return;
-  d5_find_pairs(m, in, 3 * m.act[t3 / 3] + t3 % 3);
-}
-__global__ void k5a_rows_finish(MotionDev m, InstanceSoA in) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *m.pairCount = 0;  // pair_force is done: ready for the next sub-step
+__global__ void k5a_rows_direct(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
   IBM_ACT_I;
-  d5_rows_finish(m, in, i);
-}
-__global__ void k5a_walls(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double dt) {
-  IBM_ACT_I;
-  d5_walls(m, L, in, classes, dt, i);
+  d5_row_direct(m, in, classes, dt, i);  // pair search, pair evaluation and row finalisation of this instance
+  if (m.nWalls > 0) d5_walls(m, L, in, classes, dt, i);
 }
 __global__ void k5a_merge(MotionDev m, InstanceSoA in) {
   IBM_ACT_I;
@@ -1580,11 +1571,8 @@ static int substep_launch_active(ibm_ctx* c, double localDt) {
   double* Fw = d.Fw; double* Tw = d.Tw;
   if (c->cfg.moving) {
     k5a_bin_cand<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, doCyclic ? 1 : 0);
-    k5a_find_pairs<<<blocks_for(3 * cap), 128, 0, st>>>(d, c->in);
-    k5_pair_force<<<blocks_for(std::min(d.pairCap, 4 * c->nInst + 1024), 64), 64, 0, st>>>(d, c->in, c->dClasses, localDt);
-    k5a_rows_finish<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
-    c->nLaunch += 4;
-    if (d.nWalls > 0) { k5a_walls<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt); c->nLaunch++; }
+    k5a_rows_direct<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->Lg, c->in, c->dClasses, localDt);  // (+ wall hits)
+    c->nLaunch += 2;
     if (copiesPossible) {
       k5a_merge<<<blocks_for(cap, 64), 64, 0, st>>>(d, c->in);
       c->nLaunch++;
