@@ -136,3 +136,56 @@ def test_copy_created_after_a_rebound_next_to_a_resting_body(graph):
     assert oc.n_instances > 4
     assert gc.counter("loop5_fallbacks") == 0
     gc.close()
+
+
+@pytest.mark.parametrize("mode", ["split", "split_fused"])
+def test_two_ranks_replicated_loop5_with_the_split(mode):
+    """the multi-rank design runs loop 5 redundantly on every rank: with the split (and the persistent kernel) every rank
+    must still reproduce the SERIAL oracle bit for bit - the classification and the active list may be ordered differently
+    on each rank, the trajectories may not differ (ranks = host threads on one device, in-process transport)"""
+    import threading
+    from ibmfoam_b200.cloud import LocalGroup, slab_ranges
+    n_ranks = 2
+    case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
+    case.particles.v *= 8.0
+    ranges = slab_ranges(case.mesh.nz, n_ranks)
+    group = LocalGroup(n_ranks)
+    oc = OracleCloud(case)
+    rng = np.random.default_rng(0)
+    FTs = [rng.normal(0, 1e-3, (400, 6)) for _ in range(3)]
+    ref = []
+    for s in range(3):
+        oc.set_force_torque(FTs[s][:oc.n_instances])
+        oc.combine_forces()
+        oc.advance(case.dt)
+        ref.append(oc.state_arrays())
+    out, err = [None] * n_ranks, [None] * n_ranks
+
+    def rank(r):
+        try:
+            gc = ParticleCloud(case, slab=ranges[r], local_group=group.handle, rank=r)
+            gc.set_option("active_loop5", 1)
+            gc.set_option("fused_active_loop5", int(mode == "split_fused"))
+            for s in range(3):
+                gc.set_force_torque(FTs[s][:gc.nParticles()] / n_ranks)   # the all-reduce restores the serial value exactly
+                gc.combineForces()
+                gc.advance(case.dt)
+                sg = gc.state_arrays()
+                for k in ("index", "copy", "active", "onMesh", "center", "theta", "v", "omega"):
+                    assert np.array_equal(sg[k], ref[s][k]), (r, s, k)
+            out[r] = (gc.nParticles(), gc.counter("loop5_active_instances"))
+            gc.close()
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=rank, args=(r,)) for r in range(n_ranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    for e in err:
+        if e is not None:
+            raise e
+    assert out[0][0] == out[1][0] == oc.n_instances
+    assert 0 <= out[0][1] < out[0][0]          # the split was in force on the last step
+    group.close()
