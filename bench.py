@@ -400,7 +400,7 @@ def choose_variants(local_rank, timeout_s=300, workload="big512"):
         um = info.get("update_ms", {})
         if info.get("mark2_ok") and um.get("1", 1e30) < um.get("0", 0.0):
             mark = 1
-        fm, sm, am = info["forcing_ms"], info["stress_ms"], info.get("advance_ms", {})
+        fm, sm, am = info.get("forcing_ms", {}), info.get("stress_ms", {}), info.get("advance_ms", {})
         if info.get("kernels_ok"):
             if fm.get("5", 1e30) < fm.get(str(fv), 0.0):
                 fv = 5

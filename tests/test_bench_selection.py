@@ -1,0 +1,54 @@
+"""bench.py's choice among kernel generations / loop-5 modes / marking kernels from a probe result (CPU: the probe result
+is a cached JSON file, no child process, no GPU): a variant is used only if the probe showed parity AND a lower time."""
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture()
+def bench(tmp_path, monkeypatch):
+    import bench as b
+    monkeypatch.setattr(b, "PROBE_CACHE", str(tmp_path / "probe.json"))
+    return b
+
+
+def _choose(bench, info):
+    with open(bench.PROBE_CACHE, "w") as fh:
+        json.dump(info, fh)
+    fv, sv, split, mark, got = bench.choose_variants(0)
+    assert got.get("cached")
+    return fv, sv, split, mark
+
+
+BASE = {"ok": True, "kernels_ok": True, "mark2_ok": True, "loop5_split_ok": True, "loop5_fused_active_ok": True,
+        "forcing_ms": {"2": 13.0, "5": 3.0}, "stress_ms": {"4": 9.0, "5": 2.5},
+        "advance_ms": {"0": 11.0, "1": 8.0, "2": 5.0}, "update_ms": {"0": 3.0, "1": 2.0}}
+
+
+def test_everything_verified_and_faster_is_used(bench):
+    assert _choose(bench, BASE) == (5, 5, 2, 1)
+
+
+def test_slower_variants_are_not_used(bench):
+    info = dict(BASE, forcing_ms={"2": 13.0, "5": 14.0}, stress_ms={"4": 9.0, "5": 9.5}, advance_ms={"0": 11.0, "1": 12.0, "2": 11.5},
+                update_ms={"0": 3.0, "1": 3.1})
+    assert _choose(bench, info) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
+
+
+def test_parity_failures_veto_whatever_the_time(bench):
+    info = dict(BASE, kernels_ok=False, mark2_ok=False, loop5_split_ok=False, loop5_fused_active_ok=False)
+    assert _choose(bench, info) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
+    info = dict(BASE, loop5_fused_active_ok=False)                      # the persistent kernel failed or hung: plain split
+    assert _choose(bench, info) == (5, 5, 1, 1)
+    info = dict(BASE, loop5_split_ok=True, loop5_fused_active_ok=True, advance_ms={"0": 11.0, "1": 8.0})   # no timing of mode 2
+    assert _choose(bench, info)[2] == 1
+
+
+def test_failed_probe_keeps_the_defaults(bench):
+    assert _choose(bench, {"ok": False, "error": "timeout"}) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
+    assert _choose(bench, {"ok": True}) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
