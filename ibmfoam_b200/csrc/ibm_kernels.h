@@ -4,6 +4,21 @@
 
 namespace ibm {
 
+// kernel attributes (dynamic shared-memory size, carve-out) belong to the device a kernel will run on: call sites set them
+// once per (call site, current device), so a process that drives several devices gets them on each
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
+
 // ---- ibm_kernels_ref.cu (compiled with -fmad=false) ----
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,

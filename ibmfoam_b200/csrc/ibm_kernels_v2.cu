@@ -324,18 +324,17 @@ void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
   if (s.chunk == 256) {
     constexpr int CH = 256, HB = 11;
     const size_t sm = (size_t)(4 * CH + 1) * 6 * sizeof(double) + (size_t)((1 << HB) + 4 * CH + 2) * sizeof(int) + (1 << HB) * sizeof(unsigned short);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_forcing_v2<CH, HB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.first()) cudaFuncSetAttribute(k_forcing_v2<CH, HB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     k_forcing_v2<CH, HB, 2><<<totalChunks, CH, sm, st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S, dT, F);
   } else {
     constexpr int CH = 128, HB = 10;
     const size_t sm = (size_t)(4 * CH + 1) * 6 * sizeof(double) + (size_t)((1 << HB) + 4 * CH + 2) * sizeof(int) + (1 << HB) * sizeof(unsigned short);
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (attr2.first()) {
       // the gathers are served by L1: leave it as much of the unified 228 KB as the resident CTAs allow
       int pct = getenv("IBM_V2_CARVEOUT") ? atoi(getenv("IBM_V2_CARVEOUT")) : -1;
       if (pct >= 0) cudaFuncSetAttribute(k_forcing_v2<CH, HB, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      attr2 = true;
     }
     k_forcing_v2<CH, HB, 5><<<totalChunks, CH, sm, st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S, dT, F);
   }

@@ -483,16 +483,16 @@ static size_t s3_smem() { return (size_t)7 * SBOXCAP * sizeof(double); }
 void launch_forcing_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
                        const double* Uold, const double* S, double dT, double* F) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_forcing_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem()); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(k_forcing_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem());
   if (nInst > 0 && totalChunks > 0)
     k_forcing_v3<<<totalChunks, F3_THREADS, f3_smem(), st>>>(L, classes, in, nInst, s.order, s.chunkOff, shellCell, shellJK, U, Uold, S,
                                                               dT, F);
 }
 void launch_stress_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_stress_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem()); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(k_stress_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem());
   if (nInst > 0) k_stress_v3<<<nInst, S3_THREADS, s3_smem(), st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr);
 }
 

@@ -406,8 +406,8 @@ static size_t f4_smem() {
 void launch_forcing_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
                        const double* Uold, const double* S, double dT, double* F) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_forcing_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f4_smem()); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(k_forcing_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f4_smem());
   if (nInst > 0 && totalChunks > 0)
   {
     static int dbg = getenv("IBM_V4_DBG") ? atoi(getenv("IBM_V4_DBG")) : 0;  // profiling switch: 1 = skip staging, 2 = skip gathers
@@ -420,8 +420,8 @@ static size_t s4_smem() { return (size_t)7 * SBOX4 * sizeof(double) + sizeof(Tab
 
 void launch_stress_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_stress_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4_smem()); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(k_stress_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4_smem());
   if (nInst > 0)
     k_stress_v4<<<nInst, S4_THREADS, s4_smem(), st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, dFallback);
 }

@@ -149,6 +149,7 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : (a == cudaDevAttrCooperativeLaunch) ? 1 : 0; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)1; return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return cudaSuccess; }
