@@ -188,7 +188,7 @@ int ibm_sync(ibm_ctx* ctx);
 int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant); /* 0 = reference-order kernels, 1.. = tuned generations */
 /* diagnostic counters: "loop5_active_instances" (of the last ibm_advance with the quiet/active split, else -1), "loop5_fallbacks" */
 int ibm_get_counter(ibm_ctx* ctx, const char* name, long long* value);
-int ibm_set_option(ibm_ctx* ctx, const char* name, int value); /* "graph_loop5" (default 1): sub-step launch sequence replayed as a CUDA graph; "fused_loop5" (default 0): one persistent cooperative kernel; "active_loop5" (default 0): quiet / active split of a fluid step (same results; instances that cannot interact integrate all sub-steps in one kernel), "fused_active_loop5" (default 0): with the split, the active list's sub-steps in one persistent cooperative kernel, "active_loop5_safety_ppm" (default 2000000): displacement-budget factor */
+int ibm_set_option(ibm_ctx* ctx, const char* name, int value); /* "graph_loop5" (default 1): sub-step launch sequence replayed as a CUDA graph; "fused_loop5" (default 0): one persistent cooperative kernel; "active_loop5" (default 0): quiet / active split of a fluid step (same results; instances that cannot interact integrate all sub-steps in one kernel), "fused_active_loop5" (default 0): with the split, the active list's sub-steps in one persistent cooperative kernel, "active_loop5_safety_ppm" (default 2000000): displacement-budget factor; "mark_variant" (default 0): 1 = second marking kernel (same lists); "collision_model" (default 0): see ibm_set_real_option */
 
 /* EXTENSION without a counterpart in the reference (the reference names a soft-sphere model in
  * src/particleCloud/Make/files but ships none): ibm_set_option(ctx, "collision_model", 1) replaces the hard-sphere impulse of
