@@ -19,6 +19,10 @@ leg() {  # leg <name> <seconds> <command...>
 
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/gpu.txt" 2>&1
 
+# 0. secondary ceilings of this box: fp64 FMA / rsqrt rate, launch latency (stream, graph), grid-barrier latency, copy bandwidth
+[ -x tools/microbench/microbench ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/microbench/microbench tools/microbench/microbench.cu
+leg microbench 180 tools/microbench/microbench
+
 # 1. parity on hardware, file by file (no -x: every file reports; the blind files are the zz*/zzz* ones)
 for f in tests/test_gpu_forcing.py tests/test_gpu_marking.py tests/test_gpu_stress.py tests/test_gpu_motion.py \
          tests/test_gpu_multirank.py tests/test_gpu_zz_device_api.py tests/test_gpu_zz_reference_vectors.py tests/test_host_mirror.py \
