@@ -249,10 +249,10 @@ def run_probe(args):
     case = cases.assembly(n=64, n_particles=150, seed=3, moving=True, cyclic_without_walls=True)
     f = util.caller_fields(case)
     res = {}
-    for gen in (() if args.probe_fused else (None, 5)):
+    for gen in (() if args.probe_fused else (None, 5, 6)):   # 6 = forcing v5 keeping its stencils between field phases (stress: 5)
         gc = ParticleCloud(case)
         if gen is not None:
-            gc.set_kernel_variant(gen, gen)
+            gc.set_kernel_variant(gen, min(gen, 5))
         F = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
         FT = gc.integrateSurfaceStresses(f["p"], f["tau"])
         res[gen] = (F, FT)
@@ -262,6 +262,9 @@ def run_probe(args):
         eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
         out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
         out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
+        eF6 = float(np.max(np.abs(res[6][0] - res[None][0])) / np.max(np.abs(res[None][0])))
+        out["forcing6_rel_diff"] = eF6
+        out["forcing6_ok"] = bool(eF6 < 1e-11)
     if not args.probe_fused:
         # the second marking kernel must produce the very same shell lists and statuses
         ga, gb = ParticleCloud(case), ParticleCloud(case)
@@ -304,7 +307,7 @@ def run_probe(args):
         out["ok"] = True
         print(json.dumps(out))
         return
-    if not (out["kernels_ok"] or out["loop5_split_ok"] or out["mark2_ok"]):
+    if not (out["kernels_ok"] or out["forcing6_ok"] or out["loop5_split_ok"] or out["mark2_ok"]):
         print(json.dumps(out))
         return
     t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}, "update_ms": {}}
@@ -334,7 +337,7 @@ def run_probe(args):
     U, Uold, S, P, Tau = device_fields(case.mesh, dev)
     torch.cuda.synchronize()
     cloud = ParticleCloud(case, device=0)
-    for gen_f, gen_s in ((DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]), (5, 5)):
+    for gen_f, gen_s in ((DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]), (5, 5), (6, 5)):
         cloud.set_kernel_variant(gen_f, gen_s)
         for _ in range(2):
             cloud.forcing_device(U.data_ptr(), Uold.data_ptr(), S.data_ptr(), case.dt)
@@ -401,11 +404,12 @@ def choose_variants(local_rank, timeout_s=300, workload="big512"):
         if info.get("mark2_ok") and um.get("1", 1e30) < um.get("0", 0.0):
             mark = 1
         fm, sm, am = info.get("forcing_ms", {}), info.get("stress_ms", {}), info.get("advance_ms", {})
-        if info.get("kernels_ok"):
-            if fm.get("5", 1e30) < fm.get(str(fv), 0.0):
-                fv = 5
-            if sm.get("5", 1e30) < sm.get(str(sv), 0.0):
-                sv = 5
+        best_f = fm.get(str(fv), 0.0)
+        for gen, key in ((5, "kernels_ok"), (6, "forcing6_ok")):
+            if info.get(key) and fm.get(str(gen), 1e30) < best_f:
+                fv, best_f = gen, fm[str(gen)]
+        if info.get("kernels_ok") and sm.get("5", 1e30) < sm.get(str(sv), 0.0):
+            sv = 5
         best = am.get("0", 0.0)
         for mode, key in ((1, "loop5_split_ok"), (2, "loop5_fused_active_ok")):
             if info.get(key) and am.get(str(mode), 1e30) < best:
@@ -675,7 +679,7 @@ def main():
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": f"k_forcing_v{variants[0]}", "peak_kind": f"of {peak_kind}",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_forcing_v5<cached stencils>" if variants[0] == 6 else f"k_forcing_v{variants[0]}", "peak_kind": f"of {peak_kind}",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": forcing_ms, "n_touch_closed_form": n_touch,
                 "forcing_updates_per_s": updates_per_step / (forcing_ms * 1e-3) if forcing_ms > 0 else None}
     breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}

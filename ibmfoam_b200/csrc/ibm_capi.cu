@@ -323,7 +323,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
     else if (c->forcingVariant >= 5 && c->v5Forcing)
       launch_forcing_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
-                        c->dScal + 7);
+                        c->dScal + 7, c->forcingVariant >= 6);  // 6 = the same kernel with the stencils kept between field phases
     else if (c->forcingVariant >= 4 && c->v4Forcing)
       launch_forcing_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);

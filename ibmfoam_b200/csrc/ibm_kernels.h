@@ -89,7 +89,7 @@ void launch_stress_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
 #define V5_FORCING_BOX 2208
 void launch_forcing_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
-                       const double* S, double dT, double* F, int* dFallback);
+                       const double* S, double dT, double* F, int* dFallback, bool cacheStencils = false);
 void launch_stress_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 

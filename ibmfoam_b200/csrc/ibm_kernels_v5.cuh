@@ -145,6 +145,14 @@ __host__ __device__ __forceinline__ size_t f5_smem_bytes() {
 // ------------------------------------------------------------------------------------------------
 // K2/K3 v5: direct forcing (particleCloud.C:1158-1208, particleIBM.C:210-264, :520-539), one CTA per instance
 // ------------------------------------------------------------------------------------------------
+// CACHE (variant 6): of the five stencil evaluations per column only three are distinct points - the surface layer is
+// gathered for U_old and again for S, the outer layer for S and again for U.  With CACHE every thread keeps the stencil of
+// each of its (at most F5_COLS_PER_THREAD) columns in a thread-private array from one field phase to the next (surface:
+// U_old -> S, outer: S -> U; one slot per column, overwritten after its last use) and all three phases use the outer box,
+// so that a cached cell index stays valid.  Same arithmetic, same results; it trades 40 % of the stencil fp64 work for
+// 64 bytes of local-memory traffic per column and phase, and a slightly larger box in the U_old phase.
+#define F5_COLS_PER_THREAD ((F5_MAXCOL + F5_THREADS - 1) / F5_THREADS)
+template <bool CACHE>
 __global__ void __launch_bounds__(F5_THREADS, 2)
 k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
              const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
@@ -185,7 +193,7 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     const int n = min(F5_CELLS, nS - c0);
     // the first field of the chunk starts loading now: the box is free (every gather of the previous chunk finished
     // before its last barrier) and the copies fly while the column hash and the scatter weights are built
-    stage5_async(L, Bs, Uold, C, 3, box, F5_BOX);
+    stage5_async(L, CACHE ? Bo : Bs, Uold, C, 3, box, F5_BOX);
     __pipeline_commit();
     for (int t = threadIdx.x; t < F5_HASH; t += blockDim.x) hKey[t] = -1;
     if (threadIdx.x == 0) nCol = 0;
@@ -260,10 +268,11 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     }
 
     double ax = 0.0, ay = 0.0, az = 0.0;
+    St5 cache[CACHE ? F5_COLS_PER_THREAD : 1];  // (thread-private: lives in local memory, backed by L1 / L2)
 #pragma unroll 1
     for (int phase = 0; phase < 3; ++phase) {
       const double* fld = (phase == 0) ? Uold : (phase == 1 ? S : U);
-      const Box5& B = (phase == 0) ? Bs : Bo;
+      const Box5& B = (CACHE || phase != 0) ? Bo : Bs;
       const int pxy = B.px * B.by;
       if (phase > 0) {  // (phase 0 was issued at the top of the chunk)
         stage5_async(L, B, fld, C, 3, box, F5_BOX);
@@ -272,7 +281,8 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       __pipeline_wait_prior(0);
       __syncthreads();  // the three planes of this field are in shared memory
 
-      for (int s = threadIdx.x; s < ncol; s += blockDim.x) {
+      int it = 0;
+      for (int s = threadIdx.x; s < ncol; s += blockDim.x, ++it) {
         const int key = colKey[s];
         const bool deg = key == degenerateKey;
         const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
@@ -281,10 +291,36 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
         const int layO = deg ? 0 : (phase == 0 ? 0 : 2);
         const int layS = deg ? 0 : 1;
         St5 st;
+        {  // tS partial (first: in the S phase its cached stencil is read before the slot takes the outer one)
+          const V3 x = tab4_point(sc, tab, R, cx, cy, cz, layS, jq, kq);
+          if (phase == 2) {
+            const double rx = x.x - cx, ry = x.y - cy, rz = x.z - cz;
+            cv[3] = (vx + (wy * rz - wz * ry)) * rdT; cv[4] = (vy + (wz * rx - wx * rz)) * rdT; cv[5] = (vz + (wx * ry - wy * rx)) * rdT;
+          } else {
+            bool on;
+            if (CACHE && phase == 1) { st = cache[it]; on = st.self >= 0; }
+            else {
+              on = make_st5(L, idx, idy, idz, B, x, st);
+              if (CACHE) { if (!on) { st = St5(); st.self = -1; } cache[it] = st; }
+            }
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            if (on) {
+              g0 = gat5(st, box, B.px, pxy); g1 = gat5(st, box + F5_BOX, B.px, pxy); g2 = gat5(st, box + 2 * F5_BOX, B.px, pxy);
+            }
+            if (phase == 0) { cv[3] = -rdT * g0; cv[4] = -rdT * g1; cv[5] = -rdT * g2; }
+            else { cv[3] = g0; cv[4] = g1; cv[5] = g2; }
+          }
+        }
         {  // tO partial
           const V3 x = tab4_point(sc, tab, R, cx, cy, cz, layO, jq, kq);
+          bool on;
+          if (CACHE && phase == 2) { st = cache[it]; on = st.self >= 0; }
+          else {
+            on = make_st5(L, idx, idy, idz, B, x, st);
+            if (CACHE && phase == 1) { if (!on) { st = St5(); st.self = -1; } cache[it] = st; }
+          }
           double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-          if (make_st5(L, idx, idy, idz, B, x, st)) {
+          if (on) {
             g0 = gat5(st, box, B.px, pxy); g1 = gat5(st, box + F5_BOX, B.px, pxy); g2 = gat5(st, box + 2 * F5_BOX, B.px, pxy);
           }
           if (phase == 0) { cv[0] = -rdT * g0; cv[1] = -rdT * g1; cv[2] = -rdT * g2; }
@@ -294,20 +330,6 @@ k_forcing_v5(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
             const double rx = x.x - cx, ry = x.y - cy, rz = x.z - cz;
             const double u0 = vx + (wy * rz - wz * ry), u1 = vy + (wz * rx - wx * rz), u2 = vz + (wx * ry - wy * rx);
             cv[0] = (u0 - g0) * rdT; cv[1] = (u1 - g1) * rdT; cv[2] = (u2 - g2) * rdT;
-          }
-        }
-        {  // tS partial
-          const V3 x = tab4_point(sc, tab, R, cx, cy, cz, layS, jq, kq);
-          if (phase == 2) {
-            const double rx = x.x - cx, ry = x.y - cy, rz = x.z - cz;
-            cv[3] = (vx + (wy * rz - wz * ry)) * rdT; cv[4] = (vy + (wz * rx - wx * rz)) * rdT; cv[5] = (vz + (wx * ry - wy * rx)) * rdT;
-          } else {
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            if (make_st5(L, idx, idy, idz, B, x, st)) {
-              g0 = gat5(st, box, B.px, pxy); g1 = gat5(st, box + F5_BOX, B.px, pxy); g2 = gat5(st, box + 2 * F5_BOX, B.px, pxy);
-            }
-            if (phase == 0) { cv[3] = -rdT * g0; cv[4] = -rdT * g1; cv[5] = -rdT * g2; }
-            else { cv[3] = g0; cv[4] = g1; cv[5] = g2; }
           }
         }
       }

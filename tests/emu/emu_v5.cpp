@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE — runs the fifth-generation CUDA kernels (ibmfoam_b200/csrc/ibm_kernels_v5.cuh, the very source
 // nvcc compiles for sm_100a) under the CPU emulation of tools/cuda_emu, behind a small C surface for ctypes.
 // Built by tests/test_emu_v5.py:  g++ -O1 -ffp-contract=off -Itools/cuda_emu -Iibmfoam_b200/csrc -shared -fPIC
+#include <cstdlib>
 #include <cuda_runtime.h>  // tools/cuda_emu/cuda_runtime.h
 
 #include <vector>
@@ -75,7 +76,9 @@ int emu_forcing_v5(const int* n, const double* origin, const double* delta, int 
   int fallback = 0;
   const ShapeClassDev* classes = &hc.dev;
   emu::launch((unsigned)nInst, F5_THREADS, f5_smem_bytes(), [&]() {
-    k_forcing_v5(L, classes, in, nInst, order, shellCell, shellJK, U, Uold, S, dt, F, &fallback);
+    // EMU_V5_CACHE=1: the instantiation that keeps the stencils between field phases (kernel variant 6)
+    if (std::getenv("EMU_V5_CACHE")) k_forcing_v5<true>(L, classes, in, nInst, order, shellCell, shellJK, U, Uold, S, dt, F, &fallback);
+    else k_forcing_v5<false>(L, classes, in, nInst, order, shellCell, shellJK, U, Uold, S, dt, F, &fallback);
   });
   return fallback;
 }

@@ -25,7 +25,7 @@ def _choose(bench, info):
     return fv, sv, split, mark
 
 
-BASE = {"ok": True, "kernels_ok": True, "mark2_ok": True, "loop5_split_ok": True, "loop5_fused_active_ok": True,
+BASE = {"ok": True, "kernels_ok": True, "forcing6_ok": False, "mark2_ok": True, "loop5_split_ok": True, "loop5_fused_active_ok": True,
         "forcing_ms": {"2": 13.0, "5": 3.0}, "stress_ms": {"4": 9.0, "5": 2.5},
         "advance_ms": {"0": 11.0, "1": 8.0, "2": 5.0}, "update_ms": {"0": 3.0, "1": 2.0}}
 
@@ -52,3 +52,14 @@ def test_parity_failures_veto_whatever_the_time(bench):
 def test_failed_probe_keeps_the_defaults(bench):
     assert _choose(bench, {"ok": False, "error": "timeout"}) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
     assert _choose(bench, {"ok": True}) == (bench.DEFAULT_VARIANTS["forcing"], bench.DEFAULT_VARIANTS["stress"], 0, 0)
+
+
+def test_cached_stencil_forcing_is_chosen_only_when_verified_and_fastest(bench):
+    info = dict(BASE, forcing6_ok=True, forcing_ms={"2": 13.0, "5": 3.0, "6": 2.4})
+    assert _choose(bench, info)[0] == 6
+    info = dict(BASE, forcing6_ok=True, forcing_ms={"2": 13.0, "5": 3.0, "6": 3.4})
+    assert _choose(bench, info)[0] == 5
+    info = dict(BASE, forcing6_ok=False, forcing_ms={"2": 13.0, "5": 3.0, "6": 2.4})
+    assert _choose(bench, info)[0] == 5
+    info = dict(BASE, kernels_ok=False, forcing6_ok=True, forcing_ms={"2": 13.0, "5": 3.0, "6": 2.4})   # stress v5 disagreed, forcing 6 is fine
+    assert _choose(bench, info)[:2] == (6, bench.DEFAULT_VARIANTS["stress"])

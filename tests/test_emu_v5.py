@@ -149,14 +149,29 @@ FORCING_CASES["aligned"] = _aligned
 FORCING_CASES["thick_shell"] = _thick_shell
 
 
+@pytest.mark.parametrize("cache", [False, True])
 @pytest.mark.parametrize("name", sorted(FORCING_CASES))
-def test_forcing_v5_emulated(emu, name):
+def test_forcing_v5_emulated(emu, name, cache, monkeypatch):
+    """cache = the instantiation that keeps the stencils between the field phases (kernel variant 6)"""
+    if cache:
+        monkeypatch.setenv("EMU_V5_CACHE", "1")
+    else:
+        monkeypatch.delenv("EMU_V5_CACHE", raising=False)
     case = FORCING_CASES[name]()
     F, Fo, n_upd = _forcing(emu, case)
     assert n_upd > 0 and np.max(np.abs(Fo)) > 0
     assert np.array_equal(Fo.any(axis=1), F.any(axis=1)), "support of the forcing field"
     err = util.rel_err(F, Fo)
     assert err < 1e-12, err
+
+
+def test_forcing_with_cached_stencils_equals_recomputed_stencils_bit_for_bit(emu, monkeypatch):
+    case = FORCING_CASES["asm32"]()
+    monkeypatch.delenv("EMU_V5_CACHE", raising=False)
+    F1, _, _ = _forcing(emu, case, seed=1)
+    monkeypatch.setenv("EMU_V5_CACHE", "1")
+    F2, _, _ = _forcing(emu, case, seed=1)
+    assert np.array_equal(F1, F2)   # same stencils, same gathers, same sums: the cache only saves their recomputation
 
 
 def test_forcing_v5_is_order_independent(emu):

@@ -35,7 +35,8 @@ SUBSET = [
     "tests/test_gpu_marking.py::test_marking_bit_exact",
     "tests/test_gpu_zz_reference_vectors.py::test_marking_forcing_stress_against_reference_vectors",
     "tests/test_gpu_zz_reference_vectors.py::test_trajectories_against_reference_vectors[col8-graph]",
-    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned]",
+    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned-5]",
+    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned-6]",
     "tests/test_zzz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
     "tests/test_zzz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
     "tests/test_zzz_gpu_active_loop5.py::test_copy_created_after_a_rebound_next_to_a_resting_body[fused]",

@@ -46,12 +46,13 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("variant", [5, 6])   # 6 = the same kernel keeping the stencils between the field phases
 @pytest.mark.parametrize("name", list(CASES))
-def test_forcing_v5_parity(name):
+def test_forcing_v5_parity(name, variant):
     case = CASES[name]()
     f = util.caller_fields(case)
     oc, gc = OracleCloud(case), ParticleCloud(case)
-    gc.set_kernel_variant(forcing=5, stress=5)
+    gc.set_kernel_variant(forcing=variant, stress=5)
     Fo, n_upd = oc.forcing(f["U"], f["Uold"], f["S"], case.dt)
     Fg = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
     assert n_upd > 0 and np.max(np.abs(Fo)) > 0
@@ -77,10 +78,11 @@ def test_stress_v5_parity(name):
     gc.close()
 
 
-def test_v5_against_reference_vectors():
+@pytest.mark.parametrize("variant", [5, 6])
+def test_v5_against_reference_vectors(variant):
     case, g = gu.load_static("asm24_static")
     gc = ParticleCloud(case)
-    gc.set_kernel_variant(forcing=5, stress=5)
+    gc.set_kernel_variant(forcing=variant, stress=5)
     f = util.caller_fields(case)
     F = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
     assert util.rel_err(F, gu.dense_forcing(g, case.mesh.n_cells)) < 1e-12
@@ -88,6 +90,19 @@ def test_v5_against_reference_vectors():
     ref = g["stress_FT"]
     for sl in (slice(0, 3), slice(3, 6)):
         assert np.max(np.abs(FT[:, sl] - ref[:, sl])) / np.max(np.linalg.norm(ref[:, sl], axis=1)) < 1e-10
+    gc.close()
+
+
+def test_cached_stencils_give_the_same_field_bit_for_bit():
+    """variant 6 reuses the stencils variant 5 recomputes: identical gathers, identical sums (non-overlapping shells)"""
+    case = CASES["asm48"]() if "asm48" in CASES else cases.assembly(n=48, n_particles=40, seed=2, moving=True)
+    f = util.caller_fields(case)
+    gc = ParticleCloud(case)
+    out = {}
+    for variant in (5, 6):
+        gc.set_kernel_variant(forcing=variant, stress=5)
+        out[variant] = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
+    assert np.array_equal(out[5], out[6])
     gc.close()
 
 

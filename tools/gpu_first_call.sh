@@ -36,6 +36,7 @@ leg smoke 300 $PY -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
 leg bench_probe 900 $PY bench.py --steps 5 --warmup 3
 leg bench_defaults 600 $PY bench.py --steps 5 --warmup 3 --no-probe --no-cpu-baseline
 leg bench_v5 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --no-cpu-baseline --no-e2e
+leg bench_v6 600 $PY bench.py --steps 5 --warmup 3 --variant 6 --no-cpu-baseline --no-e2e
 leg bench_v5_split 600 $PY bench.py --steps 5 --warmup 3 --variant 5 --split 1 --no-cpu-baseline --no-e2e
 leg bench_v2_split 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 1 --no-cpu-baseline --no-e2e
 leg bench_v2_split_fused 600 $PY bench.py --steps 5 --warmup 3 --no-probe --split 2 --no-cpu-baseline --no-e2e
@@ -49,6 +50,8 @@ if command -v ncu > /dev/null; then
       --log-file "$OUT/launches_v5_split.csv" $PY bench.py --steps 1 --warmup 3 --variant 5 --split 1 --no-cpu-baseline --no-e2e
   leg ncu_forcing_v5 900 ncu --set full --clock-control none --import-source on -k regex:k_forcing_v5 -s 3 -c 1 \
       -o "$OUT/forcing_v5" -f $PY bench.py --steps 1 --warmup 3 --variant 5 --no-cpu-baseline --no-e2e
+  leg ncu_forcing_v6 900 ncu --set full --clock-control none --import-source on -k regex:k_forcing_v5 -s 3 -c 1 \
+      -o "$OUT/forcing_v6" -f $PY bench.py --steps 1 --warmup 3 --variant 6 --no-cpu-baseline --no-e2e
   leg ncu_stress_v5 900 ncu --set full --clock-control none --import-source on -k regex:k_stress_v5 -s 3 -c 1 \
       -o "$OUT/stress_v5" -f $PY bench.py --steps 1 --warmup 3 --variant 5 --no-cpu-baseline --no-e2e
 fi
