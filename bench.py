@@ -15,7 +15,8 @@ integral, force combination, the literal sub-step loop, re-marking).  One cell-p
   --impl reference   the reference arm: oracle/_ref when that library exists, else the port; all host cores
 
   kernel generations   forcing v2 + stress v4 are the measured defaults.  The fifth generation (one CTA per particle,
-                cp.async staging) was written after the round's GPU budget was spent, so it is only used when
+                cp.async staging; 6 = the same forcing kernel keeping its stencils between field phases), the
+                second marking kernel and the loop-5 split were written after the round's GPU budget was spent: each is only used when
                 a child process on this very box shows parity with the defaults AND a lower time, and a second check at
                 the full size agrees; config.kernel_generations records what ran and why (--no-probe: defaults only).
 
