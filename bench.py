@@ -753,7 +753,8 @@ def main():
                                                   "selected_by": ("--variant" if args.variant >= 0 else
                                                                   "library defaults" if args.no_probe else
                                                                   "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),
-                                                  "probe": probe_info, "full_size_check": verify}},
+                                                  "probe": probe_info, "full_size_check": verify,
+                                                  "retry_after": os.environ.get("IBM_BENCH_RETRY_AFTER")}},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["n_kernel_launches"], "clocks": clocks,
                 "parallelism": None if world == 1 else f"z-slabs x{world}: fields decomposed, particle state replicated, NCCL all-reduce of F/T partials and on-mesh counts",
                 "breakdown_ms_per_step": breakdown, "wall_ms_per_step": wall_ms / args.steps}
@@ -766,5 +767,31 @@ def main():
     watchdog.cancel()
 
 
+def _guarded_main():
+    """Single-GPU runs whose kernel generations were chosen by the probe get ONE retry with the measured defaults in a fresh
+    process (fresh CUDA context) if the run raises: a variant written without hardware must not cost the bench line.
+    Multi-rank runs are not retried (the ranks would have to agree on it)."""
+    argv = sys.argv[1:]
+    retryable = (int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
+                 and "--probe-fused" not in argv and "reference" not in argv)
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException as ex:  # noqa: BLE001
+        if not retryable:
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.write(f"bench.py: run with probed kernel generations failed ({type(ex).__name__}); retrying with the defaults\n")
+        sys.stderr.flush()
+        try:
+            os.remove(PROBE_CACHE)
+        except OSError:
+            pass
+        os.environ["IBM_BENCH_RETRY_AFTER"] = f"{type(ex).__name__}: {ex}"[:300]
+        os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + argv + ["--no-probe"])
+
+
 if __name__ == "__main__":
-    main()
+    _guarded_main()

@@ -63,3 +63,23 @@ def test_cached_stencil_forcing_is_chosen_only_when_verified_and_fastest(bench):
     assert _choose(bench, info)[0] == 5
     info = dict(BASE, kernels_ok=False, forcing6_ok=True, forcing_ms={"2": 13.0, "5": 3.0, "6": 2.4})   # stress v5 disagreed, forcing 6 is fine
     assert _choose(bench, info)[:2] == (6, bench.DEFAULT_VARIANTS["stress"])
+
+
+def test_failed_run_with_probed_variants_is_retried_once_with_the_defaults(bench, monkeypatch):
+    calls = {}
+    monkeypatch.setattr(bench, "main", lambda: (_ for _ in ()).throw(RuntimeError("kernel written without hardware failed")))
+    monkeypatch.setattr(bench.os, "execv", lambda exe, argv: calls.setdefault("argv", argv))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "5"])
+    bench._guarded_main()
+    assert calls["argv"][-1] == "--no-probe" and "--steps" in calls["argv"]
+    for argv in (["bench.py", "--no-probe"], ["bench.py", "--variant", "5"], ["bench.py", "--impl", "reference"]):
+        calls.clear()
+        monkeypatch.setattr(sys, "argv", argv)
+        with pytest.raises(RuntimeError):
+            bench._guarded_main()                 # nothing to fall back to: the error surfaces
+        assert not calls
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    with pytest.raises(RuntimeError):
+        bench._guarded_main()                     # multi-rank runs are not retried
