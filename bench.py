@@ -497,7 +497,21 @@ def main():
     from ibmfoam_b200 import capi
 
     # a diverged or dead-locked multi-rank run must not sit on the GPUs until an external limit kills it
-    watchdog = threading.Timer(float(os.environ.get("IBM_BENCH_WATCHDOG_S", "1200")), lambda: (sys.stderr.write("bench.py watchdog: run exceeded its time limit\n"), os._exit(17)))
+    def _expired():
+        sys.stderr.write("bench.py watchdog: run exceeded its time limit\n")
+        sys.stderr.flush()
+        if _retryable(sys.argv[1:]):
+            # a run with probed kernel generations that hangs gets the same single retry as one that raises
+            os.environ["IBM_BENCH_RETRY_AFTER"] = "watchdog: the run with probed kernel generations exceeded its time limit"
+            try:
+                os.remove(PROBE_CACHE)
+            except OSError:
+                pass
+            os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--no-probe"])
+        os._exit(17)
+
+    limit = float(os.environ.get("IBM_BENCH_WATCHDOG_S", "700" if _retryable(sys.argv[1:]) else "1200"))
+    watchdog = threading.Timer(limit, _expired)
     watchdog.daemon = True
     watchdog.start()
 
@@ -767,13 +781,17 @@ def main():
     watchdog.cancel()
 
 
+def _retryable(argv):
+    return (int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
+            and "--probe-fused" not in argv and "reference" not in argv)
+
+
 def _guarded_main():
     """Single-GPU runs whose kernel generations were chosen by the probe get ONE retry with the measured defaults in a fresh
     process (fresh CUDA context) if the run raises: a variant written without hardware must not cost the bench line.
     Multi-rank runs are not retried (the ranks would have to agree on it)."""
     argv = sys.argv[1:]
-    retryable = (int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
-                 and "--probe-fused" not in argv and "reference" not in argv)
+    retryable = _retryable(argv)
     try:
         main()
     except SystemExit:

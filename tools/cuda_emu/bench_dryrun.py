@@ -87,6 +87,7 @@ def main(argv):
     real_choose = bench.choose_variants
     bench.choose_variants = choose_variants
     bench.cpu_baseline_sample = lambda *a, **k: (1.0, 1, 1.0, 24)  # the CPU baseline leg is not what is being dry-run
+    os.environ.setdefault("IBM_BENCH_WATCHDOG_S", "7200")   # emulated kernels are slow; the watchdog's retry is for hardware runs
     sys.argv = ["bench.py"] + argv
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
