@@ -1182,52 +1182,56 @@ k5_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restr
 // The sub-step loop of the ACTIVE instances of a split step (k5q_* above) as one persistent cooperative kernel: the active
 // list is a fraction of the cloud, so a small grid holds it and its grid-wide barriers are cheap next to the ~9 launches
 // per sub-step of the unfused chain.  Phases are those of substep_launch_active, except that every instance builds its own
-// contact row in one go (d5_row_direct) instead of the pair list + pair kernel + row finalisation: 5-6 barriers per sub-step.
+// contact row in one go (d5_row_direct) instead of the pair list + pair kernel + row finalisation, and the bins of a sub-step
+// are filled in the last phase of the previous one: 3 barriers per sub-step without periodic patches, 4 with them.
 __global__ void __launch_bounds__(256)
 k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
           int doCyclic) {
   cg::grid_group grid = cg::this_grid();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const bool copies = m.nCyc > 0;
+  // Barriers per sub-step: rows | [merge + patch scan |] integrate | copy states + bins of the NEXT sub-step.  The bins only
+  // need the centres, which are final after the integration, so they share a phase with setPositions (which writes angles
+  // and velocities of copies only); the periodic-patch candidates need those velocities and go with the rows.
+  if (m.moving && nSub > 0) {
+    const int na = *m.nAct;
+    for (int t = tid; t < na; t += nth) d5_bin(m, in, m.act[t]);
+  }
+  grid.sync();
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
     if (m.moving) {
       const int na = *m.nAct;  // only the link phase changes it, and a grid barrier follows
-      for (int t = tid; t < na; t += nth) {
-        const int i = m.act[t];
-        d5_bin(m, in, i);
-        if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
-      }
-      grid.sync();
       for (int t = tid; t < na; t += nth) {  // every instance builds and finishes its own contact row (no pair list, no atomics)
         const int i = m.act[t];
         d5_row_direct(m, in, classes, dt, i);
         if (m.nWalls > 0) d5_walls(m, L, in, classes, dt, i);
+        if (doCyclic) d5_cyclic_candidates(m, in, classes, i);
       }
+      grid.sync();  // rows complete before anybody merges them or moves a centre
       if (copies) {
-        grid.sync();
         for (int t = tid; t < na; t += nth) d5_merge(m, in, m.act[t]);
+        if (doCyclic) d5_cyclic_detect(m, L, in, classes, tid, nth);
+        grid.sync();  // merged rows read the raw rows of other instances, which the integration clears
         if (doCyclic) {
-          d5_cyclic_detect(m, L, in, classes, tid, nth);
-          grid.sync();
           const int total = *m.hitCount;  // complete after the barrier, identical for every thread
           if (total > 0) {
             d5_append(m, in, tid, nth);
             grid.sync();
             if (tid == 0) d5_append_link(m, in);
+            grid.sync();
           } else if (tid == 0) {
-            *m.candCount = 0;
+            *m.candCount = 0;  // (the next candidates phase is two barriers away)
           }
         }
       }
-      grid.sync();
     }
     {
       const int na = *m.nAct;
       for (int t = tid; t < na; t += nth) {
         const int i = m.act[t];
         if (i >= *m.nInst) continue;
-        if (in.onMesh[i] != 0) {  // the bin this instance was put in (its centre has not changed since): ready for the next sub-step
+        if (in.onMesh[i] != 0) {  // the bin this instance was put in (its centre has not changed since)
           int bx, by, bz;
           bin_of(m, ld3(in.c, i), bx, by, bz);
           m.binCnt[bx + m.nbx * (by + m.nby * bz)] = 0;
@@ -1239,15 +1243,17 @@ k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __rest
         if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
       }
     }
-    grid.sync();
-    if (copies) {
+    grid.sync();  // every bin is empty and every centre final
+    {
       const int na = *m.nAct;
       for (int t = tid; t < na; t += nth) {
         const int i = m.act[t];
-        if (i < *m.nInst && m.idxHead[in.index[i]] == i) d5_set_positions(m, in, in.index[i]);  // the first instance of a group does the group
+        if (i >= *m.nInst) continue;
+        if (copies && m.idxHead[in.index[i]] == i) d5_set_positions(m, in, in.index[i]);  // the first instance of a group does the group
+        if (m.moving && s + 1 < nSub) d5_bin(m, in, i);                                    // bins of the next sub-step
       }
-      grid.sync();
     }
+    grid.sync();
   }
 }
 
