@@ -444,6 +444,10 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_MARK_VARIANT")) c->markVariant = std::atoi(e) == 1 ? 1 : 0;
+  if (const char* e = getenv("IBM_KERNEL_VARIANT")) {  // "f,s": forcing / stress kernel generation (like ibm_set_kernel_variant)
+    int f = 0, s2 = 0;
+    if (std::sscanf(e, "%d,%d", &f, &s2) == 2) { c->forcingVariant = f; c->stressVariant = s2; }
+  }
   if (!ctx_cuda_ok(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return IBM_E_CUDA; }
   LatticeDev& L = c->L;
   L.nx = mesh->nx; L.ny = mesh->ny; L.nz = mesh->nz;
@@ -1003,6 +1007,9 @@ int ibm_set_kernel_variant(ibm_ctx* c, int fv, int sv) {
 
 int ibm_get_counter(ibm_ctx* c, const char* name, long long* value) {
   if (!c || !name || !value) return IBM_E_ARG;
+  if (std::strcmp(name, "forcing_variant") == 0) { *value = c->forcingVariant; return IBM_OK; }
+  if (std::strcmp(name, "stress_variant") == 0) { *value = c->stressVariant; return IBM_OK; }
+  if (std::strcmp(name, "mark_variant") == 0) { *value = c->markVariant; return IBM_OK; }
   return motion_counter(c, name, value) ? IBM_OK : ctx_fail(c, IBM_E_ARG, std::string("ibm_get_counter: unknown counter ") + name);
 }
 

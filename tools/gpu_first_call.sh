@@ -30,6 +30,9 @@ for f in tests/test_gpu_forcing.py tests/test_gpu_marking.py tests/test_gpu_stre
          tests/test_zzz_gpu_mark_variant.py tests/test_zzz_gpu_soft_sphere.py tests/test_zzz_gpu_v5_kernels.py; do
   [ -f "$f" ] && leg "pytest_$(basename "$f" .py)" 900 $PY -m pytest "$f" -m gpu -q -p no:cacheprovider
 done
+# the slab-decomposed path with every blind variant forced through the developer switches
+leg pytest_multirank_blind_variants 900 env IBM_KERNEL_VARIANT=6,5 IBM_MARK_VARIANT=1 IBM_ACTIVE_LOOP5=1 IBM_FUSED_ACTIVE_LOOP5=1 \
+    $PY -m pytest tests/test_gpu_multirank.py -m gpu -q -p no:cacheprovider
 leg smoke 300 $PY -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
 
 # 2. the bench line the driver will take (probe decides), then each generation forced, then the loop-5 variants
