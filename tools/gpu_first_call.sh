@@ -59,4 +59,5 @@ if command -v ncu > /dev/null; then
       -o "$OUT/stress_v5" -f $PY bench.py --steps 1 --warmup 3 --variant 5 --no-cpu-baseline --no-e2e
 fi
 grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
+python tools/summarize_first_call.py "$OUT" > "$OUT/SUMMARY.md" 2>&1
 cat "$OUT/summary.txt"
