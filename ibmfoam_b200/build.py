@@ -22,6 +22,7 @@ UNITS = [
     ("ibm_kernels_v3.cu", []),
     ("ibm_kernels_v4.cu", []),
     ("ibm_kernels_v5.cu", []),
+    ("ibm_kernels_v7.cu", []),
     ("ibm_kernels_alpha.cu", ["-fmad=false"]),
     ("ibm_kernels_util.cu", []),
     ("ibm_motion.cu", ["-fmad=false"]),

@@ -268,7 +268,9 @@ int ctx_update(ibm_ctx* c) {
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
     c->nLaunch += 9;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 20, c->dScal + 13, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->hScal[20]) return ctx_fail(c, IBM_E_STATE, "staged kernel: a gather stencil left the staged region (internal error)");
     if (!c->hScal[4]) break;
     // shell buffer too small (every rank takes the same path only if it overflows itself: the collective above is
     // re-entered by all ranks or none, because the rerun repeats it) -> grow and redo
@@ -319,18 +321,22 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
   }
   if (c->cfg.coupled) {  // particleCloud.C:1186-1189
     ctx_tic(c, T_FORCING);
-    if (c->forcingVariant == 0)
+    const int fv = (c->forcingVariant >= 7 && !c->v7ok) ? 2 : c->forcingVariant;  // classes the staged kernel cannot take: direct gather
+    if (fv >= 7)
+      launch_forcing_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
+                        c->v7capF, c->dSlowList, c->dScal + 12, c->dScal + 13);
+    else if (fv == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
-    else if (c->forcingVariant >= 5 && c->v5Forcing)
+    else if (fv >= 5 && c->v5Forcing)
       launch_forcing_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
-                        c->dScal + 7, c->forcingVariant >= 6);  // 6 = the same kernel with the stencils kept between field phases
-    else if (c->forcingVariant >= 4 && c->v4Forcing)
+                        c->dScal + 7, fv >= 6);  // 6 = the same kernel with the stencils kept between field phases
+    else if (fv >= 4 && c->v4Forcing)
       launch_forcing_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
-    else if (c->forcingVariant >= 3)
+    else if (fv >= 3)
       launch_forcing_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
-    else if (c->forcingVariant == 2)
+    else if (fv == 2)
       launch_forcing_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
     else
@@ -379,15 +385,19 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   double pRefOverRho = c->cfg.pRef / c->cfg.rhoRef;  // particleCloud.C:1213-1215
   if (!c->dTcorr) IBM_CUDA(c, cudaMalloc(&c->dTcorr, (size_t)3 * c->cap * sizeof(double)));
   ctx_tic(c, T_STRESS);
-  if (c->stressVariant == 0)
+  const int sv = (c->stressVariant >= 7 && !c->v7ok) ? 4 : c->stressVariant;
+  if (sv >= 7)
+    launch_stress_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->v7capS,
+                     c->dSlowList, c->dScal + 12, c->dScal + 13);
+  else if (sv == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
-  else if (c->stressVariant >= 5 && c->v4Stress)  // same tables and box as the fourth generation
+  else if (sv >= 5 && c->v4Stress)  // same tables and box as the fourth generation
     launch_stress_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
-  else if (c->stressVariant >= 4 && c->v4Stress)
+  else if (sv >= 4 && c->v4Stress)
     launch_stress_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
-  else if (c->stressVariant >= 3)
+  else if (sv >= 3)
     launch_stress_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
-  else if (c->stressVariant == 2)
+  else if (sv == 2)
     launch_stress_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   else
     launch_stress_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
@@ -606,7 +616,13 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
       if (!tab || cells(s.Rbound + s.delta) > V5_FORCING_BOX) c->v5Forcing = false;
     }
   }
+  {
+    std::vector<ShapeClassDev> hc;
+    for (auto& h : c->classes) hc.push_back(h.dev);
+    c->v7ok = !hc.empty() && v7_plan(c->L, hc.data(), (int)hc.size(), c->nGeometricD, c->v7capF, c->v7capS);
+  }
   c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;
+  IBM_CUDA(c, cudaMalloc(&c->dSlowList, (size_t)c->cap * sizeof(int)));
   if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
   if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
   if (schedule_alloc(c->sched, c->cap)) return ctx_fail(c, IBM_E_CUDA, "schedule_alloc failed");
@@ -656,7 +672,7 @@ int ibm_destroy(ibm_ctx* c) {
   for (auto p : c->classPools) cudaFree(p);
   for (auto& ph : c->patches) { cudaFree(ph.dCf); cudaFree(ph.dSf); cudaFree(ph.dMagSf); }
   void* frees[] = {c->dLatToCell, c->dCellToLat, c->dClasses, c->dShellCell, c->dShellJK, c->dScal, c->dKeep, c->dKeepOff,
-                   c->dU, c->dUold, c->dS, c->dF, c->dP, c->dTau, c->dI, c->dStage, c->dTcorr};
+                   c->dU, c->dUold, c->dS, c->dF, c->dP, c->dTau, c->dI, c->dStage, c->dTcorr, c->dSlowList};
   for (void* p : frees) if (p) cudaFree(p);
   if (c->hScal) cudaFreeHost(c->hScal);
   if (c->hPinned) cudaFreeHost(c->hPinned);
@@ -1010,6 +1026,15 @@ int ibm_get_counter(ibm_ctx* c, const char* name, long long* value) {
   if (std::strcmp(name, "forcing_variant") == 0) { *value = c->forcingVariant; return IBM_OK; }
   if (std::strcmp(name, "stress_variant") == 0) { *value = c->stressVariant; return IBM_OK; }
   if (std::strcmp(name, "mark_variant") == 0) { *value = c->markVariant; return IBM_OK; }
+  if (std::strcmp(name, "v7_ok") == 0) { *value = c->v7ok ? 1 : 0; return IBM_OK; }
+  if (std::strcmp(name, "v7_slow_count") == 0) {  // instances the last staged launch handed to the direct-gather kernel
+    int n = 0;
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(&n, c->dScal + 12, sizeof(int), cudaMemcpyDeviceToHost);
+    *value = n;
+    return IBM_OK;
+  }
+  if (std::strcmp(name, "v7_smem_forcing") == 0) { *value = c->v7ok ? c->v7capF.planeCap * 8LL + c->v7capF.colCap * 48LL : 0; return IBM_OK; }
   return motion_counter(c, name, value) ? IBM_OK : ctx_fail(c, IBM_E_ARG, std::string("ibm_get_counter: unknown counter ") + name);
 }
 
@@ -1022,6 +1047,17 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_check_ppm") == 0) { c->activeCheckPpm = value; return IBM_OK; }
+  if (std::strcmp(name, "v7_col_cap") == 0) {  // test hook: shrink the column capacity of the staged forcing kernel (exercises the list path)
+    if (value < 0) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: v7_col_cap >= 0");
+    c->v7capF.colCap = std::min(c->v7capF.colCap, value);
+    return IBM_OK;
+  }
+  if (std::strcmp(name, "v7_plane_cap") == 0) {  // test hook: same for the staged planes (forcing and stress)
+    if (value < 0) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: v7_plane_cap >= 0");
+    c->v7capF.planeCap = std::min(c->v7capF.planeCap, value);
+    c->v7capS.planeCap = std::min(c->v7capS.planeCap, value);
+    return IBM_OK;
+  }
   if (std::strcmp(name, "mark_variant") == 0) {
     if (value != 0 && value != 1) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: mark_variant is 0 or 1");
     c->markVariant = value;

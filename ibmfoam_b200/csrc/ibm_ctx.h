@@ -80,7 +80,11 @@ struct ibm_ctx {
   bool v5Forcing = false;                    // ... and the fifth-generation forcing kernel (its box is a little smaller)
   // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging, 4 lean staging,
   // 5 one CTA per instance + cp.async staging (not yet measured on hardware: selected explicitly only)
-  int forcingVariant = 2, stressVariant = 4;
+  // 7 one CTA per instance, ball-row staging of combined fields (round-2 default where every class fits: v7ok)
+  int forcingVariant = 7, stressVariant = 7;
+  bool v7ok = false;              // every shape class can take the seventh-generation kernels (no ellipse, tables + region fit)
+  ibm::V7Caps v7capF{}, v7capS{};  // shared-memory capacities of their launches
+  int* dSlowList = nullptr;       // [cap] instances the staged kernel handed to the direct-gather kernel (device-side list)
   ibm::Schedule sched;
   int totalChunks = 0;
   int updatesPerCall = 0;

@@ -93,6 +93,23 @@ void launch_forcing_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
 void launch_stress_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 
+// ---- ibm_kernels_v7.cu: one CTA per instance, ball-row staging of combined fields, gathers from shared memory ----
+struct V7Caps { int planeCap, colCap, rowsCap, mapCap, nTcap, nkCap, elemCap; };  // shared-memory capacities of a launch (doubles / entries)
+// capacities from the shape classes (HOST copies of the class records); false = the fast path does not apply to this cloud
+bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress);
+void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                       const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard);
+void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
+                      const V7Caps& cap, int* slowList, int* slowCount, int* guard);
+// second-generation kernels over a device-side list of instances (the ones a staged kernel could not take)
+void launch_forcing_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,
+                            const int* listCount, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                            const double* S, double dT, double* F);
+void launch_stress_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,
+                           const int* listCount, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
+
 // ---- ibm_kernels_alpha.cu: fractional solid volume fraction (extension) ----
 void launch_solid_fraction(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, int nSub,
                            double* alpha);

@@ -66,7 +66,7 @@ __global__ void k_compact_instances(InstanceSoA s, InstanceSoA d, const int* __r
   if (i >= n || !keep[i]) return;
   int j = keepOff[i];
   d.index[j] = s.index[i]; d.copy[j] = s.copy[i]; d.active[j] = s.active[i]; d.onMesh[j] = s.onMesh[i]; d.cls[j] = s.cls[i];
-  d.nShell[j] = s.nShell[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i]; d.onLocal[j] = s.onLocal[i];
+  d.nShell[j] = s.nShell[i]; d.shellOff[j] = s.shellOff[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i]; d.onLocal[j] = s.onLocal[i];
   d.rho[j] = s.rho[i]; d.age[j] = s.age[i];
   for (int q = 0; q < 3; ++q) {
     d.c[q][j] = s.c[q][i]; d.th[q][j] = s.th[q][i]; d.v[q][j] = s.v[q][i]; d.om[q][j] = s.om[q][i];

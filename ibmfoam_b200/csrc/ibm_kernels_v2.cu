@@ -89,23 +89,18 @@ __device__ __forceinline__ int find_pos(const int* __restrict__ off, int n, int 
   return lo;
 }
 
-template <int CH, int HBITS, int MINB>
-__global__ void __launch_bounds__(CH, MINB)
-k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
-             const int* __restrict__ chunkOff, const int* __restrict__ shellCell, const int* __restrict__ shellJK,
-             const double* __restrict__ U, const double* __restrict__ Uold, const double* __restrict__ S, double dT,
-             double* __restrict__ F) {
+// one work item: shell cells [c0, c0 + CH) of instance b (block-wide; ends with a barrier so that the caller may loop)
+template <int CH, int HBITS>
+__device__ __forceinline__ void forcing_v2_item(const LatticeDev& L, const ShapeClassDev* __restrict__ classes, const InstanceSoA& in, int b, int c0,
+                                                const int* __restrict__ shellCell, const int* __restrict__ shellJK,
+                                                const double* __restrict__ U, const double* __restrict__ Uold, const double* __restrict__ S,
+                                                double dT, double* __restrict__ F, double* smem2) {
   constexpr int FHASH = 1 << HBITS, FMAXCOL = 4 * CH + 1;
-  extern __shared__ double smem2[];
   double (*colVal)[6] = (double (*)[6])smem2;             // [FMAXCOL][6]
   int* hKey = (int*)(smem2 + 6 * FMAXCOL);                // [FHASH]
   int* colKey = hKey + FHASH;                             // [FMAXCOL]
   unsigned short* hSlot = (unsigned short*)(colKey + FMAXCOL + 1);  // [FHASH]
   __shared__ int nCol;
-  const int item = blockIdx.x;
-  const int pos = find_pos(chunkOff, nInst, item);
-  const int b = order[pos];
-  const int c0 = (item - chunkOff[pos]) * CH;
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double* rot = in.rot + 9 * (size_t)b;
@@ -249,17 +244,48 @@ k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     atomicAdd(&F[C + myLat], Fy * rW);
     atomicAdd(&F[2 * C + myLat], Fz * rW);
   }
+  __syncthreads();
+}
+
+template <int CH, int HBITS, int MINB>
+__global__ void __launch_bounds__(CH, MINB)
+k_forcing_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+             const int* __restrict__ chunkOff, const int* __restrict__ shellCell, const int* __restrict__ shellJK,
+             const double* __restrict__ U, const double* __restrict__ Uold, const double* __restrict__ S, double dT,
+             double* __restrict__ F) {
+  extern __shared__ double smem2[];
+  const int item = blockIdx.x;
+  const int pos = find_pos(chunkOff, nInst, item);
+  forcing_v2_item<CH, HBITS>(L, classes, in, order[pos], (item - chunkOff[pos]) * CH, shellCell, shellJK, U, Uold, S, dT, F, smem2);
+}
+
+// the instances a staged kernel (ibm_kernels_v7.cu) could not take, from a device-side list: persistent blocks, every work
+// item of every listed instance (usually the list is empty and the kernel returns at once)
+template <int CH, int HBITS>
+__global__ void __launch_bounds__(CH, 4)
+k_forcing_v2_list(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, const int* __restrict__ list,
+                  const int* __restrict__ listCount, const int* __restrict__ shellCell, const int* __restrict__ shellJK,
+                  const double* __restrict__ U, const double* __restrict__ Uold, const double* __restrict__ S, double dT,
+                  double* __restrict__ F) {
+  extern __shared__ double smem2[];
+  const int n = *listCount;
+  // work items are enumerated (instance, chunk) with a fixed bound of chunks per instance so that no prefix sum is needed
+  for (int w = blockIdx.x;; w += gridDim.x) {
+    const int e = w / 64, ch = w % 64;
+    if (e >= n) break;
+    const int b = list[e];
+    const int ns = in.nShell[b];
+    for (int c0 = ch * CH; c0 < ns; c0 += 64 * CH) forcing_v2_item<CH, HBITS>(L, classes, in, b, c0, shellCell, shellJK, U, Uold, S, dT, F, smem2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4 v2: one CTA per instance in Morton order, one thread per surface point, fixed-tree reduction
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3)
-k_stress_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
-            const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr) {
+__device__ __forceinline__ void stress_v2_instance(const LatticeDev& L, const ShapeClassDev* __restrict__ classes, const InstanceSoA& in, int b,
+                                                   const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho,
+                                                   double rhoRef, double* __restrict__ Tcorr) {
   __shared__ double red[8][9];
-  if ((int)blockIdx.x >= nInst) return;
-  const int b = order[blockIdx.x];
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double* rot = in.rot + 9 * (size_t)b;
@@ -315,6 +341,34 @@ k_stress_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
     else if (q < 6) in.T[q - 3][b] = v;
     else if (Tcorr) Tcorr[3 * b + (q - 6)] = v;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_stress_v2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+            const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr) {
+  if ((int)blockIdx.x >= nInst) return;
+  stress_v2_instance(L, classes, in, order[blockIdx.x], P, Tau, pRefOverRho, rhoRef, Tcorr);
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_stress_v2_list(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, const int* __restrict__ list,
+                 const int* __restrict__ listCount, const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho,
+                 double rhoRef, double* __restrict__ Tcorr) {
+  const int n = *listCount;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) stress_v2_instance(L, classes, in, list[e], P, Tau, pRefOverRho, rhoRef, Tcorr);
+}
+
+void launch_forcing_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,
+                            const int* listCount, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                            const double* S, double dT, double* F) {
+  constexpr int CH = 128, HB = 10;
+  const size_t sm = (size_t)(4 * CH + 1) * 6 * sizeof(double) + (size_t)((1 << HB) + 4 * CH + 2) * sizeof(int) + (1 << HB) * sizeof(unsigned short);
+  k_forcing_v2_list<CH, HB><<<592, CH, sm, st>>>(L, classes, in, list, listCount, shellCell, shellJK, U, Uold, S, dT, F);
+}
+void launch_stress_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,
+                           const int* listCount, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr) {
+  k_stress_v2_list<<<444, 256, 0, st>>>(L, classes, in, list, listCount, P, Tau, pRefOverRho, rhoRef, Tcorr);
 }
 
 void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,

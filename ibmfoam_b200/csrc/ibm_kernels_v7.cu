@@ -1,0 +1,729 @@
+// Tuned kernels, seventh generation (loops 2+3 and 4): one CTA per particle instance, the cells the instance can
+// touch staged ONCE into shared memory as ball rows, gathers served from shared memory.
+//
+// What the round-1 profile of k_forcing_v2 said (profiles/r1_lines_forcing_v2_big512_final.txt): the kernel is bound by
+// the L1 tag stage — 105 scattered 8-byte loads per column, 14.6 distinct 128-byte lines per warp-level load, ~2 cycles per
+// line.  The staged generations v3-v5 lost because they staged the bounding CUBE (2.7x the cells that are needed) with
+// 8-byte LDGSTS (8 cycles each) and evaluated every stencil once per field.  Here:
+//
+//   * the region is the exact set of lattice rows (x-runs) that a layer of shape points can reach: for every (y,z) row
+//     of the bounding box, the x-range of cells whose box intersects the ball of the layer's radius ("own" range), widened
+//     by the six face neighbours (own range +-1, united with the own ranges of the four neighbouring rows) — a superset of
+//     every cell a 7-point gather stencil of that layer reads (particleShape.C:49-66), ~45 % of the cube;
+//   * the gather is linear (particleIBMTmp.C:26-50), so the three fields are combined WHILE staging into the three
+//     plane-sets the scatter needs (particleIBM.C:238-260, App. B #7):
+//         A = S - U/dt      on the reach of the outer layer    (gathered at outer points)
+//         B = S - Uold/dt   on the reach of the surface layer  (gathered at surface points)
+//         C =   - Uold/dt   on the reach of the inner layer    (gathered at inner points)
+//     so that  tO = v(x_O)/dt + g_O(A) + g_I(C),  tS = v(x_S)/dt + g_S(B):  63 shared-memory loads per column instead of
+//     105 global ones, and every global value is read exactly once per instance with coalesced row loads;
+//   * the radial point triples ("columns") referenced by the shell cells are de-duplicated through a direct map over
+//     (j,k) and a block scan (no hash, no atomics), each column's three stencils are evaluated once;
+//   * shape points come from the class's trig tables in shared memory with the reference's exact products
+//     (sphere.C:184-190): bit-identical coordinates, hence bit-identical point->cell membership.
+//
+// Instances the fast path cannot take (ellipses, classes whose tables or region exceed the shared-memory budget, a
+// region or column count above the launch's capacities) are appended to a device list and processed by the direct-gather
+// kernel of the second generation in the same stream (k_forcing_v2_list): same results, no host round trip.
+//
+// Arithmetic differs from the reference-order kernel only by re-association (<= 1e-12 relative, tested).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "ibm_kernels.h"
+
+namespace ibm {
+
+#define V7_THREADS 256
+#define V7_NWARP (V7_THREADS / 32)
+
+// shared-memory carve-up, identical on host and device
+struct V7Layout {
+  int planes, colVal, tab, rows, colKey, colSlot, elemRow, total;  // byte offsets
+};
+__host__ __device__ inline V7Layout v7_layout(const V7Caps& c) {
+  V7Layout l;
+  int o = 0;
+  l.planes = o; o += 8 * c.planeCap;
+  l.colVal = o; o += 8 * 6 * c.colCap;
+  l.tab = o; o += 8 * (2 * c.nTcap + 3 * c.nkCap);
+  l.rows = o; o += 4 * 10 * c.rowsCap;
+  l.colKey = o; o += 4 * c.colCap;
+  l.colSlot = o; o += 2 * ((c.mapCap + 3) & ~3);
+  l.elemRow = o; o += 2 * ((c.elemCap + 3) & ~3);
+  l.total = (o + 15) & ~15;
+  return l;
+}
+
+struct Tab7 {
+  const double *cosT, *sinT, *sinP, *cosP, *ck;
+};
+__device__ __forceinline__ Tab7 tab7_load(const ShapeClassDev& sc, double* w, const V7Caps& cap) {
+  for (int j = threadIdx.x; j < sc.nTheta; j += blockDim.x) { w[j] = sc.cosT[j]; w[cap.nTcap + j] = sc.sinT[j]; }
+  double* p = w + 2 * cap.nTcap;
+  for (int k = threadIdx.x; k < sc.nk; k += blockDim.x) { p[k] = sc.sinP[k]; p[cap.nkCap + k] = sc.cosP[k]; p[2 * cap.nkCap + k] = sc.ck[k]; }
+  return Tab7{w, w + cap.nTcap, p, p + cap.nkCap, p + 2 * cap.nkCap};
+}
+
+// mesh_[index(layer,j,k)] of a sphere / cylinder: the same roundings as the host template (sphere.C:184-190, cylinder.C:143-148)
+__device__ __forceinline__ V3 tab7_point(int kind, const Tab7& t, double r, double cx, double cy, double cz, int j, int k) {
+  if (kind == 0)
+    return V3{xadd(xmul(xmul(r, t.cosT[j]), t.sinP[k]), cx), xadd(xmul(xmul(r, t.sinT[j]), t.sinP[k]), cy), xadd(xmul(r, t.cosP[k]), cz)};
+  return V3{xadd(xmul(r, t.cosT[j]), cx), xadd(xmul(r, t.sinT[j]), cy), xadd(0.0, cz)};
+}
+
+struct Box7 {
+  int i0, j0, k0;  // (unclipped x origin is not needed) first row / plane of the box, clipped to the lattice
+  int by, bz;      // rows per plane, planes
+};
+
+// exclusive scan of one int per thread over the block (V7_THREADS threads); every thread gets the block total
+__device__ __forceinline__ int block_scan7(int v, int* wsum, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < V7_NWARP; ++w) {
+    const int s = wsum[w];
+    if (w < warp) base += s;
+    tot += s;
+  }
+  total = tot;
+  __syncthreads();  // wsum may be reused
+  return base + inc - v;
+}
+
+// own x-range of row (J,K) for a layer of radius rho around (cx,cy,cz): cells whose box intersects the closed ball
+__device__ __forceinline__ void own_range7(const LatticeDev& L, double cx, double cy, double cz, double rho, int J, int K, int& lo, int& hi) {
+  const double ylo = L.oy + J * L.dy, yhi = L.oy + (J + 1) * L.dy;
+  const double zlo = L.oz + (K + L.kz0) * L.dz, zhi = L.oz + (K + L.kz0 + 1) * L.dz;
+  const double ey = fmax(fmax(ylo - cy, cy - yhi), 0.0), ez = fmax(fmax(zlo - cz, cz - zhi), 0.0);
+  const double re = rho * (1.0 + 1e-9) + 1e-9 * L.dx;  // rounding of the point coordinates and of the cell search
+  const double h2 = re * re - ey * ey - ez * ez;
+  if (h2 < 0.0) { lo = 1; hi = 0; return; }
+  const double h = sqrt(h2);
+  lo = (int)floor((cx - h - L.ox) / L.dx);
+  hi = (int)floor((cx + h - L.ox) / L.dx);
+}
+
+struct St7 { int idx[7]; double c[7]; };  // self, +x, -x, +y, -y, +z, -z: index into a plane of the set, coefficient
+
+// 7-point gather stencil of point p in plane-set `set` (particleShape.C:49-91 with lambda = 1/2 folded in).  Returns
+// 0 = point off the local mesh (contributes nothing), 1 = ok, -1 = the staged region does not hold the stencil (bug guard).
+__device__ __forceinline__ int make_st7(const LatticeDev& L, double idx, double idy, double idz, const Box7& B, const int* __restrict__ rowBase,
+                                        const int* __restrict__ rowLo, const int* __restrict__ rowHi, const V3& p, St7& s) {
+  int I, J, K;
+  if (find_cell_fast(L, idx, idy, idz, p.x, p.y, p.z, I, J, K) < 0) return 0;
+  const int bj = J - B.j0, bk = K - B.k0;
+  if (bj < 0 || bj >= B.by || bk < 0 || bk >= B.bz) return -1;
+  const int row = bj + B.by * bk;
+  if (rowLo[row] > I - (I > 0) || rowHi[row] < I + (I + 1 < L.nx)) return -1;
+  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + L.kz0 + 0.5) * L.dz) - p.z;
+  const double hx = 0.5 * L.dx, hy = 0.5 * L.dy, hz = 0.5 * L.dz;
+  const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
+  double d2[6];
+  d2[0] = (ex + hx) * (ex + hx) + ey2 + ez2;
+  d2[1] = (ex - hx) * (ex - hx) + ey2 + ez2;
+  d2[2] = ex2 + (ey + hy) * (ey + hy) + ez2;
+  d2[3] = ex2 + (ey - hy) * (ey - hy) + ez2;
+  d2[4] = ex2 + ey2 + (ez + hz) * (ez + hz);
+  d2[5] = ex2 + ey2 + (ez - hz) * (ez - hz);
+  const bool ok[6] = {I + 1 < L.nx, I > 0, J + 1 < L.ny, J > 0, K + 1 < L.nz, K > 0};
+  const int self = rowBase[row] + I;
+  s.idx[0] = self;
+  s.idx[1] = ok[0] ? self + 1 : self;
+  s.idx[2] = ok[1] ? self - 1 : self;
+  // a neighbouring row inside the lattice is inside the box and holds column I (the touched range of a row contains the
+  // own ranges of its four neighbours); guard anyway
+  int bad = 0;
+  if (ok[2]) { if (bj + 1 >= B.by || I < rowLo[row + 1] || I > rowHi[row + 1]) bad = 1; else s.idx[3] = rowBase[row + 1] + I; } else s.idx[3] = self;
+  if (ok[3]) { if (bj < 1 || I < rowLo[row - 1] || I > rowHi[row - 1]) bad = 1; else s.idx[4] = rowBase[row - 1] + I; } else s.idx[4] = self;
+  if (ok[4]) { if (bk + 1 >= B.bz || I < rowLo[row + B.by] || I > rowHi[row + B.by]) bad = 1; else s.idx[5] = rowBase[row + B.by] + I; } else s.idx[5] = self;
+  if (ok[5]) { if (bk < 1 || I < rowLo[row - B.by] || I > rowHi[row - B.by]) bad = 1; else s.idx[6] = rowBase[row - B.by] + I; } else s.idx[6] = self;
+  if (bad) return -1;
+  double w[6], W = 0.0;
+  int hot = -1;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) {
+    w[d] = ok[d] ? rsqrt(d2[d]) : 0.0;
+    if (ok[d] && d2[d] < IBM_SMALL * IBM_SMALL && hot < 0) hot = d;  // particleShape.C:69-77
+    W += w[d];
+  }
+  if (hot >= 0) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) w[d] = (d == hot) ? 1.0 : 0.0;
+    W = 1.0;
+  }
+  const double hW = (W > 0.0) ? 0.5 / W : 0.0;
+  double cs = 0.0;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) { s.c[1 + d] = w[d] * hW; cs += s.c[1 + d]; }
+  s.c[0] = cs;
+  return 1;
+}
+
+__device__ __forceinline__ double gat7(const St7& s, const double* __restrict__ f) {
+  double v = s.c[0] * f[s.idx[0]];
+#pragma unroll
+  for (int d = 1; d < 7; ++d) v = fma(s.c[d], f[s.idx[d]], v);
+  return v;
+}
+
+// Region tables of one instance: for every set (0 = outer reach, 1 = surface reach, 2 = inner reach) and row of the box
+//   rowLo/rowHi = first / last staged column, rowBase = offset of column 0 in a plane of the set (index = rowBase + I).
+// Returns the cell counts per set in n[3].  nSets limits the work (the stress kernel needs set 1 only: pass first=1,last=1).
+__device__ __forceinline__ void build_region7(const LatticeDev& L, const Box7& B, double cx, double cy, double cz, const double* rho,
+                                              int first, int last, int rowsCap, int* rowBase, int* rowLo, int* rowHi, int* rowG, int* wsum, int* n) {
+  const int rows = B.by * B.bz;
+  const int t = threadIdx.x;
+  // own ranges (several rows per thread when the box has more rows than the block has threads)
+  for (int r = t; r < rows; r += V7_THREADS) {
+    const int bj = r % B.by, bk = r / B.by;
+    for (int s = first; s <= last; ++s) {
+      int lo, hi;
+      own_range7(L, cx, cy, cz, rho[s], B.j0 + bj, B.k0 + bk, lo, hi);
+      rowLo[s * rowsCap + r] = lo;
+      rowHi[s * rowsCap + r] = hi;
+    }
+  }
+  __syncthreads();
+  // touched ranges, in registers (rows <= 4 * V7_THREADS is guaranteed by the caller)
+  int tl[3][4], th[3][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = t + q * V7_THREADS;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { tl[s][q] = 1; th[s][q] = 0; }
+    if (r >= rows) continue;
+    const int bj = r % B.by, bk = r / B.by;
+    for (int s = first; s <= last; ++s) {
+      const int* lo = rowLo + s * rowsCap;
+      const int* hi = rowHi + s * rowsCap;
+      int a = 0x7fffffff, b = -0x7fffffff;
+      if (lo[r] <= hi[r]) { a = lo[r] - 1; b = hi[r] + 1; }
+      if (bj + 1 < B.by && lo[r + 1] <= hi[r + 1]) { a = min(a, lo[r + 1]); b = max(b, hi[r + 1]); }
+      if (bj > 0 && lo[r - 1] <= hi[r - 1]) { a = min(a, lo[r - 1]); b = max(b, hi[r - 1]); }
+      if (bk + 1 < B.bz && lo[r + B.by] <= hi[r + B.by]) { a = min(a, lo[r + B.by]); b = max(b, hi[r + B.by]); }
+      if (bk > 0 && lo[r - B.by] <= hi[r - B.by]) { a = min(a, lo[r - B.by]); b = max(b, hi[r - B.by]); }
+      a = max(a, 0); b = min(b, L.nx - 1);
+      if (a > b) { a = 1; b = 0; }
+      tl[s][q] = a; th[s][q] = b;
+    }
+  }
+  __syncthreads();
+  n[0] = n[1] = n[2] = 0;
+  for (int s = first; s <= last; ++s) {
+    int run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // rows q*V7_THREADS + t: scan each stripe, carry the stripe totals
+      if (q * V7_THREADS < rows) {  // (block-uniform)
+        const int len = max(th[s][q] - tl[s][q] + 1, 0);
+        int tot;
+        const int off = block_scan7(len, wsum, tot) + run;
+        const int r = t + q * V7_THREADS;
+        if (r < rows) {
+          rowLo[s * rowsCap + r] = tl[s][q];
+          rowHi[s * rowsCap + r] = th[s][q];
+          rowBase[s * rowsCap + r] = off - tl[s][q];
+        }
+        run += tot;
+      }
+    }
+    n[s] = run;
+  }
+  // global offset of column 0 of every row (lattice index = rowG + I)
+  for (int r = t; r < rows; r += V7_THREADS) {
+    const int bj = r % B.by, bk = r / B.by;
+    rowG[r] = L.nx * ((B.j0 + bj) + L.ny * (B.k0 + bk));
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, double cy, double cz, double reach, Box7& B) {
+  const int j0 = (int)floor((cy - reach - L.oy) / L.dy) - 1, j1 = (int)floor((cy + reach - L.oy) / L.dy) + 1;
+  const int k0 = (int)floor((cz - reach - L.oz) / L.dz) - 1 - L.kz0, k1 = (int)floor((cz + reach - L.oz) / L.dz) + 1 - L.kz0;
+  B.i0 = 0;
+  B.j0 = max(j0, 0); B.k0 = max(k0, 0);
+  B.by = min(j1, L.ny - 1) - B.j0 + 1;
+  B.bz = min(k1, L.nz - 1) - B.k0 + 1;
+  return B.by > 0 && B.bz > 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2/K3 v7: direct forcing, one CTA per instance
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(V7_THREADS, 2)
+k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+             const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
+             const double* __restrict__ Uold, const double* __restrict__ S, double dT, double* __restrict__ F, V7Caps cap,
+             int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guard) {
+  extern __shared__ double smem7[];
+  __shared__ int wsum[V7_NWARP];
+  if ((int)blockIdx.x >= nInst) return;
+  const int b = order[blockIdx.x];
+  const int nShell = in.nShell[b];
+  if (in.onLocal[b] == 0 || nShell <= 0) return;
+  const ShapeClassDev sc = classes[in.cls[b]];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  const V7Layout lay = v7_layout(cap);
+  char* base = (char*)smem7;
+  double* planes = (double*)(base + lay.planes);
+  double* colVal = (double*)(base + lay.colVal);
+  double* tabD = (double*)(base + lay.tab);
+  int* rowBase = (int*)(base + lay.rows);
+  int* rowLo = rowBase + 3 * cap.rowsCap;
+  int* rowHi = rowLo + 3 * cap.rowsCap;
+  int* rowG = rowHi + 3 * cap.rowsCap;
+  int* colKey = (int*)(base + lay.colKey);
+  unsigned short* colSlot = (unsigned short*)(base + lay.colSlot);
+  unsigned short* elemRow = (unsigned short*)(base + lay.elemRow);
+
+  const int nT = sc.nTheta, nk = sc.nk;
+  const int nMap = nT * nk + 1;  // last key: App. B #3, bins with k == nk-1 reference point 0 twelve times
+  const double R = sc.d / 2.0;
+  const double rL[3] = {xadd(R, -1 * sc.delta), xadd(R, 0.0), xadd(R, sc.delta)};  // R + delta[i]  (sphere.C:167,173)
+  const double rho[3] = {rL[2], rL[1], rL[0]};                                      // set 0 = outer reach ... set 2 = inner reach
+  Box7 B;
+  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && nMap <= cap.mapCap && box7_around(L, cx, cy, cz, rho[0], B);
+  if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= 4 * V7_THREADS;
+  if (!fits) {
+    if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
+    return;
+  }
+  const Tab7 tab = tab7_load(sc, tabD, cap);
+  for (int m = threadIdx.x; m < nMap; m += V7_THREADS) colSlot[m] = 0;
+  int nS[3];
+  build_region7(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
+  const int nA = nS[0], nB = nS[1], nC = nS[2];
+  const int off = in.shellOff[b];
+
+  // ---- columns referenced by the shell cells: mark, then compact ----
+  for (int t = threadIdx.x; t < nShell; t += V7_THREADS) {
+    const int pk = shellJK[off + t];
+    const int j = pk & 0xffff, k = pk >> 16;
+    if (nk != 1 && k == nk - 1) { colSlot[nMap - 1] = 1; continue; }
+    const int jp1 = (j + 1) % nT, k1 = (nk != 1) ? k + 1 : k;
+    colSlot[j + nT * k] = 1; colSlot[jp1 + nT * k] = 1; colSlot[j + nT * k1] = 1; colSlot[jp1 + nT * k1] = 1;
+  }
+  __syncthreads();
+  int nCol = 0;
+  {
+    const int per = (nMap + V7_THREADS - 1) / V7_THREADS;
+    const int m0 = threadIdx.x * per, m1 = min(m0 + per, nMap);
+    int cnt = 0;
+    for (int m = m0; m < m1; ++m) cnt += colSlot[m];
+    int slot = block_scan7(cnt, wsum, nCol);
+    if (nCol <= cap.colCap)
+      for (int m = m0; m < m1; ++m)
+        if (colSlot[m]) { colKey[slot] = m; colSlot[m] = (unsigned short)slot; ++slot; }
+  }
+  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nCol > cap.colCap || nCol > 65535) {
+#ifdef IBM_V7_DEBUG
+    if (threadIdx.x == 0) printf("v7 slow: b=%d nA=%d nB=%d nC=%d planeCap=%d elemCap=%d nCol=%d colCap=%d nShell=%d\n", b, nA, nB, nC, cap.planeCap, cap.elemCap, nCol, cap.colCap, nShell);
+#endif
+    if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
+    return;
+  }
+  // elemRow: row of every element of set 0 (the staging loop runs over the elements of the widest set)
+  {
+    const int rows = B.by * B.bz;
+    for (int r = threadIdx.x; r < rows; r += V7_THREADS) {
+      const int lo = rowLo[r], hi = rowHi[r], o = rowBase[r] + lo;
+      for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage: every needed cell value read once, combined on the way ----
+  const size_t C = (size_t)L.nCells;
+  const double rdT = 1.0 / dT;
+  double* pA = planes;
+  double* pB = planes + 3 * nA;
+  double* pC = pB + 3 * nB;
+  const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
+  const int* loC = rowLo + 2 * cap.rowsCap; const int* hiC = rowHi + 2 * cap.rowsCap; const int* baseC = rowBase + 2 * cap.rowsCap;
+  for (int a = threadIdx.x; a < nA; a += V7_THREADS) {
+    const int row = elemRow[a];
+    const int I = a - rowBase[row];
+    const size_t g = (size_t)(rowG[row] + I);
+    const double s0 = __ldg(S + g), s1 = __ldg(S + C + g), s2 = __ldg(S + 2 * C + g);
+    const double u0 = __ldg(U + g), u1 = __ldg(U + C + g), u2 = __ldg(U + 2 * C + g);
+    const bool inB = I >= loB[row] && I <= hiB[row];
+    double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+    if (inB) { o0 = __ldg(Uold + g); o1 = __ldg(Uold + C + g); o2 = __ldg(Uold + 2 * C + g); }
+    pA[a] = fma(-rdT, u0, s0); pA[nA + a] = fma(-rdT, u1, s1); pA[2 * nA + a] = fma(-rdT, u2, s2);
+    if (inB) {
+      const int ib = baseB[row] + I;
+      pB[ib] = fma(-rdT, o0, s0); pB[nB + ib] = fma(-rdT, o1, s1); pB[2 * nB + ib] = fma(-rdT, o2, s2);
+      if (I >= loC[row] && I <= hiC[row]) {
+        const int ic = baseC[row] + I;
+        pC[ic] = -rdT * o0; pC[nC + ic] = -rdT * o1; pC[2 * nC + ic] = -rdT * o2;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- one thread per distinct column: three stencils, 63 shared-memory loads ----
+  const V3 vp{in.v[0][b], in.v[1][b], in.v[2][b]}, om{in.om[0][b], in.om[1][b], in.om[2][b]};
+  const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
+  int bad = 0;
+  for (int s = threadIdx.x; s < nCol; s += V7_THREADS) {
+    const int key = colKey[s];
+    const bool deg = key == nMap - 1;
+    const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
+    // (a degenerate bin uses point 0 = the inner point of (0,0) for all three roles, particleShape.C:148)
+    const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
+    const V3 xS = deg ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
+    const V3 xO = deg ? xI : tab7_point(sc.kind, tab, rL[2], cx, cy, cz, jq, kq);
+    double tO[3] = {0, 0, 0}, tS[3] = {0, 0, 0};
+    St7 st;
+    int r = make_st7(L, idx, idy, idz, B, baseC, loC, hiC, xI, st);
+    if (r > 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tO[q] = gat7(st, pC + q * nC);
+    }
+    bad |= r < 0;
+    r = make_st7(L, idx, idy, idz, B, rowBase, rowLo, rowHi, xO, st);
+    if (r > 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tO[q] += gat7(st, pA + q * nA);
+    }
+    bad |= r < 0;
+    {
+      const double rx = xO.x - cx, ry = xO.y - cy, rz = xO.z - cz;
+      tO[0] = fma(vp.x + (om.y * rz - om.z * ry), rdT, tO[0]);
+      tO[1] = fma(vp.y + (om.z * rx - om.x * rz), rdT, tO[1]);
+      tO[2] = fma(vp.z + (om.x * ry - om.y * rx), rdT, tO[2]);
+    }
+    r = make_st7(L, idx, idy, idz, B, baseB, loB, hiB, xS, st);
+    if (r > 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tS[q] = gat7(st, pB + q * nB);
+    }
+    bad |= r < 0;
+    {
+      const double rx = xS.x - cx, ry = xS.y - cy, rz = xS.z - cz;
+      tS[0] = fma(vp.x + (om.y * rz - om.z * ry), rdT, tS[0]);
+      tS[1] = fma(vp.y + (om.z * rx - om.x * rz), rdT, tS[1]);
+      tS[2] = fma(vp.z + (om.x * ry - om.y * rx), rdT, tS[2]);
+    }
+    double* cv = colVal + 6 * s;
+    cv[0] = tO[0]; cv[1] = tO[1]; cv[2] = tO[2]; cv[3] = tS[0]; cv[4] = tS[1]; cv[5] = tS[2];
+  }
+  if (bad) atomicExch(guard, 1);
+  __syncthreads();
+
+  // ---- one thread per shell cell: F_i = sum_q (wI_q tO_q + wS_q tS_q)/W   (particleShape.C:113-131, particleIBM.C:230-263) ----
+  for (int t = threadIdx.x; t < nShell; t += V7_THREADS) {
+    const int lat = shellCell[off + t];
+    const int pk = shellJK[off + t];
+    const int j = pk & 0xffff, k = pk >> 16;
+    const bool degBin = nk != 1 && k == nk - 1;
+    const int jp1 = (j + 1) % nT, k1 = (nk != 1) ? k + 1 : k;
+    const int jj[4] = {j, jp1, j, jp1}, kk[4] = {k, k, k1, k1};
+    const int I = lat % L.nx, J = (lat / L.nx) % L.ny, K = lat / (L.nx * L.ny);
+    const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
+    double wI[4], wS[4];
+    int slot[4];
+    int first = -1, firstS = -1;  // one-hot rule of particleShape.C:121-127: first q (0..7) within SMALL wins; q < 4 are inner points
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int jq = degBin ? 0 : jj[q], kq = degBin ? 0 : kk[q];
+      slot[q] = colSlot[degBin ? nMap - 1 : jq + nT * kq];
+      const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
+      const V3 xS = degBin ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
+      const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
+      const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
+      wI[q] = rsqrt(dI2);
+      wS[q] = rsqrt(dS2);
+      if (dI2 < IBM_SMALL * IBM_SMALL && first < 0) first = q;
+      if (dS2 < IBM_SMALL * IBM_SMALL && firstS < 0) firstS = 4 + q;
+    }
+    if (first < 0) first = firstS;
+    if (first >= 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { wI[q] = (first == q) ? 1.0 : 0.0; wS[q] = (first == 4 + q) ? 1.0 : 0.0; }
+    }
+    double Fx = 0.0, Fy = 0.0, Fz = 0.0, W = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      W += wI[q] + wS[q];
+      const double* cv = colVal + 6 * slot[q];
+      Fx = fma(wI[q], cv[0], fma(wS[q], cv[3], Fx));
+      Fy = fma(wI[q], cv[1], fma(wS[q], cv[4], Fy));
+      Fz = fma(wI[q], cv[2], fma(wS[q], cv[5], Fz));
+    }
+    const double rW = 1.0 / W;
+    atomicAdd(&F[lat], Fx * rW);
+    atomicAdd(&F[C + lat], Fy * rW);
+    atomicAdd(&F[2 * C + lat], Fz * rW);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 v7: surface-stress integral (particleIBM.C:541-581), one CTA per instance: p and the six devRhoReff components staged
+// on the reach of the surface layer only (the round-1 kernel staged the solid 11^3 box: 3.6x the bytes that are needed)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(V7_THREADS, 3)
+k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+            const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
+            V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guard) {
+  extern __shared__ double smem7[];
+  __shared__ int wsum[V7_NWARP];
+  __shared__ double red[V7_NWARP][9];
+  if ((int)blockIdx.x >= nInst) return;
+  const int b = order[blockIdx.x];
+  const ShapeClassDev sc = classes[in.cls[b]];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  const bool on = in.onLocal[b] != 0;
+  const V7Layout lay = v7_layout(cap);
+  char* base = (char*)smem7;
+  double* planes = (double*)(base + lay.planes);
+  double* tabD = (double*)(base + lay.tab);
+  int* rowBase = (int*)(base + lay.rows);
+  int* rowLo = rowBase + 3 * cap.rowsCap;
+  int* rowHi = rowLo + 3 * cap.rowsCap;
+  int* rowG = rowHi + 3 * cap.rowsCap;
+  unsigned short* elemRow = (unsigned short*)(base + lay.elemRow);
+  const int nT = sc.nTheta, nk = sc.nk;
+  const double R = sc.d / 2.0;
+  const double rho[3] = {0.0, xadd(R, 0.0), 0.0};
+  Box7 B;
+  B.by = B.bz = 0;
+  // Instances without local points (other slabs' instances on a multi-GPU run) do no work but MUST still write zero
+  // partials below: their F/T slots hold last step's combined totals, and the cross-rank sum adds whatever is in them.
+  bool work = on;
+  if (work) {
+    bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[1], B);
+    if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= 4 * V7_THREADS;
+    if (!fits) {
+      if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
+      return;  // the list kernel writes this instance's F/T
+    }
+  }
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (work) {
+    const Tab7 tab = tab7_load(sc, tabD, cap);
+    int nS[3];
+    build_region7(L, B, cx, cy, cz, rho, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);
+    const int nB = nS[1];
+    const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
+    if (7 * nB > cap.planeCap || nB > cap.elemCap) {
+      if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
+      return;
+    }
+    {
+      const int rows = B.by * B.bz;
+      for (int r = threadIdx.x; r < rows; r += V7_THREADS) {
+        const int lo = loB[r], hi = hiB[r], o = baseB[r] + lo;
+        for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
+      }
+    }
+    __syncthreads();
+    const size_t C = (size_t)L.nCells;
+    for (int a = threadIdx.x; a < nB; a += V7_THREADS) {
+      const int row = elemRow[a];
+      const int I = a - baseB[row];
+      const size_t g = (size_t)(rowG[row] + I);
+      double v[7];
+      v[0] = __ldg(P + g);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) v[1 + q] = __ldg(Tau + q * C + g);
+#pragma unroll
+      for (int q = 0; q < 7; ++q) planes[q * nB + a] = v[q];
+    }
+    __syncthreads();
+    double rot[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) rot[q] = in.rot[9 * (size_t)b + q];
+    const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
+    const double sfScale = (sc.kind == 0) ? (R * R) * sc.dTheta : R * sc.dTheta * sc.l;
+    const int nSurf = nT * nk;
+    int bad = 0;
+    for (int s = threadIdx.x; s < nSurf; s += V7_THREADS) {
+      const int i = s / nk, k = s - i * nk;
+      const int i2 = i + nT * k;
+      const V3 pt = tab7_point(sc.kind, tab, rho[1], cx, cy, cz, i, k);
+      double tau[6] = {0, 0, 0, 0, 0, 0}, pp = 0.0;
+      St7 st;
+      const int r = make_st7(L, idx, idy, idz, B, baseB, loB, hiB, pt, st);
+      bad |= r < 0;
+      if (r > 0) {
+#pragma unroll
+        for (int cmp = 0; cmp < 6; ++cmp) tau[cmp] = gat7(st, planes + (1 + cmp) * nB) * rhoRef;
+        pp = (gat7(st, planes) - 2.0 * st.c[0] * pRefOverRho) * rhoRef;
+      }
+      // App. B #5: lever arm as coded, mesh_[index2(i,k)] read through index(i,j,k)
+      const int lay2 = i2 % 3, j2 = (i2 / 3) % nT, k2 = i2 / (3 * nT);
+      const double r2 = xadd(R, lay2 == 0 ? -1 * sc.delta : (lay2 == 1 ? 0.0 : sc.delta));
+      const V3 m2 = tab7_point(sc.kind, tab, r2, cx, cy, cz, j2, k2);
+      const double Rx = m2.x - cx, Ry = m2.y - cy, Rz = m2.z - cz;
+      const double Rcx = pt.x - cx, Rcy = pt.y - cy, Rcz = pt.z - cz;
+      // Sf_[index2(i,k)]   (sphere.C:134-157, cylinder.C:116-122)
+      double sx, sy, sz;
+      if (sc.kind == 0) {
+        const double f = sfScale * tab.ck[k];
+        sx = -(tab.cosT[i] * tab.sinP[k]) * f; sy = -(tab.sinT[i] * tab.sinP[k]) * f; sz = -tab.cosP[k] * f;
+      } else {
+        sx = -tab.cosT[i] * sfScale; sy = -tab.sinT[i] * sfScale; sz = 0.0;
+      }
+      const double Sx = rot[0] * sx + rot[1] * sy + rot[2] * sz, Sy = rot[3] * sx + rot[4] * sy + rot[5] * sz,
+                   Sz = rot[6] * sx + rot[7] * sy + rot[8] * sz;
+      const double rmag = rsqrt(Sx * Sx + Sy * Sy + Sz * Sz);
+      const double nx = Sx * rmag, ny = Sy * rmag, nz = Sz * rmag;
+      const double fx = pp * sx + (tau[0] * Sx + tau[1] * Sy + tau[2] * Sz);  // App. B #6: unrotated Sf_ in the pressure term
+      const double fy = pp * sy + (tau[1] * Sx + tau[3] * Sy + tau[4] * Sz);
+      const double fz = pp * sz + (tau[2] * Sx + tau[4] * Sy + tau[5] * Sz);
+      const double fn = fx * nx + fy * ny + fz * nz;
+      const double ftx = fx - fn * nx, fty = fy - fn * ny, ftz = fz - fn * nz;
+      acc[0] += fx; acc[1] += fy; acc[2] += fz;
+      acc[3] -= fty * Rz - ftz * Ry; acc[4] -= ftz * Rx - ftx * Rz; acc[5] -= ftx * Ry - fty * Rx;
+      acc[6] -= fty * Rcz - ftz * Rcy; acc[7] -= ftz * Rcx - ftx * Rcz; acc[8] -= ftx * Rcy - fty * Rcx;
+    }
+    if (bad) atomicExch(guard, 1);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    double v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0.0;
+    for (int w = 0; w < V7_NWARP; ++w) v += red[w][threadIdx.x];
+    const int q = threadIdx.x;
+    if (q < 3) in.F[q][b] = v;
+    else if (q < 6) in.T[q - 3][b] = v;
+    else if (Tcorr) Tcorr[3 * b + (q - 6)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// Upper estimate of the staged cells of a ball of radius rho (lattice units per axis given by d[]) over centre offsets
+// within a cell: the same row construction as build_region7, evaluated on the host for a lattice of sub-cell offsets.
+static long long region_cells_host(const double* d, double rho, int nGeoD) {
+  long long worst = 0;
+  const int NS = 5;
+  for (int sz = 0; sz < (nGeoD == 3 ? NS : 1); ++sz)
+    for (int sy = 0; sy < NS; ++sy)
+      for (int sx = 0; sx < NS; ++sx) {
+        const double c[3] = {(sx + 0.013) / NS * d[0], (sy + 0.037) / NS * d[1], nGeoD == 3 ? (sz + 0.021) / NS * d[2] : 0.5 * d[2]};
+        const int j0 = (int)std::floor((c[1] - rho) / d[1]) - 2, j1 = (int)std::floor((c[1] + rho) / d[1]) + 2;
+        const int k0 = nGeoD == 3 ? (int)std::floor((c[2] - rho) / d[2]) - 2 : 0, k1 = nGeoD == 3 ? (int)std::floor((c[2] + rho) / d[2]) + 2 : 0;
+        auto own = [&](int J, int K, int& lo, int& hi) {
+          const double ey = std::max(std::max(J * d[1] - c[1], c[1] - (J + 1) * d[1]), 0.0);
+          const double ez = nGeoD == 3 ? std::max(std::max(K * d[2] - c[2], c[2] - (K + 1) * d[2]), 0.0) : 0.0;
+          const double h2 = rho * rho * (1.0 + 1e-8) - ey * ey - ez * ez;
+          if (h2 < 0) { lo = 1; hi = 0; return; }
+          const double h = std::sqrt(h2);
+          lo = (int)std::floor((c[0] - h) / d[0]); hi = (int)std::floor((c[0] + h) / d[0]);
+        };
+        long long tot = 0;
+        for (int K = k0; K <= k1; ++K)
+          for (int J = j0; J <= j1; ++J) {
+            int a = 0x7fffffff, b = -0x7fffffff, lo, hi;
+            own(J, K, lo, hi); if (lo <= hi) { a = lo - 1; b = hi + 1; }
+            own(J + 1, K, lo, hi); if (lo <= hi) { a = std::min(a, lo); b = std::max(b, hi); }
+            own(J - 1, K, lo, hi); if (lo <= hi) { a = std::min(a, lo); b = std::max(b, hi); }
+            if (nGeoD == 3) {
+              own(J, K + 1, lo, hi); if (lo <= hi) { a = std::min(a, lo); b = std::max(b, hi); }
+              own(J, K - 1, lo, hi); if (lo <= hi) { a = std::min(a, lo); b = std::max(b, hi); }
+            }
+            if (a <= b) tot += b - a + 1;
+          }
+        worst = std::max(worst, tot);
+      }
+  return worst;
+}
+
+// capacities of a launch from the shape classes (host copies); returns false when no class can take the fast path
+bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress) {
+  const int SMEM_BUDGET_F = 113 * 1024, SMEM_BUDGET_S = 74 * 1024;  // two / three resident CTAs per SM (228 KB - 1 KB per CTA)
+  V7Caps f{}, s{};
+  bool any = false;
+  const double d[3] = {L.dx, L.dy, L.dz};
+  for (int q = 0; q < nClasses; ++q) {
+    const ShapeClassDev& sc = hostClasses[q];
+    if (sc.kind == 2) return false;  // mixed populations with ellipses take the second-generation path as a whole
+    const double R = sc.d / 2.0;
+    const long long nA = region_cells_host(d, R + sc.delta, nGeoD), nB = region_cells_host(d, R, nGeoD),
+                    nC = region_cells_host(d, std::max(R - sc.delta, 0.0), nGeoD);
+    auto rowsOf = [&](double reach) {
+      long long by = (long long)std::ceil(2.0 * reach / d[1]) + 4, bz = nGeoD == 3 ? (long long)std::ceil(2.0 * reach / d[2]) + 4 : 1;
+      return std::min<long long>(by, L.ny) * std::min<long long>(bz, L.nz);
+    };
+    const double cellV = d[0] * d[1] * (nGeoD == 2 ? 1.0 : d[2]);
+    const double r0 = std::max(0.0, R - sc.delta);
+    const double vol = nGeoD == 2 ? IBM_PI * (R * R - r0 * r0) : 4.0 / 3.0 * IBM_PI * (R * R * R - r0 * r0 * r0);
+    // distinct columns of a d = 8 cells sphere: 584 on average, 631 at most, of 4 x 155 corner references (measured over
+    // 3000 random centres); beyond the capacity an instance takes the list path, so this is a performance bound only
+    const long long colEst = std::min<long long>((long long)sc.nTheta * sc.nk + 1, (long long)(4.0 * vol / cellV) + 56);
+    auto up = [](long long v) { return (int)std::min<long long>((v + v / 16 + 16 + 1) & ~1LL, 0x3fffffff); };
+    f.planeCap = std::max(f.planeCap, up(3 * (nA + nB + nC)));
+    f.colCap = std::max(f.colCap, (int)std::min<long long>(colEst, 65535));
+    f.rowsCap = std::max(f.rowsCap, (int)std::min<long long>(rowsOf(R + sc.delta), 4 * V7_THREADS));
+    f.mapCap = std::max<long long>(f.mapCap, std::min<long long>((long long)sc.nTheta * sc.nk + 1, 1 << 20));
+    f.nTcap = std::max(f.nTcap, sc.nTheta);
+    f.nkCap = std::max(f.nkCap, sc.nk);
+    f.elemCap = std::max(f.elemCap, up(nA));
+    s.planeCap = std::max(s.planeCap, up(7 * nB));
+    s.rowsCap = std::max(s.rowsCap, (int)std::min<long long>(rowsOf(R), 4 * V7_THREADS));
+    s.nTcap = f.nTcap; s.nkCap = f.nkCap;
+    s.elemCap = std::max(s.elemCap, up(nB));
+    any = true;
+  }
+  s.colCap = 0; s.mapCap = 0;
+  if (!any) return false;
+  if (v7_layout(f).total > SMEM_BUDGET_F || v7_layout(s).total > SMEM_BUDGET_S) return false;
+  if (f.elemCap > 65535 * 8 || f.rowsCap > 65535) return false;
+  forcing = f; stress = s;
+  return true;
+}
+
+void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                       const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
+  if (nInst <= 0) return;
+  const int sm = v7_layout(cap).total;
+  static PerDeviceOnce attr;
+  static int attrBytes = 0;
+  if (attr.first() || sm > attrBytes) {
+    cudaFuncSetAttribute(k_forcing_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    attrBytes = std::max(attrBytes, sm);
+  }
+  cudaMemsetAsync(slowCount, 0, sizeof(int), st);
+  k_forcing_v7<<<nInst, V7_THREADS, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList,
+                                              slowCount, guard);
+  launch_forcing_v2_list(st, L, classes, in, slowList, slowCount, shellCell, shellJK, U, Uold, S, dT, F);
+}
+
+void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
+                      const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
+  if (nInst <= 0) return;
+  const int sm = v7_layout(cap).total;
+  static PerDeviceOnce attr;
+  static int attrBytes = 0;
+  if (attr.first() || sm > attrBytes) {
+    cudaFuncSetAttribute(k_stress_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    attrBytes = std::max(attrBytes, sm);
+  }
+  cudaMemsetAsync(slowCount, 0, sizeof(int), st);
+  k_stress_v7<<<nInst, V7_THREADS, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount,
+                                             guard);
+  launch_stress_v2_list(st, L, classes, in, slowList, slowCount, P, Tau, pRefOverRho, rhoRef, Tcorr);
+}
+
+}  // namespace ibm

@@ -780,7 +780,9 @@ __global__ void k5_bin_cand(MotionDev m, InstanceSoA in, const ShapeClassDev* __
 }
 __global__ void k5_find_pairs(MotionDev m, InstanceSoA in) { d5_find_pairs(m, in, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void k5_pair_force(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, double deltaT) {
-  d5_pair_force(m, in, classes, deltaT, blockIdx.x * blockDim.x + threadIdx.x);
+  // grid-stride: the grid is sized from a typical candidate count (and frozen in a captured graph), the list may be longer
+  const int np = min(*m.pairCount, m.pairCap);
+  for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < np; h += gridDim.x * blockDim.x) d5_pair_force(m, in, classes, deltaT, h);
 }
 __global__ void k5_rows_finish(MotionDev m, InstanceSoA in) {
   d5_rows_finish(m, in, blockIdx.x * blockDim.x + threadIdx.x);

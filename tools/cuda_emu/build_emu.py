@@ -109,7 +109,7 @@ def build(verbose=False, asan=False):
     os.makedirs(SRC_OUT, exist_ok=True)
     objs = []
     units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
-    flags = ["-x", "c++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-w", "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+    flags = ["-x", "c++", "-std=c++17", "-O1", "-g", *os.environ.get("IBM_EMU_DEFS", "").split(), "-fPIC", "-ffp-contract=off", "-w", "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
     if asan:
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("emu.hpp", "cuda_runtime.h", "cuda_pipeline.h",
