@@ -35,8 +35,11 @@
 
 namespace ibm {
 
-#define V7_THREADS 256
-#define V7_NWARP (V7_THREADS / 32)
+#define V7_MAXT 320
+
+#if defined(IBM_CUDA_EMU)
+#define IBM_V7_GUARD 1  // the CPU emulation checks that every gather stencil stays inside the staged region
+#endif
 
 // shared-memory carve-up, identical on host and device
 struct V7Layout {
@@ -73,32 +76,67 @@ __device__ __forceinline__ V3 tab7_point(int kind, const Tab7& t, double r, doub
   return V3{xadd(xmul(r, t.cosT[j]), cx), xadd(xmul(r, t.sinT[j]), cy), xadd(0.0, cz)};
 }
 
+// 1/sqrt(x) and 1/x for well-scaled positive x: hardware seed (2^-22) + one third-order / two second-order steps; no
+// special-case handling (the arguments are squared distances and weight sums of order delta^2 and 1/delta)
+__device__ __forceinline__ double rsqrt7(double x) {
+#if defined(IBM_CUDA_EMU)
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);     // 1 - x y^2
+  const double p = fma(e, 0.375, 0.5);
+  return fma(p * e, y, y);                  // y (1 + e/2 + 3 e^2/8)
+#endif
+}
+__device__ __forceinline__ double rcp7(double x) {
+#if defined(IBM_CUDA_EMU)
+  return 1.0 / x;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#endif
+}
+
 struct Box7 {
-  int i0, j0, k0;  // (unclipped x origin is not needed) first row / plane of the box, clipped to the lattice
-  int by, bz;      // rows per plane, planes
+  int j0, k0;  // first row / plane of the box, clipped to the lattice
+  int by, bz;  // rows per plane, planes
+  int edge;    // the unclipped box reaches the lattice boundary: stencil neighbours may be missing, points may be off the mesh
 };
 
-// exclusive scan of one int per thread over the block (V7_THREADS threads); every thread gets the block total
-__device__ __forceinline__ int block_scan7(int v, int* wsum, int& total) {
+struct Geo7 {  // lattice constants of a launch, in registers
+  double ox, oy, oz, dx, dy, dz, idx, idy, idz, hx, hy, hz;
+  int nx, ny, nz, kz0;
+};
+__device__ __forceinline__ Geo7 geo7(const LatticeDev& L) {
+  return Geo7{L.ox, L.oy, L.oz, L.dx, L.dy, L.dz, 1.0 / L.dx, 1.0 / L.dy, 1.0 / L.dz, 0.5 * L.dx, 0.5 * L.dy, 0.5 * L.dz, L.nx, L.ny, L.nz, L.kz0};
+}
+
+// exclusive scan of two ints per thread over the block; every thread gets the block totals
+template <int NT>
+__device__ __forceinline__ void block_scan7(int& v0, int& v1, int* wsum, int& tot0, int& tot1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
+  int i0 = v0, i1 = v1;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
+    const int n0 = __shfl_up_sync(0xffffffffu, i0, o), n1 = __shfl_up_sync(0xffffffffu, i1, o);
+    if (lane >= o) { i0 += n0; i1 += n1; }
   }
-  if (lane == 31) wsum[warp] = inc;
+  if (lane == 31) { wsum[2 * warp] = i0; wsum[2 * warp + 1] = i1; }
   __syncthreads();
-  int base = 0, tot = 0;
+  int b0 = 0, b1 = 0, t0 = 0, t1 = 0;
 #pragma unroll
-  for (int w = 0; w < V7_NWARP; ++w) {
-    const int s = wsum[w];
-    if (w < warp) base += s;
-    tot += s;
+  for (int w = 0; w < NT / 32; ++w) {
+    const int s0 = wsum[2 * w], s1 = wsum[2 * w + 1];
+    if (w < warp) { b0 += s0; b1 += s1; }
+    t0 += s0; t1 += s1;
   }
-  total = tot;
+  tot0 = t0; tot1 = t1;
   __syncthreads();  // wsum may be reused
-  return base + inc - v;
+  v0 = b0 + i0 - v0; v1 = b1 + i1 - v1;
 }
 
 // own x-range of row (J,K) for a layer of radius rho around (cx,cy,cz): cells whose box intersects the closed ball
@@ -114,96 +152,129 @@ __device__ __forceinline__ void own_range7(const LatticeDev& L, double cx, doubl
   hi = (int)floor((cx + h - L.ox) / L.dx);
 }
 
-struct St7 { int idx[7]; double c[7]; };  // self, +x, -x, +y, -y, +z, -z: index into a plane of the set, coefficient
-
-// 7-point gather stencil of point p in plane-set `set` (particleShape.C:49-91 with lambda = 1/2 folded in).  Returns
-// 0 = point off the local mesh (contributes nothing), 1 = ok, -1 = the staged region does not hold the stencil (bug guard).
-__device__ __forceinline__ int make_st7(const LatticeDev& L, double idx, double idy, double idz, const Box7& B, const int* __restrict__ rowBase,
-                                        const int* __restrict__ rowLo, const int* __restrict__ rowHi, const V3& p, St7& s) {
-  int I, J, K;
-  if (find_cell_fast(L, idx, idy, idz, p.x, p.y, p.z, I, J, K) < 0) return 0;
-  const int bj = J - B.j0, bk = K - B.k0;
-  if (bj < 0 || bj >= B.by || bk < 0 || bk >= B.bz) return -1;
-  const int row = bj + B.by * bk;
-  if (rowLo[row] > I - (I > 0) || rowHi[row] < I + (I + 1 < L.nx)) return -1;
-  const double ex = (L.ox + (I + 0.5) * L.dx) - p.x, ey = (L.oy + (J + 0.5) * L.dy) - p.y, ez = (L.oz + (K + L.kz0 + 0.5) * L.dz) - p.z;
-  const double hx = 0.5 * L.dx, hy = 0.5 * L.dy, hz = 0.5 * L.dz;
-  const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
-  double d2[6];
-  d2[0] = (ex + hx) * (ex + hx) + ey2 + ez2;
-  d2[1] = (ex - hx) * (ex - hx) + ey2 + ez2;
-  d2[2] = ex2 + (ey + hy) * (ey + hy) + ez2;
-  d2[3] = ex2 + (ey - hy) * (ey - hy) + ez2;
-  d2[4] = ex2 + ey2 + (ez + hz) * (ez + hz);
-  d2[5] = ex2 + ey2 + (ez - hz) * (ez - hz);
-  const bool ok[6] = {I + 1 < L.nx, I > 0, J + 1 < L.ny, J > 0, K + 1 < L.nz, K > 0};
-  const int self = rowBase[row] + I;
-  s.idx[0] = self;
-  s.idx[1] = ok[0] ? self + 1 : self;
-  s.idx[2] = ok[1] ? self - 1 : self;
-  // a neighbouring row inside the lattice is inside the box and holds column I (the touched range of a row contains the
-  // own ranges of its four neighbours); guard anyway
-  int bad = 0;
-  if (ok[2]) { if (bj + 1 >= B.by || I < rowLo[row + 1] || I > rowHi[row + 1]) bad = 1; else s.idx[3] = rowBase[row + 1] + I; } else s.idx[3] = self;
-  if (ok[3]) { if (bj < 1 || I < rowLo[row - 1] || I > rowHi[row - 1]) bad = 1; else s.idx[4] = rowBase[row - 1] + I; } else s.idx[4] = self;
-  if (ok[4]) { if (bk + 1 >= B.bz || I < rowLo[row + B.by] || I > rowHi[row + B.by]) bad = 1; else s.idx[5] = rowBase[row + B.by] + I; } else s.idx[5] = self;
-  if (ok[5]) { if (bk < 1 || I < rowLo[row - B.by] || I > rowHi[row - B.by]) bad = 1; else s.idx[6] = rowBase[row - B.by] + I; } else s.idx[6] = self;
-  if (bad) return -1;
-  double w[6], W = 0.0;
-  int hot = -1;
-#pragma unroll
-  for (int d = 0; d < 6; ++d) {
-    w[d] = ok[d] ? rsqrt(d2[d]) : 0.0;
-    if (ok[d] && d2[d] < IBM_SMALL * IBM_SMALL && hot < 0) hot = d;  // particleShape.C:69-77
-    W += w[d];
+// cell index along one axis and the position inside the cell (fraction of the cell size).  floor(q * inv) equals
+// floor(fl(q / d)) (the DEFINED findCell) unless q/d lies within rounding of an integer; those cases take the exact division.
+__device__ __forceinline__ int cell_axis7(double q, double d, double inv, double& fr) {
+  const double t = q * inv;
+  const double s = (t - 0.5) + 6755399441055744.0;  // 1.5 * 2^52: the low word is rn(t - 0.5) as a two's-complement integer
+  int I = __double2loint(s);
+  const double f = s - 6755399441055744.0;
+  fr = t - f;
+  if (!(fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(t) < 1.0e9)) {
+    const double f2 = floor(xdiv(q, d));
+    I = (f2 > -2.0e9 && f2 < 2.0e9) ? (int)f2 : -0x40000000;  // (far outside or not a number: off the mesh)
+    fr = t - f2;
   }
-  if (hot >= 0) {
-#pragma unroll
-    for (int d = 0; d < 6; ++d) w[d] = (d == hot) ? 1.0 : 0.0;
-    W = 1.0;
-  }
-  const double hW = (W > 0.0) ? 0.5 / W : 0.0;
-  double cs = 0.0;
-#pragma unroll
-  for (int d = 0; d < 6; ++d) { s.c[1 + d] = w[d] * hW; cs += s.c[1 + d]; }
-  s.c[0] = cs;
-  return 1;
+  return I;
 }
 
-__device__ __forceinline__ double gat7(const St7& s, const double* __restrict__ f) {
-  double v = s.c[0] * f[s.idx[0]];
+struct St7 { int idx[7]; double c[7]; };  // self, +x, -x, +y, -y, +z, -z: record index in a plane-set, coefficient
+
+// 7-point gather stencil of point p in a plane-set with row table rowBase (particleShape.C:49-91 with the linear face
+// weights lambda = 1/2 folded in).  Returns false when the point is off the local mesh (it contributes nothing).
+template <bool EDGE>
+__device__ __forceinline__ bool make_st7(const Geo7& G, const Box7& B, const int* __restrict__ rowBase, const int* __restrict__ rowLo,
+                                         const int* __restrict__ rowHi, const V3& p, St7& s, int& guard) {
+  double fx, fy, fz;
+  const int I = cell_axis7(p.x - G.ox, G.dx, G.idx, fx);
+  const int J = cell_axis7(p.y - G.oy, G.dy, G.idy, fy);
+  const int K = cell_axis7(p.z - G.oz, G.dz, G.idz, fz) - G.kz0;
+  if (EDGE) {
+    if ((unsigned)I >= (unsigned)G.nx || (unsigned)J >= (unsigned)G.ny || (unsigned)K >= (unsigned)G.nz) return false;
+  }
+  const int bj = J - B.j0, bk = K - B.k0;
+  const int row = bj + B.by * bk;
+#if defined(IBM_V7_GUARD)
+  if (bj < 0 || bj >= B.by || bk < 0 || bk >= B.bz) { guard = 1; return false; }
+  if (rowLo[row] > I - (I > 0) || rowHi[row] < I + (I + 1 < G.nx)) { guard = 1; return false; }
+  if (J + 1 < G.ny && (bj + 1 >= B.by || I < rowLo[row + 1] || I > rowHi[row + 1])) { guard = 1; return false; }
+  if (J > 0 && (bj < 1 || I < rowLo[row - 1] || I > rowHi[row - 1])) { guard = 1; return false; }
+  if (K + 1 < G.nz && (bk + 1 >= B.bz || I < rowLo[row + B.by] || I > rowHi[row + B.by])) { guard = 1; return false; }
+  if (K > 0 && (bk < 1 || I < rowLo[row - B.by] || I > rowHi[row - B.by])) { guard = 1; return false; }
+  if (!EDGE && !(I > 0 && I + 1 < G.nx && J > 0 && J + 1 < G.ny && K > 0 && K + 1 < G.nz)) { guard = 1; return false; }
+#endif
+  const double ex = (0.5 - fx) * G.dx, ey = (0.5 - fy) * G.dy, ez = (0.5 - fz) * G.dz;  // cell centre - point
+  const double ex2 = ex * ex, ey2 = ey * ey, ez2 = ez * ez;
+  const double exy = ex2 + ey2, exz = ex2 + ez2, eyz = ey2 + ez2;
+  double d2[6];
+  d2[0] = fma(ex + G.hx, ex + G.hx, eyz);
+  d2[1] = fma(ex - G.hx, ex - G.hx, eyz);
+  d2[2] = fma(ey + G.hy, ey + G.hy, exz);
+  d2[3] = fma(ey - G.hy, ey - G.hy, exz);
+  d2[4] = fma(ez + G.hz, ez + G.hz, exy);
+  d2[5] = fma(ez - G.hz, ez - G.hz, exy);
+  const int self = rowBase[row] + I;
+  double w[6];
+  if (EDGE) {
+    const bool ok[6] = {I + 1 < G.nx, I > 0, J + 1 < G.ny, J > 0, K + 1 < G.nz, K > 0};
+    s.idx[0] = self;
+    s.idx[1] = ok[0] ? self + 1 : self;
+    s.idx[2] = ok[1] ? self - 1 : self;
+    s.idx[3] = ok[2] ? rowBase[row + 1] + I : self;
+    s.idx[4] = ok[3] ? rowBase[row - 1] + I : self;
+    s.idx[5] = ok[4] ? rowBase[row + B.by] + I : self;
+    s.idx[6] = ok[5] ? rowBase[row - B.by] + I : self;
 #pragma unroll
-  for (int d = 1; d < 7; ++d) v = fma(s.c[d], f[s.idx[d]], v);
-  return v;
+    for (int d = 0; d < 6; ++d) w[d] = ok[d] ? rsqrt7(d2[d]) : 0.0;
+  } else {
+    s.idx[0] = self; s.idx[1] = self + 1; s.idx[2] = self - 1;
+    s.idx[3] = rowBase[row + 1] + I; s.idx[4] = rowBase[row - 1] + I;
+    s.idx[5] = rowBase[row + B.by] + I; s.idx[6] = rowBase[row - B.by] + I;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) w[d] = rsqrt7(d2[d]);
+  }
+  double W = ((w[0] + w[1]) + (w[2] + w[3])) + (w[4] + w[5]);
+  if (W > 0.5e15) {  // a face centre within SMALL of the point: one-hot on the first such face (particleShape.C:69-77)
+    int hot = -1;
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+      if (w[d] > 0.0 && d2[d] < IBM_SMALL * IBM_SMALL && hot < 0) hot = d;
+    if (hot >= 0) {
+#pragma unroll
+      for (int d = 0; d < 6; ++d) w[d] = (d == hot) ? 1.0 : 0.0;
+      W = 1.0;
+    }
+  }
+  const double hW = (!EDGE || W > 0.0) ? 0.5 * rcp7(W) : 0.0;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) s.c[1 + d] = w[d] * hW;
+  s.c[0] = ((s.c[1] + s.c[2]) + (s.c[3] + s.c[4])) + (s.c[5] + s.c[6]);
+  return true;
+}
+
+// gather NC interleaved components of a record plane (record = NC doubles per cell)
+template <int NC>
+__device__ __forceinline__ void gat7(const St7& s, const double* __restrict__ f, double* out) {
+#pragma unroll
+  for (int q = 0; q < NC; ++q) out[q] = s.c[0] * f[NC * s.idx[0] + q];
+#pragma unroll
+  for (int d = 1; d < 7; ++d) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q) out[q] = fma(s.c[d], f[NC * s.idx[d] + q], out[q]);
+  }
 }
 
 // Region tables of one instance: for every set (0 = outer reach, 1 = surface reach, 2 = inner reach) and row of the box
-//   rowLo/rowHi = first / last staged column, rowBase = offset of column 0 in a plane of the set (index = rowBase + I).
-// Returns the cell counts per set in n[3].  nSets limits the work (the stress kernel needs set 1 only: pass first=1,last=1).
+//   rowLo/rowHi = first / last staged column, rowBase = record index of column 0 of the row (record = rowBase + I).
+// Cell counts per set in n[3].  first/last limit the sets (the stress kernel needs set 1 only).  rows <= NT (caller).
+template <int NT>
 __device__ __forceinline__ void build_region7(const LatticeDev& L, const Box7& B, double cx, double cy, double cz, const double* rho,
                                               int first, int last, int rowsCap, int* rowBase, int* rowLo, int* rowHi, int* rowG, int* wsum, int* n) {
   const int rows = B.by * B.bz;
-  const int t = threadIdx.x;
-  // own ranges (several rows per thread when the box has more rows than the block has threads)
-  for (int r = t; r < rows; r += V7_THREADS) {
-    const int bj = r % B.by, bk = r / B.by;
+  const int r = threadIdx.x;
+  const int bj = r % B.by, bk = r / B.by;
+  if (r < rows) {
     for (int s = first; s <= last; ++s) {
       int lo, hi;
       own_range7(L, cx, cy, cz, rho[s], B.j0 + bj, B.k0 + bk, lo, hi);
       rowLo[s * rowsCap + r] = lo;
       rowHi[s * rowsCap + r] = hi;
     }
+    rowG[r] = L.nx * ((B.j0 + bj) + L.ny * (B.k0 + bk));  // lattice index of column 0 of the row
   }
   __syncthreads();
-  // touched ranges, in registers (rows <= 4 * V7_THREADS is guaranteed by the caller)
-  int tl[3][4], th[3][4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int r = t + q * V7_THREADS;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) { tl[s][q] = 1; th[s][q] = 0; }
-    if (r >= rows) continue;
-    const int bj = r % B.by, bk = r / B.by;
+  int tl[3] = {1, 1, 1}, th[3] = {0, 0, 0};
+  if (r < rows) {
     for (int s = first; s <= last; ++s) {
       const int* lo = rowLo + s * rowsCap;
       const int* hi = rowHi + s * rowsCap;
@@ -215,58 +286,93 @@ __device__ __forceinline__ void build_region7(const LatticeDev& L, const Box7& B
       if (bk > 0 && lo[r - B.by] <= hi[r - B.by]) { a = min(a, lo[r - B.by]); b = max(b, hi[r - B.by]); }
       a = max(a, 0); b = min(b, L.nx - 1);
       if (a > b) { a = 1; b = 0; }
-      tl[s][q] = a; th[s][q] = b;
+      tl[s] = a; th[s] = b;
     }
   }
   __syncthreads();
-  n[0] = n[1] = n[2] = 0;
-  for (int s = first; s <= last; ++s) {
-    int run = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {  // rows q*V7_THREADS + t: scan each stripe, carry the stripe totals
-      if (q * V7_THREADS < rows) {  // (block-uniform)
-        const int len = max(th[s][q] - tl[s][q] + 1, 0);
-        int tot;
-        const int off = block_scan7(len, wsum, tot) + run;
-        const int r = t + q * V7_THREADS;
-        if (r < rows) {
-          rowLo[s * rowsCap + r] = tl[s][q];
-          rowHi[s * rowsCap + r] = th[s][q];
-          rowBase[s * rowsCap + r] = off - tl[s][q];
-        }
-        run += tot;
-      }
+  // one scan for all three sets: set 0 alone, sets 1 and 2 packed (16 bits each; the caller guarantees < 65536 cells per set)
+  int v0 = max(th[0] - tl[0] + 1, 0), v1 = max(th[1] - tl[1] + 1, 0) | (max(th[2] - tl[2] + 1, 0) << 16);
+  int t0, t1;
+  block_scan7<NT>(v0, v1, wsum, t0, t1);
+  if (r < rows) {
+    const int off[3] = {v0, v1 & 0xffff, (v1 >> 16) & 0xffff};
+    for (int s = first; s <= last; ++s) {
+      rowLo[s * rowsCap + r] = tl[s];
+      rowHi[s * rowsCap + r] = th[s];
+      rowBase[s * rowsCap + r] = off[s] - tl[s];
     }
-    n[s] = run;
   }
-  // global offset of column 0 of every row (lattice index = rowG + I)
-  for (int r = t; r < rows; r += V7_THREADS) {
-    const int bj = r % B.by, bk = r / B.by;
-    rowG[r] = L.nx * ((B.j0 + bj) + L.ny * (B.k0 + bk));
-  }
+  n[0] = t0; n[1] = t1 & 0xffff; n[2] = (t1 >> 16) & 0xffff;
   __syncthreads();
 }
 
 __device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, double cy, double cz, double reach, Box7& B) {
+  const int i0 = (int)floor((cx - reach - L.ox) / L.dx) - 1, i1 = (int)floor((cx + reach - L.ox) / L.dx) + 1;
   const int j0 = (int)floor((cy - reach - L.oy) / L.dy) - 1, j1 = (int)floor((cy + reach - L.oy) / L.dy) + 1;
   const int k0 = (int)floor((cz - reach - L.oz) / L.dz) - 1 - L.kz0, k1 = (int)floor((cz + reach - L.oz) / L.dz) + 1 - L.kz0;
-  B.i0 = 0;
   B.j0 = max(j0, 0); B.k0 = max(k0, 0);
   B.by = min(j1, L.ny - 1) - B.j0 + 1;
   B.bz = min(k1, L.nz - 1) - B.k0 + 1;
+  // interior: every point's cell AND its six neighbours exist (the box carries one cell of margin around the points' cells)
+  B.edge = !(i0 >= 0 && i1 <= L.nx - 1 && j0 >= 0 && j1 <= L.ny - 1 && k0 >= 0 && k1 <= L.nz - 1);
   return B.by > 0 && B.bz > 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2/K3 v7: direct forcing, one CTA per instance
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(V7_THREADS, 2)
+struct Col7Ctx {
+  Geo7 G; Box7 B; Tab7 tab;
+  const int *baseA, *loA, *hiA, *baseB, *loB, *hiB, *baseC, *loC, *hiC;
+  const double *pA, *pB, *pC;
+  double cx, cy, cz, rdT;
+  double rI, rS, rO;
+  V3 vp, om;
+  int kind, nT, nMap;
+};
+
+template <bool EDGE, int NT>
+__device__ __forceinline__ int columns7(const Col7Ctx& X, const int* __restrict__ colKey, int nCol, double* __restrict__ colVal) {
+  int guard = 0;
+  for (int s = threadIdx.x; s < nCol; s += NT) {
+    const int key = colKey[s];
+    const int jq = key & 0xffff, kq = key >> 16;
+    const bool deg = kq == 0x7fff;
+    // (a degenerate bin uses point 0 = the inner point of (0,0) for all three roles, particleShape.C:148)
+    const V3 xI = tab7_point(X.kind, X.tab, X.rI, X.cx, X.cy, X.cz, deg ? 0 : jq, deg ? 0 : kq);
+    const V3 xS = deg ? xI : tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, jq, kq);
+    const V3 xO = deg ? xI : tab7_point(X.kind, X.tab, X.rO, X.cx, X.cy, X.cz, jq, kq);
+    double tO[3] = {0, 0, 0}, tS[3] = {0, 0, 0}, g[3];
+    St7 st;
+    if (make_st7<EDGE>(X.G, X.B, X.baseC, X.loC, X.hiC, xI, st, guard)) { gat7<3>(st, X.pC, tO); }
+    if (make_st7<EDGE>(X.G, X.B, X.baseA, X.loA, X.hiA, xO, st, guard)) { gat7<3>(st, X.pA, g); tO[0] += g[0]; tO[1] += g[1]; tO[2] += g[2]; }
+    {
+      const double rx = xO.x - X.cx, ry = xO.y - X.cy, rz = xO.z - X.cz;
+      tO[0] = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tO[0]);
+      tO[1] = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tO[1]);
+      tO[2] = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tO[2]);
+    }
+    if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, xS, st, guard)) { gat7<3>(st, X.pB, tS); }
+    {
+      const double rx = xS.x - X.cx, ry = xS.y - X.cy, rz = xS.z - X.cz;
+      tS[0] = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tS[0]);
+      tS[1] = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tS[1]);
+      tS[2] = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tS[2]);
+    }
+    double* cv = colVal + 6 * s;
+    cv[0] = tO[0]; cv[1] = tO[1]; cv[2] = tO[2]; cv[3] = tS[0]; cv[4] = tS[1]; cv[5] = tS[2];
+  }
+  return guard;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
 k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
              const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
              const double* __restrict__ Uold, const double* __restrict__ S, double dT, double* __restrict__ F, V7Caps cap,
-             int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guard) {
+             int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
   extern __shared__ double smem7[];
-  __shared__ int wsum[V7_NWARP];
+  __shared__ int wsum[2 * (NT / 32)];
   if ((int)blockIdx.x >= nInst) return;
   const int b = order[blockIdx.x];
   const int nShell = in.nShell[b];
@@ -292,21 +398,21 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   const double rL[3] = {xadd(R, -1 * sc.delta), xadd(R, 0.0), xadd(R, sc.delta)};  // R + delta[i]  (sphere.C:167,173)
   const double rho[3] = {rL[2], rL[1], rL[0]};                                      // set 0 = outer reach ... set 2 = inner reach
   Box7 B;
-  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && nMap <= cap.mapCap && box7_around(L, cx, cy, cz, rho[0], B);
-  if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= 4 * V7_THREADS;
+  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && nk < 0x7fff && nMap <= cap.mapCap && box7_around(L, cx, cy, cz, rho[0], B);
+  if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= NT;
   if (!fits) {
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
   const Tab7 tab = tab7_load(sc, tabD, cap);
-  for (int m = threadIdx.x; m < nMap; m += V7_THREADS) colSlot[m] = 0;
+  for (int m = threadIdx.x; m < nMap; m += NT) colSlot[m] = 0;
   int nS[3];
-  build_region7(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
+  build_region7<NT>(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
   const int nA = nS[0], nB = nS[1], nC = nS[2];
   const int off = in.shellOff[b];
 
   // ---- columns referenced by the shell cells: mark, then compact ----
-  for (int t = threadIdx.x; t < nShell; t += V7_THREADS) {
+  for (int t = threadIdx.x; t < nShell; t += NT) {
     const int pk = shellJK[off + t];
     const int j = pk & 0xffff, k = pk >> 16;
     if (nk != 1 && k == nk - 1) { colSlot[nMap - 1] = 1; continue; }
@@ -316,33 +422,33 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   __syncthreads();
   int nCol = 0;
   {
-    const int per = (nMap + V7_THREADS - 1) / V7_THREADS;
+    const int per = (nMap + NT - 1) / NT;
     const int m0 = threadIdx.x * per, m1 = min(m0 + per, nMap);
-    int cnt = 0;
+    int cnt = 0, dummy = 0, dt = 0;
     for (int m = m0; m < m1; ++m) cnt += colSlot[m];
-    int slot = block_scan7(cnt, wsum, nCol);
-    if (nCol <= cap.colCap)
-      for (int m = m0; m < m1; ++m)
-        if (colSlot[m]) { colKey[slot] = m; colSlot[m] = (unsigned short)slot; ++slot; }
+    int slot = cnt;
+    block_scan7<NT>(slot, dummy, wsum, nCol, dt);
+    if (nCol <= cap.colCap && m0 < m1) {
+      int k = m0 / nT, j = m0 - k * nT;
+      for (int m = m0; m < m1; ++m) {
+        if (colSlot[m]) { colKey[slot] = (m == nMap - 1) ? (0x7fff << 16) : (j | (k << 16)); colSlot[m] = (unsigned short)slot; ++slot; }
+        if (++j == nT) { j = 0; ++k; }
+      }
+    }
   }
-  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nCol > cap.colCap || nCol > 65535) {
-#ifdef IBM_V7_DEBUG
-    if (threadIdx.x == 0) printf("v7 slow: b=%d nA=%d nB=%d nC=%d planeCap=%d elemCap=%d nCol=%d colCap=%d nShell=%d\n", b, nA, nB, nC, cap.planeCap, cap.elemCap, nCol, cap.colCap, nShell);
-#endif
+  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nA > 65535 || nCol > cap.colCap || nCol > 65535) {
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
   // elemRow: row of every element of set 0 (the staging loop runs over the elements of the widest set)
-  {
-    const int rows = B.by * B.bz;
-    for (int r = threadIdx.x; r < rows; r += V7_THREADS) {
-      const int lo = rowLo[r], hi = rowHi[r], o = rowBase[r] + lo;
-      for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
-    }
+  if ((int)threadIdx.x < B.by * B.bz) {
+    const int r = threadIdx.x;
+    const int lo = rowLo[r], hi = rowHi[r], o = rowBase[r] + lo;
+    for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
   }
   __syncthreads();
 
-  // ---- stage: every needed cell value read once, combined on the way ----
+  // ---- stage: every needed cell value read once, combined on the way (records of three components) ----
   const size_t C = (size_t)L.nCells;
   const double rdT = 1.0 / dT;
   double* pA = planes;
@@ -350,7 +456,8 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   double* pC = pB + 3 * nB;
   const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
   const int* loC = rowLo + 2 * cap.rowsCap; const int* hiC = rowHi + 2 * cap.rowsCap; const int* baseC = rowBase + 2 * cap.rowsCap;
-  for (int a = threadIdx.x; a < nA; a += V7_THREADS) {
+#pragma unroll 2
+  for (int a = threadIdx.x; a < nA; a += NT) {
     const int row = elemRow[a];
     const int I = a - rowBase[row];
     const size_t g = (size_t)(rowG[row] + I);
@@ -359,81 +466,45 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     const bool inB = I >= loB[row] && I <= hiB[row];
     double o0 = 0.0, o1 = 0.0, o2 = 0.0;
     if (inB) { o0 = __ldg(Uold + g); o1 = __ldg(Uold + C + g); o2 = __ldg(Uold + 2 * C + g); }
-    pA[a] = fma(-rdT, u0, s0); pA[nA + a] = fma(-rdT, u1, s1); pA[2 * nA + a] = fma(-rdT, u2, s2);
+    pA[3 * a] = fma(-rdT, u0, s0); pA[3 * a + 1] = fma(-rdT, u1, s1); pA[3 * a + 2] = fma(-rdT, u2, s2);
     if (inB) {
-      const int ib = baseB[row] + I;
-      pB[ib] = fma(-rdT, o0, s0); pB[nB + ib] = fma(-rdT, o1, s1); pB[2 * nB + ib] = fma(-rdT, o2, s2);
+      const int ib = 3 * (baseB[row] + I);
+      pB[ib] = fma(-rdT, o0, s0); pB[ib + 1] = fma(-rdT, o1, s1); pB[ib + 2] = fma(-rdT, o2, s2);
       if (I >= loC[row] && I <= hiC[row]) {
-        const int ic = baseC[row] + I;
-        pC[ic] = -rdT * o0; pC[nC + ic] = -rdT * o1; pC[2 * nC + ic] = -rdT * o2;
+        const int ic = 3 * (baseC[row] + I);
+        pC[ic] = -rdT * o0; pC[ic + 1] = -rdT * o1; pC[ic + 2] = -rdT * o2;
       }
     }
   }
   __syncthreads();
 
   // ---- one thread per distinct column: three stencils, 63 shared-memory loads ----
-  const V3 vp{in.v[0][b], in.v[1][b], in.v[2][b]}, om{in.om[0][b], in.om[1][b], in.om[2][b]};
-  const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
-  int bad = 0;
-  for (int s = threadIdx.x; s < nCol; s += V7_THREADS) {
-    const int key = colKey[s];
-    const bool deg = key == nMap - 1;
-    const int kq = deg ? 0 : key / nT, jq = deg ? 0 : key - kq * nT;
-    // (a degenerate bin uses point 0 = the inner point of (0,0) for all three roles, particleShape.C:148)
-    const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
-    const V3 xS = deg ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
-    const V3 xO = deg ? xI : tab7_point(sc.kind, tab, rL[2], cx, cy, cz, jq, kq);
-    double tO[3] = {0, 0, 0}, tS[3] = {0, 0, 0};
-    St7 st;
-    int r = make_st7(L, idx, idy, idz, B, baseC, loC, hiC, xI, st);
-    if (r > 0) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) tO[q] = gat7(st, pC + q * nC);
-    }
-    bad |= r < 0;
-    r = make_st7(L, idx, idy, idz, B, rowBase, rowLo, rowHi, xO, st);
-    if (r > 0) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) tO[q] += gat7(st, pA + q * nA);
-    }
-    bad |= r < 0;
-    {
-      const double rx = xO.x - cx, ry = xO.y - cy, rz = xO.z - cz;
-      tO[0] = fma(vp.x + (om.y * rz - om.z * ry), rdT, tO[0]);
-      tO[1] = fma(vp.y + (om.z * rx - om.x * rz), rdT, tO[1]);
-      tO[2] = fma(vp.z + (om.x * ry - om.y * rx), rdT, tO[2]);
-    }
-    r = make_st7(L, idx, idy, idz, B, baseB, loB, hiB, xS, st);
-    if (r > 0) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) tS[q] = gat7(st, pB + q * nB);
-    }
-    bad |= r < 0;
-    {
-      const double rx = xS.x - cx, ry = xS.y - cy, rz = xS.z - cz;
-      tS[0] = fma(vp.x + (om.y * rz - om.z * ry), rdT, tS[0]);
-      tS[1] = fma(vp.y + (om.z * rx - om.x * rz), rdT, tS[1]);
-      tS[2] = fma(vp.z + (om.x * ry - om.y * rx), rdT, tS[2]);
-    }
-    double* cv = colVal + 6 * s;
-    cv[0] = tO[0]; cv[1] = tO[1]; cv[2] = tO[2]; cv[3] = tS[0]; cv[4] = tS[1]; cv[5] = tS[2];
-  }
-  if (bad) atomicExch(guard, 1);
+  Col7Ctx X;
+  X.G = geo7(L); X.B = B; X.tab = tab;
+  X.baseA = rowBase; X.loA = rowLo; X.hiA = rowHi; X.baseB = baseB; X.loB = loB; X.hiB = hiB; X.baseC = baseC; X.loC = loC; X.hiC = hiC;
+  X.pA = pA; X.pB = pB; X.pC = pC;
+  X.cx = cx; X.cy = cy; X.cz = cz; X.rdT = rdT;
+  X.rI = rL[0]; X.rS = rL[1]; X.rO = rL[2];
+  X.vp = V3{in.v[0][b], in.v[1][b], in.v[2][b]}; X.om = V3{in.om[0][b], in.om[1][b], in.om[2][b]};
+  X.kind = sc.kind; X.nT = nT; X.nMap = nMap;
+  const int bad = B.edge ? columns7<true, NT>(X, colKey, nCol, colVal) : columns7<false, NT>(X, colKey, nCol, colVal);
+  if (bad) atomicExch(guardFlag, 1);
   __syncthreads();
 
   // ---- one thread per shell cell: F_i = sum_q (wI_q tO_q + wS_q tS_q)/W   (particleShape.C:113-131, particleIBM.C:230-263) ----
-  for (int t = threadIdx.x; t < nShell; t += V7_THREADS) {
+  const int nxy = L.nx * L.ny;
+  for (int t = threadIdx.x; t < nShell; t += NT) {
     const int lat = shellCell[off + t];
     const int pk = shellJK[off + t];
     const int j = pk & 0xffff, k = pk >> 16;
     const bool degBin = nk != 1 && k == nk - 1;
     const int jp1 = (j + 1) % nT, k1 = (nk != 1) ? k + 1 : k;
     const int jj[4] = {j, jp1, j, jp1}, kk[4] = {k, k, k1, k1};
-    const int I = lat % L.nx, J = (lat / L.nx) % L.ny, K = lat / (L.nx * L.ny);
+    const int K = lat / nxy, rem = lat - K * nxy, J = rem / L.nx, I = rem - J * L.nx;
     const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
     double wI[4], wS[4];
     int slot[4];
-    int first = -1, firstS = -1;  // one-hot rule of particleShape.C:121-127: first q (0..7) within SMALL wins; q < 4 are inner points
+    bool tiny = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int jq = degBin ? 0 : jj[q], kq = degBin ? 0 : kk[q];
@@ -442,14 +513,22 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       const V3 xS = degBin ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
       const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
       const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
-      wI[q] = rsqrt(dI2);
-      wS[q] = rsqrt(dS2);
-      if (dI2 < IBM_SMALL * IBM_SMALL && first < 0) first = q;
-      if (dS2 < IBM_SMALL * IBM_SMALL && firstS < 0) firstS = 4 + q;
+      tiny = tiny || dI2 < IBM_SMALL * IBM_SMALL || dS2 < IBM_SMALL * IBM_SMALL;
+      wI[q] = rsqrt7(fmax(dI2, 1e-300));
+      wS[q] = rsqrt7(fmax(dS2, 1e-300));
     }
-    if (first < 0) first = firstS;
-    if (first >= 0) {
-#pragma unroll
+    if (tiny) {  // one-hot rule of particleShape.C:121-127: the first q (0..7) within SMALL wins; q < 4 are inner points
+      int first = -1, firstS = -1;
+      for (int q = 0; q < 4; ++q) {
+        const int jq = degBin ? 0 : jj[q], kq = degBin ? 0 : kk[q];
+        const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
+        const V3 xS = degBin ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
+        const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
+        const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
+        if (dI2 < IBM_SMALL * IBM_SMALL && first < 0) first = q;
+        if (dS2 < IBM_SMALL * IBM_SMALL && firstS < 0) firstS = 4 + q;
+      }
+      if (first < 0) first = firstS;
       for (int q = 0; q < 4; ++q) { wI[q] = (first == q) ? 1.0 : 0.0; wS[q] = (first == 4 + q) ? 1.0 : 0.0; }
     }
     double Fx = 0.0, Fy = 0.0, Fz = 0.0, W = 0.0;
@@ -461,7 +540,7 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
       Fy = fma(wI[q], cv[1], fma(wS[q], cv[4], Fy));
       Fz = fma(wI[q], cv[2], fma(wS[q], cv[5], Fz));
     }
-    const double rW = 1.0 / W;
+    const double rW = rcp7(W);
     atomicAdd(&F[lat], Fx * rW);
     atomicAdd(&F[C + lat], Fy * rW);
     atomicAdd(&F[2 * C + lat], Fz * rW);
@@ -472,13 +551,72 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
 // K4 v7: surface-stress integral (particleIBM.C:541-581), one CTA per instance: p and the six devRhoReff components staged
 // on the reach of the surface layer only (the round-1 kernel staged the solid 11^3 box: 3.6x the bytes that are needed)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(V7_THREADS, 3)
+struct Str7Ctx {
+  Geo7 G; Box7 B; Tab7 tab;
+  const int *baseB, *loB, *hiB;
+  const double* planes;
+  double cx, cy, cz, R, delta, rS, pRefOverRho, rhoRef, sfScale;
+  double rot[9];
+  int kind, nT, nk;
+};
+
+template <bool EDGE, int NT>
+__device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
+  int guard = 0;
+  const int nSurf = X.nT * X.nk;
+  for (int s = threadIdx.x; s < nSurf; s += NT) {
+    const int i = s / X.nk, k = s - i * X.nk;
+    const int i2 = i + X.nT * k;
+    const V3 pt = tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, i, k);
+    double g[7] = {0, 0, 0, 0, 0, 0, 0};
+    double pp = 0.0;
+    St7 st;
+    if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, pt, st, guard)) {
+      gat7<7>(st, X.planes, g);
+      pp = (g[0] - 2.0 * st.c[0] * X.pRefOverRho) * X.rhoRef;
+#pragma unroll
+      for (int q = 1; q < 7; ++q) g[q] *= X.rhoRef;
+    }
+    const double* tau = g + 1;
+    // App. B #5: lever arm as coded, mesh_[index2(i,k)] read through index(i,j,k)
+    const int lay2 = i2 % 3, j2 = (i2 / 3) % X.nT, k2 = i2 / (3 * X.nT);
+    const double r2 = xadd(X.R, lay2 == 0 ? -1 * X.delta : (lay2 == 1 ? 0.0 : X.delta));
+    const V3 m2 = tab7_point(X.kind, X.tab, r2, X.cx, X.cy, X.cz, j2, k2);
+    const double Rx = m2.x - X.cx, Ry = m2.y - X.cy, Rz = m2.z - X.cz;
+    const double Rcx = pt.x - X.cx, Rcy = pt.y - X.cy, Rcz = pt.z - X.cz;
+    // Sf_[index2(i,k)]   (sphere.C:134-157, cylinder.C:116-122)
+    double sx, sy, sz;
+    if (X.kind == 0) {
+      const double f = X.sfScale * X.tab.ck[k];
+      sx = -(X.tab.cosT[i] * X.tab.sinP[k]) * f; sy = -(X.tab.sinT[i] * X.tab.sinP[k]) * f; sz = -X.tab.cosP[k] * f;
+    } else {
+      sx = -X.tab.cosT[i] * X.sfScale; sy = -X.tab.sinT[i] * X.sfScale; sz = 0.0;
+    }
+    const double* rot = X.rot;
+    const double Sx = rot[0] * sx + rot[1] * sy + rot[2] * sz, Sy = rot[3] * sx + rot[4] * sy + rot[5] * sz,
+                 Sz = rot[6] * sx + rot[7] * sy + rot[8] * sz;
+    const double rmag = rsqrt7(Sx * Sx + Sy * Sy + Sz * Sz);
+    const double nx = Sx * rmag, ny = Sy * rmag, nz = Sz * rmag;
+    const double fx = pp * sx + (tau[0] * Sx + tau[1] * Sy + tau[2] * Sz);  // App. B #6: unrotated Sf_ in the pressure term
+    const double fy = pp * sy + (tau[1] * Sx + tau[3] * Sy + tau[4] * Sz);
+    const double fz = pp * sz + (tau[2] * Sx + tau[4] * Sy + tau[5] * Sz);
+    const double fn = fx * nx + fy * ny + fz * nz;
+    const double ftx = fx - fn * nx, fty = fy - fn * ny, ftz = fz - fn * nz;
+    acc[0] += fx; acc[1] += fy; acc[2] += fz;
+    acc[3] -= fty * Rz - ftz * Ry; acc[4] -= ftz * Rx - ftx * Rz; acc[5] -= ftx * Ry - fty * Rx;
+    acc[6] -= fty * Rcz - ftz * Rcy; acc[7] -= ftz * Rcx - ftx * Rcz; acc[8] -= ftx * Rcy - fty * Rcx;
+  }
+  return guard;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
 k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
             const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
-            V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guard) {
+            V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
   extern __shared__ double smem7[];
-  __shared__ int wsum[V7_NWARP];
-  __shared__ double red[V7_NWARP][9];
+  __shared__ int wsum[2 * (NT / 32)];
+  __shared__ double red[NT / 32][9];
   if ((int)blockIdx.x >= nInst) return;
   const int b = order[blockIdx.x];
   const ShapeClassDev sc = classes[in.cls[b]];
@@ -500,36 +638,34 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   B.by = B.bz = 0;
   // Instances without local points (other slabs' instances on a multi-GPU run) do no work but MUST still write zero
   // partials below: their F/T slots hold last step's combined totals, and the cross-rank sum adds whatever is in them.
-  bool work = on;
-  if (work) {
+  if (on) {
     bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[1], B);
-    if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= 4 * V7_THREADS;
+    if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= NT;
     if (!fits) {
       if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
       return;  // the list kernel writes this instance's F/T
     }
   }
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (work) {
+  if (on) {
     const Tab7 tab = tab7_load(sc, tabD, cap);
     int nS[3];
-    build_region7(L, B, cx, cy, cz, rho, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);
+    build_region7<NT>(L, B, cx, cy, cz, rho, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);
     const int nB = nS[1];
     const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
-    if (7 * nB > cap.planeCap || nB > cap.elemCap) {
+    if (7 * nB > cap.planeCap || nB > cap.elemCap || nB > 65535) {
       if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
       return;
     }
-    {
-      const int rows = B.by * B.bz;
-      for (int r = threadIdx.x; r < rows; r += V7_THREADS) {
-        const int lo = loB[r], hi = hiB[r], o = baseB[r] + lo;
-        for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
-      }
+    if ((int)threadIdx.x < B.by * B.bz) {
+      const int r = threadIdx.x;
+      const int lo = loB[r], hi = hiB[r], o = baseB[r] + lo;
+      for (int x = lo; x <= hi; ++x) elemRow[o + x - lo] = (unsigned short)r;
     }
     __syncthreads();
     const size_t C = (size_t)L.nCells;
-    for (int a = threadIdx.x; a < nB; a += V7_THREADS) {
+#pragma unroll 2
+    for (int a = threadIdx.x; a < nB; a += NT) {
       const int row = elemRow[a];
       const int I = a - baseB[row];
       const size_t g = (size_t)(rowG[row] + I);
@@ -538,57 +674,19 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
 #pragma unroll
       for (int q = 0; q < 6; ++q) v[1 + q] = __ldg(Tau + q * C + g);
 #pragma unroll
-      for (int q = 0; q < 7; ++q) planes[q * nB + a] = v[q];
+      for (int q = 0; q < 7; ++q) planes[7 * a + q] = v[q];
     }
     __syncthreads();
-    double rot[9];
+    Str7Ctx X;
+    X.G = geo7(L); X.B = B; X.tab = tab;
+    X.baseB = baseB; X.loB = loB; X.hiB = hiB; X.planes = planes;
+    X.cx = cx; X.cy = cy; X.cz = cz; X.R = R; X.delta = sc.delta; X.rS = rho[1]; X.pRefOverRho = pRefOverRho; X.rhoRef = rhoRef;
+    X.sfScale = (sc.kind == 0) ? (R * R) * sc.dTheta : R * sc.dTheta * sc.l;
 #pragma unroll
-    for (int q = 0; q < 9; ++q) rot[q] = in.rot[9 * (size_t)b + q];
-    const double idx = 1.0 / L.dx, idy = 1.0 / L.dy, idz = 1.0 / L.dz;
-    const double sfScale = (sc.kind == 0) ? (R * R) * sc.dTheta : R * sc.dTheta * sc.l;
-    const int nSurf = nT * nk;
-    int bad = 0;
-    for (int s = threadIdx.x; s < nSurf; s += V7_THREADS) {
-      const int i = s / nk, k = s - i * nk;
-      const int i2 = i + nT * k;
-      const V3 pt = tab7_point(sc.kind, tab, rho[1], cx, cy, cz, i, k);
-      double tau[6] = {0, 0, 0, 0, 0, 0}, pp = 0.0;
-      St7 st;
-      const int r = make_st7(L, idx, idy, idz, B, baseB, loB, hiB, pt, st);
-      bad |= r < 0;
-      if (r > 0) {
-#pragma unroll
-        for (int cmp = 0; cmp < 6; ++cmp) tau[cmp] = gat7(st, planes + (1 + cmp) * nB) * rhoRef;
-        pp = (gat7(st, planes) - 2.0 * st.c[0] * pRefOverRho) * rhoRef;
-      }
-      // App. B #5: lever arm as coded, mesh_[index2(i,k)] read through index(i,j,k)
-      const int lay2 = i2 % 3, j2 = (i2 / 3) % nT, k2 = i2 / (3 * nT);
-      const double r2 = xadd(R, lay2 == 0 ? -1 * sc.delta : (lay2 == 1 ? 0.0 : sc.delta));
-      const V3 m2 = tab7_point(sc.kind, tab, r2, cx, cy, cz, j2, k2);
-      const double Rx = m2.x - cx, Ry = m2.y - cy, Rz = m2.z - cz;
-      const double Rcx = pt.x - cx, Rcy = pt.y - cy, Rcz = pt.z - cz;
-      // Sf_[index2(i,k)]   (sphere.C:134-157, cylinder.C:116-122)
-      double sx, sy, sz;
-      if (sc.kind == 0) {
-        const double f = sfScale * tab.ck[k];
-        sx = -(tab.cosT[i] * tab.sinP[k]) * f; sy = -(tab.sinT[i] * tab.sinP[k]) * f; sz = -tab.cosP[k] * f;
-      } else {
-        sx = -tab.cosT[i] * sfScale; sy = -tab.sinT[i] * sfScale; sz = 0.0;
-      }
-      const double Sx = rot[0] * sx + rot[1] * sy + rot[2] * sz, Sy = rot[3] * sx + rot[4] * sy + rot[5] * sz,
-                   Sz = rot[6] * sx + rot[7] * sy + rot[8] * sz;
-      const double rmag = rsqrt(Sx * Sx + Sy * Sy + Sz * Sz);
-      const double nx = Sx * rmag, ny = Sy * rmag, nz = Sz * rmag;
-      const double fx = pp * sx + (tau[0] * Sx + tau[1] * Sy + tau[2] * Sz);  // App. B #6: unrotated Sf_ in the pressure term
-      const double fy = pp * sy + (tau[1] * Sx + tau[3] * Sy + tau[4] * Sz);
-      const double fz = pp * sz + (tau[2] * Sx + tau[4] * Sy + tau[5] * Sz);
-      const double fn = fx * nx + fy * ny + fz * nz;
-      const double ftx = fx - fn * nx, fty = fy - fn * ny, ftz = fz - fn * nz;
-      acc[0] += fx; acc[1] += fy; acc[2] += fz;
-      acc[3] -= fty * Rz - ftz * Ry; acc[4] -= ftz * Rx - ftx * Rz; acc[5] -= ftx * Ry - fty * Rx;
-      acc[6] -= fty * Rcz - ftz * Rcy; acc[7] -= ftz * Rcx - ftx * Rcz; acc[8] -= ftx * Rcy - fty * Rcx;
-    }
-    if (bad) atomicExch(guard, 1);
+    for (int q = 0; q < 9; ++q) X.rot[q] = in.rot[9 * (size_t)b + q];
+    X.kind = sc.kind; X.nT = nT; X.nk = nk;
+    const int bad = B.edge ? stress_points7<true, NT>(X, acc) : stress_points7<false, NT>(X, acc);
+    if (bad) atomicExch(guardFlag, 1);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -600,7 +698,7 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   __syncthreads();
   if (threadIdx.x < 9) {
     double v = 0.0;
-    for (int w = 0; w < V7_NWARP; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < NT / 32; ++w) v += red[w][threadIdx.x];
     const int q = threadIdx.x;
     if (q < 3) in.F[q][b] = v;
     else if (q < 6) in.T[q - 3][b] = v;
@@ -673,13 +771,13 @@ bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses
     auto up = [](long long v) { return (int)std::min<long long>((v + v / 16 + 16 + 1) & ~1LL, 0x3fffffff); };
     f.planeCap = std::max(f.planeCap, up(3 * (nA + nB + nC)));
     f.colCap = std::max(f.colCap, (int)std::min<long long>(colEst, 65535));
-    f.rowsCap = std::max(f.rowsCap, (int)std::min<long long>(rowsOf(R + sc.delta), 4 * V7_THREADS));
+    f.rowsCap = std::max(f.rowsCap, (int)std::min<long long>(rowsOf(R + sc.delta), 192));
     f.mapCap = std::max<long long>(f.mapCap, std::min<long long>((long long)sc.nTheta * sc.nk + 1, 1 << 20));
     f.nTcap = std::max(f.nTcap, sc.nTheta);
     f.nkCap = std::max(f.nkCap, sc.nk);
     f.elemCap = std::max(f.elemCap, up(nA));
     s.planeCap = std::max(s.planeCap, up(7 * nB));
-    s.rowsCap = std::max(s.rowsCap, (int)std::min<long long>(rowsOf(R), 4 * V7_THREADS));
+    s.rowsCap = std::max(s.rowsCap, (int)std::min<long long>(rowsOf(R), 192));
     s.nTcap = f.nTcap; s.nkCap = f.nkCap;
     s.elemCap = std::max(s.elemCap, up(nB));
     any = true;
@@ -687,9 +785,44 @@ bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses
   s.colCap = 0; s.mapCap = 0;
   if (!any) return false;
   if (v7_layout(f).total > SMEM_BUDGET_F || v7_layout(s).total > SMEM_BUDGET_S) return false;
-  if (f.elemCap > 65535 * 8 || f.rowsCap > 65535) return false;
+  if (f.elemCap > 65535 || s.elemCap > 65535) return false;
   forcing = f; stress = s;
   return true;
+}
+
+static int v7_threads() {
+  static int nt = -1;
+  if (nt < 0) {
+    const char* e = getenv("IBM_V7_THREADS");
+    nt = e ? atoi(e) : 256;
+    if (nt != 256 && nt != 320 && nt != 192) nt = 256;
+  }
+  return nt;
+}
+
+template <int NT>
+static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                          const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
+                          double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard, int sm) {
+  static PerDeviceOnce attr;
+  static int attrBytes = 0;
+  if (attr.first() || sm > attrBytes) {
+    cudaFuncSetAttribute(k_forcing_v7<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    attrBytes = std::max(attrBytes, sm);
+  }
+  k_forcing_v7<NT><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
+}
+template <int NT>
+static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const Schedule& s,
+                         const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, const V7Caps& cap, int* slowList,
+                         int* slowCount, int* guard, int sm) {
+  static PerDeviceOnce attr;
+  static int attrBytes = 0;
+  if (attr.first() || sm > attrBytes) {
+    cudaFuncSetAttribute(k_stress_v7<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    attrBytes = std::max(attrBytes, sm);
+  }
+  k_stress_v7<NT><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
 }
 
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
@@ -697,15 +830,11 @@ void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
                        const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
   if (nInst <= 0) return;
   const int sm = v7_layout(cap).total;
-  static PerDeviceOnce attr;
-  static int attrBytes = 0;
-  if (attr.first() || sm > attrBytes) {
-    cudaFuncSetAttribute(k_forcing_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    attrBytes = std::max(attrBytes, sm);
-  }
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
-  k_forcing_v7<<<nInst, V7_THREADS, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList,
-                                              slowCount, guard);
+  const int nt = v7_threads();
+  if (nt == 320) forcing_v7_nt<320>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+  else if (nt == 192) forcing_v7_nt<192>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+  else forcing_v7_nt<256>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
   launch_forcing_v2_list(st, L, classes, in, slowList, slowCount, shellCell, shellJK, U, Uold, S, dT, F);
 }
 
@@ -714,15 +843,11 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
                       const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
   if (nInst <= 0) return;
   const int sm = v7_layout(cap).total;
-  static PerDeviceOnce attr;
-  static int attrBytes = 0;
-  if (attr.first() || sm > attrBytes) {
-    cudaFuncSetAttribute(k_stress_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    attrBytes = std::max(attrBytes, sm);
-  }
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
-  k_stress_v7<<<nInst, V7_THREADS, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount,
-                                             guard);
+  const int nt = v7_threads();
+  if (nt == 320) stress_v7_nt<320>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
+  else if (nt == 192) stress_v7_nt<192>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
+  else stress_v7_nt<256>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
   launch_stress_v2_list(st, L, classes, in, slowList, slowCount, P, Tau, pRefOverRho, rhoRef, Tcorr);
 }
 

@@ -82,6 +82,17 @@ struct MotionDev {
   int* violated;                   // an active instance moved farther than its B_i: the step is redone without the split
   int* noSplit;                    // the start configuration defeats the classification (see k5q_ghosts): everything is active
   double safety, check;            // budget factor; fraction of B_i the check allows (1 except in tests of the fallback)
+  // cluster mode of the split (option cluster_loop5, k5c_*): the active instances are partitioned into groups that cannot
+  // interact with one another during the step; every group runs ALL its sub-steps inside one thread block
+  int* edgeA; int* edgeB; int* nEdge; int edgeCap;   // pairs of active instances that may interact this step
+  int* label;                      // [cap] component root of an active instance
+  int* compCnt; int* compOff; int* compCur;  // [cap] members per root, exclusive offsets, placement cursors
+  int* sorted;                     // [cap] active instances grouped by component
+  int* ctaBegin; int* ctaEnd;      // [ctaBins] range of `sorted` a block of k5c_run owns
+  int ctaBins;
+  int* nextSlot;                   // next free instance slot (copies created by the blocks take provisional slots)
+  int* evSub; int* evKey;          // [cap] per provisional slot: sub-step of creation, patchSlot * cap + position of the source
+  int* clusterFail;                // a block ran out of room (members, candidates, hits): the step is redone unsplit
 };
 
 struct Motion {
@@ -115,6 +126,10 @@ struct Motion {
   bool splitAllowed = true;     // every cyclic patch is a pure translation (k5q_ghosts needs the image of a centre)
   long long nFallbacks = 0;
   int lastActive = 0;           // active instances of the previous split step (sizes the grid of k5a_fused)
+  void* scanTemp = nullptr; size_t scanTempBytes = 0;  // cub::DeviceScan scratch of the cluster mode
+  int* hEv = nullptr;           // pinned: creation records of the copies of a step (ordering them is a host-side sort)
+  int* dPerm = nullptr;         // [cap] provisional slot (relative) that goes to final slot r
+  long long nClusterSteps = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1114,6 +1129,345 @@ __global__ void k5q_snapshot(MotionDev m, InstanceSoA in, double* __restrict__ s
   if (i < m.nParticles) {
     if (restore) m.maxCopies[i] = snapMaxCopies[i]; else snapMaxCopies[i] = m.maxCopies[i];
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Cluster mode of the quiet / active split (option cluster_loop5).
+//
+// The split above still pays ~7 dependent launches (or 3-4 grid-wide barriers) per sub-step, 101 times per fluid step,
+// whatever the size of the active list: loop 5 is LATENCY bound.  But the classification knows more than "active": two
+// active instances can only influence each other during the step if they are linked by a chain of possible interactions
+// (a pair within (Dmax_i + Dmax_j)/2 + B_i + B_j, an image of one within reach of the other, the instances of one index).
+// The connected components of that graph are independent, so every component runs ALL its sub-steps inside ONE thread
+// block with block-level barriers — no kernel boundary, no grid barrier, as many blocks as there are groups of components:
+//
+//   k5c_edges        active instance -> its possible partners (the very cut-offs of k5q_classify) and its group head
+//   k5c_components   connected components (hook roots + pointer jumping, one block)
+//   k5c_count/place  members grouped by component, components packed into blocks by their offset
+//   k5c_run          per block: the sub-step loop of particleCloud::solve over its members with the same device functions
+//                    as every other mode (d5_pair_eval, d5_rows_finish, d5_walls, d5_merge, d5_cyclic_*, d5_solve,
+//                    d5_set_positions); candidates of a pair search are the members of the same component
+//   host             periodic copies created by different blocks took provisional slots in arbitrary order: their creation
+//                    records (sub-step, patch, source) are sorted into the reference's append order and the new instances
+//                    permuted accordingly (the order within one index group, which the physics depends on, is already
+//                    the reference's inside a block).
+// The budgets are CHECKED as in the plain split; a violation, or a block that runs out of room, redoes the step unsplit.
+// ------------------------------------------------------------------------------------------------
+#define K5C_THREADS 128
+#define K5C_CAP 256        // members a block can hold (including the copies it creates)
+#define K5C_FILL 96        // components are assigned to blocks by offset / K5C_FILL
+#define K5C_CAND 96
+#define K5C_HIT 48
+
+__device__ __forceinline__ void k5c_emit(const MotionDev& m, int a, int b) {
+  const int h = atomicAdd(m.nEdge, 1);
+  if (h < m.edgeCap) { m.edgeA[h] = a; m.edgeB[h] = b; }
+  else atomicExch(m.clusterFail, 1);
+}
+
+// possible partners of every active instance: same scan and cut-offs as k5q_classify, all hits instead of the first
+__global__ void k5c_edges(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *m.nAct) return;
+  const int i = m.act[t];
+  m.label[i] = i;
+  if (in.onMesh[i] == 0) return;
+  const int head = m.idxHead[in.index[i]];
+  if (head >= 0 && head != i) k5c_emit(m, i, head);
+  if (!m.moving) return;
+  const double S = split_S(m);
+  if (*m.noSplit || 2.0 * S > m.binEdge) { atomicExch(m.clusterFail, 1); return; }  // everything is active for lack of a bound: no clusters
+  const ShapeClassDev* sc = classes + in.cls[i];
+  const D3 c = ld3(in.c, i);
+  const double Bi = m.bud[i], di = dmax_of(*sc);
+  int bx, by, bz;
+  bin_of(m, c, bx, by, bz);
+  for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
+    for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
+      for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
+        const int bin = x + m.nbx * (y + m.nby * z);
+        const int nb = m.binCnt[bin];
+        if (nb > m.binCap) { atomicExch(m.clusterFail, 1); continue; }
+        for (int q = 0; q < nb; ++q) {
+          const size_t o = (size_t)bin * m.binCap + q;
+          int j, mult;
+          bin_entry(m.binItems[o], j, mult);
+          if (j == i) continue;
+          const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + Bi + mult * m.bud[j];
+          const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+          if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) k5c_emit(m, i, j);
+        }
+      }
+}
+
+// connected components of the active instances: label[i] = smallest instance of the component (one block)
+__global__ void __launch_bounds__(1024) k5c_components(MotionDev m) {
+  __shared__ int changed;
+  const int nE = min(*m.nEdge, m.edgeCap), nA = *m.nAct;
+  // an edge may name an instance that is NOT in the active list only if the classification is inconsistent: guard
+  for (int e = threadIdx.x; e < nE; e += blockDim.x)
+    if (m.quiet[m.edgeB[e]] || m.quiet[m.edgeA[e]]) atomicExch(m.clusterFail, 1);
+  __syncthreads();
+  if (*m.clusterFail) return;
+  for (int it = 0; it < 4096; ++it) {
+    if (threadIdx.x == 0) changed = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < nE; e += blockDim.x) {
+      const int ra = m.label[m.edgeA[e]], rb = m.label[m.edgeB[e]];  // roots after the compression below
+      if (ra != rb) { atomicMin(&m.label[max(ra, rb)], min(ra, rb)); changed = 1; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nA; t += blockDim.x) {
+      const int i = m.act[t];
+      int l = m.label[i];
+      while (m.label[l] != l) l = m.label[l];
+      m.label[i] = l;
+    }
+    __syncthreads();
+    if (!changed) break;
+    __syncthreads();
+  }
+}
+
+__global__ void k5c_count(MotionDev m) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *m.nAct) return;
+  atomicAdd(&m.compCnt[m.label[m.act[t]]], 1);
+}
+__global__ void k5c_place(MotionDev m) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *m.nAct) return;
+  const int i = m.act[t], r = m.label[i];
+  m.sorted[m.compOff[r] + atomicAdd(&m.compCur[r], 1)] = i;
+  if (i == r) {  // the root places its component into a block
+    const int off = m.compOff[r], cnt = m.compCnt[r];
+    const int b = off / K5C_FILL;
+    if (b >= m.ctaBins) { atomicExch(m.clusterFail, 1); return; }
+    atomicMin(&m.ctaBegin[b], off);
+    atomicMax(&m.ctaEnd[b], off + cnt);
+  }
+}
+
+// every sub-step of a quiet instance by one thread, state in registers: the arithmetic of d5_solve with empty contact and
+// wall tables (sums of nothing are exact zeros, particleIBM.C:408-414), operation for operation
+__global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts,
+                          int nSub) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *m.nInst || !m.quiet[i] || in.onMesh[i] == 0) return;
+  const ShapeClassDev* sc = classes + in.cls[i];
+  const double mass = sc->V * in.rho[i];
+  const D3 Fh = ld3(in.F, i), Th = ld3(in.T, i);
+  D3 v = ld3(in.v, i), c = ld3(in.c, i), om = ld3(in.om, i), th = ld3(in.th, i);
+  const double mI = mass * sc->I;
+  for (int s = 0; s < nSub; ++s) {
+    const double dt = dts[s];
+    if (m.moving) {
+      D3 sFc{0, 0, 0}, sFw{0, 0, 0};
+      for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
+      const D3 F = Fh + sFc + sFw;
+      v = v + dt * (F / mass + D3{m.gx, m.gy, m.gz});
+      const D3 dx = dt * v;
+      c = c + dx;
+    }
+    if (m.rotating) {
+      D3 sTc{0, 0, 0}, sTw{0, 0, 0};
+      for (int w = 0; w < m.nWalls; ++w) sTw = sTw + D3{0.0, 0.0, 0.0};
+      const D3 T = Th + sTc + sTw;
+      om = om + dt * T / mI;
+      th = th + om * dt;
+      if (th.z < 0) th.z += IBM_TWOPI;
+      if (th.z >= IBM_TWOPI) th.z -= IBM_TWOPI;
+    }
+  }
+  if (nSub > 0) {
+    if (m.moving) {
+      st3(in.v, i, v); st3(in.c, i, c);
+      int I, J, K;
+      in.active[i] = find_cell(L, c.x, c.y, c.z, I, J, K) >= 0;
+    }
+    if (m.rotating) { st3(in.om, i, om); st3(in.th, i, th); }
+  }
+}
+
+struct K5cShared {
+  int mem[K5C_CAP];       // instance (cloud position or provisional slot) of every member
+  int comp[K5C_CAP];      // its component root
+  int candKey[K5C_CAND];
+  int hitKey[K5C_HIT];
+  double hitCenter[3 * K5C_HIT];
+  int nMem, candCount, hitCount, bigN, base, fail;
+};
+
+__global__ void __launch_bounds__(K5C_THREADS)
+k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
+        int doCyclic, int n0) {
+  __shared__ K5cShared sh;
+  const int b = blockIdx.x;
+  if (b >= m.ctaBins) return;
+  const int beg = m.ctaBegin[b], end = m.ctaEnd[b];
+  if (end <= beg) return;
+  if (*m.clusterFail) return;
+  const int tid = threadIdx.x;
+  if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
+  if (tid == 0) { sh.nMem = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0; }
+  for (int t = tid; t < end - beg; t += K5C_THREADS) { const int i = m.sorted[beg + t]; sh.mem[t] = i; sh.comp[t] = m.label[i]; }
+  __syncthreads();
+  // this block's view of the motion data: private candidate / hit lists, no instance-count bound (members are valid by construction)
+  MotionDev ml = m;
+  ml.nInst = &sh.bigN;
+  ml.candCount = &sh.candCount; ml.candKey = sh.candKey; ml.candCap = K5C_CAND;
+  ml.hitCount = &sh.hitCount; ml.hitKey = sh.hitKey; ml.hitCenter = sh.hitCenter;
+  ml.overflow = &sh.fail;
+  const bool copies = m.nCyc > 0;
+  const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
+  for (int s = 0; s < nSub; ++s) {
+    const double dt = dts[s];
+    if (m.moving) {
+      const int nMem = sh.nMem;
+      for (int t = tid; t < nMem; t += K5C_THREADS) {
+        const int i = sh.mem[t];
+        if (in.onMesh[i] != 0) {
+          const D3 c = ld3(in.c, i);
+          const int comp = sh.comp[t];
+          for (int u = 0; u < nMem; ++u) {
+            if (u == t || sh.comp[u] != comp) continue;
+            const int j = sh.mem[u];
+            const D3 dd = ld3(in.c, j) - c;
+            if (dd.x * dd.x + dd.y * dd.y + dd.z * dd.z > cut) continue;  // the bin neighbourhood's cut-off (d5_find_pairs)
+            if (in.onMesh[j] == 0) continue;                               // (off-mesh instances are never entered into the bins)
+            d5_pair_eval(ml, in, classes, dt, i, j);
+          }
+          d5_rows_finish(ml, in, i);
+          if (m.nWalls > 0) d5_walls(ml, L, in, classes, dt, i);
+          if (doCyclic) d5_cyclic_candidates(ml, in, classes, i);
+        }
+      }
+      __syncthreads();  // rows complete before anybody merges them or moves a centre
+      if (copies) {
+        for (int t = tid; t < nMem; t += K5C_THREADS) d5_merge(ml, in, sh.mem[t]);
+        if (doCyclic) d5_cyclic_detect(ml, L, in, classes, tid, K5C_THREADS);
+        __syncthreads();
+        if (doCyclic) {
+          const int total = sh.hitCount;
+          if (total > 0) {
+            // provisional slots for the new copies, in this block's (patch, source) order: the reference's order among the
+            // instances this block owns; the order across blocks is settled on the host after the step
+            if (tid == 0) {
+              int base = -1;
+              if (total <= K5C_HIT && sh.nMem + total <= K5C_CAP) {
+                base = atomicAdd(m.nextSlot, total);
+                if (base + total > m.cap) base = -1;
+              }
+              sh.base = base;
+              if (base < 0) { sh.fail = 9; sh.hitCount = 0; sh.candCount = 0; }
+            }
+            __syncthreads();
+            const int base = sh.base;
+            if (base >= 0) {
+              for (int h = tid; h < total; h += K5C_THREADS) {
+                const int key = sh.hitKey[h];
+                int rank = 0;
+                for (int q = 0; q < total; ++q) rank += sh.hitKey[q] < key;
+                const int src = key % m.cap, dst = base + rank;
+                const int idx = in.index[src];
+                in.index[dst] = idx;
+                in.copy[dst] = -1;
+                in.active[dst] = 0;
+                in.onMesh[dst] = IBM_PARTIAL;
+                in.cls[dst] = m.origCls[idx];
+                for (int q = 0; q < 3; ++q) {
+                  in.c[q][dst] = sh.hitCenter[3 * h + q];
+                  in.th[q][dst] = in.th[q][src];
+                  in.v[q][dst] = in.v[q][src];
+                  in.om[q][dst] = in.om[q][src];
+                  in.F[q][dst] = 0.0;  // integratedForce_ of origParticles_[index] (never updated after construction)
+                  in.T[q][dst] = 0.0;
+                  m.c0[(size_t)q * m.cap + dst] = sh.hitCenter[3 * h + q];
+                }
+                in.rho[dst] = m.origRho[idx];
+                in.age[dst] = in.age[src];
+                in.nShell[dst] = 0; in.shellOff[dst] = 0; in.nPtsOnMesh[dst] = 0;
+                rot_from_theta(in.th[0][src], in.th[1][src], in.th[2][src], in.rot + 9 * (size_t)dst);
+                m.bud[dst] = m.bud[src];
+                m.quiet[dst] = 0;
+                m.cCnt[dst] = 0;
+                m.cCnt2[dst] = 0;
+                for (int w = 0; w < m.nWalls; ++w)
+                  for (int q = 0; q < 3; ++q) {
+                    const size_t o = 3 * ((size_t)dst * m.nWalls + w) + q;
+                    m.Fw[o] = 0.0; m.Tw[o] = 0.0; m.Fw2[o] = 0.0; m.Tw2[o] = 0.0;
+                  }
+                m.evSub[dst] = s;
+                m.evKey[dst] = key;
+                // the copy joins the component of its source
+                int compSrc = 0;
+                for (int u = 0; u < sh.nMem; ++u) if (sh.mem[u] == src) compSrc = sh.comp[u];
+                sh.mem[sh.nMem + rank] = dst;
+                sh.comp[sh.nMem + rank] = compSrc;
+              }
+              __syncthreads();
+              if (tid == 0) {  // sequential part: copy ids and the same-index lists, in append order (d5_append_link)
+                for (int t2 = 0; t2 < total; ++t2) {
+                  const int dst = base + t2;
+                  const int idx = in.index[dst];
+                  in.copy[dst] = m.maxCopies[idx] + 1;
+                  m.maxCopies[idx] += 1;
+                  m.instNext[dst] = -1;
+                  const int tail = m.idxTail[idx];
+                  if (tail >= 0) m.instNext[tail] = dst; else m.idxHead[idx] = dst;
+                  m.idxTail[idx] = dst;
+                }
+                sh.nMem += total;
+                sh.hitCount = 0;
+                sh.candCount = 0;
+              }
+            }
+            __syncthreads();
+          } else if (tid == 0) {
+            sh.candCount = 0;
+          }
+        }
+      }
+    }
+    {
+      const int nMem = sh.nMem;
+      for (int t = tid; t < nMem; t += K5C_THREADS) {
+        const int i = sh.mem[t];
+        d5_solve(ml, L, in, classes, dt, copies ? m.cCnt2 : m.cCnt, copies ? m.cIdx2 : m.cIdx, copies ? m.cF2 : m.cF, copies ? m.cT2 : m.cT,
+                 copies ? m.Fw2 : m.Fw, copies ? m.Tw2 : m.Tw, m.cCnt, m.cCnt2, i);
+        const double B = m.check * m.bud[i];
+        const D3 d0 = ld3(in.c, i) - D3{m.c0[i], m.c0[(size_t)m.cap + i], m.c0[2 * (size_t)m.cap + i]};
+        if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
+      }
+    }
+    __syncthreads();  // every centre final
+    if (copies) {
+      const int nMem = sh.nMem;
+      for (int t = tid; t < nMem; t += K5C_THREADS) {
+        const int i = sh.mem[t];
+        if (m.idxHead[in.index[i]] == i) d5_set_positions(ml, in, in.index[i]);  // the first instance of a group does the group
+      }
+      __syncthreads();
+    }
+    if (sh.fail) break;  // (block-uniform: written before the last barrier)
+  }
+  if (tid == 0 && sh.fail) atomicExch(m.clusterFail, 1);
+}
+
+// new instances [n0, n0 + total) into the reference's append order: dst slot n0 + r takes provisional slot n0 + perm[r]
+__global__ void k5c_permute(InstanceSoA s, InstanceSoA d, const int* __restrict__ perm, int n0, int total, int back) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total) return;
+  const int i = back ? n0 + r : n0 + perm[r], j = n0 + r;
+  d.index[j] = s.index[i]; d.copy[j] = s.copy[i]; d.active[j] = s.active[i]; d.onMesh[j] = s.onMesh[i]; d.cls[j] = s.cls[i];
+  d.nShell[j] = s.nShell[i]; d.shellOff[j] = s.shellOff[i]; d.nPtsOnMesh[j] = s.nPtsOnMesh[i]; d.onLocal[j] = s.onLocal[i];
+  d.rho[j] = s.rho[i]; d.age[j] = s.age[i];
+  for (int q = 0; q < 3; ++q) {
+    d.c[q][j] = s.c[q][i]; d.th[q][j] = s.th[q][i]; d.v[q][j] = s.v[q][i]; d.om[q][j] = s.om[q][i];
+    d.F[q][j] = s.F[q][i]; d.T[q][j] = s.T[q][i];
+  }
+  for (int q = 0; q < 9; ++q) d.rot[9 * (size_t)j + q] = s.rot[9 * (size_t)i + q];
 }
 
 // ------------------------------------------------------------------------------------------------

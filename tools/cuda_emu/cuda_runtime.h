@@ -200,6 +200,7 @@ inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o)
 inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
 inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { unsigned o = *p; if (o == c) *p = v; return o; }
 inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
+inline int __double2loint(double d) { long long l; std::memcpy(&l, &d, 8); return (int)(unsigned)(l & 0xffffffffLL); }
 inline long long __double_as_longlong(double d) { long long l; std::memcpy(&l, &d, 8); return l; }
 inline double __longlong_as_double(long long l) { double d; std::memcpy(&d, &l, 8); return d; }
 using std::fabs;
