@@ -453,6 +453,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_GRAPH_LOOP5")) c->graphLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_CLUSTER_LOOP5")) c->clusterLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_MARK_VARIANT")) c->markVariant = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("IBM_KERNEL_VARIANT")) {  // "f,s": forcing / stress kernel generation (like ibm_set_kernel_variant)
     int f = 0, s2 = 0;
@@ -1044,14 +1045,10 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "graph_loop5") == 0) { c->graphLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
   if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "cluster_loop5") == 0) { c->clusterLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_check_ppm") == 0) { c->activeCheckPpm = value; return IBM_OK; }
-  if (std::strcmp(name, "v7_col_cap") == 0) {  // test hook: shrink the column capacity of the staged forcing kernel (exercises the list path)
-    if (value < 0) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: v7_col_cap >= 0");
-    c->v7capF.colCap = std::min(c->v7capF.colCap, value);
-    return IBM_OK;
-  }
   if (std::strcmp(name, "v7_plane_cap") == 0) {  // test hook: same for the staged planes (forcing and stress)
     if (value < 0) return ctx_fail(c, IBM_E_ARG, "ibm_set_option: v7_plane_cap >= 0");
     c->v7capF.planeCap = std::min(c->v7capF.planeCap, value);

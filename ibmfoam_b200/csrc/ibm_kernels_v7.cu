@@ -140,16 +140,16 @@ __device__ __forceinline__ void block_scan7(int& v0, int& v1, int* wsum, int& to
 }
 
 // own x-range of row (J,K) for a layer of radius rho around (cx,cy,cz): cells whose box intersects the closed ball
-__device__ __forceinline__ void own_range7(const LatticeDev& L, double cx, double cy, double cz, double rho, int J, int K, int& lo, int& hi) {
+__device__ __forceinline__ void own_range7(const LatticeDev& L, double idx, double cx, double cy, double cz, double rho, int J, int K, int& lo, int& hi) {
   const double ylo = L.oy + J * L.dy, yhi = L.oy + (J + 1) * L.dy;
   const double zlo = L.oz + (K + L.kz0) * L.dz, zhi = L.oz + (K + L.kz0 + 1) * L.dz;
   const double ey = fmax(fmax(ylo - cy, cy - yhi), 0.0), ez = fmax(fmax(zlo - cz, cz - zhi), 0.0);
-  const double re = rho * (1.0 + 1e-9) + 1e-9 * L.dx;  // rounding of the point coordinates and of the cell search
+  const double re = rho * (1.0 + 1e-9) + 1e-9 * L.dx;  // rounding of the point coordinates, of the cell search and of the products below
   const double h2 = re * re - ey * ey - ez * ez;
   if (h2 < 0.0) { lo = 1; hi = 0; return; }
   const double h = sqrt(h2);
-  lo = (int)floor((cx - h - L.ox) / L.dx);
-  hi = (int)floor((cx + h - L.ox) / L.dx);
+  lo = (int)floor((cx - h - L.ox) * idx);
+  hi = (int)floor((cx + h - L.ox) * idx);
 }
 
 // cell index along one axis and the position inside the cell (fraction of the cell size).  floor(q * inv) equals
@@ -224,11 +224,16 @@ __device__ __forceinline__ bool make_st7(const Geo7& G, const Box7& B, const int
     for (int d = 0; d < 6; ++d) w[d] = rsqrt7(d2[d]);
   }
   double W = ((w[0] + w[1]) + (w[2] + w[3])) + (w[4] + w[5]);
-  if (W > 0.5e15) {  // a face centre within SMALL of the point: one-hot on the first such face (particleShape.C:69-77)
-    int hot = -1;
+  if (!(W <= 0.5e15)) {  // a face centre within SMALL of the point (the seeded rsqrt7 turns d2 = 0 into NaN: caught here too)
+    int hot = -1;        // one-hot on the first such face (particleShape.C:69-77)
+    const bool ok6[6] = {!EDGE || I + 1 < G.nx, !EDGE || I > 0, !EDGE || J + 1 < G.ny, !EDGE || J > 0, !EDGE || K + 1 < G.nz, !EDGE || K > 0};
+    W = 0.0;
 #pragma unroll
-    for (int d = 0; d < 6; ++d)
-      if (w[d] > 0.0 && d2[d] < IBM_SMALL * IBM_SMALL && hot < 0) hot = d;
+    for (int d = 0; d < 6; ++d) {
+      w[d] = ok6[d] ? rsqrt(d2[d]) : 0.0;  // library version: exact handling of 0
+      if (ok6[d] && d2[d] < IBM_SMALL * IBM_SMALL && hot < 0) hot = d;
+      W += w[d];
+    }
     if (hot >= 0) {
 #pragma unroll
       for (int d = 0; d < 6; ++d) w[d] = (d == hot) ? 1.0 : 0.0;
@@ -263,10 +268,11 @@ __device__ __forceinline__ void build_region7(const LatticeDev& L, const Box7& B
   const int rows = B.by * B.bz;
   const int r = threadIdx.x;
   const int bj = r % B.by, bk = r / B.by;
+  const double idx = 1.0 / L.dx;
   if (r < rows) {
     for (int s = first; s <= last; ++s) {
       int lo, hi;
-      own_range7(L, cx, cy, cz, rho[s], B.j0 + bj, B.k0 + bk, lo, hi);
+      own_range7(L, idx, cx, cy, cz, rho[s], B.j0 + bj, B.k0 + bk, lo, hi);
       rowLo[s * rowsCap + r] = lo;
       rowHi[s * rowsCap + r] = hi;
     }
@@ -307,9 +313,11 @@ __device__ __forceinline__ void build_region7(const LatticeDev& L, const Box7& B
 }
 
 __device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, double cy, double cz, double reach, Box7& B) {
-  const int i0 = (int)floor((cx - reach - L.ox) / L.dx) - 1, i1 = (int)floor((cx + reach - L.ox) / L.dx) + 1;
-  const int j0 = (int)floor((cy - reach - L.oy) / L.dy) - 1, j1 = (int)floor((cy + reach - L.oy) / L.dy) + 1;
-  const int k0 = (int)floor((cz - reach - L.oz) / L.dz) - 1 - L.kz0, k1 = (int)floor((cz + reach - L.oz) / L.dz) + 1 - L.kz0;
+  const double re = reach * (1.0 + 1e-9) + 1e-9 * L.dx;  // (covers the rounding of the products with the inverse spacings)
+  const double ix = 1.0 / L.dx, iy = 1.0 / L.dy, iz = 1.0 / L.dz;
+  const int i0 = (int)floor((cx - re - L.ox) * ix) - 1, i1 = (int)floor((cx + re - L.ox) * ix) + 1;
+  const int j0 = (int)floor((cy - re - L.oy) * iy) - 1, j1 = (int)floor((cy + re - L.oy) * iy) + 1;
+  const int k0 = (int)floor((cz - re - L.oz) * iz) - 1 - L.kz0, k1 = (int)floor((cz + re - L.oz) * iz) + 1 - L.kz0;
   B.j0 = max(j0, 0); B.k0 = max(k0, 0);
   B.by = min(j1, L.ny - 1) - B.j0 + 1;
   B.bz = min(k1, L.nz - 1) - B.k0 + 1;
@@ -321,52 +329,103 @@ __device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, doub
 // ------------------------------------------------------------------------------------------------
 // K2/K3 v7: direct forcing, one CTA per instance
 // ------------------------------------------------------------------------------------------------
-struct Col7Ctx {
+struct Task7Ctx {
   Geo7 G; Box7 B; Tab7 tab;
   const int *baseA, *loA, *hiA, *baseB, *loB, *hiB, *baseC, *loC, *hiC;
   const double *pA, *pB, *pC;
   double cx, cy, cz, rdT;
   double rI, rS, rO;
   V3 vp, om;
-  int kind, nT, nMap;
+  int kind, nT, nk;
 };
 
+// The shell cells of the instance, four lanes per cell (one per corner column of its polar bin): each lane evaluates the
+// three gather stencils of its column and weighs the two column terms with the cell's inverse distances to the inner and
+// surface points (particleShape.C:113-131); the four lanes are summed by two shuffles and lane 0 adds F_i to the field
+// (particleIBM.C:230-263).  A d = 8 sphere has 584 distinct columns for 4 x 155 corner references: sharing columns between
+// cells would save 6 % of the stencils and cost a 32 KB table, a compaction pass and a barrier.
 template <bool EDGE, int NT>
-__device__ __forceinline__ int columns7(const Col7Ctx& X, const int* __restrict__ colKey, int nCol, double* __restrict__ colVal) {
+__device__ __forceinline__ int cells7(const Task7Ctx& X, const int* __restrict__ shellCell, const int* __restrict__ shellJK, int nShell,
+                                      size_t C, double* __restrict__ F) {
   int guard = 0;
-  for (int s = threadIdx.x; s < nCol; s += NT) {
-    const int key = colKey[s];
-    const int jq = key & 0xffff, kq = key >> 16;
-    const bool deg = kq == 0x7fff;
-    // (a degenerate bin uses point 0 = the inner point of (0,0) for all three roles, particleShape.C:148)
-    const V3 xI = tab7_point(X.kind, X.tab, X.rI, X.cx, X.cy, X.cz, deg ? 0 : jq, deg ? 0 : kq);
-    const V3 xS = deg ? xI : tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, jq, kq);
-    const V3 xO = deg ? xI : tab7_point(X.kind, X.tab, X.rO, X.cx, X.cy, X.cz, jq, kq);
-    double tO[3] = {0, 0, 0}, tS[3] = {0, 0, 0}, g[3];
-    St7 st;
-    if (make_st7<EDGE>(X.G, X.B, X.baseC, X.loC, X.hiC, xI, st, guard)) { gat7<3>(st, X.pC, tO); }
-    if (make_st7<EDGE>(X.G, X.B, X.baseA, X.loA, X.hiA, xO, st, guard)) { gat7<3>(st, X.pA, g); tO[0] += g[0]; tO[1] += g[1]; tO[2] += g[2]; }
-    {
-      const double rx = xO.x - X.cx, ry = xO.y - X.cy, rz = xO.z - X.cz;
-      tO[0] = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tO[0]);
-      tO[1] = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tO[1]);
-      tO[2] = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tO[2]);
+  const int nTask = 4 * nShell;
+  const int nxy = X.G.nx * X.G.ny;
+  for (int base = 0; base < nTask; base += NT) {
+    const int task = base + threadIdx.x;
+    const bool valid = task < nTask;
+    double fx = 0.0, fy = 0.0, fz = 0.0, wsum = 0.0, tOx = 0.0, tOy = 0.0, tOz = 0.0, tSx = 0.0, tSy = 0.0, tSz = 0.0;
+    int lat = 0, tinyI = 0, tinyS = 0;
+    if (valid) {
+      const int cell = task >> 2, q = task & 3;
+      lat = shellCell[cell];
+      const int pk = shellJK[cell];
+      const int j = pk & 0xffff, k = pk >> 16;
+      const bool deg = X.nk != 1 && k == X.nk - 1;  // App. B #3: bins with k == nk-1 reference point 0 twelve times
+      int jq = (q & 1) ? (j + 1 == X.nT ? 0 : j + 1) : j;
+      int kq = (q & 2) ? (X.nk != 1 ? k + 1 : k) : k;
+      if (deg) { jq = 0; kq = 0; }
+      // (a degenerate bin uses point 0 = the inner point of (0,0) for all three roles, particleShape.C:148)
+      const V3 xI = tab7_point(X.kind, X.tab, X.rI, X.cx, X.cy, X.cz, jq, kq);
+      const V3 xS = deg ? xI : tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, jq, kq);
+      const V3 xO = deg ? xI : tab7_point(X.kind, X.tab, X.rO, X.cx, X.cy, X.cz, jq, kq);
+      double g[3];
+      St7 st;
+      if (make_st7<EDGE>(X.G, X.B, X.baseC, X.loC, X.hiC, xI, st, guard)) { gat7<3>(st, X.pC, g); tOx = g[0]; tOy = g[1]; tOz = g[2]; }
+      if (make_st7<EDGE>(X.G, X.B, X.baseA, X.loA, X.hiA, xO, st, guard)) { gat7<3>(st, X.pA, g); tOx += g[0]; tOy += g[1]; tOz += g[2]; }
+      {
+        const double rx = xO.x - X.cx, ry = xO.y - X.cy, rz = xO.z - X.cz;
+        tOx = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tOx);
+        tOy = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tOy);
+        tOz = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tOz);
+      }
+      if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, xS, st, guard)) { gat7<3>(st, X.pB, g); tSx = g[0]; tSy = g[1]; tSz = g[2]; }
+      {
+        const double rx = xS.x - X.cx, ry = xS.y - X.cy, rz = xS.z - X.cz;
+        tSx = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tSx);
+        tSy = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tSy);
+        tSz = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tSz);
+      }
+      const int K = lat / nxy, rem = lat - K * nxy, J = rem / X.G.nx, I = rem - J * X.G.nx;
+      const double Cx = X.G.ox + (I + 0.5) * X.G.dx, Cy = X.G.oy + (J + 0.5) * X.G.dy, Cz = X.G.oz + (K + X.G.kz0 + 0.5) * X.G.dz;
+      const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
+      const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
+      tinyI = dI2 < IBM_SMALL * IBM_SMALL;
+      tinyS = dS2 < IBM_SMALL * IBM_SMALL;
+      const double wI = rsqrt7(fmax(dI2, 1e-300)), wS = rsqrt7(fmax(dS2, 1e-300));
+      wsum = wI + wS;
+      fx = fma(wI, tOx, wS * tSx); fy = fma(wI, tOy, wS * tSy); fz = fma(wI, tOz, wS * tSz);
     }
-    if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, xS, st, guard)) { gat7<3>(st, X.pB, tS); }
-    {
-      const double rx = xS.x - X.cx, ry = xS.y - X.cy, rz = xS.z - X.cz;
-      tS[0] = fma(X.vp.x + (X.om.y * rz - X.om.z * ry), X.rdT, tS[0]);
-      tS[1] = fma(X.vp.y + (X.om.z * rx - X.om.x * rz), X.rdT, tS[1]);
-      tS[2] = fma(X.vp.z + (X.om.x * ry - X.om.y * rx), X.rdT, tS[2]);
+    // the four corners of a cell sit in four adjacent lanes (NT and the warp size are multiples of 4)
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned quad = 0xfu << (lane & ~3u);
+    const unsigned anyI = __ballot_sync(0xffffffffu, tinyI) & quad, anyS = __ballot_sync(0xffffffffu, tinyS) & quad;
+    if (anyI | anyS) {
+      // one-hot rule of particleShape.C:121-127: the first q (0..7) within SMALL wins; q < 4 are the inner points
+      const int first = anyI ? (__ffs(anyI) - 1) - (int)(lane & ~3u) : 4 + (__ffs(anyS) - 1) - (int)(lane & ~3u);
+      const int q = lane & 3;
+      const double wI = (first == q) ? 1.0 : 0.0, wS = (first == 4 + q) ? 1.0 : 0.0;
+      wsum = wI + wS;
+      fx = fma(wI, tOx, wS * tSx); fy = fma(wI, tOy, wS * tSy); fz = fma(wI, tOz, wS * tSz);
     }
-    double* cv = colVal + 6 * s;
-    cv[0] = tO[0]; cv[1] = tO[1]; cv[2] = tO[2]; cv[3] = tS[0]; cv[4] = tS[1]; cv[5] = tS[2];
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      fx += __shfl_xor_sync(0xffffffffu, fx, o);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o);
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if (valid && (lane & 3u) == 0) {
+      const double rW = rcp7(wsum);
+      atomicAdd(&F[lat], fx * rW);
+      atomicAdd(&F[C + lat], fy * rW);
+      atomicAdd(&F[2 * C + lat], fz * rW);
+    }
   }
   return guard;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
              const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
              const double* __restrict__ Uold, const double* __restrict__ S, double dT, double* __restrict__ F, V7Caps cap,
@@ -382,61 +441,29 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   const V7Layout lay = v7_layout(cap);
   char* base = (char*)smem7;
   double* planes = (double*)(base + lay.planes);
-  double* colVal = (double*)(base + lay.colVal);
   double* tabD = (double*)(base + lay.tab);
   int* rowBase = (int*)(base + lay.rows);
   int* rowLo = rowBase + 3 * cap.rowsCap;
   int* rowHi = rowLo + 3 * cap.rowsCap;
   int* rowG = rowHi + 3 * cap.rowsCap;
-  int* colKey = (int*)(base + lay.colKey);
-  unsigned short* colSlot = (unsigned short*)(base + lay.colSlot);
   unsigned short* elemRow = (unsigned short*)(base + lay.elemRow);
 
   const int nT = sc.nTheta, nk = sc.nk;
-  const int nMap = nT * nk + 1;  // last key: App. B #3, bins with k == nk-1 reference point 0 twelve times
   const double R = sc.d / 2.0;
   const double rL[3] = {xadd(R, -1 * sc.delta), xadd(R, 0.0), xadd(R, sc.delta)};  // R + delta[i]  (sphere.C:167,173)
   const double rho[3] = {rL[2], rL[1], rL[0]};                                      // set 0 = outer reach ... set 2 = inner reach
   Box7 B;
-  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && nk < 0x7fff && nMap <= cap.mapCap && box7_around(L, cx, cy, cz, rho[0], B);
+  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[0], B);
   if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= NT;
   if (!fits) {
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
   const Tab7 tab = tab7_load(sc, tabD, cap);
-  for (int m = threadIdx.x; m < nMap; m += NT) colSlot[m] = 0;
   int nS[3];
   build_region7<NT>(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
   const int nA = nS[0], nB = nS[1], nC = nS[2];
-  const int off = in.shellOff[b];
-
-  // ---- columns referenced by the shell cells: mark, then compact ----
-  for (int t = threadIdx.x; t < nShell; t += NT) {
-    const int pk = shellJK[off + t];
-    const int j = pk & 0xffff, k = pk >> 16;
-    if (nk != 1 && k == nk - 1) { colSlot[nMap - 1] = 1; continue; }
-    const int jp1 = (j + 1) % nT, k1 = (nk != 1) ? k + 1 : k;
-    colSlot[j + nT * k] = 1; colSlot[jp1 + nT * k] = 1; colSlot[j + nT * k1] = 1; colSlot[jp1 + nT * k1] = 1;
-  }
-  __syncthreads();
-  int nCol = 0;
-  {
-    const int per = (nMap + NT - 1) / NT;
-    const int m0 = threadIdx.x * per, m1 = min(m0 + per, nMap);
-    int cnt = 0, dummy = 0, dt = 0;
-    for (int m = m0; m < m1; ++m) cnt += colSlot[m];
-    int slot = cnt;
-    block_scan7<NT>(slot, dummy, wsum, nCol, dt);
-    if (nCol <= cap.colCap && m0 < m1) {
-      int k = m0 / nT, j = m0 - k * nT;
-      for (int m = m0; m < m1; ++m) {
-        if (colSlot[m]) { colKey[slot] = (m == nMap - 1) ? (0x7fff << 16) : (j | (k << 16)); colSlot[m] = (unsigned short)slot; ++slot; }
-        if (++j == nT) { j = 0; ++k; }
-      }
-    }
-  }
-  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nA > 65535 || nCol > cap.colCap || nCol > 65535) {
+  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nA > 65535) {
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
@@ -478,73 +505,17 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   }
   __syncthreads();
 
-  // ---- one thread per distinct column: three stencils, 63 shared-memory loads ----
-  Col7Ctx X;
+  Task7Ctx X;
   X.G = geo7(L); X.B = B; X.tab = tab;
   X.baseA = rowBase; X.loA = rowLo; X.hiA = rowHi; X.baseB = baseB; X.loB = loB; X.hiB = hiB; X.baseC = baseC; X.loC = loC; X.hiC = hiC;
   X.pA = pA; X.pB = pB; X.pC = pC;
   X.cx = cx; X.cy = cy; X.cz = cz; X.rdT = rdT;
   X.rI = rL[0]; X.rS = rL[1]; X.rO = rL[2];
   X.vp = V3{in.v[0][b], in.v[1][b], in.v[2][b]}; X.om = V3{in.om[0][b], in.om[1][b], in.om[2][b]};
-  X.kind = sc.kind; X.nT = nT; X.nMap = nMap;
-  const int bad = B.edge ? columns7<true, NT>(X, colKey, nCol, colVal) : columns7<false, NT>(X, colKey, nCol, colVal);
+  X.kind = sc.kind; X.nT = nT; X.nk = nk;
+  const int off = in.shellOff[b];
+  const int bad = B.edge ? cells7<true, NT>(X, shellCell + off, shellJK + off, nShell, C, F) : cells7<false, NT>(X, shellCell + off, shellJK + off, nShell, C, F);
   if (bad) atomicExch(guardFlag, 1);
-  __syncthreads();
-
-  // ---- one thread per shell cell: F_i = sum_q (wI_q tO_q + wS_q tS_q)/W   (particleShape.C:113-131, particleIBM.C:230-263) ----
-  const int nxy = L.nx * L.ny;
-  for (int t = threadIdx.x; t < nShell; t += NT) {
-    const int lat = shellCell[off + t];
-    const int pk = shellJK[off + t];
-    const int j = pk & 0xffff, k = pk >> 16;
-    const bool degBin = nk != 1 && k == nk - 1;
-    const int jp1 = (j + 1) % nT, k1 = (nk != 1) ? k + 1 : k;
-    const int jj[4] = {j, jp1, j, jp1}, kk[4] = {k, k, k1, k1};
-    const int K = lat / nxy, rem = lat - K * nxy, J = rem / L.nx, I = rem - J * L.nx;
-    const double Cx = L.ox + (I + 0.5) * L.dx, Cy = L.oy + (J + 0.5) * L.dy, Cz = L.oz + (K + L.kz0 + 0.5) * L.dz;
-    double wI[4], wS[4];
-    int slot[4];
-    bool tiny = false;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int jq = degBin ? 0 : jj[q], kq = degBin ? 0 : kk[q];
-      slot[q] = colSlot[degBin ? nMap - 1 : jq + nT * kq];
-      const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
-      const V3 xS = degBin ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
-      const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
-      const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
-      tiny = tiny || dI2 < IBM_SMALL * IBM_SMALL || dS2 < IBM_SMALL * IBM_SMALL;
-      wI[q] = rsqrt7(fmax(dI2, 1e-300));
-      wS[q] = rsqrt7(fmax(dS2, 1e-300));
-    }
-    if (tiny) {  // one-hot rule of particleShape.C:121-127: the first q (0..7) within SMALL wins; q < 4 are inner points
-      int first = -1, firstS = -1;
-      for (int q = 0; q < 4; ++q) {
-        const int jq = degBin ? 0 : jj[q], kq = degBin ? 0 : kk[q];
-        const V3 xI = tab7_point(sc.kind, tab, rL[0], cx, cy, cz, jq, kq);
-        const V3 xS = degBin ? xI : tab7_point(sc.kind, tab, rL[1], cx, cy, cz, jq, kq);
-        const double dI2 = (Cx - xI.x) * (Cx - xI.x) + (Cy - xI.y) * (Cy - xI.y) + (Cz - xI.z) * (Cz - xI.z);
-        const double dS2 = (Cx - xS.x) * (Cx - xS.x) + (Cy - xS.y) * (Cy - xS.y) + (Cz - xS.z) * (Cz - xS.z);
-        if (dI2 < IBM_SMALL * IBM_SMALL && first < 0) first = q;
-        if (dS2 < IBM_SMALL * IBM_SMALL && firstS < 0) firstS = 4 + q;
-      }
-      if (first < 0) first = firstS;
-      for (int q = 0; q < 4; ++q) { wI[q] = (first == q) ? 1.0 : 0.0; wS[q] = (first == 4 + q) ? 1.0 : 0.0; }
-    }
-    double Fx = 0.0, Fy = 0.0, Fz = 0.0, W = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      W += wI[q] + wS[q];
-      const double* cv = colVal + 6 * slot[q];
-      Fx = fma(wI[q], cv[0], fma(wS[q], cv[3], Fx));
-      Fy = fma(wI[q], cv[1], fma(wS[q], cv[4], Fy));
-      Fz = fma(wI[q], cv[2], fma(wS[q], cv[5], Fz));
-    }
-    const double rW = rcp7(W);
-    atomicAdd(&F[lat], Fx * rW);
-    atomicAdd(&F[C + lat], Fy * rW);
-    atomicAdd(&F[2 * C + lat], Fz * rW);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -748,7 +719,7 @@ static long long region_cells_host(const double* d, double rho, int nGeoD) {
 
 // capacities of a launch from the shape classes (host copies); returns false when no class can take the fast path
 bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress) {
-  const int SMEM_BUDGET_F = 113 * 1024, SMEM_BUDGET_S = 74 * 1024;  // two / three resident CTAs per SM (228 KB - 1 KB per CTA)
+  const int SMEM_BUDGET_F = 113 * 1024, SMEM_BUDGET_S = 113 * 1024;  // at least two resident CTAs per SM (228 KB - 1 KB per CTA)
   V7Caps f{}, s{};
   bool any = false;
   const double d[3] = {L.dx, L.dy, L.dz};
@@ -770,9 +741,9 @@ bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses
     const long long colEst = std::min<long long>((long long)sc.nTheta * sc.nk + 1, (long long)(4.0 * vol / cellV) + 56);
     auto up = [](long long v) { return (int)std::min<long long>((v + v / 16 + 16 + 1) & ~1LL, 0x3fffffff); };
     f.planeCap = std::max(f.planeCap, up(3 * (nA + nB + nC)));
-    f.colCap = std::max(f.colCap, (int)std::min<long long>(colEst, 65535));
+    (void)colEst;
     f.rowsCap = std::max(f.rowsCap, (int)std::min<long long>(rowsOf(R + sc.delta), 192));
-    f.mapCap = std::max<long long>(f.mapCap, std::min<long long>((long long)sc.nTheta * sc.nk + 1, 1 << 20));
+
     f.nTcap = std::max(f.nTcap, sc.nTheta);
     f.nkCap = std::max(f.nkCap, sc.nk);
     f.elemCap = std::max(f.elemCap, up(nA));
@@ -795,22 +766,22 @@ static int v7_threads() {
   if (nt < 0) {
     const char* e = getenv("IBM_V7_THREADS");
     nt = e ? atoi(e) : 256;
-    if (nt != 256 && nt != 320 && nt != 192) nt = 256;
+    if (nt != 256 && nt != 320 && nt != 192 && nt != 224) nt = 256;
   }
   return nt;
 }
 
-template <int NT>
+template <int NT, int MINB>
 static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                           const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
                           double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard, int sm) {
   static PerDeviceOnce attr;
   static int attrBytes = 0;
   if (attr.first() || sm > attrBytes) {
-    cudaFuncSetAttribute(k_forcing_v7<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_forcing_v7<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_forcing_v7<NT><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
+  k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
 }
 template <int NT>
 static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const Schedule& s,
@@ -832,9 +803,15 @@ void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
-  if (nt == 320) forcing_v7_nt<320>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-  else if (nt == 192) forcing_v7_nt<192>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-  else forcing_v7_nt<256>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+  // resident CTAs per SM follow from the staged planes (a d = 8 cells sphere: 71 KB -> three); the register bound goes with it
+  const bool three = 3 * (sm + 1024) <= 228 * 1024;
+  if (nt == 320) forcing_v7_nt<320, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+  else if (nt == 192) { if (three) forcing_v7_nt<192, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+                        else forcing_v7_nt<192, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
+  else if (nt == 224) { if (three) forcing_v7_nt<224, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+                        else forcing_v7_nt<224, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
+  else { if (three) forcing_v7_nt<256, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
+         else forcing_v7_nt<256, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
   launch_forcing_v2_list(st, L, classes, in, slowList, slowCount, shellCell, shellJK, U, Uold, S, dT, F);
 }
 
@@ -846,7 +823,7 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
   if (nt == 320) stress_v7_nt<320>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
-  else if (nt == 192) stress_v7_nt<192>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
+  else if (nt == 192 || nt == 224) stress_v7_nt<192>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
   else stress_v7_nt<256>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
   launch_stress_v2_list(st, L, classes, in, slowList, slowCount, P, Tau, pRefOverRho, rhoRef, Tcorr);
 }

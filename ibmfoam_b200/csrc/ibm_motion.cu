@@ -130,6 +130,7 @@ struct Motion {
   int* hEv = nullptr;           // pinned: creation records of the copies of a step (ordering them is a host-side sort)
   int* dPerm = nullptr;         // [cap] provisional slot (relative) that goes to final slot r
   long long nClusterSteps = 0;
+  int lastFlags = 0;            // clusterFail + 1000 violated + 1e6 overflow of the last cluster step (diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1159,6 +1160,7 @@ __global__ void k5q_snapshot(MotionDev m, InstanceSoA in, double* __restrict__ s
 #define K5C_FILL 96        // components are assigned to blocks by offset / K5C_FILL
 #define K5C_CAND 96
 #define K5C_HIT 48
+#define K5C_EVN 4096      // creation records read back with the flags of a step (more: a second copy)
 
 __device__ __forceinline__ void k5c_emit(const MotionDev& m, int a, int b) {
   const int h = atomicAdd(m.nEdge, 1);
@@ -1670,6 +1672,7 @@ __global__ void k_stats(MotionDev m, InstanceSoA in, const ShapeClassDev* __rest
 }
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_copy_int(int* dst, const int* src) { *dst = *src; }
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -1734,6 +1737,23 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.sOwn, cap) && dalloc(c, M, &d.uMax, cap) && dalloc(c, M, &d.bud, cap) && dalloc(c, M, &d.noSplit, 1) && dalloc(c, M, &M->snap, 12 * cap) &&
             dalloc(c, M, &M->snapActive, cap) && dalloc(c, M, &M->snapMaxCopies, (size_t)std::max(1, c->nParticles));
   if (!ok) return IBM_E_CUDA;
+  // cluster mode of the split
+  d.edgeCap = (int)std::min<size_t>(8 * cap + 1024, 0x3fffffff);
+  d.ctaBins = (int)(cap / K5C_FILL) + 2;
+  ok = dalloc(c, M, &d.edgeA, (size_t)d.edgeCap) && dalloc(c, M, &d.edgeB, (size_t)d.edgeCap) && dalloc(c, M, &d.nEdge, 1) &&
+       dalloc(c, M, &d.label, cap) && dalloc(c, M, &d.compCnt, cap) && dalloc(c, M, &d.compOff, cap + 1) && dalloc(c, M, &d.compCur, cap) &&
+       dalloc(c, M, &d.sorted, cap) && dalloc(c, M, &d.ctaBegin, (size_t)d.ctaBins) && dalloc(c, M, &d.ctaEnd, (size_t)d.ctaBins) &&
+       dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) &&
+       dalloc(c, M, &M->dPerm, cap);
+  if (!ok) return IBM_E_CUDA;
+  {
+    size_t sb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sb, d.compCnt, d.compOff, c->cap);
+    M->scanTempBytes = sb + 256;
+    if (!ctx_cuda_ok(c, cudaMalloc(&M->scanTemp, M->scanTempBytes), "cudaMalloc(scan)")) return IBM_E_CUDA;
+    M->allocs.push_back(M->scanTemp);
+    if (!ctx_cuda_ok(c, cudaMallocHost(&M->hEv, (2 * K5C_EVN + 16) * sizeof(int)), "cudaMallocHost(events)")) return IBM_E_CUDA;
+  }
   d.activeMode = 0;
   d.safety = 2.0;
   d.check = 1.0;
@@ -1862,6 +1882,8 @@ void motion_invalidate_groups(ibm_ctx* c) {
 bool motion_counter(ibm_ctx* c, const char* name, long long* value) {
   Motion* M = (Motion*)c->motion;
   if (std::strcmp(name, "loop5_fallbacks") == 0) { *value = M ? M->nFallbacks : 0; return true; }
+  if (std::strcmp(name, "loop5_cluster_flags") == 0) { *value = M ? M->lastFlags : 0; return true; }
+  if (std::strcmp(name, "loop5_cluster_steps") == 0) { *value = M ? M->nClusterSteps : 0; return true; }
   if (std::strcmp(name, "loop5_active_instances") == 0) { *value = (M && M->d.activeMode) ? c->hScal[11] : -1; return true; }  // of the last advance
   return false;
 }
@@ -1952,8 +1974,8 @@ static int substep_launch_active(ibm_ctx* c, double localDt) {
   return IBM_OK;
 }
 
-// start of a split step: bounds, bins at the start positions, classification, then every sub-step of the quiet instances
-static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
+// start of a split step: bounds, bins at the start positions, classification
+static void active_classify(ibm_ctx* c, double dtStep) {
   Motion* M = (Motion*)c->motion;
   MotionDev& d = M->d;
   cudaStream_t st = c->stream;
@@ -1970,9 +1992,45 @@ static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
   k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge, doCyclic ? 1 : 0);
   if (c->nParticles > 0) { k5q_group_budget<<<blocks_for(c->nParticles), 128, 0, st>>>(d); c->nLaunch++; }
   k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  c->nLaunch += 5;
+}
+
+// ... then every sub-step of the quiet instances (the per-sub-step chain of the active ones follows)
+static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  active_classify(c, dtStep);
   cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
-  k5q_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
-  c->nLaunch += 6;
+  k5q_quiet<<<blocks_for(c->cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
+  c->nLaunch += 1;
+}
+
+// cluster mode: classification, components, packing, quiet instances, then ONE launch for every sub-step of the active ones
+static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  cudaStream_t st = c->stream;
+  const int cap = c->cap;
+  const int doCyclic = (d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls)) ? 1 : 0;
+  active_classify(c, dtStep);
+  cudaMemsetAsync(d.nEdge, 0, sizeof(int), st);
+  cudaMemsetAsync(d.clusterFail, 0, sizeof(int), st);
+  cudaMemsetAsync(d.compCnt, 0, (size_t)cap * sizeof(int), st);
+  cudaMemsetAsync(d.compCur, 0, (size_t)cap * sizeof(int), st);
+  cudaMemsetAsync(d.ctaBegin, 0x7f, (size_t)d.ctaBins * sizeof(int), st);
+  cudaMemsetAsync(d.ctaEnd, 0, (size_t)d.ctaBins * sizeof(int), st);
+  k_copy_int<<<1, 1, 0, st>>>(d.nextSlot, d.nInst);
+  k5c_edges<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  k5c_components<<<1, 1024, 0, st>>>(d);
+  k5c_count<<<blocks_for(cap), 128, 0, st>>>(d);
+  size_t tb = M->scanTempBytes;
+  cub::DeviceScan::ExclusiveSum(M->scanTemp, tb, d.compCnt, d.compOff, cap, st);
+  k5c_place<<<blocks_for(cap), 128, 0, st>>>(d);
+  cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
+  k5c_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
+  k5c_run<<<d.ctaBins, K5C_THREADS, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub, doCyclic, 0);
+  c->nLaunch += 9;
 }
 
 static int finish_substeps(ibm_ctx* c) {
@@ -2069,7 +2127,81 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
         if (split) substep_launch_active(c, ls); else substep_launch(c, ls);
       }
     };
-    if (split && c->fusedActive && M->fusedActBlocks > 0) {
+    const bool cluster = split && c->clusterLoop5;
+    bool clusterRedo = false;
+    if (cluster) {
+      // one launch sequence per fluid step, no per-sub-step kernel boundary; flags, the instance count and the creation
+      // records of new copies come back with ONE synchronisation
+      cluster_sequence(c, dt, nSub);
+      M->nClusterSteps++;
+      MotionDev& d = M->d;
+      int* h = M->hEv;
+      IBM_CUDA(c, cudaMemcpyAsync(h + 0, d.nextSlot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaMemcpyAsync(h + 1, d.clusterFail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaMemcpyAsync(h + 2, d.violated, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaMemcpyAsync(h + 3, d.nAct, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaMemcpyAsync(h + 4, d.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      const int evn = std::min(K5C_EVN, c->cap - nInst0);
+      if (evn > 0) {
+        IBM_CUDA(c, cudaMemcpyAsync(h + 16, d.evSub + nInst0, (size_t)evn * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        IBM_CUDA(c, cudaMemcpyAsync(h + 16 + K5C_EVN, d.evKey + nInst0, (size_t)evn * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      }
+      IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+      IBM_CUDA(c, cudaGetLastError());
+      M->lastActive = h[3];
+      c->hScal[11] = h[3];
+      M->lastFlags = h[1] * 1 + h[2] * 1000 + h[4] * 1000000;
+      if (h[1] || h[2] || h[4]) {
+        clusterRedo = true;  // no room in a block, a budget outrun, or a table overflow: redo the step unsplit (which reports real overflows)
+      } else {
+        const int total = h[0] - nInst0;
+        if (total > 0) {
+          std::vector<int> sub(total), key(total);
+          if (total <= evn) {
+            std::copy(h + 16, h + 16 + total, sub.begin());
+            std::copy(h + 16 + K5C_EVN, h + 16 + K5C_EVN + total, key.begin());
+          } else {
+            IBM_CUDA(c, cudaMemcpy(sub.data(), d.evSub + nInst0, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
+            IBM_CUDA(c, cudaMemcpy(key.data(), d.evKey + nInst0, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
+          }
+          // the reference appends, sub-step by sub-step, patch-major and in cloud order of the source within a patch
+          // (particleCloud.C:685-832); a source may itself be a copy created in an earlier sub-step of this step
+          std::vector<int> ord(total), fin(total, -1), perm(total);
+          for (int r = 0; r < total; ++r) ord[r] = r;
+          std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return sub[a] < sub[b]; });
+          int placed = 0;
+          for (int a = 0; a < total;) {
+            int b = a;
+            while (b < total && sub[ord[b]] == sub[ord[a]]) ++b;
+            auto srcPos = [&](int r) {
+              const int src = key[r] % c->cap;
+              return src < nInst0 ? src : nInst0 + fin[src - nInst0];
+            };
+            std::sort(ord.begin() + a, ord.begin() + b, [&](int x, int y) {
+              const int px = key[x] / c->cap, py = key[y] / c->cap;
+              if (px != py) return px < py;
+              return srcPos(x) < srcPos(y);
+            });
+            for (int q = a; q < b; ++q) { fin[ord[q]] = placed; perm[placed] = ord[q]; ++placed; }
+            a = b;
+          }
+          bool identity = true;
+          for (int r = 0; r < total; ++r) identity = identity && perm[r] == r;
+          if (!identity) {
+            IBM_CUDA(c, cudaMemcpyAsync(M->dPerm, perm.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            k5c_permute<<<blocks_for(total), 128, 0, c->stream>>>(c->in, c->in2, M->dPerm, nInst0, total, 0);
+            k5c_permute<<<blocks_for(total), 128, 0, c->stream>>>(c->in2, c->in, M->dPerm, nInst0, total, 1);
+            c->nLaunch += 2;
+            IBM_CUDA(c, cudaStreamSynchronize(c->stream));  // perm is a local
+          }
+          k_set_int<<<1, 1, 0, c->stream>>>(d.nInst, nInst0 + total);
+          c->nLaunch++;
+          c->nInst = nInst0 + total;
+          M->groupsValid = false;  // the same-index lists hold provisional slots: relink from the final order
+          M->graphValid = false;
+        }
+      }
+    } else if (split && c->fusedActive && M->fusedActBlocks > 0) {
       // prologue as plain launches, then ONE cooperative kernel for every sub-step of the active list.  Its grid is sized
       // from the active count of the previous step (the kernel strides, so any size is correct) and bounded by co-residency.
       active_prologue(c, dt, nSub);
@@ -2118,9 +2250,11 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       sequence();
     }
     if (split) {
-      if ((rc = finish_substeps(c))) { ctx_toc(c); return rc; }
-      M->lastActive = c->hScal[11];
-      if (c->hScal[10]) {
+      if (!cluster) {
+        if ((rc = finish_substeps(c))) { ctx_toc(c); return rc; }
+        M->lastActive = c->hScal[11];
+      }
+      if (cluster ? clusterRedo : c->hScal[10] != 0) {
         // an active instance outran the displacement budget: put the start of the step back and redo it without the split
         M->nFallbacks++;
         k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 1);
@@ -2159,6 +2293,7 @@ void motion_destroy(ibm_ctx* c) {
   Motion* M = (Motion*)c->motion;
   if (!M) return;
   if (M->graphExec) cudaGraphExecDestroy(M->graphExec);
+  if (M->hEv) cudaFreeHost(M->hEv);
   for (void* p : M->allocs) cudaFree(p);
   if (M->cubTemp) cudaFree(M->cubTemp);
   delete M;

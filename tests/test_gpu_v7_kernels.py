@@ -71,14 +71,14 @@ def test_big_sphere_class_takes_direct_path():
     gc.close()
 
 
-@pytest.mark.parametrize("hook", ["v7_col_cap", "v7_plane_cap"])
+@pytest.mark.parametrize("hook", ["v7_plane_cap"])
 def test_overflowing_instances_go_through_the_list_kernel(hook):
     case = _moving(util.small_assembly(48, 40))
     f = util.caller_fields(case)
     oc, gc = OracleCloud(case), ParticleCloud(case)
     if not gc.counter("v7_ok"):
         pytest.skip("class does not fit")
-    gc.set_option(hook, 300 if hook == "v7_col_cap" else 3000)
+    gc.set_option(hook, 3000)
     _check(case, gc, oc, f, expect_slow=True)
     gc.close()
 

@@ -25,6 +25,7 @@ def _cloud(case, graph, safety_ppm=None, check_ppm=None):
     gc.set_option("graph_loop5", int(graph is True))
     gc.set_option("active_loop5", 1)
     gc.set_option("fused_active_loop5", int(graph == "fused"))   # the active list's sub-steps in one cooperative kernel
+    gc.set_option("cluster_loop5", int(graph == "cluster"))      # independent groups, every sub-step of a group in one block
     if safety_ppm is not None:
         gc.set_option("active_loop5_safety_ppm", int(safety_ppm))
     if check_ppm is not None:
@@ -53,7 +54,7 @@ def _run_vs_oracle(case, n_steps, graph, safety_ppm=None, ft_scale=1e-3, seed=0,
     return oc, gc, actives
 
 
-@pytest.mark.parametrize("graph", [True, False, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, False, "fused"])
 def test_dilute_assembly_most_instances_are_quiet(graph):
     case = cases.assembly(n=64, n_particles=120, seed=9, moving=True, cyclic_without_walls=True)
     oc, gc, actives = _run_vs_oracle(case, 3, graph)
@@ -62,7 +63,7 @@ def test_dilute_assembly_most_instances_are_quiet(graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, False, "fused"])
 def test_fast_assembly_with_periodic_copies_and_deletion(graph):
     case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     case.particles.v *= 25.0
@@ -72,13 +73,13 @@ def test_fast_assembly_with_periodic_copies_and_deletion(graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, "fused"])
 def test_two_spheres_head_on(graph):
     _, gc, _ = _run_vs_oracle(cases.two_spheres(n=40, e=0.8, speed=0.7, gap=0.3), 3, graph)
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, "fused"])
 def test_colliding_cylinders_walls_and_copies(graph):
     case = cases.colliding_particles()
     rng = np.random.default_rng(2)
@@ -90,7 +91,7 @@ def test_colliding_cylinders_walls_and_copies(graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, False, "fused"])
 def test_exceeded_budget_redoes_the_step_without_the_split(graph):
     """the check allows a vanishing fraction of the budget: active instances outrun it at once -> snapshot restored, unsplit
     path, same result"""
@@ -102,7 +103,7 @@ def test_exceeded_budget_redoes_the_step_without_the_split(graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, "fused"])
 @pytest.mark.parametrize("name", ["col8", "wc2d_cyl", "wc3d_sph"])
 def test_trajectories_against_reference_vectors_with_the_split(name, graph):
     case, g, n_steps = gu.load_dynamic(name)
@@ -116,7 +117,7 @@ def test_trajectories_against_reference_vectors_with_the_split(name, graph):
     gc.close()
 
 
-@pytest.mark.parametrize("graph", [True, False, "fused"])
+@pytest.mark.parametrize("graph", ["cluster", True, False, "fused"])
 def test_copy_created_after_a_rebound_next_to_a_resting_body(graph):
     """A body inside the reach of a periodic patch but moving AWAY from it has no copy; a contact turns it round in mid-step,
     the copy appears on the far side and at once overlaps a body that rests there with nothing near it at the start of the
