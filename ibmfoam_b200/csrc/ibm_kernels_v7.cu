@@ -580,8 +580,8 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
   return guard;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
             const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
             V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
@@ -783,17 +783,17 @@ static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClass
   }
   k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
 }
-template <int NT>
+template <int NT, int MINB>
 static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const Schedule& s,
                          const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, const V7Caps& cap, int* slowList,
                          int* slowCount, int* guard, int sm) {
   static PerDeviceOnce attr;
   static int attrBytes = 0;
   if (attr.first() || sm > attrBytes) {
-    cudaFuncSetAttribute(k_stress_v7<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_stress_v7<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_stress_v7<NT><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
+  k_stress_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
 }
 
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
@@ -822,9 +822,13 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
-  if (nt == 320) stress_v7_nt<320>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
-  else if (nt == 192 || nt == 224) stress_v7_nt<192>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
-  else stress_v7_nt<256>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm);
+  const bool three = 3 * (sm + 1024) <= 228 * 1024;
+#define IBM_S7(NT_, MB_) stress_v7_nt<NT_, MB_>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm)
+  if (nt == 320) IBM_S7(320, 2);
+  else if (nt == 192) { if (three) IBM_S7(192, 3); else IBM_S7(192, 2); }
+  else if (nt == 224) { if (three) IBM_S7(224, 3); else IBM_S7(224, 2); }
+  else { if (three) IBM_S7(256, 3); else IBM_S7(256, 2); }
+#undef IBM_S7
   launch_stress_v2_list(st, L, classes, in, slowList, slowCount, P, Tau, pRefOverRho, rhoRef, Tcorr);
 }
 

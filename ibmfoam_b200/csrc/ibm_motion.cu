@@ -954,14 +954,32 @@ __global__ void k5q_ghosts(MotionDev m, InstanceSoA in, const ShapeClassDev* __r
   }
 }
 
+// bins that can hold an entry within `cut` of c, never more than the +-2 neighbourhood the callers are entitled to
+// (2 S <= binEdge is checked by them): most instances need +-1, 27 bins instead of 125
+struct BinRange { int x0, x1, y0, y1, z0, z1; };
+__device__ __forceinline__ BinRange bin_range(const MotionDev& m, D3 c, double cut) {
+  int bx, by, bz;
+  bin_of(m, c, bx, by, bz);
+  const double inv = 1.0 / m.binEdge, pad = cut * (1.0 + 1e-9) + 1e-9 * m.binEdge;
+  BinRange r;
+  r.x0 = max(max(bx - 2, 0), (int)floor((c.x - pad - m.bx0) * inv)); r.x1 = min(min(bx + 2, m.nbx - 1), (int)floor((c.x + pad - m.bx0) * inv));
+  r.y0 = max(max(by - 2, 0), (int)floor((c.y - pad - m.by0) * inv)); r.y1 = min(min(by + 2, m.nby - 1), (int)floor((c.y + pad - m.by0) * inv));
+  r.z0 = max(max(bz - 2, 0), (int)floor((c.z - pad - m.bz0) * inv)); r.z1 = min(min(bz + 2, m.nbz - 1), (int)floor((c.z + pad - m.bz0) * inv));
+  if (m.nbz == 1) { r.z0 = 0; r.z1 = 0; }
+  // an instance clamped into an edge bin (centre outside the binned region) keeps the full neighbourhood
+  if (r.x0 > bx || r.x1 < bx) { r.x0 = max(bx - 2, 0); r.x1 = min(bx + 2, m.nbx - 1); }
+  if (r.y0 > by || r.y1 < by) { r.y0 = max(by - 2, 0); r.y1 = min(by + 2, m.nby - 1); }
+  if (r.z0 > bz || r.z1 < bz) { r.z0 = max(bz - 2, 0); r.z1 = min(bz + 2, m.nbz - 1); }
+  return r;
+}
+
 // maximum of src over the bodies and images within Rij + 2 S of position c (instance i itself and its own images excluded)
 __device__ __forceinline__ double nbr_scan_max(const MotionDev& m, const InstanceSoA& in, const ShapeClassDev* __restrict__ classes,
                                                const double* __restrict__ src, D3 c, double di, int i, double S, double u) {
-  int bx, by, bz;
-  bin_of(m, c, bx, by, bz);
-  for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
-    for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
-      for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
+  const BinRange br = bin_range(m, c, 0.5 * (di + m.binEdge) + 2.0 * S);  // (binEdge = the largest diameter)
+  for (int z = br.z0; z <= br.z1; ++z)
+    for (int y = br.y0; y <= br.y1; ++y)
+      for (int x = br.x0; x <= br.x1; ++x) {
         const int bin = x + m.nbx * (y + m.nby * z);
         const int nb = min(m.binCnt[bin], m.binCap);
         for (int q = 0; q < nb; ++q) {
@@ -1039,12 +1057,12 @@ __global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* _
     if (quiet && m.moving) {
       if (2.0 * S > m.binEdge) quiet = 0;  // the +-2-bin search below no longer covers the cut-off: no split this step
       else {
-        int bx, by, bz;
-        bin_of(m, c, bx, by, bz);
         const double di = dmax_of(*sc);
-        for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1) && quiet; ++z)
-          for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1) && quiet; ++y)
-            for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1) && quiet; ++x) {
+        // (every budget is at most S: bud = safety * (a maximum of s) + floor, split_S; an image counts up to 4 budgets)
+        const BinRange br = bin_range(m, c, 0.5 * (di + m.binEdge) + Bi + 4.0 * S);
+        for (int z = br.z0; z <= br.z1 && quiet; ++z)
+          for (int y = br.y0; y <= br.y1 && quiet; ++y)
+            for (int x = br.x0; x <= br.x1 && quiet; ++x) {
               const int bin = x + m.nbx * (y + m.nby * z);
               const int nb = m.binCnt[bin];
               if (nb > m.binCap) { quiet = 0; break; }  // overflowing bin: entries are missing, decide nothing from it
@@ -1156,8 +1174,8 @@ __global__ void k5q_snapshot(MotionDev m, InstanceSoA in, double* __restrict__ s
 // The budgets are CHECKED as in the plain split; a violation, or a block that runs out of room, redoes the step unsplit.
 // ------------------------------------------------------------------------------------------------
 #define K5C_THREADS 128
-#define K5C_CAP 256        // members a block can hold (including the copies it creates)
-#define K5C_FILL 96        // components are assigned to blocks by offset / K5C_FILL
+#define K5C_CAP 160        // members a block can hold (including the copies it creates)
+#define K5C_FILL 56        // components are assigned to blocks by offset / K5C_FILL
 #define K5C_CAND 96
 #define K5C_HIT 48
 #define K5C_EVN 4096      // creation records read back with the flags of a step (more: a second copy)
@@ -1183,11 +1201,10 @@ __global__ void k5c_edges(MotionDev m, InstanceSoA in, const ShapeClassDev* __re
   const ShapeClassDev* sc = classes + in.cls[i];
   const D3 c = ld3(in.c, i);
   const double Bi = m.bud[i], di = dmax_of(*sc);
-  int bx, by, bz;
-  bin_of(m, c, bx, by, bz);
-  for (int z = max(bz - 2, 0); z <= min(bz + 2, m.nbz - 1); ++z)
-    for (int y = max(by - 2, 0); y <= min(by + 2, m.nby - 1); ++y)
-      for (int x = max(bx - 2, 0); x <= min(bx + 2, m.nbx - 1); ++x) {
+  const BinRange br = bin_range(m, c, 0.5 * (di + m.binEdge) + Bi + 4.0 * S);
+  for (int z = br.z0; z <= br.z1; ++z)
+    for (int y = br.y0; y <= br.y1; ++y)
+      for (int x = br.x0; x <= br.x1; ++x) {
         const int bin = x + m.nbx * (y + m.nby * z);
         const int nb = m.binCnt[bin];
         if (nb > m.binCap) { atomicExch(m.clusterFail, 1); continue; }
@@ -1292,18 +1309,186 @@ __global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const Shape
   }
 }
 
+#define K5C_PATCH 8         // wall / cyclic patches a block keeps in shared memory (more: every sub-step takes the general path)
+
+struct K5cPatch { double lo[3], hi[3], nrm[3], shift[3]; int planar, uniformShift, type; };
+
 struct K5cShared {
+  // state of the members, resident for the whole fluid step
+  double px[K5C_CAP], py[K5C_CAP], pz[K5C_CAP], vx[K5C_CAP], vy[K5C_CAP], vz[K5C_CAP];
+  double wx[K5C_CAP], wy[K5C_CAP], wz[K5C_CAP], tx[K5C_CAP], ty[K5C_CAP], tz[K5C_CAP];
+  double Fx[K5C_CAP], Fy[K5C_CAP], Fz[K5C_CAP], Tx[K5C_CAP], Ty[K5C_CAP], Tz[K5C_CAP];
+  double mass[K5C_CAP], mI[K5C_CAP], rad[K5C_CAP], dmx[K5C_CAP], bud[K5C_CAP];
+  double c0x[K5C_CAP], c0y[K5C_CAP], c0z[K5C_CAP];
   int mem[K5C_CAP];       // instance (cloud position or provisional slot) of every member
   int comp[K5C_CAP];      // its component root
+  int index[K5C_CAP];
+  int flags[K5C_CAP];     // K5F_*
+  K5cPatch wall[K5C_PATCH], cyc[K5C_PATCH];
   int candKey[K5C_CAND];
   int hitKey[K5C_HIT];
   double hitCenter[3 * K5C_HIT];
-  int nMem, candCount, hitCount, bigN, base, fail;
+  int nMem, candCount, hitCount, bigN, base, fail, patchesFit;
 };
+#define K5F_ONMESH 1
+#define K5F_ACTIVE 2
+#define K5F_MULTI 4     // its index has several instances
+#define K5F_ISO 8       // isotropic in the sense of particleIBM.C:60-74 (App. B #21)
+#define K5F_NOPATCH 16  // no wall / cyclic patch within reach + budget of where it started: patch tests skipped for the whole step
+
+// member slot <- global instance arrays
+__device__ __forceinline__ void k5c_load(K5cShared& sh, int t, const MotionDev& m, const InstanceSoA& in, const ShapeClassDev* __restrict__ classes,
+                                         int doCyclic) {
+  const int i = sh.mem[t];
+  const ShapeClassDev* sc = classes + in.cls[i];
+  sh.px[t] = in.c[0][i]; sh.py[t] = in.c[1][i]; sh.pz[t] = in.c[2][i];
+  sh.vx[t] = in.v[0][i]; sh.vy[t] = in.v[1][i]; sh.vz[t] = in.v[2][i];
+  sh.wx[t] = in.om[0][i]; sh.wy[t] = in.om[1][i]; sh.wz[t] = in.om[2][i];
+  sh.tx[t] = in.th[0][i]; sh.ty[t] = in.th[1][i]; sh.tz[t] = in.th[2][i];
+  sh.Fx[t] = in.F[0][i]; sh.Fy[t] = in.F[1][i]; sh.Fz[t] = in.F[2][i];
+  sh.Tx[t] = in.T[0][i]; sh.Ty[t] = in.T[1][i]; sh.Tz[t] = in.T[2][i];
+  const double mass = sc->V * in.rho[i];
+  sh.mass[t] = mass;
+  sh.mI[t] = mass * sc->I;
+  sh.rad[t] = sc->Rbound;
+  const D3 D = classD(*sc);
+  sh.dmx[t] = cmptMax3(D);
+  sh.bud[t] = m.bud[i];
+  sh.c0x[t] = m.c0[i]; sh.c0y[t] = m.c0[(size_t)m.cap + i]; sh.c0z[t] = m.c0[2 * (size_t)m.cap + i];
+  const int idx = in.index[i];
+  sh.index[t] = idx;
+  const int head = m.idxHead[idx];
+  int f = 0;
+  if (in.onMesh[i] != 0) f |= K5F_ONMESH;
+  if (in.active[i]) f |= K5F_ACTIVE;
+  if (head >= 0 && m.instNext[head] >= 0) f |= K5F_MULTI;
+  if ((D.x + D.y + D.z) / 3.0 == cmptMax3(D)) f |= K5F_ISO;
+  if (sh.patchesFit) {
+    const D3 c0{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
+    const double reach = sc->Rbound + 1.001 * sh.bud[t] + 1e-9 * m.binEdge;
+    bool near = false;
+    for (int w = 0; w < m.nWalls && !near; ++w) {
+      const K5cPatch& p = sh.wall[w];
+      const double dx = fmax(fmax(p.lo[0] - c0.x, c0.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c0.y, c0.y - p.hi[1]), 0.0),
+                   dz = fmax(fmax(p.lo[2] - c0.z, c0.z - p.hi[2]), 0.0);
+      near = dx * dx + dy * dy + dz * dz <= reach * reach;
+    }
+    for (int q = 0; q < m.nCyc && !near && doCyclic; ++q) {
+      const K5cPatch& p = sh.cyc[q];
+      const double dx = fmax(fmax(p.lo[0] - c0.x, c0.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c0.y, c0.y - p.hi[1]), 0.0),
+                   dz = fmax(fmax(p.lo[2] - c0.z, c0.z - p.hi[2]), 0.0);
+      near = dx * dx + dy * dy + dz * dz <= reach * reach;
+    }
+    if (!near) f |= K5F_NOPATCH;
+  }
+  sh.flags[t] = f;
+}
+
+// kinematic state of a member slot <-> global arrays (around a sub-step that takes the general path)
+__device__ __forceinline__ void k5c_store_state(const K5cShared& sh, int t, const InstanceSoA& in) {
+  const int i = sh.mem[t];
+  in.c[0][i] = sh.px[t]; in.c[1][i] = sh.py[t]; in.c[2][i] = sh.pz[t];
+  in.v[0][i] = sh.vx[t]; in.v[1][i] = sh.vy[t]; in.v[2][i] = sh.vz[t];
+  in.om[0][i] = sh.wx[t]; in.om[1][i] = sh.wy[t]; in.om[2][i] = sh.wz[t];
+  in.th[0][i] = sh.tx[t]; in.th[1][i] = sh.ty[t]; in.th[2][i] = sh.tz[t];
+  in.active[i] = (sh.flags[t] & K5F_ACTIVE) ? 1 : 0;
+}
+__device__ __forceinline__ void k5c_reload_state(K5cShared& sh, int t, const MotionDev& m, const InstanceSoA& in) {
+  const int i = sh.mem[t];
+  sh.px[t] = in.c[0][i]; sh.py[t] = in.c[1][i]; sh.pz[t] = in.c[2][i];
+  sh.vx[t] = in.v[0][i]; sh.vy[t] = in.v[1][i]; sh.vz[t] = in.v[2][i];
+  sh.wx[t] = in.om[0][i]; sh.wy[t] = in.om[1][i]; sh.wz[t] = in.om[2][i];
+  sh.tx[t] = in.th[0][i]; sh.ty[t] = in.th[1][i]; sh.tz[t] = in.th[2][i];
+  int f = sh.flags[t] & ~(K5F_ACTIVE | K5F_MULTI);
+  if (in.active[i]) f |= K5F_ACTIVE;
+  const int head = m.idxHead[sh.index[t]];
+  if (head >= 0 && m.instNext[head] >= 0) f |= K5F_MULTI;  // (its index may have got a copy in this sub-step)
+  sh.flags[t] = f;
+}
+
+// Can anything but free flight happen to member t in this sub-step?  A superset of what the general path would act on:
+// a pair that overlaps and approaches (particleCloud.C:502-509), a wall or periodic patch within reach (particleIBM.C:453-517).
+__device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const MotionDev& m, int doCyclic) {
+  const int f = sh.flags[t];
+  if (!(f & K5F_ONMESH) || !m.moving) return false;
+  const int nMem = sh.nMem, comp = sh.comp[t], idx = sh.index[t];
+  const D3 c{sh.px[t], sh.py[t], sh.pz[t]}, v{sh.vx[t], sh.vy[t], sh.vz[t]};
+  for (int u = 0; u < nMem; ++u) {
+    if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
+    const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
+    const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
+    if (mag3(cu - c) > R) continue;                                   // particleIBM.C:56-59
+    if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) return true;  // contact law with history-free overlap force / ellipse iteration
+    if (!(R > mag3(cu - c))) continue;                                // particleIBM.C:60-74
+    const D3 vu{sh.vx[u], sh.vy[u], sh.vz[u]};
+    const bool iAmP1 = idx > sh.index[u];
+    const D3 x12 = iAmP1 ? (c - cu) : (cu - c);
+    const D3 v12 = iAmP1 ? (v - vu) : (vu - v);
+    if (dot3(x12, v12) < 0) return true;
+  }
+  if (f & K5F_NOPATCH) return false;
+  if (!sh.patchesFit) return true;
+  const double r = sh.rad[t];
+  for (int w = 0; w < m.nWalls; ++w) {
+    const K5cPatch& p = sh.wall[w];
+    const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
+                 dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
+    if (dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300) return true;
+  }
+  if (doCyclic)
+    for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates
+      const K5cPatch& p = sh.cyc[q];
+      if (p.type != IBM_CYCLIC) continue;
+      const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
+                   dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
+      if (!(dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300)) continue;
+      if (p.planar && !(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
+      if (p.uniformShift) {
+        const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
+        bool have = false;
+        for (int u = 0; u < nMem && !have; ++u)
+          if (sh.index[u] == idx) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
+        if (have) continue;
+      }
+      return true;
+    }
+  return false;
+}
+
+// free flight of member t over one sub-step: d5_solve with empty contact and wall tables, operation for operation
+__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt) {
+  if (!(sh.flags[t] & K5F_ONMESH)) return;
+  if (m.moving) {
+    D3 sFc{0, 0, 0}, sFw{0, 0, 0};
+    for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
+    const D3 F = D3{sh.Fx[t], sh.Fy[t], sh.Fz[t]} + sFc + sFw;
+    D3 v{sh.vx[t], sh.vy[t], sh.vz[t]};
+    v = v + dt * (F / sh.mass[t] + D3{m.gx, m.gy, m.gz});
+    sh.vx[t] = v.x; sh.vy[t] = v.y; sh.vz[t] = v.z;
+    const D3 dx = dt * v;
+    const D3 c = D3{sh.px[t], sh.py[t], sh.pz[t]} + dx;
+    sh.px[t] = c.x; sh.py[t] = c.y; sh.pz[t] = c.z;
+    int I, J, K;
+    const bool act = find_cell(L, c.x, c.y, c.z, I, J, K) >= 0;  // particleIBM.C:417-424
+    sh.flags[t] = act ? (sh.flags[t] | K5F_ACTIVE) : (sh.flags[t] & ~K5F_ACTIVE);
+  }
+  if (m.rotating) {
+    D3 sTc{0, 0, 0}, sTw{0, 0, 0};
+    for (int w = 0; w < m.nWalls; ++w) sTw = sTw + D3{0.0, 0.0, 0.0};
+    const D3 T = D3{sh.Tx[t], sh.Ty[t], sh.Tz[t]} + sTc + sTw;
+    D3 om{sh.wx[t], sh.wy[t], sh.wz[t]};
+    om = om + dt * T / sh.mI[t];
+    sh.wx[t] = om.x; sh.wy[t] = om.y; sh.wz[t] = om.z;
+    D3 th = D3{sh.tx[t], sh.ty[t], sh.tz[t]} + om * dt;
+    if (th.z < 0) th.z += IBM_TWOPI;
+    if (th.z >= IBM_TWOPI) th.z -= IBM_TWOPI;
+    sh.tx[t] = th.x; sh.ty[t] = th.y; sh.tz[t] = th.z;
+  }
+}
 
 __global__ void __launch_bounds__(K5C_THREADS)
 k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
-        int doCyclic, int n0) {
+        int doCyclic, int generalOnly) {
   __shared__ K5cShared sh;
   const int b = blockIdx.x;
   if (b >= m.ctaBins) return;
@@ -1312,8 +1497,20 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   if (*m.clusterFail) return;
   const int tid = threadIdx.x;
   if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
-  if (tid == 0) { sh.nMem = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0; }
+  if (tid == 0) {
+    sh.nMem = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0;
+    sh.patchesFit = m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH;
+  }
+  if (m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH && tid < m.nWalls + m.nCyc) {
+    const bool isWall = tid < m.nWalls;
+    const PatchDev& p = m.patches[isWall ? m.wallPatch[tid] : m.cycPatch[tid - m.nWalls]];
+    K5cPatch& q = isWall ? sh.wall[tid] : sh.cyc[tid - m.nWalls];
+    for (int a = 0; a < 3; ++a) { q.lo[a] = p.lo[a]; q.hi[a] = p.hi[a]; q.nrm[a] = p.nrm[a]; q.shift[a] = p.shift[a]; }
+    q.planar = p.planar; q.uniformShift = p.uniformShift; q.type = p.type;
+  }
   for (int t = tid; t < end - beg; t += K5C_THREADS) { const int i = m.sorted[beg + t]; sh.mem[t] = i; sh.comp[t] = m.label[i]; }
+  __syncthreads();
+  for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_load(sh, t, m, in, classes, doCyclic);
   __syncthreads();
   // this block's view of the motion data: private candidate / hit lists, no instance-count bound (members are valid by construction)
   MotionDev ml = m;
@@ -1325,6 +1522,41 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
+    // ---- can anything but free flight happen to a member in this sub-step? ----
+    int ev = generalOnly;
+    if (!ev)
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) ev |= k5c_event(sh, t, m, doCyclic) ? 1 : 0;
+    ev = __syncthreads_or(ev);
+    if (!ev) {
+      // ---- no: every member integrates on its own (particleIBM.C:393-450), then copies exchange state (particleCloud.C:411-443) ----
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
+        k5c_free_flight(sh, t, m, L, dt);
+        const double B = m.check * sh.bud[t];
+        const D3 d0 = D3{sh.px[t], sh.py[t], sh.pz[t]} - D3{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
+        if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
+      }
+      __syncthreads();
+      if (copies) {
+        // setPositions in cloud order: the first inactive instance of an index hands theta, v, omega to all the others
+        // (every later inactive one then holds that very state already).  Its own state does not change: no race.
+        for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
+          if (!(sh.flags[t] & K5F_MULTI)) continue;
+          int src = -1, srcInst = 0x7fffffff;
+          for (int u = 0; u < sh.nMem; ++u)
+            if (sh.index[u] == sh.index[t] && !(sh.flags[u] & K5F_ACTIVE) && sh.mem[u] < srcInst) { src = u; srcInst = sh.mem[u]; }
+          if (src >= 0 && src != t) {
+            sh.tx[t] = sh.tx[src]; sh.ty[t] = sh.ty[src]; sh.tz[t] = sh.tz[src];
+            sh.vx[t] = sh.vx[src]; sh.vy[t] = sh.vy[src]; sh.vz[t] = sh.vz[src];
+            sh.wx[t] = sh.wx[src]; sh.wy[t] = sh.wy[src]; sh.wz[t] = sh.wz[src];
+          }
+        }
+        __syncthreads();
+      }
+      continue;
+    }
+    // ---- yes: this sub-step takes the general path on the global arrays ----
+    for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_store_state(sh, t, in);
+    __syncthreads();
     if (m.moving) {
       const int nMem = sh.nMem;
       for (int t = tid; t < nMem; t += K5C_THREADS) {
@@ -1424,6 +1656,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
                 sh.hitCount = 0;
                 sh.candCount = 0;
               }
+              __syncthreads();
+              for (int t = sh.nMem - total + tid; t < sh.nMem; t += K5C_THREADS) k5c_load(sh, t, m, in, classes, doCyclic);  // the new members
             }
             __syncthreads();
           } else if (tid == 0) {
@@ -1452,8 +1686,11 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       }
       __syncthreads();
     }
+    for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_reload_state(sh, t, m, in);
+    __syncthreads();
     if (sh.fail) break;  // (block-uniform: written before the last barrier)
   }
+  for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_store_state(sh, t, in);
   if (tid == 0 && sh.fail) atomicExch(m.clusterFail, 1);
 }
 
@@ -2029,7 +2266,7 @@ static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
   k5c_place<<<blocks_for(cap), 128, 0, st>>>(d);
   cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
   k5c_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
-  k5c_run<<<d.ctaBins, K5C_THREADS, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub, doCyclic, 0);
+  k5c_run<<<d.ctaBins, K5C_THREADS, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub, doCyclic, c->clusterGeneralOnly ? 1 : 0);
   c->nLaunch += 9;
 }
 

@@ -25,6 +25,7 @@ typedef void* cudaStream_t;
 #define gridDim (::emu::blk()->gridDim)
 
 inline void __syncthreads() { ::emu::syncthreads(); }
+inline int __syncthreads_or(int pred) { return ::emu::syncthreads_or(pred); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { ::emu::group_barrier(mask); }
 
 template <class T> inline T __ldg(const T* p) { return *p; }

@@ -45,6 +45,7 @@ struct Block {
   std::vector<std::map<unsigned, GroupBarrier>> groups;  // per warp: one rendez-vous object per participation mask
   std::vector<double> shflBuf;     // [warp][32] exchange slots (doubles hold ints exactly)
   const std::function<void()>* body = nullptr;
+  int orAcc = 0;  // __syncthreads_or accumulator
 };
 
 inline Block*& blk() { static Block* b = nullptr; return b; }
@@ -56,6 +57,18 @@ inline void yield() { Block* b = blk(); swapcontext(&b->fibers[b->cur].ctx, &b->
 inline void syncthreads() {
   cur().state = 1;
   yield();
+}
+
+// block-wide OR of a predicate (three rendez-vous: deposit, read, reset)
+inline int syncthreads_or(int pred) {
+  Block* b = blk();
+  if (pred) b->orAcc = 1;
+  syncthreads();
+  const int r = b->orAcc;
+  syncthreads();
+  b->orAcc = 0;
+  syncthreads();
+  return r;
 }
 
 inline int lane_id() { const Fiber& f = cur(); return (int)(f.tid.x % 32); }
