@@ -764,6 +764,9 @@ def main():
                            "kernel_generations": {"forcing": variants[0], "stress": variants[1], "marking": 1 + variants[3], "marking_full_size_check": mark_check, "loop5_quiet_active_split": bool(variants[2]), "loop5_active_list_fused": variants[2] == 2,
                                                   "loop5_active_instances": cloud.counter("loop5_active_instances") if variants[2] else None,
                                                   "loop5_fallbacks": cloud.counter("loop5_fallbacks") if variants[2] else None,
+                                                  "loop5_cluster_steps": cloud.counter("loop5_cluster_steps") if variants[2] else None,
+                                                  "loop5_block_substeps": cloud.counter("loop5_block_substeps") if variants[2] else None,
+                                                  "loop5_general_substeps": cloud.counter("loop5_general_substeps") if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else
                                                                   "library defaults" if args.no_probe else
                                                                   "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),

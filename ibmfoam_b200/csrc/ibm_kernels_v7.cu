@@ -101,9 +101,16 @@ __device__ __forceinline__ double rcp7(double x) {
 #endif
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(IBM_CUDA_EMU)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 struct Box7 {
   int j0, k0;  // first row / plane of the box, clipped to the lattice
   int by, bz;  // rows per plane, planes
+  int i0, bx;  // first column and width of the bounding box (prefetch only)
   int edge;    // the unclipped box reaches the lattice boundary: stencil neighbours may be missing, points may be off the mesh
 };
 
@@ -321,6 +328,7 @@ __device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, doub
   B.j0 = max(j0, 0); B.k0 = max(k0, 0);
   B.by = min(j1, L.ny - 1) - B.j0 + 1;
   B.bz = min(k1, L.nz - 1) - B.k0 + 1;
+  B.i0 = max(i0, 0); B.bx = min(i1, L.nx - 1) - B.i0 + 1;
   // interior: every point's cell AND its six neighbours exist (the box carries one cell of margin around the points' cells)
   B.edge = !(i0 >= 0 && i1 <= L.nx - 1 && j0 >= 0 && j1 <= L.ny - 1 && k0 >= 0 && k1 <= L.nz - 1);
   return B.by > 0 && B.bz > 0;
@@ -459,6 +467,20 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
+  // the lines of the bounding rows on their way into L2 while the region tables are built (the staging loads then wait
+  // for an L2 hit instead of a DRAM access)
+  {
+    const size_t C = (size_t)L.nCells;
+    const int rows = B.by * B.bz;
+    for (int r = threadIdx.x; r < 2 * rows; r += NT) {  // two 128-byte lines cover a row of up to 16 cells
+      const int row = r >> 1, bj = row % B.by, bk = row / B.by;
+      const size_t g = (size_t)L.nx * ((size_t)(B.j0 + bj) + (size_t)L.ny * (size_t)(B.k0 + bk)) + (size_t)B.i0 + ((r & 1) ? (size_t)(B.bx - 1) : 0);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { prefetch_l2(S + q * C + g); prefetch_l2(U + q * C + g); prefetch_l2(Uold + q * C + g); }
+    }
+  }
+  const V3 vp{in.v[0][b], in.v[1][b], in.v[2][b]}, omv{in.om[0][b], in.om[1][b], in.om[2][b]};
+  const int off = in.shellOff[b];
   const Tab7 tab = tab7_load(sc, tabD, cap);
   int nS[3];
   build_region7<NT>(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
@@ -511,9 +533,8 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   X.pA = pA; X.pB = pB; X.pC = pC;
   X.cx = cx; X.cy = cy; X.cz = cz; X.rdT = rdT;
   X.rI = rL[0]; X.rS = rL[1]; X.rO = rL[2];
-  X.vp = V3{in.v[0][b], in.v[1][b], in.v[2][b]}; X.om = V3{in.om[0][b], in.om[1][b], in.om[2][b]};
+  X.vp = vp; X.om = omv;
   X.kind = sc.kind; X.nT = nT; X.nk = nk;
-  const int off = in.shellOff[b];
   const int bad = B.edge ? cells7<true, NT>(X, shellCell + off, shellJK + off, nShell, C, F) : cells7<false, NT>(X, shellCell + off, shellJK + off, nShell, C, F);
   if (bad) atomicExch(guardFlag, 1);
 }
@@ -619,6 +640,17 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   }
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (on) {
+    {
+      const size_t C = (size_t)L.nCells;
+      const int rows = B.by * B.bz;
+      for (int r = threadIdx.x; r < 2 * rows; r += NT) {
+        const int row = r >> 1, bj = row % B.by, bk = row / B.by;
+        const size_t g = (size_t)L.nx * ((size_t)(B.j0 + bj) + (size_t)L.ny * (size_t)(B.k0 + bk)) + (size_t)B.i0 + ((r & 1) ? (size_t)(B.bx - 1) : 0);
+        prefetch_l2(P + g);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) prefetch_l2(Tau + q * C + g);
+      }
+    }
     const Tab7 tab = tab7_load(sc, tabD, cap);
     int nS[3];
     build_region7<NT>(L, B, cx, cy, cz, rho, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);

@@ -92,6 +92,7 @@ struct MotionDev {
   int ctaBins;
   int* nextSlot;                   // next free instance slot (copies created by the blocks take provisional slots)
   int* evSub; int* evKey;          // [cap] per provisional slot: sub-step of creation, patchSlot * cap + position of the source
+  unsigned long long* clusterStat; // [2] block sub-steps in total / on the general path (diagnostics of the last steps)
   int* clusterFail;                // a block ran out of room (members, candidates, hits): the step is redone unsplit
 };
 
@@ -1311,7 +1312,7 @@ __global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const Shape
 
 #define K5C_PATCH 8         // wall / cyclic patches a block keeps in shared memory (more: every sub-step takes the general path)
 
-struct K5cPatch { double lo[3], hi[3], nrm[3], shift[3]; int planar, uniformShift, type; };
+struct K5cPatch { double lo[3], hi[3], nrm[3], shift[3]; int planar, uniformShift, type, lattice, axis; };
 
 struct K5cShared {
   // state of the members, resident for the whole fluid step
@@ -1406,9 +1407,30 @@ __device__ __forceinline__ void k5c_reload_state(K5cShared& sh, int t, const Mot
   sh.flags[t] = f;
 }
 
+// Is a face centre of the patch within r of c?  patchHit / wallHit need one (particleIBM.C:466-472, 505-511).  Exact-enough for
+// lattice-ordered planar patches (face centres = transverse cell centres), "maybe" otherwise: a superset either way.
+__device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const LatticeDev& L, D3 c, double r) {
+  const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
+               dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
+  const double r2 = r * r * (1.0 + 1e-9) + 1e-300;
+  if (!(dx * dx + dy * dy + dz * dz <= r2)) return false;
+  if (!p.lattice) return true;
+  const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz}, c3[3] = {c.x, c.y, c.z};
+  const int n3[3] = {L.nx, L.ny, L.nz};
+  double d2 = 0.0;
+  for (int a = 0; a < 3; ++a) {
+    if (a == p.axis) { const double e = c3[a] - p.lo[a]; d2 += e * e; continue; }
+    double t = floor((c3[a] - o3[a]) / d3[a]);
+    t = fmin(fmax(t, 0.0), (double)(n3[a] - 1));
+    const double e = c3[a] - (o3[a] + (t + 0.5) * d3[a]);
+    d2 += e * e;
+  }
+  return d2 <= r2 * (1.0 + 1e-9) + 1e-18 * (d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
+}
+
 // Can anything but free flight happen to member t in this sub-step?  A superset of what the general path would act on:
 // a pair that overlaps and approaches (particleCloud.C:502-509), a wall or periodic patch within reach (particleIBM.C:453-517).
-__device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const MotionDev& m, int doCyclic) {
+__device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic) {
   const int f = sh.flags[t];
   if (!(f & K5F_ONMESH) || !m.moving) return false;
   const int nMem = sh.nMem, comp = sh.comp[t], idx = sh.index[t];
@@ -1429,19 +1451,13 @@ __device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const Moti
   if (f & K5F_NOPATCH) return false;
   if (!sh.patchesFit) return true;
   const double r = sh.rad[t];
-  for (int w = 0; w < m.nWalls; ++w) {
-    const K5cPatch& p = sh.wall[w];
-    const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
-                 dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
-    if (dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300) return true;
-  }
+  for (int w = 0; w < m.nWalls; ++w)
+    if (k5c_face_in_reach(sh.wall[w], L, c, r)) return true;
   if (doCyclic)
-    for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates
+    for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates + the reach of a face centre (d5_cyclic_detect)
       const K5cPatch& p = sh.cyc[q];
       if (p.type != IBM_CYCLIC) continue;
-      const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
-                   dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
-      if (!(dx * dx + dy * dy + dz * dz <= r * r * (1.0 + 1e-9) + 1e-300)) continue;
+      if (!k5c_face_in_reach(p, L, c, r)) continue;
       if (p.planar && !(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
       if (p.uniformShift) {
         const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
@@ -1506,7 +1522,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     const PatchDev& p = m.patches[isWall ? m.wallPatch[tid] : m.cycPatch[tid - m.nWalls]];
     K5cPatch& q = isWall ? sh.wall[tid] : sh.cyc[tid - m.nWalls];
     for (int a = 0; a < 3; ++a) { q.lo[a] = p.lo[a]; q.hi[a] = p.hi[a]; q.nrm[a] = p.nrm[a]; q.shift[a] = p.shift[a]; }
-    q.planar = p.planar; q.uniformShift = p.uniformShift; q.type = p.type;
+    q.planar = p.planar; q.uniformShift = p.uniformShift; q.type = p.type; q.lattice = p.latticeOrdered; q.axis = p.side / 2;
   }
   for (int t = tid; t < end - beg; t += K5C_THREADS) { const int i = m.sorted[beg + t]; sh.mem[t] = i; sh.comp[t] = m.label[i]; }
   __syncthreads();
@@ -1525,8 +1541,9 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     // ---- can anything but free flight happen to a member in this sub-step? ----
     int ev = generalOnly;
     if (!ev)
-      for (int t = tid; t < sh.nMem; t += K5C_THREADS) ev |= k5c_event(sh, t, m, doCyclic) ? 1 : 0;
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) ev |= k5c_event(sh, t, m, L, doCyclic) ? 1 : 0;
     ev = __syncthreads_or(ev);
+    if (tid == 0) { atomicAdd(&m.clusterStat[0], 1ULL); if (ev) atomicAdd(&m.clusterStat[1], 1ULL); }
     if (!ev) {
       // ---- no: every member integrates on its own (particleIBM.C:393-450), then copies exchange state (particleCloud.C:411-443) ----
       for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
@@ -1980,7 +1997,7 @@ static int motion_init(ibm_ctx* c) {
   ok = dalloc(c, M, &d.edgeA, (size_t)d.edgeCap) && dalloc(c, M, &d.edgeB, (size_t)d.edgeCap) && dalloc(c, M, &d.nEdge, 1) &&
        dalloc(c, M, &d.label, cap) && dalloc(c, M, &d.compCnt, cap) && dalloc(c, M, &d.compOff, cap + 1) && dalloc(c, M, &d.compCur, cap) &&
        dalloc(c, M, &d.sorted, cap) && dalloc(c, M, &d.ctaBegin, (size_t)d.ctaBins) && dalloc(c, M, &d.ctaEnd, (size_t)d.ctaBins) &&
-       dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) &&
+       dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) && dalloc(c, M, &d.clusterStat, 2) &&
        dalloc(c, M, &M->dPerm, cap);
   if (!ok) return IBM_E_CUDA;
   {
@@ -2119,6 +2136,13 @@ void motion_invalidate_groups(ibm_ctx* c) {
 bool motion_counter(ibm_ctx* c, const char* name, long long* value) {
   Motion* M = (Motion*)c->motion;
   if (std::strcmp(name, "loop5_fallbacks") == 0) { *value = M ? M->nFallbacks : 0; return true; }
+  if (M && (std::strcmp(name, "loop5_block_substeps") == 0 || std::strcmp(name, "loop5_general_substeps") == 0)) {
+    unsigned long long h[2] = {0, 0};
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h, M->d.clusterStat, sizeof(h), cudaMemcpyDeviceToHost);
+    *value = (long long)h[std::strcmp(name, "loop5_general_substeps") == 0 ? 1 : 0];
+    return true;
+  }
   if (std::strcmp(name, "loop5_cluster_flags") == 0) { *value = M ? M->lastFlags : 0; return true; }
   if (std::strcmp(name, "loop5_cluster_steps") == 0) { *value = M ? M->nClusterSteps : 0; return true; }
   if (std::strcmp(name, "loop5_active_instances") == 0) { *value = (M && M->d.activeMode) ? c->hScal[11] : -1; return true; }  // of the last advance
