@@ -1325,11 +1325,13 @@ struct K5cShared {
   int comp[K5C_CAP];      // its component root
   int index[K5C_CAP];
   int flags[K5C_CAP];     // K5F_*
+  unsigned short cb[K5C_CAP], ce[K5C_CAP];  // slots [cb, ce) hold the component of the member as it was at the start of the step;
+                                            // copies created since sit in [nMem0, nMem)
   K5cPatch wall[K5C_PATCH], cyc[K5C_PATCH];
   int candKey[K5C_CAND];
   int hitKey[K5C_HIT];
   double hitCenter[3 * K5C_HIT];
-  int nMem, candCount, hitCount, bigN, base, fail, patchesFit;
+  int nMem, nMem0, candCount, hitCount, bigN, base, fail, patchesFit;
 };
 #define K5F_ONMESH 1
 #define K5F_ACTIVE 2
@@ -1407,6 +1409,11 @@ __device__ __forceinline__ void k5c_reload_state(K5cShared& sh, int t, const Mot
   sh.flags[t] = f;
 }
 
+// slots that can hold a member of the same component as slot t: its component's range at the start of the step, then the
+// copies the block has created since
+#define K5C_FOR_COMPONENT(sh, t, u) \
+  for (int u = (sh).cb[t], u##_e = (sh).ce[t]; u < (sh).nMem; u = (u + 1 == u##_e && u##_e <= (sh).nMem0) ? max((sh).nMem0, u##_e) : u + 1)
+
 // Is a face centre of the patch within r of c?  patchHit / wallHit need one (particleIBM.C:466-472, 505-511).  Exact-enough for
 // lattice-ordered planar patches (face centres = transverse cell centres), "maybe" otherwise: a superset either way.
 __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const LatticeDev& L, D3 c, double r) {
@@ -1433,9 +1440,9 @@ __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const Latti
 __device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic) {
   const int f = sh.flags[t];
   if (!(f & K5F_ONMESH) || !m.moving) return false;
-  const int nMem = sh.nMem, comp = sh.comp[t], idx = sh.index[t];
+  const int comp = sh.comp[t], idx = sh.index[t];
   const D3 c{sh.px[t], sh.py[t], sh.pz[t]}, v{sh.vx[t], sh.vy[t], sh.vz[t]};
-  for (int u = 0; u < nMem; ++u) {
+  K5C_FOR_COMPONENT(sh, t, u) {
     if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
     const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
     const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
@@ -1462,8 +1469,8 @@ __device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const Moti
       if (p.uniformShift) {
         const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
         bool have = false;
-        for (int u = 0; u < nMem && !have; ++u)
-          if (sh.index[u] == idx) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
+        K5C_FOR_COMPONENT(sh, t, u)
+          if (sh.index[u] == idx && !have) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
         if (have) continue;
       }
       return true;
@@ -1514,7 +1521,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const int tid = threadIdx.x;
   if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
   if (tid == 0) {
-    sh.nMem = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0;
+    sh.nMem = end - beg; sh.nMem0 = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0;
     sh.patchesFit = m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH;
   }
   if (m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH && tid < m.nWalls + m.nCyc) {
@@ -1524,7 +1531,11 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     for (int a = 0; a < 3; ++a) { q.lo[a] = p.lo[a]; q.hi[a] = p.hi[a]; q.nrm[a] = p.nrm[a]; q.shift[a] = p.shift[a]; }
     q.planar = p.planar; q.uniformShift = p.uniformShift; q.type = p.type; q.lattice = p.latticeOrdered; q.axis = p.side / 2;
   }
-  for (int t = tid; t < end - beg; t += K5C_THREADS) { const int i = m.sorted[beg + t]; sh.mem[t] = i; sh.comp[t] = m.label[i]; }
+  for (int t = tid; t < end - beg; t += K5C_THREADS) {
+    const int i = m.sorted[beg + t], root = m.label[i];
+    sh.mem[t] = i; sh.comp[t] = root;
+    sh.cb[t] = (unsigned short)(m.compOff[root] - beg); sh.ce[t] = (unsigned short)(m.compOff[root] - beg + m.compCnt[root]);
+  }
   __syncthreads();
   for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_load(sh, t, m, in, classes, doCyclic);
   __syncthreads();
@@ -1559,7 +1570,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
           if (!(sh.flags[t] & K5F_MULTI)) continue;
           int src = -1, srcInst = 0x7fffffff;
-          for (int u = 0; u < sh.nMem; ++u)
+          K5C_FOR_COMPONENT(sh, t, u)
             if (sh.index[u] == sh.index[t] && !(sh.flags[u] & K5F_ACTIVE) && sh.mem[u] < srcInst) { src = u; srcInst = sh.mem[u]; }
           if (src >= 0 && src != t) {
             sh.tx[t] = sh.tx[src]; sh.ty[t] = sh.ty[src]; sh.tz[t] = sh.tz[src];
@@ -1581,7 +1592,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         if (in.onMesh[i] != 0) {
           const D3 c = ld3(in.c, i);
           const int comp = sh.comp[t];
-          for (int u = 0; u < nMem; ++u) {
+          K5C_FOR_COMPONENT(sh, t, u) {
             if (u == t || sh.comp[u] != comp) continue;
             const int j = sh.mem[u];
             const D3 dd = ld3(in.c, j) - c;
@@ -1652,10 +1663,11 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
                 m.evSub[dst] = s;
                 m.evKey[dst] = key;
                 // the copy joins the component of its source
-                int compSrc = 0;
-                for (int u = 0; u < sh.nMem; ++u) if (sh.mem[u] == src) compSrc = sh.comp[u];
+                int compSrc = 0, cbS = 0, ceS = 0;
+                for (int u = 0; u < sh.nMem; ++u) if (sh.mem[u] == src) { compSrc = sh.comp[u]; cbS = sh.cb[u]; ceS = sh.ce[u]; }
                 sh.mem[sh.nMem + rank] = dst;
                 sh.comp[sh.nMem + rank] = compSrc;
+                sh.cb[sh.nMem + rank] = (unsigned short)cbS; sh.ce[sh.nMem + rank] = (unsigned short)ceS;
               }
               __syncthreads();
               if (tid == 0) {  // sequential part: copy ids and the same-index lists, in append order (d5_append_link)
