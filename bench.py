@@ -217,7 +217,8 @@ def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345, impl="port", max
 # generation on a small assembly and (b) are faster on a 256^3 workload.  A child process, so that a kernel fault or a
 # hang cannot take the measurement down: any failure just keeps the defaults.
 # ------------------------------------------------------------------------------------------------
-DEFAULT_VARIANTS = {"forcing": 2, "stress": 4}
+DEFAULT_VARIANTS = {"forcing": 7, "stress": 7}   # the library defaults (round 2): staged seventh-generation kernels
+DEFAULT_SPLIT = 1                                 # loop 5: quiet / active split in cluster mode (library option active_loop5)
 PROBE_CACHE = os.path.join("/tmp", "ibmfoam_b200_probe.json")
 
 
@@ -480,7 +481,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1, help="-1 = probe (verified + faster generation per kernel), >= 0 = force that generation")
     ap.add_argument("--mark", type=int, default=-1, help="marking kernel: -1 = as probed (first version without a probe), 0 / 1 = forced")
-    ap.add_argument("--no-probe", action="store_true", help="library defaults without the child-process probe")
+    ap.add_argument("--no-probe", action="store_true", help="(default since round 2) library defaults without the child-process probe")
+    ap.add_argument("--probe-generations", action="store_true", help="round-1 behaviour: a child process compares kernel generations first")
     ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 = off, 1 = on, 2 = on with the active list in one cooperative kernel")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--probe-fused", action="store_true", help=argparse.SUPPRESS)
@@ -524,11 +526,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     # which kernel generation: local rank 0 asks a child process BEFORE joining the process group (the others wait in the
     # rendezvous), then everyone gets its answer
-    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0, 0]   # forcing generation, stress generation, loop-5 mode, marking kernel
+    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], DEFAULT_SPLIT, 0]   # forcing generation, stress generation, loop-5 mode, marking kernel
     probe_info = None
     if args.variant >= 0:
-        variants = [args.variant, args.variant, 0, 0]
-    elif not args.no_probe and rank == 0:
+        variants = [args.variant, args.variant, DEFAULT_SPLIT, 0]
+    elif args.probe_generations and rank == 0:
         variants[0], variants[1], variants[2], variants[3], probe_info = choose_variants(local_rank, workload=args.workload)
     if args.split >= 0:
         variants[2] = min(max(args.split, 0), 2)
@@ -768,7 +770,7 @@ def main():
                                                   "loop5_block_substeps": cloud.counter("loop5_block_substeps") if variants[2] else None,
                                                   "loop5_general_substeps": cloud.counter("loop5_general_substeps") if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else
-                                                                  "library defaults" if args.no_probe else
+                                                                  "library defaults" if not args.probe_generations else
                                                                   "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),
                                                   "probe": probe_info, "full_size_check": verify,
                                                   "retry_after": os.environ.get("IBM_BENCH_RETRY_AFTER")}},
@@ -785,7 +787,7 @@ def main():
 
 
 def _retryable(argv):
-    return (int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
+    return ("--probe-generations" in argv and int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
             and "--probe-fused" not in argv and "reference" not in argv)
 
 

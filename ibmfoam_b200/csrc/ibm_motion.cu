@@ -1331,7 +1331,7 @@ struct K5cShared {
   int candKey[K5C_CAND];
   int hitKey[K5C_HIT];
   double hitCenter[3 * K5C_HIT];
-  int nMem, nMem0, candCount, hitCount, bigN, base, fail, patchesFit;
+  int nMem, nMem0, candCount, hitCount, bigN, base, fail, patchesFit, evMask[2];
 };
 #define K5F_ONMESH 1
 #define K5F_ACTIVE 2
@@ -1437,9 +1437,12 @@ __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const Latti
 
 // Can anything but free flight happen to member t in this sub-step?  A superset of what the general path would act on:
 // a pair that overlaps and approaches (particleCloud.C:502-509), a wall or periodic patch within reach (particleIBM.C:453-517).
-__device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic) {
+// 0 = nothing, 1 = only contacts between isotropic single-instance bodies under the reference's impulse law (the resident path
+// evaluates them itself, k5c_contact_sum), 2 = anything else (the sub-step takes the general path)
+__device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic) {
   const int f = sh.flags[t];
-  if (!(f & K5F_ONMESH) || !m.moving) return false;
+  if (!(f & K5F_ONMESH) || !m.moving) return 0;
+  int code = 0;
   const int comp = sh.comp[t], idx = sh.index[t];
   const D3 c{sh.px[t], sh.py[t], sh.pz[t]}, v{sh.vx[t], sh.vy[t], sh.vz[t]};
   K5C_FOR_COMPONENT(sh, t, u) {
@@ -1447,19 +1450,22 @@ __device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const Moti
     const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
     const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
     if (mag3(cu - c) > R) continue;                                   // particleIBM.C:56-59
-    if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) return true;  // contact law with history-free overlap force / ellipse iteration
+    if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) return 2;  // contact law with history-free overlap force / ellipse iteration
     if (!(R > mag3(cu - c))) continue;                                // particleIBM.C:60-74
     const D3 vu{sh.vx[u], sh.vy[u], sh.vz[u]};
     const bool iAmP1 = idx > sh.index[u];
     const D3 x12 = iAmP1 ? (c - cu) : (cu - c);
     const D3 v12 = iAmP1 ? (v - vu) : (vu - v);
-    if (dot3(x12, v12) < 0) return true;
+    if (dot3(x12, v12) < 0) {
+      if ((f | sh.flags[u]) & K5F_MULTI) return 2;  // copies share the larger entry (particleCloud.C:525-554): general path
+      code = 1;
+    }
   }
-  if (f & K5F_NOPATCH) return false;
-  if (!sh.patchesFit) return true;
+  if (f & K5F_NOPATCH) return code;
+  if (!sh.patchesFit) return 2;
   const double r = sh.rad[t];
   for (int w = 0; w < m.nWalls; ++w)
-    if (k5c_face_in_reach(sh.wall[w], L, c, r)) return true;
+    if (k5c_face_in_reach(sh.wall[w], L, c, r)) return 2;
   if (doCyclic)
     for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates + the reach of a face centre (d5_cyclic_detect)
       const K5cPatch& p = sh.cyc[q];
@@ -1473,16 +1479,55 @@ __device__ __forceinline__ bool k5c_event(const K5cShared& sh, int t, const Moti
           if (sh.index[u] == idx && !have) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
         if (have) continue;
       }
-      return true;
+      return 2;
     }
-  return false;
+  return code;
 }
 
-// free flight of member t over one sub-step: d5_solve with empty contact and wall tables, operation for operation
-__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt) {
+// sum(collisionForces_) of member t for a sub-step whose only events are contacts of isotropic single-instance bodies:
+// every entry as d5_pair_eval writes it (particleCloud.C:505-521), summed in partner-index order (particleIBM.C:408-411).
+// The torque entries are -+F ^ hitPt with hitPt = 0 (particleIBM.C:56-74): exact zeros.
+__device__ __forceinline__ D3 k5c_contact_sum(const K5cShared& sh, int t, const MotionDev& m, double deltaT, bool& overflow) {
+  D3 sum{0, 0, 0};
+  if (!(sh.flags[t] & K5F_ONMESH)) return sum;
+  const int comp = sh.comp[t], idx = sh.index[t];
+  const D3 c{sh.px[t], sh.py[t], sh.pz[t]}, v{sh.vx[t], sh.vy[t], sh.vz[t]};
+  int eIdx[4];
+  D3 eF[4];
+  int n = 0;
+  K5C_FOR_COMPONENT(sh, t, u) {
+    if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
+    const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
+    const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
+    if (mag3(cu - c) > R) continue;
+    if (!(R > mag3(cu - c))) continue;
+    const D3 vu{sh.vx[u], sh.vy[u], sh.vz[u]};
+    const bool iAmP1 = idx > sh.index[u];
+    const D3 x12 = iAmP1 ? (c - cu) : (cu - c);
+    const D3 v12 = iAmP1 ? (v - vu) : (vu - v);
+    if (!(dot3(x12, v12) < 0)) continue;
+    const double mi = sh.mass[t], mj = sh.mass[u];
+    double mass1 = iAmP1 ? mi : mj, mass2 = iAmP1 ? mj : mi;
+    double M = mass1 * mass2 / (mass1 + mass2);
+    double x12Dotv12 = dot3(x12, v12);
+    double x12Sqr = magSqr3(x12);
+    D3 F = 2.0 * M * x12Dotv12 / x12Sqr * x12 * m.e / deltaT;  // particleCloud.C:513
+    const D3 myF = iAmP1 ? -F : F;
+    if (n >= 4) { overflow = true; continue; }
+    int q = n++;
+    while (q > 0 && eIdx[q - 1] > sh.index[u]) { eIdx[q] = eIdx[q - 1]; eF[q] = eF[q - 1]; --q; }
+    eIdx[q] = sh.index[u]; eF[q] = myF;
+  }
+  for (int q = 0; q < n; ++q) sum = sum + eF[q];
+  return sum;
+}
+
+// member t over one sub-step: d5_solve with the given sum of contact forces (zero in free flight), zero contact torques and
+// empty wall tables, operation for operation
+__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt, D3 sFc) {
   if (!(sh.flags[t] & K5F_ONMESH)) return;
   if (m.moving) {
-    D3 sFc{0, 0, 0}, sFw{0, 0, 0};
+    D3 sFw{0, 0, 0};
     for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
     const D3 F = D3{sh.Fx[t], sh.Fy[t], sh.Fz[t]} + sFc + sFw;
     D3 v{sh.vx[t], sh.vy[t], sh.vz[t]};
@@ -1521,7 +1566,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const int tid = threadIdx.x;
   if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
   if (tid == 0) {
-    sh.nMem = end - beg; sh.nMem0 = end - beg; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0;
+    sh.nMem = end - beg; sh.nMem0 = end - beg; sh.evMask[0] = 0; sh.evMask[1] = 0; sh.candCount = 0; sh.hitCount = 0; sh.bigN = 0x7fffffff; sh.fail = 0;
     sh.patchesFit = m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH;
   }
   if (m.nWalls <= K5C_PATCH && m.nCyc <= K5C_PATCH && tid < m.nWalls + m.nCyc) {
@@ -1550,15 +1595,29 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
     // ---- can anything but free flight happen to a member in this sub-step? ----
-    int ev = generalOnly;
-    if (!ev)
-      for (int t = tid; t < sh.nMem; t += K5C_THREADS) ev |= k5c_event(sh, t, m, L, doCyclic) ? 1 : 0;
-    ev = __syncthreads_or(ev);
-    if (tid == 0) { atomicAdd(&m.clusterStat[0], 1ULL); if (ev) atomicAdd(&m.clusterStat[1], 1ULL); }
-    if (!ev) {
-      // ---- no: every member integrates on its own (particleIBM.C:393-450), then copies exchange state (particleCloud.C:411-443) ----
+    int evl = generalOnly ? 2 : 0;
+    if (!evl)
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) evl = max(evl, k5c_event(sh, t, m, L, doCyclic));
+    if (evl) atomicOr(&sh.evMask[s & 1], evl);
+    __syncthreads();
+    const int ev = sh.evMask[s & 1];
+    if (tid == 0) sh.evMask[(s + 1) & 1] = 0;  // (nobody reads or writes the other word before the next barrier)
+    if (tid == 0) { atomicAdd(&m.clusterStat[0], 1ULL); if (ev & 2) atomicAdd(&m.clusterStat[1], 1ULL); }
+    if (!(ev & 2)) {
+      // ---- no, or contacts the resident path evaluates itself: every member integrates (particleIBM.C:393-450), then copies
+      //      exchange state (particleCloud.C:411-443) ----
+      D3 sums[(K5C_CAP + K5C_THREADS - 1) / K5C_THREADS];
+      bool over = false;
+      if (ev & 1) {  // contact forces from the positions and velocities at the start of the sub-step, for everybody, THEN move
+        int q = 0;
+        for (int t = tid; t < sh.nMem; t += K5C_THREADS) sums[q++] = k5c_contact_sum(sh, t, m, dt, over);
+        if (over) sh.fail = 8;
+        __syncthreads();
+      }
+      int q = 0;
       for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
-        k5c_free_flight(sh, t, m, L, dt);
+        k5c_free_flight(sh, t, m, L, dt, (ev & 1) ? sums[q] : D3{0, 0, 0});
+        ++q;
         const double B = m.check * sh.bud[t];
         const D3 d0 = D3{sh.px[t], sh.py[t], sh.pz[t]} - D3{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
         if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
@@ -1580,6 +1639,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         }
         __syncthreads();
       }
+      if (sh.fail) break;
       continue;
     }
     // ---- yes: this sub-step takes the general path on the global arrays ----
