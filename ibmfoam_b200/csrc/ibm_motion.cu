@@ -1558,6 +1558,7 @@ __global__ void __launch_bounds__(K5C_THREADS)
 k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts, int nSub,
         int doCyclic, int generalOnly) {
   __shared__ K5cShared sh;
+  const long long tLaunch = clock64();
   const int b = blockIdx.x;
   if (b >= m.ctaBins) return;
   const int beg = m.ctaBegin[b], end = m.ctaEnd[b];
@@ -1592,8 +1593,11 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   ml.overflow = &sh.fail;
   const bool copies = m.nCyc > 0;
   const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
+  long long tEv = 0, tFl = 0, tSp = 0, tGen = 0;
+  const long long tStart = clock64();
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
+    const long long t0 = clock64();
     // ---- can anything but free flight happen to a member in this sub-step? ----
     int evl = generalOnly ? 2 : 0;
     if (!evl)
@@ -1602,6 +1606,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     __syncthreads();
     const int ev = sh.evMask[s & 1];
     if (tid == 0) sh.evMask[(s + 1) & 1] = 0;  // (nobody reads or writes the other word before the next barrier)
+    const long long t1 = clock64();
+    tEv += t1 - t0;
     if (tid == 0) { atomicAdd(&m.clusterStat[0], 1ULL); if (ev & 2) atomicAdd(&m.clusterStat[1], 1ULL); }
     if (!(ev & 2)) {
       // ---- no, or contacts the resident path evaluates itself: every member integrates (particleIBM.C:393-450), then copies
@@ -1623,6 +1629,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         if (magSqr3(d0) > B * B) atomicExch(m.violated, 1);
       }
       __syncthreads();
+      const long long t2 = clock64();
+      tFl += t2 - t1;
       if (copies) {
         // setPositions in cloud order: the first inactive instance of an index hands theta, v, omega to all the others
         // (every later inactive one then holds that very state already).  Its own state does not change: no race.
@@ -1639,6 +1647,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         }
         __syncthreads();
       }
+      tSp += clock64() - t2;
       if (sh.fail) break;
       continue;
     }
@@ -1777,7 +1786,14 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     }
     for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_reload_state(sh, t, m, in);
     __syncthreads();
+    tGen += clock64() - t1;
     if (sh.fail) break;  // (block-uniform: written before the last barrier)
+  }
+  if (tid == 0) {  // diagnostics: the slowest block's cycles per phase
+    atomicMax(&m.clusterStat[2], (unsigned long long)tEv); atomicMax(&m.clusterStat[3], (unsigned long long)tFl);
+    atomicMax(&m.clusterStat[4], (unsigned long long)tSp); atomicMax(&m.clusterStat[5], (unsigned long long)tGen);
+    atomicMax(&m.clusterStat[6], (unsigned long long)(clock64() - tStart)); atomicMax(&m.clusterStat[7], (unsigned long long)sh.nMem);
+    atomicMax(&m.clusterStat[8], (unsigned long long)(tStart - tLaunch));
   }
   for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_store_state(sh, t, in);
   if (tid == 0 && sh.fail) atomicExch(m.clusterFail, 1);
@@ -2069,7 +2085,7 @@ static int motion_init(ibm_ctx* c) {
   ok = dalloc(c, M, &d.edgeA, (size_t)d.edgeCap) && dalloc(c, M, &d.edgeB, (size_t)d.edgeCap) && dalloc(c, M, &d.nEdge, 1) &&
        dalloc(c, M, &d.label, cap) && dalloc(c, M, &d.compCnt, cap) && dalloc(c, M, &d.compOff, cap + 1) && dalloc(c, M, &d.compCur, cap) &&
        dalloc(c, M, &d.sorted, cap) && dalloc(c, M, &d.ctaBegin, (size_t)d.ctaBins) && dalloc(c, M, &d.ctaEnd, (size_t)d.ctaBins) &&
-       dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) && dalloc(c, M, &d.clusterStat, 2) &&
+       dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) && dalloc(c, M, &d.clusterStat, 16) &&
        dalloc(c, M, &M->dPerm, cap);
   if (!ok) return IBM_E_CUDA;
   {
@@ -2208,6 +2224,14 @@ void motion_invalidate_groups(ibm_ctx* c) {
 bool motion_counter(ibm_ctx* c, const char* name, long long* value) {
   Motion* M = (Motion*)c->motion;
   if (std::strcmp(name, "loop5_fallbacks") == 0) { *value = M ? M->nFallbacks : 0; return true; }
+  if (M && std::strncmp(name, "loop5_stat", 10) == 0) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h, M->d.clusterStat, sizeof(h), cudaMemcpyDeviceToHost);
+    const int q = std::atoi(name + 10);
+    *value = (q >= 0 && q < 16) ? (long long)h[q] : -1;
+    return true;
+  }
   if (M && (std::strcmp(name, "loop5_block_substeps") == 0 || std::strcmp(name, "loop5_general_substeps") == 0)) {
     unsigned long long h[2] = {0, 0};
     cudaStreamSynchronize(c->stream);

@@ -44,6 +44,7 @@ inline double max(double a, double b) { return a > b ? a : b; }
 
 inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline long long clock64() { return 0; }
 inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomicCAS(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
 inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
