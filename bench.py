@@ -769,7 +769,7 @@ def main():
                                                   "loop5_cluster_steps": cloud.counter("loop5_cluster_steps") if variants[2] else None,
                                                   "loop5_block_substeps": cloud.counter("loop5_block_substeps") if variants[2] else None,
                                                   "loop5_general_substeps": cloud.counter("loop5_general_substeps") if variants[2] else None,
-                                                  "loop5_slowest_block_cycles": {k: cloud.counter("loop5_stat%d" % q) for q, k in ((2, "event"), (3, "flight"), (4, "setpos"), (5, "general"), (6, "loop"), (7, "members"), (8, "load"))} if variants[2] else None,
+                                                  "loop5_slowest_block_cycles": {k: cloud.counter("loop5_stat%d" % q) for q, k in ((2, "event"), (3, "flight"), (4, "setpos"), (5, "general"), (6, "loop"), (7, "members"), (8, "load"), (9, "pair_thread"), (10, "event_thread"))} if variants[2] else None,
                                                   "selected_by": ("--variant" if args.variant >= 0 else
                                                                   "library defaults" if not args.probe_generations else
                                                                   "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),

@@ -1325,6 +1325,7 @@ struct K5cShared {
   int comp[K5C_CAP];      // its component root
   int index[K5C_CAP];
   int flags[K5C_CAP];     // K5F_*
+  unsigned short ring[K5C_CAP];             // next member slot with the same index (circular; itself when alone)
   unsigned short cb[K5C_CAP], ce[K5C_CAP];  // slots [cb, ce) hold the component of the member as it was at the start of the step;
                                             // copies created since sit in [nMem0, nMem)
   K5cPatch wall[K5C_PATCH], cyc[K5C_PATCH];
@@ -1414,6 +1415,17 @@ __device__ __forceinline__ void k5c_reload_state(K5cShared& sh, int t, const Mot
 #define K5C_FOR_COMPONENT(sh, t, u) \
   for (int u = (sh).cb[t], u##_e = (sh).ce[t]; u < (sh).nMem; u = (u + 1 == u##_e && u##_e <= (sh).nMem0) ? max((sh).nMem0, u##_e) : u + 1)
 
+// next member with the same index after slot t, cyclically (needs index[] of every member)
+__device__ __forceinline__ void k5c_link_ring(K5cShared& sh, int t) {
+  int nxt = -1, first = -1;
+  K5C_FOR_COMPONENT(sh, t, u) {
+    if (sh.index[u] != sh.index[t]) continue;
+    if (first < 0) first = u;
+    if (u > t && nxt < 0) nxt = u;
+  }
+  sh.ring[t] = (unsigned short)(nxt >= 0 ? nxt : first);
+}
+
 // Is a face centre of the patch within r of c?  patchHit / wallHit need one (particleIBM.C:466-472, 505-511).  Exact-enough for
 // lattice-ordered planar patches (face centres = transverse cell centres), "maybe" otherwise: a superset either way.
 __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const LatticeDev& L, D3 c, double r) {
@@ -1439,7 +1451,8 @@ __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const Latti
 // a pair that overlaps and approaches (particleCloud.C:502-509), a wall or periodic patch within reach (particleIBM.C:453-517).
 // 0 = nothing, 1 = only contacts between isotropic single-instance bodies under the reference's impulse law (the resident path
 // evaluates them itself, k5c_contact_sum), 2 = anything else (the sub-step takes the general path)
-__device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic) {
+__device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic, long long& tPair) {
+  const long long tp0 = clock64();
   const int f = sh.flags[t];
   if (!(f & K5F_ONMESH) || !m.moving) return 0;
   int code = 0;
@@ -1449,6 +1462,7 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
     if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
     const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
     const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
+    if (magSqr3(cu - c) > R * R * (1.0 + 1e-9)) continue;             // (surely mag > R: spares the square root)
     if (mag3(cu - c) > R) continue;                                   // particleIBM.C:56-59
     if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) return 2;  // contact law with history-free overlap force / ellipse iteration
     if (!(R > mag3(cu - c))) continue;                                // particleIBM.C:60-74
@@ -1461,6 +1475,7 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
       code = 1;
     }
   }
+  tPair += clock64() - tp0;
   if (f & K5F_NOPATCH) return code;
   if (!sh.patchesFit) return 2;
   const double r = sh.rad[t];
@@ -1475,8 +1490,7 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
       if (p.uniformShift) {
         const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
         bool have = false;
-        K5C_FOR_COMPONENT(sh, t, u)
-          if (sh.index[u] == idx && !have) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
+        for (int u = sh.ring[t]; u != t && !have; u = sh.ring[u]) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
         if (have) continue;
       }
       return 2;
@@ -1524,7 +1538,7 @@ __device__ __forceinline__ D3 k5c_contact_sum(const K5cShared& sh, int t, const 
 
 // member t over one sub-step: d5_solve with the given sum of contact forces (zero in free flight), zero contact torques and
 // empty wall tables, operation for operation
-__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt, D3 sFc) {
+__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt, D3 sFc, bool needActive) {
   if (!(sh.flags[t] & K5F_ONMESH)) return;
   if (m.moving) {
     D3 sFw{0, 0, 0};
@@ -1536,9 +1550,13 @@ __device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const Moti
     const D3 dx = dt * v;
     const D3 c = D3{sh.px[t], sh.py[t], sh.pz[t]} + dx;
     sh.px[t] = c.x; sh.py[t] = c.y; sh.pz[t] = c.z;
-    int I, J, K;
-    const bool act = find_cell(L, c.x, c.y, c.z, I, J, K) >= 0;  // particleIBM.C:417-424
-    sh.flags[t] = act ? (sh.flags[t] | K5F_ACTIVE) : (sh.flags[t] & ~K5F_ACTIVE);
+    if (needActive) {
+      // particleIBM.C:417-424.  active_ is read by setPositions of the copies of an index and by the log block after the last
+      // sub-step: instances without copies only need the last one (a general sub-step recomputes it for everybody)
+      int I, J, K;
+      const bool act = find_cell(L, c.x, c.y, c.z, I, J, K) >= 0;
+      sh.flags[t] = act ? (sh.flags[t] | K5F_ACTIVE) : (sh.flags[t] & ~K5F_ACTIVE);
+    }
   }
   if (m.rotating) {
     D3 sTc{0, 0, 0}, sTw{0, 0, 0};
@@ -1585,6 +1603,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   __syncthreads();
   for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_load(sh, t, m, in, classes, doCyclic);
   __syncthreads();
+  for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_link_ring(sh, t);
+  __syncthreads();
   // this block's view of the motion data: private candidate / hit lists, no instance-count bound (members are valid by construction)
   MotionDev ml = m;
   ml.nInst = &sh.bigN;
@@ -1593,7 +1613,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   ml.overflow = &sh.fail;
   const bool copies = m.nCyc > 0;
   const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
-  long long tEv = 0, tFl = 0, tSp = 0, tGen = 0;
+  long long tEv = 0, tFl = 0, tSp = 0, tGen = 0, tPair = 0, tEvOwn = 0;
   const long long tStart = clock64();
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
@@ -1601,7 +1621,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     // ---- can anything but free flight happen to a member in this sub-step? ----
     int evl = generalOnly ? 2 : 0;
     if (!evl)
-      for (int t = tid; t < sh.nMem; t += K5C_THREADS) evl = max(evl, k5c_event(sh, t, m, L, doCyclic));
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) evl = max(evl, k5c_event(sh, t, m, L, doCyclic, tPair));
+    tEvOwn += clock64() - t0;
     if (evl) atomicOr(&sh.evMask[s & 1], evl);
     __syncthreads();
     const int ev = sh.evMask[s & 1];
@@ -1622,7 +1643,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       }
       int q = 0;
       for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
-        k5c_free_flight(sh, t, m, L, dt, (ev & 1) ? sums[q] : D3{0, 0, 0});
+        k5c_free_flight(sh, t, m, L, dt, (ev & 1) ? sums[q] : D3{0, 0, 0}, s == nSub - 1 || (sh.flags[t] & K5F_MULTI) != 0);
         ++q;
         const double B = m.check * sh.bud[t];
         const D3 d0 = D3{sh.px[t], sh.py[t], sh.pz[t]} - D3{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
@@ -1637,8 +1658,9 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
         for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
           if (!(sh.flags[t] & K5F_MULTI)) continue;
           int src = -1, srcInst = 0x7fffffff;
-          K5C_FOR_COMPONENT(sh, t, u)
-            if (sh.index[u] == sh.index[t] && !(sh.flags[u] & K5F_ACTIVE) && sh.mem[u] < srcInst) { src = u; srcInst = sh.mem[u]; }
+          if (!(sh.flags[t] & K5F_ACTIVE)) { src = t; srcInst = sh.mem[t]; }
+          for (int u = sh.ring[t]; u != t; u = sh.ring[u])
+            if (!(sh.flags[u] & K5F_ACTIVE) && sh.mem[u] < srcInst) { src = u; srcInst = sh.mem[u]; }
           if (src >= 0 && src != t) {
             sh.tx[t] = sh.tx[src]; sh.ty[t] = sh.ty[src]; sh.tz[t] = sh.tz[src];
             sh.vx[t] = sh.vx[src]; sh.vy[t] = sh.vy[src]; sh.vz[t] = sh.vz[src];
@@ -1784,11 +1806,12 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       }
       __syncthreads();
     }
-    for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_reload_state(sh, t, m, in);
+    for (int t = tid; t < sh.nMem; t += K5C_THREADS) { k5c_reload_state(sh, t, m, in); k5c_link_ring(sh, t); }
     __syncthreads();
     tGen += clock64() - t1;
     if (sh.fail) break;  // (block-uniform: written before the last barrier)
   }
+  atomicMax(&m.clusterStat[9], (unsigned long long)tPair); atomicMax(&m.clusterStat[10], (unsigned long long)tEvOwn);
   if (tid == 0) {  // diagnostics: the slowest block's cycles per phase
     atomicMax(&m.clusterStat[2], (unsigned long long)tEv); atomicMax(&m.clusterStat[3], (unsigned long long)tFl);
     atomicMax(&m.clusterStat[4], (unsigned long long)tSp); atomicMax(&m.clusterStat[5], (unsigned long long)tGen);
