@@ -1310,6 +1310,7 @@ __global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const Shape
   }
 }
 
+#define K5C_NP 6            // possible contact partners a member keeps in its list (more: it scans its whole component)
 #define K5C_PATCH 8         // wall / cyclic patches a block keeps in shared memory (more: every sub-step takes the general path)
 
 struct K5cPatch { double lo[3], hi[3], nrm[3], shift[3]; int planar, uniformShift, type, lattice, axis; };
@@ -1325,6 +1326,7 @@ struct K5cShared {
   int comp[K5C_CAP];      // its component root
   int index[K5C_CAP];
   int flags[K5C_CAP];     // K5F_*
+  unsigned char nbr[K5C_CAP][K5C_NP], nNbr[K5C_CAP];  // members that can come within contact distance this step (from c0 and the budgets)
   unsigned short ring[K5C_CAP];             // next member slot with the same index (circular; itself when alone)
   unsigned short cb[K5C_CAP], ce[K5C_CAP];  // slots [cb, ce) hold the component of the member as it was at the start of the step;
                                             // copies created since sit in [nMem0, nMem)
@@ -1338,6 +1340,7 @@ struct K5cShared {
 #define K5F_ACTIVE 2
 #define K5F_MULTI 4     // its index has several instances
 #define K5F_ISO 8       // isotropic in the sense of particleIBM.C:60-74 (App. B #21)
+#define K5F_SCANALL 32  // more possible partners than the list holds
 #define K5F_NOPATCH 16  // no wall / cyclic patch within reach + budget of where it started: patch tests skipped for the whole step
 
 // member slot <- global instance arrays
@@ -1415,6 +1418,25 @@ __device__ __forceinline__ void k5c_reload_state(K5cShared& sh, int t, const Mot
 #define K5C_FOR_COMPONENT(sh, t, u) \
   for (int u = (sh).cb[t], u##_e = (sh).ce[t]; u < (sh).nMem; u = (u + 1 == u##_e && u##_e <= (sh).nMem0) ? max((sh).nMem0, u##_e) : u + 1)
 
+// Possible contact partners of slot t during this step: both bodies stay within their budget of where they started (checked
+// every sub-step), so only pairs whose START centres are within (Dmax_t + Dmax_u)/2 + B_t + B_u can pass particleIBM.C:56-59.
+__device__ __forceinline__ void k5c_build_nbrs(K5cShared& sh, int t) {
+  int n = 0, f = sh.flags[t] & ~K5F_SCANALL;
+  const D3 c0{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
+  K5C_FOR_COMPONENT(sh, t, u) {
+    if (u == t || sh.comp[u] != sh.comp[t] || sh.index[u] == sh.index[t]) continue;
+    const double lim = 0.5 * (sh.dmx[t] + sh.dmx[u]) + 1.0001 * (sh.bud[t] + sh.bud[u]) + 1e-9 * (sh.dmx[t] + sh.dmx[u]);
+    if (magSqr3(D3{sh.c0x[u], sh.c0y[u], sh.c0z[u]} - c0) > lim * lim) continue;
+    if (n < K5C_NP) sh.nbr[t][n++] = (unsigned char)u; else f |= K5F_SCANALL;
+  }
+  sh.nNbr[t] = (unsigned char)n;
+  sh.flags[t] = f;
+}
+// the slots to test against slot t for a contact: its list, or its whole component when the list overflowed
+#define K5C_FOR_PARTNERS(sh, t, u, ...)                                                      \
+  if ((sh).flags[t] & K5F_SCANALL) { K5C_FOR_COMPONENT(sh, t, u) { __VA_ARGS__ } }           \
+  else { for (int u##_q = 0; u##_q < (int)(sh).nNbr[t]; ++u##_q) { const int u = (sh).nbr[t][u##_q]; __VA_ARGS__ } }
+
 // next member with the same index after slot t, cyclically (needs index[] of every member)
 __device__ __forceinline__ void k5c_link_ring(K5cShared& sh, int t) {
   int nxt = -1, first = -1;
@@ -1458,23 +1480,25 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
   int code = 0;
   const int comp = sh.comp[t], idx = sh.index[t];
   const D3 c{sh.px[t], sh.py[t], sh.pz[t]}, v{sh.vx[t], sh.vy[t], sh.vz[t]};
-  K5C_FOR_COMPONENT(sh, t, u) {
+  bool other = false;
+  K5C_FOR_PARTNERS(sh, t, u, {
     if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
     const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
     const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
     if (magSqr3(cu - c) > R * R * (1.0 + 1e-9)) continue;             // (surely mag > R: spares the square root)
     if (mag3(cu - c) > R) continue;                                   // particleIBM.C:56-59
-    if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) return 2;  // contact law with history-free overlap force / ellipse iteration
+    if (m.model != 0 || !(f & K5F_ISO) || !(sh.flags[u] & K5F_ISO)) { other = true; continue; }  // overlap force without history / ellipse iteration
     if (!(R > mag3(cu - c))) continue;                                // particleIBM.C:60-74
     const D3 vu{sh.vx[u], sh.vy[u], sh.vz[u]};
     const bool iAmP1 = idx > sh.index[u];
     const D3 x12 = iAmP1 ? (c - cu) : (cu - c);
     const D3 v12 = iAmP1 ? (v - vu) : (vu - v);
     if (dot3(x12, v12) < 0) {
-      if ((f | sh.flags[u]) & K5F_MULTI) return 2;  // copies share the larger entry (particleCloud.C:525-554): general path
-      code = 1;
+      if ((f | sh.flags[u]) & K5F_MULTI) other = true;  // copies share the larger entry (particleCloud.C:525-554): general path
+      else code = 1;
     }
-  }
+  })
+  if (other) return 2;
   tPair += clock64() - tp0;
   if (f & K5F_NOPATCH) return code;
   if (!sh.patchesFit) return 2;
@@ -1509,10 +1533,11 @@ __device__ __forceinline__ D3 k5c_contact_sum(const K5cShared& sh, int t, const 
   int eIdx[4];
   D3 eF[4];
   int n = 0;
-  K5C_FOR_COMPONENT(sh, t, u) {
+  K5C_FOR_PARTNERS(sh, t, u, {
     if (u == t || sh.comp[u] != comp || sh.index[u] == idx || !(sh.flags[u] & K5F_ONMESH)) continue;
     const D3 cu{sh.px[u], sh.py[u], sh.pz[u]};
     const double R = 0.5 * (sh.dmx[t] + sh.dmx[u]);
+    if (magSqr3(cu - c) > R * R * (1.0 + 1e-9)) continue;
     if (mag3(cu - c) > R) continue;
     if (!(R > mag3(cu - c))) continue;
     const D3 vu{sh.vx[u], sh.vy[u], sh.vz[u]};
@@ -1531,7 +1556,7 @@ __device__ __forceinline__ D3 k5c_contact_sum(const K5cShared& sh, int t, const 
     int q = n++;
     while (q > 0 && eIdx[q - 1] > sh.index[u]) { eIdx[q] = eIdx[q - 1]; eF[q] = eF[q - 1]; --q; }
     eIdx[q] = sh.index[u]; eF[q] = myF;
-  }
+  })
   for (int q = 0; q < n; ++q) sum = sum + eF[q];
   return sum;
 }
@@ -1603,7 +1628,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   __syncthreads();
   for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_load(sh, t, m, in, classes, doCyclic);
   __syncthreads();
-  for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_link_ring(sh, t);
+  for (int t = tid; t < sh.nMem; t += K5C_THREADS) { k5c_link_ring(sh, t); k5c_build_nbrs(sh, t); }
   __syncthreads();
   // this block's view of the motion data: private candidate / hit lists, no instance-count bound (members are valid by construction)
   MotionDev ml = m;
@@ -1674,6 +1699,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       continue;
     }
     // ---- yes: this sub-step takes the general path on the global arrays ----
+    const int nMemBefore = sh.nMem;
     for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_store_state(sh, t, in);
     __syncthreads();
     if (m.moving) {
@@ -1806,7 +1832,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       }
       __syncthreads();
     }
-    for (int t = tid; t < sh.nMem; t += K5C_THREADS) { k5c_reload_state(sh, t, m, in); k5c_link_ring(sh, t); }
+    const bool grew = sh.nMem != nMemBefore;  // (block-uniform)
+    for (int t = tid; t < sh.nMem; t += K5C_THREADS) { k5c_reload_state(sh, t, m, in); k5c_link_ring(sh, t); if (grew) k5c_build_nbrs(sh, t); }
     __syncthreads();
     tGen += clock64() - t1;
     if (sh.fail) break;  // (block-uniform: written before the last barrier)
