@@ -1046,6 +1046,7 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
   if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_loop5") == 0) { c->clusterLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "cluster_one_block_cc") == 0) { c->clusterOneBlockCC = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_general_only") == 0) { c->clusterGeneralOnly = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }

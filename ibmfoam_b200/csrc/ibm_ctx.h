@@ -98,6 +98,7 @@ struct ibm_ctx {
   int markVariant = 0;            // 1 = k1_mark2 (compacted polar-bin phase), same outputs
   int collisionModel = 0;         // EXTENSION: 1 = soft-sphere contact law (ibm_motion.cu d5_pair_force); 0 = the reference's impulse
   double softKn = 0.0, softGammaN = 0.0, softGammaT = 0.0, softMu = 0.0;
+  bool clusterOneBlockCC = false;  // test hook: connected components by the single-block kernel
   bool clusterGeneralOnly = false; // test hook: every sub-step of a block takes the general path (no resident fast path)
   bool clusterLoop5 = true;       // split steps: independent groups of active instances, all sub-steps of a group in one block (k5c_run)
   bool fusedActive = false;       // split steps: the active list's sub-steps in one persistent cooperative kernel (k5a_fused)

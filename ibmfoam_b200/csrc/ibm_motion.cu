@@ -1250,6 +1250,32 @@ __global__ void __launch_bounds__(1024) k5c_components(MotionDev m) {
   }
 }
 
+// the same in rounds of two grid-wide kernels (hook the roots of every edge, then compress every path): the single block above
+// spends 0.19 ms on 2.5 x 10^4 active instances; a last hook pass with `check` raises clusterFail if an edge still joins two roots
+__global__ void k5c_cc_guard(MotionDev m) {
+  const int nE = min(*m.nEdge, m.edgeCap);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x)
+    if (m.quiet[m.edgeB[e]] || m.quiet[m.edgeA[e]]) atomicExch(m.clusterFail, 1);
+}
+__global__ void k5c_cc_hook(MotionDev m, int check) {
+  const int nE = min(*m.nEdge, m.edgeCap);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+    const int ra = m.label[m.edgeA[e]], rb = m.label[m.edgeB[e]];
+    if (ra != rb) {
+      if (check) atomicExch(m.clusterFail, 1);
+      else atomicMin(&m.label[max(ra, rb)], min(ra, rb));
+    }
+  }
+}
+__global__ void k5c_cc_compress(MotionDev m) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *m.nAct) return;
+  const int i = m.act[t];
+  int l = m.label[i];
+  while (m.label[l] != l) l = m.label[l];
+  m.label[i] = l;
+}
+
 __global__ void k5c_count(MotionDev m) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *m.nAct) return;
@@ -1327,6 +1353,7 @@ struct K5cShared {
   int index[K5C_CAP];
   int flags[K5C_CAP];     // K5F_*
   unsigned char nbr[K5C_CAP][K5C_NP], nNbr[K5C_CAP];  // members that can come within contact distance this step (from c0 and the budgets)
+  unsigned short pmask[K5C_CAP];            // walls (bits 0-7) and cyclic patches (bits 8-15) within reach + budget of where it started
   unsigned short ring[K5C_CAP];             // next member slot with the same index (circular; itself when alone)
   unsigned short cb[K5C_CAP], ce[K5C_CAP];  // slots [cb, ce) hold the component of the member as it was at the start of the step;
                                             // copies created since sit in [nMem0, nMem)
@@ -1373,20 +1400,21 @@ __device__ __forceinline__ void k5c_load(K5cShared& sh, int t, const MotionDev& 
   if (sh.patchesFit) {
     const D3 c0{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
     const double reach = sc->Rbound + 1.001 * sh.bud[t] + 1e-9 * m.binEdge;
-    bool near = false;
-    for (int w = 0; w < m.nWalls && !near; ++w) {
+    int mask = 0;
+    for (int w = 0; w < m.nWalls; ++w) {
       const K5cPatch& p = sh.wall[w];
       const double dx = fmax(fmax(p.lo[0] - c0.x, c0.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c0.y, c0.y - p.hi[1]), 0.0),
                    dz = fmax(fmax(p.lo[2] - c0.z, c0.z - p.hi[2]), 0.0);
-      near = dx * dx + dy * dy + dz * dz <= reach * reach;
+      if (dx * dx + dy * dy + dz * dz <= reach * reach) mask |= 1 << w;
     }
-    for (int q = 0; q < m.nCyc && !near && doCyclic; ++q) {
+    for (int q = 0; q < m.nCyc && doCyclic; ++q) {
       const K5cPatch& p = sh.cyc[q];
       const double dx = fmax(fmax(p.lo[0] - c0.x, c0.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c0.y, c0.y - p.hi[1]), 0.0),
                    dz = fmax(fmax(p.lo[2] - c0.z, c0.z - p.hi[2]), 0.0);
-      near = dx * dx + dy * dy + dz * dz <= reach * reach;
+      if (dx * dx + dy * dy + dz * dz <= reach * reach) mask |= 256 << q;
     }
-    if (!near) f |= K5F_NOPATCH;
+    sh.pmask[t] = (unsigned short)mask;
+    if (!mask) f |= K5F_NOPATCH;
   }
   sh.flags[t] = f;
 }
@@ -1503,10 +1531,12 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
   if (f & K5F_NOPATCH) return code;
   if (!sh.patchesFit) return 2;
   const double r = sh.rad[t];
+  const int pmask = sh.pmask[t];
   for (int w = 0; w < m.nWalls; ++w)
-    if (k5c_face_in_reach(sh.wall[w], L, c, r)) return 2;
+    if (((pmask >> w) & 1) && k5c_face_in_reach(sh.wall[w], L, c, r)) return 2;
   if (doCyclic)
     for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates + the reach of a face centre (d5_cyclic_detect)
+      if (!((pmask >> (8 + q)) & 1)) continue;
       const K5cPatch& p = sh.cyc[q];
       if (p.type != IBM_CYCLIC) continue;
       if (!k5c_face_in_reach(p, L, c, r)) continue;
@@ -1563,14 +1593,24 @@ __device__ __forceinline__ D3 k5c_contact_sum(const K5cShared& sh, int t, const 
 
 // member t over one sub-step: d5_solve with the given sum of contact forces (zero in free flight), zero contact torques and
 // empty wall tables, operation for operation
-__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt, D3 sFc, bool needActive) {
+// Free flight repeats two quotients with the same operands in every sub-step: F/m + g (contact sum zero) and dt T/(m I)
+// (one dt for all sub-steps but possibly the last); a thread keeps them for the members it steps.
+struct K5cCache { D3 acc; D3 dW; double dtW; int validAcc; };
+
+__device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, double dt, D3 sFc, bool contact,
+                                                bool needActive, K5cCache& ca) {
   if (!(sh.flags[t] & K5F_ONMESH)) return;
   if (m.moving) {
-    D3 sFw{0, 0, 0};
-    for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
-    const D3 F = D3{sh.Fx[t], sh.Fy[t], sh.Fz[t]} + sFc + sFw;
+    D3 acc;
+    if (contact || !ca.validAcc) {
+      D3 sFw{0, 0, 0};
+      for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
+      const D3 F = D3{sh.Fx[t], sh.Fy[t], sh.Fz[t]} + sFc + sFw;
+      acc = F / sh.mass[t] + D3{m.gx, m.gy, m.gz};
+      if (!contact) { ca.acc = acc; ca.validAcc = 1; }
+    } else acc = ca.acc;
     D3 v{sh.vx[t], sh.vy[t], sh.vz[t]};
-    v = v + dt * (F / sh.mass[t] + D3{m.gx, m.gy, m.gz});
+    v = v + dt * acc;
     sh.vx[t] = v.x; sh.vy[t] = v.y; sh.vz[t] = v.z;
     const D3 dx = dt * v;
     const D3 c = D3{sh.px[t], sh.py[t], sh.pz[t]} + dx;
@@ -1586,9 +1626,13 @@ __device__ __forceinline__ void k5c_free_flight(K5cShared& sh, int t, const Moti
   if (m.rotating) {
     D3 sTc{0, 0, 0}, sTw{0, 0, 0};
     for (int w = 0; w < m.nWalls; ++w) sTw = sTw + D3{0.0, 0.0, 0.0};
-    const D3 T = D3{sh.Tx[t], sh.Ty[t], sh.Tz[t]} + sTc + sTw;
+    if (ca.dtW != dt) {
+      const D3 T = D3{sh.Tx[t], sh.Ty[t], sh.Tz[t]} + sTc + sTw;
+      ca.dW = dt * T / sh.mI[t];
+      ca.dtW = dt;
+    }
     D3 om{sh.wx[t], sh.wy[t], sh.wz[t]};
-    om = om + dt * T / sh.mI[t];
+    om = om + ca.dW;
     sh.wx[t] = om.x; sh.wy[t] = om.y; sh.wz[t] = om.z;
     D3 th = D3{sh.tx[t], sh.ty[t], sh.tz[t]} + om * dt;
     if (th.z < 0) th.z += IBM_TWOPI;
@@ -1639,6 +1683,8 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const bool copies = m.nCyc > 0;
   const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
   long long tEv = 0, tFl = 0, tSp = 0, tGen = 0, tPair = 0, tEvOwn = 0;
+  K5cCache cache[(K5C_CAP + K5C_THREADS - 1) / K5C_THREADS];
+  for (auto& ca : cache) { ca.validAcc = 0; ca.dtW = -1.0; }
   const long long tStart = clock64();
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
@@ -1668,7 +1714,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       }
       int q = 0;
       for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
-        k5c_free_flight(sh, t, m, L, dt, (ev & 1) ? sums[q] : D3{0, 0, 0}, s == nSub - 1 || (sh.flags[t] & K5F_MULTI) != 0);
+        k5c_free_flight(sh, t, m, L, dt, (ev & 1) ? sums[q] : D3{0, 0, 0}, (ev & 1) != 0, s == nSub - 1 || (sh.flags[t] & K5F_MULTI) != 0, cache[q]);
         ++q;
         const double B = m.check * sh.bud[t];
         const D3 d0 = D3{sh.px[t], sh.py[t], sh.pz[t]} - D3{sh.c0x[t], sh.c0y[t], sh.c0z[t]};
@@ -1833,6 +1879,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
       __syncthreads();
     }
     const bool grew = sh.nMem != nMemBefore;  // (block-uniform)
+    if (grew) for (auto& ca : cache) { ca.validAcc = 0; ca.dtW = -1.0; }
     for (int t = tid; t < sh.nMem; t += K5C_THREADS) { k5c_reload_state(sh, t, m, in); k5c_link_ring(sh, t); if (grew) k5c_build_nbrs(sh, t); }
     __syncthreads();
     tGen += clock64() - t1;
@@ -2429,7 +2476,17 @@ static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
   cudaMemsetAsync(d.ctaEnd, 0, (size_t)d.ctaBins * sizeof(int), st);
   k_copy_int<<<1, 1, 0, st>>>(d.nextSlot, d.nInst);
   k5c_edges<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
-  k5c_components<<<1, 1024, 0, st>>>(d);
+  if (c->clusterOneBlockCC) {
+    k5c_components<<<1, 1024, 0, st>>>(d);
+  } else {
+    k5c_cc_guard<<<148, 256, 0, st>>>(d);
+    for (int round = 0; round < 12; ++round) {
+      k5c_cc_hook<<<148, 256, 0, st>>>(d, 0);
+      k5c_cc_compress<<<blocks_for(cap), 128, 0, st>>>(d);
+    }
+    k5c_cc_hook<<<148, 256, 0, st>>>(d, 1);  // not converged after 12 rounds (a chain of thousands of bodies): the step is redone unsplit
+    c->nLaunch += 25;
+  }
   k5c_count<<<blocks_for(cap), 128, 0, st>>>(d);
   size_t tb = M->scanTempBytes;
   cub::DeviceScan::ExclusiveSum(M->scanTemp, tb, d.compCnt, d.compOff, cap, st);
