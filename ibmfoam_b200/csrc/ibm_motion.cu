@@ -1484,21 +1484,20 @@ __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const Latti
   const double r2 = r * r * (1.0 + 1e-9) + 1e-300;
   if (!(dx * dx + dy * dy + dz * dz <= r2)) return false;
   if (!p.lattice) return true;
-  const double o3[3] = {L.ox, L.oy, L.oz}, d3[3] = {L.dx, L.dy, L.dz}, c3[3] = {c.x, c.y, c.z};
-  const int n3[3] = {L.nx, L.ny, L.nz};
-  double d2 = 0.0;
-  for (int a = 0; a < 3; ++a) {
-    if (a == p.axis) { const double e = c3[a] - p.lo[a]; d2 += e * e; continue; }
-    double t = floor((c3[a] - o3[a]) / d3[a]);
-    t = fmin(fmax(t, 0.0), (double)(n3[a] - 1));
-    const double e = c3[a] - (o3[a] + (t + 0.5) * d3[a]);
-    d2 += e * e;
-  }
-  return d2 <= r2 * (1.0 + 1e-9) + 1e-18 * (d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
+  // distance to the nearest face centre: the patch plane along its axis, the centre of the containing transverse cell otherwise
+  // (products with the inverse spacing: a rounding across a cell boundary picks a centre that is equally far away)
+  auto axisDist = [&](int a, double ca, double o, double d, int n, double plane) {
+    if (a == p.axis) return ca - plane;
+    double t = floor((ca - o) * (1.0 / d));
+    t = fmin(fmax(t, 0.0), (double)(n - 1));
+    return ca - (o + (t + 0.5) * d);
+  };
+  const double ex = axisDist(0, c.x, L.ox, L.dx, L.nx, p.lo[0]), ey = axisDist(1, c.y, L.oy, L.dy, L.ny, p.lo[1]),
+               ez = axisDist(2, c.z, L.oz, L.dz, L.nz, p.lo[2]);
+  const double d2 = ex * ex + ey * ey + ez * ez;
+  return d2 <= r2 * (1.0 + 1e-9) + 1e-18 * (L.dx * L.dx + L.dy * L.dy + L.dz * L.dz);
 }
 
-// Can anything but free flight happen to member t in this sub-step?  A superset of what the general path would act on:
-// a pair that overlaps and approaches (particleCloud.C:502-509), a wall or periodic patch within reach (particleIBM.C:453-517).
 // 0 = nothing, 1 = only contacts between isotropic single-instance bodies under the reference's impulse law (the resident path
 // evaluates them itself, k5c_contact_sum), 2 = anything else (the sub-step takes the general path)
 __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic, long long& tPair) {
