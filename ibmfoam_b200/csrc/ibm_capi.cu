@@ -207,9 +207,9 @@ static int upload_classes(ibm_ctx* c) {
 }
 
 static int alloc_instances(ibm_ctx* c, InstanceSoA& s, int cap) {
-  auto ai = [&](int** p) -> bool {
-    if (!ctx_cuda_ok(c, cudaMalloc(p, (size_t)cap * sizeof(int)), "cudaMalloc(instances)")) return false;
-    cudaMemset(*p, 0, (size_t)cap * sizeof(int));
+  auto ai = [&](int** p) -> bool {  // (one spare slot: ctx_update sends a flag behind the last instance's point count)
+    if (!ctx_cuda_ok(c, cudaMalloc(p, ((size_t)cap + 1) * sizeof(int)), "cudaMalloc(instances)")) return false;
+    cudaMemset(*p, 0, ((size_t)cap + 1) * sizeof(int));
     c->instAllocs.push_back(*p);
     return true;
   };
@@ -258,9 +258,14 @@ int ctx_update(ibm_ctx* c) {
     // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
     launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant);
     if (comm_ranks(c) > 1 && c->nInst > 0) {
-      // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs
-      int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst, 1);
+      // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs.  The shell
+      // overflow flag of this rank travels in the slot behind the last instance, so that every rank sees an overflow
+      // anywhere and all of them take the same path (retry together instead of one rank leaving the collectives)
+      launch_copy_int(c->stream, c->in.nPtsOnMesh + c->nInst, c->dScal + 4);
+      int rcc = comm_allreduce_sum(c, c->in.nPtsOnMesh, (size_t)c->nInst + 1, 1);
       if (rcc) return rcc;
+      launch_copy_int(c->stream, c->dScal + 4, c->in.nPtsOnMesh + c->nInst);
+      c->nLaunch += 2;
     }
     launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
     launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
@@ -275,10 +280,10 @@ int ctx_update(ibm_ctx* c) {
     // shell buffer too small (every rank takes the same path only if it overflows itself: the collective above is
     // re-entered by all ranks or none, because the rerun repeats it) -> grow and redo
     cudaFree(c->dShellCell); cudaFree(c->dShellJK);
-    c->shellCap = (int)std::min<long long>((long long)c->hScal[1] * 5 / 4 + 4096, 0x7fffffff);
+    c->shellCap = (int)std::min<long long>(std::max<long long>((long long)c->hScal[1] * 5 / 4 + 4096, (long long)c->shellCap * 2), 0x7fffffff);
     IBM_CUDA(c, cudaMalloc(&c->dShellCell, (size_t)c->shellCap * sizeof(int)));
     IBM_CUDA(c, cudaMalloc(&c->dShellJK, (size_t)c->shellCap * sizeof(int)));
-    if (comm_ranks(c) > 1) return ctx_fail(c, IBM_E_CAPACITY, "shell buffer overflow on a multi-rank run (unexpected: sized from the whole cloud)");
+    // (multi-rank: the flag was summed over the ranks above, so every rank is here and repeats the collective)
   }
   if (c->nInst > 0 && c->hScal[0] < c->nInst) {  // deleteInActiveParticles (particleCloud.C:940-950)
     launch_compact_instances(c->stream, c->in, c->in2, c->dKeep, c->dKeepOff, c->nInst);

@@ -92,7 +92,7 @@ struct ibm_ctx {
   bool chunk256 = false;    // direct-gather forcing kernel: 256 shell cells per work item (one item per d=8 sphere)
   bool fusedLoop5 = false;  // one persistent cooperative kernel for the sub-step loop
   bool graphLoop5 = true;   // else: the per-phase launch sequence of a fluid step replayed as a CUDA graph
-  bool activeLoop5 = false; // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
+  bool activeLoop5 = true;  // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
                             // sub-step; written after round 1's GPU budget was spent, verified under emulation only
   int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (>= 1: a quiet instance needs B_i >= s_i)
   int markVariant = 0;            // 1 = k1_mark2 (compacted polar-bin phase), same outputs

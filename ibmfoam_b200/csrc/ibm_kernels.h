@@ -121,6 +121,7 @@ void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const Ins
 void launch_exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total);
 void launch_aos_to_soa(cudaStream_t st, const LatticeDev& L, const double* aos, int nComp, double* soa);
 void launch_soa_to_aos(cudaStream_t st, const LatticeDev& L, const double* soa, int nComp, double* aos);
+void launch_copy_int(cudaStream_t st, int* dst, const int* src);
 void launch_clear_shell_cells(cudaStream_t st, const int* shellCell, int total, size_t C, double* F);
 
 }  // namespace ibm

@@ -180,6 +180,9 @@ void launch_aos_to_soa(cudaStream_t st, const LatticeDev& L, const double* aos, 
 void launch_soa_to_aos(cudaStream_t st, const LatticeDev& L, const double* soa, int nComp, double* aos) {
   k_soa_to_aos<<<grid_for(L.nCells, 256), 256, 0, st>>>(L, soa, nComp, aos);
 }
+__global__ void k_copy_one_int(int* dst, const int* src) { *dst = *src; }
+void launch_copy_int(cudaStream_t st, int* dst, const int* src) { k_copy_one_int<<<1, 1, 0, st>>>(dst, src); }
+
 void launch_clear_shell_cells(cudaStream_t st, const int* shellCell, int total, size_t C, double* F) {
   if (total > 0) k_clear_shell_cells<<<grid_for(total, 256), 256, 0, st>>>(shellCell, total, C, F);
 }

@@ -33,7 +33,7 @@ def _compare(oc, gc, exact=True, tol=1e-9):
 FUSED = [1]
 
 
-@pytest.fixture(autouse=True, params=["graph", "fused", "plain"])
+@pytest.fixture(autouse=True, params=["cluster", "graph", "fused", "plain"])
 def _loop5_mode(request):
     FUSED[0] = request.param
     yield
@@ -41,6 +41,7 @@ def _loop5_mode(request):
 
 def _gpu_cloud(case):
     gc = ParticleCloud(case)
+    gc.set_option("active_loop5", int(FUSED[0] == "cluster"))   # the library default: quiet / active split in cluster mode
     gc.set_option("fused_loop5", int(FUSED[0] == "fused"))
     gc.set_option("graph_loop5", int(FUSED[0] == "graph"))
     return gc

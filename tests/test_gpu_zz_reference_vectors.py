@@ -61,7 +61,7 @@ def test_marking_forcing_stress_against_reference_vectors(name):
     gc.close()
 
 
-@pytest.mark.parametrize("mode", ["graph", "plain"])
+@pytest.mark.parametrize("mode", ["cluster", "graph", "plain"])
 @pytest.mark.parametrize("name", ["col8", "wc2d_cyl", "wc3d_sph"])
 def test_trajectories_against_reference_vectors(name, mode):
     """Each fluid step: the F/T the reference used for that step go in, ibm_advance runs the literal 100/101 sub-step loop
@@ -69,6 +69,7 @@ def test_trajectories_against_reference_vectors(name, mode):
     kinematics must equal the reference's bit for bit."""
     case, g, n_steps = gu.load_dynamic(name)
     gc = ParticleCloud(case)
+    gc.set_option("active_loop5", int(mode == "cluster"))
     gc.set_option("fused_loop5", 0)
     gc.set_option("graph_loop5", int(mode == "graph"))
     for s in range(1, n_steps + 1):
