@@ -17,11 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # arithmetic has to match an x86-64 build of the reference bit for bit.
 UNITS = [
     ("ibm_kernels_ref.cu", ["-fmad=false"]),
-    ("ibm_kernels_fast.cu", []),
     ("ibm_kernels_v2.cu", []),
-    ("ibm_kernels_v3.cu", []),
-    ("ibm_kernels_v4.cu", []),
-    ("ibm_kernels_v5.cu", []),
     ("ibm_kernels_v7.cu", []),
     ("ibm_kernels_alpha.cu", ["-fmad=false"]),
     ("ibm_kernels_util.cu", []),

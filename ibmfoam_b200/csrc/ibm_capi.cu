@@ -298,7 +298,6 @@ int ctx_update(ibm_ctx* c) {
   c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;   // extent of the shell buffer in use
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
   c->updatesPerCall = c->nInst > 0 ? c->hScal[3] : 0;
-  if (schedule_fill_items(c->stream, c->sched, c->nInst, c->totalChunks)) return ctx_fail(c, IBM_E_CUDA, "schedule_fill_items failed");
   // I.ibm (particleCloud::updateI, particleCloud.C:952-969) is not an input of loops 2-5: it is refreshed with the cell
   // lists by definition (App. B #13) but only MATERIALISED when somebody asks for it (ibm_get_indicator) - an 8-byte
   // write per mesh cell and a kernel per update otherwise spent on a field nobody reads
@@ -326,26 +325,17 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
   }
   if (c->cfg.coupled) {  // particleCloud.C:1186-1189
     ctx_tic(c, T_FORCING);
-    const int fv = (c->forcingVariant >= 7 && !c->v7ok) ? 2 : c->forcingVariant;  // classes the staged kernel cannot take: direct gather
-    if (fv >= 7)
+    // 7 = staged kernel (ibm_kernels_v7.cu) where every shape class fits it, 0 = reference-order yardstick, anything else (and
+    // clouds the staged kernel cannot take: ellipses, very large bodies) = the direct-gather kernel (ibm_kernels_v2.cu)
+    const int fv = c->forcingVariant;
+    if (fv >= 7 && c->v7ok)
       launch_forcing_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
                         c->v7capF, c->dSlowList, c->dScal + 12, c->dScal + 13);
     else if (fv == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
-    else if (fv >= 5 && c->v5Forcing)
-      launch_forcing_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
-                        c->dScal + 7, fv >= 6);  // 6 = the same kernel with the stencils kept between field phases
-    else if (fv >= 4 && c->v4Forcing)
-      launch_forcing_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
-                        dS, dt, F);
-    else if (fv >= 3)
-      launch_forcing_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
-                        dS, dt, F);
-    else if (fv == 2)
+    else
       launch_forcing_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->totalChunks, c->dShellCell, c->dShellJK, dU, dUold,
                         dS, dt, F);
-    else
-      launch_forcing_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
     c->nLaunch++;
     ctx_toc(c);
     if (!dFext) c->fLive = true;
@@ -390,22 +380,14 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   double pRefOverRho = c->cfg.pRef / c->cfg.rhoRef;  // particleCloud.C:1213-1215
   if (!c->dTcorr) IBM_CUDA(c, cudaMalloc(&c->dTcorr, (size_t)3 * c->cap * sizeof(double)));
   ctx_tic(c, T_STRESS);
-  const int sv = (c->stressVariant >= 7 && !c->v7ok) ? 4 : c->stressVariant;
-  if (sv >= 7)
+  const int sv = c->stressVariant;
+  if (sv >= 7 && c->v7ok)
     launch_stress_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->v7capS,
                      c->dSlowList, c->dScal + 12, c->dScal + 13);
   else if (sv == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
-  else if (sv >= 5 && c->v4Stress)  // same tables and box as the fourth generation
-    launch_stress_v5(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
-  else if (sv >= 4 && c->v4Stress)
-    launch_stress_v4(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->dScal + 6);
-  else if (sv >= 3)
-    launch_stress_v3(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
-  else if (sv == 2)
-    launch_stress_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   else
-    launch_stress_fast(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
+    launch_stress_v2(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   c->nLaunch++;
   ctx_toc(c);
   IBM_CUDA(c, cudaGetLastError());
@@ -600,28 +582,6 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   }
   int rc = upload_classes(c);
   if (rc) return rc;
-  {
-    // fourth-generation kernels need the class tables and the staged box to fit their shared-memory budget
-    c->v4Stress = c->v4Forcing = c->v5Forcing = !c->classes.empty();
-    const double d3[3] = {c->L.dx, c->L.dy, c->L.dz};
-    for (auto& h : c->classes) {
-      const ShapeClassDev& s = h.dev;
-      bool tab = s.kind != IBM_ELLIPSE && s.nTheta <= V4_MAX_NTHETA && s.nk <= V4_MAX_NK;
-      auto cells = [&](double reach) {
-        long long n = 1;
-        for (int q = 0; q < 3; ++q) {
-          long long e = (long long)std::ceil(2.0 * reach / d3[q]) + 3;  // floor(x+y)-floor(x) <= ceil(y), +1 inclusive, +2 margins
-          const int nq = q == 0 ? c->L.nx : (q == 1 ? c->L.ny : c->L.nz);
-          e = std::min<long long>(e, nq);
-          n *= (q == 0) ? (e | 1) : e;
-        }
-        return n;
-      };
-      if (!tab || cells(s.Rbound) > V4_STRESS_BOX) c->v4Stress = false;
-      if (!tab || cells(s.Rbound + s.delta) > V4_FORCING_BOX) c->v4Forcing = false;
-      if (!tab || cells(s.Rbound + s.delta) > V5_FORCING_BOX) c->v5Forcing = false;
-    }
-  }
   {
     std::vector<ShapeClassDev> hc;
     for (auto& h : c->classes) hc.push_back(h.dev);

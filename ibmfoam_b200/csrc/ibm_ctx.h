@@ -76,10 +76,8 @@ struct ibm_ctx {
   double* hPinned = nullptr;  // small pinned scratch for results
   size_t hPinnedDoubles = 0;
 
-  bool v4Stress = false, v4Forcing = false;  // every shape class fits the fourth-generation kernels (tables + staged box)
-  bool v5Forcing = false;                    // ... and the fifth-generation forcing kernel (its box is a little smaller)
-  // 0 reference-order, 1 first tuned, 2 scheduled + de-duplicated, 3 + shared-memory staging, 4 lean staging,
-  // 5 one CTA per instance + cp.async staging (not yet measured on hardware: selected explicitly only)
+  // kernel generation of loops 2-4: 0 reference-order (every sum and division as coded: the on-device yardstick), 2 direct gather
+  // with Morton-scheduled work items (round-1 default; now the path for clouds the staged kernels cannot take),
   // 7 one CTA per instance, ball-row staging of combined fields (round-2 default where every class fits: v7ok)
   int forcingVariant = 7, stressVariant = 7;
   bool v7ok = false;              // every shape class can take the seventh-generation kernels (no ellipse, tables + region fit)

@@ -38,21 +38,13 @@ void launch_forcing_ref(cudaStream_t st, const LatticeDev& L, const ShapeClassDe
 void launch_stress_ref(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
 
-// ---- ibm_kernels_fast.cu ----
-void launch_forcing_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                         const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S, double dT,
-                         double* F);
-void launch_stress_fast(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                        const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
-
 // ---- schedule (ibm_kernels_util.cu): Morton-sorted instance order + table of <=FORCING_CHUNK-cell work items ----
 #define FORCING_CHUNK 128
 struct Schedule {
   unsigned* keys = nullptr; unsigned* keysSorted = nullptr;
   int* iota = nullptr; int* order = nullptr;      // order[pos] = instance scheduled at position pos
   int* chunkCnt = nullptr; int* chunkOff = nullptr;  // per sorted position; chunkOff has n+1 entries
-  int* itemPos = nullptr; int itemCap = 0;           // sorted position of every work item (filled on demand)
-  int chunk = FORCING_CHUNK;                         // shell cells per work item (128: staged kernels, 256: direct-gather v2)
+  int chunk = FORCING_CHUNK;                         // shell cells per work item of the direct-gather kernel (128, or 256 with option chunk256)
   void* temp = nullptr; size_t tempBytes = 0;
   int cap = 0;
 };
@@ -66,32 +58,6 @@ void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
                        const double* Uold, const double* S, double dT, double* F);
 void launch_stress_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
-
-void launch_forcing_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                       const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
-                       const double* Uold, const double* S, double dT, double* F);
-void launch_stress_v3(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
-
-// ---- ibm_kernels_v4.cu ----
-#define V4_MAX_NTHETA 256
-#define V4_MAX_NK 128
-#define V4_STRESS_BOX 1792
-#define V4_FORCING_BOX 2560
-void launch_forcing_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                       const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
-                       const double* Uold, const double* S, double dT, double* F);
-int schedule_fill_items(cudaStream_t st, Schedule& s, int nInst, int totalChunks);
-void launch_stress_v4(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
-
-// ---- ibm_kernels_v5.cu (kernels in ibm_kernels_v5.cuh): one CTA per instance, cp.async box staging, forcing split by field ----
-#define V5_FORCING_BOX 2208
-void launch_forcing_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
-                       const double* S, double dT, double* F, int* dFallback, bool cacheStencils = false);
-void launch_stress_v5(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, int* dFallback);
 
 // ---- ibm_kernels_v7.cu: one CTA per instance, ball-row staging of combined fields, gathers from shared memory ----
 struct V7Caps { int planeCap, colCap, rowsCap, mapCap, nTcap, nkCap, elemCap; };  // shared-memory capacities of a launch (doubles / entries)

@@ -125,22 +125,8 @@ int schedule_alloc(Schedule& s, int cap) {
   A(&s.temp, s.tempBytes);
   return e == cudaSuccess ? 0 : -1;
 }
-__global__ void k_item_pos(const int* __restrict__ chunkOff, int n, int* __restrict__ itemPos) {
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= n) return;
-  for (int it = chunkOff[pos]; it < chunkOff[pos + 1]; ++it) itemPos[it] = pos;
-}
-int schedule_fill_items(cudaStream_t st, Schedule& s, int nInst, int totalChunks) {
-  if (totalChunks > s.itemCap) {
-    if (s.itemPos) cudaFree(s.itemPos);
-    s.itemCap = totalChunks + totalChunks / 4 + 1024;
-    if (cudaMalloc((void**)&s.itemPos, (size_t)s.itemCap * sizeof(int)) != cudaSuccess) { s.itemPos = nullptr; s.itemCap = 0; return -1; }
-  }
-  if (nInst > 0 && totalChunks > 0) k_item_pos<<<(nInst + 255) / 256, 256, 0, st>>>(s.chunkOff, nInst, s.itemPos);
-  return 0;
-}
 void schedule_free(Schedule& s) {
-  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp, s.itemPos};
+  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp};
   for (void* p : ps) if (p) cudaFree(p);
   s = Schedule{};
 }

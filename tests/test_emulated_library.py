@@ -35,12 +35,13 @@ SUBSET = [
     "tests/test_gpu_marking.py::test_marking_bit_exact",
     "tests/test_gpu_zz_reference_vectors.py::test_marking_forcing_stress_against_reference_vectors",
     "tests/test_gpu_zz_reference_vectors.py::test_trajectories_against_reference_vectors[col8-graph]",
-    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned-5]",
-    "tests/test_zzz_gpu_v5_kernels.py::test_forcing_v5_parity[aligned-6]",
-    "tests/test_zzz_gpu_v5_kernels.py::test_stress_v5_parity[wc3d]",
-    "tests/test_zzz_gpu_v5_kernels.py::test_solid_fraction_extension_matches_its_definition",
+    "tests/test_gpu_v7_kernels.py",
+    "tests/test_zzz_gpu_solid_fraction.py",
     "tests/test_zzz_gpu_active_loop5.py::test_copy_created_after_a_rebound_next_to_a_resting_body[fused]",
+    "tests/test_zzz_gpu_active_loop5.py::test_copy_created_after_a_rebound_next_to_a_resting_body[cluster]",
     "tests/test_zzz_gpu_active_loop5.py::test_two_spheres_head_on[fused]",
+    "tests/test_zzz_gpu_active_loop5.py::test_two_spheres_head_on[cluster]",
+    "tests/test_gpu_zz_reference_vectors.py::test_trajectories_against_reference_vectors[wc2d_cyl-cluster]",
     "tests/test_gpu_motion.py::test_two_spheres_head_on_closed_form[fused]",
     "tests/test_zzz_gpu_soft_sphere.py",
     "tests/test_zzz_gpu_mark_variant.py",
@@ -87,7 +88,7 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
 
 @pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (several minutes)")
 @pytest.mark.parametrize("path", ["tests/test_gpu_forcing.py", "tests/test_gpu_marking.py", "tests/test_gpu_stress.py", "tests/test_gpu_motion.py",
-                                  "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_zzz_gpu_v5_kernels.py", "tests/test_zzz_gpu_active_loop5.py",
+                                  "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_gpu_v7_kernels.py", "tests/test_zzz_gpu_solid_fraction.py", "tests/test_zzz_gpu_active_loop5.py",
                                   "tests/test_zz_gpu_validation_cases.py", "tests/test_zzz_gpu_soft_sphere.py", "tests/test_zzz_gpu_mark_variant.py"])
 def test_gpu_parity_file_under_emulation(emu_lib, path):
     _child(emu_lib, [path], timeout=6000)
@@ -107,6 +108,6 @@ def test_bench_control_flow_dry_run(emu_lib):
         assert key in line, key
     assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0
     kg = line["config"]["kernel_generations"]
-    assert kg["probe"]["ok"] and kg["probe"]["kernels_ok"] and kg["probe"]["loop5_split_ok"]
+    assert kg["forcing"] == 7 and kg["stress"] == 7
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key

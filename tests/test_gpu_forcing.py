@@ -35,7 +35,7 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 7])
+@pytest.mark.parametrize("variant", [0, 2, 7])   # reference-order yardstick, direct gather, staged
 def test_forcing_parity(name, variant):
     case = CASES[name]()
     f = util.caller_fields(case)

@@ -17,7 +17,7 @@ def _err(a, b):
 
 
 @pytest.mark.parametrize("name", ["cyl30", "sph48", "asm48", "col", "ellipse2"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 7])
+@pytest.mark.parametrize("variant", [0, 2, 7])   # reference-order yardstick, direct gather, staged
 def test_stress_parity(name, variant):
     case = {"cyl30": cases.cylinder_re30, "sph48": lambda: cases.sphere_case(n=48), "asm48": lambda: util.small_assembly(48, 40),
             "col": cases.colliding_particles, "ellipse2": util.ellipse_case}[name]()

@@ -35,7 +35,7 @@ def test_marking_forcing_stress_against_reference_vectors(name):
     assert np.array_equal(gc.indicator(), gu.indicator(g, case.mesh.n_cells))
     f = util.caller_fields(case)
     Fref = gu.dense_forcing(g, case.mesh.n_cells)
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 2, 7):
         gc.set_kernel_variant(forcing=variant, stress=variant)
         F = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
         err = util.rel_err(F, Fref)
@@ -46,7 +46,7 @@ def test_marking_forcing_stress_against_reference_vectors(name):
             scale = np.max(np.linalg.norm(ref[:, sl], axis=1))
             e2 = float(np.max(np.abs(FT[:, sl] - ref[:, sl])) / scale)
             assert e2 < (1e-13 if variant == 0 else 1e-10), (variant, e2)        # tolerance: 1e-10 relative
-    assert gc.timings()["n_updates"] == 5 * int(g["forcing_updates"])
+    assert gc.timings()["n_updates"] == 3 * int(g["forcing_updates"])
     gc.combineForces()
     st = gc.state_arrays()
     ref = g["combined_FT"]
