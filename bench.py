@@ -1,26 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the immersed-boundary hot path (BASELINE.json metric: IB cell-particle updates/s).
 
-A "step" is one fluid time step of the IB path over the synthetic scale-up workload (512^3 periodic box,
-10^5 moving spheres d = 8 cells): particleCloud::forcing (nOuter = 1) + particleCloud::solve (surface-stress
-integral, force combination, the literal sub-step loop, re-marking).  One cell-particle update = one
+A "step" is one fluid time step of the IB path over the synthetic scale-up workload (512^3 periodic box, 10^5 moving
+spheres d = 8 cells): particleCloud::forcing (nOuter = 1) + particleCloud::solve (surface-stress integral, force combination,
+the literal 100/101 sub-step loop with collisions and periodic copies, re-marking).  One cell-particle update = one
 (shell cell, particle instance) pair receiving its forcing contribution.
 
-  value     device-resident: SoA fields already in HBM, kernels only
-  e2e       through the host C-ABI calls with pinned host AoS fields, H2D/D2H inside the timed region
-  roofline  forcing kernel: algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, rank 0, N = 1 only;
-                next to it the reference's OWN code (oracle/_ref, compiled from /root/reference against oracle/mockfoam)
-                on a smaller sample it can finish (it allocates a labelList(nFaces) per shape point per update)
-  --impl reference   the reference arm: oracle/_ref when that library exists, else the port; all host cores
+  value         device-resident: SoA fields already in HBM, the library's kernels only (CUDA events on its stream)
+  e2e           through the host C-ABI calls ibm_forcing + ibm_solve with HOST arrays in OpenFOAM's layout, copies inside the
+                timed region: U, U.oldTime and p registered once with ibm_host_register (fields that live in the mesh registry),
+                S, devRhoReff and the returned F in ordinary pageable memory (temporaries of the solver), i.e. what
+                shim/particleCloud.C hands over
+  roofline      forcing kernel: algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
+  cpu_baseline  rank 0, N = 1 only: the CPU oracle (restatement, fast search) on one core AND on all cores, and the reference's
+                own code as coded (oracle/_ref) on a box it can finish; every sample is a moving assembly of the workload's
+                shape and solid fraction and runs the SAME step (forcing + solve with the sub-step loop)
+  --impl reference   the reference arm: oracle/_ref (the reference's own sources against oracle/mockfoam) when present, else the
+                port, one process per host core like the reference's one-MPI-rank-per-subdomain model
 
-  kernel generations   forcing v2 + stress v4 are the measured defaults.  The fifth generation (one CTA per particle,
-                cp.async staging; 6 = the same forcing kernel keeping its stencils between field phases), the
-                second marking kernel and the loop-5 split were written after the round's GPU budget was spent: each is only used when
-                a child process on this very box shows parity with the defaults AND a lower time, and a second check at
-                the full size agrees; config.kernel_generations records what ran and why (--no-probe: defaults only).
-
-python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128] [--variant G | --no-probe] [--split 0|1|2] [--mark 0|1]
+python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload big512|big256|asm128]
+                [--variant G] [--split 0|1] [--no-e2e] [--no-cpu-baseline]
 """
 from __future__ import annotations
 
@@ -184,25 +183,27 @@ def run_step_device(cloud, ptrs, dt, have_motion):
 
 
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libibm_ref.so")
-REF_SAMPLE_N = 32   # the as-coded reference costs O(nFaces) per shape point per update: 0.8 s per step at 32^3, 10 s at 48^3
+PORT_SAMPLE_N = 64  # the port's loop 5 visits all ordered pairs like the reference (particleCloud.C:484-523): 196 spheres per box
+REF_SAMPLE_N = 32   # the as-coded reference costs O(nCells) per particle and O(nFaces) per shape point per update
 
 
-def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345, impl="port", max_steps=8):
-    """A CPU implementation of the path (1 thread, like one MPI rank of the reference) on a bounded sample of the same
-    workload: an n^3 periodic box at the same solid fraction and particle shape.  impl="port": the oracle restatement
-    (fast ijk search); impl="reference": the reference's own code as coded (oracle/_ref)."""
+def cpu_sample(seconds_budget=12.0, n=64, seed=12345, impl="port", max_steps=6):
+    """One CPU implementation of the SAME step (forcing + solve: stress integral, force combination, the literal sub-step
+    loop, re-marking) on a bounded sample of the workload: an n^3 periodic box of moving spheres d = 8 at the workload's solid
+    fraction and velocity distribution.  impl="port": the oracle restatement (fast ijk search); impl="reference": the
+    reference's own code as coded (oracle/_ref).  One thread, like one MPI rank of the reference."""
     from ibmfoam_b200 import cases
     from oracle.pyoracle import OracleCloud
     import ibm_testutil as util
-    case = cases.assembly(n=n, moving=False, seed=seed)
+    # (the reference as coded never creates periodic copies in a box without wall patches, particleCloud.C:661-664, App. B #10)
+    case = cases.assembly(n=n, moving=True, seed=seed, cyclic_without_walls=(impl != "reference"))
     f = util.caller_fields(case)
     oc = OracleCloud(case, impl=impl)
     t0 = time.perf_counter()
     steps, updates = 0, 0
     while True:
         _, nu = oc.forcing(f["U"], f["Uold"], f["S"], case.dt)
-        oc.integrate_stress(f["p"], f["tau"])
-        oc.update()
+        oc.solve(f["p"], f["tau"], case.dt)
         steps += 1
         updates += nu
         if time.perf_counter() - t0 > seconds_budget or steps >= max_steps:
@@ -211,260 +212,57 @@ def cpu_baseline_sample(seconds_budget=20.0, n=128, seed=12345, impl="port", max
     return updates / el, steps, el, case.particles.n
 
 
-# ------------------------------------------------------------------------------------------------
-# kernel-generation probe.  The fifth-generation forcing / stress kernels were written after the GPU budget of round 1 was
-# spent: they are only used if, ON THIS BOX, a child process shows that they (a) agree with the default
-# generation on a small assembly and (b) are faster on a 256^3 workload.  A child process, so that a kernel fault or a
-# hang cannot take the measurement down: any failure just keeps the defaults.
-# ------------------------------------------------------------------------------------------------
-DEFAULT_VARIANTS = {"forcing": 7, "stress": 7}   # the library defaults (round 2): staged seventh-generation kernels
-DEFAULT_SPLIT = 1                                 # loop 5: quiet / active split in cluster mode (library option active_loop5)
-PROBE_CACHE = os.path.join("/tmp", "ibmfoam_b200_probe.json")
+def _sample_worker(args):
+    seed, budget, n, impl, max_steps = args
+    return cpu_sample(budget, n, seed, impl, max_steps)
 
 
-def _time_loop5(big, mode):
-    """ms per fluid step of loop 5 (+ re-marking) at the workload's own instance count; mode as in run_probe"""
-    from ibmfoam_b200.cloud import ParticleCloud
-    gc = ParticleCloud(big, device=0)
-    gc.set_option("active_loop5", int(mode > 0))
-    gc.set_option("fused_active_loop5", int(mode == 2))
-    for _ in range(2):
-        gc.advance(big.dt)
-    gc.sync()
-    gc.timings(reset=True)
-    for _ in range(4):
-        gc.advance(big.dt)
-    gc.sync()
-    ms = gc.timings()["advance_ms"] / 4
-    gc.close()
-    return ms
-
-
-def run_probe(args):
-    """child: python bench.py --probe  ->  one JSON line {"ok", "forcing_ms": {gen: ms}, "stress_ms": {gen: ms}, ...}"""
-    import torch
-    from ibmfoam_b200 import cases
-    from ibmfoam_b200.cloud import ParticleCloud
-    import ibm_testutil as util
-    out = {"ok": False}
-    # (a) parity against the default generation, through the host C ABI
-    case = cases.assembly(n=64, n_particles=150, seed=3, moving=True, cyclic_without_walls=True)
-    f = util.caller_fields(case)
-    res = {}
-    for gen in (() if args.probe_fused else (None, 5, 6)):   # 6 = forcing v5 keeping its stencils between field phases (stress: 5)
-        gc = ParticleCloud(case)
-        if gen is not None:
-            gc.set_kernel_variant(gen, min(gen, 5))
-        F = gc.forcing(f["S"], f["U"], f["Uold"], case.dt)
-        FT = gc.integrateSurfaceStresses(f["p"], f["tau"])
-        res[gen] = (F, FT)
-        gc.close()
-    if not args.probe_fused:
-        eF = float(np.max(np.abs(res[5][0] - res[None][0])) / np.max(np.abs(res[None][0])))
-        eT = float(np.max(np.abs(res[5][1] - res[None][1])) / np.max(np.abs(res[None][1])))
-        out.update({"forcing_rel_diff": eF, "stress_rel_diff": eT})
-        out["kernels_ok"] = bool(eF < 1e-11 and eT < 1e-9)
-        eF6 = float(np.max(np.abs(res[6][0] - res[None][0])) / np.max(np.abs(res[None][0])))
-        out["forcing6_rel_diff"] = eF6
-        out["forcing6_ok"] = bool(eF6 < 1e-11)
-    if not args.probe_fused:
-        # the second marking kernel must produce the very same shell lists and statuses
-        ga, gb = ParticleCloud(case), ParticleCloud(case)
-        gb.set_option("mark_variant", 1)
-        gb.update()
-        sa, sb = ga.state_arrays(), gb.state_arrays()
-        same = all(np.array_equal(sa[k], sb[k]) for k in ("nShell", "onMesh", "active", "N"))
-        for inst in range(ga.nParticles()):
-            if not same:
-                break
-            x, y = ga.shell(inst), gb.shell(inst)
-            same = np.array_equal(x["cells"], y["cells"]) and np.array_equal(x["jk"], y["jk"])
-        out["mark2_ok"] = bool(same)
-        ga.close(); gb.close()
-    # the quiet/active split of loop 5 must give the very same trajectory as the unsplit path (bit for bit)
-    fast = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
-    fast.particles.v *= 25.0
-    fast.dt = 0.5
-    traj = {}
-    modes = (0, 2) if args.probe_fused else (0, 1)   # 0 = unsplit chain, 1 = quiet/active split, 2 = split with the active
-    for split in modes:                               # list in one cooperative kernel (probed by a child of its own)
-        gc = ParticleCloud(fast)
-        gc.set_option("active_loop5", int(split > 0))
-        gc.set_option("fused_active_loop5", int(split == 2))
-        rng = np.random.default_rng(0)
-        for _ in range(4):
-            gc.set_force_torque(rng.normal(0, 1e-3, (gc.nParticles(), 6)))
-            gc.combineForces()
-            gc.advance(fast.dt)
-        traj[split] = gc.state_arrays()
-        gc.close()
-    key = "loop5_fused_active_ok" if args.probe_fused else "loop5_split_ok"
-    out[key] = bool(all(np.array_equal(traj[0][k], traj[modes[1]][k]) for k in traj[0]))
-    if args.probe_fused:
-        out["advance_ms"] = {}
-        if out[key]:
-            big = make_case(args.workload)
-            if big.cloud.moving:
-                out["advance_ms"]["2"] = _time_loop5(big, 2)
-        out["ok"] = True
-        print(json.dumps(out))
-        return
-    if not (out["kernels_ok"] or out["forcing6_ok"] or out["loop5_split_ok"] or out["mark2_ok"]):
-        print(json.dumps(out))
-        return
-    t = {"forcing_ms": {}, "stress_ms": {}, "advance_ms": {}, "update_ms": {}}
-    # (b) loop 5 at the run's own instance count (it needs the particles, not the fields): without / with the split
-    if out["loop5_split_ok"] or out["mark2_ok"]:
-        big = make_case(args.workload)
-        if big.cloud.moving and out["loop5_split_ok"]:
-            for split in (0, 1):
-                t["advance_ms"][str(split)] = _time_loop5(big, split)
-        if out["mark2_ok"]:
-            gc = ParticleCloud(big, device=0)
-            for mv in (0, 1):
-                gc.set_option("mark_variant", mv)
-                for _ in range(2):
-                    gc.update()
-                gc.sync()
-                gc.timings(reset=True)
-                for _ in range(4):
-                    gc.update()
-                gc.sync()
-                t["update_ms"][str(mv)] = gc.timings()["update_ms"] / 4
-            gc.close()
-        del big
-    # (c) forcing / stress kernels on a 256^3 / 12.5k-sphere workload, device-resident fields
-    case = make_case("big256")
-    dev = torch.device("cuda", 0)
-    U, Uold, S, P, Tau = device_fields(case.mesh, dev)
-    torch.cuda.synchronize()
-    cloud = ParticleCloud(case, device=0)
-    for gen_f, gen_s in ((DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]), (5, 5), (6, 5)):
-        cloud.set_kernel_variant(gen_f, gen_s)
-        for _ in range(2):
-            cloud.forcing_device(U.data_ptr(), Uold.data_ptr(), S.data_ptr(), case.dt)
-            cloud.integrate_stress_device(P.data_ptr(), Tau.data_ptr())
-        cloud.sync()
-        cloud.timings(reset=True)
-        for _ in range(5):
-            cloud.forcing_device(U.data_ptr(), Uold.data_ptr(), S.data_ptr(), case.dt)
-            cloud.integrate_stress_device(P.data_ptr(), Tau.data_ptr())
-        cloud.sync()
-        tm = cloud.timings()
-        t["forcing_ms"][str(gen_f)] = tm["forcing_ms"] / 5
-        t["stress_ms"][str(gen_s)] = tm["stress_ms"] / 5
-    cloud.close()
-    out.update(t)
-    out["ok"] = True
-    print(json.dumps(out))
-
-
-def choose_variants(local_rank, timeout_s=300, workload="big512"):
-    """parent: run the probe in a child process on this rank's GPU (or reuse the result an earlier run on this box left in
-    /tmp) and pick, per kernel, the faster verified generation.  Returns (forcing, stress, info)."""
-    info = None
-    try:
-        if os.path.exists(PROBE_CACHE) and time.time() - os.path.getmtime(PROBE_CACHE) < 6 * 3600:
-            with open(PROBE_CACHE) as fh:
-                info = json.load(fh)
-            info["cached"] = True
-    except Exception:
-        info = None
-    if info is None:
-        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
-                                                                "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        ids = vis.split(",") if vis else None
-        env["CUDA_VISIBLE_DEVICES"] = ids[local_rank] if ids and local_rank < len(ids) else str(local_rank)
-        def child(flag, limit):
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, "--workload", workload], capture_output=True, text=True,
-                                   timeout=limit, env=env)
-                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-                return json.loads(line[-1]) if (r.returncode == 0 and line) else {"ok": False, "error": (r.stderr or "no output")[-300:]}
-            except Exception as ex:  # timeout, crash, malformed output: keep the defaults
-                return {"ok": False, "error": repr(ex)[:300]}
-
-        info = child("--probe", timeout_s)
-        if info.get("ok") and info.get("loop5_split_ok"):
-            # the persistent cooperative kernel of the active list gets a child (and a shorter leash) of its own: a
-            # grid-wide barrier that never completes on this box must not cost the other results
-            fused = child("--probe-fused", 100)
-            info["loop5_fused_active_ok"] = bool(fused.get("ok") and fused.get("loop5_fused_active_ok"))
-            if info["loop5_fused_active_ok"]:
-                info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
-            elif not fused.get("ok"):
-                info["loop5_fused_active_error"] = fused.get("error", "")[:200]
-        try:
-            with open(PROBE_CACHE, "w") as fh:
-                json.dump(info, fh)
-        except Exception:
-            pass
-    fv, sv, split, mark = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], 0, 0
-    if info.get("ok"):
-        um = info.get("update_ms", {})
-        if info.get("mark2_ok") and um.get("1", 1e30) < um.get("0", 0.0):
-            mark = 1
-        fm, sm, am = info.get("forcing_ms", {}), info.get("stress_ms", {}), info.get("advance_ms", {})
-        best_f = fm.get(str(fv), 0.0)
-        for gen, key in ((5, "kernels_ok"), (6, "forcing6_ok")):
-            if info.get(key) and fm.get(str(gen), 1e30) < best_f:
-                fv, best_f = gen, fm[str(gen)]
-        if info.get("kernels_ok") and sm.get("5", 1e30) < sm.get(str(sv), 0.0):
-            sv = 5
-        best = am.get("0", 0.0)
-        for mode, key in ((1, "loop5_split_ok"), (2, "loop5_fused_active_ok")):
-            if info.get(key) and am.get(str(mode), 1e30) < best:
-                split, best = mode, am[str(mode)]
-    return fv, sv, split, mark, info
-
-
-def _ref_worker(args):
-    seed, budget, n, impl = args
-    return cpu_baseline_sample(budget, n, seed, impl)
+def all_cores_sample(impl, n, budget, max_steps, cores=None):
+    import multiprocessing as mp
+    cores = cores or (os.cpu_count() or 1)
+    with mp.Pool(cores) as pool:
+        res = pool.map(_sample_worker, [(1000 + 17 * r, budget, n, impl, max_steps) for r in range(cores)])
+    return sum(r[0] for r in res), cores, max(r[2] / r[1] for r in res), res[0][3], min(r[1] for r in res)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores, one process per core
-    like the reference's one-MPI-rank-per-subdomain model.  oracle/_ref (the reference's sources compiled against
-    oracle/mockfoam) when that library exists, else the oracle port."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  The as-coded reference scans
+    every mesh cell per particle (sphere.C:198-243) and allocates a labelList(nFaces) per shape point per update
+    (particleShape.C:54): big512 itself is out of its reach by orders of magnitude, so each step is a bounded sample of
+    that workload, as the measurement contract prescribes - one 32^3 periodic sub-box of moving spheres per core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     from oracle import pyoracle
-    cores = os.cpu_count() or 1
     impl = "reference" if (os.path.exists(REF_LIB) or os.path.isdir(pyoracle.REFERENCE_SRC)) else "port"
     pyoracle.lib(impl)  # build / load once in the parent; the forked workers inherit it
-    n = REF_SAMPLE_N if impl == "reference" else 128
-    budget = 12.0
+    n = REF_SAMPLE_N if impl == "reference" else PORT_SAMPLE_N
     vals, per_step = [], []
     t_all = time.perf_counter()
+    cores = os.cpu_count() or 1
+    npart = 0
     for it in range(args.warmup + args.steps):
-        if it == args.warmup:
-            t_all = time.perf_counter()
-        with mp.Pool(cores) as pool:
-            res = pool.map(_ref_worker, [(1000 + 17 * it + r, budget if it >= args.warmup else 1.0, n, impl) for r in range(cores)])
-        if it >= args.warmup:
-            vals.append(sum(r[0] for r in res))
-            per_step.append(max(r[2] / r[1] for r in res))
-        if time.perf_counter() - t_all > 150:
+        timed = it >= args.warmup
+        v, cores, step_s, npart, _ = all_cores_sample(impl, n, 10.0 if timed else 1.0, 4 if timed else 1)
+        if timed:
+            vals.append(v)
+            per_step.append(step_s)
+        if time.perf_counter() - t_all > 170 and vals:
             break
     v = float(np.mean(vals))
-    npart = res[0][3]
     if impl == "reference":
-        note = ("the reference's own sources (particleShape/sphere/particleIBM/particleCloud .C) compiled against oracle/mockfoam, "
-                "as coded: O(nCells) marking scan per particle and a labelList(nFaces) per shape point per update")
-        how = "as coded"
+        how = ("the reference's own sources (particleShape/sphere/particleIBM/particleCloud .C) compiled against oracle/mockfoam, as coded")
     else:
-        note, how = "reference algorithm on host cores (oracle port; oracle/_ref not present)", "fast (ijk) search"
+        how = "oracle port (oracle/_ref not present), fast (ijk) search"
+    sample = (f"{cores} independent {n}^3 periodic sub-boxes of the workload ({npart} moving spheres d=8 each, same solid fraction, "
+              f"shape and velocity distribution), one per core; step = forcing + solve (stress integral, combineForces, the literal "
+              f"sub-step loop, update) as in the b200 arm; {how}")
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "note": note},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": impl,
-                             "sample": f"{cores} independent {n}^3 periodic sub-boxes ({npart} spheres d=8 each, same solid fraction and "
-                                       f"shape as the workload), forcing + stress integral + re-marking per step, {how}"},
+            "config": {"workload": args.workload, "sample": sample,
+                       "note": "bounded sample of the workload per step (the as-coded reference is O(nCells) per particle: 512^3 x 10^5 is out of reach)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": impl, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -472,48 +270,31 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="big512")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", type=int, default=-1, help="-1 = probe (verified + faster generation per kernel), >= 0 = force that generation")
-    ap.add_argument("--mark", type=int, default=-1, help="marking kernel: -1 = as probed (first version without a probe), 0 / 1 = forced")
-    ap.add_argument("--no-probe", action="store_true", help="(default since round 2) library defaults without the child-process probe")
-    ap.add_argument("--probe-generations", action="store_true", help="round-1 behaviour: a child process compares kernel generations first")
-    ap.add_argument("--split", type=int, default=-1, help="loop-5 quiet/active split: -1 = as probed (off without a probe), 0 = off, 1 = on, 2 = on with the active list in one cooperative kernel")
-    ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--probe-fused", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--variant", type=int, default=-1, help="kernel generation of loops 2-4: -1 = library default (7, staged), 2 = direct gather, 0 = reference order")
+    ap.add_argument("--split", type=int, default=-1, help="loop 5: -1 = library default (quiet / active split in cluster mode), 0 = the unsplit chain as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-        return
-    if args.probe or args.probe_fused:
-        run_probe(args)
         return
 
     import torch
     from ibmfoam_b200.cloud import ParticleCloud
     from ibmfoam_b200 import capi
 
-    # a diverged or dead-locked multi-rank run must not sit on the GPUs until an external limit kills it
+    # a dead-locked multi-rank run must not sit on the GPUs until an external limit kills it
     def _expired():
         sys.stderr.write("bench.py watchdog: run exceeded its time limit\n")
         sys.stderr.flush()
-        if _retryable(sys.argv[1:]):
-            # a run with probed kernel generations that hangs gets the same single retry as one that raises
-            os.environ["IBM_BENCH_RETRY_AFTER"] = "watchdog: the run with probed kernel generations exceeded its time limit"
-            try:
-                os.remove(PROBE_CACHE)
-            except OSError:
-                pass
-            os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--no-probe"])
         os._exit(17)
 
-    limit = float(os.environ.get("IBM_BENCH_WATCHDOG_S", "700" if _retryable(sys.argv[1:]) else "1200"))
-    watchdog = threading.Timer(limit, _expired)
+    watchdog = threading.Timer(float(os.environ.get("IBM_BENCH_WATCHDOG_S", "900")), _expired)
     watchdog.daemon = True
     watchdog.start()
 
@@ -524,26 +305,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the immersed-boundary path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # which kernel generation: local rank 0 asks a child process BEFORE joining the process group (the others wait in the
-    # rendezvous), then everyone gets its answer
-    variants = [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], DEFAULT_SPLIT, 0]   # forcing generation, stress generation, loop-5 mode, marking kernel
-    probe_info = None
-    if args.variant >= 0:
-        variants = [args.variant, args.variant, DEFAULT_SPLIT, 0]
-    elif args.probe_generations and rank == 0:
-        variants[0], variants[1], variants[2], variants[3], probe_info = choose_variants(local_rank, workload=args.workload)
-    if args.split >= 0:
-        variants[2] = min(max(args.split, 0), 2)
-    if args.mark >= 0:
-        variants[3] = 1 if args.mark else 0
     if world > 1:
         import torch.distributed as dist
         import datetime
-        # (the other ranks wait here while rank 0 runs the probe children: up to ~7 minutes if both hang)
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=30))
-        vt = torch.tensor(variants, device=dev, dtype=torch.int32)
-        dist.broadcast(vt, 0)
-        variants = [int(x) for x in vt.tolist()]
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=15))
 
     case = make_case(args.workload)
     gmesh = case.mesh
@@ -562,27 +327,13 @@ def main():
         nccl_id = bytes(idt.cpu().tolist())
     t0 = time.time()
     cloud = ParticleCloud(case, device=local_rank, slab=slab, nccl_id=nccl_id, rank=rank, n_ranks=world)
-    cloud.set_kernel_variant(variants[0], variants[1])
-    cloud.set_option("active_loop5", int(variants[2] > 0))
-    cloud.set_option("fused_active_loop5", int(variants[2] == 2))
-    mark_check = None
-    if variants[3]:
-        # full-size check of the second marking kernel: same shell count and on-mesh status for every instance
-        st0 = cloud.state_arrays()
-        cloud.set_option("mark_variant", 1)
-        cloud.update()
-        st1 = cloud.state_arrays()
-        mark_check = bool(np.array_equal(st0["nShell"], st1["nShell"]) and np.array_equal(st0["onMesh"], st1["onMesh"]))
-        if not mark_check:
-            variants[3] = 0
-            cloud.set_option("mark_variant", 0)
-            cloud.update()
+    if args.variant >= 0:
+        cloud.set_kernel_variant(args.variant, args.variant)
+    if args.split >= 0:
+        cloud.set_option("active_loop5", int(args.split > 0))
+    generations = {"forcing": cloud.counter("forcing_variant"), "stress": cloud.counter("stress_variant"),
+                   "staged_kernels_apply": bool(cloud.counter("v7_ok"))}
     setup_s = time.time() - t0
-    have_motion = True
-    try:
-        cloud.combineForces()
-    except capi.IbmError:
-        have_motion = False
     U, Uold, S, P, Tau = device_fields(mesh, dev)
     torch.cuda.synchronize()
     ptrs = (U.data_ptr(), Uold.data_ptr(), S.data_ptr(), P.data_ptr(), Tau.data_ptr())
@@ -598,74 +349,39 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # A generation chosen by the probe is verified once more at the FULL size, on the device, against the default
-    # generation (forcing field 1e-11, force/torque 1e-9 relative); any disagreement reverts to the defaults.
-    verify = None
-    if args.variant < 0 and variants[:2] != [DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]]:
-        Fa = torch.empty_like(U)
-        Fb = torch.empty_like(U)
-
-        def outputs(fv, sv, Fbuf):
-            cloud.set_kernel_variant(fv, sv)
-            cloud.forcing_device(ptrs[0], ptrs[1], ptrs[2], dt, Fbuf.data_ptr())
-            cloud.integrate_stress_device(ptrs[3], ptrs[4])
-            cloud.sync()
-            st = cloud.state_arrays()
-            return np.concatenate([st["F"], st["T"]], axis=1)
-
-        FTa = outputs(DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"], Fa)
-        FTb = outputs(variants[0], variants[1], Fb)
-        torch.cuda.synchronize()
-        eF = float(((Fb - Fa).abs().max() / Fa.abs().max()).item())
-        eT = float(np.max(np.abs(FTb - FTa)) / max(np.max(np.abs(FTa)), 1e-300))
-        ok = eF < 1e-11 and eT < 1e-9
-        if world > 1:
-            import torch.distributed as dist
-            flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            ok = bool(flag.item())
-        verify = {"forcing_rel_diff": eF, "force_torque_rel_diff": eT, "ok": ok}
-        if not ok:
-            variants[0], variants[1] = DEFAULT_VARIANTS["forcing"], DEFAULT_VARIANTS["stress"]
-        cloud.set_kernel_variant(variants[0], variants[1])
-        del Fa, Fb
-
     for _ in range(max(3, args.warmup)):
-        run_step_device(cloud, ptrs, dt, have_motion)
+        run_step_device(cloud, ptrs, dt, True)
     barrier()
     if world > 1:
-        # replicated particle state: after the warm-up steps every rank must hold the same instance list and finite
-        # kinematics; a diverged run is reported at once instead of being timed (or left to the watchdog)
+        # replicated particle directory: after the warm-up steps every rank must hold the same instance list and the same
+        # kinematics; a diverged run is reported at once instead of being timed
         import torch.distributed as dist
         st = cloud.state_arrays()
         finite = bool(np.isfinite(st["center"]).all() and np.isfinite(st["v"]).all() and np.isfinite(st["F"]).all())
-        vloc = float(np.abs(st["v"]).max()) if finite else 0.0
-        chk = torch.tensor([cloud.nParticles(), -cloud.nParticles(), 1 if finite else 0, vloc, -vloc], device=dev, dtype=torch.float64)
-        dist.all_reduce(chk, op=dist.ReduceOp.MIN)   # every rank sees the same five numbers and takes the same decision
-        n_min, n_max, all_finite, v_min, v_max = int(chk[0].item()), int(-chk[1].item()), chk[2].item() == 1, chk[3].item(), -chk[4].item()
-        if not (n_min == n_max and all_finite and (v_max - v_min) <= 1e-9 * max(v_max, 1e-300)):
+        chk_sum = float(np.sum(st["center"]) + np.sum(st["v"]) + np.sum(st["omega"])) if finite else 0.0
+        chk = torch.tensor([cloud.nParticles(), -cloud.nParticles(), 1 if finite else 0, chk_sum, -chk_sum], device=dev, dtype=torch.float64)
+        dist.all_reduce(chk, op=dist.ReduceOp.MIN)
+        n_min, n_max, all_finite, c_min, c_max = int(chk[0].item()), int(-chk[1].item()), chk[2].item() == 1, chk[3].item(), -chk[4].item()
+        if not (n_min == n_max and all_finite and c_min == c_max):
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "impl": "b200",
                                   "error": f"ranks diverged during warm-up: instances min/max {n_min}/{n_max}, finite {all_finite}, "
-                                           f"max|v| min/max {v_min}/{v_max}"}))
+                                           f"state checksum min/max {c_min}/{c_max}"}))
             os._exit(3)
     cloud.timings(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
-    ev0.record()
     for _ in range(args.steps):
-        run_step_device(cloud, ptrs, dt, have_motion)
+        run_step_device(cloud, ptrs, dt, True)
     cloud.sync()
-    ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop()
     tm = cloud.timings()
-    # device time of the step = sum of the library's CUDA-event intervals on its own stream (torch events only see
-    # torch's stream); the wall clock around the synchronised region bounds it from above.
+    # device time of the step = sum of the library's CUDA-event intervals on its own stream (torch events only see torch's
+    # stream); the wall clock around the synchronised region bounds it from above and is what the step is charged
     dev_ms = tm["update_ms"] + tm["forcing_ms"] + tm["stress_ms"] + tm["advance_ms"]
     step_ms = max(wall_ms, dev_ms) / args.steps
     if world > 1:
@@ -688,39 +404,48 @@ def main():
     forcing_ms = tm["forcing_ms"] / max(1, tm["n_forcing_calls"])
     achieved = alg_bytes / (forcing_ms * 1e-3) / 1e9 if forcing_ms > 0 else 0.0
     traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this kernel
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == args.workload and world == 1 and variants[0] == 2:  # the capture is of k_forcing_v2
-            traffic = next(v["dram_bytes"] for k, v in tj["kernels"].items() if "k_forcing" in k)
+        if tj.get("workload") == args.workload and world == 1 and generations["forcing"] == 7 and generations["staged_kernels_apply"]:
+            traffic = next(v["dram_bytes"] for k, v in tj["kernels"].items() if "k_forcing_v7" in k)
     except Exception:
         traffic = None
+    kname = "k_forcing_v7" if (generations["forcing"] >= 7 and generations["staged_kernels_apply"]) else ("k_forcing_ref" if generations["forcing"] == 0 else "k_forcing_v2")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_forcing_v5<cached stencils>" if variants[0] == 6 else f"k_forcing_v{variants[0]}", "peak_kind": f"of {peak_kind}",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": kname, "peak_kind": f"of {peak_kind}",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": forcing_ms, "n_touch_closed_form": n_touch,
-                "forcing_updates_per_s": updates_per_step / (forcing_ms * 1e-3) if forcing_ms > 0 else None}
+                "forcing_updates_per_s": updates_per_step / (forcing_ms * 1e-3) if forcing_ms > 0 else None,
+                "stress_kernel_ms": tm["stress_ms"] / args.steps,
+                "stress_frac": (((56.0 * 4.0 / 3.0 * math.pi * (5 ** 3 - 3 ** 3) + 48.0) * n_inst * (local_updates / max(updates_per_step, 1.0))) / (tm["stress_ms"] / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tm["stress_ms"] > 0 else None}
     breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}
+    loop5 = {k: cloud.counter(k) for k in ("loop5_active_instances", "loop5_fallbacks", "loop5_cluster_steps", "loop5_block_substeps", "loop5_general_substeps")}
+    gpu_launches = tm["n_kernel_launches"]
 
-    # ---- e2e: host C-ABI calls, pinned AoS buffers, copies inside the timed region ----
+    # ---- e2e: host C-ABI calls with host arrays in OpenFOAM's layout, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
         C = mesh.n_cells
-        pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
-        hU, hUold, hS, hF, hP, hTau = pin(C, 3), pin(C, 3), pin(C, 3), pin(C, 3), pin(C), pin(C, 6)
-        hU.copy_(U.reshape(3, C).t()); hUold.copy_(Uold.reshape(3, C).t()); hS.copy_(S.reshape(3, C).t())
-        hP.copy_(P.reshape(C)); hTau.copy_(Tau.reshape(6, C).t())
         L = capi.load()
         import ctypes as Ct
-        vp = lambda t: Ct.c_void_p(t.data_ptr())
+        hU, hUold, hP = np.empty((C, 3)), np.empty((C, 3)), np.empty(C)            # registry fields: registered once
+        hS, hTau, hF = np.empty((C, 3)), np.empty((C, 6)), np.empty((C, 3))      # temporaries of the solver: pageable
+        tmp = torch.empty((C, 6), dtype=torch.float64, pin_memory=True)
+        for dst, src, nc in ((hU, U, 3), (hUold, Uold, 3), (hS, S, 3), (hTau, Tau, 6)):
+            tmp[:, :nc].copy_(src.reshape(nc, C).t())
+            dst[...] = tmp[:, :nc].numpy()
+        tmp[:, 0].copy_(P.reshape(C))
+        hP[...] = tmp[:, 0].numpy()
+        del tmp
+        vp = lambda a: Ct.c_void_p(a.ctypes.data)
+        for a in (hU, hUold, hP):
+            capi.check(L.ibm_host_register(cloud.handle, vp(a), a.nbytes), cloud.handle)
 
         def e2e_step():
             capi.check(L.ibm_forcing(cloud.handle, vp(hU), vp(hUold), vp(hS), dt, vp(hF)), cloud.handle)
-            if have_motion:
-                st = capi.SolveStats()
-                capi.check(L.ibm_solve(cloud.handle, vp(hP), vp(hTau), dt, Ct.byref(st)), cloud.handle)
-            else:
-                capi.check(L.ibm_integrate_stress(cloud.handle, vp(hP), vp(hTau), None), cloud.handle)
-                cloud.update()
+            st = capi.SolveStats()
+            capi.check(L.ibm_solve(cloud.handle, vp(hP), vp(hTau), dt, Ct.byref(st)), cloud.handle)
+            return float(hF[0, 0]) + st.totK   # the step's results are on the host
 
         e2e_step()
         cloud.timings(reset=True)
@@ -733,50 +458,48 @@ def main():
         e2e_ms = (time.perf_counter() - t1) * 1e3 / args.e2e_steps
         tm2 = cloud.timings()
         upd2 = tm2["n_updates"] / max(1, tm2["n_forcing_calls"])
+        pinned_b, staged_b = cloud.counter("h2d_pinned_bytes"), cloud.counter("h2d_staged_bytes")
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([upd2, -e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t[:1], op=dist.ReduceOp.SUM)
             dist.all_reduce(t[1:], op=dist.ReduceOp.MIN)
             upd2, e2e_ms = float(t[0].item()), -float(t[1].item())
+        for a in (hU, hUold, hP):
+            L.ibm_host_unregister(cloud.handle, vp(a))
         e2e = {"value": upd2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": tm2["h2d_bytes"] // args.e2e_steps,
                "d2h_bytes_per_step": tm2["d2h_bytes"] // args.e2e_steps, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                "h2d_ms_per_step": tm2["h2d_ms"] / args.e2e_steps, "d2h_ms_per_step": tm2["d2h_ms"] / args.e2e_steps,
-               "layout_ms_per_step": tm2["layout_ms"] / args.e2e_steps}
+               "layout_ms_per_step": tm2["layout_ms"] / args.e2e_steps,
+               "host_buffers": {"U, U.oldTime, p": "registered once with ibm_host_register (cudaHostRegister): direct DMA",
+                                "S, devRhoReff, F": "pageable numpy arrays: staged through the library's two pinned 32 MB chunks by 4 host threads",
+                                "h2d_direct_bytes_per_step": pinned_b // args.e2e_steps, "h2d_staged_bytes_per_step": staged_b // args.e2e_steps}}
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
-        v, steps, el, npart = cpu_baseline_sample()
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"128^3 sub-box, {npart} spheres d=8 (same solid fraction/shape as the workload), {steps} steps of "
-                         f"forcing + stress integral + re-marking in {el:.1f} s, fast (ijk) search, 1 thread"}
+        v1, steps1, el1, npart = cpu_sample(8.0, PORT_SAMPLE_N, 12345, "port", 6)
+        vall, cores, _, _, nsteps = all_cores_sample("port", PORT_SAMPLE_N, 8.0, 6)
+        cpu = {"value": vall, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} independent {PORT_SAMPLE_N}^3 periodic sub-boxes, {npart} moving spheres d=8 each (the workload's shape, solid fraction and "
+                         f"velocity distribution), >= {nsteps} steps of forcing + solve (stress integral, combineForces, sub-step loop, update) "
+                         f"per core, oracle restatement with the fast (ijk) search, one thread per box",
+               "one_core": {"value": v1, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"one such box, {steps1} steps in {el1:.1f} s"}}
         if os.path.exists(REF_LIB):  # the reference's own code, as coded, on the sample it can finish
-            v2, steps2, el2, npart2 = cpu_baseline_sample(6.0, REF_SAMPLE_N, 12345, "reference", 6)
+            v2, steps2, el2, npart2 = cpu_sample(6.0, REF_SAMPLE_N, 12345, "reference", 4)
             cpu["reference_as_coded"] = {"value": v2, "unit": UNIT, "cores": 1, "kind": "reference",
-                                         "sample": f"{REF_SAMPLE_N}^3 sub-box, {npart2} spheres, {steps2} steps in {el2:.1f} s (oracle/_ref)"}
+                                         "sample": f"{REF_SAMPLE_N}^3 periodic sub-box, {npart2} moving spheres, {steps2} steps of the same step in {el2:.1f} s (oracle/_ref)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "cells": gmesh.n_cells, "particles": case.particles.n, "instances": n_inst,
-                           "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)" if have_motion else "n/a",
-                           "step": "forcing + solve(stress, combine, sub-steps, re-marking)" if have_motion else "forcing + stress + re-marking (loop 5 not built)",
+                           "updates_per_step": updates_per_step, "nOuter": 1, "sub_steps": "literal loop (100/101)",
+                           "step": "forcing + solve(stress, combine, sub-steps, re-marking)",
                            "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s,
-                           "kernel_generations": {"forcing": variants[0], "stress": variants[1], "marking": 1 + variants[3], "marking_full_size_check": mark_check, "loop5_quiet_active_split": bool(variants[2]), "loop5_active_list_fused": variants[2] == 2,
-                                                  "loop5_active_instances": cloud.counter("loop5_active_instances") if variants[2] else None,
-                                                  "loop5_fallbacks": cloud.counter("loop5_fallbacks") if variants[2] else None,
-                                                  "loop5_cluster_steps": cloud.counter("loop5_cluster_steps") if variants[2] else None,
-                                                  "loop5_block_substeps": cloud.counter("loop5_block_substeps") if variants[2] else None,
-                                                  "loop5_general_substeps": cloud.counter("loop5_general_substeps") if variants[2] else None,
-                                                  "loop5_slowest_block_cycles": {k: cloud.counter("loop5_stat%d" % q) for q, k in ((2, "event"), (3, "flight"), (4, "setpos"), (5, "general"), (6, "loop"), (7, "members"), (8, "load"), (9, "pair_thread"), (10, "event_thread"))} if variants[2] else None,
-                                                  "selected_by": ("--variant" if args.variant >= 0 else
-                                                                  "library defaults" if not args.probe_generations else
-                                                                  "child-process probe: parity with the default generation on a 64^3 assembly, then the faster one on big256"),
-                                                  "probe": probe_info, "full_size_check": verify,
-                                                  "retry_after": os.environ.get("IBM_BENCH_RETRY_AFTER")}},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["n_kernel_launches"], "clocks": clocks,
-                "parallelism": None if world == 1 else f"z-slabs x{world}: fields decomposed, particle state replicated, NCCL all-reduce of F/T partials and on-mesh counts",
+                           "kernel_generations": generations, "loop5": loop5},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+                "parallelism": None if world == 1 else f"z-slabs x{world}: fields decomposed, particle directory replicated, NCCL all-reduce of F/T partials and on-mesh counts",
                 "breakdown_ms_per_step": breakdown, "wall_ms_per_step": wall_ms / args.steps}
         print(json.dumps(line))
     barrier()
@@ -787,35 +510,5 @@ def main():
     watchdog.cancel()
 
 
-def _retryable(argv):
-    return ("--probe-generations" in argv and int(os.environ.get("WORLD_SIZE", "1")) == 1 and "--no-probe" not in argv and "--variant" not in argv and "--probe" not in argv
-            and "--probe-fused" not in argv and "reference" not in argv)
-
-
-def _guarded_main():
-    """Single-GPU runs whose kernel generations were chosen by the probe get ONE retry with the measured defaults in a fresh
-    process (fresh CUDA context) if the run raises: a variant written without hardware must not cost the bench line.
-    Multi-rank runs are not retried (the ranks would have to agree on it)."""
-    argv = sys.argv[1:]
-    retryable = _retryable(argv)
-    try:
-        main()
-    except SystemExit:
-        raise
-    except BaseException as ex:  # noqa: BLE001
-        if not retryable:
-            raise
-        import traceback
-        traceback.print_exc()
-        sys.stderr.write(f"bench.py: run with probed kernel generations failed ({type(ex).__name__}); retrying with the defaults\n")
-        sys.stderr.flush()
-        try:
-            os.remove(PROBE_CACHE)
-        except OSError:
-            pass
-        os.environ["IBM_BENCH_RETRY_AFTER"] = f"{type(ex).__name__}: {ex}"[:300]
-        os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + argv + ["--no-probe"])
-
-
 if __name__ == "__main__":
-    _guarded_main()
+    main()

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "ibm_ctx.h"
 
@@ -346,13 +347,88 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
   return IBM_OK;
 }
 
+// ---- host <-> device transfers of caller-owned arrays ------------------------------------------------------------
+// OpenFOAM's field storage is ordinary (pageable) memory unless the caller registered it (ibm_host_register, which the shim
+// does for the fields that persist across time steps: U, U.oldTime(), p).  A registered / pinned array is copied directly by
+// the DMA engine; a pageable one goes through two library-owned pinned chunks, filled by a few host threads while the
+// previous chunk is on the bus (cudaMemcpyAsync on pageable memory is a synchronous staged copy at a fraction of the rate).
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static const size_t kChunkBytes = (size_t)32 << 20;
+static int ensure_chunks(ibm_ctx* c) {
+  if (c->hChunk[0]) return IBM_OK;
+  for (int q = 0; q < 2; ++q) {
+    IBM_CUDA(c, cudaMallocHost(&c->hChunk[q], kChunkBytes));
+    IBM_CUDA(c, cudaEventCreateWithFlags(&c->chunkEv[q], cudaEventDisableTiming));
+  }
+  return IBM_OK;
+}
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  const int nT = 4;
+  if (bytes < ((size_t)1 << 20)) { std::memcpy(dst, src, bytes); return; }
+  std::thread th[nT];
+  const size_t per = ((bytes / nT) + 63) & ~(size_t)63;
+  for (int t = 0; t < nT; ++t) {
+    const size_t o = std::min(bytes, t * per), n = std::min(bytes - o, per);
+    th[t] = std::thread([=] { if (n) std::memcpy((char*)dst + o, (const char*)src + o, n); });
+  }
+  for (int t = 0; t < nT; ++t) th[t].join();
+}
+static int h2d_bytes(ibm_ctx* c, const void* host, size_t bytes, void* dev) {
+  if (host_is_pinned(host)) {
+    IBM_CUDA(c, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2dPinnedBytes += (long long)bytes;
+    return IBM_OK;
+  }
+  int rc = ensure_chunks(c);
+  if (rc) return rc;
+  int k = 0;
+  for (size_t o = 0; o < bytes; o += kChunkBytes, ++k) {
+    const size_t n = std::min(kChunkBytes, bytes - o);
+    const int q = k & 1;
+    if (k >= 2) IBM_CUDA(c, cudaEventSynchronize(c->chunkEv[q]));  // the copy that last used this chunk has left it
+    parallel_memcpy(c->hChunk[q], (const char*)host + o, n);
+    IBM_CUDA(c, cudaMemcpyAsync((char*)dev + o, c->hChunk[q], n, cudaMemcpyHostToDevice, c->stream));
+    IBM_CUDA(c, cudaEventRecord(c->chunkEv[q], c->stream));
+  }
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));  // the chunks are free again when the call returns
+  c->h2dStagedBytes += (long long)bytes;
+  return IBM_OK;
+}
+static int d2h_bytes(ibm_ctx* c, const void* dev, size_t bytes, void* host) {
+  if (host_is_pinned(host)) {
+    IBM_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return IBM_OK;
+  }
+  int rc = ensure_chunks(c);
+  if (rc) return rc;
+  const size_t nChunks = (bytes + kChunkBytes - 1) / kChunkBytes;
+  for (size_t k = 0; k <= nChunks; ++k) {  // chunk k on the bus while chunk k-1 is copied out
+    if (k < nChunks) {
+      const size_t o = k * kChunkBytes, n = std::min(kChunkBytes, bytes - o);
+      IBM_CUDA(c, cudaMemcpyAsync(c->hChunk[k & 1], (const char*)dev + o, n, cudaMemcpyDeviceToHost, c->stream));
+      IBM_CUDA(c, cudaEventRecord(c->chunkEv[k & 1], c->stream));
+    }
+    if (k >= 1) {
+      const size_t o = (k - 1) * kChunkBytes, n = std::min(kChunkBytes, bytes - o);
+      IBM_CUDA(c, cudaEventSynchronize(c->chunkEv[(k - 1) & 1]));
+      parallel_memcpy((char*)host + o, c->hChunk[(k - 1) & 1], n);
+    }
+  }
+  return IBM_OK;
+}
+
 static int h2d_field(ibm_ctx* c, const double* hostAoS, int nComp, double* dSoA) {
   const size_t n = (size_t)nComp * c->L.nCells;
   int rc = ctx_ensure_stage(c, n);
   if (rc) return rc;
   ctx_tic(c, T_H2D);
-  IBM_CUDA(c, cudaMemcpyAsync(c->dStage, hostAoS, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  rc = h2d_bytes(c, hostAoS, n * sizeof(double), c->dStage);
   ctx_toc(c);
+  if (rc) return rc;
   c->h2dBytes += (long long)(n * sizeof(double));
   ctx_tic(c, T_LAYOUT);
   launch_aos_to_soa(c->stream, c->L, c->dStage, nComp, dSoA);
@@ -370,8 +446,9 @@ static int d2h_field(ibm_ctx* c, const double* dSoA, int nComp, double* hostAoS)
   c->nLaunch++;
   ctx_toc(c);
   ctx_tic(c, T_D2H);
-  IBM_CUDA(c, cudaMemcpyAsync(hostAoS, c->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  rc = d2h_bytes(c, c->dStage, n * sizeof(double), hostAoS);
   ctx_toc(c);
+  if (rc) return rc;
   c->d2hBytes += (long long)(n * sizeof(double));
   return IBM_OK;
 }
@@ -642,6 +719,7 @@ int ibm_destroy(ibm_ctx* c) {
   for (void* p : frees) if (p) cudaFree(p);
   if (c->hScal) cudaFreeHost(c->hScal);
   if (c->hPinned) cudaFreeHost(c->hPinned);
+  for (int q = 0; q < 2; ++q) { if (c->hChunk[q]) cudaFreeHost(c->hChunk[q]); if (c->chunkEv[q]) cudaEventDestroy(c->chunkEv[q]); }
   cudaStreamDestroy(c->stream);
   delete c;
   return IBM_OK;
@@ -973,6 +1051,24 @@ int ibm_download_field(ibm_ctx* c, const double* dSoA, int nComp, double* hostAo
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   return IBM_OK;
 }
+// cudaHostRegister of a caller-owned array that persists across calls (shim: U, U.oldTime(), p): its transfers then run at the
+// full DMA rate instead of through the staging chunks.  Unregister before the array is freed.
+int ibm_host_register(ibm_ctx* c, const void* ptr, size_t bytes) {
+  if (!c || !ptr || bytes == 0) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  if (host_is_pinned(ptr)) return IBM_OK;
+  cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return ctx_fail(c, IBM_E_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+  return IBM_OK;
+}
+int ibm_host_unregister(ibm_ctx* c, const void* ptr) {
+  if (!c || !ptr) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+  if (e != cudaSuccess) { cudaGetLastError(); return ctx_fail(c, IBM_E_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+  return IBM_OK;
+}
+
 int ibm_sync(ibm_ctx* c) {
   if (!c) return IBM_E_ARG;
   cudaSetDevice(c->device);
@@ -992,6 +1088,8 @@ int ibm_get_counter(ibm_ctx* c, const char* name, long long* value) {
   if (std::strcmp(name, "forcing_variant") == 0) { *value = c->forcingVariant; return IBM_OK; }
   if (std::strcmp(name, "stress_variant") == 0) { *value = c->stressVariant; return IBM_OK; }
   if (std::strcmp(name, "mark_variant") == 0) { *value = c->markVariant; return IBM_OK; }
+  if (std::strcmp(name, "h2d_pinned_bytes") == 0) { *value = c->h2dPinnedBytes; return IBM_OK; }   // since the last ibm_timings_reset
+  if (std::strcmp(name, "h2d_staged_bytes") == 0) { *value = c->h2dStagedBytes; return IBM_OK; }
   if (std::strcmp(name, "v7_ok") == 0) { *value = c->v7ok ? 1 : 0; return IBM_OK; }
   if (std::strcmp(name, "v7_slow_count") == 0) {  // instances the last staged launch handed to the direct-gather kernel
     int n = 0;
@@ -1066,6 +1164,7 @@ int ibm_timings_reset(ibm_ctx* c) {
   resolve_events(c);
   for (double& x : c->accMs) x = 0;
   c->h2dBytes = c->d2hBytes = c->nLaunch = c->nForcingCalls = c->nUpdates = 0;
+  c->h2dPinnedBytes = c->h2dStagedBytes = 0;
   return IBM_OK;
 }
 

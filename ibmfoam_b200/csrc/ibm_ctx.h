@@ -74,6 +74,9 @@ struct ibm_ctx {
   bool fLive = false;       // dF holds a previous forcing result on the current shell cells
   bool fEverZeroed = false;
   double* hPinned = nullptr;  // small pinned scratch for results
+  void* hChunk[2] = {nullptr, nullptr};          // pinned staging chunks for pageable caller arrays
+  cudaEvent_t chunkEv[2] = {nullptr, nullptr};
+  long long h2dPinnedBytes = 0, h2dStagedBytes = 0;  // host->device bytes copied directly from pinned / registered arrays, through the chunks
   size_t hPinnedDoubles = 0;
 
   // kernel generation of loops 2-4: 0 reference-order (every sum and division as coded: the on-device yardstick), 2 direct gather

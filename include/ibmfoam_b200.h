@@ -14,7 +14,9 @@
  *   - one ibm_ctx per particleCloud, bound to one CUDA device and one stream; not re-entrant.
  *   - all arithmetic is fp64 (OpenFOAM scalar), labels are 32-bit.
  *   - "host" entry points take caller-ordered AoS arrays exactly as OpenFOAM stores them
- *     (vector = 3 doubles, symmTensor = xx xy xz yy yz zz) and include the pinned H2D/D2H copies;
+ *     (vector = 3 doubles, symmTensor = xx xy xz yy yz zz) and include the H2D/D2H copies: an array that is pinned or was
+ *     registered with ibm_host_register is copied directly by the DMA engine; ordinary pageable memory (OpenFOAM's default)
+ *     goes through two library-owned pinned chunks filled by host threads while the previous chunk is on the bus;
  *     "_device" entry points take device pointers to structure-of-arrays fields in LATTICE order
  *     ([component][k][j][i], i fastest) and never touch the host.
  *   - there is no CPU fallback: without a CUDA device ibm_create fails with IBM_E_CUDA.
@@ -184,6 +186,11 @@ int ibm_device_field_bytes(ibm_ctx* ctx, int nComponents, size_t* bytes);
 /* caller AoS (host) -> lattice SoA (device) and back, using the ctx stream and pinned staging */
 int ibm_upload_field(ibm_ctx* ctx, const double* hostAoS, int nComponents, double* dSoA);
 int ibm_download_field(ibm_ctx* ctx, const double* dSoA, int nComponents, double* hostAoS);
+/* cudaHostRegister / cudaHostUnregister of a caller-owned host array that persists across calls (the shim registers U,
+ * U.oldTime() and p: fields that live in the mesh registry, UEqn.H:20-26, particleCloud.C:1193-1194, 1212); temporaries such as S,
+ * devRhoReff() and the returned forcing field take the staged path */
+int ibm_host_register(ibm_ctx* ctx, const void* ptr, size_t bytes);
+int ibm_host_unregister(ibm_ctx* ctx, const void* ptr);
 int ibm_sync(ibm_ctx* ctx);
 int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant); /* 0 = reference-order kernels, 1.. = tuned generations */
 /* diagnostic counters: "loop5_active_instances" (of the last ibm_advance with the quiet/active split, else -1), "loop5_fallbacks",

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE — a DRY RUN of bench.py's control flow on a machine without a GPU: the emulated library
 (build_emu.py) stands in for libibmfoam_b200.so, torch's CUDA entry points are replaced by CPU stand-ins, and every
-workload is shrunk to a 32^3 box.  It exists to catch mistakes in bench.py's logic (kernel-generation probe, full-size
-re-verification, timing bookkeeping, end-to-end leg, JSON assembly) before GPU time is spent on them.  The numbers it
+workload is shrunk to a 32^3 box.  It exists to catch mistakes in bench.py's logic (timing bookkeeping, end-to-end leg,
+JSON assembly) before GPU time is spent on them.  The numbers it
 prints are meaningless and are marked as such ("dry_run": true); bench.py itself contains no such switch.
 
     python tools/cuda_emu/bench_dryrun.py [bench.py arguments]"""
@@ -62,40 +62,13 @@ def main(argv):
         return cases.assembly(n=n, phi=0.2, moving=moving, cyclic_without_walls=True)
 
     bench.make_case = make_case
-    bench.PROBE_CACHE = os.path.join("/tmp", f"ibmfoam_b200_probe_dryrun_{os.getpid()}.json")
-
-    def choose_variants(local_rank, timeout_s=0, workload="big512"):
-        """both probes in-process (the real ones run in children on the GPU), merged as bench.choose_variants merges them,
-        then bench.py's own selection logic on the result"""
-        def part(fused):
-            buf = io.StringIO()
-            args = type("A", (), {"workload": workload, "probe_fused": fused})()
-            with contextlib.redirect_stdout(buf):
-                bench.run_probe(args)
-            return json.loads([ln for ln in buf.getvalue().splitlines() if ln.startswith("{")][-1])
-
-        info = part(False)
-        if info.get("ok") and info.get("loop5_split_ok"):
-            fused = part(True)
-            info["loop5_fused_active_ok"] = bool(fused.get("ok") and fused.get("loop5_fused_active_ok"))
-            if info["loop5_fused_active_ok"]:
-                info.setdefault("advance_ms", {}).update(fused.get("advance_ms", {}))
-        with open(bench.PROBE_CACHE, "w") as fh:
-            json.dump(info, fh)
-        return real_choose(local_rank, workload=workload)   # (forcing, stress, loop-5 mode, marking kernel, info)
-
-    real_choose = bench.choose_variants
-    bench.choose_variants = choose_variants
-    bench.cpu_baseline_sample = lambda *a, **k: (1.0, 1, 1.0, 24)  # the CPU baseline leg is not what is being dry-run
+    bench.cpu_sample = lambda *a, **k: (1.0, 1, 1.0, 24)            # the CPU baseline legs are not what is being dry-run
+    bench.all_cores_sample = lambda *a, **k: (1.0, 1, 1.0, 24, 1)
     os.environ.setdefault("IBM_BENCH_WATCHDOG_S", "7200")   # emulated kernels are slow; the watchdog's retry is for hardware runs
     sys.argv = ["bench.py"] + argv
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         bench.main()
-    try:
-        os.remove(bench.PROBE_CACHE)
-    except OSError:
-        pass
     line = json.loads([ln for ln in buf.getvalue().splitlines() if ln.startswith("{")][-1])
     line["dry_run"] = True
     print(json.dumps(line))

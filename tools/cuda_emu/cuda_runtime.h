@@ -162,6 +162,24 @@ inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu::Event; return cudaSuccess; }
+#define cudaEventDisableTiming 2u
+#define cudaHostRegisterDefault 0u
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emu::Event; return cudaSuccess; }
+// registered host arrays (by base pointer): what cudaPointerGetAttributes reports as pinned
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+inline std::vector<std::pair<const char*, size_t>>& emu_registered() { static std::vector<std::pair<const char*, size_t>> v; return v; }
+inline cudaError_t cudaHostRegister(void* p, size_t n, unsigned) { emu_registered().push_back({(const char*)p, n}); return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void* p) {
+  auto& v = emu_registered();
+  for (size_t i = 0; i < v.size(); ++i) if (v[i].first == (const char*)p) { v.erase(v.begin() + i); return cudaSuccess; }
+  return cudaErrorInvalidValue;
+}
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = const_cast<void*>(p);
+  for (auto& r : emu_registered()) if ((const char*)p >= r.first && (const char*)p < r.first + r.second) a->type = cudaMemoryTypeHost;
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
