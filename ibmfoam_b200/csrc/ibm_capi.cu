@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "ibm_ctx.h"
@@ -350,14 +352,14 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
 // ---- host <-> device transfers of caller-owned arrays ------------------------------------------------------------
 // OpenFOAM's field storage is ordinary (pageable) memory unless the caller registered it (ibm_host_register, which the shim
 // does for the fields that persist across time steps: U, U.oldTime(), p).  A registered / pinned array is copied directly by
-// the DMA engine; a pageable one goes through two library-owned pinned chunks, filled by a few host threads while the
+// the DMA engine; a pageable one goes through two library-owned pinned 64 MB chunks, filled by eight host threads while the
 // previous chunk is on the bus (cudaMemcpyAsync on pageable memory is a synchronous staged copy at a fraction of the rate).
 static bool host_is_pinned(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
-static const size_t kChunkBytes = (size_t)32 << 20;
+static const size_t kChunkBytes = (size_t)64 << 20;
 static int ensure_chunks(ibm_ctx* c) {
   if (c->hChunk[0]) return IBM_OK;
   for (int q = 0; q < 2; ++q) {
@@ -366,16 +368,51 @@ static int ensure_chunks(ibm_ctx* c) {
   }
   return IBM_OK;
 }
-static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const int nT = 4;
-  if (bytes < ((size_t)1 << 20)) { std::memcpy(dst, src, bytes); return; }
+// a few persistent host threads that split one memcpy between them (one pool per process, started on first use)
+struct CopyPool {
+  static const int nT = 8;
   std::thread th[nT];
-  const size_t per = ((bytes / nT) + 63) & ~(size_t)63;
-  for (int t = 0; t < nT; ++t) {
-    const size_t o = std::min(bytes, t * per), n = std::min(bytes - o, per);
-    th[t] = std::thread([=] { if (n) std::memcpy((char*)dst + o, (const char*)src + o, n); });
+  std::mutex mu;
+  std::condition_variable cvGo, cvDone;
+  long generation = 0;
+  int pending = 0;
+  bool stop = false;
+  char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
+  CopyPool() {
+    for (int t = 0; t < nT; ++t) th[t] = std::thread([this, t] { work(t); });
   }
-  for (int t = 0; t < nT; ++t) th[t].join();
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cvGo.notify_all();
+    for (auto& x : th) if (x.joinable()) x.join();
+  }
+  void work(int t) {
+    long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu);
+      cvGo.wait(lk, [&] { return stop || generation != seen; });
+      if (stop) return;
+      seen = generation;
+      char* d = dst; const char* s2 = src; const size_t n = bytes;
+      lk.unlock();
+      const size_t per = ((n / nT) + 4095) & ~(size_t)4095;
+      const size_t o = std::min(n, (size_t)t * per), len = std::min(n - o, per);
+      if (len) std::memcpy(d + o, s2 + o, len);
+      lk.lock();
+      if (--pending == 0) cvDone.notify_all();
+    }
+  }
+  void copy(void* d, const void* s2, size_t n) {
+    std::unique_lock<std::mutex> lk(mu);
+    dst = (char*)d; src = (const char*)s2; bytes = n; pending = nT; ++generation;
+    cvGo.notify_all();
+    cvDone.wait(lk, [&] { return pending == 0; });
+  }
+};
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)1 << 20)) { std::memcpy(dst, src, bytes); return; }
+  static CopyPool pool;
+  pool.copy(dst, src, bytes);
 }
 static int h2d_bytes(ibm_ctx* c, const void* host, size_t bytes, void* dev) {
   if (host_is_pinned(host)) {
