@@ -93,6 +93,7 @@ SYMBOLS = {
     "ibm_device_field_bytes": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
     "ibm_upload_field": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "ibm_download_field": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "ibm_restore_particles": (C.c_int, [_VP, C.c_int, _VP]),
     "ibm_host_register": (C.c_int, [_VP, _VP, C.c_size_t]),
     "ibm_host_unregister": (C.c_int, [_VP, _VP]),
     "ibm_sync": (C.c_int, [_VP]),

@@ -166,6 +166,11 @@ class ParticleCloud:
             out[k] = np.array([list(getattr(s, k)) for s in st], dtype=np.float64).reshape(n, 3)
         return out
 
+    def restore(self, states):
+        """particleCloud::readParticles(): replace the instance list by the given ParticleState records (see ibm_restore_particles)"""
+        arr = (capi.ParticleState * max(1, len(states)))(*states)
+        check(self._L.ibm_restore_particles(self._h, len(states), arr), self._h)
+
     def set_force_torque(self, FT):
         FT = _c(FT)
         check(self._L.ibm_set_force_torque(self._h, _ptr(FT)), self._h)

@@ -888,6 +888,72 @@ int ibm_get_particles(ibm_ctx* c, ibm_particle_state* out) {
   return IBM_OK;
 }
 
+int ibm_restore_particles(ibm_ctx* c, int n, const ibm_particle_state* st) {
+  if (!c || n < 0 || (n > 0 && !st)) return ctx_fail(c, IBM_E_ARG, "ibm_restore_particles: bad arguments");
+  if (c->cap == 0) return ctx_fail(c, IBM_E_STATE, "ibm_restore_particles: call ibm_set_particles first (origParticles_)");
+  if (n > c->cap) return ctx_fail(c, IBM_E_CAPACITY, "ibm_restore_particles: more instances than ibm_cloud_cfg.maxInstances");
+  cudaSetDevice(c->device);
+  IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i)
+    if (st[i].index < 0 || st[i].index >= c->nParticles) return ctx_fail(c, IBM_E_ARG, "ibm_restore_particles: index outside IBMProperties");
+  clear_live_F(c);  // (the shell lists of the instances that go away still say where F is non-zero)
+  std::vector<int> iv(std::max(n, 1));
+  std::vector<double> dv(std::max(n, 1));
+  auto upI = [&](int* dst, auto f) { for (int i = 0; i < n; ++i) iv[i] = f(i); cudaMemcpy(dst, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice); };
+  auto upD = [&](double* dst, auto f) { for (int i = 0; i < n; ++i) dv[i] = f(i); cudaMemcpy(dst, dv.data(), n * sizeof(double), cudaMemcpyHostToDevice); };
+  if (n > 0) {
+    upI(c->in.index, [&](int i) { return st[i].index; });
+    upI(c->in.copy, [&](int i) { return st[i].copy; });
+    upI(c->in.active, [&](int i) { return st[i].active; });
+    upI(c->in.onMesh, [&](int) { return IBM_ON_MESH; });
+    upI(c->in.cls, [&](int i) { return c->origCls[st[i].index]; });
+    upI(c->in.nShell, [&](int) { return 0; });
+    upI(c->in.shellOff, [&](int) { return 0; });
+    for (int q = 0; q < 3; ++q) {
+      upD(c->in.c[q], [&](int i) { return st[i].center[q]; });
+      upD(c->in.th[q], [&](int i) { return st[i].theta[q]; });
+      upD(c->in.v[q], [&](int i) { return st[i].v[q]; });
+      upD(c->in.om[q], [&](int i) { return st[i].omega[q]; });
+      upD(c->in.F[q], [&](int) { return 0.0; });
+      upD(c->in.T[q], [&](int) { return 0.0; });
+    }
+    upD(c->in.rho, [&](int i) { return st[i].rho; });
+    upD(c->in.age, [&](int i) { return st[i].age; });
+  }
+  c->nInst = n;
+  c->totalShell = 0;
+  motion_invalidate_groups(c);
+  int rc = ctx_update(c);  // update() + deleteInActiveParticles (particleCloud.C:1125)
+  if (rc) return rc;
+  // AS CODED: particleIBM::readFields builds every shape with particleShape::New(mesh, particle.<index>, center) - i.e. with the
+  // DICTIONARY's theta - and only then overwrites theta_ (particleIBMIO.C:196-204): until the first update() after the restart
+  // the rotation matrix (and, for ellipses, the point mesh and the cell lists) are those of the initial orientation.  So the
+  // lists are built once more with the dictionary angles in place, and the restored angles go back afterwards.
+  if (c->nInst > 0) {
+    const int m = c->nInst;
+    std::vector<int> idx(m);
+    std::vector<double> th(3 * (size_t)m), tmp(m);
+    cudaMemcpy(idx.data(), c->in.index, m * sizeof(int), cudaMemcpyDeviceToHost);
+    for (int q = 0; q < 3; ++q) {
+      cudaMemcpy(th.data() + (size_t)q * m, c->in.th[q], m * sizeof(double), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < m; ++i) tmp[i] = c->orig[idx[i]].theta[q];
+      cudaMemcpy(c->in.th[q], tmp.data(), m * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if ((rc = ctx_update(c))) return rc;
+    if (c->nInst != m) return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_restore_particles: an instance is on the mesh with its restored angle and off it with the dictionary's");
+    for (int q = 0; q < 3; ++q) cudaMemcpy(c->in.th[q], th.data() + (size_t)q * m, m * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  // maxCopies_[index] = 0 for every surviving instance (particleCloud.C:1127-1131), -1 for indices without one
+  std::fill(c->maxCopies.begin(), c->maxCopies.end(), -1);
+  if (c->nInst > 0) {
+    std::vector<int> idx(c->nInst);
+    cudaMemcpy(idx.data(), c->in.index, c->nInst * sizeof(int), cudaMemcpyDeviceToHost);
+    for (int i : idx) c->maxCopies[i] = 0;
+  }
+  motion_reset_copies(c);
+  return IBM_OK;
+}
+
 int ibm_set_force_torque(ibm_ctx* c, const double* FT) {
   if (!c || !FT) return IBM_E_ARG;
   cudaSetDevice(c->device);

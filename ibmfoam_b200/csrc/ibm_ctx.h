@@ -129,6 +129,7 @@ int motion_substep(ibm_ctx* c, double localDt);
 void motion_destroy(ibm_ctx* c);
 void motion_invalidate_groups(ibm_ctx* c);
 void motion_invalidate_graph(ibm_ctx* c);
+void motion_reset_copies(ibm_ctx* c);  // copy counters of loop 5 <- c->maxCopies (after a restart)
 bool motion_counter(ibm_ctx* c, const char* name, long long* value);
 int combine_forces(ibm_ctx* c);
 // ibm_comm.cu

@@ -2527,6 +2527,11 @@ static void refresh_contact_model(ibm_ctx* c) {
   d.model = c->collisionModel; d.kn = c->softKn; d.gn = c->softGammaN; d.gt = c->softGammaT; d.mu = c->softMu;
 }
 
+void motion_reset_copies(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  if (M && c->nParticles > 0) cudaMemcpy(M->d.maxCopies, c->maxCopies.data(), c->nParticles * sizeof(int), cudaMemcpyHostToDevice);
+}
+
 void motion_invalidate_graph(ibm_ctx* c) {
   if (c->motion) ((Motion*)c->motion)->graphValid = false;  // MotionDev is captured by value
 }

@@ -161,6 +161,11 @@ int ibm_substep(ibm_ctx* ctx, double localDt);
 /* ---- accessors ----------------------------------------------------------------------------------- */
 int ibm_n_instances(ibm_ctx* ctx, int* n);                    /* Cloud<particleIBM>::size(), particleCloud.H:282-285 */
 int ibm_get_particles(ibm_ctx* ctx, ibm_particle_state* out); /* [nInstances] */
+/* particleCloud::readParticles + the tail of the constructor on a restart (particleCloudIO.C:47-69, particleIBMIO.C:111-213,
+ * particleCloud.C:1119-1133): the instance list is REPLACED by the n records read from <time>/lagrangian/IBMparticles (index, copy,
+ * active, center, theta, v, omega, rho, age; shape from particle.<index> of IBMProperties, i.e. from ibm_set_particles), then
+ * update(), deleteInActiveParticles and maxCopies_[index] = 0 as coded.  F, T start from zero like a freshly read particleIBM. */
+int ibm_restore_particles(ibm_ctx* ctx, int n, const ibm_particle_state* st);
 int ibm_set_force_torque(ibm_ctx* ctx, const double* FT);     /* particleIBM::F()/T() non-const refs, particleIBMI.H:136-149 */
 int ibm_cd(ibm_ctx* ctx, double* out);                        /* particleCloud::Cd, particleCloud.C:1231-1240 */
 int ibm_max_co_num(ibm_ctx* ctx, double* out);                /* particleCloud::maxCoNum — always 0, particleCloud.C:1145-1156 */

@@ -89,6 +89,8 @@ int main(int argc, char** argv)
             pd.add("omega", vector(om[0], om[1], om[2]));
         }
         if (!in) { std::fprintf(stderr, "bad case file\n"); return 2; }
+        int nRestart = 0;   // optional trailing number: steps to run with a SECOND cloud constructed from the written time directory
+        if (!(in >> nRestart)) nRestart = 0;
 
         // ---- the fields the solver owns ----
         const word t0 = runTime.timeName();
@@ -117,14 +119,15 @@ int main(int argc, char** argv)
         };
 
         // ---- createFields.H:60 ----
-        particleCloud particles(mesh, IBMProperties, dimensionedVector("g", dimAcceleration, vector(g[0], g[1], g[2])));
+        std::unique_ptr<particleCloud> cloudPtr(new particleCloud(mesh, IBMProperties, dimensionedVector("g", dimAcceleration, vector(g[0], g[1], g[2]))));
 
         std::FILE* out = std::fopen(argv[2], "wb");
         std::fprintf(out, "dropin %d %d %d\n", mesh.nCells(), nSteps, nOuter);
         double CoNum = 0;
         fill(0.0);
-        for (int step = 1; step <= nSteps; ++step)
+        for (int step = 1; step <= nSteps + nRestart; ++step)
         {
+            particleCloud& particles = *cloudPtr;
             static_cast<Field<vector>&>(Uold) = U;                   // U.oldTime() of the new step
             runTime.setTime(step*dt);
             fill(0.37*step);
@@ -143,7 +146,18 @@ int main(int argc, char** argv)
             std::vector<double> cd;
             forAll(Cds, i) cd.push_back(Cds[i]);
             dump(out, "Cd", cd);
+            if (step == nSteps && nRestart > 0)
+            {
+                // ---- restart (reference particleCloud.C:1119-1123): runTime.write(), the cloud goes away, a NEW cloud is constructed
+                //      at a time != 0 and reads <time>/lagrangian/IBMparticles back (particleCloudIO.C:47-69) ----
+                mockWrittenFields().clear();
+                particles.writeObject(IOstream::ASCII, IOstream::versionNumber(), IOstream::UNCOMPRESSED, true);
+                cloudPtr.reset();
+                cloudPtr.reset(new particleCloud(mesh, IBMProperties, dimensionedVector("g", dimAcceleration, vector(g[0], g[1], g[2]))));
+                dump(out, "restarted", {double(cloudPtr->nParticles())});
+            }
         }
+        particleCloud& particles = *cloudPtr;
         dump(out, "CoNum", {CoNum});
         // ---- runTime.write(): lagrangian/IBMparticles/* ----
         mockWrittenFields().clear();
@@ -153,6 +167,32 @@ int main(int argc, char** argv)
             auto it = mockWrittenFields().find(std::string(runTime.timeName()) + "/lagrangian/IBMparticles/" + name);
             if (it == mockWrittenFields().end()) { std::fprintf(stderr, "field %s was not written\n", name); return 3; }
             dump(out, name, it->second);
+        }
+        // ---- the per-particle class API (reference particleIBM.H:194-391): accessors read through the cloud's particles ----
+        {
+            std::vector<double> mass, vAt, rr, idx;
+            const vector probe(origin[0] + 0.31*Lx, origin[1] + 0.47*Ly, origin[2] + (nz > 1 ? 0.53*Lz : 0.5*Lz));
+#ifdef DROPIN_REFERENCE
+            forAllConstIter(Cloud<particleIBM>, particles, iter)
+            {
+                const particleIBM& q = iter();
+#else
+            const List<particleIBM> views(particles.particles());
+            forAll(views, vi)
+            {
+                const particleIBM& q = views[vi];
+#endif
+                idx.push_back(q.index());
+                mass.push_back(q.mass());
+                rr.push_back(q.r(probe));
+                rr.push_back(q.d());
+                const vector w(q.v(probe));
+                vAt.push_back(w.x()); vAt.push_back(w.y()); vAt.push_back(w.z());
+            }
+            dump(out, "view_index", idx);
+            dump(out, "view_mass", mass);
+            dump(out, "view_r", rr);
+            dump(out, "view_vAt", vAt);
         }
         std::fclose(out);
     }

@@ -139,11 +139,20 @@ Foam::particleCloud::particleCloud
         p.rho = readScalar(pDict.lookup("rho"));
     }
     check(ibm_set_particles(ctx_, init.size(), init.begin()), "particleCloud");
+    // restart: the instances come from <time>/lagrangian/IBMparticles instead of the dictionary (reference particleCloud.C:1095-1123)
+    if (mesh_.time().value() != 0)
+    {
+        readParticles();
+    }
     check(ibm_get_indicator(ctx_, I_.primitiveFieldRef().begin()), "updateI");
 }
 
 Foam::particleCloud::~particleCloud()
 {
+    forAll(registered_, i)
+    {
+        ibm_host_unregister(ctx_, registered_[i]);
+    }
     ibm_destroy(ctx_);
 }
 
@@ -175,6 +184,10 @@ Foam::tmp<Foam::volVectorField> Foam::particleCloud::forcing(const volVectorFiel
     if (!coupled_) return tmpF;
 
     const volVectorField& U = mesh_.lookupObject<volVectorField>("U");
+    // U and U.oldTime() live in the mesh registry for the whole run: their storage is registered once so that the copies run
+    // at the full DMA rate (S and the returned F are temporaries: the library stages them through its pinned chunks)
+    registerField(U.primitiveField().begin(), U.size()*sizeof(vector));
+    registerField(U.oldTime().primitiveField().begin(), U.size()*sizeof(vector));
     // Foam::vector is three contiguous doubles: internal fields are handed over without a copy
     check
     (
@@ -215,9 +228,23 @@ void Foam::particleCloud::Cd(IOField<scalar>& Cds) const
     ibm_cd(ctx_, Cds.begin());
 }
 
+void Foam::particleCloud::registerField(const void* ptr, const std::size_t bytes) const
+{
+    forAll(registered_, i)
+    {
+        if (registered_[i] == ptr) return;
+    }
+    if (ibm_host_register(ctx_, ptr, bytes) == IBM_OK)   // (a refusal only costs speed: the staged path takes over)
+    {
+        registered_.setSize(registered_.size() + 1);
+        registered_[registered_.size() - 1] = ptr;
+    }
+}
+
 void Foam::particleCloud::solve()
 {
     const volScalarField& p = mesh_.lookupObject<volScalarField>("p");
+    registerField(p.primitiveField().begin(), p.size()*sizeof(scalar));
     tmp<volSymmTensorField> tau(devRhoReff());
     ibm_solve_stats st;
     check
@@ -248,6 +275,9 @@ void Foam::particleCloud::writeFields() const
     const label n = nParticles();
     List<ibm_particle_state> st(n);
     if (n) ibm_get_particles(ctx_, st.begin());
+    // lagrangian/IBMparticles/positions (particle::writeFields, called first by particleIBM::writeFields): the lagrangian
+    // position the reference tracks with the centre (particleIBM.C:313, 426-433); its presence is what readParticles keys on
+    IOField<vector> positions(IOobject("positions", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
     IOField<label> index(IOobject("index", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
     IOField<label> copy(IOobject("copy", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
     IOField<label> active(IOobject("active", time().timeName(), "lagrangian/IBMparticles", mesh_, IOobject::NO_READ), n);
@@ -261,11 +291,13 @@ void Foam::particleCloud::writeFields() const
     {
         index[i] = st[i].index; copy[i] = st[i].copy; active[i] = st[i].active;
         center[i] = vector(st[i].center[0], st[i].center[1], st[i].center[2]);
+        positions[i] = center[i];
         theta[i] = vector(st[i].theta[0], st[i].theta[1], st[i].theta[2]);
         v[i] = vector(st[i].v[0], st[i].v[1], st[i].v[2]);
         omega[i] = vector(st[i].omega[0], st[i].omega[1], st[i].omega[2]);
         rho[i] = st[i].rho; age[i] = st[i].age;
     }
+    positions.write(n > 0);
     index.write(); copy.write(); active.write(); center.write(); theta.write(); v.write(); omega.write();
     rho.write(); age.write();
 }
@@ -284,7 +316,56 @@ bool Foam::particleCloud::writeObject
 
 void Foam::particleCloud::readParticles()
 {
-    NotImplemented;  // restart from lagrangian/IBMparticles: SURVEY §8(f) row 1
+    // reference particleCloudIO.C:47-69 + particleIBMIO.C:111-213: positions decide whether there is anything to read; the
+    // per-particle fields are MUST_READ; every particle gets the shape of particle.<index> at the stored centre
+    const fileName dir("lagrangian/IBMparticles");
+    const word t(mesh_.time().timeName());
+    IOobject posIO("positions", t, dir, mesh_, IOobject::READ_IF_PRESENT, IOobject::NO_WRITE, false);
+    if (!posIO.typeHeaderOk<IOField<vector>>(false))
+    {
+        // "Assuming the initial cloud contains 0 particles" (particleCloudIO.C:62-68)
+        check(ibm_restore_particles(ctx_, 0, nullptr), "readParticles");
+        return;
+    }
+    auto io = [&](const char* name) { return IOobject(name, t, dir, mesh_, IOobject::MUST_READ, IOobject::NO_WRITE, false); };
+    IOField<label> index(io("index"), true), copy(io("copy"), true), active(io("active"), true);
+    IOField<vector> center(io("center"), true), theta(io("theta"), true), v(io("v"), true), omega(io("omega"), true);
+    IOField<scalar> rho(io("rho"), true), age(io("age"), true);
+    const label n = index.size();
+    if (copy.size() != n || active.size() != n || center.size() != n || theta.size() != n || v.size() != n || omega.size() != n
+     || rho.size() != n || age.size() != n)
+    {
+        FatalErrorInFunction << "lagrangian/IBMparticles fields of different sizes at time " << t << exit(FatalError);
+    }
+    List<ibm_particle_state> st(n);
+    forAll(st, i)
+    {
+        ibm_particle_state& s = st[i];
+        s.index = index[i]; s.copy = copy[i]; s.active = active[i]; s.onMesh = IBM_ON_MESH;
+        forAll(center[i], d)
+        {
+            s.center[d] = center[i][d]; s.theta[d] = theta[i][d]; s.v[d] = v[i][d]; s.omega[d] = omega[i][d];
+            s.F[d] = 0; s.T[d] = 0;
+        }
+        s.rho = rho[i]; s.age = age[i]; s.nShell = 0; s.N = 0;
+    }
+    check(ibm_restore_particles(ctx_, n, n ? st.begin() : nullptr), "readParticles");
+}
+
+// ---- per-particle view (reference particleIBM.H:194-391): the state lives on the GPU, a view is a snapshot of one instance ----
+Foam::List<Foam::particleIBM> Foam::particleCloud::particles() const
+{
+    const label n = nParticles();
+    List<ibm_particle_state> st(n);
+    if (n) ibm_get_particles(ctx_, st.begin());
+    List<particleIBM> out(n);
+    forAll(out, i)
+    {
+        double m = 0, inertia = 0;
+        ibm_particle_mass(ctx_, i, &m, &inertia);
+        out[i] = particleIBM(st[i], m, inertia, dict_.subDict(IOobject::groupName("particle", Foam::name(label(st[i].index)))), UInf_, rhoRef_);
+    }
+    return out;
 }
 
 // ---- the viscous stress stays OpenFOAM's (it is not part of the GPU path).  Same sources, in the same order of

@@ -40,7 +40,7 @@ def cyl2d_fixed():
 CASES = {"spheres3d": spheres3d, "cyl2d_fixed": cyl2d_fixed}
 
 
-def write_case(path, case, n_steps, n_outer):
+def write_case(path, case, n_steps, n_outer, n_restart=0):
     m, c, p = case.mesh, case.cloud, case.particles
     assert not m.blocks
     r = repr  # shortest round-trip representation of a double
@@ -55,6 +55,10 @@ def write_case(path, case, n_steps, n_outer):
             f.write(f"{int(p.kind[i])} " + " ".join(r(float(x)) for x in p.position[i]) + f" {r(float(p.d[i]))} {r(float(p.a[i]))} {r(float(p.b[i]))} "
                     f"{int(p.nTheta[i])} {r(float(p.delta[i]))} {r(float(p.rho[i]))} " + " ".join(r(float(x)) for x in p.theta[i]) + " " +
                     " ".join(r(float(x)) for x in p.v[i]) + " " + " ".join(r(float(x)) for x in p.omega[i]) + "\n")
+        if n_restart:
+            # after n_steps the driver writes the time directory, destroys the cloud and constructs a NEW one from it (time != 0:
+            # particleCloud::readParticles), then runs n_restart more steps
+            f.write(f"{int(n_restart)}\n")
 
 
 def run(binary, case_path, out_path, timeout=600):

@@ -44,3 +44,20 @@ def test_shim_side_has_no_cpu_fallback(tmp_path):
     du.write_case(cp, case, n_steps, n_outer)
     r = du.run(du.SHIM_BIN, cp, op)
     assert r.returncode != 0 and "CUDA" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(du.REFERENCE_BIN), reason="shim/dropin/_build/dropin_reference not built (needs /root/reference)")
+def test_reference_side_restarts_from_the_written_time_directory(tmp_path):
+    """the reference's own restart path (particleCloud.C:1119-1123 -> particleCloudIO.C:47-69 -> particleIBMIO.C:111-213): after
+    n steps the driver writes lagrangian/IBMparticles/*, destroys the cloud and constructs a new one at time != 0"""
+    case, n_steps, n_outer = du.CASES["spheres3d"]()
+    cp, op = str(tmp_path / "case.txt"), str(tmp_path / "out.bin")
+    du.write_case(cp, case, 3, 1, n_restart=3)
+    r = du.run(du.REFERENCE_BIN, cp, op)
+    assert r.returncode == 0, r.stderr
+    _, recs = du.parse(op)
+    tags = [t for t, _ in recs]
+    assert tags.count("restarted") == 1 and tags.count("F") == 6
+    d = dict(recs)
+    assert d["restarted"][0] == case.particles.n          # every instance came back from the time directory
+    assert len(d["index"]) == case.particles.n

@@ -86,6 +86,33 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
             assert np.max(np.abs(a - b)) <= (1e-12 if tag == "F" else 1e-9) * max(np.max(np.abs(a)), 1e-300), tag
 
 
+def test_shim_restart_under_emulation(emu_lib, tmp_path):
+    """write -> destroy -> construct at time != 0 (readParticles) -> continue: shim + emulated library against the reference's own
+    restart path (particleCloudIO.C:47-69, particleIBMIO.C:111-213), moving spheres; also the particleIBM views at the end"""
+    import numpy as np
+    import dropin_util as du
+    if not os.path.exists(du.REFERENCE_BIN):
+        pytest.skip("dropin_reference not built (needs /root/reference)")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "shim", "dropin"), "-s", "shim_emu"])
+    case, _, _ = du.CASES["spheres3d"]()
+    cp = str(tmp_path / "case.txt")
+    du.write_case(cp, case, 3, 1, n_restart=3)
+    outs = {}
+    for side, binary in (("reference", du.REFERENCE_BIN), ("shim", os.path.join(du.BUILD, "dropin_shim_emu"))):
+        op = str(tmp_path / f"{side}.bin")
+        r = du.run(binary, cp, op)
+        assert r.returncode == 0, (side, r.stderr)
+        outs[side] = du.parse(op)
+    (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]
+    assert h_ref == h_shim and [t for t, _ in rec_ref] == [t for t, _ in rec_shim]
+    assert dict(rec_shim)["restarted"][0] == case.particles.n
+    for (tag, a), (_, b) in zip(rec_ref, rec_shim):
+        if tag in ("index", "copy", "active", "CoNum", "restarted", "view_index"):
+            assert np.array_equal(a, b), tag
+        else:
+            assert np.max(np.abs(a - b)) <= (1e-12 if tag == "F" else 1e-9) * max(np.max(np.abs(a)), 1e-300), tag
+
+
 @pytest.mark.skipif(not os.environ.get("IBM_RUN_EMULATED_FULL"), reason="set IBM_RUN_EMULATED_FULL=1 (several minutes)")
 @pytest.mark.parametrize("path", ["tests/test_gpu_forcing.py", "tests/test_gpu_marking.py", "tests/test_gpu_stress.py", "tests/test_gpu_motion.py",
                                   "tests/test_gpu_multirank.py", "tests/test_gpu_zz_reference_vectors.py", "tests/test_gpu_zz_device_api.py", "tests/test_gpu_v7_kernels.py", "tests/test_zzz_gpu_solid_fraction.py", "tests/test_zzz_gpu_active_loop5.py",

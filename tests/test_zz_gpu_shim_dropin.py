@@ -39,3 +39,31 @@ def test_shim_is_a_drop_in_for_the_reference_class(tmp_path, name):
         else:
             scale = max(np.max(np.abs(a)), 1e-300)
             assert np.max(np.abs(a - b)) < 1e-9 * scale, (tag, np.max(np.abs(a - b)) / scale)
+
+
+@pytest.mark.skipif(not (os.path.exists(du.REFERENCE_BIN) and os.path.exists(du.SHIM_BIN)), reason="drop-in binaries not built")
+@pytest.mark.parametrize("name", sorted(du.CASES))
+def test_restart_through_the_shim_matches_the_reference(tmp_path, name):
+    """write -> destroy -> construct at time != 0 (particleCloud::readParticles) -> continue, on both sides of the boundary: the
+    shim's readParticles / ibm_restore_particles against the reference's particleCloudIO.C:47-69 + particleIBMIO.C:111-213"""
+    case, n_steps, n_outer = du.CASES[name]()
+    cp = str(tmp_path / "case.txt")
+    du.write_case(cp, case, 3, 1, n_restart=3)
+    outs = {}
+    for side, binary in (("reference", du.REFERENCE_BIN), ("shim", du.SHIM_BIN)):
+        op = str(tmp_path / f"{side}.bin")
+        r = du.run(binary, cp, op)
+        assert r.returncode == 0, (side, r.stderr)
+        outs[side] = du.parse(op)
+    (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]
+    assert h_ref == h_shim and [t for t, _ in rec_ref] == [t for t, _ in rec_shim]
+    assert dict(rec_ref)["restarted"][0] == dict(rec_shim)["restarted"][0]
+    for (tag, a), (_, b) in zip(rec_ref, rec_shim):
+        assert a.shape == b.shape, tag
+        if tag in ("index", "copy", "active", "CoNum", "restarted"):
+            assert np.array_equal(a, b), tag
+        elif tag == "F":
+            assert np.max(np.abs(a - b)) < 1e-12 * np.max(np.abs(a)), tag
+        else:
+            scale = max(np.max(np.abs(a)), 1e-300)
+            assert np.max(np.abs(a - b)) < 1e-9 * scale, (tag, np.max(np.abs(a - b)) / scale)
