@@ -272,7 +272,7 @@ int ctx_update(ibm_ctx* c) {
     }
     launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
     launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
-    launch_exclusive_scan(c->stream, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
+    if (c->nInst > 0) launch_exclusive_scan_total(c->stream, c->sched, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
     c->nLaunch += 9;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -298,6 +298,7 @@ int ctx_update(ibm_ctx* c) {
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  c->schedN = c->nInst;
   c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;   // extent of the shell buffer in use
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
   c->updatesPerCall = c->nInst > 0 ? c->hScal[3] : 0;
@@ -706,8 +707,8 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
   if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
   if (schedule_alloc(c->sched, c->cap)) return ctx_fail(c, IBM_E_CUDA, "schedule_alloc failed");
-  IBM_CUDA(c, cudaMalloc(&c->dKeep, (size_t)c->cap * sizeof(int)));
-  IBM_CUDA(c, cudaMalloc(&c->dKeepOff, (size_t)c->cap * sizeof(int)));
+  IBM_CUDA(c, cudaMalloc(&c->dKeep, ((size_t)c->cap + 1) * sizeof(int)));
+  IBM_CUDA(c, cudaMalloc(&c->dKeepOff, ((size_t)c->cap + 1) * sizeof(int)));
   // upload originals: particleIBM(mesh, dict, index)  particleIBM.C:269-315
   std::vector<int> iv(n);
   std::vector<double> dv(n);

@@ -87,6 +87,7 @@ struct ibm_ctx {
   ibm::V7Caps v7capF{}, v7capS{};  // shared-memory capacities of their launches
   int* dSlowList = nullptr;       // [cap] instances the staged kernel handed to the direct-gather kernel (device-side list)
   ibm::Schedule sched;
+  int schedN = 0;          // instances the schedule's Morton order covers (set by ctx_update; 0 = no valid order)
   int totalChunks = 0;
   int updatesPerCall = 0;
 

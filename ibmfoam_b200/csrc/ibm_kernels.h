@@ -85,6 +85,7 @@ void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* k
 void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,
                               int nInst);
 void launch_exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total);
+void launch_exclusive_scan_total(cudaStream_t st, Schedule& s, const int* in, int* out, int n, int* total);
 void launch_aos_to_soa(cudaStream_t st, const LatticeDev& L, const double* aos, int nComp, double* soa);
 void launch_soa_to_aos(cudaStream_t st, const LatticeDev& L, const double* soa, int nComp, double* aos);
 void launch_copy_int(cudaStream_t st, int* dst, const int* src);

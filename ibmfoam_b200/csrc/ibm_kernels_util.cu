@@ -59,6 +59,7 @@ __global__ void k_clear_shell_cells(const int* __restrict__ shellCell, int total
 __global__ void k_keep_flags(InstanceSoA in, int n, int* __restrict__ keep) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = in.onMesh[i] != 0;
+  else if (i == n) keep[i] = 0;  // sentinel: the exclusive scan over n + 1 entries leaves the total behind the last offset
 }
 
 __global__ void k_compact_instances(InstanceSoA s, InstanceSoA d, const int* __restrict__ keep, const int* __restrict__ keepOff, int n) {
@@ -144,7 +145,7 @@ void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceS
 }
 
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep) {
-  if (nInst > 0) k_keep_flags<<<(nInst + 255) / 256, 256, 0, st>>>(in, nInst, keep);
+  if (nInst > 0) k_keep_flags<<<(nInst + 256) / 256, 256, 0, st>>>(in, nInst, keep);
 }
 void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const InstanceSoA& dst, const int* keep, const int* keepOff,
                               int nInst) {
@@ -153,6 +154,13 @@ void launch_compact_instances(cudaStream_t st, const InstanceSoA& src, const Ins
 
 void launch_exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total) {
   k_exclusive_scan<<<1, 1024, 0, st>>>(in, out, n, total);
+}
+// in[n] must be a zero sentinel and out hold n + 1 entries: out[n] is the total (device-wide scan, ~6 us at n = 1e5 where the
+// single-block kernel above takes 100 us)
+void launch_exclusive_scan_total(cudaStream_t st, Schedule& s, const int* in, int* out, int n, int* total) {
+  size_t tb = s.tempBytes;
+  cub::DeviceScan::ExclusiveSum(s.temp, tb, in, out, n + 1, st);
+  k_last_offset<<<1, 1, 0, st>>>(out, n, total);
 }
 static int grid_for(size_t n, int block, int maxBlocks = 148 * 16) {
   size_t g = (n + block - 1) / block;

@@ -129,6 +129,7 @@ struct Motion {
   int lastActive = 0;           // active instances of the previous split step (sizes the grid of k5a_fused)
   void* scanTemp = nullptr; size_t scanTempBytes = 0;  // cub::DeviceScan scratch of the cluster mode
   int* hEv = nullptr;           // pinned: creation records of the copies of a step (ordering them is a host-side sort)
+  double* dFtPack = nullptr;    // [6][cap] F / T partials packed for the cross-rank sum
   int* dPerm = nullptr;         // [cap] provisional slot (relative) that goes to final slot r
   long long nClusterSteps = 0;
   int lastFlags = 0;            // clusterFail + 1000 violated + 1e6 overflow of the last cluster step (diagnostics)
@@ -998,10 +999,12 @@ __device__ __forceinline__ double nbr_scan_max(const MotionDev& m, const Instanc
 
 // one hop of the neighbourhood maximum: dst_i = scale * max(src_i, src_j over the bodies and images near instance i AND near
 // the places where a copy of i may appear this step) + floor
+// (threads follow the Morton order of the schedule, `order`: neighbouring threads scan neighbouring bins)
 __global__ void k5q_nbrmax(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ src,
-                           double* __restrict__ dst, double scale, double floorB, int doCyclic) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *m.nInst) return;
+                           double* __restrict__ dst, double scale, double floorB, int doCyclic, const int* __restrict__ order, int nOrder) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *m.nInst) return;
+  const int i = (t < nOrder) ? order[t] : t;
   double u = src[i];
   const double S = split_S(m);
   if (in.onMesh[i] != 0 && m.moving && 2.0 * S <= m.binEdge) {
@@ -1035,11 +1038,12 @@ __global__ void k5q_group_budget(MotionDev m) {
   for (int p = head; p >= 0; p = m.instNext[p]) m.bud[p] = b;
 }
 
-__global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k5q_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const int* __restrict__ order, int nOrder) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const double S = split_S(m);
-  if (i == 0) *m.budget = S;
-  if (i >= *m.nInst) return;
+  if (t == 0) *m.budget = S;
+  if (t >= *m.nInst) return;
+  const int i = (t < nOrder) ? order[t] : t;
   const D3 c = ld3(in.c, i);
   int quiet = 1;
   if (in.onMesh[i] != 0) {  // (an instance that is off the mesh does not move at all: particleIBM.C:400-403)
@@ -1478,7 +1482,7 @@ __device__ __forceinline__ void k5c_link_ring(K5cShared& sh, int t) {
 
 // Is a face centre of the patch within r of c?  patchHit / wallHit need one (particleIBM.C:466-472, 505-511).  Exact-enough for
 // lattice-ordered planar patches (face centres = transverse cell centres), "maybe" otherwise: a superset either way.
-__device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const LatticeDev& L, D3 c, double r) {
+__device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const LatticeDev& L, D3 inv, D3 c, double r) {
   const double dx = fmax(fmax(p.lo[0] - c.x, c.x - p.hi[0]), 0.0), dy = fmax(fmax(p.lo[1] - c.y, c.y - p.hi[1]), 0.0),
                dz = fmax(fmax(p.lo[2] - c.z, c.z - p.hi[2]), 0.0);
   const double r2 = r * r * (1.0 + 1e-9) + 1e-300;
@@ -1486,21 +1490,21 @@ __device__ __forceinline__ bool k5c_face_in_reach(const K5cPatch& p, const Latti
   if (!p.lattice) return true;
   // distance to the nearest face centre: the patch plane along its axis, the centre of the containing transverse cell otherwise
   // (products with the inverse spacing: a rounding across a cell boundary picks a centre that is equally far away)
-  auto axisDist = [&](int a, double ca, double o, double d, int n, double plane) {
+  auto axisDist = [&](int a, double ca, double o, double d, double id, int n, double plane) {
     if (a == p.axis) return ca - plane;
-    double t = floor((ca - o) * (1.0 / d));
+    double t = floor((ca - o) * id);
     t = fmin(fmax(t, 0.0), (double)(n - 1));
     return ca - (o + (t + 0.5) * d);
   };
-  const double ex = axisDist(0, c.x, L.ox, L.dx, L.nx, p.lo[0]), ey = axisDist(1, c.y, L.oy, L.dy, L.ny, p.lo[1]),
-               ez = axisDist(2, c.z, L.oz, L.dz, L.nz, p.lo[2]);
+  const double ex = axisDist(0, c.x, L.ox, L.dx, inv.x, L.nx, p.lo[0]), ey = axisDist(1, c.y, L.oy, L.dy, inv.y, L.ny, p.lo[1]),
+               ez = axisDist(2, c.z, L.oz, L.dz, inv.z, L.nz, p.lo[2]);
   const double d2 = ex * ex + ey * ey + ez * ez;
   return d2 <= r2 * (1.0 + 1e-9) + 1e-18 * (L.dx * L.dx + L.dy * L.dy + L.dz * L.dz);
 }
 
 // 0 = nothing, 1 = only contacts between isotropic single-instance bodies under the reference's impulse law (the resident path
 // evaluates them itself, k5c_contact_sum), 2 = anything else (the sub-step takes the general path)
-__device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, int doCyclic, long long& tPair) {
+__device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const MotionDev& m, const LatticeDev& L, D3 inv, int doCyclic, long long& tPair) {
   const long long tp0 = clock64();
   const int f = sh.flags[t];
   if (!(f & K5F_ONMESH) || !m.moving) return 0;
@@ -1532,13 +1536,13 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
   const double r = sh.rad[t];
   const int pmask = sh.pmask[t];
   for (int w = 0; w < m.nWalls; ++w)
-    if (((pmask >> w) & 1) && k5c_face_in_reach(sh.wall[w], L, c, r)) return 2;
+    if (((pmask >> w) & 1) && k5c_face_in_reach(sh.wall[w], L, inv, c, r)) return 2;
   if (doCyclic)
     for (int q = 0; q < m.nCyc; ++q) {  // d5_cyclic_candidates + the reach of a face centre (d5_cyclic_detect)
       if (!((pmask >> (8 + q)) & 1)) continue;
       const K5cPatch& p = sh.cyc[q];
       if (p.type != IBM_CYCLIC) continue;
-      if (!k5c_face_in_reach(p, L, c, r)) continue;
+      if (!k5c_face_in_reach(p, L, inv, c, r)) continue;
       if (p.planar && !(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
       if (p.uniformShift) {
         const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
@@ -1682,6 +1686,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const bool copies = m.nCyc > 0;
   const double cut = m.binEdge * m.binEdge * (1.0 + 1e-9);
   long long tEv = 0, tFl = 0, tSp = 0, tGen = 0, tPair = 0, tEvOwn = 0;
+  const D3 invSpacing{1.0 / L.dx, 1.0 / L.dy, 1.0 / L.dz};
   K5cCache cache[(K5C_CAP + K5C_THREADS - 1) / K5C_THREADS];
   for (auto& ca : cache) { ca.validAcc = 0; ca.dtW = -1.0; }
   const long long tStart = clock64();
@@ -1691,7 +1696,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     // ---- can anything but free flight happen to a member in this sub-step? ----
     int evl = generalOnly ? 2 : 0;
     if (!evl)
-      for (int t = tid; t < sh.nMem; t += K5C_THREADS) evl = max(evl, k5c_event(sh, t, m, L, doCyclic, tPair));
+      for (int t = tid; t < sh.nMem; t += K5C_THREADS) evl = max(evl, k5c_event(sh, t, m, L, invSpacing, doCyclic, tPair));
     tEvOwn += clock64() - t0;
     if (evl) atomicOr(&sh.evMask[s & 1], evl);
     __syncthreads();
@@ -2053,6 +2058,17 @@ k5a_fused(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __rest
   }
 }
 
+// the six F / T components of every instance in one buffer [6][n] and back: ONE all-reduce instead of six
+__global__ void k_pack_ft(InstanceSoA in, int n, double* __restrict__ buf, int unpack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (unpack) { in.F[q][i] = buf[(size_t)q * n + i]; in.T[q][i] = buf[(size_t)(3 + q) * n + i]; }
+    else { buf[(size_t)q * n + i] = in.F[q][i]; buf[(size_t)(3 + q) * n + i] = in.T[q][i]; }
+  }
+}
+
 // particleCloud::combineForces, serial branch (particleCloud.C:268-312)
 __global__ void k_combine_forces(MotionDev m, InstanceSoA in) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2082,11 +2098,15 @@ __global__ void k_group_link(const int* __restrict__ keys, const int* __restrict
   m.instNext[pos] = last ? -1 : vals[q + 1];
 }
 
-// end-of-solve log block (particleCloud.C:1296-1308): fixed-shape tree => deterministic
-__global__ void k_stats(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int n, double* out) {
-  __shared__ double red[32][10];
+// end-of-solve log block (particleCloud.C:1296-1308): fixed-shape tree => deterministic.  Two levels: every block reduces a
+// fixed contiguous segment of the instances, one block then adds the segment sums in order.
+#define STATS_BLOCKS 64
+__global__ void __launch_bounds__(256) k_stats_partial(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, int n, double* part) {
+  __shared__ double red[8][10];
   double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int seg = (n + STATS_BLOCKS - 1) / STATS_BLOCKS;
+  const int i0 = blockIdx.x * seg, i1 = min(i0 + seg, n);
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     double act = in.active[i] ? 1.0 : 0.0;
     D3 v = ld3(in.v, i), om = ld3(in.om, i);
     double mass = classes[in.cls[i]].V * in.rho[i];
@@ -2105,6 +2125,13 @@ __global__ void k_stats(MotionDev m, InstanceSoA in, const ShapeClassDev* __rest
   if (threadIdx.x < 10) {
     double v = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    part[blockIdx.x * 10 + threadIdx.x] = v;
+  }
+}
+__global__ void k_stats_final(const double* __restrict__ part, double* out) {
+  if (threadIdx.x < 10) {
+    double v = 0;
+    for (int b = 0; b < STATS_BLOCKS; ++b) v += part[b * 10 + threadIdx.x];
     out[threadIdx.x] = v;
   }
 }
@@ -2169,7 +2196,7 @@ static int motion_init(ibm_ctx* c) {
             dalloc(c, M, &d.binCnt, (size_t)d.nbx * d.nby * d.nbz) && dalloc(c, M, &d.binItems, (size_t)d.nbx * d.nby * d.nbz * d.binCap) &&
             dalloc(c, M, &d.binPos, (size_t)3 * d.nbx * d.nby * d.nbz * d.binCap) && dalloc(c, M, &d.pairCount, 1) &&
             dalloc(c, M, &d.pairI, (size_t)d.pairCap) && dalloc(c, M, &d.pairJ, (size_t)d.pairCap) && dalloc(c, M, &d.cPos, cap * CONTACT_CAP) &&
-            dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16) &&
+            dalloc(c, M, &M->dIdxKeys, cap) && dalloc(c, M, &M->dIdxKeys2, cap) && dalloc(c, M, &M->dStats, 16 + 10 * STATS_BLOCKS) &&
             dalloc(c, M, &d.act, cap) && dalloc(c, M, &d.nAct, 1) && dalloc(c, M, &d.quiet, cap) && dalloc(c, M, &d.c0, 3 * cap) &&
             dalloc(c, M, &d.vaBits, 2) && dalloc(c, M, &d.budget, 1) && dalloc(c, M, &d.violated, 1) &&
             dalloc(c, M, &d.sOwn, cap) && dalloc(c, M, &d.uMax, cap) && dalloc(c, M, &d.bud, cap) && dalloc(c, M, &d.noSplit, 1) && dalloc(c, M, &M->snap, 12 * cap) &&
@@ -2182,7 +2209,7 @@ static int motion_init(ibm_ctx* c) {
        dalloc(c, M, &d.label, cap) && dalloc(c, M, &d.compCnt, cap) && dalloc(c, M, &d.compOff, cap + 1) && dalloc(c, M, &d.compCur, cap) &&
        dalloc(c, M, &d.sorted, cap) && dalloc(c, M, &d.ctaBegin, (size_t)d.ctaBins) && dalloc(c, M, &d.ctaEnd, (size_t)d.ctaBins) &&
        dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) && dalloc(c, M, &d.clusterStat, 16) &&
-       dalloc(c, M, &M->dPerm, cap);
+       dalloc(c, M, &M->dPerm, cap) && dalloc(c, M, &M->dFtPack, 6 * cap);
   if (!ok) return IBM_E_CUDA;
   {
     size_t sb = 0;
@@ -2348,10 +2375,10 @@ int combine_forces(ibm_ctx* c) {
   if (comm_ranks(c) > 1 && c->nInst > 0) {
     // cross-rank part of combineForces (particleCloud.C:236-237): every rank holds every instance, so the partials
     // of one instance over the slabs are summed element-wise
-    for (int q = 0; q < 3; ++q) {
-      if ((rc = comm_allreduce_sum(c, c->in.F[q], (size_t)c->nInst, 0))) return rc;
-      if ((rc = comm_allreduce_sum(c, c->in.T[q], (size_t)c->nInst, 0))) return rc;
-    }
+    k_pack_ft<<<blocks_for(c->nInst), 128, 0, c->stream>>>(c->in, c->nInst, M->dFtPack, 0);
+    if ((rc = comm_allreduce_sum(c, M->dFtPack, (size_t)6 * c->nInst, 0))) return rc;
+    k_pack_ft<<<blocks_for(c->nInst), 128, 0, c->stream>>>(c->in, c->nInst, M->dFtPack, 1);
+    c->nLaunch += 2;
   }
   if (c->nParticles > 0) {
     k_combine_forces<<<blocks_for(c->nParticles), 128, 0, c->stream>>>(M->d, c->in);
@@ -2441,10 +2468,11 @@ static void active_classify(ibm_ctx* c, double dtStep) {
   k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
   k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
   if (doCyclic) { k5q_ghosts<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses); c->nLaunch++; }
-  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0, doCyclic ? 1 : 0);
-  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge, doCyclic ? 1 : 0);
+  // the schedule's Morton order is a permutation of the instances the last update() saw (c->schedN of them)
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0, doCyclic ? 1 : 0, c->sched.order, c->schedN);
+  k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge, doCyclic ? 1 : 0, c->sched.order, c->schedN);
   if (c->nParticles > 0) { k5q_group_budget<<<blocks_for(c->nParticles), 128, 0, st>>>(d); c->nLaunch++; }
-  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, c->sched.order, c->schedN);
   c->nLaunch += 5;
 }
 
@@ -2743,8 +2771,9 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
   if ((rc = ctx_update(c))) return rc;  // invalidates the same-index lists when instances were deleted
   if ((rc = ensure_motion(c))) return rc;
   if (stats) {
-    k_stats<<<1, 1024, 0, c->stream>>>(M->d, c->in, c->dClasses, c->nInst, M->dStats);
-    c->nLaunch++;
+    k_stats_partial<<<STATS_BLOCKS, 256, 0, c->stream>>>(M->d, c->in, c->dClasses, c->nInst, M->dStats + 16);
+    k_stats_final<<<1, 32, 0, c->stream>>>(M->dStats + 16, M->dStats);
+    c->nLaunch += 2;
     double h[10];
     IBM_CUDA(c, cudaMemcpyAsync(h, M->dStats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
