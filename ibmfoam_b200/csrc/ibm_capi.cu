@@ -403,7 +403,9 @@ struct CopyPool {
       if (--pending == 0) cvDone.notify_all();
     }
   }
+  std::mutex callers;  // one copy at a time: contexts of several host threads (in-process ranks) share the pool
   void copy(void* d, const void* s2, size_t n) {
+    std::lock_guard<std::mutex> one(callers);
     std::unique_lock<std::mutex> lk(mu);
     dst = (char*)d; src = (const char*)s2; bytes = n; pending = nT; ++generation;
     cvGo.notify_all();

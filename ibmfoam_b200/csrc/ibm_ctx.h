@@ -97,7 +97,7 @@ struct ibm_ctx {
   bool activeLoop5 = true;  // quiet / active split of a fluid step (ibm_motion.cu, k5q_bounds): same results, less work per
                             // sub-step; written after round 1's GPU budget was spent, verified under emulation only
   int activeSafetyPpm = 2000000;  // displacement-budget safety factor in parts per million (>= 1: a quiet instance needs B_i >= s_i)
-  int markVariant = 0;            // 1 = k1_mark2 (compacted polar-bin phase), same outputs
+  int markVariant = 1;            // 1 = k1_mark2 (compacted polar-bin phase; 1.46 vs 2.07 ms per update at 512^3 / 10^5), 0 = k1_mark; same outputs
   int collisionModel = 0;         // EXTENSION: 1 = soft-sphere contact law (ibm_motion.cu d5_pair_force); 0 = the reference's impulse
   double softKn = 0.0, softGammaN = 0.0, softGammaT = 0.0, softMu = 0.0;
   bool clusterOneBlockCC = false;  // test hook: connected components by the single-block kernel

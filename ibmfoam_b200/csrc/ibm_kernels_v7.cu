@@ -254,6 +254,18 @@ __device__ __forceinline__ bool make_st7(const Geo7& G, const Box7& B, const int
   return true;
 }
 
+// gather NC component planes (component q of cell idx at f[q * n + idx])
+template <int NC>
+__device__ __forceinline__ void gat7_planes(const St7& s, const double* __restrict__ f, int n, double* out) {
+#pragma unroll
+  for (int q = 0; q < NC; ++q) out[q] = s.c[0] * f[q * n + s.idx[0]];
+#pragma unroll
+  for (int d = 1; d < 7; ++d) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q) out[q] = fma(s.c[d], f[q * n + s.idx[d]], out[q]);
+  }
+}
+
 // gather NC interleaved components of a record plane (record = NC doubles per cell)
 template <int NC>
 __device__ __forceinline__ void gat7(const St7& s, const double* __restrict__ f, double* out) {
@@ -549,10 +561,10 @@ struct Str7Ctx {
   const double* planes;
   double cx, cy, cz, R, delta, rS, pRefOverRho, rhoRef, sfScale;
   double rot[9];
-  int kind, nT, nk;
+  int kind, nT, nk, nB;
 };
 
-template <bool EDGE, int NT>
+template <bool EDGE, int NT, bool SOA>
 __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
   int guard = 0;
   const int nSurf = X.nT * X.nk;
@@ -564,7 +576,7 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
     double pp = 0.0;
     St7 st;
     if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, pt, st, guard)) {
-      gat7<7>(st, X.planes, g);
+      if (SOA) gat7_planes<7>(st, X.planes, X.nB, g); else gat7<7>(st, X.planes, g);
       pp = (g[0] - 2.0 * st.c[0] * X.pRefOverRho) * X.rhoRef;
 #pragma unroll
       for (int q = 1; q < 7; ++q) g[q] *= X.rhoRef;
@@ -601,7 +613,7 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
   return guard;
 }
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool SOA>
 __global__ void __launch_bounds__(NT, MINB)
 k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
             const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
@@ -677,7 +689,7 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
 #pragma unroll
       for (int q = 0; q < 6; ++q) v[1 + q] = __ldg(Tau + q * C + g);
 #pragma unroll
-      for (int q = 0; q < 7; ++q) planes[7 * a + q] = v[q];
+      for (int q = 0; q < 7; ++q) planes[SOA ? q * nB + a : 7 * a + q] = v[q];
     }
     __syncthreads();
     Str7Ctx X;
@@ -687,8 +699,8 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
     X.sfScale = (sc.kind == 0) ? (R * R) * sc.dTheta : R * sc.dTheta * sc.l;
 #pragma unroll
     for (int q = 0; q < 9; ++q) X.rot[q] = in.rot[9 * (size_t)b + q];
-    X.kind = sc.kind; X.nT = nT; X.nk = nk;
-    const int bad = B.edge ? stress_points7<true, NT>(X, acc) : stress_points7<false, NT>(X, acc);
+    X.kind = sc.kind; X.nT = nT; X.nk = nk; X.nB = nB;
+    const int bad = B.edge ? stress_points7<true, NT, SOA>(X, acc) : stress_points7<false, NT, SOA>(X, acc);
     if (bad) atomicExch(guardFlag, 1);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -815,17 +827,17 @@ static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClass
   }
   k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
 }
-template <int NT, int MINB>
+template <int NT, int MINB, bool SOA>
 static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const Schedule& s,
                          const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, const V7Caps& cap, int* slowList,
                          int* slowCount, int* guard, int sm) {
   static PerDeviceOnce attr;
   static int attrBytes = 0;
   if (attr.first() || sm > attrBytes) {
-    cudaFuncSetAttribute(k_stress_v7<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_stress_v7<NT, MINB, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_stress_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
+  k_stress_v7<NT, MINB, SOA><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
 }
 
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
@@ -855,7 +867,10 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
-#define IBM_S7(NT_, MB_) stress_v7_nt<NT_, MB_>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm)
+  static int soa = -1;
+  if (soa < 0) { const char* e = getenv("IBM_V7_STRESS_SOA"); soa = e ? atoi(e) : 0; }
+#define IBM_S7(NT_, MB_) do { if (soa) stress_v7_nt<NT_, MB_, true>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); \
+                              else stress_v7_nt<NT_, MB_, false>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); } while (0)
   if (nt == 320) IBM_S7(320, 2);
   else if (nt == 192) { if (three) IBM_S7(192, 3); else IBM_S7(192, 2); }
   else if (nt == 224) { if (three) IBM_S7(224, 3); else IBM_S7(224, 2); }

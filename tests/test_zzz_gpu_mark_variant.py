@@ -1,6 +1,5 @@
-"""Marking kernel, second version (ibm_set_option "mark_variant" = 1, k1_mark2: radial test over the bounding box, polar
-bins over the compacted list): the outputs must be those of the first version - bit-exact against the oracle.
-Written after the round's GPU budget was spent; verified under the CPU emulation (tools/cuda_emu).  Not a default."""
+"""Both marking kernels (ibm_set_option "mark_variant": 1 = k1_mark2, the default since round 2 - radial test over the bounding
+box, polar bins over the compacted list; 0 = k1_mark, the single-pass first version): bit-exact against the oracle."""
 import numpy as np
 import pytest
 
@@ -12,10 +11,19 @@ import ibm_testutil as util
 pytestmark = pytest.mark.gpu
 
 
+VARIANT = [1]
+
+
+@pytest.fixture(autouse=True, params=[1, 0])
+def _variant(request):
+    VARIANT[0] = request.param
+    yield
+
+
 def _cloud(case, **kw):
     gc = ParticleCloud(case, **kw)
-    gc.set_option("mark_variant", 1)
-    gc.update()                      # the constructor marked with the default kernel: mark again with the second version
+    gc.set_option("mark_variant", VARIANT[0])
+    gc.update()                      # the constructor marked with the default kernel: mark again with the requested version
     return gc
 
 
