@@ -1191,6 +1191,59 @@ __device__ __forceinline__ void k5c_emit(const MotionDev& m, int a, int b) {
   else atomicExch(m.clusterFail, 1);
 }
 
+// k5q_classify and k5c_edges in one pass (cluster mode): quiet / active decision with the cut-offs of k5q_classify, every
+// possible partner emitted as an edge, the group head linked, label initialised
+__global__ void k5c_classify(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const int* __restrict__ order, int nOrder) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const double S = split_S(m);
+  if (t == 0) *m.budget = S;
+  if (t >= *m.nInst) return;
+  const int i = (t < nOrder) ? order[t] : t;
+  int quiet = 1;
+  if (in.onMesh[i] != 0) {  // (an instance that is off the mesh does not move at all: particleIBM.C:400-403)
+    const D3 c = ld3(in.c, i);
+    const ShapeClassDev* sc = classes + in.cls[i];
+    const double Bi = m.bud[i];
+    const int head = m.idxHead[in.index[i]];
+    const bool multi = head >= 0 && m.instNext[head] >= 0;
+    if (multi) quiet = 0;
+    if (*m.noSplit) { quiet = 0; atomicExch(m.clusterFail, 1); }
+    if (m.moving) {
+      if (quiet) {
+        const double reach = sc->Rbound + Bi;
+        for (int w = 0; w < m.nWalls && quiet; ++w)
+          if (patch_in_reach(m.patches[m.wallPatch[w]], c, reach)) quiet = 0;
+        for (int s = 0; s < m.nCyc && quiet; ++s)
+          if (patch_in_reach(m.patches[m.cycPatch[s]], c, reach)) quiet = 0;
+      }
+      if (2.0 * S > m.binEdge) { quiet = 0; atomicExch(m.clusterFail, 1); }  // no bound on the interactions: no clusters this step
+      else {
+        const double di = dmax_of(*sc);
+        const BinRange br = bin_range(m, c, 0.5 * (di + m.binEdge) + Bi + 4.0 * S);
+        for (int z = br.z0; z <= br.z1; ++z)
+          for (int y = br.y0; y <= br.y1; ++y)
+            for (int x = br.x0; x <= br.x1; ++x) {
+              const int bin = x + m.nbx * (y + m.nby * z);
+              const int nb = m.binCnt[bin];
+              if (nb > m.binCap) { quiet = 0; atomicExch(m.clusterFail, 1); continue; }  // entries are missing
+              for (int q = 0; q < nb; ++q) {
+                const size_t o = (size_t)bin * m.binCap + q;
+                int j, mult;
+                bin_entry(m.binItems[o], j, mult);
+                if (j == i) continue;
+                const double cut = 0.5 * (di + dmax_of(classes[in.cls[j]])) + Bi + mult * m.bud[j];
+                const double ddx = m.binPos[3 * o] - c.x, ddy = m.binPos[3 * o + 1] - c.y, ddz = m.binPos[3 * o + 2] - c.z;
+                if (ddx * ddx + ddy * ddy + ddz * ddz <= cut * cut * (1.0 + 1e-9)) { quiet = 0; k5c_emit(m, i, j); }
+              }
+            }
+      }
+    }
+    if (multi && head != i) k5c_emit(m, i, head);
+  }
+  m.quiet[i] = quiet;
+  if (!quiet) { m.act[atomicAdd(m.nAct, 1)] = i; m.label[i] = i; }
+}
+
 // possible partners of every active instance: same scan and cut-offs as k5q_classify, all hits instead of the first
 __global__ void k5c_edges(MotionDev m, InstanceSoA in, const ShapeClassDev* __restrict__ classes) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1310,21 +1363,31 @@ __global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const Shape
   const D3 Fh = ld3(in.F, i), Th = ld3(in.T, i);
   D3 v = ld3(in.v, i), c = ld3(in.c, i), om = ld3(in.om, i), th = ld3(in.th, i);
   const double mI = mass * sc->I;
+  // F/m + g and dt T/(m I) have the same operands in every sub-step (one dt for all but possibly the last): evaluated once
+  D3 acc{0, 0, 0}, dW{0, 0, 0};
+  double dtW = -1.0;
+  if (m.moving) {
+    D3 sFc{0, 0, 0}, sFw{0, 0, 0};
+    for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
+    const D3 F = Fh + sFc + sFw;
+    acc = F / mass + D3{m.gx, m.gy, m.gz};
+  }
   for (int s = 0; s < nSub; ++s) {
     const double dt = dts[s];
     if (m.moving) {
-      D3 sFc{0, 0, 0}, sFw{0, 0, 0};
-      for (int w = 0; w < m.nWalls; ++w) sFw = sFw + D3{0.0, 0.0, 0.0};
-      const D3 F = Fh + sFc + sFw;
-      v = v + dt * (F / mass + D3{m.gx, m.gy, m.gz});
+      v = v + dt * acc;
       const D3 dx = dt * v;
       c = c + dx;
     }
     if (m.rotating) {
-      D3 sTc{0, 0, 0}, sTw{0, 0, 0};
-      for (int w = 0; w < m.nWalls; ++w) sTw = sTw + D3{0.0, 0.0, 0.0};
-      const D3 T = Th + sTc + sTw;
-      om = om + dt * T / mI;
+      if (dtW != dt) {
+        D3 sTc{0, 0, 0}, sTw{0, 0, 0};
+        for (int w = 0; w < m.nWalls; ++w) sTw = sTw + D3{0.0, 0.0, 0.0};
+        const D3 T = Th + sTc + sTw;
+        dW = dt * T / mI;
+        dtW = dt;
+      }
+      om = om + dW;
       th = th + om * dt;
       if (th.z < 0) th.z += IBM_TWOPI;
       if (th.z >= IBM_TWOPI) th.z -= IBM_TWOPI;
@@ -1542,7 +1605,8 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
       if (!((pmask >> (8 + q)) & 1)) continue;
       const K5cPatch& p = sh.cyc[q];
       if (p.type != IBM_CYCLIC) continue;
-      if (!k5c_face_in_reach(p, L, inv, c, r)) continue;
+      // every condition is necessary for a new copy; the cheap ones first (most bodies near a patch move away from it or have
+      // their copy already)
       if (p.planar && !(dot3(v, D3{p.nrm[0], p.nrm[1], p.nrm[2]}) > 0)) continue;
       if (p.uniformShift) {
         const D3 nc = c + D3{p.shift[0], p.shift[1], p.shift[2]};
@@ -1550,6 +1614,7 @@ __device__ __forceinline__ int k5c_event(const K5cShared& sh, int t, const Motio
         for (int u = sh.ring[t]; u != t && !have; u = sh.ring[u]) have = magSqr3(nc - D3{sh.px[u], sh.py[u], sh.pz[u]}) < 0.25e-8;
         if (have) continue;
       }
+      if (!k5c_face_in_reach(p, L, inv, c, r)) continue;
       return 2;
     }
   return code;
@@ -2455,7 +2520,7 @@ static int substep_launch_active(ibm_ctx* c, double localDt) {
 }
 
 // start of a split step: bounds, bins at the start positions, classification
-static void active_classify(ibm_ctx* c, double dtStep) {
+static void active_classify(ibm_ctx* c, double dtStep, bool clusterMode = false) {
   Motion* M = (Motion*)c->motion;
   MotionDev& d = M->d;
   cudaStream_t st = c->stream;
@@ -2472,7 +2537,7 @@ static void active_classify(ibm_ctx* c, double dtStep) {
   k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.sOwn, d.uMax, 1.0, 0.0, doCyclic ? 1 : 0, c->sched.order, c->schedN);
   k5q_nbrmax<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, d.uMax, d.bud, d.safety, 1e-12 * d.binEdge, doCyclic ? 1 : 0, c->sched.order, c->schedN);
   if (c->nParticles > 0) { k5q_group_budget<<<blocks_for(c->nParticles), 128, 0, st>>>(d); c->nLaunch++; }
-  k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, c->sched.order, c->schedN);
+  if (!clusterMode) k5q_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, c->sched.order, c->schedN);
   c->nLaunch += 5;
 }
 
@@ -2494,15 +2559,15 @@ static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
   cudaStream_t st = c->stream;
   const int cap = c->cap;
   const int doCyclic = (d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls)) ? 1 : 0;
-  active_classify(c, dtStep);
   cudaMemsetAsync(d.nEdge, 0, sizeof(int), st);
   cudaMemsetAsync(d.clusterFail, 0, sizeof(int), st);
+  active_classify(c, dtStep, true);  // budgets; the decision itself is k5c_classify below (it also emits the edges)
   cudaMemsetAsync(d.compCnt, 0, (size_t)cap * sizeof(int), st);
   cudaMemsetAsync(d.compCur, 0, (size_t)cap * sizeof(int), st);
   cudaMemsetAsync(d.ctaBegin, 0x7f, (size_t)d.ctaBins * sizeof(int), st);
   cudaMemsetAsync(d.ctaEnd, 0, (size_t)d.ctaBins * sizeof(int), st);
   k_copy_int<<<1, 1, 0, st>>>(d.nextSlot, d.nInst);
-  k5c_edges<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses);
+  k5c_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, c->sched.order, c->schedN);
   if (c->clusterOneBlockCC) {
     k5c_components<<<1, 1024, 0, st>>>(d);
   } else {
