@@ -841,16 +841,34 @@ int ibm_substep(ibm_ctx* c, double localDt) {
   return motion_substep(c, localDt);
 }
 
+// the sparse re-zeroing of the forcing field (its consumer is done with it once solve() is called) beside the stress integral
+static void clear_F_on_side(ibm_ctx* c) {
+  cudaStream_t side = motion_side_stream(c);
+  if (!side || !c->fLive || !c->dF) return;
+  launch_clear_shell_cells(side, c->dShellCell, c->totalShell, (size_t)c->L.nCells, c->dF);
+  c->nLaunch++;
+  c->fLive = false;
+  // (the side stream's work is joined by motion_advance before the shell lists are rebuilt)
+}
+
 int ibm_solve(ibm_ctx* c, const double* p, const double* tau6, double dt, ibm_solve_stats* stats) {
-  int rc = ibm_integrate_stress(c, p, tau6, nullptr);
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  int rc = motion_prepare_async(c, dt);
   if (rc) return rc;
+  clear_F_on_side(c);
+  if ((rc = ibm_integrate_stress(c, p, tau6, nullptr))) return rc;
   if ((rc = combine_forces(c))) return rc;
   return motion_advance(c, dt, stats);
 }
 
 int ibm_solve_device(ibm_ctx* c, const double* dP, const double* dTau6, double dt, ibm_solve_stats* stats) {
-  int rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr);
+  if (!c) return IBM_E_ARG;
+  cudaSetDevice(c->device);
+  int rc = motion_prepare_async(c, dt);
   if (rc) return rc;
+  clear_F_on_side(c);
+  if ((rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr))) return rc;
   if ((rc = combine_forces(c))) return rc;
   return motion_advance(c, dt, stats);
 }
@@ -1216,6 +1234,7 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_loop5") == 0) { c->clusterLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_one_block_cc") == 0) { c->clusterOneBlockCC = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "async_prepare") == 0) { c->asyncPrepare = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_general_only") == 0) { c->clusterGeneralOnly = value != 0; return IBM_OK; }
   if (std::strcmp(name, "active_loop5_safety_ppm") == 0) { c->activeSafetyPpm = value; return IBM_OK; }
   if (std::strcmp(name, "fused_active_loop5") == 0) { c->fusedActive = value != 0; return IBM_OK; }

@@ -100,6 +100,7 @@ struct ibm_ctx {
   int markVariant = 1;            // 1 = k1_mark2 (compacted polar-bin phase; 1.46 vs 2.07 ms per update at 512^3 / 10^5), 0 = k1_mark; same outputs
   int collisionModel = 0;         // EXTENSION: 1 = soft-sphere contact law (ibm_motion.cu d5_pair_force); 0 = the reference's impulse
   double softKn = 0.0, softGammaN = 0.0, softGammaT = 0.0, softMu = 0.0;
+  bool asyncPrepare = true;        // ibm_solve: loop-5 classification and the re-zeroing of F on a side stream beside the stress integral
   bool clusterOneBlockCC = false;  // test hook: connected components by the single-block kernel
   bool clusterGeneralOnly = false; // test hook: every sub-step of a block takes the general path (no resident fast path)
   bool clusterLoop5 = true;       // split steps: independent groups of active instances, all sub-steps of a group in one block (k5c_run)
@@ -126,6 +127,8 @@ int ctx_ensure_pinned(ibm_ctx* c, size_t doubles);
 int ctx_update(ibm_ctx* c);
 // ibm_motion.cu
 int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats);
+int motion_prepare_async(ibm_ctx* c, double dt);   // classification of the coming advance on a side stream (call before the stress integral)
+cudaStream_t motion_side_stream(ibm_ctx* c);      // that stream while a prepared classification is pending, else null
 int motion_substep(ibm_ctx* c, double localDt);
 void motion_destroy(ibm_ctx* c);
 void motion_invalidate_groups(ibm_ctx* c);

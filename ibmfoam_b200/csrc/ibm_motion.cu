@@ -132,6 +132,9 @@ struct Motion {
   double* dFtPack = nullptr;    // [6][cap] F / T partials packed for the cross-rank sum
   int* dPerm = nullptr;         // [cap] provisional slot (relative) that goes to final slot r
   long long nClusterSteps = 0;
+  cudaStream_t side = nullptr;  // classification of the coming advance beside the stress integral (motion_prepare_async)
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool prepared = false; double preparedDt = 0.0; int preparedNInst = 0;
   int lastFlags = 0;            // clusterFail + 1000 violated + 1e6 overflow of the last cluster step (diagnostics)
 };
 
@@ -2520,7 +2523,7 @@ static int substep_launch_active(ibm_ctx* c, double localDt) {
 }
 
 // start of a split step: bounds, bins at the start positions, classification
-static void active_classify(ibm_ctx* c, double dtStep, bool clusterMode = false) {
+static void active_classify(ibm_ctx* c, double dtStep, bool clusterMode = false, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr) {
   Motion* M = (Motion*)c->motion;
   MotionDev& d = M->d;
   cudaStream_t st = c->stream;
@@ -2530,7 +2533,12 @@ static void active_classify(ibm_ctx* c, double dtStep, bool clusterMode = false)
   cudaMemsetAsync(d.nAct, 0, sizeof(int), st);
   cudaMemsetAsync(d.violated, 0, sizeof(int), st);
   cudaMemsetAsync(d.noSplit, 0, sizeof(int), st);
-  k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);
+  k5q_bounds<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, dtStep);  // (reads the hydrodynamic force: before anything rewrites it)
+  if (side) {  // everything below only needs positions, velocities and the bounds: it may run beside the caller's next kernels
+    cudaEventRecord(fork, st);
+    cudaStreamWaitEvent(side, fork, 0);
+    st = side;
+  }
   k5_bin<<<blocks_for(cap), 128, 0, st>>>(d, c->in);
   if (doCyclic) { k5q_ghosts<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses); c->nLaunch++; }
   // the schedule's Morton order is a permutation of the instances the last update() saw (c->schedN of them)
@@ -2553,20 +2561,22 @@ static void active_prologue(ibm_ctx* c, double dtStep, int nSub) {
 }
 
 // cluster mode: classification, components, packing, quiet instances, then ONE launch for every sub-step of the active ones
-static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
+// cluster mode, part 1: classification, components, packing.  With a side stream (motion_prepare_async) everything after
+// the displacement bounds runs beside the caller's next kernels - the surface-stress integral of the same solve() - and
+// `join` is recorded behind it.
+static void cluster_prepare(ibm_ctx* c, double dtStep, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr) {
   Motion* M = (Motion*)c->motion;
   MotionDev& d = M->d;
-  cudaStream_t st = c->stream;
   const int cap = c->cap;
-  const int doCyclic = (d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls)) ? 1 : 0;
-  cudaMemsetAsync(d.nEdge, 0, sizeof(int), st);
-  cudaMemsetAsync(d.clusterFail, 0, sizeof(int), st);
-  active_classify(c, dtStep, true);  // budgets; the decision itself is k5c_classify below (it also emits the edges)
+  cudaMemsetAsync(d.nEdge, 0, sizeof(int), c->stream);
+  cudaMemsetAsync(d.clusterFail, 0, sizeof(int), c->stream);
+  k_copy_int<<<1, 1, 0, c->stream>>>(d.nextSlot, d.nInst);
+  active_classify(c, dtStep, true, side, fork);  // budgets; the decision itself is k5c_classify below (it also emits the edges)
+  cudaStream_t st = side ? side : c->stream;
   cudaMemsetAsync(d.compCnt, 0, (size_t)cap * sizeof(int), st);
   cudaMemsetAsync(d.compCur, 0, (size_t)cap * sizeof(int), st);
   cudaMemsetAsync(d.ctaBegin, 0x7f, (size_t)d.ctaBins * sizeof(int), st);
   cudaMemsetAsync(d.ctaEnd, 0, (size_t)d.ctaBins * sizeof(int), st);
-  k_copy_int<<<1, 1, 0, st>>>(d.nextSlot, d.nInst);
   k5c_classify<<<blocks_for(cap), 128, 0, st>>>(d, c->in, c->dClasses, c->sched.order, c->schedN);
   if (c->clusterOneBlockCC) {
     k5c_components<<<1, 1024, 0, st>>>(d);
@@ -2584,9 +2594,18 @@ static void cluster_sequence(ibm_ctx* c, double dtStep, int nSub) {
   cub::DeviceScan::ExclusiveSum(M->scanTemp, tb, d.compCnt, d.compOff, cap, st);
   k5c_place<<<blocks_for(cap), 128, 0, st>>>(d);
   cudaMemsetAsync(d.binCnt, 0, (size_t)d.nbx * d.nby * d.nbz * sizeof(int), st);
-  k5c_quiet<<<blocks_for(cap), 128, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
-  k5c_run<<<d.ctaBins, K5C_THREADS, 0, st>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub, doCyclic, c->clusterGeneralOnly ? 1 : 0);
-  c->nLaunch += 9;
+  c->nLaunch += 7;
+  if (side) cudaEventRecord(join, side);
+}
+
+// cluster mode, part 2: every sub-step of the quiet instances in one kernel, every sub-step of the active ones in another
+static void cluster_execute(ibm_ctx* c, int nSub) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  const int doCyclic = (d.nCyc > 0 && (d.nWalls > 0 || c->cfg.cyclicWithoutWalls)) ? 1 : 0;
+  k5c_quiet<<<blocks_for(c->cap), 128, 0, c->stream>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub);
+  k5c_run<<<d.ctaBins, K5C_THREADS, 0, c->stream>>>(d, c->Lg, c->in, c->dClasses, M->dDts, nSub, doCyclic, c->clusterGeneralOnly ? 1 : 0);
+  c->nLaunch += 2;
 }
 
 static int finish_substeps(ibm_ctx* c) {
@@ -2641,16 +2660,9 @@ int motion_substep(ibm_ctx* c, double localDt) {
   return finish_substeps(c);
 }
 
-int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
-  int rc = ensure_motion(c);
-  if (rc) return rc;
-  Motion* M = (Motion*)c->motion;
-  refresh_contact_model(c);
-  ctx_tic(c, T_ADVANCE);
-  // literal loop of particleCloud.C:1247-1275 (App. B #22): the schedule of local time steps is plain fp64
-  // scalar arithmetic, evaluated here and handed to the persistent kernel
+// literal loop of particleCloud.C:1247-1275 (App. B #22): the schedule of local time steps is plain fp64 scalar arithmetic
+static int substep_schedule(double dt, double* dts) {
   int nSub = 0;
-  double dts[256];
   double localDt = dt / 100.0, localTime = localDt;
   while (localTime < dt) {
     if (nSub < 256) dts[nSub] = localDt;
@@ -2658,7 +2670,62 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     if (localTime + localDt > dt) localDt = dt - localTime;
     else localTime += localDt;
   }
+  return nSub;
+}
+
+static bool cluster_applies(ibm_ctx* c, int nSub) {
+  Motion* M = (Motion*)c->motion;
+  return !c->fusedLoop5 && c->activeLoop5 && c->clusterLoop5 && M->splitAllowed && nSub <= 256 && c->nInst > 0;
+}
+
+// Called by ibm_solve BEFORE the surface-stress integral: the classification of the coming advance (bounds from the force
+// and torque of the previous solve - any bound is safe, the budgets are checked), on a side stream beside the stress
+// kernel; the sparse re-zeroing of the forcing field rides along.  motion_advance picks the result up.
+int motion_prepare_async(ibm_ctx* c, double dt) {
+  int rc = ensure_motion(c);
+  if (rc) return rc;
+  Motion* M = (Motion*)c->motion;
+  M->prepared = false;
+  if (!c->asyncPrepare) return IBM_OK;
+  double dts[256];
+  const int nSub = substep_schedule(dt, dts);
+  if (!cluster_applies(c, nSub)) return IBM_OK;
+  if (!M->side) {
+    IBM_CUDA(c, cudaStreamCreateWithFlags(&M->side, cudaStreamNonBlocking));
+    IBM_CUDA(c, cudaEventCreateWithFlags(&M->evFork, cudaEventDisableTiming));
+    IBM_CUDA(c, cudaEventCreateWithFlags(&M->evJoin, cudaEventDisableTiming));
+  }
+  refresh_contact_model(c);
+  M->d.activeMode = 1;
+  M->d.safety = std::max(1.0, 1e-6 * c->activeSafetyPpm);
+  M->d.check = std::min(1.0, 1e-6 * c->activeCheckPpm);
   ensure_bins_clear(c);
+  IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 0);
+  c->nLaunch++;
+  cluster_prepare(c, dt, M->side, M->evFork, M->evJoin);
+  M->prepared = true;
+  M->preparedDt = dt;
+  M->preparedNInst = c->nInst;
+  IBM_CUDA(c, cudaGetLastError());
+  return IBM_OK;
+}
+cudaStream_t motion_side_stream(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  return (M && M->prepared) ? M->side : nullptr;
+}
+
+int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
+  int rc = ensure_motion(c);
+  if (rc) return rc;
+  Motion* M = (Motion*)c->motion;
+  refresh_contact_model(c);
+  ctx_tic(c, T_ADVANCE);
+  double dts[256];
+  int nSub = substep_schedule(dt, dts);
+  const bool prepared = M->prepared && M->preparedDt == dt && M->preparedNInst == c->nInst && cluster_applies(c, nSub);
+  M->prepared = false;
+  if (!prepared) ensure_bins_clear(c);
   if (c->fusedLoop5 && nSub <= 256 && M->fusedBlocks > 0) {
     MotionDev& d = M->d;
     IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -2676,7 +2743,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     M->d.activeMode = split ? 1 : 0;
     M->d.safety = std::max(1.0, 1e-6 * c->activeSafetyPpm);  // (a quiet instance needs B_i >= s_i)
     M->d.check = std::min(1.0, 1e-6 * c->activeCheckPpm);
-    if (split) {
+    if (split && !prepared) {
       IBM_CUDA(c, cudaMemcpyAsync(M->dDts, dts, nSub * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       k5q_snapshot<<<blocks_for(std::max(c->cap, c->nParticles)), 128, 0, c->stream>>>(M->d, c->in, M->snap, M->snapActive, M->snapMaxCopies, 0);
       c->nLaunch++;
@@ -2693,7 +2760,9 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     if (cluster) {
       // one launch sequence per fluid step, no per-sub-step kernel boundary; flags, the instance count and the creation
       // records of new copies come back with ONE synchronisation
-      cluster_sequence(c, dt, nSub);
+      if (prepared) IBM_CUDA(c, cudaStreamWaitEvent(c->stream, M->evJoin, 0));  // classified beside the stress integral
+      else cluster_prepare(c, dt);
+      cluster_execute(c, nSub);
       M->nClusterSteps++;
       MotionDev& d = M->d;
       int* h = M->hEv;
@@ -2856,6 +2925,7 @@ void motion_destroy(ibm_ctx* c) {
   if (!M) return;
   if (M->graphExec) cudaGraphExecDestroy(M->graphExec);
   if (M->hEv) cudaFreeHost(M->hEv);
+  if (M->side) { cudaStreamSynchronize(M->side); cudaStreamDestroy(M->side); cudaEventDestroy(M->evFork); cudaEventDestroy(M->evJoin); }
   for (void* p : M->allocs) cudaFree(p);
   if (M->cubTemp) cudaFree(M->cubTemp);
   delete M;
