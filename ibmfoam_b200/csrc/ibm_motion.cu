@@ -2691,7 +2691,10 @@ int motion_prepare_async(ibm_ctx* c, double dt) {
   const int nSub = substep_schedule(dt, dts);
   if (!cluster_applies(c, nSub)) return IBM_OK;
   if (!M->side) {
-    IBM_CUDA(c, cudaStreamCreateWithFlags(&M->side, cudaStreamNonBlocking));
+    // highest priority: its small kernels must be scheduled as blocks of the (SM-filling) stress kernel retire, not after it
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    IBM_CUDA(c, cudaStreamCreateWithPriority(&M->side, cudaStreamNonBlocking, prHi));
     IBM_CUDA(c, cudaEventCreateWithFlags(&M->evFork, cudaEventDisableTiming));
     IBM_CUDA(c, cudaEventCreateWithFlags(&M->evJoin, cudaEventDisableTiming));
   }
