@@ -12,7 +12,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def stage(msg):
+    print(f"[nccl_worker rank {os.environ.get('RANK')}] {msg}", flush=True)
+
+
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)  # a rank stuck in a collective shows where, and the test ends
     import torch
     import torch.distributed as dist
     from ibmfoam_b200 import cases
@@ -29,6 +35,7 @@ def main():
         idt.copy_(torch.tensor(list(nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
     nccl_id = bytes(idt.cpu().tolist())
+    stage("process group up")
 
     # ---- loops 1-4 on slabs + combineForces over NCCL ----
     case = cases.assembly(n=48, n_particles=70, seed=11, moving=True, cyclic_without_walls=True)
@@ -46,6 +53,7 @@ def main():
     k0, k1 = ranges[rank]
     sl = slice(k0 * nxy, k1 * nxy)
     gc = ParticleCloud(case, device=local, slab=(k0, k1), nccl_id=nccl_id, rank=rank, n_ranks=world)
+    stage("cloud 1 created")
     oc = oracles[rank]
     sg, so = gc.state_arrays(), oc.state_arrays()
     pos = {int(i): n for n, i in enumerate(sg["index"])}
@@ -56,12 +64,14 @@ def main():
     Fg = gc.forcing(f_lat["S"][sl], f_lat["U"][sl], f_lat["Uold"][sl], case.dt)
     assert util.rel_err(Fg, Fo) < 1e-12
     gc.integrateSurfaceStresses(f_lat["p"][sl], f_lat["tau"][sl])
+    stage("loops 1-4 done")
     gc.combineForces()  # ncclAllReduce of the partials + the same-index sum
     tot = np.zeros((case.particles.n, 6))
     for rr, o2 in enumerate(oracles):
         for n_o, idx in enumerate(o2.state_arrays()["index"]):
             tot[pos[int(idx)]] += FTo[rr][n_o]
     st = gc.state_arrays()
+    stage("combined")
     got = np.concatenate([st["F"], st["T"]], axis=1)
     scale = max(np.max(np.abs(x)) for x in FTo)
     assert np.max(np.abs(got - tot)) < 1e-10 * scale, np.max(np.abs(got - tot)) / scale
@@ -71,6 +81,7 @@ def main():
     dist.broadcast(t0, 0)
     assert torch.equal(t, t0), "combined F/T differ between ranks"
     gc.close()
+    stage("cloud 1 closed")
 
     # ---- loop 5 replicated over the ranks == the serial reference, with periodic copies and deletions ----
     fast = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
@@ -79,6 +90,7 @@ def main():
     ocs = OracleCloud(fast)
     gcs = ParticleCloud(fast, device=local, slab=slab_ranges(fast.mesh.nz, world)[rank], nccl_id=nccl_unique_id_shared(dist, dev, rank),
                         rank=rank, n_ranks=world)
+    stage("cloud 2 created")
     rng = np.random.default_rng(0)
     for s in range(3):
         FT = rng.normal(0, 1e-3, (400, 6))
@@ -87,6 +99,7 @@ def main():
         a, b = ocs.state_arrays(), gcs.state_arrays()
         for k in ("index", "copy", "active", "onMesh", "center", "theta", "v", "omega"):
             assert np.array_equal(a[k], b[k]), (k, s)
+        stage(f"step {s} equal")
     assert ocs.n_instances != 60
     gcs.close()
     dist.barrier()

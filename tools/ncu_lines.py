@@ -3,6 +3,7 @@ usage: python tools/ncu_lines.py report.ncu-rep kernel_regex [top]"""
 import csv, subprocess, sys, collections
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+SORTKEY = sys.argv[4] if len(sys.argv) > 4 else "samples"   # or "inst"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kern}"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -26,6 +27,6 @@ for r in rows:
 tot = sum(a["samples"] for a in agg.values())
 ti = sum(a["inst"] for a in agg.values())
 print(f"total samples {tot}, warp instructions {ti}")
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][SORTKEY])[:top]:
     st = ",".join(f"{k}:{v}" for k, v in a["stalls"].most_common(3))
     print(f"{a['samples']/tot:6.3f} inst {a['inst']/ti:5.3f} tags {a['tags']:9d} shw {a['shw']:8d}/{a['shi']:8d} {f}:{ln:4d} [{st}] {a['src'][:90]}")
