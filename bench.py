@@ -419,7 +419,7 @@ def main():
                 "stress_kernel_ms": tm["stress_ms"] / args.steps,
                 "stress_frac": (((56.0 * 4.0 / 3.0 * math.pi * (5 ** 3 - 3 ** 3) + 48.0) * n_inst * (local_updates / max(updates_per_step, 1.0))) / (tm["stress_ms"] / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tm["stress_ms"] > 0 else None}
     breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}
-    loop5 = {k: cloud.counter(k) for k in ("loop5_active_instances", "loop5_fallbacks", "loop5_cluster_steps", "loop5_block_substeps", "loop5_general_substeps")}
+    loop5 = {k: cloud.counter(k) for k in ("loop5_active_instances", "loop5_fallbacks", "loop5_cluster_steps", "loop5_block_substeps", "loop5_general_substeps", "loop5_owned_steps")}
     gpu_launches = tm["n_kernel_launches"]
 
     # ---- e2e: host C-ABI calls with host arrays in OpenFOAM's layout, copies inside the timed region ----
@@ -499,7 +499,10 @@ def main():
                            "l2": "inputs (13 GB of fields) larger than L2; no explicit flush", "setup_s": setup_s,
                            "kernel_generations": generations, "loop5": loop5},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-                "parallelism": None if world == 1 else f"z-slabs x{world}: fields decomposed, particle directory replicated, NCCL all-reduce of F/T partials and on-mesh counts",
+                "parallelism": None if world == 1 else (f"z-slabs x{world}: fields decomposed; loops 1-4 on the local slab; loop 5 "
+                                                              + ("owned by slab (a rank advances the instances and contact groups whose centre lies in its slab; states and new periodic copies exchanged once per fluid step over NCCL)"
+                                                                 if cloud.counter("loop5_owned_steps") > 0 else "replicated on every rank")
+                                                              + "; NCCL all-reduce of F/T partials and on-mesh counts"),
                 "breakdown_ms_per_step": breakdown, "wall_ms_per_step": wall_ms / args.steps}
         print(json.dumps(line))
     barrier()

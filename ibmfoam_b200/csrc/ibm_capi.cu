@@ -558,6 +558,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_CHUNK256")) c->chunk256 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CLUSTER_LOOP5")) c->clusterLoop5 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_OWNED_LOOP5")) c->ownedLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_MARK_VARIANT")) c->markVariant = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("IBM_KERNEL_VARIANT")) {  // "f,s": forcing / stress kernel generation (like ibm_set_kernel_variant)
     int f = 0, s2 = 0;
@@ -1233,6 +1234,7 @@ int ibm_set_option(ibm_ctx* c, const char* name, int value) {
   if (std::strcmp(name, "chunk256") == 0) { c->chunk256 = value != 0; return c->cap != 0 ? ctx_update(c) : IBM_OK; }
   if (std::strcmp(name, "active_loop5") == 0) { c->activeLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_loop5") == 0) { c->clusterLoop5 = value != 0; return IBM_OK; }
+  if (std::strcmp(name, "owned_loop5") == 0) { c->ownedLoop5 = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_one_block_cc") == 0) { c->clusterOneBlockCC = value != 0; return IBM_OK; }
   if (std::strcmp(name, "async_prepare") == 0) { c->asyncPrepare = value != 0; return IBM_OK; }
   if (std::strcmp(name, "cluster_general_only") == 0) { c->clusterGeneralOnly = value != 0; return IBM_OK; }

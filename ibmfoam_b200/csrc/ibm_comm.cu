@@ -24,7 +24,7 @@ namespace ibm {
 // ---- minimal NCCL ABI (nccl.h: ncclUniqueId is 128 opaque bytes; enums are stable across 2.x) ----
 typedef struct ncclComm* ncclComm_t;
 struct NcclUniqueId { char internal[128]; };
-enum { kNcclSum = 0, kNcclInt32 = 2, kNcclFloat64 = 8 };
+enum { kNcclSum = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclFloat64 = 8 };
 typedef int (*fn_GetUniqueId)(NcclUniqueId*);
 typedef int (*fn_CommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
 typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
@@ -103,13 +103,14 @@ __global__ void k_sum_ranks(const void* const* src, int nRanks, size_t count, T*
 int comm_ranks(ibm_ctx* c) { return c->comm ? ((Comm*)c->comm)->nRanks : 1; }
 int comm_rank(ibm_ctx* c) { return c->comm ? ((Comm*)c->comm)->rank : 0; }
 
-// in-place all-reduce(sum) of `count` doubles (isInt = 0) or int32 (isInt = 1) on the ctx stream
+// in-place all-reduce(sum) of `count` doubles (isInt = 0), int32 (isInt = 1) or int64 (isInt = 2: bit patterns of values
+// that exactly one rank contributes travel unchanged, x + 0 + ... + 0 being exact in integers) on the ctx stream
 int comm_allreduce_sum(ibm_ctx* c, void* buf, size_t count, int isInt) {
   Comm* cm = (Comm*)c->comm;
   if (!cm || cm->nRanks == 1 || count == 0) return IBM_OK;
-  const size_t esz = isInt ? sizeof(int) : sizeof(double);
+  const size_t esz = isInt == 1 ? sizeof(int) : sizeof(double);
   if (cm->nccl) {
-    int rc = g_nccl.AllReduce(buf, buf, count, isInt ? kNcclInt32 : kNcclFloat64, kNcclSum, cm->nccl, c->stream);
+    int rc = g_nccl.AllReduce(buf, buf, count, isInt == 1 ? kNcclInt32 : (isInt == 2 ? kNcclInt64 : kNcclFloat64), kNcclSum, cm->nccl, c->stream);
     if (rc != 0) return ctx_fail(c, IBM_E_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     return IBM_OK;
   }
@@ -125,7 +126,8 @@ int comm_allreduce_sum(ibm_ctx* c, void* buf, size_t count, int isInt) {
   lg->barrier();                                   // all contributions complete and published
   IBM_CUDA(c, cudaMemcpyAsync(cm->dSrcList, lg->src.data(), lg->n * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
   int blocks = (int)std::min<size_t>((count + 255) / 256, 1184);
-  if (isInt) k_sum_ranks<int><<<blocks, 256, 0, c->stream>>>(cm->dSrcList, lg->n, count, (int*)cm->tmp);
+  if (isInt == 1) k_sum_ranks<int><<<blocks, 256, 0, c->stream>>>(cm->dSrcList, lg->n, count, (int*)cm->tmp);
+  else if (isInt == 2) k_sum_ranks<long long><<<blocks, 256, 0, c->stream>>>(cm->dSrcList, lg->n, count, (long long*)cm->tmp);
   else k_sum_ranks<double><<<blocks, 256, 0, c->stream>>>(cm->dSrcList, lg->n, count, (double*)cm->tmp);
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   lg->barrier();                                   // everyone has finished reading the sources

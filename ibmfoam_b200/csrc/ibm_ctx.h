@@ -104,6 +104,7 @@ struct ibm_ctx {
   bool clusterOneBlockCC = false;  // test hook: connected components by the single-block kernel
   bool clusterGeneralOnly = false; // test hook: every sub-step of a block takes the general path (no resident fast path)
   bool clusterLoop5 = true;       // split steps: independent groups of active instances, all sub-steps of a group in one block (k5c_run)
+  bool ownedLoop5 = true;         // multi-GPU cluster steps: every rank advances the instances / groups its slab owns, one exchange per fluid step
   bool fusedActive = false;       // split steps: the active list's sub-steps in one persistent cooperative kernel (k5a_fused)
   int activeCheckPpm = 1000000;   // fraction of B_i the per-sub-step check allows (tests shrink it to force the fallback)
   // motion (loop 5) scratch lives in ibm_motion.cu

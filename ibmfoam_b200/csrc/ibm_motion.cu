@@ -94,6 +94,14 @@ struct MotionDev {
   int* evSub; int* evKey;          // [cap] per provisional slot: sub-step of creation, patchSlot * cap + position of the source
   unsigned long long* clusterStat; // [2] block sub-steps in total / on the general path (diagnostics of the last steps)
   int* clusterFail;                // a block ran out of room (members, candidates, hits): the step is redone unsplit
+  // multi-GPU, cluster mode (option owned_loop5): loop 5 is partitioned by subdomain.  An instance that integrates alone
+  // belongs to the rank whose z-slab holds its centre at the start of the step, a block of k5c_run to the rank that owns its
+  // first member; every rank advances what it owns and the new states (and new periodic copies) are exchanged once per
+  // fluid step (k5x_pack / all-reduce / k5x_unpack) - the counterpart of particleCloud.C:316-444, 838-899
+  int owned, rank, nRanks;
+  int slabK0[17];                  // first global z-plane of every rank's slab; [nRanks] = planes of the global mesh
+  double ownOz, ownDz; int ownNz;
+  int* mine;                       // [cap] 1 = this rank advanced the instance in this step
 };
 
 struct Motion {
@@ -136,6 +144,10 @@ struct Motion {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   bool prepared = false; double preparedDt = 0.0; int preparedNInst = 0;
   int lastFlags = 0;            // clusterFail + 1000 violated + 1e6 overflow of the last cluster step (diagnostics)
+  long long* dX = nullptr;      // exchange buffer of the owned mode (k5x_pack)
+  size_t xWords = 0;
+  bool slabsKnown = false;
+  long long nOwnedSteps = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1355,12 +1367,26 @@ __global__ void k5c_place(MotionDev m) {
   }
 }
 
+// rank that owns a centre at height z (owned mode): the slab that holds the z-plane of the cell the centre lies in, centres
+// below / above the mesh going to the first / last slab
+__device__ __forceinline__ int owner_of(const MotionDev& m, double z) {
+  const double q = floor((z - m.ownOz) / m.ownDz);
+  int K = q > 0.0 ? (q < (double)(m.ownNz - 1) ? (int)q : m.ownNz - 1) : 0;  // (a NaN ends up in plane 0 on every rank)
+  int r = 0;
+  while (r + 1 < m.nRanks && K >= m.slabK0[r + 1]) ++r;
+  return r;
+}
+
 // every sub-step of a quiet instance by one thread, state in registers: the arithmetic of d5_solve with empty contact and
 // wall tables (sums of nothing are exact zeros, particleIBM.C:408-414), operation for operation
 __global__ void k5c_quiet(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restrict__ classes, const double* __restrict__ dts,
                           int nSub) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *m.nInst || !m.quiet[i] || in.onMesh[i] == 0) return;
+  if (m.owned) {
+    if (owner_of(m, in.c[2][i]) != m.rank) return;  // somebody else's: its new state arrives with the exchange
+    m.mine[i] = 1;
+  }
   const ShapeClassDev* sc = classes + in.cls[i];
   const double mass = sc->V * in.rho[i];
   const D3 Fh = ld3(in.F, i), Th = ld3(in.T, i);
@@ -1722,6 +1748,7 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const int beg = m.ctaBegin[b], end = m.ctaEnd[b];
   if (end <= beg) return;
   if (*m.clusterFail) return;
+  if (m.owned && owner_of(m, m.c0[2 * (size_t)m.cap + m.sorted[beg]]) != m.rank) return;  // a block belongs to the owner of its first member
   const int tid = threadIdx.x;
   if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
   if (tid == 0) {
@@ -1964,8 +1991,139 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
     atomicMax(&m.clusterStat[6], (unsigned long long)(clock64() - tStart)); atomicMax(&m.clusterStat[7], (unsigned long long)sh.nMem);
     atomicMax(&m.clusterStat[8], (unsigned long long)(tStart - tLaunch));
   }
-  for (int t = tid; t < sh.nMem; t += K5C_THREADS) k5c_store_state(sh, t, in);
+  for (int t = tid; t < sh.nMem; t += K5C_THREADS) {
+    k5c_store_state(sh, t, in);
+    if (m.owned) m.mine[sh.mem[t]] = 1;
+  }
   if (tid == 0 && sh.fail) atomicExch(m.clusterFail, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Owned mode: the exchange of a fluid step.  One buffer of 64-bit words, summed over the ranks as integers (every word is
+// written by at most one rank with a value, by the others with 0, so bit patterns travel unchanged):
+//   header [32]            [0] new copies in total, [1] clusterFail, [2] violated, [3] overflow, [8 + r] new copies of rank r
+//   touched [n0]           1 where the rank advanced the instance
+//   state [13][n0]         centre, v, omega, theta, active of the instances it advanced
+//   records [nRanks][Q]    the periodic copies it created (provisional slots n0, n0 + 1, ... of that rank), K5X_REC words each
+// ------------------------------------------------------------------------------------------------
+#define K5X_HEAD 32
+#define K5X_REC 32
+#define K5X_Q 256
+__device__ __forceinline__ long long dbits(double x) { return __double_as_longlong(x); }
+__device__ __forceinline__ double bitsd(long long x) { return __longlong_as_double(x); }
+
+__global__ void k5x_pack(MotionDev m, InstanceSoA in, int n0, long long* __restrict__ X) {
+  const size_t N0 = (size_t)n0;
+  long long* T = X + K5X_HEAD;
+  long long* S = T + N0;
+  long long* R = S + 13 * N0;
+  const int cnt = *m.nextSlot - n0;
+  const int nRec = m.nRanks * K5X_Q;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n0 + nRec + K5X_HEAD; t += gridDim.x * blockDim.x) {
+    if (t < n0) {
+      const int i = t;
+      const bool me = m.mine[i] != 0;
+      T[i] = me ? 1 : 0;
+      for (int q = 0; q < 3; ++q) {
+        S[(size_t)q * N0 + i] = me ? dbits(in.c[q][i]) : 0;
+        S[(size_t)(3 + q) * N0 + i] = me ? dbits(in.v[q][i]) : 0;
+        S[(size_t)(6 + q) * N0 + i] = me ? dbits(in.om[q][i]) : 0;
+        S[(size_t)(9 + q) * N0 + i] = me ? dbits(in.th[q][i]) : 0;
+      }
+      S[(size_t)12 * N0 + i] = me ? (long long)in.active[i] : 0;
+    } else if (t < n0 + nRec) {
+      const int rq = t - n0, r = rq / K5X_Q, q = rq - r * K5X_Q;
+      long long* rec = R + (size_t)rq * K5X_REC;
+      const bool me = r == m.rank && q < cnt;
+      if (!me) {
+        for (int w = 0; w < K5X_REC; ++w) rec[w] = 0;
+      } else {
+        const int s = n0 + q;
+        rec[0] = in.index[s]; rec[1] = in.copy[s]; rec[2] = in.active[s]; rec[3] = in.onMesh[s]; rec[4] = in.cls[s];
+        rec[5] = m.evSub[s]; rec[6] = m.evKey[s];
+        for (int a = 0; a < 3; ++a) {
+          rec[7 + a] = dbits(in.c[a][s]); rec[10 + a] = dbits(in.th[a][s]); rec[13 + a] = dbits(in.v[a][s]); rec[16 + a] = dbits(in.om[a][s]);
+        }
+        rec[19] = dbits(in.rho[s]); rec[20] = dbits(in.age[s]); rec[21] = dbits(m.bud[s]);
+        for (int a = 0; a < 9; ++a) rec[22 + a] = dbits(in.rot[9 * (size_t)s + a]);
+        rec[31] = 1;
+      }
+    } else {
+      const int h = t - n0 - nRec;
+      long long v = 0;
+      if (h == 0) v = cnt > 0 ? cnt : 0;
+      else if (h == 1) v = (*m.clusterFail != 0 || cnt > K5X_Q || cnt < 0) ? 1 : 0;
+      else if (h == 2) v = *m.violated != 0;
+      else if (h == 3) v = *m.overflow != 0;
+      else if (h == 8 + m.rank) v = cnt > 0 ? cnt : 0;
+      X[h] = v;
+    }
+  }
+}
+
+__global__ void k5x_unpack(MotionDev m, InstanceSoA in, int n0, const long long* __restrict__ X) {
+  const size_t N0 = (size_t)n0;
+  const long long* T = X + K5X_HEAD;
+  const long long* S = T + N0;
+  const long long* R = S + 13 * N0;
+  const int nRec = m.nRanks * K5X_Q;
+  const long long total = X[0];
+  const bool bad = X[1] != 0 || (long long)n0 + total > (long long)m.cap;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n0 + nRec + 1; t += gridDim.x * blockDim.x) {
+    if (t < n0) {
+      const int i = t;
+      m.mine[i] = 0;  // (ready for the next step)
+      if (T[i] == 1) {
+        for (int q = 0; q < 3; ++q) {
+          in.c[q][i] = bitsd(S[(size_t)q * N0 + i]);
+          in.v[q][i] = bitsd(S[(size_t)(3 + q) * N0 + i]);
+          in.om[q][i] = bitsd(S[(size_t)(6 + q) * N0 + i]);
+          in.th[q][i] = bitsd(S[(size_t)(9 + q) * N0 + i]);
+        }
+        in.active[i] = (int)S[(size_t)12 * N0 + i];
+      } else if (T[i] != 0) {
+        atomicExch(m.clusterFail, 1);  // two ranks advanced the same instance: the ownership rule was not the same everywhere
+      }
+    } else if (t < n0 + nRec) {
+      if (bad) continue;
+      const int rq = t - n0, r = rq / K5X_Q, q = rq - r * K5X_Q;
+      if (q >= X[8 + r]) continue;
+      int off = 0;
+      for (int r2 = 0; r2 < r; ++r2) off += (int)X[8 + r2];
+      const long long* rec = R + (size_t)rq * K5X_REC;
+      const int dst = n0 + off + q;
+      const int idx = (int)rec[0];
+      in.index[dst] = idx; in.copy[dst] = (int)rec[1]; in.active[dst] = (int)rec[2]; in.onMesh[dst] = (int)rec[3]; in.cls[dst] = (int)rec[4];
+      m.evSub[dst] = (int)rec[5];
+      {
+        // the source of a copy may itself be a copy created earlier in the step: its provisional slot moves with its rank's offset
+        const int key = (int)rec[6], patch = key / m.cap;
+        int src = key - patch * m.cap;
+        if (src >= n0) src += off;
+        m.evKey[dst] = patch * m.cap + src;
+      }
+      for (int a = 0; a < 3; ++a) {
+        in.c[a][dst] = bitsd(rec[7 + a]); in.th[a][dst] = bitsd(rec[10 + a]); in.v[a][dst] = bitsd(rec[13 + a]); in.om[a][dst] = bitsd(rec[16 + a]);
+        in.F[a][dst] = 0.0; in.T[a][dst] = 0.0;
+        m.c0[(size_t)a * m.cap + dst] = bitsd(rec[7 + a]);
+      }
+      in.rho[dst] = bitsd(rec[19]); in.age[dst] = bitsd(rec[20]); m.bud[dst] = bitsd(rec[21]);
+      for (int a = 0; a < 9; ++a) in.rot[9 * (size_t)dst + a] = bitsd(rec[22 + a]);
+      in.nShell[dst] = 0; in.shellOff[dst] = 0; in.nPtsOnMesh[dst] = 0;
+      m.quiet[dst] = 0; m.cCnt[dst] = 0; m.cCnt2[dst] = 0; m.mine[dst] = 0;
+      for (int w = 0; w < m.nWalls; ++w)
+        for (int a = 0; a < 3; ++a) {
+          const size_t o = 3 * ((size_t)dst * m.nWalls + w) + a;
+          m.Fw[o] = 0.0; m.Tw[o] = 0.0; m.Fw2[o] = 0.0; m.Tw2[o] = 0.0;
+        }
+      atomicMax(&m.maxCopies[idx], (int)rec[1]);  // (the copies of one index all come from one block, hence from one rank)
+    } else {
+      *m.nextSlot = bad ? n0 : n0 + (int)total;
+      if (bad) *m.clusterFail = 1;
+      if (X[2] != 0) *m.violated = 1;
+      if (X[3] != 0) *m.overflow = 1;
+    }
+  }
 }
 
 // new instances [n0, n0 + total) into the reference's append order: dst slot n0 + r takes provisional slot n0 + perm[r]
@@ -2277,8 +2435,9 @@ static int motion_init(ibm_ctx* c) {
        dalloc(c, M, &d.label, cap) && dalloc(c, M, &d.compCnt, cap) && dalloc(c, M, &d.compOff, cap + 1) && dalloc(c, M, &d.compCur, cap) &&
        dalloc(c, M, &d.sorted, cap) && dalloc(c, M, &d.ctaBegin, (size_t)d.ctaBins) && dalloc(c, M, &d.ctaEnd, (size_t)d.ctaBins) &&
        dalloc(c, M, &d.nextSlot, 1) && dalloc(c, M, &d.evSub, cap) && dalloc(c, M, &d.evKey, cap) && dalloc(c, M, &d.clusterFail, 1) && dalloc(c, M, &d.clusterStat, 16) &&
-       dalloc(c, M, &M->dPerm, cap) && dalloc(c, M, &M->dFtPack, 6 * cap);
+       dalloc(c, M, &M->dPerm, std::max<size_t>(cap, 32)) && dalloc(c, M, &M->dFtPack, 6 * cap) && dalloc(c, M, &d.mine, cap);
   if (!ok) return IBM_E_CUDA;
+  d.owned = 0; d.rank = 0; d.nRanks = 1;
   {
     size_t sb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, sb, d.compCnt, d.compOff, c->cap);
@@ -2432,6 +2591,7 @@ bool motion_counter(ibm_ctx* c, const char* name, long long* value) {
   }
   if (std::strcmp(name, "loop5_cluster_flags") == 0) { *value = M ? M->lastFlags : 0; return true; }
   if (std::strcmp(name, "loop5_cluster_steps") == 0) { *value = M ? M->nClusterSteps : 0; return true; }
+  if (std::strcmp(name, "loop5_owned_steps") == 0) { *value = M ? M->nOwnedSteps : 0; return true; }
   if (std::strcmp(name, "loop5_active_instances") == 0) { *value = (M && M->d.activeMode) ? c->hScal[11] : -1; return true; }  // of the last advance
   return false;
 }
@@ -2673,6 +2833,60 @@ static int substep_schedule(double dt, double* dts) {
   return nSub;
 }
 
+// Owned mode (multi-GPU cluster steps): who owns what.  The slabs of the ranks are gathered once (every rank knows only its
+// own, ibm_set_slab); ranks whose slabs do not tile the z-planes in rank order (every rank holding the whole mesh, say) fall
+// back to equal shares of the planes.
+static int owned_setup(ibm_ctx* c) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  const int nR = comm_ranks(c);
+  d.owned = 0;
+  if (!c->ownedLoop5 || nR < 2 || nR > 16) return IBM_OK;
+  if (!M->slabsKnown) {
+    int h[17] = {0};
+    h[comm_rank(c)] = c->L.kz0;
+    int* dTmp = (int*)M->dPerm;  // (scratch of the step's end, free here)
+    IBM_CUDA(c, cudaMemcpyAsync(dTmp, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    int rc = comm_allreduce_sum(c, dTmp, 17, 1);
+    if (rc) return rc;
+    IBM_CUDA(c, cudaMemcpyAsync(h, dTmp, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int nz = c->Lg.nz;
+    bool tiles = h[0] == 0;
+    for (int r = 1; r < nR; ++r) tiles = tiles && h[r] > h[r - 1] && h[r] < nz;
+    for (int r = 0; r < nR; ++r) d.slabK0[r] = tiles ? h[r] : (int)((long long)nz * r / nR);
+    d.slabK0[nR] = nz;
+    d.ownOz = c->Lg.oz; d.ownDz = c->Lg.dz; d.ownNz = nz;
+    d.rank = comm_rank(c); d.nRanks = nR;
+    M->slabsKnown = true;
+  }
+  d.owned = 1;
+  return IBM_OK;
+}
+
+// the exchange of an owned step: after it every rank holds the new state of every instance, the new copies of all ranks at
+// provisional slots in rank order, and the OR of the failure flags
+static int owned_exchange(ibm_ctx* c, int n0) {
+  Motion* M = (Motion*)c->motion;
+  MotionDev& d = M->d;
+  const size_t words = (size_t)K5X_HEAD + 14 * (size_t)n0 + (size_t)d.nRanks * K5X_Q * K5X_REC;
+  if (M->xWords < words) {
+    const size_t want = (size_t)K5X_HEAD + 14 * (size_t)c->cap + (size_t)d.nRanks * K5X_Q * K5X_REC;
+    if (M->dX) cudaFree(M->dX);
+    M->dX = nullptr; M->xWords = 0;
+    IBM_CUDA(c, cudaMalloc(&M->dX, want * sizeof(long long)));
+    M->xWords = want;
+  }
+  const int threads = n0 + d.nRanks * K5X_Q + K5X_HEAD;
+  k5x_pack<<<blocks_for(threads), 128, 0, c->stream>>>(d, c->in, n0, M->dX);
+  int rc = comm_allreduce_sum(c, M->dX, words, 2);
+  if (rc) return rc;
+  k5x_unpack<<<blocks_for(threads), 128, 0, c->stream>>>(d, c->in, n0, M->dX);
+  c->nLaunch += 2;
+  M->nOwnedSteps++;
+  return IBM_OK;
+}
+
 static bool cluster_applies(ibm_ctx* c, int nSub) {
   Motion* M = (Motion*)c->motion;
   return !c->fusedLoop5 && c->activeLoop5 && c->clusterLoop5 && M->splitAllowed && nSub <= 256 && c->nInst > 0;
@@ -2765,7 +2979,10 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       // records of new copies come back with ONE synchronisation
       if (prepared) IBM_CUDA(c, cudaStreamWaitEvent(c->stream, M->evJoin, 0));  // classified beside the stress integral
       else cluster_prepare(c, dt);
+      if ((rc = owned_setup(c))) { ctx_toc(c); return rc; }
+      if (M->d.owned) IBM_CUDA(c, cudaMemsetAsync(M->d.mine, 0, (size_t)c->cap * sizeof(int), c->stream));
       cluster_execute(c, nSub);
+      if (M->d.owned && (rc = owned_exchange(c, nInst0))) { ctx_toc(c); return rc; }
       M->nClusterSteps++;
       MotionDev& d = M->d;
       int* h = M->hEv;
@@ -2931,6 +3148,7 @@ void motion_destroy(ibm_ctx* c) {
   if (M->side) { cudaStreamSynchronize(M->side); cudaStreamDestroy(M->side); cudaEventDestroy(M->evFork); cudaEventDestroy(M->evJoin); }
   for (void* p : M->allocs) cudaFree(p);
   if (M->cubTemp) cudaFree(M->cubTemp);
+  if (M->dX) cudaFree(M->dX);
   delete M;
   c->motion = nullptr;
 }

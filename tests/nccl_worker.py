@@ -101,6 +101,7 @@ def main():
             assert np.array_equal(a[k], b[k]), (k, s)
         stage(f"step {s} equal")
     assert ocs.n_instances != 60
+    assert gcs.counter("loop5_owned_steps") > 0  # every rank advanced what its slab owns; states and copies came over NCCL
     gcs.close()
     dist.barrier()
     if rank == 0:

@@ -106,10 +106,12 @@ def test_loops_1_to_4_match_decomposed_oracle(n_ranks):
     group.close()
 
 
-def test_loop5_replicated_equals_serial_oracle():
-    """Loop 5 runs redundantly on every rank from identical state: trajectories, periodic copies and deletions are
-    those of the SERIAL reference (decomposition-independent), bit for bit, on every rank."""
-    n_ranks = 2
+@pytest.mark.parametrize("n_ranks,owned", [(2, 1), (3, 1), (2, 0)])
+def test_loop5_replicated_equals_serial_oracle(n_ranks, owned):
+    """Loop 5 over several ranks: trajectories, periodic copies and deletions are those of the SERIAL reference
+    (decomposition-independent), bit for bit, on every rank.  owned = 1 (default): every rank advances the instances and
+    groups its slab owns and the states / new copies are exchanged once per fluid step; owned = 0: every rank advances
+    everything redundantly from identical state."""
     case = cases.assembly(n=48, n_particles=60, seed=4, moving=True, cyclic_without_walls=True)
     case.particles.v *= 25.0
     case.dt = 0.5
@@ -127,6 +129,7 @@ def test_loop5_replicated_equals_serial_oracle():
 
     def rank(r):
         gc = ParticleCloud(case, slab=ranges[r], local_group=group.handle, rank=r)
+        gc.set_option("owned_loop5", owned)
         for s in range(3):
             # hand each rank 1/n of the total so that the all-reduce restores the serial value exactly (powers of two)
             gc.set_force_torque(FTs[s][:gc.nParticles()] / n_ranks)
@@ -138,9 +141,11 @@ def test_loop5_replicated_equals_serial_oracle():
             for k in ("center", "theta", "v", "omega"):
                 assert np.array_equal(sg[k], ref[s][k]), k
         n = gc.nParticles()
+        assert gc.counter("loop5_cluster_steps") > 0
+        assert (gc.counter("loop5_owned_steps") > 0) == bool(owned)
         gc.close()
         return n
 
     ns = _run_ranks(n_ranks, rank)
-    assert ns[0] == ns[1] == oc.n_instances and ns[0] != 60
+    assert all(n == oc.n_instances for n in ns) and ns[0] != 60
     group.close()
