@@ -419,7 +419,7 @@ def main():
                 "stress_kernel_ms": tm["stress_ms"] / args.steps,
                 "stress_frac": (((56.0 * 4.0 / 3.0 * math.pi * (5 ** 3 - 3 ** 3) + 48.0) * n_inst * (local_updates / max(updates_per_step, 1.0))) / (tm["stress_ms"] / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tm["stress_ms"] > 0 else None}
     breakdown = {k: tm[k] / args.steps for k in ("update_ms", "forcing_ms", "stress_ms", "advance_ms")}
-    loop5 = {k: cloud.counter(k) for k in ("loop5_active_instances", "loop5_fallbacks", "loop5_cluster_steps", "loop5_block_substeps", "loop5_general_substeps", "loop5_owned_steps")}
+    loop5 = {k: cloud.counter(k) for k in ("loop5_active_instances", "loop5_fallbacks", "loop5_cluster_steps", "loop5_block_substeps", "loop5_general_substeps", "loop5_owned_steps", "loop5_cluster_flags")}
     gpu_launches = tm["n_kernel_launches"]
 
     # ---- e2e: host C-ABI calls with host arrays in OpenFOAM's layout, copies inside the timed region ----

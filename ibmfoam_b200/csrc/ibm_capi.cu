@@ -274,6 +274,7 @@ int ctx_update(ibm_ctx* c) {
     launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
     if (c->nInst > 0) launch_exclusive_scan_total(c->stream, c->sched, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    if (c->v7ok) { launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
     c->nLaunch += 9;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 20, c->dScal + 13, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -294,6 +295,7 @@ int ctx_update(ibm_ctx* c) {
     c->nInst = c->hScal[0];
     motion_invalidate_groups(c);
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    if (c->v7ok) { launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
     c->nLaunch += 6;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -333,7 +335,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     // clouds the staged kernel cannot take: ellipses, very large bodies) = the direct-gather kernel (ibm_kernels_v2.cu)
     const int fv = c->forcingVariant;
     if (fv >= 7 && c->v7ok)
-      launch_forcing_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
+      launch_forcing_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7prep, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F,
                         c->v7capF, c->dSlowList, c->dScal + 12, c->dScal + 13);
     else if (fv == 0)
       launch_forcing_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, dU, dUold, dS, dt, F);
@@ -360,7 +362,16 @@ static bool host_is_pinned(const void* p) {
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
-static const size_t kChunkBytes = (size_t)64 << 20;
+static size_t chunk_bytes() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("IBM_CHUNK_MB");  // developer switch
+    const int mb = e ? std::min(1024, std::max(1, std::atoi(e))) : 64;
+    v = (size_t)mb << 20;
+  }
+  return v;
+}
+#define kChunkBytes chunk_bytes()
 static int ensure_chunks(ibm_ctx* c) {
   if (c->hChunk[0]) return IBM_OK;
   for (int q = 0; q < 2; ++q) {
@@ -371,8 +382,8 @@ static int ensure_chunks(ibm_ctx* c) {
 }
 // a few persistent host threads that split one memcpy between them (one pool per process, started on first use)
 struct CopyPool {
-  static const int nT = 8;
-  std::thread th[nT];
+  int nT = 8;
+  std::thread th[32];
   std::mutex mu;
   std::condition_variable cvGo, cvDone;
   long generation = 0;
@@ -380,6 +391,9 @@ struct CopyPool {
   bool stop = false;
   char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
   CopyPool() {
+    // eight threads fill a pinned chunk at about the rate the bus empties it on the boxes measured; IBM_COPY_THREADS overrides
+    if (const char* e = getenv("IBM_COPY_THREADS")) nT = std::min(32, std::max(1, std::atoi(e)));
+    else nT = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
     for (int t = 0; t < nT; ++t) th[t] = std::thread([this, t] { work(t); });
   }
   ~CopyPool() {
@@ -499,7 +513,7 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   ctx_tic(c, T_STRESS);
   const int sv = c->stressVariant;
   if (sv >= 7 && c->v7ok)
-    launch_stress_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->v7capS,
+    launch_stress_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7prep, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->v7capS,
                      c->dSlowList, c->dScal + 12, c->dScal + 13);
   else if (sv == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
@@ -707,6 +721,7 @@ int ibm_set_particles(ibm_ctx* c, int n, const ibm_particle_init* init) {
   }
   c->cap = c->cfg.maxInstances > 0 ? std::max(c->cfg.maxInstances, n) : 2 * n + 64;
   IBM_CUDA(c, cudaMalloc(&c->dSlowList, (size_t)c->cap * sizeof(int)));
+  if (c->v7ok && v7_prep_alloc(c->v7prep, c->cap, std::max(c->v7capF.rowsCap, c->v7capS.rowsCap))) return ctx_fail(c, IBM_E_CUDA, "v7_prep_alloc failed");
   if ((rc = alloc_instances(c, c->in, c->cap))) return rc;
   if ((rc = alloc_instances(c, c->in2, c->cap))) return rc;
   if (schedule_alloc(c->sched, c->cap)) return ctx_fail(c, IBM_E_CUDA, "schedule_alloc failed");
@@ -750,6 +765,7 @@ int ibm_destroy(ibm_ctx* c) {
   motion_destroy(c);
   comm_destroy(c);
   schedule_free(c->sched);
+  v7_prep_free(c->v7prep);
   for (auto& p : c->events) { cudaEventDestroy(p.a); if (p.b) cudaEventDestroy(p.b); }
   for (auto e : c->eventPool) cudaEventDestroy(e);
   for (auto p : c->instAllocs) cudaFree(p);

@@ -85,6 +85,7 @@ struct ibm_ctx {
   int forcingVariant = 7, stressVariant = 7;
   bool v7ok = false;              // every shape class can take the seventh-generation kernels (no ellipse, tables + region fit)
   ibm::V7Caps v7capF{}, v7capS{};  // shared-memory capacities of their launches
+  ibm::V7Prep v7prep;             // launch records of the staged kernels (k7_prepare), rebuilt by every update
   int* dSlowList = nullptr;       // [cap] instances the staged kernel handed to the direct-gather kernel (device-side list)
   ibm::Schedule sched;
   int schedN = 0;          // instances the schedule's Morton order covers (set by ctx_update; 0 = no valid order)

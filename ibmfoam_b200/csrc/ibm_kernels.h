@@ -61,13 +61,32 @@ void launch_stress_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
 
 // ---- ibm_kernels_v7.cu: one CTA per instance, ball-row staging of combined fields, gathers from shared memory ----
 struct V7Caps { int planeCap, colCap, rowsCap, mapCap, nTcap, nkCap, elemCap; };  // shared-memory capacities of a launch (doubles / entries)
+// Per-instance launch records of the staged kernels, built once per update (k7_prepare) in SCHEDULE order, so that a CTA
+// finds everything its prologue needs - which instance, its box, the staged rows of the three reaches - with loads that
+// depend on nothing but blockIdx (one memory round trip instead of the chain order -> instance -> class -> box -> rows, and
+// no per-call recomputation of the region: the centres only change in solve(), which ends with an update)
+struct V7Hdr {
+  int b, cls, nShell, shellOff, flags;  // flags: 1 has local points, 2 the staged path applies (geometry), 4 box touches the lattice boundary
+  int j0, k0, by, bz, i0, bx;           // bounding box of the outer reach (Box7)
+  int nA, nB, nC, pad0, pad1;           // staged cells of the outer / surface / inner reach
+  double cx, cy, cz, pad2;
+};
+struct V7Prep {
+  V7Hdr* hdr = nullptr;       // [cap]
+  unsigned* rows = nullptr;   // [cap][rowsCap][3]: first column - i0 | (last column - i0) << 8 | offset of the row << 16; empty row: 0xff
+  int rowsCap = 0, cap = 0;
+};
 // capacities from the shape classes (HOST copies of the class records); false = the fast path does not apply to this cloud
 bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress);
+int v7_prep_alloc(V7Prep& p, int cap, int rowsCap);
+void v7_prep_free(V7Prep& p);
+void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, const V7Caps& capF, const V7Prep& prep);
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                       const Schedule& s, const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
                        const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard);
 void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
+                      const Schedule& s, const V7Prep& prep, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
                       const V7Caps& cap, int* slowList, int* slowCount, int* guard);
 // second-generation kernels over a device-side list of instances (the ones a staged kernel could not take)
 void launch_forcing_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,

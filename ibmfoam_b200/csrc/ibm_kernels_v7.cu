@@ -347,6 +347,126 @@ __device__ __forceinline__ bool box7_around(const LatticeDev& L, double cx, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// Launch records (V7Hdr + packed row tables), once per update
+// ------------------------------------------------------------------------------------------------
+#define V7_F_LOCAL 1
+#define V7_F_FITS 2
+#define V7_F_EDGE 4
+
+// 64 threads per instance: the kernel is a chain of dependent loads and barriers (latency, not work), so the point is to
+// have many instances in flight per SM (32 CTAs of two warps)
+#define K7P_NT 64
+#define K7P_ROWS 256
+__global__ void __launch_bounds__(K7P_NT)
+k7_prepare(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order, V7Caps cap,
+           V7Hdr* __restrict__ hdr, unsigned* __restrict__ rowsOut, int rowsCapG) {
+  __shared__ short lo0[3][K7P_ROWS], hi0[3][K7P_ROWS];  // own ranges, relative to the box
+  __shared__ short lo1[3][K7P_ROWS], hi1[3][K7P_ROWS];  // widened by the face neighbours
+  __shared__ int offs[3][K7P_ROWS];
+  __shared__ int laneTot[3][32];
+  if ((int)blockIdx.x >= nInst) return;
+  const int b = order[blockIdx.x];
+  const int cls = in.cls[b];
+  const ShapeClassDev sc = classes[cls];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  const double R = sc.d / 2.0;
+  const double rho[3] = {xadd(R, sc.delta), xadd(R, 0.0), xadd(R, -1 * sc.delta)};  // set 0 = outer reach ... set 2 = inner reach
+  Box7 B;
+  B.j0 = B.k0 = B.by = B.bz = B.i0 = B.bx = B.edge = 0;
+  bool fits = sc.kind != 2 && sc.nTheta <= cap.nTcap && sc.nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[0], B);
+  const int rows = B.by * B.bz;
+  if (fits) fits = rows <= rowsCapG && rows <= K7P_ROWS && B.bx <= 250;
+  int nS[3] = {0, 0, 0};
+  if (fits) {  // (block-uniform)
+    const double idx = 1.0 / L.dx;
+    for (int r = threadIdx.x; r < rows; r += K7P_NT) {
+      const int bk = r / B.by, bj = r - bk * B.by;
+      for (int s = 0; s < 3; ++s) {
+        int lo, hi;
+        own_range7(L, idx, cx, cy, cz, rho[s], B.j0 + bj, B.k0 + bk, lo, hi);
+        // (a range is only compared and widened by one: clamping it to the box's neighbourhood keeps it in 16 bits)
+        lo = max(lo, B.i0 - 2); hi = min(hi, B.i0 + B.bx + 1);
+        if (lo > hi) { lo = B.i0 + 1; hi = B.i0; }
+        lo0[s][r] = (short)(lo - B.i0); hi0[s][r] = (short)(hi - B.i0);
+      }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += K7P_NT) {
+      const int bk = r / B.by, bj = r - bk * B.by;
+      for (int s = 0; s < 3; ++s) {
+        const short* lo = lo0[s];
+        const short* hi = hi0[s];
+        int a = 0x7fff, e = -0x7fff;
+        if (lo[r] <= hi[r]) { a = lo[r] - 1; e = hi[r] + 1; }
+        if (bj + 1 < B.by && lo[r + 1] <= hi[r + 1]) { a = min(a, (int)lo[r + 1]); e = max(e, (int)hi[r + 1]); }
+        if (bj > 0 && lo[r - 1] <= hi[r - 1]) { a = min(a, (int)lo[r - 1]); e = max(e, (int)hi[r - 1]); }
+        if (bk + 1 < B.bz && lo[r + B.by] <= hi[r + B.by]) { a = min(a, (int)lo[r + B.by]); e = max(e, (int)hi[r + B.by]); }
+        if (bk > 0 && lo[r - B.by] <= hi[r - B.by]) { a = min(a, (int)lo[r - B.by]); e = max(e, (int)hi[r - B.by]); }
+        a = max(a, -B.i0); e = min(e, L.nx - 1 - B.i0);  // the lattice
+        if (a > e) { a = 1; e = 0; }
+        lo1[s][r] = (short)a; hi1[s][r] = (short)e;
+      }
+    }
+    __syncthreads();
+    // exclusive offsets of the rows, per set: warp 0, eight consecutive rows per lane
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x, r0 = lane * (K7P_ROWS / 32);
+      int tot[3] = {0, 0, 0};
+      for (int q = 0; q < K7P_ROWS / 32; ++q) {
+        const int r = r0 + q;
+        for (int s = 0; s < 3; ++s) {
+          if (r < rows) { offs[s][r] = tot[s]; tot[s] += max(hi1[s][r] - lo1[s][r] + 1, 0); }
+        }
+      }
+      for (int s = 0; s < 3; ++s) {
+        int incl = tot[s];
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        laneTot[s][lane] = incl - tot[s];
+        nS[s] = __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && nS[0] > 65535) nS[0] = -1;
+    for (int r = threadIdx.x; r < rows; r += K7P_NT) {
+      const int lane = r / (K7P_ROWS / 32);
+      for (int s = 0; s < 3; ++s) {
+        const int lo = lo1[s][r], hi = hi1[s][r];
+        unsigned w = 0xffu;  // empty: first > last
+        if (lo <= hi) w = (unsigned)lo | ((unsigned)hi << 8) | ((unsigned)((offs[s][r] + laneTot[s][lane]) & 0xffff) << 16);
+        rowsOut[((size_t)blockIdx.x * rowsCapG + r) * 3 + s] = w;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (fits && nS[0] < 0) fits = false;
+    V7Hdr h;
+    h.b = b; h.cls = cls; h.nShell = in.nShell[b]; h.shellOff = in.shellOff[b];
+    h.flags = (in.onLocal[b] != 0 ? V7_F_LOCAL : 0) | (fits ? V7_F_FITS : 0) | (B.edge ? V7_F_EDGE : 0);
+    h.j0 = B.j0; h.k0 = B.k0; h.by = B.by; h.bz = B.bz; h.i0 = B.i0; h.bx = B.bx;
+    h.nA = max(nS[0], 0); h.nB = nS[1]; h.nC = nS[2]; h.pad0 = 0; h.pad1 = 0;
+    h.cx = cx; h.cy = cy; h.cz = cz; h.pad2 = 0.0;
+    hdr[blockIdx.x] = h;
+  }
+}
+
+// row tables of a CTA from its packed record (sets first..last); rowG as build_region7 leaves it.  No barrier inside.
+__device__ __forceinline__ void load_region7(const LatticeDev& L, const Box7& B, const unsigned* __restrict__ packed, int first, int last, int rowsCap,
+                                             int* rowBase, int* rowLo, int* rowHi, int* rowG) {
+  const int r = threadIdx.x;
+  if (r < B.by * B.bz) {
+    for (int s = first; s <= last; ++s) {
+      const unsigned w = __ldg(packed + 3 * r + s);
+      const int lo = B.i0 + (int)(w & 0xffu), hi = B.i0 + (int)((w >> 8) & 0xffu);
+      rowLo[s * rowsCap + r] = lo;
+      rowHi[s * rowsCap + r] = hi;
+      rowBase[s * rowsCap + r] = (int)(w >> 16) - lo;
+    }
+    const int bk = r / B.by, bj = r - bk * B.by;
+    rowG[r] = L.nx * ((B.j0 + bj) + L.ny * (B.k0 + bk));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2/K3 v7: direct forcing, one CTA per instance
 // ------------------------------------------------------------------------------------------------
 struct Task7Ctx {
@@ -446,18 +566,17 @@ __device__ __forceinline__ int cells7(const Task7Ctx& X, const int* __restrict__
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const V7Hdr* __restrict__ hdrs,
+             const unsigned* __restrict__ rowsPacked, int rowsCapG,
              const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
              const double* __restrict__ Uold, const double* __restrict__ S, double dT, double* __restrict__ F, V7Caps cap,
              int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
   extern __shared__ double smem7[];
-  __shared__ int wsum[2 * (NT / 32)];
   if ((int)blockIdx.x >= nInst) return;
-  const int b = order[blockIdx.x];
-  const int nShell = in.nShell[b];
-  if (in.onLocal[b] == 0 || nShell <= 0) return;
-  const ShapeClassDev sc = classes[in.cls[b]];
-  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  const V7Hdr h = hdrs[blockIdx.x];
+  const int b = h.b;
+  const int nShell = h.nShell;
+  if (!(h.flags & V7_F_LOCAL) || nShell <= 0) return;
   const V7Layout lay = v7_layout(cap);
   char* base = (char*)smem7;
   double* planes = (double*)(base + lay.planes);
@@ -468,39 +587,34 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   int* rowG = rowHi + 3 * cap.rowsCap;
   unsigned short* elemRow = (unsigned short*)(base + lay.elemRow);
 
-  const int nT = sc.nTheta, nk = sc.nk;
-  const double R = sc.d / 2.0;
-  const double rL[3] = {xadd(R, -1 * sc.delta), xadd(R, 0.0), xadd(R, sc.delta)};  // R + delta[i]  (sphere.C:167,173)
-  const double rho[3] = {rL[2], rL[1], rL[0]};                                      // set 0 = outer reach ... set 2 = inner reach
   Box7 B;
-  bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[0], B);
-  if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= NT;
-  if (!fits) {
+  B.j0 = h.j0; B.k0 = h.k0; B.by = h.by; B.bz = h.bz; B.i0 = h.i0; B.bx = h.bx; B.edge = (h.flags & V7_F_EDGE) ? 1 : 0;
+  const int nA = h.nA, nB = h.nB, nC = h.nC;
+  if (!(h.flags & V7_F_FITS) || B.by * B.bz > cap.rowsCap || B.by * B.bz > NT || 3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap) {
     if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
     return;
   }
-  // the lines of the bounding rows on their way into L2 while the region tables are built (the staging loads then wait
-  // for an L2 hit instead of a DRAM access)
+  // the lines of the bounding rows on their way into L2 while the tables are unpacked (the staging loads then wait for an L2
+  // hit instead of a DRAM access)
   {
     const size_t C = (size_t)L.nCells;
     const int rows = B.by * B.bz;
     for (int r = threadIdx.x; r < 2 * rows; r += NT) {  // two 128-byte lines cover a row of up to 16 cells
-      const int row = r >> 1, bj = row % B.by, bk = row / B.by;
+      const int row = r >> 1, bk = row / B.by, bj = row - bk * B.by;
       const size_t g = (size_t)L.nx * ((size_t)(B.j0 + bj) + (size_t)L.ny * (size_t)(B.k0 + bk)) + (size_t)B.i0 + ((r & 1) ? (size_t)(B.bx - 1) : 0);
 #pragma unroll
       for (int q = 0; q < 3; ++q) { prefetch_l2(S + q * C + g); prefetch_l2(U + q * C + g); prefetch_l2(Uold + q * C + g); }
     }
   }
+  const ShapeClassDev sc = classes[h.cls];
+  const double cx = h.cx, cy = h.cy, cz = h.cz;
+  const int nT = sc.nTheta, nk = sc.nk;
+  const double R = sc.d / 2.0;
+  const double rL[3] = {xadd(R, -1 * sc.delta), xadd(R, 0.0), xadd(R, sc.delta)};  // R + delta[i]  (sphere.C:167,173)
   const V3 vp{in.v[0][b], in.v[1][b], in.v[2][b]}, omv{in.om[0][b], in.om[1][b], in.om[2][b]};
-  const int off = in.shellOff[b];
+  const int off = h.shellOff;
   const Tab7 tab = tab7_load(sc, tabD, cap);
-  int nS[3];
-  build_region7<NT>(L, B, cx, cy, cz, rho, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);  // (ends with a barrier)
-  const int nA = nS[0], nB = nS[1], nC = nS[2];
-  if (3 * (nA + nB + nC) > cap.planeCap || nA > cap.elemCap || nA > 65535) {
-    if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
-    return;
-  }
+  load_region7(L, B, rowsPacked + (size_t)blockIdx.x * rowsCapG * 3, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
   // elemRow: row of every element of set 0 (the staging loop runs over the elements of the widest set)
   if ((int)threadIdx.x < B.by * B.bz) {
     const int r = threadIdx.x;
@@ -568,9 +682,16 @@ template <bool EDGE, int NT, bool SOA>
 __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
   int guard = 0;
   const int nSurf = X.nT * X.nk;
+  // the index splits below by reciprocal multiplication (the integer divisions were a tenth of the kernel's instructions):
+  // exact for the 16-bit ranges they are used on - (n + 1/2)/d is at least 1/(2d) away from an integer, 6e-8 n/d of rounding is less
+  const bool small = nSurf <= 65535;
+  const float invNT = 1.0f / (float)X.nT;
   for (int s = threadIdx.x; s < nSurf; s += NT) {
-    const int i = s / X.nk, k = s - i * X.nk;
-    const int i2 = i + X.nT * k;
+    // s = index2(i,k) = i + nT k: the lanes of a warp walk along a circle of latitude, where neighbouring points are
+    // 2 pi R sin(phi) / nT apart - more of them share a cell (one shared-memory broadcast) than along a meridian
+    const int k = small ? (int)(((float)s + 0.5f) * invNT) : s / X.nT;
+    const int i = s - k * X.nT;
+    const int i2 = s;
     const V3 pt = tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, i, k);
     double g[7] = {0, 0, 0, 0, 0, 0, 0};
     double pp = 0.0;
@@ -583,7 +704,15 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
     }
     const double* tau = g + 1;
     // App. B #5: lever arm as coded, mesh_[index2(i,k)] read through index(i,j,k)
-    const int lay2 = i2 % 3, j2 = (i2 / 3) % X.nT, k2 = i2 / (3 * X.nT);
+    int lay2, j2, k2;
+    if (small) {
+      const int q3 = (int)(((unsigned)i2 * 43691u) >> 17);  // i2 / 3 for i2 < 2^16
+      lay2 = i2 - 3 * q3;
+      k2 = (int)(((float)q3 + 0.5f) * invNT);
+      j2 = q3 - k2 * X.nT;
+    } else {
+      lay2 = i2 % 3; j2 = (i2 / 3) % X.nT; k2 = i2 / (3 * X.nT);
+    }
     const double r2 = xadd(X.R, lay2 == 0 ? -1 * X.delta : (lay2 == 1 ? 0.0 : X.delta));
     const V3 m2 = tab7_point(X.kind, X.tab, r2, X.cx, X.cy, X.cz, j2, k2);
     const double Rx = m2.x - X.cx, Ry = m2.y - X.cy, Rz = m2.z - X.cz;
@@ -615,17 +744,16 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
 
 template <int NT, int MINB, bool SOA>
 __global__ void __launch_bounds__(NT, MINB)
-k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const int* __restrict__ order,
+k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const V7Hdr* __restrict__ hdrs,
+            const unsigned* __restrict__ rowsPacked, int rowsCapG,
             const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
             V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
   extern __shared__ double smem7[];
-  __shared__ int wsum[2 * (NT / 32)];
   __shared__ double red[NT / 32][9];
   if ((int)blockIdx.x >= nInst) return;
-  const int b = order[blockIdx.x];
-  const ShapeClassDev sc = classes[in.cls[b]];
-  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
-  const bool on = in.onLocal[b] != 0;
+  const V7Hdr h = hdrs[blockIdx.x];
+  const int b = h.b;
+  const bool on = (h.flags & V7_F_LOCAL) != 0;
   const V7Layout lay = v7_layout(cap);
   char* base = (char*)smem7;
   double* planes = (double*)(base + lay.planes);
@@ -635,20 +763,16 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
   int* rowHi = rowLo + 3 * cap.rowsCap;
   int* rowG = rowHi + 3 * cap.rowsCap;
   unsigned short* elemRow = (unsigned short*)(base + lay.elemRow);
-  const int nT = sc.nTheta, nk = sc.nk;
-  const double R = sc.d / 2.0;
-  const double rho[3] = {0.0, xadd(R, 0.0), 0.0};
+  // the box of the OUTER reach (the launch record is shared with the forcing kernel): the rows beyond the surface reach are
+  // empty in set 1
   Box7 B;
-  B.by = B.bz = 0;
+  B.j0 = h.j0; B.k0 = h.k0; B.by = h.by; B.bz = h.bz; B.i0 = h.i0; B.bx = h.bx; B.edge = (h.flags & V7_F_EDGE) ? 1 : 0;
+  const int nB = h.nB;
   // Instances without local points (other slabs' instances on a multi-GPU run) do no work but MUST still write zero
   // partials below: their F/T slots hold last step's combined totals, and the cross-rank sum adds whatever is in them.
-  if (on) {
-    bool fits = sc.kind != 2 && nT <= cap.nTcap && nk <= cap.nkCap && box7_around(L, cx, cy, cz, rho[1], B);
-    if (fits) fits = B.by * B.bz <= cap.rowsCap && B.by * B.bz <= NT;
-    if (!fits) {
-      if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
-      return;  // the list kernel writes this instance's F/T
-    }
+  if (on && (!(h.flags & V7_F_FITS) || B.by * B.bz > cap.rowsCap || B.by * B.bz > NT || 7 * nB > cap.planeCap || nB > cap.elemCap)) {
+    if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
+    return;  // the list kernel writes this instance's F/T
   }
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (on) {
@@ -656,22 +780,24 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
       const size_t C = (size_t)L.nCells;
       const int rows = B.by * B.bz;
       for (int r = threadIdx.x; r < 2 * rows; r += NT) {
-        const int row = r >> 1, bj = row % B.by, bk = row / B.by;
+        const int row = r >> 1, bk = row / B.by, bj = row - bk * B.by;
         const size_t g = (size_t)L.nx * ((size_t)(B.j0 + bj) + (size_t)L.ny * (size_t)(B.k0 + bk)) + (size_t)B.i0 + ((r & 1) ? (size_t)(B.bx - 1) : 0);
         prefetch_l2(P + g);
 #pragma unroll
         for (int q = 0; q < 6; ++q) prefetch_l2(Tau + q * C + g);
       }
     }
+    const ShapeClassDev sc = classes[h.cls];
+    const double cx = h.cx, cy = h.cy, cz = h.cz;
+    const int nT = sc.nTheta, nk = sc.nk;
+    const double R = sc.d / 2.0;
+    const double rhoS = xadd(R, 0.0);
+    double rot9[9];  // (asked for early: the answer is back long before the points need it)
+#pragma unroll
+    for (int q = 0; q < 9; ++q) rot9[q] = __ldg(in.rot + 9 * (size_t)b + q);
     const Tab7 tab = tab7_load(sc, tabD, cap);
-    int nS[3];
-    build_region7<NT>(L, B, cx, cy, cz, rho, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG, wsum, nS);
-    const int nB = nS[1];
+    load_region7(L, B, rowsPacked + (size_t)blockIdx.x * rowsCapG * 3, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
     const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
-    if (7 * nB > cap.planeCap || nB > cap.elemCap || nB > 65535) {
-      if (threadIdx.x == 0) slowList[atomicAdd(slowCount, 1)] = b;
-      return;
-    }
     if ((int)threadIdx.x < B.by * B.bz) {
       const int r = threadIdx.x;
       const int lo = loB[r], hi = hiB[r], o = baseB[r] + lo;
@@ -695,10 +821,10 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
     Str7Ctx X;
     X.G = geo7(L); X.B = B; X.tab = tab;
     X.baseB = baseB; X.loB = loB; X.hiB = hiB; X.planes = planes;
-    X.cx = cx; X.cy = cy; X.cz = cz; X.R = R; X.delta = sc.delta; X.rS = rho[1]; X.pRefOverRho = pRefOverRho; X.rhoRef = rhoRef;
+    X.cx = cx; X.cy = cy; X.cz = cz; X.R = R; X.delta = sc.delta; X.rS = rhoS; X.pRefOverRho = pRefOverRho; X.rhoRef = rhoRef;
     X.sfScale = (sc.kind == 0) ? (R * R) * sc.dTheta : R * sc.dTheta * sc.l;
 #pragma unroll
-    for (int q = 0; q < 9; ++q) X.rot[q] = in.rot[9 * (size_t)b + q];
+    for (int q = 0; q < 9; ++q) X.rot[q] = rot9[q];
     X.kind = sc.kind; X.nT = nT; X.nk = nk; X.nB = nB;
     const int bad = B.edge ? stress_points7<true, NT, SOA>(X, acc) : stress_points7<false, NT, SOA>(X, acc);
     if (bad) atomicExch(guardFlag, 1);
@@ -798,6 +924,7 @@ bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses
     any = true;
   }
   s.colCap = 0; s.mapCap = 0;
+  s.rowsCap = std::max(s.rowsCap, f.rowsCap);  // the launch records carry the box of the OUTER reach for both kernels
   if (!any) return false;
   if (v7_layout(f).total > SMEM_BUDGET_F || v7_layout(s).total > SMEM_BUDGET_S) return false;
   if (f.elemCap > 65535 || s.elemCap > 65535) return false;
@@ -815,9 +942,28 @@ static int v7_threads() {
   return nt;
 }
 
+int v7_prep_alloc(V7Prep& p, int cap, int rowsCap) {
+  v7_prep_free(p);
+  if (cap <= 0 || rowsCap <= 0) return 0;
+  if (cudaMalloc(&p.hdr, (size_t)cap * sizeof(V7Hdr)) != cudaSuccess) return 1;
+  if (cudaMalloc(&p.rows, (size_t)cap * rowsCap * 3 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p.hdr); p.hdr = nullptr; return 1; }
+  p.cap = cap; p.rowsCap = rowsCap;
+  return 0;
+}
+void v7_prep_free(V7Prep& p) {
+  if (p.hdr) cudaFree(p.hdr);
+  if (p.rows) cudaFree(p.rows);
+  p = V7Prep{};
+}
+void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                       const Schedule& s, const V7Caps& capF, const V7Prep& prep) {
+  if (nInst <= 0) return;
+  k7_prepare<<<nInst, K7P_NT, 0, st>>>(L, classes, in, nInst, s.order, capF, prep.hdr, prep.rows, prep.rowsCap);
+}
+
 template <int NT, int MINB>
 static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                          const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
+                          const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
                           double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard, int sm) {
   static PerDeviceOnce attr;
   static int attrBytes = 0;
@@ -825,10 +971,10 @@ static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClass
     cudaFuncSetAttribute(k_forcing_v7<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
+  k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, prep.hdr, prep.rows, prep.rowsCap, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
 }
 template <int NT, int MINB, bool SOA>
-static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const Schedule& s,
+static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const V7Prep& prep,
                          const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, const V7Caps& cap, int* slowList,
                          int* slowCount, int* guard, int sm) {
   static PerDeviceOnce attr;
@@ -837,40 +983,41 @@ static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassD
     cudaFuncSetAttribute(k_stress_v7<NT, MINB, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_stress_v7<NT, MINB, SOA><<<nInst, NT, sm, st>>>(L, classes, in, nInst, s.order, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
+  k_stress_v7<NT, MINB, SOA><<<nInst, NT, sm, st>>>(L, classes, in, nInst, prep.hdr, prep.rows, prep.rowsCap, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
 }
 
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                       const Schedule& s, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
+                       const Schedule& s, const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
                        const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
   if (nInst <= 0) return;
+  (void)s;
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
   // resident CTAs per SM follow from the staged planes (a d = 8 cells sphere: 71 KB -> three); the register bound goes with it
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
-  if (nt == 320) forcing_v7_nt<320, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-  else if (nt == 192) { if (three) forcing_v7_nt<192, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-                        else forcing_v7_nt<192, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
-  else if (nt == 224) { if (three) forcing_v7_nt<224, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-                        else forcing_v7_nt<224, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
-  else { if (three) forcing_v7_nt<256, 3>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm);
-         else forcing_v7_nt<256, 2>(st, L, classes, in, nInst, s, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm); }
+#define IBM_F7(NT_, MB_) forcing_v7_nt<NT_, MB_>(st, L, classes, in, nInst, prep, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm)
+  if (nt == 320) IBM_F7(320, 2);
+  else if (nt == 192) { if (three) IBM_F7(192, 3); else IBM_F7(192, 2); }
+  else if (nt == 224) { if (three) IBM_F7(224, 3); else IBM_F7(224, 2); }
+  else { if (three) IBM_F7(256, 3); else IBM_F7(256, 2); }
+#undef IBM_F7
   launch_forcing_v2_list(st, L, classes, in, slowList, slowCount, shellCell, shellJK, U, Uold, S, dT, F);
 }
 
 void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                      const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
+                      const Schedule& s, const V7Prep& prep, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
                       const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
   if (nInst <= 0) return;
+  (void)s;
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
   const int nt = v7_threads();
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
   static int soa = -1;
   if (soa < 0) { const char* e = getenv("IBM_V7_STRESS_SOA"); soa = e ? atoi(e) : 0; }
-#define IBM_S7(NT_, MB_) do { if (soa) stress_v7_nt<NT_, MB_, true>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); \
-                              else stress_v7_nt<NT_, MB_, false>(st, L, classes, in, nInst, s, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); } while (0)
+#define IBM_S7(NT_, MB_) do { if (soa) stress_v7_nt<NT_, MB_, true>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); \
+                              else stress_v7_nt<NT_, MB_, false>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); } while (0)
   if (nt == 320) IBM_S7(320, 2);
   else if (nt == 192) { if (three) IBM_S7(192, 3); else IBM_S7(192, 2); }
   else if (nt == 224) { if (three) IBM_S7(224, 3); else IBM_S7(224, 2); }

@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 
@@ -1748,7 +1749,10 @@ k5c_run(MotionDev m, LatticeDev L, InstanceSoA in, const ShapeClassDev* __restri
   const int beg = m.ctaBegin[b], end = m.ctaEnd[b];
   if (end <= beg) return;
   if (*m.clusterFail) return;
-  if (m.owned && owner_of(m, m.c0[2 * (size_t)m.cap + m.sorted[beg]]) != m.rank) return;  // a block belongs to the owner of its first member
+  // a block belongs to the owner of the root (smallest instance) of its first component: the components sit at offsets that
+  // follow from the labels alone, whereas the order of the members inside one is that of an atomic counter and differs
+  // from rank to rank
+  if (m.owned && owner_of(m, m.c0[2 * (size_t)m.cap + m.label[m.sorted[beg]]]) != m.rank) return;
   const int tid = threadIdx.x;
   if (end - beg > K5C_CAP) { if (tid == 0) atomicExch(m.clusterFail, 1); return; }
   if (tid == 0) {
@@ -2882,6 +2886,13 @@ static int owned_exchange(ibm_ctx* c, int n0) {
   int rc = comm_allreduce_sum(c, M->dX, words, 2);
   if (rc) return rc;
   k5x_unpack<<<blocks_for(threads), 128, 0, c->stream>>>(d, c->in, n0, M->dX);
+  if (getenv("IBM_DEBUG_OWNED")) {  // developer switch: the summed header of the exchange
+    long long hx[K5X_HEAD];
+    cudaMemcpyAsync(hx, M->dX, sizeof(hx), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    fprintf(stderr, "[owned rank %d] n0 %d words %zu total %lld fail %lld violated %lld overflow %lld counts %lld %lld %lld %lld slabs %d %d %d\n", d.rank, n0, words,
+            hx[0], hx[1], hx[2], hx[3], hx[8], hx[9], hx[10], hx[11], d.slabK0[0], d.slabK0[1], d.slabK0[2]);
+  }
   c->nLaunch += 2;
   M->nOwnedSteps++;
   return IBM_OK;

@@ -99,8 +99,9 @@ def main():
         a, b = ocs.state_arrays(), gcs.state_arrays()
         for k in ("index", "copy", "active", "onMesh", "center", "theta", "v", "omega"):
             assert np.array_equal(a[k], b[k]), (k, s)
-        stage(f"step {s} equal")
+        stage(f"step {s} equal; owned steps {gcs.counter('loop5_owned_steps')}, fallbacks {gcs.counter('loop5_fallbacks')}, flags {gcs.counter('loop5_cluster_flags')}")
     assert ocs.n_instances != 60
+    assert gcs.counter("loop5_fallbacks") == 0
     assert gcs.counter("loop5_owned_steps") > 0  # every rank advanced what its slab owns; states and copies came over NCCL
     gcs.close()
     dist.barrier()

@@ -127,6 +127,14 @@ def test_loop5_replicated_equals_serial_oracle(n_ranks, owned):
         oc.advance(case.dt)
         ref.append(oc.state_arrays())
 
+    g1 = ParticleCloud(case)  # one GPU, for the number of fallbacks of the split on this case
+    for s in range(3):
+        g1.set_force_torque(FTs[s][:g1.nParticles()])
+        g1.combineForces()
+        g1.advance(case.dt)
+    fallbacks_serial = g1.counter("loop5_fallbacks")
+    g1.close()
+
     def rank(r):
         gc = ParticleCloud(case, slab=ranges[r], local_group=group.handle, rank=r)
         gc.set_option("owned_loop5", owned)
@@ -143,6 +151,7 @@ def test_loop5_replicated_equals_serial_oracle(n_ranks, owned):
         n = gc.nParticles()
         assert gc.counter("loop5_cluster_steps") > 0
         assert (gc.counter("loop5_owned_steps") > 0) == bool(owned)
+        assert gc.counter("loop5_fallbacks") == fallbacks_serial, "the ranks must not fall back where one GPU does not"
         gc.close()
         return n
 

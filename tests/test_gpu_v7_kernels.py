@@ -35,8 +35,10 @@ def _check(case, gc, oc, f, expect_slow=None):
     FTo = oc.integrate_stress(f["p"], f["tau"])
     FTg = gc.integrateSurfaceStresses(f["p"], f["tau"])
     assert np.max(np.abs(FTg - FTo)) < 1e-10 * np.max(np.abs(FTo))
+    slow_s = gc.counter("v7_slow_count")
     if expect_slow is not None:
         assert (slow_f > 0) == expect_slow, slow_f
+        assert (slow_s > 0) == expect_slow, slow_s  # the stress kernel takes the same instances the same way
     return slow_f
 
 
