@@ -472,7 +472,7 @@ def main():
                "h2d_ms_per_step": tm2["h2d_ms"] / args.e2e_steps, "d2h_ms_per_step": tm2["d2h_ms"] / args.e2e_steps,
                "layout_ms_per_step": tm2["layout_ms"] / args.e2e_steps,
                "host_buffers": {"U, U.oldTime, p": "registered once with ibm_host_register (cudaHostRegister): direct DMA",
-                                "S, devRhoReff, F": "pageable numpy arrays: staged through the library's two pinned 64 MB chunks by 8 host threads",
+                                "S, devRhoReff, F": "pageable numpy arrays: staged through the library's two pinned 64 MB chunks by up to 16 host threads (one per core)",
                                 "h2d_direct_bytes_per_step": pinned_b // args.e2e_steps, "h2d_staged_bytes_per_step": staged_b // args.e2e_steps}}
 
     cpu = None

@@ -46,6 +46,48 @@ static void resolve_events(ibm_ctx* c) {
   }
   c->events.clear();
 }
+static void marks_resolve(ibm_ctx* c) {
+  if (c->dbgMarks.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  auto add = [](std::vector<std::pair<std::string, std::vector<float>>>& acc, const std::string& k, double v) {
+    for (auto& e : acc) if (e.first == k) { e.second.push_back((float)v); return; }
+    acc.push_back({k, {(float)v}});
+  };
+  for (size_t i = 1; i < c->dbgMarks.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->dbgMarks[i - 1].second, c->dbgMarks[i].second);
+    const std::string k = std::string(c->dbgMarks[i - 1].first) + " -> " + c->dbgMarks[i].first;
+    add(c->dbgAcc, k, ms);
+    add(c->dbgAccHost, k, (c->dbgHost[i] - c->dbgHost[i - 1]) * 1e3);
+  }
+  for (auto& m : c->dbgMarks) cudaEventDestroy(m.second);
+  c->dbgMarks.clear(); c->dbgHost.clear();
+}
+void ctx_mark(ibm_ctx* c, const char* label) {
+  if (!c->dbgTiming) return;
+  if (c->dbgMarks.size() >= 512) marks_resolve(c);
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, c->stream);
+  c->dbgMarks.push_back({label, e});
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  c->dbgHost.push_back(ts.tv_sec + 1e-9 * ts.tv_nsec);
+}
+void ctx_marks_report(ibm_ctx* c) {
+  if (!c->dbgTiming) return;
+  marks_resolve(c);
+  int rank = comm_rank(c);
+  auto median = [](std::vector<float> v) { std::sort(v.begin(), v.end()); return v.empty() ? 0.0f : v[v.size() / 2]; };
+  for (size_t i = 0; i < c->dbgAcc.size(); ++i)
+    fprintf(stderr, "[timing rank %d] %-44s median: device %8.3f ms  host %8.3f ms  (n=%zu)\n", rank, c->dbgAcc[i].first.c_str(),
+            median(c->dbgAcc[i].second), median(c->dbgAccHost[i].second), c->dbgAcc[i].second.size());
+  for (int q = 2; q <= 8; ++q) {
+    long long v = 0;
+    char name[32];
+    snprintf(name, sizeof(name), "loop5_stat%d", q);
+    if (motion_counter(c, name, &v)) fprintf(stderr, "[timing rank %d] %s = %lld\n", rank, name, v);
+  }
+}
 void ctx_tic(ibm_ctx* c, int cat) {
   if (c->events.size() >= 2048) resolve_events(c);
   EventPair p{get_event(c), nullptr, cat};
@@ -259,7 +301,9 @@ int ctx_update(ibm_ctx* c) {
   for (int attempt = 0; attempt < 8; ++attempt) {
     IBM_CUDA(c, cudaMemsetAsync(c->dScal, 0, 8 * sizeof(int), c->stream));
     // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
+    ctx_mark(c, "update:begin");
     launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant);
+    ctx_mark(c, "update:marked");
     if (comm_ranks(c) > 1 && c->nInst > 0) {
       // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs.  The shell
       // overflow flag of this rank travels in the slot behind the last instance, so that every rank sees an overflow
@@ -270,15 +314,19 @@ int ctx_update(ibm_ctx* c) {
       launch_copy_int(c->stream, c->dScal + 4, c->in.nPtsOnMesh + c->nInst);
       c->nLaunch += 2;
     }
+    ctx_mark(c, "update:counts summed");
     launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
     launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
     if (c->nInst > 0) launch_exclusive_scan_total(c->stream, c->sched, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    ctx_mark(c, "update:scheduled");
     if (c->v7ok) { launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
+    ctx_mark(c, "update:prepared");
     c->nLaunch += 9;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 20, c->dScal + 13, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    ctx_mark(c, "update:synced");
     if (c->hScal[20]) return ctx_fail(c, IBM_E_STATE, "staged kernel: a gather stencil left the staged region (internal error)");
     if (!c->hScal[4]) break;
     // shell buffer too small (every rank takes the same path only if it overflows itself: the collective above is
@@ -330,6 +378,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
     IBM_CUDA(c, cudaMemsetAsync(F, 0, 3 * C * sizeof(double), c->stream));
   }
   if (c->cfg.coupled) {  // particleCloud.C:1186-1189
+    ctx_mark(c, "forcing:begin");
     ctx_tic(c, T_FORCING);
     // 7 = staged kernel (ibm_kernels_v7.cu) where every shape class fits it, 0 = reference-order yardstick, anything else (and
     // clouds the staged kernel cannot take: ellipses, very large bodies) = the direct-gather kernel (ibm_kernels_v2.cu)
@@ -344,6 +393,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
                         dS, dt, F);
     c->nLaunch++;
     ctx_toc(c);
+    ctx_mark(c, "forcing:end");
     if (!dFext) c->fLive = true;
     c->nForcingCalls++;
     c->nUpdates += c->updatesPerCall;
@@ -355,7 +405,7 @@ static int forcing_on_device(ibm_ctx* c, const double* dU, const double* dUold, 
 // ---- host <-> device transfers of caller-owned arrays ------------------------------------------------------------
 // OpenFOAM's field storage is ordinary (pageable) memory unless the caller registered it (ibm_host_register, which the shim
 // does for the fields that persist across time steps: U, U.oldTime(), p).  A registered / pinned array is copied directly by
-// the DMA engine; a pageable one goes through two library-owned pinned 64 MB chunks, filled by eight host threads while the
+// the DMA engine; a pageable one goes through two library-owned pinned 64 MB chunks, filled by up to sixteen host threads (one per core) while the
 // previous chunk is on the bus (cudaMemcpyAsync on pageable memory is a synchronous staged copy at a fraction of the rate).
 static bool host_is_pinned(const void* p) {
   cudaPointerAttributes a{};
@@ -391,9 +441,10 @@ struct CopyPool {
   bool stop = false;
   char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
   CopyPool() {
-    // eight threads fill a pinned chunk at about the rate the bus empties it on the boxes measured; IBM_COPY_THREADS overrides
+    // measured on the 16-core host of a B200 box (gpurun_out/r2t, 17.2 GB up + 3.2 GB down per step): 4 threads 580 ms per
+    // end-to-end step, 8: 528, 16: 453 (49 GB/s on a 55 GB/s link); 16 MB chunks or 256 MB chunks are no better than 64 MB
     if (const char* e = getenv("IBM_COPY_THREADS")) nT = std::min(32, std::max(1, std::atoi(e)));
-    else nT = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    else nT = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     for (int t = 0; t < nT; ++t) th[t] = std::thread([this, t] { work(t); });
   }
   ~CopyPool() {
@@ -573,6 +624,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   if (const char* e = getenv("IBM_ACTIVE_LOOP5")) c->activeLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_CLUSTER_LOOP5")) c->clusterLoop5 = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_OWNED_LOOP5")) c->ownedLoop5 = std::atoi(e) != 0;
+  if (const char* e = getenv("IBM_DEBUG_TIMING")) c->dbgTiming = std::atoi(e) != 0;
   if (const char* e = getenv("IBM_MARK_VARIANT")) c->markVariant = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("IBM_KERNEL_VARIANT")) {  // "f,s": forcing / stress kernel generation (like ibm_set_kernel_variant)
     int f = 0, s2 = 0;
@@ -762,6 +814,7 @@ int ibm_destroy(ibm_ctx* c) {
   if (!c) return IBM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  ctx_marks_report(c);
   motion_destroy(c);
   comm_destroy(c);
   schedule_free(c->sched);
@@ -882,12 +935,18 @@ int ibm_solve(ibm_ctx* c, const double* p, const double* tau6, double dt, ibm_so
 int ibm_solve_device(ibm_ctx* c, const double* dP, const double* dTau6, double dt, ibm_solve_stats* stats) {
   if (!c) return IBM_E_ARG;
   cudaSetDevice(c->device);
+  ctx_mark(c, "solve:begin");
   int rc = motion_prepare_async(c, dt);
   if (rc) return rc;
   clear_F_on_side(c);
+  ctx_mark(c, "solve:prepared");
   if ((rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr))) return rc;
+  ctx_mark(c, "solve:stress done");
   if ((rc = combine_forces(c))) return rc;
-  return motion_advance(c, dt, stats);
+  ctx_mark(c, "solve:combined");
+  rc = motion_advance(c, dt, stats);
+  ctx_mark(c, "solve:end");
+  return rc;
 }
 
 int ibm_n_instances(ibm_ctx* c, int* n) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ibmfoam_b200.h"
@@ -113,6 +114,11 @@ struct ibm_ctx {
   // comm
   void* comm = nullptr;
 
+  // developer timeline (IBM_DEBUG_TIMING=1): named marks on the stream, mean interval between consecutive marks printed at destroy
+  bool dbgTiming = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> dbgMarks;
+  std::vector<double> dbgHost;
+  std::vector<std::pair<std::string, std::vector<float>>> dbgAcc, dbgAccHost;  // samples per "A -> B"
   std::vector<ibm::EventPair> events;
   std::vector<cudaEvent_t> eventPool;
   double accMs[ibm::T_NCAT] = {0, 0, 0, 0, 0, 0, 0};
@@ -122,6 +128,8 @@ struct ibm_ctx {
 namespace ibm {
 int ctx_fail(ibm_ctx* c, int code, const std::string& msg);
 bool ctx_cuda_ok(ibm_ctx* c, cudaError_t e, const char* what);
+void ctx_mark(ibm_ctx* c, const char* label);   // no-op unless IBM_DEBUG_TIMING is set
+void ctx_marks_report(ibm_ctx* c);
 void ctx_tic(ibm_ctx* c, int cat);
 void ctx_toc(ibm_ctx* c);
 int ctx_ensure_stage(ibm_ctx* c, size_t doubles);

@@ -367,6 +367,16 @@ k7_prepare(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA 
   if ((int)blockIdx.x >= nInst) return;
   const int b = order[blockIdx.x];
   const int cls = in.cls[b];
+  const int local = in.onLocal[b];
+  if (local == 0) {  // no point on this rank's slab (other ranks' instances on a multi-GPU run): the kernels only need to know that
+    if (threadIdx.x == 0) {
+      V7Hdr h{};
+      h.b = b; h.cls = cls; h.nShell = in.nShell[b]; h.shellOff = in.shellOff[b];
+      h.cx = in.c[0][b]; h.cy = in.c[1][b]; h.cz = in.c[2][b];
+      hdr[blockIdx.x] = h;
+    }
+    return;
+  }
   const ShapeClassDev sc = classes[cls];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   const double R = sc.d / 2.0;
@@ -441,7 +451,7 @@ k7_prepare(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA 
     if (fits && nS[0] < 0) fits = false;
     V7Hdr h;
     h.b = b; h.cls = cls; h.nShell = in.nShell[b]; h.shellOff = in.shellOff[b];
-    h.flags = (in.onLocal[b] != 0 ? V7_F_LOCAL : 0) | (fits ? V7_F_FITS : 0) | (B.edge ? V7_F_EDGE : 0);
+    h.flags = V7_F_LOCAL | (fits ? V7_F_FITS : 0) | (B.edge ? V7_F_EDGE : 0);
     h.j0 = B.j0; h.k0 = B.k0; h.by = B.by; h.bz = B.bz; h.i0 = B.i0; h.bx = B.bx;
     h.nA = max(nS[0], 0); h.nB = nS[1]; h.nC = nS[2]; h.pad0 = 0; h.pad1 = 0;
     h.cx = cx; h.cy = cy; h.cz = cz; h.pad2 = 0.0;
@@ -684,14 +694,26 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
   const int nSurf = X.nT * X.nk;
   // the index splits below by reciprocal multiplication (the integer divisions were a tenth of the kernel's instructions):
   // exact for the 16-bit ranges they are used on - (n + 1/2)/d is at least 1/(2d) away from an integer, 6e-8 n/d of rounding is less
-  const bool small = nSurf <= 65535;
-  const float invNT = 1.0f / (float)X.nT;
+  const bool small = nSurf <= 32767;
+  const float invNT = 1.0f / (float)X.nT, inv2NT = 0.5f / (float)X.nT;
+  // Order of the points: two circles of latitude at a time, alternating between them, so that the 16 lanes of a half-warp
+  // hold an 8 x 2 patch of the polar grid.  Neighbouring points are about half a cell apart: such a patch lies in 2-4 cells,
+  // lanes in the same cell read the same shared-memory words (one broadcast), and the bank conflicts between the few distinct
+  // cells that remain are rare - 1.1 wavefronts per half-warp load against 2.0 for a walk along a meridian (measured: the
+  // gather of the first version was 761 M wavefronts for 333 M loads and the kernel was bound by them).
+  // (an odd last circle goes alone at the end: no empty slots - 1250 points of a d = 8 sphere are five rounds of 256 threads,
+  // 1300 slots would be six)
+  const int nPaired = 2 * X.nT * (X.nk >> 1);
   for (int s = threadIdx.x; s < nSurf; s += NT) {
-    // s = index2(i,k) = i + nT k: the lanes of a warp walk along a circle of latitude, where neighbouring points are
-    // 2 pi R sin(phi) / nT apart - more of them share a cell (one shared-memory broadcast) than along a meridian
-    const int k = small ? (int)(((float)s + 0.5f) * invNT) : s / X.nT;
-    const int i = s - k * X.nT;
-    const int i2 = s;
+    int i, k;
+    if (s < nPaired) {
+      const int kp = small ? (int)(((float)s + 0.5f) * inv2NT) : s / (2 * X.nT);
+      const int rem = s - kp * 2 * X.nT;
+      i = rem >> 1; k = 2 * kp + (rem & 1);
+    } else {
+      i = s - nPaired; k = X.nk - 1;
+    }
+    const int i2 = i + X.nT * k;
     const V3 pt = tab7_point(X.kind, X.tab, X.rS, X.cx, X.cy, X.cz, i, k);
     double g[7] = {0, 0, 0, 0, 0, 0, 0};
     double pp = 0.0;
@@ -932,14 +954,18 @@ bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses
   return true;
 }
 
-static int v7_threads() {
-  static int nt = -1;
-  if (nt < 0) {
+static int v7_threads(bool stress) {  // developer switches: IBM_V7_THREADS (both kernels), IBM_V7_THREADS_F / _S (one of them)
+  static int nt[2] = {-1, -1};
+  if (nt[0] < 0) {
     const char* e = getenv("IBM_V7_THREADS");
-    nt = e ? atoi(e) : 256;
-    if (nt != 256 && nt != 320 && nt != 192 && nt != 224) nt = 256;
+    const char* ef = getenv("IBM_V7_THREADS_F");
+    const char* es = getenv("IBM_V7_THREADS_S");
+    nt[0] = ef ? atoi(ef) : (e ? atoi(e) : 256);
+    nt[1] = es ? atoi(es) : (e ? atoi(e) : 256);
+    for (int q = 0; q < 2; ++q)
+      if (nt[q] != 256 && nt[q] != 320 && nt[q] != 192 && nt[q] != 224) nt[q] = 256;
   }
-  return nt;
+  return nt[stress ? 1 : 0];
 }
 
 int v7_prep_alloc(V7Prep& p, int cap, int rowsCap) {
@@ -993,7 +1019,7 @@ void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
   (void)s;
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
-  const int nt = v7_threads();
+  const int nt = v7_threads(false);
   // resident CTAs per SM follow from the staged planes (a d = 8 cells sphere: 71 KB -> three); the register bound goes with it
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
 #define IBM_F7(NT_, MB_) forcing_v7_nt<NT_, MB_>(st, L, classes, in, nInst, prep, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard, sm)
@@ -1012,7 +1038,7 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
   (void)s;
   const int sm = v7_layout(cap).total;
   cudaMemsetAsync(slowCount, 0, sizeof(int), st);
-  const int nt = v7_threads();
+  const int nt = v7_threads(true);
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
   static int soa = -1;
   if (soa < 0) { const char* e = getenv("IBM_V7_STRESS_SOA"); soa = e ? atoi(e) : 0; }

@@ -2883,8 +2883,10 @@ static int owned_exchange(ibm_ctx* c, int n0) {
   }
   const int threads = n0 + d.nRanks * K5X_Q + K5X_HEAD;
   k5x_pack<<<blocks_for(threads), 128, 0, c->stream>>>(d, c->in, n0, M->dX);
+  ctx_mark(c, "advance:packed");
   int rc = comm_allreduce_sum(c, M->dX, words, 2);
   if (rc) return rc;
+  ctx_mark(c, "advance:all-reduced");
   k5x_unpack<<<blocks_for(threads), 128, 0, c->stream>>>(d, c->in, n0, M->dX);
   if (getenv("IBM_DEBUG_OWNED")) {  // developer switch: the summed header of the exchange
     long long hx[K5X_HEAD];
@@ -2992,8 +2994,11 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       else cluster_prepare(c, dt);
       if ((rc = owned_setup(c))) { ctx_toc(c); return rc; }
       if (M->d.owned) IBM_CUDA(c, cudaMemsetAsync(M->d.mine, 0, (size_t)c->cap * sizeof(int), c->stream));
+      ctx_mark(c, "advance:classified");
       cluster_execute(c, nSub);
+      ctx_mark(c, "advance:sub-steps done");
       if (M->d.owned && (rc = owned_exchange(c, nInst0))) { ctx_toc(c); return rc; }
+      ctx_mark(c, "advance:exchanged");
       M->nClusterSteps++;
       MotionDev& d = M->d;
       int* h = M->hEv;
@@ -3008,6 +3013,7 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
         IBM_CUDA(c, cudaMemcpyAsync(h + 16 + K5C_EVN, d.evKey + nInst0, (size_t)evn * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       }
       IBM_CUDA(c, cudaStreamSynchronize(c->stream));
+      ctx_mark(c, "advance:flags read");
       IBM_CUDA(c, cudaGetLastError());
       M->lastActive = h[3];
       c->hScal[11] = h[3];
@@ -3131,7 +3137,9 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
     }
   }
   ctx_toc(c);
+  ctx_mark(c, "advance:copies ordered");
   if ((rc = finish_substeps(c))) return rc;
+  ctx_mark(c, "advance:finished");
   // update() for every instance, deleteInActiveParticles, (indicator), then the log block
   if ((rc = ctx_update(c))) return rc;  // invalidates the same-index lists when instances were deleted
   if ((rc = ensure_motion(c))) return rc;
