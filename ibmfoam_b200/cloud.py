@@ -26,9 +26,10 @@ def _c(a, dt=np.float64):
 
 class ParticleCloud:
     def __init__(self, case=None, *, mesh=None, cloud=None, particles=None, device=0, max_instances=0,
-                 slab=None, local_group=None, nccl_id=None, rank=0, n_ranks=1):
-        """slab=(k0,k1): this rank's z-planes of the (whole) mesh; local_group / nccl_id select the transport of the
-        F/T and status all-reduces (multi-GPU: slab-decomposed fields, replicated particle state)."""
+                 slab=None, halo=0, local_group=None, nccl_id=None, rank=0, n_ranks=1):
+        """slab=(k0,k1): this rank's z-planes of the (whole) mesh; halo: read-only planes of the neighbouring slabs on either
+        side (ibm_set_slab_halo: the fields then cover self.local_planes); local_group / nccl_id select the transport of
+        the all-reduces (multi-GPU: slab-decomposed fields, particle directory on every rank)."""
         L = capi.load()
         if case is not None:
             mesh, cloud, particles = case.mesh, case.cloud, case.particles
@@ -63,9 +64,15 @@ class ParticleCloud:
         self._L = L
         self.n_cells = mesh.n_cells
         self.slab = slab
+        self.local_planes = (0, mesh.nz) if slab is None else (int(slab[0]), int(slab[1]))
         if slab is not None:
-            check(L.ibm_set_slab(h, int(slab[0]), int(slab[1])), h)
-            self.n_cells = mesh.nx * mesh.ny * (int(slab[1]) - int(slab[0]))
+            if halo:
+                lo, hi = C.c_int(), C.c_int()
+                check(L.ibm_set_slab_halo(h, int(slab[0]), int(slab[1]), int(halo), C.byref(lo), C.byref(hi)), h)
+                self.local_planes = (lo.value, hi.value)  # planes the cell fields of this rank cover (owned + halo)
+            else:
+                check(L.ibm_set_slab(h, int(slab[0]), int(slab[1])), h)
+            self.n_cells = mesh.nx * mesh.ny * (self.local_planes[1] - self.local_planes[0])
         if local_group is not None:
             check(L.ibm_comm_init_local(h, local_group, int(rank)), h)
         elif nccl_id is not None:

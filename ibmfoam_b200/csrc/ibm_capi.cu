@@ -638,6 +638,7 @@ int ibm_create(const ibm_mesh_desc* mesh, const ibm_cloud_cfg* cfg, int device, 
   L.dx = mesh->delta[0]; L.dy = mesh->delta[1]; L.dz = mesh->delta[2];
   L.latToCell = nullptr; L.cellToLat = nullptr;
   L.kz0 = 0;
+  L.ownK0 = 0; L.ownK1 = L.nz;
   c->zMin = L.oz;
   c->zMax = L.oz + L.nz * L.dz;
   // caller cell numbering
@@ -835,17 +836,24 @@ int ibm_destroy(ibm_ctx* c) {
   return IBM_OK;
 }
 
-int ibm_set_slab(ibm_ctx* c, int k0, int k1) {
+int ibm_set_slab_halo(ibm_ctx* c, int k0, int k1, int halo, int* localK0, int* localK1) {
   if (!c) return IBM_E_ARG;
   if (c->cap != 0) return ctx_fail(c, IBM_E_STATE, "ibm_set_slab: call before ibm_set_particles");
   if (c->Lg.latToCell) return ctx_fail(c, IBM_E_UNSUPPORTED, "ibm_set_slab: slab decomposition needs a single-block lattice");
-  if (k0 < 0 || k1 > c->Lg.nz || k0 >= k1) return ctx_fail(c, IBM_E_ARG, "ibm_set_slab: bad plane range");
+  if (k0 < 0 || k1 > c->Lg.nz || k0 >= k1 || halo < 0) return ctx_fail(c, IBM_E_ARG, "ibm_set_slab: bad plane range");
+  const int lo = std::max(0, k0 - halo), hi = std::min(c->Lg.nz, k1 + halo);
   c->L = c->Lg;
-  c->L.kz0 = k0;
-  c->L.nz = k1 - k0;
+  c->L.kz0 = lo;
+  c->L.nz = hi - lo;
+  c->L.ownK0 = k0 - lo;
+  c->L.ownK1 = k1 - lo;
   c->L.nCells = c->L.nx * c->L.ny * c->L.nz;
+  if (localK0) *localK0 = lo;
+  if (localK1) *localK1 = hi;
   return IBM_OK;
 }
+
+int ibm_set_slab(ibm_ctx* c, int k0, int k1) { return ibm_set_slab_halo(c, k0, k1, 0, nullptr, nullptr); }
 
 int ibm_update(ibm_ctx* c) {
   if (!c) return IBM_E_ARG;

@@ -31,7 +31,15 @@ struct LatticeDev {
   int kz0;               // slab decomposition: global z-plane of local plane 0 (nz is the LOCAL plane count);
                          // geometry is always evaluated with the global plane index K + kz0, exactly as a
                          // decomposed OpenFOAM mesh keeps the global cell centres
+  int ownK0, ownK1;      // local planes [ownK0, ownK1) are OWNED by this rank, the others are a read-only halo of the
+                         // neighbouring slabs (ibm_set_slab_halo): shell cells are marked, shape points counted and surface
+                         // points integrated in owned planes only; gathers read the halo.  Without a halo: 0, nz.
 };
+// z-extent of the owned planes; does lattice cell latIdx lie in one
+__device__ __forceinline__ double own_zlo(const LatticeDev& L) { return L.oz + (L.kz0 + L.ownK0) * L.dz; }
+__device__ __forceinline__ double own_zhi(const LatticeDev& L) { return L.oz + (L.kz0 + L.ownK1) * L.dz; }
+__device__ __forceinline__ bool has_halo(const LatticeDev& L) { return L.ownK0 > 0 || L.ownK1 < L.nz; }
+__device__ __forceinline__ bool owned_plane(const LatticeDev& L, int K) { return K >= L.ownK0 && K < L.ownK1; }
 
 struct ShapeClassDev {
   int kind, nTheta, nk, N;

@@ -79,7 +79,7 @@ __device__ __forceinline__ Box bounding_box(const LatticeDev& L, double cx, doub
   Box b;
   b.i0 = max(0, (int)floor((cx - R - L.ox) / L.dx) - 1); b.i1 = min(L.nx - 1, (int)floor((cx + R - L.ox) / L.dx) + 1);
   b.j0 = max(0, (int)floor((cy - R - L.oy) / L.dy) - 1); b.j1 = min(L.ny - 1, (int)floor((cy + R - L.oy) / L.dy) + 1);
-  b.k0 = max(0, (int)floor((cz - R - L.oz) / L.dz) - 1 - L.kz0); b.k1 = min(L.nz - 1, (int)floor((cz + R - L.oz) / L.dz) + 1 - L.kz0);
+  b.k0 = max(L.ownK0, (int)floor((cz - R - L.oz) / L.dz) - 1 - L.kz0); b.k1 = min(L.ownK1 - 1, (int)floor((cz + R - L.oz) / L.dz) + 1 - L.kz0);  // owned planes only
   return b;
 }
 
@@ -131,12 +131,12 @@ __global__ void k1_count(LatticeDev L, const ShapeClassDev* __restrict__ classes
   for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {
     V3 p = shape_point(sc, srot, cx, cy, cz, n);
     int I, J, K;
-    if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0) ++on;
+    if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0 && owned_plane(L, K)) ++on;
   }
   int nOn = block_sum(on, sm);
   if (threadIdx.x == 0) {
     int I, J, K;
-    int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
+    int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0 && owned_plane(L, K);
     in.nShell[b] = nShell;
     in.nPtsOnMesh[b] = nOn;  // local count; summed over the slabs before k1_status on several GPUs
     in.onLocal[b] = (nOn == 0 && !cOn) ? 0 : (nOn == sc.N ? 2 : 1);
@@ -152,11 +152,11 @@ __device__ __forceinline__ void mark_finish(const LatticeDev& L, const ShapeClas
   const double mx = 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
   rOut += mx;
   const bool inside = cx - rOut > L.ox && cx + rOut < L.ox + L.nx * L.dx && cy - rOut > L.oy && cy + rOut < L.oy + L.ny * L.dy &&
-                      (L.nz == 1 && sc.kind != 0 ? (cz > L.oz + L.kz0 * L.dz && cz < L.oz + (L.kz0 + L.nz) * L.dz)
-                                                 : (cz - rOut > L.oz + L.kz0 * L.dz && cz + rOut < L.oz + (L.kz0 + L.nz) * L.dz));
-  // ... and none when the outer layer cannot reach the local lattice at all (other slabs' instances on a multi-GPU run)
+                      (L.nz == 1 && sc.kind != 0 ? (cz > own_zlo(L) && cz < own_zhi(L))
+                                                 : (cz - rOut > own_zlo(L) && cz + rOut < own_zhi(L)));
+  // ... and none when the outer layer cannot reach the owned planes at all (other slabs' instances on a multi-GPU run)
   const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
-                       cz + rOut < L.oz + L.kz0 * L.dz || cz - rOut > L.oz + (L.kz0 + L.nz) * L.dz;
+                       cz + rOut < own_zlo(L) || cz - rOut > own_zhi(L);
   int nOn;
   if (inside) {
     nOn = sc.N;
@@ -167,13 +167,13 @@ __device__ __forceinline__ void mark_finish(const LatticeDev& L, const ShapeClas
     for (int n = threadIdx.x; n < sc.N; n += blockDim.x) {
       V3 p = shape_point(sc, srot, cx, cy, cz, n);
       int I, J, K;
-      if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0) ++on;
+      if (find_cell(L, p.x, p.y, p.z, I, J, K) >= 0 && owned_plane(L, K)) ++on;
     }
     nOn = block_sum(on, sm);
   }
   if (threadIdx.x == 0) {
     int I, J, K;
-    const int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0;
+    const int cOn = find_cell(L, cx, cy, cz, I, J, K) >= 0 && owned_plane(L, K);
     in.nShell[b] = off >= 0 ? nShell : 0;
     in.shellOff[b] = off >= 0 ? off : 0;
     in.nPtsOnMesh[b] = nOn;
@@ -290,7 +290,7 @@ __global__ void k1_mark2(LatticeDev L, const ShapeClassDev* __restrict__ classes
     double rOut = sc.Rbound + sc.delta;
     rOut += 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
     const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
-                         cz + rOut < L.oz + L.kz0 * L.dz || cz - rOut > L.oz + (L.kz0 + L.nz) * L.dz;
+                         cz + rOut < own_zlo(L) || cz - rOut > own_zhi(L);
     if (outside) {
       if (threadIdx.x == 0) {
         double r9[9];
@@ -687,7 +687,8 @@ __global__ void k_stress_ref(LatticeDev L, const ShapeClassDev* __restrict__ cla
       if (on) {  // interpolateFromMesh returns early for OFF_MESH particles: fields stay zero
         Stencil st;
         make_stencil(L, pt, st);
-        if (st.self >= 0) {
+        // (with a halo a surface point is integrated by the rank that owns the plane of its cell, and by no other)
+        if (st.self >= 0 && (!has_halo(L) || owned_plane(L, st.self / (L.nx * L.ny)))) {
           for (int q = 0; q < st.n; ++q) {
             double ww = xdiv(st.w[q], st.W);
             bool own = (st.selfOwner >> q) & 1;

@@ -302,7 +302,7 @@ __device__ __forceinline__ void stress_v2_instance(const LatticeDev& L, const Sh
     if (on) {
       Stencil7 st;
       make_stencil7(L, idx, idy, idz, pt, st);
-      if (st.self >= 0) {
+      if (st.self >= 0 && (!has_halo(L) || owned_plane(L, st.self / (L.nx * L.ny)))) {  // halo: integrated by the owner of the point's plane
 #pragma unroll
         for (int cmp = 0; cmp < 6; ++cmp) tau[cmp] = gather7(st, Tau + cmp * C) * rhoRef;
         pp = (gather7(st, P) - 2.0 * st.cSelf * pRefOverRho) * rhoRef;

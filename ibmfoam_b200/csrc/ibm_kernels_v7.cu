@@ -116,10 +116,10 @@ struct Box7 {
 
 struct Geo7 {  // lattice constants of a launch, in registers
   double ox, oy, oz, dx, dy, dz, idx, idy, idz, hx, hy, hz;
-  int nx, ny, nz, kz0;
+  int nx, ny, nz, kz0, ownK0, ownK1;
 };
 __device__ __forceinline__ Geo7 geo7(const LatticeDev& L) {
-  return Geo7{L.ox, L.oy, L.oz, L.dx, L.dy, L.dz, 1.0 / L.dx, 1.0 / L.dy, 1.0 / L.dz, 0.5 * L.dx, 0.5 * L.dy, 0.5 * L.dz, L.nx, L.ny, L.nz, L.kz0};
+  return Geo7{L.ox, L.oy, L.oz, L.dx, L.dy, L.dz, 1.0 / L.dx, 1.0 / L.dy, 1.0 / L.dz, 0.5 * L.dx, 0.5 * L.dy, 0.5 * L.dz, L.nx, L.ny, L.nz, L.kz0, L.ownK0, L.ownK1};
 }
 
 // exclusive scan of two ints per thread over the block; every thread gets the block totals
@@ -181,7 +181,7 @@ struct St7 { int idx[7]; double c[7]; };  // self, +x, -x, +y, -y, +z, -z: recor
 // weights lambda = 1/2 folded in).  Returns false when the point is off the local mesh (it contributes nothing).
 template <bool EDGE>
 __device__ __forceinline__ bool make_st7(const Geo7& G, const Box7& B, const int* __restrict__ rowBase, const int* __restrict__ rowLo,
-                                         const int* __restrict__ rowHi, const V3& p, St7& s, int& guard) {
+                                         const int* __restrict__ rowHi, const V3& p, St7& s, int& guard, const bool ownedOnly = false) {
   double fx, fy, fz;
   const int I = cell_axis7(p.x - G.ox, G.dx, G.idx, fx);
   const int J = cell_axis7(p.y - G.oy, G.dy, G.idy, fy);
@@ -189,6 +189,8 @@ __device__ __forceinline__ bool make_st7(const Geo7& G, const Box7& B, const int
   if (EDGE) {
     if ((unsigned)I >= (unsigned)G.nx || (unsigned)J >= (unsigned)G.ny || (unsigned)K >= (unsigned)G.nz) return false;
   }
+  // the stress integral with a halo (ibm_set_slab_halo): a surface point belongs to the rank that owns the plane of its cell
+  if (ownedOnly && (K < G.ownK0 || K >= G.ownK1)) return false;
   const int bj = J - B.j0, bk = K - B.k0;
   const int row = bj + B.by * bk;
 #if defined(IBM_V7_GUARD)
@@ -718,7 +720,7 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
     double g[7] = {0, 0, 0, 0, 0, 0, 0};
     double pp = 0.0;
     St7 st;
-    if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, pt, st, guard)) {
+    if (make_st7<EDGE>(X.G, X.B, X.baseB, X.loB, X.hiB, pt, st, guard, true)) {
       if (SOA) gat7_planes<7>(st, X.planes, X.nB, g); else gat7<7>(st, X.planes, g);
       pp = (g[0] - 2.0 * st.c[0] * X.pRefOverRho) * X.rhoRef;
 #pragma unroll

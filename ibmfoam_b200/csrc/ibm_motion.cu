@@ -2848,7 +2848,7 @@ static int owned_setup(ibm_ctx* c) {
   if (!c->ownedLoop5 || nR < 2 || nR > 16) return IBM_OK;
   if (!M->slabsKnown) {
     int h[17] = {0};
-    h[comm_rank(c)] = c->L.kz0;
+    h[comm_rank(c)] = c->L.kz0 + c->L.ownK0;  // first OWNED plane
     int* dTmp = (int*)M->dPerm;  // (scratch of the step's end, free here)
     IBM_CUDA(c, cudaMemcpyAsync(dTmp, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     int rc = comm_allreduce_sum(c, dTmp, 17, 1);

@@ -222,6 +222,16 @@ int ibm_timings_reset(ibm_ctx* ctx);
  * rank: ibm_create(WHOLE mesh) -> ibm_set_slab -> ibm_comm_init -> ibm_set_particles(ALL particles).
  * Cell fields handed to ibm_forcing / ibm_integrate_stress are then the rank's own z-planes [k0,k1). --- */
 int ibm_set_slab(ibm_ctx* ctx, int k0, int k1);
+/* EXTENSION (the reference's parallel results depend on the decomposition, particleShape.C:45-47,59): the same
+ * slab with `halo` read-only planes of the neighbouring slabs on either side (clipped at the mesh).  The caller's cell
+ * fields then cover the planes [*localK0, *localK1) returned here, halo planes filled with the neighbours' values (what a
+ * processor-patch exchange provides).  Shell cells are marked, shape points counted and surface points integrated in the
+ * owned planes [k0,k1) only, gathers read the halo: when the halo is deep enough that every stencil is complete, forcing
+ * field, force and torque equal the SERIAL run's, whatever the decomposition.  Deep enough: (2 delta + polar-bin arc)/dz + 1
+ * planes (3-4) for the regular polar bins; but the degenerate bins at the pole of a sphere reference point 0 - the OPPOSITE
+ * pole - as coded (particleShape.C:148, App. B #3), so a sphere needs (d + delta)/dz + 1 planes to be exact.
+ * halo = 0 is ibm_set_slab. */
+int ibm_set_slab_halo(ibm_ctx* ctx, int k0, int k1, int halo, int* localK0, int* localK1);
 int ibm_comm_unique_id_bytes(void);
 int ibm_comm_get_unique_id(void* idBytes);               /* rank 0; broadcast the bytes with the launcher's own transport */
 int ibm_comm_init(ibm_ctx* ctx, const void* idBytes, int rank, int nRanks);   /* NCCL, one process per GPU */

@@ -106,6 +106,60 @@ def test_loops_1_to_4_match_decomposed_oracle(n_ranks):
     group.close()
 
 
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_halo_makes_results_decomposition_independent(n_ranks):
+    """EXTENSION: with a few read-only halo planes per slab every gather stencil is complete, so the shell
+    lists of the ranks tile the serial ones, the forcing field on the owned planes is the SERIAL field, and the summed
+    force / torque the serial force / torque - whatever the decomposition (the reference's depend on it, particleShape.C:45-47)."""
+    case = cases.assembly(n=48, n_particles=70, seed=11, moving=True, cyclic_without_walls=True)
+    ranges = slab_ranges(case.mesh.nz, n_ranks)
+    f_lat = cases.synthetic_fields(case.mesh)
+    nxy = case.mesh.nx * case.mesh.ny
+    group = LocalGroup(n_ranks)
+    oc = OracleCloud(case)  # the WHOLE mesh
+    Fo, _ = oc.forcing(f_lat["U"], f_lat["Uold"], f_lat["S"], case.dt)
+    FTo = oc.integrate_stress(f_lat["p"], f_lat["tau"])
+    so = oc.state_arrays()
+    shells = [oc.shell(n) for n in range(len(so["index"]))]
+    # d = 8 cells: the degenerate polar bins of a sphere reference point 0 at the opposite pole (App. B #3), so the halo has to
+    # span the body for bit-level agreement; 4 planes leave two cells of this case with an incomplete stencil
+    halo = 10
+
+    def rank(r):
+        k0, k1 = ranges[r]
+        gc = ParticleCloud(case, slab=(k0, k1), halo=halo, local_group=group.handle, rank=r)
+        lo, hi = gc.local_planes
+        assert lo == max(0, k0 - halo) and hi == min(case.mesh.nz, k1 + halo)
+        sl = slice(lo * nxy, hi * nxy)
+        sg = gc.state_arrays()
+        assert np.array_equal(sg["index"], so["index"]) and np.array_equal(sg["onMesh"], so["onMesh"])
+        # marking: the serial shell of every instance restricted to the owned planes (cell ids are local: + lo planes)
+        n_cells_owned = 0
+        for n in range(len(so["index"])):
+            a, b = shells[n], gc.shell(n)
+            keep = (a["cells"] // nxy >= k0) & (a["cells"] // nxy < k1)
+            assert np.array_equal(a["cells"][keep] - lo * nxy, b["cells"]) and np.array_equal(a["jk"][keep], b["jk"])
+            n_cells_owned += int(keep.sum())
+        # forcing: the serial field on the owned planes, nothing in the halo planes
+        Fg = gc.forcing(f_lat["S"][sl], f_lat["U"][sl], f_lat["Uold"][sl], case.dt)
+        own = slice((k0 - lo) * nxy, (k1 - lo) * nxy)
+        assert util.rel_err(Fg[own], Fo[k0 * nxy:k1 * nxy]) < 1e-12
+        assert not np.any(Fg[:(k0 - lo) * nxy]) and not np.any(Fg[(k1 - lo) * nxy:])
+        gc.integrateSurfaceStresses(f_lat["p"][sl], f_lat["tau"][sl])
+        gc.combineForces()
+        st = gc.state_arrays()
+        got = np.concatenate([st["F"], st["T"]], axis=1)
+        gc.close()
+        return got, n_cells_owned
+
+    res = _run_ranks(n_ranks, rank)
+    scale = np.max(np.abs(FTo))
+    for got, _ in res:
+        assert np.max(np.abs(got - FTo)) < 1e-10 * scale  # the SERIAL force and torque of every instance
+    assert sum(n for _, n in res) == sum(len(s["cells"]) for s in shells)
+    group.close()
+
+
 @pytest.mark.parametrize("n_ranks,owned", [(2, 1), (3, 1), (2, 0)])
 def test_loop5_replicated_equals_serial_oracle(n_ranks, owned):
     """Loop 5 over several ranks: trajectories, periodic copies and deletions are those of the SERIAL reference
