@@ -60,7 +60,7 @@ void launch_stress_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
                       const Schedule& s, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr);
 
 // ---- ibm_kernels_v7.cu: one CTA per instance, ball-row staging of combined fields, gathers from shared memory ----
-struct V7Caps { int planeCap, colCap, rowsCap, mapCap, nTcap, nkCap, elemCap; };  // shared-memory capacities of a launch (doubles / entries)
+struct V7Caps { int planeCap, colCap, rowsCap, mapCap, nTcap, nkCap, elemCap, prefetch; };  // shared-memory capacities of a launch (doubles / entries)
 // Per-instance launch records of the staged kernels, built once per update (k7_prepare) in SCHEDULE order, so that a CTA
 // finds everything its prologue needs - which instance, its box, the staged rows of the three reaches - with loads that
 // depend on nothing but blockIdx (one memory round trip instead of the chain order -> instance -> class -> box -> rows, and
