@@ -283,30 +283,13 @@ __global__ void k1_mark2(LatticeDev L, const ShapeClassDev* __restrict__ classes
   if (b >= nInst) return;
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
-  {
-    // An instance whose outer layer cannot reach the local lattice (other slabs' instances on a multi-GPU run: 7 of 8 on
-    // eight GPUs) has no shell cell and no point here: one thread writes what mark_finish would and the block is gone,
-    // without the four barriers below.  Same test as mark_finish.
-    double rOut = sc.Rbound + sc.delta;
-    rOut += 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
-    const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
-                         cz + rOut < own_zlo(L) || cz - rOut > own_zhi(L);
-    if (outside) {
-      if (threadIdx.x == 0) {
-        double r9[9];
-        set_rotation_matrix(in.th[0][b], in.th[1][b], in.th[2][b], r9);
-        for (int q = 0; q < 9; ++q) in.rot[9 * (size_t)b + q] = r9[q];
-        if (sc.kind == 2) {
-          double tz = in.th[2][b];
-          if (tz < 0) tz = xadd(tz, IBM_TWOPI);
-          if (tz > IBM_TWOPI) tz = xsub(tz, IBM_TWOPI);
-          in.th[2][b] = tz;
-        }
-        in.nShell[b] = 0; in.shellOff[b] = 0; in.nPtsOnMesh[b] = 0; in.onLocal[b] = 0;
-      }
-      return;
-    }
-  }
+  // An instance whose outer layer cannot reach the owned planes (other slabs' instances on a multi-GPU run: 7 of 8 on eight
+  // GPUs) has no shell cell and no point here: thread 0 writes what mark_finish would and the block is gone, without the
+  // four barriers below.  Same test as mark_finish.
+  double rOutQ = sc.Rbound + sc.delta;
+  rOutQ += 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOutQ) + 1e-300;
+  const bool outsideQ = cx + rOutQ < L.ox || cx - rOutQ > L.ox + L.nx * L.dx || cy + rOutQ < L.oy || cy - rOutQ > L.oy + L.ny * L.dy ||
+                        cz + rOutQ < own_zlo(L) || cz - rOutQ > own_zhi(L);
   if (threadIdx.x == 0) {
     set_rotation_matrix(in.th[0][b], in.th[1][b], in.th[2][b], srot);  // particleShape::moveMesh (particleShape.C:291-295)
     for (int q = 0; q < 9; ++q) in.rot[9 * (size_t)b + q] = srot[q];
@@ -317,7 +300,9 @@ __global__ void k1_mark2(LatticeDev L, const ShapeClassDev* __restrict__ classes
       in.th[2][b] = tz;
     }
     nList = 0; nDirect = 0;
+    if (outsideQ) { in.nShell[b] = 0; in.shellOff[b] = 0; in.nPtsOnMesh[b] = 0; in.onLocal[b] = 0; }
   }
+  if (outsideQ) return;  // (block-uniform)
   __syncthreads();
   const double thz = in.th[2][b];
   Box bx = bounding_box(L, cx, cy, cz, sc.Rbound);

@@ -3092,27 +3092,42 @@ int motion_advance(ibm_ctx* c, double dt, ibm_solve_stats* stats) {
       // per schedule of local time steps and replay it — the sub-step kernels are a few microseconds each
       bool same = M->graphExec && M->graphValid && M->graphActive == split && M->graphSafety == M->d.safety * M->d.check && M->graphDt == dt && c->nInst <= M->graphNInst && (int)M->graphDts.size() == nSub;
       for (int s = 0; same && s < nSub; ++s) same = M->graphDts[s] == dts[s];
+      bool graphOk = true;
       if (!same) {
         if (M->graphExec) { cudaGraphExecDestroy(M->graphExec); M->graphExec = nullptr; }
+        M->graphValid = false;
         cudaGraph_t g = nullptr;
-        IBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const long long before = c->nLaunch;
-        sequence();
-        M->graphLaunches = c->nLaunch - before;
-        c->nLaunch = before;
-        IBM_CUDA(c, cudaStreamEndCapture(c->stream, &g));
-        cudaError_t e = cudaGraphInstantiate(&M->graphExec, g, 0);
-        cudaGraphDestroy(g);
-        IBM_CUDA(c, e);
-        M->graphDts.assign(dts, dts + nSub);
-        M->graphValid = true;
-        M->graphActive = split;
-        M->graphSafety = M->d.safety * M->d.check;
-        M->graphDt = dt;
-        M->graphNInst = c->nInst;
+        // no early return between BeginCapture and EndCapture: an error inside must end the capture, drop the partial graph
+        // and leave the timer pair balanced (the step then runs as plain launches)
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+          const long long before = c->nLaunch;
+          sequence();
+          M->graphLaunches = c->nLaunch - before;
+          c->nLaunch = before;
+          e = cudaStreamEndCapture(c->stream, &g);
+          if (e == cudaSuccess) e = cudaGraphInstantiate(&M->graphExec, g, 0);
+          if (g) cudaGraphDestroy(g);
+        }
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          M->graphExec = nullptr;
+          graphOk = false;
+        } else {
+          M->graphDts.assign(dts, dts + nSub);
+          M->graphValid = true;
+          M->graphActive = split;
+          M->graphSafety = M->d.safety * M->d.check;
+          M->graphDt = dt;
+          M->graphNInst = c->nInst;
+        }
       }
-      IBM_CUDA(c, cudaGraphLaunch(M->graphExec, c->stream));
-      c->nLaunch += M->graphLaunches;
+      if (graphOk) {
+        if (!ctx_cuda_ok(c, cudaGraphLaunch(M->graphExec, c->stream), "cudaGraphLaunch")) { ctx_toc(c); return IBM_E_CUDA; }
+        c->nLaunch += M->graphLaunches;
+      } else {
+        sequence();
+      }
     } else {
       sequence();
     }
