@@ -302,6 +302,21 @@ int ctx_update(ibm_ctx* c) {
     IBM_CUDA(c, cudaMemsetAsync(c->dScal, 0, 8 * sizeof(int), c->stream));
     // dScal: [0] kept instances, [1] shell cursor, [2] work items, [3] updates per forcing call, [4] shell overflow
     ctx_mark(c, "update:begin");
+    // The Morton order of the schedule and the geometry of the launch records need the centres only: they run on a side
+    // stream beside the marking kernel (0.5 ms of latency-bound kernels off the critical path); what depends on the marking
+    // (work-item table, shell segments, has-local-points flags) follows on the main stream after the join.
+    if (!c->updSide) {
+      IBM_CUDA(c, cudaStreamCreateWithFlags(&c->updSide, cudaStreamNonBlocking));
+      IBM_CUDA(c, cudaEventCreateWithFlags(&c->updFork, cudaEventDisableTiming));
+      IBM_CUDA(c, cudaEventCreateWithFlags(&c->updJoin, cudaEventDisableTiming));
+    }
+    IBM_CUDA(c, cudaEventRecord(c->updFork, c->stream));
+    IBM_CUDA(c, cudaStreamWaitEvent(c->updSide, c->updFork, 0));
+    if (c->nInst > 0) {
+      launch_schedule_order(c->updSide, c->L, c->in, c->nInst, c->sched);
+      if (c->v7ok) { launch_v7_prepare(c->updSide, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
+    }
+    IBM_CUDA(c, cudaEventRecord(c->updJoin, c->updSide));
     launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant);
     ctx_mark(c, "update:marked");
     if (comm_ranks(c) > 1 && c->nInst > 0) {
@@ -318,9 +333,11 @@ int ctx_update(ibm_ctx* c) {
     launch_k1_status(c->stream, c->Lg, c->dClasses, c->in, c->nInst);
     launch_keep_flags(c->stream, c->in, c->nInst, c->dKeep);
     if (c->nInst > 0) launch_exclusive_scan_total(c->stream, c->sched, c->dKeep, c->dKeepOff, c->nInst, c->dScal + 0);
-    launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
-    ctx_mark(c, "update:scheduled");
-    if (c->v7ok) { launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
+    ctx_mark(c, "update:status, keep scan");
+    IBM_CUDA(c, cudaStreamWaitEvent(c->stream, c->updJoin, 0));
+    ctx_mark(c, "update:joined");
+    if (c->nInst > 0) launch_schedule_chunks(c->stream, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
+    if (c->v7ok) { launch_v7_finish(c->stream, c->in, c->nInst, c->sched, c->v7prep); c->nLaunch++; }
     ctx_mark(c, "update:prepared");
     c->nLaunch += 9;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -343,7 +360,11 @@ int ctx_update(ibm_ctx* c) {
     c->nInst = c->hScal[0];
     motion_invalidate_groups(c);
     launch_build_schedule(c->stream, c->L, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
-    if (c->v7ok) { launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
+    if (c->v7ok) {
+      launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep);
+      launch_v7_finish(c->stream, c->in, c->nInst, c->sched, c->v7prep);
+      c->nLaunch += 2;
+    }
     c->nLaunch += 6;
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -820,6 +841,7 @@ int ibm_destroy(ibm_ctx* c) {
   comm_destroy(c);
   schedule_free(c->sched);
   v7_prep_free(c->v7prep);
+  if (c->updSide) { cudaStreamSynchronize(c->updSide); cudaStreamDestroy(c->updSide); cudaEventDestroy(c->updFork); cudaEventDestroy(c->updJoin); }
   for (auto& p : c->events) { cudaEventDestroy(p.a); if (p.b) cudaEventDestroy(p.b); }
   for (auto e : c->eventPool) cudaEventDestroy(e);
   for (auto p : c->instAllocs) cudaFree(p);

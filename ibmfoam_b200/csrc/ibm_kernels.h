@@ -46,6 +46,7 @@ struct Schedule {
   int* chunkCnt = nullptr; int* chunkOff = nullptr;  // per sorted position; chunkOff has n+1 entries
   int chunk = FORCING_CHUNK;                         // shell cells per work item of the direct-gather kernel (128, or 256 with option chunk256)
   void* temp = nullptr; size_t tempBytes = 0;
+  void* temp2 = nullptr;                             // scratch of the sort (it may run on a side stream beside the scans that use temp)
   int cap = 0;
 };
 int schedule_alloc(Schedule& s, int cap);
@@ -53,6 +54,9 @@ void schedule_free(Schedule& s);
 // builds order[] and chunkOff[]; writes the total number of work items to *dTotalChunks
 void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks,
                            int* dTotalUpdates);
+// its two halves: the Morton order needs the centres only (it can run beside the marking kernel), the work-item table the shell counts
+void launch_schedule_order(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s);
+void launch_schedule_chunks(cudaStream_t st, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks, int* dTotalUpdates);
 void launch_forcing_v2(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, int totalChunks, const int* shellCell, const int* shellJK, const double* U,
                        const double* Uold, const double* S, double dT, double* F);
@@ -80,8 +84,11 @@ struct V7Prep {
 bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress);
 int v7_prep_alloc(V7Prep& p, int cap, int rowsCap);
 void v7_prep_free(V7Prep& p);
+// geometry of the records (needs the centres and the order only: may run beside the marking kernel) ...
 void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, const V7Caps& capF, const V7Prep& prep);
+// ... and what the marking kernel decides: shell segment, has-local-points flag
+void launch_v7_finish(cudaStream_t st, const InstanceSoA& in, int nInst, const Schedule& s, const V7Prep& prep);
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
                        const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard);

@@ -124,24 +124,31 @@ int schedule_alloc(Schedule& s, int cap) {
   A((void**)&s.iota, cap * sizeof(int)); A((void**)&s.order, cap * sizeof(int));
   A((void**)&s.chunkCnt, (cap + 1) * sizeof(int)); A((void**)&s.chunkOff, (cap + 1) * sizeof(int));
   A(&s.temp, s.tempBytes);
+  A(&s.temp2, s.tempBytes);
   return e == cudaSuccess ? 0 : -1;
 }
 void schedule_free(Schedule& s) {
-  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp};
+  void* ps[] = {s.keys, s.keysSorted, s.iota, s.order, s.chunkCnt, s.chunkOff, s.temp, s.temp2};
   for (void* p : ps) if (p) cudaFree(p);
   s = Schedule{};
 }
-void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks,
-                           int* dTotalUpdates) {
+void launch_schedule_order(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s) {
   const int cap = s.cap;
   k_morton_keys<<<(cap + 255) / 256, 256, 0, st>>>(L, in, nInst, cap, s.keys, s.iota);
   size_t tb = s.tempBytes;
-  cub::DeviceRadixSort::SortPairs(s.temp, tb, s.keys, s.keysSorted, s.iota, s.order, cap, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(s.temp2, tb, s.keys, s.keysSorted, s.iota, s.order, cap, 0, 32, st);
+}
+void launch_schedule_chunks(cudaStream_t st, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks, int* dTotalUpdates) {
   cudaMemsetAsync(dTotalUpdates, 0, sizeof(int), st);
   k_chunk_counts<<<(nInst + 256) / 256, 256, 0, st>>>(in, s.order, nInst, s.chunkCnt, dTotalUpdates, s.chunk);
-  tb = s.tempBytes;
+  size_t tb = s.tempBytes;
   cub::DeviceScan::ExclusiveSum(s.temp, tb, s.chunkCnt, s.chunkOff, nInst + 1, st);
   k_last_offset<<<1, 1, 0, st>>>(s.chunkOff, nInst, dTotalChunks);
+}
+void launch_build_schedule(cudaStream_t st, const LatticeDev& L, const InstanceSoA& in, int nInst, Schedule& s, int* dTotalChunks,
+                           int* dTotalUpdates) {
+  launch_schedule_order(st, L, in, nInst, s);
+  launch_schedule_chunks(st, in, nInst, s, dTotalChunks, dTotalUpdates);
 }
 
 void launch_keep_flags(cudaStream_t st, const InstanceSoA& in, int nInst, int* keep) {

@@ -369,18 +369,26 @@ k7_prepare(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA 
   if ((int)blockIdx.x >= nInst) return;
   const int b = order[blockIdx.x];
   const int cls = in.cls[b];
-  const int local = in.onLocal[b];
-  if (local == 0) {  // no point on this rank's slab (other ranks' instances on a multi-GPU run): the kernels only need to know that
-    if (threadIdx.x == 0) {
-      V7Hdr h{};
-      h.b = b; h.cls = cls; h.nShell = in.nShell[b]; h.shellOff = in.shellOff[b];
-      h.cx = in.c[0][b]; h.cy = in.c[1][b]; h.cz = in.c[2][b];
-      hdr[blockIdx.x] = h;
-    }
-    return;
-  }
   const ShapeClassDev sc = classes[cls];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  {
+    // The outer layer cannot reach the owned planes (other ranks' instances on a multi-GPU run): the kernels only need to know
+    // that.  The test of the marking kernel (mark_finish), so that this kernel needs nothing the marking kernel writes and
+    // can run beside it; k7_finish adds the shell segment and clears the flag of instances without local points.
+    double rOut = sc.Rbound + sc.delta;
+    rOut += 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
+    const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
+                         cz + rOut < own_zlo(L) || cz - rOut > own_zhi(L);
+    if (outside) {
+      if (threadIdx.x == 0) {
+        V7Hdr h{};
+        h.b = b; h.cls = cls;
+        h.cx = cx; h.cy = cy; h.cz = cz;
+        hdr[blockIdx.x] = h;
+      }
+      return;
+    }
+  }
   const double R = sc.d / 2.0;
   const double rho[3] = {xadd(R, sc.delta), xadd(R, 0.0), xadd(R, -1 * sc.delta)};  // set 0 = outer reach ... set 2 = inner reach
   Box7 B;
@@ -452,13 +460,22 @@ k7_prepare(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA 
   if (threadIdx.x == 0) {
     if (fits && nS[0] < 0) fits = false;
     V7Hdr h;
-    h.b = b; h.cls = cls; h.nShell = in.nShell[b]; h.shellOff = in.shellOff[b];
+    h.b = b; h.cls = cls; h.nShell = 0; h.shellOff = 0;  // (k7_finish)
     h.flags = V7_F_LOCAL | (fits ? V7_F_FITS : 0) | (B.edge ? V7_F_EDGE : 0);
     h.j0 = B.j0; h.k0 = B.k0; h.by = B.by; h.bz = B.bz; h.i0 = B.i0; h.bx = B.bx;
     h.nA = max(nS[0], 0); h.nB = nS[1]; h.nC = nS[2]; h.pad0 = 0; h.pad1 = 0;
     h.cx = cx; h.cy = cy; h.cz = cz; h.pad2 = 0.0;
     hdr[blockIdx.x] = h;
   }
+}
+
+__global__ void k7_finish(InstanceSoA in, int nInst, const int* __restrict__ order, V7Hdr* __restrict__ hdr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nInst) return;
+  const int b = order[t];
+  hdr[t].nShell = in.nShell[b];
+  hdr[t].shellOff = in.shellOff[b];
+  if (in.onLocal[b] == 0) hdr[t].flags &= ~V7_F_LOCAL;
 }
 
 // row tables of a CTA from its packed record (sets first..last); rowG as build_region7 leaves it.  No barrier inside.
@@ -992,6 +1009,11 @@ void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
                        const Schedule& s, const V7Caps& capF, const V7Prep& prep) {
   if (nInst <= 0) return;
   k7_prepare<<<nInst, K7P_NT, 0, st>>>(L, classes, in, nInst, s.order, capF, prep.hdr, prep.rows, prep.rowsCap);
+}
+
+void launch_v7_finish(cudaStream_t st, const InstanceSoA& in, int nInst, const Schedule& s, const V7Prep& prep) {
+  if (nInst <= 0) return;
+  k7_finish<<<(nInst + 255) / 256, 256, 0, st>>>(in, nInst, s.order, prep.hdr);
 }
 
 template <int NT, int MINB>
