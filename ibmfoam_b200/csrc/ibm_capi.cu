@@ -337,10 +337,14 @@ int ctx_update(ibm_ctx* c) {
     IBM_CUDA(c, cudaStreamWaitEvent(c->stream, c->updJoin, 0));
     ctx_mark(c, "update:joined");
     if (c->nInst > 0) launch_schedule_chunks(c->stream, c->in, c->nInst, c->sched, c->dScal + 2, c->dScal + 3);
-    if (c->v7ok) { launch_v7_finish(c->stream, c->in, c->nInst, c->sched, c->v7prep); c->nLaunch++; }
+    if (c->v7ok) {
+      launch_v7_finish(c->stream, c->in, c->nInst, c->sched, c->v7prep);
+      if (comm_ranks(c) > 1) { launch_v7_compact(c->stream, c->nInst, c->sched, c->v7prep, c->dScal + 5); c->nLaunch += 4; }
+      c->nLaunch++;
+    }
     ctx_mark(c, "update:prepared");
     c->nLaunch += 9;
-    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 6 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaMemcpyAsync(c->hScal + 20, c->dScal + 13, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
     ctx_mark(c, "update:synced");
@@ -363,12 +367,15 @@ int ctx_update(ibm_ctx* c) {
     if (c->v7ok) {
       launch_v7_prepare(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep);
       launch_v7_finish(c->stream, c->in, c->nInst, c->sched, c->v7prep);
+      if (comm_ranks(c) > 1) { launch_v7_compact(c->stream, c->nInst, c->sched, c->v7prep, c->dScal + 5); c->nLaunch += 4; }
       c->nLaunch += 2;
     }
     c->nLaunch += 6;
-    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IBM_CUDA(c, cudaMemcpyAsync(c->hScal, c->dScal, 6 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IBM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  // several ranks: the staged kernels launch one CTA per instance with local points (1/G of the directory)
+  c->v7prep.nLocal = (c->v7ok && comm_ranks(c) > 1) ? c->hScal[5] : -1;
   c->schedN = c->nInst;
   c->totalShell = c->nInst > 0 ? c->hScal[1] : 0;   // extent of the shell buffer in use
   c->totalChunks = c->nInst > 0 ? c->hScal[2] : 0;
@@ -584,9 +591,12 @@ static int stress_on_device(ibm_ctx* c, const double* dP, const double* dTau, do
   if (!c->dTcorr) IBM_CUDA(c, cudaMalloc(&c->dTcorr, (size_t)3 * c->cap * sizeof(double)));
   ctx_tic(c, T_STRESS);
   const int sv = c->stressVariant;
-  if (sv >= 7 && c->v7ok)
+  if (sv >= 7 && c->v7ok) {
+    const bool clr = c->clearFInStress && c->fLive && c->dF && c->nInst > 0;
     launch_stress_v7(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7prep, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr, c->v7capS,
-                     c->dSlowList, c->dScal + 12, c->dScal + 13);
+                     c->dSlowList, c->dScal + 12, c->dScal + 13, clr ? c->dF : nullptr, c->dShellCell);
+    if (clr) c->fLive = false;
+  }
   else if (sv == 0)
     launch_stress_ref(c->stream, c->L, c->dClasses, c->in, c->nInst, dP, dTau, pRefOverRho, c->cfg.rhoRef, c->dTcorr);
   else
@@ -945,6 +955,7 @@ int ibm_substep(ibm_ctx* c, double localDt) {
 static void clear_F_on_side(ibm_ctx* c) {
   cudaStream_t side = motion_side_stream(c);
   if (!side || !c->fLive || !c->dF) return;
+  if (c->stressVariant >= 7 && c->v7ok) return;  // the staged stress kernel does it on the way (clearFInStress)
   launch_clear_shell_cells(side, c->dShellCell, c->totalShell, (size_t)c->L.nCells, c->dF);
   c->nLaunch++;
   c->fLive = false;
@@ -957,7 +968,10 @@ int ibm_solve(ibm_ctx* c, const double* p, const double* tau6, double dt, ibm_so
   int rc = motion_prepare_async(c, dt);
   if (rc) return rc;
   clear_F_on_side(c);
-  if ((rc = ibm_integrate_stress(c, p, tau6, nullptr))) return rc;
+  c->clearFInStress = true;
+  rc = ibm_integrate_stress(c, p, tau6, nullptr);
+  c->clearFInStress = false;
+  if (rc) return rc;
   if ((rc = combine_forces(c))) return rc;
   return motion_advance(c, dt, stats);
 }
@@ -970,7 +984,10 @@ int ibm_solve_device(ibm_ctx* c, const double* dP, const double* dTau6, double d
   if (rc) return rc;
   clear_F_on_side(c);
   ctx_mark(c, "solve:prepared");
-  if ((rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr))) return rc;
+  c->clearFInStress = true;
+  rc = ibm_integrate_stress_device(c, dP, dTau6, nullptr);
+  c->clearFInStress = false;
+  if (rc) return rc;
   ctx_mark(c, "solve:stress done");
   if ((rc = combine_forces(c))) return rc;
   ctx_mark(c, "solve:combined");

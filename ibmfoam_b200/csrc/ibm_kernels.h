@@ -79,6 +79,12 @@ struct V7Prep {
   V7Hdr* hdr = nullptr;       // [cap]
   unsigned* rows = nullptr;   // [cap][rowsCap][3]: first column - i0 | (last column - i0) << 8 | offset of the row << 16; empty row: 0xff
   int rowsCap = 0, cap = 0;
+  // multi-GPU: the records of the instances with local points, compacted in schedule order (pad0 = schedule position, which
+  // indexes `rows`), so that the staged kernels launch one CTA per LOCAL instance instead of one per instance of the directory
+  V7Hdr* hdrLocal = nullptr;  // [cap]
+  int* flag = nullptr;        // [cap + 1]
+  int* flagOff = nullptr;     // [cap + 1]
+  int nLocal = -1;            // records in hdrLocal; -1 = not compacted (one GPU): the kernels take hdr / blockIdx as they are
 };
 // capacities from the shape classes (HOST copies of the class records); false = the fast path does not apply to this cloud
 bool v7_plan(const LatticeDev& L, const ShapeClassDev* hostClasses, int nClasses, int nGeoD, V7Caps& forcing, V7Caps& stress);
@@ -89,12 +95,15 @@ void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
                        const Schedule& s, const V7Caps& capF, const V7Prep& prep);
 // ... and what the marking kernel decides: shell segment, has-local-points flag
 void launch_v7_finish(cudaStream_t st, const InstanceSoA& in, int nInst, const Schedule& s, const V7Prep& prep);
+// ... and, on several ranks, the compacted list of the local records (count to *dCount; the caller reads it back into prep.nLocal)
+void launch_v7_compact(cudaStream_t st, int nInst, Schedule& s, const V7Prep& prep, int* dCount);
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                        const Schedule& s, const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold,
                        const double* S, double dT, double* F, const V7Caps& cap, int* slowList, int* slowCount, int* guard);
 void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const V7Prep& prep, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
-                      const V7Caps& cap, int* slowList, int* slowCount, int* guard);
+                      const V7Caps& cap, int* slowList, int* slowCount, int* guard, double* Fclear = nullptr, const int* shellCell = nullptr);
+// (Fclear: the forcing field, to be re-zeroed at every instance's shell cells on the way - solve() only)
 // second-generation kernels over a device-side list of instances (the ones a staged kernel could not take)
 void launch_forcing_v2_list(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, const int* list,
                             const int* listCount, const int* shellCell, const int* shellJK, const double* U, const double* Uold,

@@ -478,6 +478,26 @@ __global__ void k7_finish(InstanceSoA in, int nInst, const int* __restrict__ ord
   if (in.onLocal[b] == 0) hdr[t].flags &= ~V7_F_LOCAL;
 }
 
+__global__ void k7_local_flags(int nInst, const V7Hdr* __restrict__ hdr, int* __restrict__ flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nInst) return;
+  flag[t] = (t < nInst && (hdr[t].flags & V7_F_LOCAL)) ? 1 : 0;  // (one entry past the end for the scan's total)
+}
+__global__ void k7_local_compact(int nInst, const V7Hdr* __restrict__ hdr, const int* __restrict__ flag, const int* __restrict__ off,
+                                 V7Hdr* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nInst || !flag[t]) return;
+  V7Hdr h = hdr[t];
+  h.pad0 = t;
+  out[off[t]] = h;
+}
+// force / torque partials of every instance <- 0 (the staged stress kernel then only visits the instances with local points)
+__global__ void k7_zero_ft(InstanceSoA in, int nInst, double* __restrict__ Tcorr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nInst) return;
+  for (int q = 0; q < 3; ++q) { in.F[q][t] = 0.0; in.T[q][t] = 0.0; if (Tcorr) Tcorr[3 * (size_t)t + q] = 0.0; }
+}
+
 // row tables of a CTA from its packed record (sets first..last); rowG as build_region7 leaves it.  No barrier inside.
 __device__ __forceinline__ void load_region7(const LatticeDev& L, const Box7& B, const unsigned* __restrict__ packed, int first, int last, int rowsCap,
                                              int* rowBase, int* rowLo, int* rowHi, int* rowG) {
@@ -596,7 +616,7 @@ __device__ __forceinline__ int cells7(const Task7Ctx& X, const int* __restrict__
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const V7Hdr* __restrict__ hdrs,
-             const unsigned* __restrict__ rowsPacked, int rowsCapG,
+             const unsigned* __restrict__ rowsPacked, int rowsCapG, int identity,
              const int* __restrict__ shellCell, const int* __restrict__ shellJK, const double* __restrict__ U,
              const double* __restrict__ Uold, const double* __restrict__ S, double dT, double* __restrict__ F, V7Caps cap,
              int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
@@ -643,7 +663,9 @@ k_forcing_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSo
   const V3 vp{in.v[0][b], in.v[1][b], in.v[2][b]}, omv{in.om[0][b], in.om[1][b], in.om[2][b]};
   const int off = h.shellOff;
   const Tab7 tab = tab7_load(sc, tabD, cap);
-  load_region7(L, B, rowsPacked + (size_t)blockIdx.x * rowsCapG * 3, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
+  // (compacted launch on several ranks: the record carries its schedule position; on one GPU it is blockIdx, known at once)
+  const int pos = identity ? (int)blockIdx.x : h.pad0;
+  load_region7(L, B, rowsPacked + (size_t)pos * rowsCapG * 3, 0, 2, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
   // elemRow: row of every element of set 0 (the staging loop runs over the elements of the widest set)
   if ((int)threadIdx.x < B.by * B.bz) {
     const int r = threadIdx.x;
@@ -786,15 +808,26 @@ __device__ __forceinline__ int stress_points7(const Str7Ctx& X, double* acc) {
 template <int NT, int MINB, bool SOA>
 __global__ void __launch_bounds__(NT, MINB)
 k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, const V7Hdr* __restrict__ hdrs,
-            const unsigned* __restrict__ rowsPacked, int rowsCapG,
+            const unsigned* __restrict__ rowsPacked, int rowsCapG, int identity,
             const double* __restrict__ P, const double* __restrict__ Tau, double pRefOverRho, double rhoRef, double* __restrict__ Tcorr,
-            V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag) {
+            V7Caps cap, int* __restrict__ slowList, int* __restrict__ slowCount, int* __restrict__ guardFlag,
+            double* __restrict__ Fclear, const int* __restrict__ shellCell) {
   extern __shared__ double smem7[];
   __shared__ double red[NT / 32][9];
   if ((int)blockIdx.x >= nInst) return;
   const V7Hdr h = hdrs[blockIdx.x];
   const int b = h.b;
   const bool on = (h.flags & V7_F_LOCAL) != 0;
+  if (Fclear) {
+    // solve(): the consumer of the forcing field is done with it, and the field has to be zero again at the cells the last
+    // forcing() wrote before the shell lists are rebuilt.  Every instance re-zeroes its own shell cells here - stores that
+    // nobody waits for - instead of a separate kernel over all of them beside this one (0.87 ms of contended side-stream work).
+    const size_t C = (size_t)L.nCells;
+    for (int q = threadIdx.x; q < h.nShell; q += NT) {
+      const int lat = __ldg(shellCell + h.shellOff + q);
+      Fclear[lat] = 0.0; Fclear[C + lat] = 0.0; Fclear[2 * C + lat] = 0.0;
+    }
+  }
   const V7Layout lay = v7_layout(cap);
   char* base = (char*)smem7;
   double* planes = (double*)(base + lay.planes);
@@ -837,7 +870,8 @@ k_stress_v7(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA
 #pragma unroll
     for (int q = 0; q < 9; ++q) rot9[q] = __ldg(in.rot + 9 * (size_t)b + q);
     const Tab7 tab = tab7_load(sc, tabD, cap);
-    load_region7(L, B, rowsPacked + (size_t)blockIdx.x * rowsCapG * 3, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
+    const int pos = identity ? (int)blockIdx.x : h.pad0;
+    load_region7(L, B, rowsPacked + (size_t)pos * rowsCapG * 3, 1, 1, cap.rowsCap, rowBase, rowLo, rowHi, rowG);
     const int* loB = rowLo + cap.rowsCap; const int* hiB = rowHi + cap.rowsCap; const int* baseB = rowBase + cap.rowsCap;
     if ((int)threadIdx.x < B.by * B.bz) {
       const int r = threadIdx.x;
@@ -997,12 +1031,17 @@ int v7_prep_alloc(V7Prep& p, int cap, int rowsCap) {
   if (cap <= 0 || rowsCap <= 0) return 0;
   if (cudaMalloc(&p.hdr, (size_t)cap * sizeof(V7Hdr)) != cudaSuccess) return 1;
   if (cudaMalloc(&p.rows, (size_t)cap * rowsCap * 3 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p.hdr); p.hdr = nullptr; return 1; }
-  p.cap = cap; p.rowsCap = rowsCap;
+  if (cudaMalloc(&p.hdrLocal, (size_t)cap * sizeof(V7Hdr)) != cudaSuccess || cudaMalloc(&p.flag, ((size_t)cap + 1) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&p.flagOff, ((size_t)cap + 1) * sizeof(int)) != cudaSuccess) { v7_prep_free(p); return 1; }
+  p.cap = cap; p.rowsCap = rowsCap; p.nLocal = -1;
   return 0;
 }
 void v7_prep_free(V7Prep& p) {
   if (p.hdr) cudaFree(p.hdr);
   if (p.rows) cudaFree(p.rows);
+  if (p.hdrLocal) cudaFree(p.hdrLocal);
+  if (p.flag) cudaFree(p.flag);
+  if (p.flagOff) cudaFree(p.flagOff);
   p = V7Prep{};
 }
 void launch_v7_prepare(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
@@ -1016,6 +1055,13 @@ void launch_v7_finish(cudaStream_t st, const InstanceSoA& in, int nInst, const S
   k7_finish<<<(nInst + 255) / 256, 256, 0, st>>>(in, nInst, s.order, prep.hdr);
 }
 
+void launch_v7_compact(cudaStream_t st, int nInst, Schedule& s, const V7Prep& prep, int* dCount) {
+  if (nInst <= 0) { cudaMemsetAsync(dCount, 0, sizeof(int), st); return; }
+  k7_local_flags<<<(nInst + 256) / 256, 256, 0, st>>>(nInst, prep.hdr, prep.flag);
+  launch_exclusive_scan_total(st, s, prep.flag, prep.flagOff, nInst, dCount);
+  k7_local_compact<<<(nInst + 255) / 256, 256, 0, st>>>(nInst, prep.hdr, prep.flag, prep.flagOff, prep.hdrLocal);
+}
+
 template <int NT, int MINB>
 static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                           const V7Prep& prep, const int* shellCell, const int* shellJK, const double* U, const double* Uold, const double* S,
@@ -1026,19 +1072,28 @@ static void forcing_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClass
     cudaFuncSetAttribute(k_forcing_v7<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_forcing_v7<NT, MINB><<<nInst, NT, sm, st>>>(L, classes, in, nInst, prep.hdr, prep.rows, prep.rowsCap, shellCell, shellJK, U, Uold, S, dT, F, cap, slowList, slowCount, guard);
+  const bool ident = prep.nLocal < 0;
+  const int n = ident ? nInst : prep.nLocal;
+  if (n > 0)
+    k_forcing_v7<NT, MINB><<<n, NT, sm, st>>>(L, classes, in, n, ident ? prep.hdr : prep.hdrLocal, prep.rows, prep.rowsCap, ident ? 1 : 0, shellCell, shellJK,
+                                             U, Uold, S, dT, F, cap, slowList, slowCount, guard);
 }
 template <int NT, int MINB, bool SOA>
 static void stress_v7_nt(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, const V7Prep& prep,
                          const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr, const V7Caps& cap, int* slowList,
-                         int* slowCount, int* guard, int sm) {
+                         int* slowCount, int* guard, int sm, double* Fclear, const int* shellCell) {
   static PerDeviceOnce attr;
   static int attrBytes = 0;
   if (attr.first() || sm > attrBytes) {
     cudaFuncSetAttribute(k_stress_v7<NT, MINB, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     attrBytes = std::max(attrBytes, sm);
   }
-  k_stress_v7<NT, MINB, SOA><<<nInst, NT, sm, st>>>(L, classes, in, nInst, prep.hdr, prep.rows, prep.rowsCap, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard);
+  const bool ident = prep.nLocal < 0;
+  const int n = ident ? nInst : prep.nLocal;
+  if (!ident) k7_zero_ft<<<(nInst + 255) / 256, 256, 0, st>>>(in, nInst, Tcorr);  // the instances without local points contribute zero partials
+  if (n > 0)
+    k_stress_v7<NT, MINB, SOA><<<n, NT, sm, st>>>(L, classes, in, n, ident ? prep.hdr : prep.hdrLocal, prep.rows, prep.rowsCap, ident ? 1 : 0, P, Tau, pRefOverRho,
+                                                 rhoRef, Tcorr, cap, slowList, slowCount, guard, Fclear, shellCell);
 }
 
 void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
@@ -1062,7 +1117,7 @@ void launch_forcing_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev
 
 void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                       const Schedule& s, const V7Prep& prep, const double* P, const double* Tau, double pRefOverRho, double rhoRef, double* Tcorr,
-                      const V7Caps& cap, int* slowList, int* slowCount, int* guard) {
+                      const V7Caps& cap, int* slowList, int* slowCount, int* guard, double* Fclear, const int* shellCell) {
   if (nInst <= 0) return;
   (void)s;
   const int sm = v7_layout(cap).total;
@@ -1071,8 +1126,8 @@ void launch_stress_v7(cudaStream_t st, const LatticeDev& L, const ShapeClassDev*
   const bool three = 3 * (sm + 1024) <= 228 * 1024;
   static int soa = -1;
   if (soa < 0) { const char* e = getenv("IBM_V7_STRESS_SOA"); soa = e ? atoi(e) : 0; }
-#define IBM_S7(NT_, MB_) do { if (soa) stress_v7_nt<NT_, MB_, true>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); \
-                              else stress_v7_nt<NT_, MB_, false>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm); } while (0)
+#define IBM_S7(NT_, MB_) do { if (soa) stress_v7_nt<NT_, MB_, true>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm, Fclear, shellCell); \
+                              else stress_v7_nt<NT_, MB_, false>(st, L, classes, in, nInst, prep, P, Tau, pRefOverRho, rhoRef, Tcorr, cap, slowList, slowCount, guard, sm, Fclear, shellCell); } while (0)
   if (nt == 320) IBM_S7(320, 2);
   else if (nt == 192) { if (three) IBM_S7(192, 3); else IBM_S7(192, 2); }
   else if (nt == 224) { if (three) IBM_S7(224, 3); else IBM_S7(224, 2); }
