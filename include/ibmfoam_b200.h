@@ -201,7 +201,21 @@ int ibm_set_kernel_variant(ibm_ctx* ctx, int forcingVariant, int stressVariant);
 /* diagnostic counters: "loop5_active_instances" (of the last ibm_advance with the quiet/active split, else -1), "loop5_fallbacks",
  * "forcing_variant", "stress_variant", "mark_variant" (what is in force, also when set through the IBM_* environment switches) */
 int ibm_get_counter(ibm_ctx* ctx, const char* name, long long* value);
-int ibm_set_option(ibm_ctx* ctx, const char* name, int value); /* "graph_loop5" (default 1): sub-step launch sequence replayed as a CUDA graph; "fused_loop5" (default 0): one persistent cooperative kernel; "active_loop5" (default 0): quiet / active split of a fluid step (same results; instances that cannot interact integrate all sub-steps in one kernel), "fused_active_loop5" (default 0): with the split, the active list's sub-steps in one persistent cooperative kernel, "active_loop5_safety_ppm" (default 2000000): displacement-budget factor; "mark_variant" (default 0): 1 = second marking kernel (same lists); "collision_model" (default 0): see ibm_set_real_option */
+/* Switches (defaults are what bench.py measures; every schedule of loop 5 gives the same results, bit for bit):
+ *   "active_loop5" (1)    quiet / active split of a fluid step: instances that provably cannot touch anything integrate all
+ *                         their sub-steps in one kernel; budgets are checked, a violation redoes the step unsplit
+ *   "cluster_loop5" (1)   with the split: every group of possibly interacting instances runs all its sub-steps in one block
+ *   "async_prepare" (1)   ibm_solve: the classification of the coming advance on a side stream beside the stress integral
+ *   "owned_loop5" (1)     several ranks: a rank advances the instances and groups whose centre lies in its slab; states and
+ *                         new periodic copies are exchanged once per fluid step (0: every rank advances everything)
+ *   "graph_loop5" (1)     the general per-sub-step launch sequence (the fallback) replayed as a CUDA graph
+ *   "fused_loop5" (0), "fused_active_loop5" (0)   that sequence / the active list as one persistent cooperative kernel
+ *   "active_loop5_safety_ppm" (2000000)   displacement-budget factor in parts per million
+ *   "mark_variant" (1)    1 = k1_mark2, 0 = k1_mark (same lists)
+ *   "collision_model" (0) see ibm_set_real_option
+ * Counters (ibm_get_counter) beyond those above: "loop5_cluster_steps", "loop5_owned_steps", "loop5_cluster_flags",
+ * "loop5_block_substeps", "loop5_general_substeps", "v7_ok", "v7_slow_count", "h2d_pinned_bytes", "h2d_staged_bytes". */
+int ibm_set_option(ibm_ctx* ctx, const char* name, int value);
 
 /* EXTENSION without a counterpart in the reference (the reference names a soft-sphere model in
  * src/particleCloud/Make/files but ships none): ibm_set_option(ctx, "collision_model", 1) replaces the hard-sphere impulse of
