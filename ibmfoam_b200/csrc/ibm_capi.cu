@@ -317,7 +317,18 @@ int ctx_update(ibm_ctx* c) {
       if (c->v7ok) { launch_v7_prepare(c->updSide, c->L, c->dClasses, c->in, c->nInst, c->sched, c->v7capF, c->v7prep); c->nLaunch++; }
     }
     IBM_CUDA(c, cudaEventRecord(c->updJoin, c->updSide));
-    launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant);
+    const bool nearOnly = comm_ranks(c) > 1 && c->markVariant == 1 && c->nInst > 0;
+    if (nearOnly) {
+      if (!c->dNearFlag) {
+        IBM_CUDA(c, cudaMalloc(&c->dNearFlag, ((size_t)c->cap + 1) * sizeof(int)));
+        IBM_CUDA(c, cudaMalloc(&c->dNearOff, ((size_t)c->cap + 1) * sizeof(int)));
+        IBM_CUDA(c, cudaMalloc(&c->dNearList, ((size_t)c->cap + 1) * sizeof(int)));
+      }
+      launch_k1_far(c->stream, c->L, c->dClasses, c->in, c->nInst, c->sched, c->dNearFlag, c->dNearOff, c->dNearList, c->dScal + 6);
+      c->nLaunch += 4;
+    }
+    launch_k1_mark(c->stream, c->L, c->dClasses, c->in, c->nInst, c->dShellCell, c->dShellJK, c->shellCap, c->dScal + 1, c->dScal + 4, c->markVariant,
+                   nearOnly ? c->dNearList : nullptr, nearOnly ? c->dScal + 6 : nullptr);
     ctx_mark(c, "update:marked");
     if (comm_ranks(c) > 1 && c->nInst > 0) {
       // the on-mesh status of an instance is a property of the whole mesh: sum the point counts over the slabs.  The shell
@@ -858,7 +869,8 @@ int ibm_destroy(ibm_ctx* c) {
   for (auto p : c->classPools) cudaFree(p);
   for (auto& ph : c->patches) { cudaFree(ph.dCf); cudaFree(ph.dSf); cudaFree(ph.dMagSf); }
   void* frees[] = {c->dLatToCell, c->dCellToLat, c->dClasses, c->dShellCell, c->dShellJK, c->dScal, c->dKeep, c->dKeepOff,
-                   c->dU, c->dUold, c->dS, c->dF, c->dP, c->dTau, c->dI, c->dStage, c->dTcorr, c->dSlowList};
+                   c->dU, c->dUold, c->dS, c->dF, c->dP, c->dTau, c->dI, c->dStage, c->dTcorr, c->dSlowList,
+                   c->dNearFlag, c->dNearOff, c->dNearList};
   for (void* p : frees) if (p) cudaFree(p);
   if (c->hScal) cudaFreeHost(c->hScal);
   if (c->hPinned) cudaFreeHost(c->hPinned);

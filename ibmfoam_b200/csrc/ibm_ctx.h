@@ -86,6 +86,7 @@ struct ibm_ctx {
   int forcingVariant = 7, stressVariant = 7;
   bool v7ok = false;              // every shape class can take the seventh-generation kernels (no ellipse, tables + region fit)
   ibm::V7Caps v7capF{}, v7capS{};  // shared-memory capacities of their launches
+  int *dNearFlag = nullptr, *dNearOff = nullptr, *dNearList = nullptr;  // [cap + 1]: marking over the instances near the slab (several ranks)
   bool clearFInStress = false;     // set by ibm_solve around its stress integral: the staged stress kernel re-zeroes the forcing field
   cudaStream_t updSide = nullptr;  // ctx_update: Morton order + launch records beside the marking kernel
   cudaEvent_t updFork = nullptr, updJoin = nullptr;

@@ -22,7 +22,12 @@ struct PerDeviceOnce {
 // ---- ibm_kernels_ref.cu (compiled with -fmad=false) ----
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant = 0);
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant = 0, const int* nearList = nullptr,
+                    const int* nearCount = nullptr);
+struct Schedule;
+// several ranks: the instances far from the slab settled by one thread each, the others listed for the marking kernel (variant 1)
+void launch_k1_far(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, Schedule& s,
+                   int* nearFlag, int* nearOff, int* nearList, int* dNearCount);
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst);
 void launch_k1_fill(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
                     int* shellCell, int* shellJK);

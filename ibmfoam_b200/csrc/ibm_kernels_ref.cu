@@ -272,15 +272,49 @@ __device__ __forceinline__ void split_box_index(int t, int bi, int bij, float rb
   if (i < 0) { --j; i += bi; } else if (i >= bi) { ++j; i -= bi; }
 }
 
+// Several ranks: most instances of the directory are far from a rank's slab.  One THREAD per instance settles those (what
+// the marking kernel writes for an instance whose outer layer cannot reach the owned planes: rotation matrix, the ellipse's
+// wrapped angle, zero counts) and flags the others; the marking kernel then runs over the compacted list of the flagged
+// ones (its grid is still the directory - the list length lives on the device - but a block beyond the list leaves after
+// one load instead of a class record, a centre and three sincos).
+__global__ void k1_far(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst, int* __restrict__ nearFlag) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nInst) return;
+  if (b == nInst) { nearFlag[b] = 0; return; }  // (one entry past the end for the scan's total)
+  const ShapeClassDev& sc = classes[in.cls[b]];
+  const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
+  double rOut = sc.Rbound + sc.delta;
+  rOut += 1e-9 * (fabs(cx) + fabs(cy) + fabs(cz) + rOut) + 1e-300;
+  const bool outside = cx + rOut < L.ox || cx - rOut > L.ox + L.nx * L.dx || cy + rOut < L.oy || cy - rOut > L.oy + L.ny * L.dy ||
+                       cz + rOut < own_zlo(L) || cz - rOut > own_zhi(L);
+  nearFlag[b] = outside ? 0 : 1;
+  if (!outside) return;
+  double r9[9];
+  set_rotation_matrix(in.th[0][b], in.th[1][b], in.th[2][b], r9);
+  for (int q = 0; q < 9; ++q) in.rot[9 * (size_t)b + q] = r9[q];
+  if (sc.kind == 2) {
+    double tz = in.th[2][b];
+    if (tz < 0) tz = xadd(tz, IBM_TWOPI);
+    if (tz > IBM_TWOPI) tz = xsub(tz, IBM_TWOPI);
+    in.th[2][b] = tz;
+  }
+  in.nShell[b] = 0; in.shellOff[b] = 0; in.nPtsOnMesh[b] = 0; in.onLocal[b] = 0;
+}
+__global__ void k1_near_list(int nInst, const int* __restrict__ nearFlag, const int* __restrict__ nearOff, int* __restrict__ nearList) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nInst && nearFlag[b]) nearList[nearOff[b]] = b;
+}
+
 __global__ void k1_mark2(LatticeDev L, const ShapeClassDev* __restrict__ classes, InstanceSoA in, int nInst,
                          int* __restrict__ shellCell, int* __restrict__ shellJK, int shellCap, int* __restrict__ cursor,
-                         int* __restrict__ overflow) {
+                         int* __restrict__ overflow, const int* __restrict__ nearList, const int* __restrict__ nearCount) {
   __shared__ int sm[32];
   __shared__ double srot[9];
   __shared__ int listCell[K1_LIST], listJK[K1_LIST];
   __shared__ int nList, segOff, nDirect;
-  const int b = blockIdx.x;
-  if (b >= nInst) return;
+  if ((int)blockIdx.x >= nInst) return;
+  if (nearList && (int)blockIdx.x >= *nearCount) return;  // (block-uniform)
+  const int b = nearList ? nearList[blockIdx.x] : (int)blockIdx.x;
   const ShapeClassDev sc = classes[in.cls[b]];
   const double cx = in.c[0][b], cy = in.c[1][b], cz = in.c[2][b];
   // An instance whose outer layer cannot reach the owned planes (other slabs' instances on a multi-GPU run: 7 of 8 on eight
@@ -737,10 +771,19 @@ __global__ void k_stress_ref(LatticeDev L, const ShapeClassDev* __restrict__ cla
 void launch_k1_count(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
   if (nInst > 0) k1_count<<<nInst, 128, 0, st>>>(L, classes, in, nInst);
 }
-void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
-                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant) {
+void launch_k1_far(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst, Schedule& s,
+                   int* nearFlag, int* nearOff, int* nearList, int* dNearCount) {
   if (nInst <= 0) return;
-  if (variant == 1) k1_mark2<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
+  k1_far<<<(nInst + 256) / 256, 256, 0, st>>>(L, classes, in, nInst, nearFlag);
+  launch_exclusive_scan_total(st, s, nearFlag, nearOff, nInst, dNearCount);
+  k1_near_list<<<(nInst + 255) / 256, 256, 0, st>>>(nInst, nearFlag, nearOff, nearList);
+}
+
+void launch_k1_mark(cudaStream_t st, const LatticeDev& L, const ShapeClassDev* classes, const InstanceSoA& in, int nInst,
+                    int* shellCell, int* shellJK, int shellCap, int* cursor, int* overflow, int variant, const int* nearList,
+                    const int* nearCount) {
+  if (nInst <= 0) return;
+  if (variant == 1) k1_mark2<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow, nearList, nearCount);
   else k1_mark<<<nInst, 128, 0, st>>>(L, classes, in, nInst, shellCell, shellJK, shellCap, cursor, overflow);
 }
 void launch_k1_status(cudaStream_t st, const LatticeDev& Lg, const ShapeClassDev* classes, const InstanceSoA& in, int nInst) {
