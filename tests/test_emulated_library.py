@@ -45,6 +45,9 @@ SUBSET = [
     "tests/test_gpu_motion.py::test_two_spheres_head_on_closed_form[fused]",
     "tests/test_zzz_gpu_soft_sphere.py",
     "tests/test_zzz_gpu_mark_variant.py",
+    # several ranks (in-process transport): near-slab marking list, compacted launches, halo
+    "tests/test_gpu_multirank.py::test_loops_1_to_4_match_decomposed_oracle[2]",
+    "tests/test_gpu_multirank.py::test_halo_makes_results_decomposition_independent[2]",
 ]
 
 
