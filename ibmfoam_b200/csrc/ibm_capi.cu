@@ -1014,32 +1014,34 @@ int ibm_n_instances(ibm_ctx* c, int* n) {
   return IBM_OK;
 }
 
+// the accessor records assembled on the device (one thread per instance), so that the host gets them with ONE copy
+__global__ void k_pack_particle_state(InstanceSoA in, const ShapeClassDev* __restrict__ classes, int n, ibm_particle_state* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ibm_particle_state s;
+  s.index = in.index[i]; s.copy = in.copy[i]; s.active = in.active[i]; s.onMesh = in.onMesh[i];
+  for (int q = 0; q < 3; ++q) {
+    s.center[q] = in.c[q][i]; s.theta[q] = in.th[q][i]; s.v[q] = in.v[q][i]; s.omega[q] = in.om[q][i];
+    s.F[q] = in.F[q][i]; s.T[q] = in.T[q][i];
+  }
+  s.rho = in.rho[i]; s.age = in.age[i];
+  s.nShell = in.nShell[i]; s.N = classes[in.cls[i]].N;
+  out[i] = s;
+}
+
 int ibm_get_particles(ibm_ctx* c, ibm_particle_state* out) {
   if (!c || (!out && c->nInst > 0)) return ctx_fail(c, IBM_E_ARG, "ibm_get_particles: null argument");
   cudaSetDevice(c->device);
   const int n = c->nInst;
   if (n == 0) return IBM_OK;
+  const size_t bytes = (size_t)n * sizeof(ibm_particle_state);
+  int rc = ctx_ensure_stage(c, (bytes + sizeof(double) - 1) / sizeof(double));
+  if (rc) return rc;
+  ibm_particle_state* d = (ibm_particle_state*)c->dStage;
+  k_pack_particle_state<<<(n + 127) / 128, 128, 0, c->stream>>>(c->in, c->dClasses, n, d);
+  c->nLaunch++;
+  IBM_CUDA(c, cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, c->stream));
   IBM_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<int> iv(n);
-  std::vector<double> dv(n);
-  auto dnI = [&](const int* src, auto f) { cudaMemcpy(iv.data(), src, n * sizeof(int), cudaMemcpyDeviceToHost); for (int i = 0; i < n; ++i) f(i, iv[i]); };
-  auto dnD = [&](const double* src, auto f) { cudaMemcpy(dv.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost); for (int i = 0; i < n; ++i) f(i, dv[i]); };
-  dnI(c->in.index, [&](int i, int v) { out[i].index = v; });
-  dnI(c->in.copy, [&](int i, int v) { out[i].copy = v; });
-  dnI(c->in.active, [&](int i, int v) { out[i].active = v; });
-  dnI(c->in.onMesh, [&](int i, int v) { out[i].onMesh = v; });
-  dnI(c->in.nShell, [&](int i, int v) { out[i].nShell = v; });
-  dnI(c->in.cls, [&](int i, int v) { out[i].N = c->classes[v].dev.N; });
-  for (int q = 0; q < 3; ++q) {
-    dnD(c->in.c[q], [&](int i, double v) { out[i].center[q] = v; });
-    dnD(c->in.th[q], [&](int i, double v) { out[i].theta[q] = v; });
-    dnD(c->in.v[q], [&](int i, double v) { out[i].v[q] = v; });
-    dnD(c->in.om[q], [&](int i, double v) { out[i].omega[q] = v; });
-    dnD(c->in.F[q], [&](int i, double v) { out[i].F[q] = v; });
-    dnD(c->in.T[q], [&](int i, double v) { out[i].T[q] = v; });
-  }
-  dnD(c->in.rho, [&](int i, double v) { out[i].rho = v; });
-  dnD(c->in.age, [&](int i, double v) { out[i].age = v; });
   IBM_CUDA(c, cudaGetLastError());
   return IBM_OK;
 }
