@@ -106,6 +106,8 @@ SYMBOLS = {
     "ibm_comm_unique_id_bytes": (C.c_int, []),
     "ibm_comm_get_unique_id": (C.c_int, [_VP]),
     "ibm_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "ibm_lattice_from_arrays": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "ibm_set_slab": (C.c_int, [_VP, C.c_int, C.c_int]),
     "ibm_set_slab_halo": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ibm_comm_info": (C.c_int, [_VP, c_int_p, c_int_p]),

@@ -880,6 +880,80 @@ int ibm_destroy(ibm_ctx* c) {
   return IBM_OK;
 }
 
+int ibm_lattice_from_arrays(const double* C, int nCells, int nGeometricD, int nPatches, const double* const* patchCf, const int* patchNFaces,
+                            int* n, double* origin, double* delta, int* patchSide, int* latticeToCell, int* identity) {
+  if (!C || nCells <= 0 || !n || !origin || !delta || (nPatches > 0 && (!patchCf || !patchNFaces || !patchSide)))
+    return ctx_fail(nullptr, IBM_E_ARG, "ibm_lattice_from_arrays: bad arguments");
+  double lo[3], hi[3], step[3];
+  for (int d = 0; d < 3; ++d) { lo[d] = 1e300; hi[d] = -1e300; }
+  for (int c = 0; c < nCells; ++c)
+    for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], C[3 * (size_t)c + d]); hi[d] = std::max(hi[d], C[3 * (size_t)c + d]); }
+  const double span = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-300));
+  long long nn[3];
+  for (int d = 0; d < 3; ++d) {
+    // spacing = the smallest centre coordinate above the lowest one
+    double s = 1e300;
+    const double tol = 1e-9 * span;
+    for (int c = 0; c < nCells; ++c) { const double x = C[3 * (size_t)c + d] - lo[d]; if (x > tol && x < s) s = x; }
+    if (s > 1e299) { step[d] = 0.0; nn[d] = 1; continue; }   // one layer of cells along d
+    step[d] = s;
+    nn[d] = (long long)std::floor((hi[d] - lo[d]) / s + 0.5) + 1;
+  }
+  if (nn[0] * nn[1] * nn[2] != (long long)nCells)
+    return ctx_fail(nullptr, IBM_E_UNSUPPORTED, "ibm_lattice_from_arrays: the cell centres are not a uniform lattice (graded or unstructured mesh)");
+  // a single layer has no spacing of its own: the caller's empty direction (2-D cases); take the spacing of x
+  for (int d = 0; d < 3; ++d)
+    if (nn[d] == 1) step[d] = (nGeometricD == 2 && step[0] > 0) ? step[0] : (step[0] > 0 ? step[0] : 1.0);
+  std::vector<char> seen((size_t)nCells, 0);
+  bool ident = true;
+  for (int c = 0; c < nCells; ++c) {
+    long long idx[3];
+    for (int d = 0; d < 3; ++d) {
+      const double t = (C[3 * (size_t)c + d] - lo[d]) / step[d];
+      idx[d] = (long long)std::floor(t + 0.5);
+      if (idx[d] < 0 || idx[d] >= nn[d] || std::fabs(t - (double)idx[d]) > 1e-6)
+        return ctx_fail(nullptr, IBM_E_UNSUPPORTED, "ibm_lattice_from_arrays: the cell centres are not a uniform lattice (graded or unstructured mesh)");
+    }
+    const size_t lat = (size_t)(idx[0] + nn[0] * (idx[1] + nn[1] * idx[2]));
+    if (seen[lat]) return ctx_fail(nullptr, IBM_E_UNSUPPORTED, "ibm_lattice_from_arrays: two cells share a lattice position");
+    seen[lat] = 1;
+    if (latticeToCell) latticeToCell[lat] = c;
+    ident = ident && lat == (size_t)c;
+  }
+  for (int d = 0; d < 3; ++d) { n[d] = (int)nn[d]; delta[d] = step[d]; origin[d] = lo[d] - 0.5 * step[d]; }
+  // the thickness of a single layer is not in the cell centres: it is the distance between the two patches that bound it
+  for (int d = 0; d < 3; ++d) {
+    if (nn[d] != 1) continue;
+    double below = -1e300, above = 1e300;
+    for (int p = 0; p < nPatches; ++p) {
+      const int nf = patchNFaces[p];
+      if (nf <= 0) continue;
+      const double v = patchCf[p][d];
+      bool flat = true;
+      for (int f = 1; f < nf && flat; ++f) flat = std::fabs(patchCf[p][3 * (size_t)f + d] - v) <= 1e-9 * span;
+      if (!flat) continue;
+      if (v < lo[d]) below = std::max(below, v);
+      if (v > lo[d]) above = std::min(above, v);
+    }
+    if (below > -1e299 && above < 1e299) { origin[d] = below; delta[d] = above - below; }
+  }
+  if (identity) *identity = ident ? 1 : 0;
+  for (int p = 0; p < nPatches; ++p) {
+    patchSide[p] = -1;
+    const int nf = patchNFaces[p];
+    if (nf <= 0) { patchSide[p] = IBM_XMIN; continue; }  // (an empty patch hits nothing: any side)
+    for (int side = 0; side < 6 && patchSide[p] < 0; ++side) {
+      const int d = side / 2;
+      const double plane = (side & 1) ? origin[d] + n[d] * delta[d] : origin[d];
+      bool all = true;
+      for (int f = 0; f < nf && all; ++f) all = std::fabs(patchCf[p][3 * (size_t)f + d] - plane) <= 1e-6 * delta[d];
+      if (all) patchSide[p] = side;
+    }
+    if (patchSide[p] < 0) return ctx_fail(nullptr, IBM_E_UNSUPPORTED, "ibm_lattice_from_arrays: a boundary patch does not lie on one side of the lattice");
+  }
+  return IBM_OK;
+}
+
 int ibm_set_slab_halo(ibm_ctx* c, int k0, int k1, int halo, int* localK0, int* localK1) {
   if (!c) return IBM_E_ARG;
   if (c->cap != 0) return ctx_fail(c, IBM_E_STATE, "ibm_set_slab: call before ibm_set_particles");

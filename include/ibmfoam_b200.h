@@ -70,6 +70,17 @@ typedef struct {
   const ibm_patch_desc* patches;
 } ibm_mesh_desc;
 
+/* The reference reads its geometry from polyMesh (mesh.C(), mesh.Cf(): particleShape.C:39-66, sphere.C:208-216).  This helper
+ * recognises the uniform lattice in those raw arrays, so that a caller need not describe it: n[3], origin[3], delta[3]
+ * from the cell centres of any mesh whose cells are the cells of a uniform hex lattice, in ANY numbering (one blockMesh
+ * block, several, renumbered); latticeToCell[nCells] (may be NULL) receives the caller's cell id of every lattice cell and
+ * *identity tells whether it is the identity (then ibm_mesh_desc.latticeToCell may stay NULL); patchSide[p] the lattice side
+ * (IBM_XMIN..IBM_ZMAX) the face centres patchCf[p][patchNFaces[p]][3] lie on.  Host-only, no CUDA call.  IBM_E_UNSUPPORTED:
+ * the centres are not a uniform lattice (graded or unstructured mesh) or a patch does not lie on one side. */
+int ibm_lattice_from_arrays(const double* cellCentres, int nCells, int nGeometricD, int nPatches, const double* const* patchCf,
+                            const int* patchNFaces, int* n, double* origin, double* delta, int* patchSide, int* latticeToCell,
+                            int* identity);
+
 /* constant/IBMProperties top level + g (particleCloud.C:989-1005, 1034-1036; createFields.H:1) */
 typedef struct {
   int moving, rotating, coupled;

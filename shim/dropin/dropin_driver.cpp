@@ -15,6 +15,7 @@
 // case file (text): see tests/test_zz_gpu_shim_dropin.py::write_case.
 #include "particleCloud.H"
 
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 
@@ -63,13 +64,18 @@ int main(int argc, char** argv)
         flow.add("UInf", vector(UInf[0], UInf[1], UInf[2]));
         flow.add("rhoInf", scalar(rhoInf));
         flow.add("pInf", scalar(pInf));
-        dictionary& lat = IBMProperties.addDict("lattice");   // read by the shim only (the numbers of system/blockMeshDict)
-        lat.add("n", vector(nx, ny, nz));
-        lat.add("origin", vector(origin[0], origin[1], origin[2]));
-        lat.add("delta", vector(delta[0], delta[1], delta[2]));
-        std::vector<std::string> sides;
-        for (int p = 0; p < nPatches; ++p) sides.push_back(sideName[side[p]]);
-        lat.add("patchSides", sides);
+        if (!std::getenv("DROPIN_NO_LATTICE"))
+        {
+            // optional entry, read by the shim only (the numbers of system/blockMeshDict); without it the shim hands polyMesh's
+            // cell and face centres to ibm_lattice_from_arrays, which is what the comparison test does as well
+            dictionary& lat = IBMProperties.addDict("lattice");
+            lat.add("n", vector(nx, ny, nz));
+            lat.add("origin", vector(origin[0], origin[1], origin[2]));
+            lat.add("delta", vector(delta[0], delta[1], delta[2]));
+            std::vector<std::string> sides;
+            for (int p = 0; p < nPatches; ++p) sides.push_back(sideName[side[p]]);
+            lat.add("patchSides", sides);
+        }
         for (int i = 0; i < nPart; ++i)
         {
             int kind, nTheta;

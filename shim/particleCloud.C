@@ -20,26 +20,57 @@ void Foam::particleCloud::check(const int rc, const char* where) const
 
 void Foam::particleCloud::describeMesh(ibm_mesh_desc& md, List<ibm_patch_desc>& pats, labelList& blocks) const
 {
-    // IBMProperties { lattice { n (nx ny nz); origin (x y z); delta (dx dy dz); blocks ((i0 i1 j0 j1 k0 k1) ...); } }
-    const dictionary& lat = dict_.subDict("lattice");
-    const labelVector n(lat.lookup("n"));
-    const vector origin(lat.lookup("origin")), delta(lat.lookup("delta"));
-    md.nx = n.x(); md.ny = n.y(); md.nz = n.z();
-    forAll(origin, d) { md.origin[d] = origin[d]; md.delta[d] = delta[d]; }
-    if (lat.found("blocks"))
-    {
-        List<labelList> b(lat.lookup("blocks"));
-        blocks.setSize(6*b.size());
-        forAll(b, i) forAll(b[i], j) blocks[6*i + j] = b[i][j];
-    }
-    md.nBlocks = blocks.size()/6;
-    md.blocks = blocks.size() ? blocks.begin() : nullptr;
-    md.latticeToCell = nullptr;
-
-    // boundary patches with their OpenFOAM face arrays (particleIBM.C:466-470, 504-508)
     const fvBoundaryMesh& bm = mesh_.boundary();
     pats.setSize(bm.size());
-    const wordList sides(lat.lookup("patchSides"));   // one of xMin xMax yMin yMax zMin zMax per patch
+    labelList sideOf(bm.size(), label(0));
+    md.nBlocks = 0; md.blocks = nullptr; md.latticeToCell = nullptr;
+    if (!dict_.found("lattice"))
+    {
+        // What the reference has: polyMesh's own arrays (mesh.C(), mesh.Cf(): particleShape.C:39-66).  The library recognises
+        // the uniform lattice in them, in whatever order blockMesh numbered the cells, and refuses anything else.
+        const vectorField& cc = mesh_.C().primitiveField();
+        List<const double*> cf(bm.size());
+        labelList nf(bm.size());
+        forAll(bm, patchi)
+        {
+            cf[patchi] = reinterpret_cast<const double*>(mesh_.Cf().boundaryField()[patchi].begin());
+            nf[patchi] = bm[patchi].size();
+        }
+        int n[3], identity = 1;
+        latticeToCell_.setSize(cc.size());
+        check(ibm_lattice_from_arrays(reinterpret_cast<const double*>(cc.begin()), cc.size(), mesh_.nGeometricD(), bm.size(),
+                                      cf.begin(), nf.begin(), n, md.origin, md.delta, sideOf.begin(), latticeToCell_.begin(), &identity),
+              "mesh (uniform lattice expected)");
+        md.nx = n[0]; md.ny = n[1]; md.nz = n[2];
+        if (!identity) md.latticeToCell = latticeToCell_.begin();
+    }
+    else
+    {
+        // optional: IBMProperties { lattice { n (nx ny nz); origin (x y z); delta (dx dy dz); blocks ((i0 i1 j0 j1 k0 k1) ...);
+        // patchSides (xMin ...); } } - the numbers of system/blockMeshDict, for callers that have them at hand
+        const dictionary& lat = dict_.subDict("lattice");
+        const labelVector n(lat.lookup("n"));
+        const vector origin(lat.lookup("origin")), delta(lat.lookup("delta"));
+        md.nx = n.x(); md.ny = n.y(); md.nz = n.z();
+        forAll(origin, d) { md.origin[d] = origin[d]; md.delta[d] = delta[d]; }
+        if (lat.found("blocks"))
+        {
+            List<labelList> b(lat.lookup("blocks"));
+            blocks.setSize(6*b.size());
+            forAll(b, i) forAll(b[i], j) blocks[6*i + j] = b[i][j];
+        }
+        md.nBlocks = blocks.size()/6;
+        md.blocks = blocks.size() ? blocks.begin() : nullptr;
+        const wordList sides(lat.lookup("patchSides"));   // one of xMin xMax yMin yMax zMin zMax per patch
+        forAll(bm, patchi)
+        {
+            const word& s = sides[patchi];
+            sideOf[patchi] = s == "xMin" ? IBM_XMIN : s == "xMax" ? IBM_XMAX : s == "yMin" ? IBM_YMIN
+                           : s == "yMax" ? IBM_YMAX : s == "zMin" ? IBM_ZMIN : IBM_ZMAX;
+        }
+    }
+
+    // boundary patches with their OpenFOAM face arrays (particleIBM.C:466-470, 504-508)
     forAll(bm, patchi)
     {
         ibm_patch_desc& p = pats[patchi];
@@ -48,9 +79,7 @@ void Foam::particleCloud::describeMesh(ibm_mesh_desc& md, List<ibm_patch_desc>& 
           : isA<cyclicFvPatch>(bm[patchi]) ? IBM_CYCLIC
           : isA<processorFvPatch>(bm[patchi]) ? IBM_PROCESSOR
           : isA<emptyFvPatch>(bm[patchi]) ? IBM_EMPTY : IBM_PATCH;
-        const word& s = sides[patchi];
-        p.side = s == "xMin" ? IBM_XMIN : s == "xMax" ? IBM_XMAX : s == "yMin" ? IBM_YMIN
-               : s == "yMax" ? IBM_YMAX : s == "zMin" ? IBM_ZMIN : IBM_ZMAX;
+        p.side = sideOf[patchi];
         p.neighbPatch =
             isA<cyclicFvPatch>(bm[patchi])
           ? refCast<const cyclicPolyPatch>(mesh_.boundaryMesh()[patchi]).neighbPatchID() : -1;

@@ -61,8 +61,11 @@ def write_case(path, case, n_steps, n_outer, n_restart=0):
             f.write(f"{int(n_restart)}\n")
 
 
-def run(binary, case_path, out_path, timeout=600):
-    return subprocess.run([binary, case_path, out_path], capture_output=True, text=True, timeout=timeout)
+def run(binary, case_path, out_path, timeout=600, no_lattice=False):
+    """no_lattice: the driver leaves the optional `lattice` entry out of IBMProperties, so that the shim hands polyMesh's own
+    cell / face centres to ibm_lattice_from_arrays (what a stock IBMFoam case provides)"""
+    env = dict(os.environ, DROPIN_NO_LATTICE="1") if no_lattice else None
+    return subprocess.run([binary, case_path, out_path], capture_output=True, text=True, timeout=timeout, env=env)
 
 
 def parse(path):

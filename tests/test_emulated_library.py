@@ -64,8 +64,11 @@ def test_refused_cooperative_launch_falls_back_to_the_unfused_chain(emu_lib):
     assert " passed" in out and "failed" not in out
 
 
-def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
-    """shim/particleCloud.C + the emulated library against the reference's own class through the same solver-side driver"""
+@pytest.mark.parametrize("no_lattice", [False, True])
+def test_shim_drop_in_under_emulation(emu_lib, tmp_path, no_lattice):
+    """shim/particleCloud.C + the emulated library against the reference's own class through the same solver-side driver;
+    no_lattice: without the optional `lattice` dictionary entry - the shim describes the mesh from polyMesh's cell and face
+    centres alone (ibm_lattice_from_arrays), as it would in a stock IBMFoam case"""
     import numpy as np
     import dropin_util as du
     if not os.path.exists(du.REFERENCE_BIN):
@@ -77,7 +80,7 @@ def test_shim_drop_in_under_emulation(emu_lib, tmp_path):
     outs = {}
     for side, binary in (("reference", du.REFERENCE_BIN), ("shim", os.path.join(du.BUILD, "dropin_shim_emu"))):
         op = str(tmp_path / f"{side}.bin")
-        r = du.run(binary, cp, op)
+        r = du.run(binary, cp, op, no_lattice=no_lattice)
         assert r.returncode == 0, (side, r.stderr)
         outs[side] = du.parse(op)
     (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]

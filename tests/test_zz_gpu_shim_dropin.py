@@ -16,15 +16,16 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(not (os.path.exists(du.REFERENCE_BIN) and os.path.exists(du.SHIM_BIN)), reason="drop-in binaries not built")
+@pytest.mark.parametrize("no_lattice", [False, True])
 @pytest.mark.parametrize("name", sorted(du.CASES))
-def test_shim_is_a_drop_in_for_the_reference_class(tmp_path, name):
+def test_shim_is_a_drop_in_for_the_reference_class(tmp_path, name, no_lattice):
     case, n_steps, n_outer = du.CASES[name]()
     cp = str(tmp_path / "case.txt")
     du.write_case(cp, case, n_steps, n_outer)
     outs = {}
     for side, binary in (("reference", du.REFERENCE_BIN), ("shim", du.SHIM_BIN)):
         op = str(tmp_path / f"{side}.bin")
-        r = du.run(binary, cp, op)
+        r = du.run(binary, cp, op, no_lattice=no_lattice)  # (no_lattice: mesh described from polyMesh's arrays alone)
         assert r.returncode == 0, (side, r.stderr)
         outs[side] = du.parse(op)
     (h_ref, rec_ref), (h_shim, rec_shim) = outs["reference"], outs["shim"]
